@@ -1,0 +1,399 @@
+// capi.cu -- the C ABI of include/vloam_b200.h on top of the stage files.
+#include <stdlib.h>
+#include <string>
+#include <vector>
+#include "common.cuh"
+
+static bool g_capture_default = false;
+// stage files ask through this hook whether to keep per-pass association snapshots
+bool vl_debug_capture(const vloam_b200_ctx* c) { return c->h_vScalars && c->h_vScalars[0] != 0; }
+int vl_lm_rescan_sorted(vloam_b200_ctx* c);
+
+extern "C" {
+
+void vloam_b200_default_params(vloam_b200_params* p) {
+  p->n_scans = 64; p->minimum_range = 5.0f; p->line_res = 0.4f; p->plane_res = 0.8f; p->mapping_skip_frame = 1; p->reserved = 0;
+}
+
+const char* vloam_b200_last_error(const vloam_b200_ctx* c) { return c ? c->err : "null context"; }
+
+#define VL_CUDA_CREATE(call)                                                                                       \
+  do {                                                                                                             \
+    cudaError_t e_ = (call);                                                                                       \
+    if (e_ != cudaSuccess) { fprintf(stderr, "vloam_b200_create: %s: %s\n", #call, cudaGetErrorString(e_)); return VLOAM_E_CUDA; } \
+  } while (0)
+
+int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** out) {
+  if (!p || !out) return VLOAM_E_INVALID;
+  // SR.cpp:58-61, 255-259: only 16 / 32 / 64 beams (128 = builder extension)
+  if (p->n_scans != 16 && p->n_scans != 32 && p->n_scans != 64 && p->n_scans != 128) return VLOAM_E_INVALID;
+  if (!(p->line_res >= 0.05f) || !(p->plane_res >= 0.05f) || p->mapping_skip_frame < 1) return VLOAM_E_INVALID;
+  VL_CUDA_CREATE(cudaSetDevice(device));
+  vloam_b200_ctx* c = new vloam_b200_ctx();
+  c->prm = *p; c->device = device; c->err[0] = 0; c->launches = 0; c->timing = false; c->cur = 0;
+  c->sr_counts_valid = false; c->n_in = 0; c->lo_inited = false; c->lo_frameCount = 0; c->lm_frameCount = 0; c->lm_optimized = 0; c->skip_frame = false;
+  c->nKept = c->nSharp = c->nLessSharp = c->nFlat = c->nLessFlat = 0; c->nCornerLast = c->nSurfLast = 0;
+  c->cornerLastPtr = nullptr; c->surfLastPtr = nullptr;
+  for (int k = 0; k < 4; ++k) c->dbgLoCost[k] = c->dbgLmCost[k] = 0;
+  for (int k = 0; k < 3; ++k) c->stage_ms[k] = 0;
+  cudaDeviceProp prop;
+  VL_CUDA_CREATE(cudaGetDeviceProperties(&prop, device));
+  c->num_sms = prop.multiProcessorCount;
+  VL_CUDA_CREATE(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (int k = 0; k < 4; ++k) VL_CUDA_CREATE(cudaEventCreate(&c->ev[k]));
+  const int R = VL_MAX_RINGS, S = VL_MAX_RINGS * VL_SECTORS;
+  VL_CUDA_CREATE(cudaMalloc(&c->ringCount, sizeof(int) * R));
+  VL_CUDA_CREATE(cudaMalloc(&c->ringStart, sizeof(int) * (R + 1)));
+  VL_CUDA_CREATE(cudaMemset(c->ringCount, 0, sizeof(int) * R));
+  VL_CUDA_CREATE(cudaMemset(c->ringStart, 0, sizeof(int) * (R + 1)));
+  VL_CUDA_CREATE(cudaMalloc(&c->srs, sizeof(SrScalars)));
+  VL_CUDA_CREATE(cudaMemset(c->srs, 0, sizeof(SrScalars)));
+  VL_CUDA_CREATE(cudaMallocHost(&c->h_srs, sizeof(SrScalars)));
+  memset(c->h_srs, 0, sizeof(SrScalars));
+  VL_CUDA_CREATE(cudaMalloc(&c->provSharp, sizeof(int) * S * 2));
+  VL_CUDA_CREATE(cudaMalloc(&c->provLess, sizeof(int) * S * 20));
+  VL_CUDA_CREATE(cudaMalloc(&c->provFlat, sizeof(int) * S * 4));
+  int** smalls[] = {&c->cntSharp, &c->cntLess, &c->cntFlat, &c->offSharp, &c->offLess, &c->offFlat};
+  for (int** q : smalls) { VL_CUDA_CREATE(cudaMalloc(q, sizeof(int) * S)); VL_CUDA_CREATE(cudaMemset(*q, 0, sizeof(int) * S)); }
+  VL_CUDA_CREATE(cudaMalloc(&c->ringDsCount, sizeof(int) * R));
+  VL_CUDA_CREATE(cudaMalloc(&c->ringDsOff, sizeof(int) * R));
+  VL_CUDA_CREATE(cudaMalloc(&c->los, sizeof(LoScalars)));
+  VL_CUDA_CREATE(cudaMallocHost(&c->h_los, sizeof(LoScalars)));
+  LoScalars hl; memset(&hl, 0, sizeof hl); hl.para_q[3] = 1.0; hl.q_w[3] = 1.0;  // LO.cpp:81-91
+  VL_CUDA_CREATE(cudaMemcpy(c->los, &hl, sizeof hl, cudaMemcpyHostToDevice));
+  *c->h_los = hl;
+  VL_CUDA_CREATE(cudaMalloc(&c->evalOut, sizeof(EvalOut)));
+  VL_CUDA_CREATE(cudaMalloc(&c->lms, sizeof(LmSolveState)));
+  VL_CUDA_CREATE(cudaMemset(c->lms, 0, sizeof(LmSolveState)));
+  VL_CUDA_CREATE(cudaMallocHost(&c->h_lms, sizeof(LmSolveState)));
+  VL_CUDA_CREATE(cudaMalloc(&c->lmm, sizeof(LmScalars)));
+  VL_CUDA_CREATE(cudaMallocHost(&c->h_lmm, sizeof(LmScalars)));
+  VL_CUDA_CREATE(cudaMalloc(&c->cubeC, sizeof(MapCubeTable)));
+  VL_CUDA_CREATE(cudaMalloc(&c->cubeS, sizeof(MapCubeTable)));
+  VL_CUDA_CREATE(cudaMalloc(&c->vScalars, sizeof(int) * 256));
+  VL_CUDA_CREATE(cudaMemset(c->vScalars, 0, sizeof(int) * 256));
+  VL_CUDA_CREATE(cudaMallocHost(&c->h_vScalars, sizeof(int) * 256));
+  memset(c->h_vScalars, 0, sizeof(int) * 256);
+  c->h_vScalars[0] = g_capture_default ? 1 : 0;
+  const int r = vl_lm_init(c);
+  if (r != VLOAM_OK) { fprintf(stderr, "vloam_b200_create: %s\n", c->err); return r; }
+  VL_CUDA_CREATE(cudaDeviceSynchronize());
+  *out = c;
+  return VLOAM_OK;
+}
+
+void vloam_b200_destroy(vloam_b200_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  // Device memory is released wholesale: contexts live for a whole replay (MAIN.cpp:118-124).
+  void* singles[] = {c->ringCount, c->ringStart, c->srs, c->provSharp, c->provLess, c->provFlat, c->cntSharp, c->cntLess, c->cntFlat,
+                     c->offSharp, c->offLess, c->offFlat, c->ringDsCount, c->ringDsOff, c->los, c->evalOut, c->lms, c->lmm, c->cubeC,
+                     c->cubeS, c->vScalars};
+  for (void* p : singles) if (p) cudaFree(p);
+  void* bufs[] = {c->in.p, c->ring.p, c->ori.p, c->blockHist.p, c->cloud.p, c->curv.p, c->label.p, c->picked.p, c->sortScratch.p,
+                  c->lessFlatProv.p, c->selIdx.p, c->sharp.p, c->lessSharp[0].p, c->lessSharp[1].p, c->flat.p, c->lessFlat[0].p,
+                  c->lessFlat[1].p, c->loCornerIdx.p, c->loSurfIdx.p, c->factors.p, c->factorValid.p, c->evalPartials.p,
+                  c->poolC.p, c->poolS.p, c->stackC.p, c->stackS.p, c->fromMapC.p, c->fromMapS.p, c->knnIdx.p, c->knnD2.p, c->knnOk.p,
+                  c->vKeys.p, c->vHead.p, c->vScan.p, c->vOut.p, c->vIn.p, c->tailKeys.p, c->staging.p};
+  for (void* p : bufs) if (p) cudaFree(p);
+  cudaFreeHost(c->h_srs); cudaFreeHost(c->h_los); cudaFreeHost(c->h_lms); cudaFreeHost(c->h_lmm); cudaFreeHost(c->h_vScalars);
+  for (int k = 0; k < 4; ++k) cudaEventDestroy(c->ev[k]);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+__global__ void k_begin_frame(LmScalars* s) { if (threadIdx.x == 0) s->validNum = 0; }  // LM.cpp:132-136
+
+int vloam_b200_begin_frame(vloam_b200_ctx* c) {
+  VL_CUDA(cudaSetDevice(c->device));
+  VL_LAUNCH(k_begin_frame, 1, 32, 0, c->lmm);
+  return VLOAM_OK;
+}
+
+int vloam_b200_scan_registration_device(vloam_b200_ctx* c, const float* d_xyz, int n, int stride) {
+  if (n < 0 || stride < 3) { snprintf(c->err, sizeof c->err, "bad cloud shape"); return VLOAM_E_INVALID; }
+  if (c->timing) VL_CUDA(cudaEventRecord(c->ev[0], c->stream));
+  VL_TRY(vl_sr_run(c, d_xyz, n, stride));
+  if (c->timing) VL_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  return VLOAM_OK;
+}
+
+int vloam_b200_scan_registration(vloam_b200_ctx* c, const float* xyz, int n, int stride) {
+  if (n < 0 || stride < 3 || (n > 0 && !xyz)) { snprintf(c->err, sizeof c->err, "bad cloud shape"); return VLOAM_E_INVALID; }
+  VL_TRY(vl_reserve(c, c->in, (size_t)max(n, 1) * stride));
+  if (n > 0) VL_CUDA(cudaMemcpyAsync(c->in.p, xyz, (size_t)n * stride * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  return vloam_b200_scan_registration_device(c, c->in.p, n, stride);
+}
+
+int vloam_b200_get_cloud(vloam_b200_ctx* c, int which, float* out, int cap_points) {
+  VL_TRY(vl_sr_sync_counts(c));
+  const float4* src = nullptr; int n = 0;
+  switch (which) {
+    case VLOAM_CLOUD_FULL: src = c->cloud.p; n = c->nKept; break;
+    case VLOAM_CLOUD_SHARP: src = c->sharp.p; n = c->nSharp; break;
+    case VLOAM_CLOUD_LESS_SHARP: src = c->lessSharp[c->cur].p; n = c->nLessSharp; break;
+    case VLOAM_CLOUD_FLAT: src = c->flat.p; n = c->nFlat; break;
+    case VLOAM_CLOUD_LESS_FLAT: src = c->lessFlat[c->cur].p; n = c->nLessFlat; break;
+    case VLOAM_CLOUD_CORNER_LAST: src = c->cornerLastPtr; n = c->nCornerLast; break;
+    case VLOAM_CLOUD_SURF_LAST: src = c->surfLastPtr; n = c->nSurfLast; break;
+    default: snprintf(c->err, sizeof c->err, "unknown cloud id %d", which); return VLOAM_E_INVALID;
+  }
+  if (out && n > 0) {
+    if (cap_points < n) { snprintf(c->err, sizeof c->err, "cloud buffer too small (%d < %d)", cap_points, n); return VLOAM_E_CAPACITY; }
+    VL_CUDA(cudaMemcpyAsync(out, src, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+    VL_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return n;
+}
+
+int vloam_b200_laser_odometry(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, int use_prior, double* q_w, double* t_w,
+                              double* q_lc, double* t_lc, int* skip_frame) {
+  if (use_prior && (!prior_q || !prior_t)) { snprintf(c->err, sizeof c->err, "use_prior without a prior"); return VLOAM_E_INVALID; }
+  VL_TRY(vl_lo_run(c, prior_q, prior_t, use_prior));
+  if (c->timing) VL_CUDA(cudaEventRecord(c->ev[2], c->stream));
+  if (q_w || t_w || q_lc || t_lc) {
+    VL_CUDA(cudaMemcpyAsync(c->h_los, c->los, sizeof(LoScalars), cudaMemcpyDeviceToHost, c->stream));
+    VL_CUDA(cudaStreamSynchronize(c->stream));
+    if (q_w) memcpy(q_w, c->h_los->q_w, 32);
+    if (t_w) memcpy(t_w, c->h_los->t_w, 24);
+    if (q_lc) memcpy(q_lc, c->h_los->para_q, 32);
+    if (t_lc) memcpy(t_lc, c->h_los->para_t, 24);
+  }
+  if (skip_frame) *skip_frame = c->skip_frame ? 1 : 0;
+  return VLOAM_OK;
+}
+
+int vloam_b200_laser_mapping(vloam_b200_ctx* c, double* q_w, double* t_w) {
+  VL_TRY(vl_lm_run(c));
+  if (c->timing) VL_CUDA(cudaEventRecord(c->ev[3], c->stream));
+  if (q_w || t_w) {
+    VL_CUDA(cudaMemcpyAsync(c->h_lmm, c->lmm, sizeof(LmScalars), cudaMemcpyDeviceToHost, c->stream));
+    VL_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->h_lmm->overflow) { snprintf(c->err, sizeof c->err, "map pool exhausted"); return VLOAM_E_CAPACITY; }
+    const double* q = c->skip_frame ? c->h_lmm->q_hf : c->h_lmm->pose;
+    const double* t = c->skip_frame ? c->h_lmm->t_hf : c->h_lmm->pose + 4;
+    if (q_w) memcpy(q_w, q, 32);
+    if (t_w) memcpy(t_w, t, 24);
+  }
+  return VLOAM_OK;
+}
+
+static int process_common(vloam_b200_ctx* c, double* pose_out) {
+  VL_TRY(vloam_b200_laser_odometry(c, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr));
+  if (pose_out) {
+    VL_TRY(vl_lm_run(c));
+    if (c->timing) VL_CUDA(cudaEventRecord(c->ev[3], c->stream));
+    VL_CUDA(cudaMemcpyAsync(c->h_los, c->los, sizeof(LoScalars), cudaMemcpyDeviceToHost, c->stream));
+    VL_CUDA(cudaMemcpyAsync(c->h_lmm, c->lmm, sizeof(LmScalars), cudaMemcpyDeviceToHost, c->stream));
+    VL_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->h_lmm->overflow) { snprintf(c->err, sizeof c->err, "map pool exhausted"); return VLOAM_E_CAPACITY; }
+    memcpy(pose_out, c->h_los->q_w, 32); memcpy(pose_out + 4, c->h_los->t_w, 24);
+    memcpy(pose_out + 7, c->skip_frame ? c->h_lmm->q_hf : c->h_lmm->pose, 32);
+    memcpy(pose_out + 11, c->skip_frame ? c->h_lmm->t_hf : c->h_lmm->pose + 4, 24);
+    return VLOAM_OK;
+  }
+  return vloam_b200_laser_mapping(c, nullptr, nullptr);
+}
+
+int vloam_b200_process_frame(vloam_b200_ctx* c, const float* xyz, int n, int stride, double* pose_out) {
+  VL_TRY(vloam_b200_begin_frame(c));
+  VL_TRY(vloam_b200_scan_registration(c, xyz, n, stride));
+  return process_common(c, pose_out);
+}
+int vloam_b200_process_frame_device(vloam_b200_ctx* c, const float* d_xyz, int n, int stride, double* pose_out) {
+  VL_TRY(vloam_b200_begin_frame(c));
+  VL_TRY(vloam_b200_scan_registration_device(c, d_xyz, n, stride));
+  return process_common(c, pose_out);
+}
+
+int vloam_b200_synchronize(vloam_b200_ctx* c) { VL_CUDA(cudaStreamSynchronize(c->stream)); return VLOAM_OK; }
+void* vloam_b200_stream(vloam_b200_ctx* c) { return (void*)c->stream; }
+long long vloam_b200_kernel_launches(const vloam_b200_ctx* c) { return c->launches; }
+int vloam_b200_set_timing(vloam_b200_ctx* c, int enabled) { c->timing = enabled != 0; return VLOAM_OK; }
+int vloam_b200_stage_ms(vloam_b200_ctx* c, float* ms3) {
+  if (!c->timing) { snprintf(c->err, sizeof c->err, "timing is off"); return VLOAM_E_INVALID; }
+  VL_CUDA(cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < 3; ++k) VL_CUDA(cudaEventElapsedTime(&ms3[k], c->ev[k], c->ev[k + 1]));
+  return VLOAM_OK;
+}
+
+int vloam_b200_lo_associate(vloam_b200_ctx* c, const double* x, int* corner_idx, int* surf_idx) { return vl_lo_associate_only(c, x, corner_idx, surf_idx); }
+
+// ---- name-keyed state access ----------------------------------------------------------------
+static long put_dev(vloam_b200_ctx* c, const void* dsrc, size_t bytes, void* out, long cap) {
+  if (out && bytes && (long)bytes <= cap) {
+    if (cudaMemcpyAsync(out, dsrc, bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) {
+      snprintf(c->err, sizeof c->err, "debug_get copy failed"); return VLOAM_E_CUDA;
+    }
+  }
+  return (long)bytes;
+}
+static long put_host(const void* src, size_t bytes, void* out, long cap) { if (out && (long)bytes <= cap && bytes) memcpy(out, src, bytes); return (long)bytes; }
+
+long vloam_b200_debug_get(vloam_b200_ctx* c, const char* name, void* out, long cap) {
+  const std::string n(name);
+  if (n.rfind("sr.", 0) == 0 || n.rfind("lo.", 0) == 0) { if (vl_sr_sync_counts(c) != VLOAM_OK) return VLOAM_E_CUDA; }
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) return VLOAM_E_CUDA;
+  if (n == "sr.laserCloud") return put_dev(c, c->cloud.p, (size_t)c->nKept * 16, out, cap);
+  if (n == "sr.sharp") return put_dev(c, c->sharp.p, (size_t)c->nSharp * 16, out, cap);
+  if (n == "sr.lessSharp") return put_dev(c, c->lessSharp[c->cur].p, (size_t)c->nLessSharp * 16, out, cap);
+  if (n == "sr.flat") return put_dev(c, c->flat.p, (size_t)c->nFlat * 16, out, cap);
+  if (n == "sr.lessFlat") return put_dev(c, c->lessFlat[c->cur].p, (size_t)c->nLessFlat * 16, out, cap);
+  if (n == "sr.curvature") return put_dev(c, c->curv.p, (size_t)c->nKept * 4, out, cap);
+  if (n == "sr.label") return put_dev(c, c->label.p, (size_t)c->nKept * 4, out, cap);
+  if (n == "sr.scanStartInd" || n == "sr.scanEndInd") {
+    std::vector<int> rs(VL_MAX_RINGS + 1), rc(VL_MAX_RINGS);
+    cudaMemcpy(rs.data(), c->ringStart, sizeof(int) * (VL_MAX_RINGS + 1), cudaMemcpyDeviceToHost);
+    cudaMemcpy(rc.data(), c->ringCount, sizeof(int) * VL_MAX_RINGS, cudaMemcpyDeviceToHost);
+    std::vector<int> v(c->prm.n_scans);
+    for (int r = 0; r < c->prm.n_scans; ++r) v[r] = n == "sr.scanStartInd" ? rs[r] + 5 : rs[r] + rc[r] - 6;
+    return put_host(v.data(), v.size() * 4, out, cap);
+  }
+  if (n == "lo.cornerLast") return put_dev(c, c->cornerLastPtr, (size_t)c->nCornerLast * 16, out, cap);
+  if (n == "lo.surfLast") return put_dev(c, c->surfLastPtr, (size_t)c->nSurfLast * 16, out, cap);
+  if (n == "lo.pose") {
+    LoScalars h; cudaMemcpy(&h, c->los, sizeof h, cudaMemcpyDeviceToHost);
+    double v[14]; memcpy(v, h.q_w, 32); memcpy(v + 4, h.t_w, 24); memcpy(v + 7, h.para_q, 32); memcpy(v + 11, h.para_t, 24);
+    return put_host(v, sizeof v, out, cap);
+  }
+  for (int k = 0; k < 2; ++k) {
+    const std::string s = std::to_string(k);
+    if (n == "lo.assoc.corner" + s) return put_dev(c, c->dbgLoCorner[k].p, (size_t)c->nSharp * 8, out, cap);
+    if (n == "lo.assoc.surf" + s) return put_dev(c, c->dbgLoSurf[k].p, (size_t)c->nFlat * 12, out, cap);
+    if (n.rfind("lm.knn.", 0) == 0 && n.back() == ('0' + k)) {
+      const std::string kind = n.substr(7, n.size() - 8);
+      const int Qc = c->h_lmm->Qc, Qs = c->h_lmm->Qs;
+      if (kind == "cidx") return put_dev(c, c->dbgKnnIdx[k][0].p, (size_t)Qc * 20, out, cap);
+      if (kind == "sidx") return put_dev(c, c->dbgKnnIdx[k][1].p, (size_t)Qs * 20, out, cap);
+      if (kind == "cd2") return put_dev(c, c->dbgKnnD2[k][0].p, (size_t)Qc * 20, out, cap);
+      if (kind == "sd2") return put_dev(c, c->dbgKnnD2[k][1].p, (size_t)Qs * 20, out, cap);
+      if (kind == "cok") return put_dev(c, c->dbgKnnOk[k][0].p, (size_t)Qc * 4, out, cap);
+      if (kind == "sok") return put_dev(c, c->dbgKnnOk[k][1].p, (size_t)Qs * 4, out, cap);
+    }
+  }
+  if (n == "lo.costs") return put_host(c->dbgLoCost, sizeof c->dbgLoCost, out, cap);
+  if (n == "lm.costs") return put_host(c->dbgLmCost, sizeof c->dbgLmCost, out, cap);
+  if (n == "lm.pose" || n == "lm.state" || n == "lm.validInd") {
+    LmScalars h; cudaMemcpy(&h, c->lmm, sizeof h, cudaMemcpyDeviceToHost);
+    if (n == "lm.pose") { double v[14]; memcpy(v, h.pose, 56); memcpy(v + 7, h.q_wmap_wodom, 32); memcpy(v + 11, h.t_wmap_wodom, 24); return put_host(v, sizeof v, out, cap); }
+    if (n == "lm.state") { int v[5] = {h.cenW, h.cenH, h.cenD, c->lm_frameCount, c->lm_optimized}; return put_host(v, sizeof v, out, cap); }
+    return put_host(h.validInd, (size_t)h.validNum * 4, out, cap);
+  }
+  if (n == "lm.cornerStack") return put_dev(c, c->stackC.p, (size_t)c->h_lmm->Qc * 16, out, cap);
+  if (n == "lm.surfStack") return put_dev(c, c->stackS.p, (size_t)c->h_lmm->Qs * 16, out, cap);
+  if (n == "lm.cornerFromMap") return put_dev(c, c->fromMapC.p, (size_t)c->h_lmm->Mc * 16, out, cap);
+  if (n == "lm.surfFromMap") return put_dev(c, c->fromMapS.p, (size_t)c->h_lmm->Ms * 16, out, cap);
+  if (n == "lm.cornerMap" || n == "lm.surfMap") {
+    long bytes = 0;
+    if (vl_lm_export_map(c, n == "lm.surfMap", out, cap, &bytes) != VLOAM_OK) return VLOAM_E_CUDA;
+    return bytes;
+  }
+  snprintf(c->err, sizeof c->err, "unknown buffer name '%s'", name);
+  return VLOAM_E_NAME;
+}
+
+int vloam_b200_debug_set(vloam_b200_ctx* c, const char* name, const void* data, long bytes) {
+  const std::string n(name);
+  VL_CUDA(cudaStreamSynchronize(c->stream));
+  if (n == "debug.capture") { c->h_vScalars[0] = (bytes >= 4 && *(const int*)data) ? 1 : 0; return VLOAM_OK; }
+  if (n == "lo.last") {  // blob: int nc, int ns, corner points, surf points  (the state solveLO swaps in, LO.cpp:558-574)
+    const int* hdr = (const int*)data;
+    if (bytes < 8 || bytes != 8 + ((long)hdr[0] + hdr[1]) * 16) { snprintf(c->err, sizeof c->err, "lo.last blob size mismatch"); return VLOAM_E_INVALID; }
+    const int o = c->cur ^ 1;  // the buffer the next frame will not write
+    VL_TRY(vl_reserve(c, c->lessSharp[o], (size_t)max(hdr[0], 1)));
+    VL_TRY(vl_reserve(c, c->lessFlat[o], (size_t)max(hdr[1], 1)));
+    const char* p = (const char*)data + 8;
+    if (hdr[0]) VL_CUDA(cudaMemcpy(c->lessSharp[o].p, p, (size_t)hdr[0] * 16, cudaMemcpyHostToDevice));
+    if (hdr[1]) VL_CUDA(cudaMemcpy(c->lessFlat[o].p, p + (size_t)hdr[0] * 16, (size_t)hdr[1] * 16, cudaMemcpyHostToDevice));
+    // make that buffer the current one so the next frame (cur ^= 1) writes the other
+    c->cur = o;
+    c->cornerLastPtr = c->lessSharp[o].p; c->surfLastPtr = c->lessFlat[o].p;
+    c->nCornerLast = hdr[0]; c->nSurfLast = hdr[1];
+    c->lo_inited = true;
+    return VLOAM_OK;
+  }
+  if (n == "lo.pose") {
+    if (bytes != 14 * 8) return VLOAM_E_INVALID;
+    const double* v = (const double*)data;
+    LoScalars h; VL_CUDA(cudaMemcpy(&h, c->los, sizeof h, cudaMemcpyDeviceToHost));
+    memcpy(h.q_w, v, 32); memcpy(h.t_w, v + 4, 24); memcpy(h.para_q, v + 7, 32); memcpy(h.para_t, v + 11, 24);
+    VL_CUDA(cudaMemcpy(c->los, &h, sizeof h, cudaMemcpyHostToDevice));
+    return VLOAM_OK;
+  }
+  if (n == "lm.pose" || n == "lm.state") {
+    LmScalars h; VL_CUDA(cudaMemcpy(&h, c->lmm, sizeof h, cudaMemcpyDeviceToHost));
+    if (n == "lm.pose") {
+      if (bytes != 14 * 8) return VLOAM_E_INVALID;
+      const double* v = (const double*)data;
+      memcpy(h.pose, v, 56); memcpy(h.q_wmap_wodom, v + 7, 32); memcpy(h.t_wmap_wodom, v + 11, 24);
+    } else {
+      if (bytes < 16) return VLOAM_E_INVALID;
+      const int* v = (const int*)data;
+      h.cenW = v[0]; h.cenH = v[1]; h.cenD = v[2]; c->lm_frameCount = v[3];
+    }
+    VL_CUDA(cudaMemcpy(c->lmm, &h, sizeof h, cudaMemcpyHostToDevice));
+    if (n == "lm.state") VL_TRY(vl_lm_rescan_sorted(c));  // voxel keys are relative to the cube origin
+    return VLOAM_OK;
+  }
+  if (n == "lm.cornerMap") return vl_lm_import_map(c, 0, data, bytes);
+  if (n == "lm.surfMap") return vl_lm_import_map(c, 1, data, bytes);
+  snprintf(c->err, sizeof c->err, "unknown buffer name '%s'", name);
+  return VLOAM_E_NAME;
+}
+
+int vloam_b200_voxel_grid(vloam_b200_ctx* c, const float* in, int n, float leaf, float* out, int cap_points) {
+  if (n < 0 || !(leaf > 0.f)) return VLOAM_E_INVALID;
+  VL_TRY(vl_reserve(c, c->vIn, (size_t)max(n, 1)));
+  VL_TRY(vl_reserve(c, c->vOut, (size_t)max(n, 1)));
+  if (n) VL_CUDA(cudaMemcpyAsync(c->vIn.p, in, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+  int* d_count = c->vScalars + 16;
+  VL_TRY(vl_voxel_grid_device(c, c->vIn.p, n, nullptr, leaf, c->vOut.p, d_count));
+  int m = 0;
+  VL_CUDA(cudaMemcpyAsync(&m, d_count, 4, cudaMemcpyDeviceToHost, c->stream));
+  VL_CUDA(cudaStreamSynchronize(c->stream));
+  if (m > cap_points) { snprintf(c->err, sizeof c->err, "voxel_grid output buffer too small"); return VLOAM_E_CAPACITY; }
+  if (m && out) { VL_CUDA(cudaMemcpyAsync(out, c->vOut.p, (size_t)m * 16, cudaMemcpyDeviceToHost, c->stream)); VL_CUDA(cudaStreamSynchronize(c->stream)); }
+  return m;
+}
+
+static int upload_factors(vloam_b200_ctx* c, const double* factors, int nf) {
+  VL_TRY(vl_reserve(c, c->factors, (size_t)max(nf, 1) * 10));
+  VL_TRY(vl_reserve(c, c->factorValid, (size_t)max(nf, 1)));
+  if (nf) {
+    VL_CUDA(cudaMemcpyAsync(c->factors.p, factors, (size_t)nf * 80, cudaMemcpyHostToDevice, c->stream));
+    std::vector<int> ones(nf, 1);
+    VL_CUDA(cudaMemcpyAsync(c->factorValid.p, ones.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, c->stream));
+    VL_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return VLOAM_OK;
+}
+
+int vloam_b200_evaluate(vloam_b200_ctx* c, const double* factors, int nf, const double* x, double* cost, double* H, double* g) {
+  VL_TRY(upload_factors(c, factors, nf));
+  double* d_x = reinterpret_cast<double*>(c->vScalars + 32);
+  VL_CUDA(cudaMemcpyAsync(d_x, x, 56, cudaMemcpyHostToDevice, c->stream));
+  VL_TRY(vl_evaluate_once(c, nf, d_x, c->evalOut));
+  EvalOut h;
+  VL_CUDA(cudaMemcpyAsync(&h, c->evalOut, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  VL_CUDA(cudaStreamSynchronize(c->stream));
+  int t = 0;
+  for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { H[i * 6 + j] = h.v[t]; H[j * 6 + i] = h.v[t]; ++t; }
+  for (int i = 0; i < 6; ++i) g[i] = h.v[21 + i];
+  *cost = h.v[27];
+  return VLOAM_OK;
+}
+
+int vloam_b200_solve(vloam_b200_ctx* c, const double* factors, int nf, double* x, double* log4) {
+  VL_TRY(upload_factors(c, factors, nf));
+  double* d_x = reinterpret_cast<double*>(c->vScalars + 32);
+  VL_CUDA(cudaMemcpyAsync(d_x, x, 56, cudaMemcpyHostToDevice, c->stream));
+  double costs[2] = {0, 0};
+  VL_TRY(vl_solve(c, nf, d_x, costs));
+  VL_CUDA(cudaMemcpyAsync(x, d_x, 56, cudaMemcpyDeviceToHost, c->stream));
+  VL_CUDA(cudaStreamSynchronize(c->stream));
+  if (log4) { log4[0] = nf ? c->h_lms->iter : 0; log4[1] = 0; log4[2] = costs[0]; log4[3] = costs[1]; }
+  return VLOAM_OK;
+}
+
+}  // extern "C"

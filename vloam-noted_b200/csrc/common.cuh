@@ -1,0 +1,258 @@
+// common.cuh -- context, device buffers and launch helpers shared by the stage files.
+//
+// Everything on the hot path runs as hand-written CUDA on the context's single
+// stream.  The host side only orders launches and reads back a handful of
+// counts at explicit sync points; it never computes on point data.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "vloam_b200.h"
+
+#define VL_MAX_RINGS 128
+#define VL_SECTORS 6
+#define VL_CUBE_W 21
+#define VL_CUBE_H 21
+#define VL_CUBE_D 11
+#define VL_CUBE_NUM (VL_CUBE_W * VL_CUBE_H * VL_CUBE_D)
+#define VL_MAX_VALID 125  // laserCloudValidInd[125], laser_mapping.h:127
+
+// ---- device-resident scalars (one struct per context, also mirrored in pinned host memory)
+struct SrScalars {
+  int firstValid, lastValid;  // first / last point surviving the NaN + range filter
+  int trigger;                // input index of the first point that sets halfPassed (INT_MAX if none)
+  float startOri, endOri;     // scan_registration.cpp:185-197
+  int count;                  // kept points == laserCloud size
+  int nSharp, nLessSharp, nFlat, nLessFlat;
+  int blocksDone;             // last-block-done counter for the ring scan
+  int pad;
+};
+
+struct LmSolveState {  // trust-region LM state, lives on the device (lm_solver.cu)
+  double x[7];         // current iterate {qx,qy,qz,qw,tx,ty,tz}
+  double xc[7];        // candidate
+  double best[7];
+  double scale[6];     // Jacobi scaling, computed once at iteration 0
+  double diag[6];
+  double H[21], g[6];  // accepted-point normal equations (unscaled, robustified)
+  double cost, cand_cost, min_cost, model_cost_change;
+  double radius, decrease_factor, x_norm, gmax;
+  int reuse_diagonal, done, iter, last_successful, have_candidate, nfactors;
+  double initial_cost, final_cost;
+};
+
+struct EvalOut {  // one robustified evaluation: 21 upper-triangular H, 6 g, cost
+  double v[28];
+};
+
+struct MapCubeTable {  // per cube slot: where its points live in the pool
+  int start[VL_CUBE_NUM];
+  int count[VL_CUBE_NUM];
+  int cap[VL_CUBE_NUM];
+  int sorted[VL_CUBE_NUM];  // length of the prefix whose voxel keys are strictly increasing
+};
+
+struct LmScalars {
+  int cenW, cenH, cenD;             // laserCloudCen{Width,Height,Depth}
+  int validNum;
+  int validInd[VL_MAX_VALID];
+  int Mc, Ms;                       // sub-map sizes
+  int Qc, Qs;                       // downsampled stack sizes
+  int tailC, tailS;                 // unsorted tail points in the valid cubes (incl. this frame's inserts)
+  int poolTopC, poolTopS;
+  int overflow;                     // set when a pool / buffer bound was hit
+  int optimized;
+  double pose[7];                   // q_w_curr, t_w_curr (parameters[7], laser_mapping.h:156)
+  double q_wmap_wodom[4], t_wmap_wodom[3];
+  double q_wodom[4], t_wodom[3];
+  double q_hf[4], t_hf[3];
+};
+
+struct LoScalars {
+  double para_q[4], para_t[3];  // q_last_curr, t_last_curr (laser_odometry.h:127-131)
+  double q_w[4], t_w[3];        // q_w_curr, t_w_curr
+  int corner_correspondence, plane_correspondence;
+};
+
+template <typename T>
+struct DBuf {  // growable device buffer
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+};
+
+struct vloam_b200_ctx {
+  vloam_b200_params prm;
+  int device;
+  cudaStream_t stream;
+  char err[512];
+  long long launches;
+  int num_sms;
+  bool timing;
+  cudaEvent_t ev[4];
+  float stage_ms[3];
+
+  // ---- scan registration
+  DBuf<float> in;            // raw input (n * stride floats)
+  int n_in, stride;
+  DBuf<int> ring;            // per input point ring id or -1
+  DBuf<float> ori;           // per input point -atan2f(y,x)
+  DBuf<int> blockHist;       // [ring][block] counts -> exclusive offsets
+  int* ringCount;            // [VL_MAX_RINGS]
+  int* ringStart;            // [VL_MAX_RINGS + 1]
+  SrScalars* srs;            // device
+  SrScalars* h_srs;          // pinned host mirror
+  DBuf<float4> cloud;        // laserCloud
+  DBuf<float> curv;
+  DBuf<int> label;
+  DBuf<unsigned char> picked;
+  DBuf<unsigned long long> sortScratch;  // oversize sector / ring sorts
+  int* provSharp; int* provLess; int* provFlat;  // provisional picks (indices) per (ring, sector)
+  int* cntSharp; int* cntLess; int* cntFlat;     // per (ring, sector)
+  int* offSharp; int* offLess; int* offFlat;     // exclusive offsets
+  DBuf<float4> lessFlatProv;  // per-ring downsampled points at ringStart[r]
+  int* ringDsCount; int* ringDsOff;
+  DBuf<int> selIdx;           // per-ring compacted selection (original indices)
+  DBuf<float4> sharp, lessSharp[2], flat, lessFlat[2];  // [cur] of the double-buffered pair is this frame
+  int cur;                    // index of this frame's lessSharp / lessFlat buffer
+  int nKept, nSharp, nLessSharp, nFlat, nLessFlat;  // host copies (valid after the SR sync point)
+  bool sr_counts_valid;
+
+  // ---- laser odometry
+  LoScalars* los; LoScalars* h_los;
+  int nCornerLast, nSurfLast;  // host counts of the "last" clouds (= other buffer of the pair)
+  bool lo_inited; int lo_frameCount;
+  float4* cornerLastPtr; float4* surfLastPtr;  // after solveLO's swap
+  DBuf<int> loCornerIdx, loSurfIdx;   // association results (2 / 3 ints per query)
+  DBuf<double> factors;               // 10 doubles per factor slot
+  DBuf<int> factorValid;
+  DBuf<EvalOut> evalPartials;
+  EvalOut* evalOut;
+  LmSolveState* lms; LmSolveState* h_lms;
+  DBuf<int> dbgLoCorner[2], dbgLoSurf[2];
+  double dbgLoCost[4];
+  bool skip_frame;
+
+  // ---- laser mapping
+  LmScalars* lmm; LmScalars* h_lmm;
+  MapCubeTable* cubeC; MapCubeTable* cubeS;  // device
+  DBuf<float4> poolC, poolS;
+  DBuf<float4> stackC, stackS;
+  DBuf<float4> fromMapC, fromMapS;
+  int lm_frameCount;
+  int lm_optimized;  // host copy: did the last solveMapping run the optimisation (LM.cpp:514)
+  DBuf<int> knnIdx; DBuf<float> knnD2; DBuf<int> knnOk;
+  DBuf<int> dbgKnnIdx[2][2]; DBuf<float> dbgKnnD2[2][2]; DBuf<int> dbgKnnOk[2][2];
+  double dbgLmCost[4];
+  // search grid over the sub-map
+  DBuf<int> gridCellStart[2]; DBuf<int> gridPointIdx[2]; DBuf<int> gridCellOfPoint[2];
+  struct GridParams* gridPrm;  // device [2]
+  // voxel filter scratch
+  DBuf<unsigned long long> vKeys; DBuf<int> vHead; DBuf<int> vScan;
+  DBuf<float4> vOut; DBuf<float4> vIn;
+  int* vScalars;  // device scratch ints
+  int* h_vScalars;
+  // refilter scratch
+  DBuf<unsigned long long> tailKeys; DBuf<float4> staging;
+  DBuf<int> tmpI[4];
+};
+
+struct GridParams {
+  float ox, oy, oz;   // origin (min corner)
+  float inv;          // 1 / cell
+  int nx, ny, nz;
+  int ncell;
+  int npoints;
+};
+
+// ---- error handling ---------------------------------------------------------
+#define VL_CUDA(call)                                                                     \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      snprintf(c->err, sizeof c->err, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      return VLOAM_E_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+#define VL_TRY(call)            \
+  do {                          \
+    int r_ = (call);            \
+    if (r_ != VLOAM_OK) return r_; \
+  } while (0)
+
+#define VL_LAUNCH(kernel, grid, block, smem, ...)                    \
+  do {                                                               \
+    kernel<<<(grid), (block), (smem), c->stream>>>(__VA_ARGS__);     \
+    c->launches++;                                                   \
+  } while (0)
+
+template <typename T>
+static inline int vl_reserve(vloam_b200_ctx* c, DBuf<T>& b, size_t n, bool keep = false) {
+  if (n <= b.cap) return VLOAM_OK;
+  size_t ncap = b.cap ? b.cap : 1024;
+  while (ncap < n) ncap *= 2;
+  T* np = nullptr;
+  VL_CUDA(cudaMalloc(&np, ncap * sizeof(T)));
+  if (keep && b.p && b.cap) VL_CUDA(cudaMemcpyAsync(np, b.p, b.cap * sizeof(T), cudaMemcpyDeviceToDevice, c->stream));
+  if (b.p) { VL_CUDA(cudaStreamSynchronize(c->stream)); VL_CUDA(cudaFree(b.p)); }
+  b.p = np; b.cap = ncap;
+  return VLOAM_OK;
+}
+
+static inline int vl_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- stage entry points (one per .cu file) ------------------------------------
+int vl_sr_run(vloam_b200_ctx* c, const float* d_xyz, int n, int stride);
+int vl_sr_sync_counts(vloam_b200_ctx* c);
+int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, int use_prior);
+int vl_lo_associate_only(vloam_b200_ctx* c, const double* x, int* corner_idx, int* surf_idx);
+int vl_lm_run(vloam_b200_ctx* c);
+int vl_lm_init(vloam_b200_ctx* c);
+int vl_lm_export_map(vloam_b200_ctx* c, int which, void* out, long cap, long* bytes);
+int vl_lm_import_map(vloam_b200_ctx* c, int which, const void* data, long bytes);
+
+// sort / voxel primitives (voxel_grid.cu)
+int vl_sort_u64(vloam_b200_ctx* c, unsigned long long* d_keys, int n_pow2);
+// pcl::VoxelGrid of d_in[0..n) -> d_out, count written to *d_count (device int); n is a host bound,
+// d_n (device int, may be null) is the actual count.
+int vl_voxel_grid_device(vloam_b200_ctx* c, const float4* d_in, int n, const int* d_n, float leaf, float4* d_out, int* d_count);
+
+// solver (lm_solver.cu): evaluates factor slots [0, nslots) with validity flags.
+int vl_solve(vloam_b200_ctx* c, int nslots, double* d_x_inout, double* costs2 /* host, may be null */);
+int vl_evaluate_once(vloam_b200_ctx* c, int nslots, const double* d_x, EvalOut* d_out);
+
+// ---- shared device helpers -----------------------------------------------------
+#ifdef __CUDACC__
+// Eigen quaternion * vector (no normalisation): uv = u x v; uv += uv; v + w*uv + u x uv.
+__device__ __forceinline__ void vl_qrot(const double q[4], double vx, double vy, double vz, double o[3]) {
+  const double ux = q[0], uy = q[1], uz = q[2], w = q[3];
+  double uvx = uy * vz - uz * vy;
+  double uvy = uz * vx - ux * vz;
+  double uvz = ux * vy - uy * vx;
+  uvx += uvx; uvy += uvy; uvz += uvz;
+  const double cx = uy * uvz - uz * uvy;
+  const double cy = uz * uvx - ux * uvz;
+  const double cz = ux * uvy - uy * uvx;
+  o[0] = (vx + w * uvx) + cx;
+  o[1] = (vy + w * uvy) + cy;
+  o[2] = (vz + w * uvz) + cz;
+}
+__device__ __forceinline__ void vl_qmul(const double a[4], const double b[4], double o[4]) {
+  const double ax = a[0], ay = a[1], az = a[2], aw = a[3];
+  const double bx = b[0], by = b[1], bz = b[2], bw = b[3];
+  const double w = aw * bw - ax * bx - ay * by - az * bz;
+  const double x = aw * bx + ax * bw + ay * bz - az * by;
+  const double y = aw * by + ay * bw + az * bx - ax * bz;
+  const double z = aw * bz + az * bw + ax * by - ay * bx;
+  o[0] = x; o[1] = y; o[2] = z; o[3] = w;
+}
+// FLANN L2_Simple<float>: acc = 0; acc += d*d over x, y, z (f32, no FMA: -fmad=false).
+__device__ __forceinline__ float vl_dist2(float qx, float qy, float qz, float px, float py, float pz) {
+  float acc = 0.f, d;
+  d = qx - px; acc += d * d;
+  d = qy - py; acc += d * d;
+  d = qz - pz; acc += d * d;
+  return acc;
+}
+#endif

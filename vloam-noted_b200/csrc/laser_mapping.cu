@@ -1,0 +1,975 @@
+// laser_mapping.cu -- LaserMapping::input / solveMapping (laser_mapping.cpp:178-814) as CUDA.
+//
+// Map layout in HBM.  The reference keeps 2 x 4851 per-cube PCL clouds (LM.h:117-150).
+// Here each cube of each kind (corner / surf) is a segment [start, start+count) of one
+// big float4 pool plus a `sorted` length: the prefix whose voxel keys are strictly
+// increasing (what a previous VoxelGrid pass left behind); anything after it is an
+// unsorted tail (raw appends to cubes outside the 5x5x3 window).  Rolling the 21x21x11
+// window (LM.cpp:252-444) permutes the 4851-entry table, it never moves points.
+//
+// Per frame:
+//   lm_prepare        input() + centre cube + roll + valid-cube list + gather offsets
+//   lm_gather         the 75 valid cubes -> contiguous cornerFromMap / surfFromMap (canonical kNN ids)
+//   vl_voxel_grid     current less-sharp / less-flat -> cornerStack / surfStack (LM.cpp:492-500)
+//   [sync S2: Mc, Ms, Qc, Qs, tail sizes]
+//   grid build        counting sort of both sub-maps into 2 m cells over the 250x250x150 m window
+//   2 x { lm_knn_fit (5-NN + PCA line / QR plane -> factor slots), vl_solve }
+//   lm_transform_update, then the map update:
+//   rf_*              VoxelGrid re-filter of the valid cubes (LM.cpp:795-808) WITHOUT re-sorting the
+//                     map: only tails + this frame's points are sorted, then merged into the
+//                     already-ordered prefixes (exact: a prefix has one point per voxel and
+//                     the lowest point indices, so every run is [prefix point?] + tail points)
+#include <limits.h>
+#include <float.h>
+#include <math_constants.h>
+#include "common.cuh"
+
+#define LM_CELL 2.0f
+#define LM_GX 125
+#define LM_GY 125
+#define LM_GZ 75
+#define LM_NCELL (LM_GX * LM_GY * LM_GZ)
+#define LM_NSEG 250  // (kind, valid slot)
+
+struct RfWork {
+  int slotOfCube[VL_CUBE_NUM];          // valid slot of a cube index or -1
+  int gatherOff[2][VL_MAX_VALID + 1];   // exclusive offsets of the valid cubes inside fromMap
+  int tailOff[LM_NSEG + 1];             // exclusive offsets of existing-tail keys
+  int prefOff[LM_NSEG + 1];             // exclusive offsets of prefix points
+  int tailBegin[LM_NSEG + 1];           // per segment range in the sorted key array
+  int outOff[LM_NSEG + 1];              // staging offsets
+  int outCount[LM_NSEG];
+  int firstViolation[LM_NSEG];
+  int nKeysValid;
+  float gridOrigin[3];
+  int Qc, Qs;
+};
+
+__device__ __forceinline__ int lm_cube_of(float v, int cen) {  // LM.cpp:747-756
+  const double t = (double)v + 25.0;
+  int c = (int)(t / 50.0) + cen;
+  if (t < 0) c--;
+  return c;
+}
+
+// voxel key of a map point inside cube (ci,cj,ck): 10 bits per axis, (iz, iy, ix) order ==
+// ascending pcl::VoxelGrid linear index inside any bounding box of that cube's points.
+__device__ __forceinline__ unsigned lm_vox_key(const float4 p, float inv, int ci, int cj, int ck, int cenW, int cenH, int cenD) {
+  const int bx = (int)floorf(__fmul_rn((float)(50 * (ci - cenW) - 25), inv)) - 2;
+  const int by = (int)floorf(__fmul_rn((float)(50 * (cj - cenH) - 25), inv)) - 2;
+  const int bz = (int)floorf(__fmul_rn((float)(50 * (ck - cenD) - 25), inv)) - 2;
+  const int ix = min(max((int)floorf(__fmul_rn(p.x, inv)) - bx, 0), 1023);
+  const int iy = min(max((int)floorf(__fmul_rn(p.y, inv)) - by, 0), 1023);
+  const int iz = min(max((int)floorf(__fmul_rn(p.z, inv)) - bz, 0), 1023);
+  return ((unsigned)iz << 20) | ((unsigned)iy << 10) | (unsigned)ix;
+}
+__device__ __forceinline__ unsigned lm_vox_key_cube(const float4 p, float inv, int cube, const LmScalars* s) {
+  const int ci = cube % VL_CUBE_W, cj = (cube / VL_CUBE_W) % VL_CUBE_H, ck = cube / (VL_CUBE_W * VL_CUBE_H);
+  return lm_vox_key(p, inv, ci, cj, ck, s->cenW, s->cenH, s->cenD);
+}
+
+// ---- LaserMapping::input (LM.cpp:178-209) + centre cube / roll / valid list (LM.cpp:228-466)
+__global__ void __launch_bounds__(1024) lm_prepare(LmScalars* __restrict__ s, const LoScalars* __restrict__ lo, MapCubeTable* __restrict__ tc,
+                                                   MapCubeTable* __restrict__ ts, RfWork* __restrict__ w, int skip) {
+  __shared__ int shift[3];
+  __shared__ int center[3];
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 4; ++k) s->q_wodom[k] = lo->q_w[k];
+    for (int k = 0; k < 3; ++k) s->t_wodom[k] = lo->t_w[k];
+    double r[3];
+    vl_qrot(s->q_wmap_wodom, s->t_wodom[0], s->t_wodom[1], s->t_wodom[2], r);
+    if (skip) {
+      vl_qmul(s->q_wmap_wodom, s->q_wodom, s->q_hf);
+      for (int k = 0; k < 3; ++k) s->t_hf[k] = r[k] + s->t_wmap_wodom[k];
+    } else {
+      double qn[4];
+      vl_qmul(s->q_wmap_wodom, s->q_wodom, qn);
+      for (int k = 0; k < 4; ++k) s->pose[k] = qn[k];
+      for (int k = 0; k < 3; ++k) s->pose[4 + k] = r[k] + s->t_wmap_wodom[k];
+    }
+    int cI = (int)((s->pose[4] + 25.0) / 50.0) + s->cenW;
+    int cJ = (int)((s->pose[5] + 25.0) / 50.0) + s->cenH;
+    int cK = (int)((s->pose[6] + 25.0) / 50.0) + s->cenD;
+    if (s->pose[4] + 25.0 < 0) cI--;
+    if (s->pose[5] + 25.0 < 0) cJ--;
+    if (s->pose[6] + 25.0 < 0) cK--;
+    int sI = 0, sJ = 0, sK = 0;
+    if (!skip) {  // net effect of the six while loops: contents move by +s along an axis
+      while (cI < 3) { cI++; sI++; }
+      while (cI >= VL_CUBE_W - 3) { cI--; sI--; }
+      while (cJ < 3) { cJ++; sJ++; }
+      while (cJ >= VL_CUBE_H - 3) { cJ--; sJ--; }
+      while (cK < 3) { cK++; sK++; }
+      while (cK >= VL_CUBE_D - 3) { cK--; sK--; }
+      s->cenW += sI; s->cenH += sJ; s->cenD += sK;
+    }
+    shift[0] = sI; shift[1] = sJ; shift[2] = sK;
+    center[0] = cI; center[1] = cJ; center[2] = cK;
+  }
+  __syncthreads();
+  if (skip) return;
+  const int sI = shift[0], sJ = shift[1], sK = shift[2];
+  if (sI != 0 || sJ != 0 || sK != 0) {
+    // new[i,j,k] = old[i-sI, j-sJ, k-sK]; entries whose source wrapped are the cleared slabs (they
+    // keep the storage of the entry that fell off the other side).
+    int v[5][8]; bool wrap[5];
+    for (int q = 0; q < 5; ++q) {
+      const int d = threadIdx.x + q * 1024;
+      if (d >= VL_CUBE_NUM) break;
+      const int i = d % VL_CUBE_W, j = (d / VL_CUBE_W) % VL_CUBE_H, k = d / (VL_CUBE_W * VL_CUBE_H);
+      const int si = i - sI, sj = j - sJ, sk = k - sK;
+      wrap[q] = si < 0 || si >= VL_CUBE_W || sj < 0 || sj >= VL_CUBE_H || sk < 0 || sk >= VL_CUBE_D;
+      // saturating modulo: multi-cube jumps still give a bijection
+      const int mi = ((si % VL_CUBE_W) + VL_CUBE_W) % VL_CUBE_W, mj = ((sj % VL_CUBE_H) + VL_CUBE_H) % VL_CUBE_H,
+                mk = ((sk % VL_CUBE_D) + VL_CUBE_D) % VL_CUBE_D;
+      const int src = mi + VL_CUBE_W * mj + VL_CUBE_W * VL_CUBE_H * mk;
+      v[q][0] = tc->start[src]; v[q][1] = tc->count[src]; v[q][2] = tc->cap[src]; v[q][3] = tc->sorted[src];
+      v[q][4] = ts->start[src]; v[q][5] = ts->count[src]; v[q][6] = ts->cap[src]; v[q][7] = ts->sorted[src];
+    }
+    __syncthreads();
+    for (int q = 0; q < 5; ++q) {
+      const int d = threadIdx.x + q * 1024;
+      if (d >= VL_CUBE_NUM) break;
+      tc->start[d] = v[q][0]; tc->count[d] = wrap[q] ? 0 : v[q][1]; tc->cap[d] = v[q][2]; tc->sorted[d] = wrap[q] ? 0 : v[q][3];
+      ts->start[d] = v[q][4]; ts->count[d] = wrap[q] ? 0 : v[q][5]; ts->cap[d] = v[q][6]; ts->sorted[d] = wrap[q] ? 0 : v[q][7];
+    }
+  }
+  for (int d = threadIdx.x; d < VL_CUBE_NUM; d += 1024) w->slotOfCube[d] = -1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int cI = center[0], cJ = center[1], cK = center[2];
+    int nv = s->validNum;  // LaserMapping::reset zeroes it once per frame (LM.cpp:132-136)
+    for (int i = cI - 2; i <= cI + 2; i++)
+      for (int j = cJ - 2; j <= cJ + 2; j++)
+        for (int k = cK - 1; k <= cK + 1; k++)
+          if (i >= 0 && i < VL_CUBE_W && j >= 0 && j < VL_CUBE_H && k >= 0 && k < VL_CUBE_D && nv < VL_MAX_VALID)
+            s->validInd[nv++] = i + VL_CUBE_W * j + VL_CUBE_W * VL_CUBE_H * k;
+    s->validNum = nv;
+    int mc = 0, ms = 0, tailAcc = 0, prefAcc = 0;
+    for (int q = 0; q < nv; ++q) {
+      const int cb = s->validInd[q];
+      w->slotOfCube[cb] = q;
+      w->gatherOff[0][q] = mc; w->gatherOff[1][q] = ms;
+      mc += tc->count[cb]; ms += ts->count[cb];
+    }
+    w->gatherOff[0][nv] = mc; w->gatherOff[1][nv] = ms;
+    s->Mc = mc; s->Ms = ms;
+    int tC = 0, tS = 0;
+    for (int kind = 0; kind < 2; ++kind)
+      for (int q = 0; q < VL_MAX_VALID; ++q) {
+        const int sg = kind * VL_MAX_VALID + q;
+        w->tailOff[sg] = tailAcc; w->prefOff[sg] = prefAcc;
+        if (q < nv) {
+          const MapCubeTable* t = kind ? ts : tc;
+          const int cb = s->validInd[q];
+          const int tl = t->count[cb] - t->sorted[cb];
+          tailAcc += tl; prefAcc += t->sorted[cb];
+          if (kind) tS += tl; else tC += tl;
+        }
+      }
+    w->tailOff[LM_NSEG] = tailAcc; w->prefOff[LM_NSEG] = prefAcc;
+    s->tailC = tC; s->tailS = tS;
+    w->gridOrigin[0] = (float)(50 * (cI - 2 - s->cenW) - 25);
+    w->gridOrigin[1] = (float)(50 * (cJ - 2 - s->cenH) - 25);
+    w->gridOrigin[2] = (float)(50 * (cK - 1 - s->cenD) - 25);
+  }
+}
+
+// LM.cpp:476-485: concatenate the valid cubes (loop order of LM.cpp:448-452) into the sub-map clouds
+__global__ void __launch_bounds__(256) lm_gather(const LmScalars* __restrict__ s, const RfWork* __restrict__ w,
+                                                 const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts,
+                                                 const float4* __restrict__ poolC, const float4* __restrict__ poolS,
+                                                 float4* __restrict__ outC, float4* __restrict__ outS) {
+  const int nv = s->validNum, mc = s->Mc, total = s->Mc + s->Ms;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
+    const int kind = g >= mc;
+    const int e = kind ? g - mc : g;
+    const int* off = w->gatherOff[kind];
+    int lo = 0, hi = nv;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid] <= e) lo = mid; else hi = mid; }
+    const int cb = s->validInd[lo];
+    if (kind) outS[e] = poolS[ts->start[cb] + (e - off[lo])];
+    else outC[e] = poolC[tc->start[cb] + (e - off[lo])];
+  }
+}
+
+// ---- search grid: counting sort of both sub-maps into 2 m cells --------------------------------
+__device__ __forceinline__ int lm_cell_coord(float v, float o, int n) {
+  const int cidx = (int)floorf(__fmul_rn(__fsub_rn(v, o), 1.0f / LM_CELL));
+  return min(max(cidx, 0), n - 1);
+}
+__global__ void __launch_bounds__(256) lm_grid_count(const LmScalars* __restrict__ s, const RfWork* __restrict__ w,
+                                                     const float4* __restrict__ mapC, const float4* __restrict__ mapS,
+                                                     int* __restrict__ cellCount, int* __restrict__ cellOfPoint) {
+  const int mc = s->Mc, total = s->Mc + s->Ms;
+  const float ox = w->gridOrigin[0], oy = w->gridOrigin[1], oz = w->gridOrigin[2];
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
+    const int kind = g >= mc;
+    const float4 p = kind ? mapS[g - mc] : mapC[g];
+    const int cell = kind * LM_NCELL + lm_cell_coord(p.x, ox, LM_GX) + LM_GX * (lm_cell_coord(p.y, oy, LM_GY) + LM_GY * lm_cell_coord(p.z, oz, LM_GZ));
+    cellOfPoint[g] = cell;
+    atomicAdd(&cellCount[cell], 1);
+  }
+}
+// exclusive scan over 2*LM_NCELL counts: tile sums (1024 per block) -> scan of tile sums -> apply
+__global__ void __launch_bounds__(256) lm_scan_tiles(const int* __restrict__ in, int n, int* __restrict__ tileSum) {
+  int acc = 0;
+  const int base = blockIdx.x * 1024;
+  for (int q = 0; q < 4; ++q) { const int t = base + q * 256 + threadIdx.x; if (t < n) acc += in[t]; }
+  __shared__ int ws[8];
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) { int v = 0; for (int k = 0; k < 8; ++k) v += ws[k]; tileSum[blockIdx.x] = v; }
+}
+__global__ void __launch_bounds__(1024) lm_scan_sums(int* __restrict__ tileSum, int nTiles) {
+  __shared__ int buf[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nTiles; base += 1024) {
+    const int b = base + threadIdx.x;
+    const int own = b < nTiles ? tileSum[b] : 0;
+    buf[threadIdx.x] = own;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+      const int v = threadIdx.x >= d ? buf[threadIdx.x - d] : 0;
+      __syncthreads();
+      buf[threadIdx.x] += v;
+      __syncthreads();
+    }
+    if (b < nTiles) tileSum[b] = carry + buf[threadIdx.x] - own;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += buf[1023];
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256) lm_scan_apply(const int* __restrict__ in, int n, const int* __restrict__ tileSum, int* __restrict__ out) {
+  __shared__ int ws[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int running = tileSum[blockIdx.x];
+  for (int q = 0; q < 4; ++q) {
+    const int t = blockIdx.x * 1024 + q * 256 + threadIdx.x;
+    const int v = t < n ? in[t] : 0;
+    int inc = v;
+    for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+    if (lane == 31) ws[warp] = inc;
+    __syncthreads();
+    int before = 0, all = 0;
+    for (int k = 0; k < 8; ++k) { if (k < warp) before += ws[k]; all += ws[k]; }
+    if (t < n) out[t] = running + before + inc - v;
+    running += all;
+    __syncthreads();
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = running;  // total
+}
+__global__ void __launch_bounds__(256) lm_grid_fill(const LmScalars* __restrict__ s, const float4* __restrict__ mapC,
+                                                    const float4* __restrict__ mapS, const int* __restrict__ cellOfPoint,
+                                                    const int* __restrict__ cellStart, int* __restrict__ cellFill,
+                                                    float4* __restrict__ sortedPts) {
+  const int mc = s->Mc, total = s->Mc + s->Ms;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
+    const int kind = g >= mc;
+    const int id = kind ? g - mc : g;  // canonical index inside its own sub-map cloud
+    const float4 p = kind ? mapS[id] : mapC[id];
+    const int cell = cellOfPoint[g];
+    const int pos = cellStart[cell] + atomicAdd(&cellFill[cell], 1);
+    sortedPts[pos] = make_float4(p.x, p.y, p.z, __int_as_float(id));
+  }
+}
+
+// ---- fits -------------------------------------------------------------------------------------
+// Same cyclic-Jacobi routine as the oracle's restatement of SelfAdjointEigenSolver (oracle_math.cpp).
+__device__ void lm_sym_eig3(double a[3][3], double evals[3], double evecs[3][3]) {
+  double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    const double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
+    if (off == 0.0) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        if (a[p][q] == 0.0) continue;
+        const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+        const double apq = a[p][q];
+        a[p][p] -= t * apq;
+        a[q][q] += t * apq;
+        a[p][q] = a[q][p] = 0.0;
+        const int r = 3 - p - q;
+        const double arp = a[r][p], arq = a[r][q];
+        a[r][p] = a[p][r] = cs * arp - sn * arq;
+        a[r][q] = a[q][r] = sn * arp + cs * arq;
+        for (int k = 0; k < 3; ++k) {
+          const double vkp = v[k][p], vkq = v[k][q];
+          v[k][p] = cs * vkp - sn * vkq;
+          v[k][q] = sn * vkp + cs * vkq;
+        }
+      }
+  }
+  int ord[3] = {0, 1, 2};  // stable insertion sort by eigenvalue (matches std::sort on 3 distinct keys)
+  for (int i = 1; i < 3; ++i) for (int j = i; j > 0 && a[ord[j]][ord[j]] < a[ord[j - 1]][ord[j - 1]]; --j) { const int t = ord[j]; ord[j] = ord[j - 1]; ord[j - 1] = t; }
+  for (int cidx = 0; cidx < 3; ++cidx) {
+    evals[cidx] = a[ord[cidx]][ord[cidx]];
+    for (int r = 0; r < 3; ++r) evecs[r][cidx] = v[r][ord[cidx]];
+  }
+}
+
+// ColPivHouseholderQR<5x3>::solve restated exactly as oracle_math.cpp does.
+__device__ void lm_qr_solve_5x3(double A[5][3], double b[5], double x[3]) {
+  int perm[3] = {0, 1, 2};
+  double maxpivot = 0.0, diag[3] = {0, 0, 0};
+  for (int k = 0; k < 3; ++k) {
+    int best = k; double bestn = -1.0;
+    for (int j = k; j < 3; ++j) { double n2 = 0; for (int i = k; i < 5; ++i) n2 += A[i][j] * A[i][j]; if (n2 > bestn) { bestn = n2; best = j; } }
+    if (best != k) { for (int i = 0; i < 5; ++i) { const double t = A[i][k]; A[i][k] = A[i][best]; A[i][best] = t; } const int t = perm[k]; perm[k] = perm[best]; perm[best] = t; }
+    double tail2 = 0; for (int i = k + 1; i < 5; ++i) tail2 += A[i][k] * A[i][k];
+    const double c0 = A[k][k];
+    double beta, tau, v[5] = {0, 0, 0, 0, 0};
+    if (tail2 <= DBL_MIN) { tau = 0; beta = c0; }
+    else {
+      beta = sqrt(c0 * c0 + tail2);
+      if (c0 >= 0) beta = -beta;
+      for (int i = k + 1; i < 5; ++i) v[i] = A[i][k] / (c0 - beta);
+      tau = (beta - c0) / beta;
+    }
+    v[k] = 1.0;
+    if (tau != 0) {
+      for (int j = k + 1; j < 3; ++j) {
+        double sm = 0; for (int i = k; i < 5; ++i) sm += v[i] * A[i][j];
+        sm *= tau; for (int i = k; i < 5; ++i) A[i][j] -= sm * v[i];
+      }
+      double sm = 0; for (int i = k; i < 5; ++i) sm += v[i] * b[i];
+      sm *= tau; for (int i = k; i < 5; ++i) b[i] -= sm * v[i];
+    }
+    A[k][k] = beta; for (int i = k + 1; i < 5; ++i) A[i][k] = 0;
+    diag[k] = beta;
+    if (fabs(beta) > maxpivot) maxpivot = fabs(beta);
+  }
+  int rank = 0;
+  for (int k = 0; k < 3; ++k) if (fabs(diag[k]) > DBL_EPSILON * 3.0 * maxpivot) ++rank;
+  double y[3] = {0, 0, 0};
+  for (int k = rank - 1; k >= 0; --k) { double sm = b[k]; for (int j = k + 1; j < rank; ++j) sm -= A[k][j] * y[j]; y[k] = sm / A[k][k]; }
+  for (int k = 0; k < 3; ++k) x[perm[k]] = y[k];
+}
+
+// One warp per downsampled feature: 5-NN in the 3x3x3 cell neighbourhood (exact inside the 1 m
+// acceptance ball), ordered by (d2, canonical id); then the line / plane fit.
+__global__ void __launch_bounds__(256) lm_knn_fit(const LmScalars* __restrict__ s, const RfWork* __restrict__ w,
+                                                  const float4* __restrict__ stackC, const float4* __restrict__ stackS,
+                                                  const float4* __restrict__ mapC, const float4* __restrict__ mapS,
+                                                  const int* __restrict__ cellStart, const float4* __restrict__ sortedPts,
+                                                  int* __restrict__ knnIdx, float* __restrict__ knnD2, int* __restrict__ knnOk,
+                                                  double* __restrict__ factors, int* __restrict__ valid) {
+  const int lane = threadIdx.x & 31;
+  const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int Qc = s->Qc, Qs = s->Qs;
+  if (qi >= Qc + Qs) return;
+  const int kind = qi >= Qc;
+  const float4 po = kind ? stackS[qi - Qc] : stackC[qi];
+  double r[3];
+  vl_qrot(s->pose, (double)po.x, (double)po.y, (double)po.z, r);  // pointAssociateToMap (LM.cpp:154-164)
+  const float sx = (float)(r[0] + s->pose[4]), sy = (float)(r[1] + s->pose[5]), sz = (float)(r[2] + s->pose[6]);
+  const float ox = w->gridOrigin[0], oy = w->gridOrigin[1], oz = w->gridOrigin[2];
+  const int cx = (int)floorf(__fmul_rn(__fsub_rn(sx, ox), 1.0f / LM_CELL));
+  const int cy = (int)floorf(__fmul_rn(__fsub_rn(sy, oy), 1.0f / LM_CELL));
+  const int cz = (int)floorf(__fmul_rn(__fsub_rn(sz, oz), 1.0f / LM_CELL));
+  float bd[5]; int bi[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) { bd[k] = CUDART_INF_F; bi[k] = 0x7fffffff; }
+  for (int row = 0; row < 9; ++row) {  // 9 (y,z) rows; the 3 x-adjacent cells of a row are contiguous
+    const int yy = cy - 1 + row % 3, zz = cz - 1 + row / 3;
+    if (yy < 0 || yy >= LM_GY || zz < 0 || zz >= LM_GZ) continue;
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, LM_GX - 1);
+    if (x0 > x1) continue;
+    const int c0 = kind * LM_NCELL + x0 + LM_GX * (yy + LM_GY * zz);
+    const int beg = cellStart[c0], end = cellStart[c0 + (x1 - x0) + 1];
+    for (int p = beg + lane; p < end; p += 32) {
+      const float4 t = __ldg(&sortedPts[p]);
+      const float d = vl_dist2(sx, sy, sz, t.x, t.y, t.z);
+      const int id = __float_as_int(t.w);
+      if (d < bd[4] || (d == bd[4] && id < bi[4])) {  // insertion into the lane-local sorted top-5
+        bd[4] = d; bi[4] = id;
+#pragma unroll
+        for (int k = 4; k > 0; --k)
+          if (bd[k] < bd[k - 1] || (bd[k] == bd[k - 1] && bi[k] < bi[k - 1])) {
+            const float td = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td;
+            const int ti = bi[k]; bi[k] = bi[k - 1]; bi[k - 1] = ti;
+          }
+      }
+    }
+  }
+  // merge the 32 lane-local lists: pop the global minimum five times
+  float nd[5]; int ni[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    float d = bd[0]; int id = bi[0]; int src = lane;
+    for (int off = 16; off > 0; off >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, d, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, id, off);
+      const int os = __shfl_xor_sync(0xffffffffu, src, off);
+      if (od < d || (od == d && oi < id)) { d = od; id = oi; src = os; }
+    }
+    nd[k] = d; ni[k] = id;
+    if (lane == src && id != 0x7fffffff) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { bd[q] = bd[q + 1]; bi[q] = bi[q + 1]; }
+      bd[4] = CUDART_INF_F; bi[4] = 0x7fffffff;
+    }
+  }
+  if (lane != 0) return;
+  const bool have5 = ni[4] != 0x7fffffff;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) { knnIdx[qi * 5 + k] = (ni[k] == 0x7fffffff) ? -1 : ni[k]; knnD2[qi * 5 + k] = nd[k]; }
+  bool ok = false;
+  double* f = factors + (size_t)qi * 10;
+  if (have5 && (double)nd[4] < 1.0) {
+    const float4* map = kind ? mapS : mapC;
+    double P[5][3];
+    for (int j = 0; j < 5; ++j) { const float4 t = map[ni[j]]; P[j][0] = t.x; P[j][1] = t.y; P[j][2] = t.z; }
+    if (!kind) {  // LM.cpp:559-603: PCA line test
+      double cen[3] = {0, 0, 0};
+      for (int j = 0; j < 5; ++j) for (int k = 0; k < 3; ++k) cen[k] = cen[k] + P[j][k];
+      for (int k = 0; k < 3; ++k) cen[k] = cen[k] / 5.0;
+      double cov[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      for (int j = 0; j < 5; ++j) {
+        const double z[3] = {P[j][0] - cen[0], P[j][1] - cen[1], P[j][2] - cen[2]};
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) cov[a][b] = cov[a][b] + z[a] * z[b];
+      }
+      double ev[3], evec[3][3];
+      lm_sym_eig3(cov, ev, evec);
+      if (ev[2] > 3 * ev[1]) {
+        ok = true;
+        f[0] = 0.0; f[1] = po.x; f[2] = po.y; f[3] = po.z;
+        for (int k = 0; k < 3; ++k) { const double u = evec[k][2]; f[4 + k] = 0.1 * u + cen[k]; f[7 + k] = -0.1 * u + cen[k]; }
+      }
+    } else {  // LM.cpp:637-680: least-squares plane n.p + 1 = 0, 0.2 m flatness check
+      double A[5][3], B[5] = {-1, -1, -1, -1, -1}, nrm[3];
+      for (int j = 0; j < 5; ++j) for (int k = 0; k < 3; ++k) A[j][k] = P[j][k];
+      lm_qr_solve_5x3(A, B, nrm);
+      const double nn = sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
+      const double d = 1 / nn;
+      if (nn > 0) { nrm[0] /= nn; nrm[1] /= nn; nrm[2] /= nn; }
+      bool planeValid = true;
+      for (int j = 0; j < 5; ++j)
+        if (fabs(nrm[0] * P[j][0] + nrm[1] * P[j][1] + nrm[2] * P[j][2] + d) > 0.2) { planeValid = false; break; }
+      if (planeValid) {
+        ok = true;
+        f[0] = 2.0; f[1] = po.x; f[2] = po.y; f[3] = po.z;
+        f[4] = nrm[0]; f[5] = nrm[1]; f[6] = nrm[2]; f[7] = d; f[8] = 0; f[9] = 0;
+      }
+    }
+  }
+  valid[qi] = ok ? 1 : 0;
+  knnOk[qi] = ok ? 1 : 0;
+}
+
+__global__ void lm_transform_update(LmScalars* s) {  // LM.cpp:147-151
+  if (threadIdx.x != 0) return;
+  const double* q = s->q_wodom;
+  const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  const double qi[4] = {-q[0] / n2, -q[1] / n2, -q[2] / n2, q[3] / n2};
+  vl_qmul(s->pose, qi, s->q_wmap_wodom);
+  double r[3];
+  vl_qrot(s->q_wmap_wodom, s->t_wodom[0], s->t_wodom[1], s->t_wodom[2], r);
+  for (int k = 0; k < 3; ++k) s->t_wmap_wodom[k] = s->pose[4 + k] - r[k];
+}
+
+// ---- map update: insert (LM.cpp:741-788) + per-cube VoxelGrid re-filter (LM.cpp:795-808) -------
+// sort key: [63:56] segment (kind*125 + valid slot) | [55:26] voxel (iz,iy,ix) | [25:0] order
+// order: existing tail point -> its position in the cube; new point -> 2^25 + stack index.
+__device__ __forceinline__ float lm_leaf_inv(const vloam_b200_params& p, int kind) { return __fdiv_rn(1.0f, kind ? p.plane_res : p.line_res); }
+
+__global__ void __launch_bounds__(256) rf_keys(const LmScalars* __restrict__ s, const RfWork* __restrict__ w, vloam_b200_params prm,
+                                               const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts,
+                                               const float4* __restrict__ poolC, const float4* __restrict__ poolS,
+                                               const float4* __restrict__ stackC, const float4* __restrict__ stackS,
+                                               float4* __restrict__ newPts, int* __restrict__ newCube,
+                                               unsigned long long* __restrict__ keys, int P) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= P) return;
+  const int tailTotal = w->tailOff[LM_NSEG];
+  const int Qc = s->Qc, Qs = s->Qs;
+  unsigned long long key = ~0ull;
+  if (g < tailTotal) {  // an existing tail point of a valid cube
+    int lo = 0, hi = LM_NSEG;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (w->tailOff[mid] <= g) lo = mid; else hi = mid; }
+    const int kind = lo / VL_MAX_VALID, slot = lo % VL_MAX_VALID;
+    const int cb = s->validInd[slot];
+    const MapCubeTable* t = kind ? ts : tc;
+    const int pos = t->sorted[cb] + (g - w->tailOff[lo]);
+    const float4 p = (kind ? poolS : poolC)[t->start[cb] + pos];
+    const unsigned vk = lm_vox_key_cube(p, lm_leaf_inv(prm, kind), cb, s);
+    key = ((unsigned long long)lo << 56) | ((unsigned long long)vk << 26) | (unsigned long long)pos;
+  } else if (g < tailTotal + Qc + Qs) {  // this frame's point i of the stacks
+    const int i = g - tailTotal;
+    const int kind = i >= Qc;
+    const float4 po = kind ? stackS[i - Qc] : stackC[i];
+    double r[3];
+    vl_qrot(s->pose, (double)po.x, (double)po.y, (double)po.z, r);
+    const float4 p = make_float4((float)(r[0] + s->pose[4]), (float)(r[1] + s->pose[5]), (float)(r[2] + s->pose[6]), po.w);
+    const int ci = lm_cube_of(p.x, s->cenW), cj = lm_cube_of(p.y, s->cenH), ck = lm_cube_of(p.z, s->cenD);
+    int cb = -1;
+    if (ci >= 0 && ci < VL_CUBE_W && cj >= 0 && cj < VL_CUBE_H && ck >= 0 && ck < VL_CUBE_D) cb = ci + VL_CUBE_W * cj + VL_CUBE_W * VL_CUBE_H * ck;
+    newPts[i] = p;
+    const int slot = cb >= 0 ? w->slotOfCube[cb] : -1;
+    newCube[i] = (cb >= 0 && slot < 0) ? cb : -1;  // only cubes outside the window need the raw append path
+    if (slot >= 0) {
+      const unsigned vk = lm_vox_key(p, lm_leaf_inv(prm, kind), ci, cj, ck, s->cenW, s->cenH, s->cenD);
+      key = ((unsigned long long)(kind * VL_MAX_VALID + slot) << 56) | ((unsigned long long)vk << 26) | (unsigned long long)((1u << 25) + (unsigned)i);
+    }
+  }
+  keys[g] = key;
+}
+
+__device__ __forceinline__ float4 rf_key_point(unsigned long long key, const LmScalars* s, const MapCubeTable* tc, const MapCubeTable* ts,
+                                               const float4* poolC, const float4* poolS, const float4* newPts) {
+  const unsigned ord = (unsigned)(key & 0x3ffffffull);
+  if (ord >= (1u << 25)) return newPts[ord - (1u << 25)];
+  const int sg = (int)(key >> 56);
+  const int kind = sg / VL_MAX_VALID, cb = s->validInd[sg % VL_MAX_VALID];
+  return (kind ? poolS : poolC)[(kind ? ts : tc)->start[cb] + (int)ord];
+}
+#define RF_VOX(key) ((unsigned)(((key) >> 26) & 0x3fffffffull))
+
+__global__ void __launch_bounds__(256) rf_segments(const unsigned long long* __restrict__ keys, int P, RfWork* __restrict__ w) {
+  const int sg = threadIdx.x;
+  if (sg > LM_NSEG) return;
+  const unsigned long long target = (unsigned long long)sg << 56;
+  int lo = 0, hi = P;  // first index with key >= target
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < target) lo = mid + 1; else hi = mid; }
+  w->tailBegin[sg] = lo;
+  if (sg == LM_NSEG) w->nKeysValid = lo;
+  if (sg < LM_NSEG) w->firstViolation[sg] = INT_MAX;
+}
+
+// For each sorted tail key: is it the head of a run that no prefix point owns?
+__global__ void __launch_bounds__(256) rf_match(const unsigned long long* __restrict__ keys, const LmScalars* __restrict__ s,
+                                                const RfWork* __restrict__ w, vloam_b200_params prm, const MapCubeTable* __restrict__ tc,
+                                                const MapCubeTable* __restrict__ ts, const float4* __restrict__ poolC,
+                                                const float4* __restrict__ poolS, int* __restrict__ unmatchedHead) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= w->nKeysValid) return;
+  const unsigned long long key = keys[t];
+  const int sg = (int)(key >> 56);
+  const unsigned vk = RF_VOX(key);
+  const bool head = (t == w->tailBegin[sg]) || RF_VOX(keys[t - 1]) != vk;
+  int um = 0;
+  if (head) {
+    const int kind = sg / VL_MAX_VALID, cb = s->validInd[sg % VL_MAX_VALID];
+    const MapCubeTable* tb = kind ? ts : tc;
+    const float4* pool = (kind ? poolS : poolC) + tb->start[cb];
+    const float inv = lm_leaf_inv(prm, kind);
+    int lo = 0, hi = tb->sorted[cb];
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (lm_vox_key_cube(pool[mid], inv, cb, s) < vk) lo = mid + 1; else hi = mid; }
+    const bool matched = lo < tb->sorted[cb] && lm_vox_key_cube(pool[lo], inv, cb, s) == vk;
+    um = matched ? 0 : 1;
+  }
+  unmatchedHead[t] = um;
+}
+
+__global__ void __launch_bounds__(1024) rf_scan_layout(int* __restrict__ unmatched, const LmScalars* __restrict__ s, RfWork* __restrict__ w,
+                                                       const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts) {
+  // exclusive scan of unmatched[0..n) in place, unmatched[n] = total
+  __shared__ int buf[1024];
+  __shared__ int carry;
+  const int n = w->nKeysValid;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int b = base + threadIdx.x;
+    const int own = b < n ? unmatched[b] : 0;
+    buf[threadIdx.x] = own;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+      const int v = threadIdx.x >= d ? buf[threadIdx.x - d] : 0;
+      __syncthreads();
+      buf[threadIdx.x] += v;
+      __syncthreads();
+    }
+    if (b < n) unmatched[b] = carry + buf[threadIdx.x] - own;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += buf[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    unmatched[n] = carry;
+    int acc = 0;
+    for (int sg = 0; sg < LM_NSEG; ++sg) {
+      const int kind = sg / VL_MAX_VALID, slot = sg % VL_MAX_VALID;
+      int cnt = 0;
+      if (slot < s->validNum) {
+        const int cb = s->validInd[slot];
+        cnt = (kind ? ts : tc)->sorted[cb] + (unmatched[w->tailBegin[sg + 1]] - unmatched[w->tailBegin[sg]]);
+      }
+      w->outOff[sg] = acc; w->outCount[sg] = cnt;
+      acc += cnt;
+    }
+    w->outOff[LM_NSEG] = acc;
+  }
+}
+
+__device__ __forceinline__ float4 rf_fold(float4 acc, const float4 p) {
+  return make_float4(__fadd_rn(acc.x, p.x), __fadd_rn(acc.y, p.y), __fadd_rn(acc.z, p.z), __fadd_rn(acc.w, p.w));
+}
+__device__ __forceinline__ float4 rf_centroid(const float4 acc, int n) {
+  const float fn = (float)n;
+  return make_float4(__fdiv_rn(acc.x, fn), __fdiv_rn(acc.y, fn), __fdiv_rn(acc.z, fn), __fdiv_rn(acc.w, fn));
+}
+
+// new voxels: runs of tail keys that no prefix point owns
+__global__ void __launch_bounds__(256) rf_emit_new(const unsigned long long* __restrict__ keys, const int* __restrict__ uScan,
+                                                   const LmScalars* __restrict__ s, const RfWork* __restrict__ w, vloam_b200_params prm,
+                                                   const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts,
+                                                   const float4* __restrict__ poolC, const float4* __restrict__ poolS,
+                                                   const float4* __restrict__ newPts, float4* __restrict__ staging) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = w->nKeysValid;
+  if (t >= n) return;
+  if (uScan[t + 1] == uScan[t]) return;  // not an unmatched head
+  const unsigned long long key = keys[t];
+  const int sg = (int)(key >> 56);
+  const unsigned vk = RF_VOX(key);
+  const int segEnd = w->tailBegin[sg + 1];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int cnt = 0;
+  for (int q = t; q < segEnd && RF_VOX(keys[q]) == vk; ++q) { acc = rf_fold(acc, rf_key_point(keys[q], s, tc, ts, poolC, poolS, newPts)); ++cnt; }
+  const int kind = sg / VL_MAX_VALID, cb = s->validInd[sg % VL_MAX_VALID];
+  const MapCubeTable* tb = kind ? ts : tc;
+  const float4* pool = (kind ? poolS : poolC) + tb->start[cb];
+  const float inv = lm_leaf_inv(prm, kind);
+  int lo = 0, hi = tb->sorted[cb];
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (lm_vox_key_cube(pool[mid], inv, cb, s) < vk) lo = mid + 1; else hi = mid; }
+  staging[w->outOff[sg] + lo + (uScan[t] - uScan[w->tailBegin[sg]])] = rf_centroid(acc, cnt);
+}
+
+// prefix points: shifted by the new voxels that sort before them; absorb a matching tail run
+__global__ void __launch_bounds__(256) rf_emit_prefix(const unsigned long long* __restrict__ keys, const int* __restrict__ uScan,
+                                                      const LmScalars* __restrict__ s, const RfWork* __restrict__ w, vloam_b200_params prm,
+                                                      const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts,
+                                                      const float4* __restrict__ poolC, const float4* __restrict__ poolS,
+                                                      const float4* __restrict__ newPts, float4* __restrict__ staging) {
+  const int total = w->prefOff[LM_NSEG];
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
+    int lo = 0, hi = LM_NSEG;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (w->prefOff[mid] <= g) lo = mid; else hi = mid; }
+    const int sg = lo, i = g - w->prefOff[sg];
+    const int kind = sg / VL_MAX_VALID, cb = s->validInd[sg % VL_MAX_VALID];
+    const MapCubeTable* tb = kind ? ts : tc;
+    const float4 p = (kind ? poolS : poolC)[tb->start[cb] + i];
+    const unsigned vk = lm_vox_key_cube(p, lm_leaf_inv(prm, kind), cb, s);
+    int a = w->tailBegin[sg], b = w->tailBegin[sg + 1];
+    const int segBegin = a, segEnd = b;
+    while (a < b) { const int mid = (a + b) >> 1; if (RF_VOX(keys[mid]) < vk) a = mid + 1; else b = mid; }
+    float4 acc = rf_fold(make_float4(0.f, 0.f, 0.f, 0.f), p);
+    int cnt = 1;
+    for (int q = a; q < segEnd && RF_VOX(keys[q]) == vk; ++q) { acc = rf_fold(acc, rf_key_point(keys[q], s, tc, ts, poolC, poolS, newPts)); ++cnt; }
+    staging[w->outOff[sg] + i + (uScan[a] - uScan[segBegin])] = rf_centroid(acc, cnt);
+  }
+}
+
+// grow cube storage where the re-filtered cloud no longer fits (bump allocation from the pool top)
+__global__ void rf_alloc(LmScalars* __restrict__ s, const RfWork* __restrict__ w, MapCubeTable* __restrict__ tc, MapCubeTable* __restrict__ ts,
+                         int poolCapC, int poolCapS) {
+  if (threadIdx.x != 0) return;
+  for (int sg = 0; sg < LM_NSEG; ++sg) {
+    const int kind = sg / VL_MAX_VALID, slot = sg % VL_MAX_VALID;
+    if (slot >= s->validNum) continue;
+    const int cb = s->validInd[slot];
+    MapCubeTable* tb = kind ? ts : tc;
+    const int need = w->outCount[sg];
+    if (need > tb->cap[cb]) {
+      const int ncap = max(2 * need, 256);
+      int& top = kind ? s->poolTopS : s->poolTopC;
+      if (top + ncap > (kind ? poolCapS : poolCapC)) { s->overflow = 1; continue; }
+      tb->start[cb] = top; tb->cap[cb] = ncap; top += ncap;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) rf_commit(const float4* __restrict__ staging, LmScalars* __restrict__ s, RfWork* __restrict__ w,
+                                                 vloam_b200_params prm, MapCubeTable* __restrict__ tc, MapCubeTable* __restrict__ ts,
+                                                 float4* __restrict__ poolC, float4* __restrict__ poolS) {
+  const int total = w->outOff[LM_NSEG];
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
+    int lo = 0, hi = LM_NSEG;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (w->outOff[mid] <= g) lo = mid; else hi = mid; }
+    const int sg = lo, k = g - w->outOff[sg];
+    const int kind = sg / VL_MAX_VALID, cb = s->validInd[sg % VL_MAX_VALID];
+    MapCubeTable* tb = kind ? ts : tc;
+    if (w->outCount[sg] > tb->cap[cb]) continue;  // pool exhausted (overflow flag is set)
+    const float4 p = staging[g];
+    (kind ? poolS : poolC)[tb->start[cb] + k] = p;
+    if (k > 0) {  // does the re-filtered cloud keep one point per voxel in ascending order?
+      const float inv = lm_leaf_inv(prm, kind);
+      if (lm_vox_key_cube(staging[g - 1], inv, cb, s) >= lm_vox_key_cube(p, inv, cb, s)) atomicMin(&w->firstViolation[sg], k);
+    }
+  }
+}
+
+__global__ void rf_finish(LmScalars* __restrict__ s, const RfWork* __restrict__ w, MapCubeTable* __restrict__ tc, MapCubeTable* __restrict__ ts) {
+  const int sg = threadIdx.x;
+  if (sg >= LM_NSEG) return;
+  const int kind = sg / VL_MAX_VALID, slot = sg % VL_MAX_VALID;
+  if (slot >= s->validNum) return;
+  const int cb = s->validInd[slot];
+  MapCubeTable* tb = kind ? ts : tc;
+  if (w->outCount[sg] > tb->cap[cb]) return;
+  tb->count[cb] = w->outCount[sg];
+  tb->sorted[cb] = min(w->outCount[sg], w->firstViolation[sg]);
+}
+
+// Points that land in a cube outside the 5x5x3 window are appended raw, in stack order (LM.cpp:762, 786).
+__global__ void __launch_bounds__(1024) rf_append_outside(LmScalars* __restrict__ s, const float4* __restrict__ newPts,
+                                                          const int* __restrict__ newCube, MapCubeTable* __restrict__ tc,
+                                                          MapCubeTable* __restrict__ ts, float4* __restrict__ poolC, float4* __restrict__ poolS,
+                                                          int poolCapC, int poolCapS) {
+  const int Qc = s->Qc, total = s->Qc + s->Qs;
+  __shared__ int sNewStart, sOldStart, sCopy;
+  for (int base = 0; base < total; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int cb = i < total ? newCube[i] : -1;
+    if (__syncthreads_or(cb >= 0) == 0) continue;
+    // rare path: serialise the chunk in stack order
+    for (int k = 0; k < 1024 && base + k < total; ++k) {
+      const int cbk = newCube[base + k];
+      if (cbk < 0) continue;
+      const int kind = (base + k) >= Qc;
+      MapCubeTable* tb = kind ? ts : tc;
+      float4* pool = kind ? poolS : poolC;
+      if (threadIdx.x == 0) {
+        sCopy = 0;
+        if (tb->count[cbk] + 1 > tb->cap[cbk]) {
+          const int ncap = max(2 * (tb->count[cbk] + 1), 256);
+          int& top = kind ? s->poolTopS : s->poolTopC;
+          if (top + ncap > (kind ? poolCapS : poolCapC)) { s->overflow = 1; sCopy = -1; }
+          else { sOldStart = tb->start[cbk]; sNewStart = top; top += ncap; tb->start[cbk] = sNewStart; tb->cap[cbk] = ncap; sCopy = 1; }
+        }
+      }
+      __syncthreads();
+      if (sCopy == 1) for (int q = threadIdx.x; q < tb->count[cbk]; q += 1024) pool[sNewStart + q] = pool[sOldStart + q];
+      __syncthreads();
+      if (threadIdx.x == 0 && sCopy >= 0) { pool[tb->start[cbk] + tb->count[cbk]] = newPts[base + k]; tb->count[cbk]++; }
+      __syncthreads();
+    }
+  }
+}
+
+// after an import: longest strictly increasing voxel-key prefix of every cube
+__global__ void __launch_bounds__(256) lm_scan_sorted(const LmScalars* __restrict__ s, vloam_b200_params prm, MapCubeTable* __restrict__ t,
+                                                      const float4* __restrict__ pool, int kind) {
+  const int cb = blockIdx.x;
+  __shared__ int firstBad;
+  if (threadIdx.x == 0) firstBad = INT_MAX;
+  __syncthreads();
+  const int n = t->count[cb];
+  const float inv = lm_leaf_inv(prm, kind);
+  const float4* p = pool + t->start[cb];
+  for (int k = 1 + threadIdx.x; k < n; k += blockDim.x)
+    if (lm_vox_key_cube(p[k - 1], inv, cb, s) >= lm_vox_key_cube(p[k], inv, cb, s)) atomicMin(&firstBad, k);
+  __syncthreads();
+  if (threadIdx.x == 0) t->sorted[cb] = min(n, firstBad);
+}
+
+__global__ void lm_set_counts(LmScalars* s, const int* qc, const int* qs) { if (threadIdx.x == 0) { s->Qc = *qc; s->Qs = *qs; } }
+
+// -----------------------------------------------------------------------------------------------
+#define LM_POOL_C (16 << 20)
+#define LM_POOL_S (48 << 20)
+
+struct LmDevice {  // extra device state owned by this file
+  RfWork* work;
+  int* cellCount;   // 2*LM_NCELL + 1 (scan output in place: cellStart)
+  int* cellStart;
+  int* cellFill;
+  int* tileSum;
+  DBuf<int> cellOfPoint;
+  DBuf<float4> sortedPts;
+  DBuf<float4> newPts; DBuf<int> newCube;
+  DBuf<int> unmatched;
+  int* dQ;          // two device ints: Qc, Qs from the voxel filters
+  long long hMapUpperC, hMapUpperS;  // host upper bounds on the total map size
+};
+static LmDevice* lmdev(vloam_b200_ctx* c) { return reinterpret_cast<LmDevice*>(c->gridPrm); }
+
+int vl_lm_init(vloam_b200_ctx* c) {
+  LmDevice* d = new LmDevice();
+  c->gridPrm = reinterpret_cast<GridParams*>(d);
+  VL_CUDA(cudaMalloc(&d->work, sizeof(RfWork)));
+  VL_CUDA(cudaMemset(d->work, 0, sizeof(RfWork)));
+  VL_CUDA(cudaMalloc(&d->cellCount, sizeof(int) * (2 * LM_NCELL + 1)));
+  VL_CUDA(cudaMalloc(&d->cellStart, sizeof(int) * (2 * LM_NCELL + 1)));
+  VL_CUDA(cudaMalloc(&d->cellFill, sizeof(int) * (2 * LM_NCELL + 1)));
+  VL_CUDA(cudaMalloc(&d->tileSum, sizeof(int) * (vl_div_up(2 * LM_NCELL, 1024) + 1)));
+  VL_CUDA(cudaMalloc(&d->dQ, sizeof(int) * 2));
+  d->hMapUpperC = d->hMapUpperS = 0;
+  VL_TRY(vl_reserve(c, c->poolC, LM_POOL_C));
+  VL_TRY(vl_reserve(c, c->poolS, LM_POOL_S));
+  VL_CUDA(cudaMemset(c->cubeC, 0, sizeof(MapCubeTable)));
+  VL_CUDA(cudaMemset(c->cubeS, 0, sizeof(MapCubeTable)));
+  LmScalars h;
+  memset(&h, 0, sizeof h);
+  h.cenW = 10; h.cenH = 10; h.cenD = 5;  // LM.h:75-78
+  h.pose[3] = 1.0; h.q_wmap_wodom[3] = 1.0; h.q_wodom[3] = 1.0; h.q_hf[3] = 1.0;
+  VL_CUDA(cudaMemcpy(c->lmm, &h, sizeof h, cudaMemcpyHostToDevice));
+  *c->h_lmm = h;
+  return VLOAM_OK;
+}
+
+extern bool vl_debug_capture(const vloam_b200_ctx* c);
+
+int vl_lm_run(vloam_b200_ctx* c) {
+  LmDevice* d = lmdev(c);
+  const int skip = c->skip_frame ? 1 : 0;
+  VL_LAUNCH(lm_prepare, 1, 1024, 0, c->lmm, c->los, c->cubeC, c->cubeS, d->work, skip);
+  if (skip) { VL_CUDA(cudaGetLastError()); return VLOAM_OK; }
+  const int gsGrid = c->num_sms * 8;
+  VL_TRY(vl_reserve(c, c->fromMapC, (size_t)max(d->hMapUpperC, 1LL)));
+  VL_TRY(vl_reserve(c, c->fromMapS, (size_t)max(d->hMapUpperS, 1LL)));
+  VL_LAUNCH(lm_gather, gsGrid, 256, 0, c->lmm, d->work, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, c->fromMapC.p, c->fromMapS.p);
+  // LM.cpp:492-500: VoxelGrid of this frame's less-sharp / less-flat clouds
+  VL_TRY(vl_reserve(c, c->stackC, (size_t)max(c->nCornerLast, 1)));
+  VL_TRY(vl_reserve(c, c->stackS, (size_t)max(c->nSurfLast, 1)));
+  VL_TRY(vl_voxel_grid_device(c, c->cornerLastPtr, c->nCornerLast, nullptr, c->prm.line_res, c->stackC.p, d->dQ));
+  VL_TRY(vl_voxel_grid_device(c, c->surfLastPtr, c->nSurfLast, nullptr, c->prm.plane_res, c->stackS.p, d->dQ + 1));
+  VL_LAUNCH(lm_set_counts, 1, 32, 0, c->lmm, d->dQ, d->dQ + 1);
+  // ---- sync point S2
+  VL_CUDA(cudaMemcpyAsync(c->h_lmm, c->lmm, sizeof(LmScalars), cudaMemcpyDeviceToHost, c->stream));
+  VL_CUDA(cudaStreamSynchronize(c->stream));
+  const int Mc = c->h_lmm->Mc, Ms = c->h_lmm->Ms, Qc = c->h_lmm->Qc, Qs = c->h_lmm->Qs;
+  const int tailTotal = c->h_lmm->tailC + c->h_lmm->tailS;
+  const int nq = Qc + Qs;
+  bool optimized = false;
+  if (Mc > 10 && Ms > 50 && nq > 0) {  // LM.cpp:514
+    optimized = true;
+    const int total = Mc + Ms;
+    const int nCells = 2 * LM_NCELL;
+    VL_TRY(vl_reserve(c, d->cellOfPoint, (size_t)total));
+    VL_TRY(vl_reserve(c, d->sortedPts, (size_t)total));
+    VL_CUDA(cudaMemsetAsync(d->cellCount, 0, sizeof(int) * (nCells + 1), c->stream));
+    VL_CUDA(cudaMemsetAsync(d->cellFill, 0, sizeof(int) * (nCells + 1), c->stream));
+    VL_LAUNCH(lm_grid_count, gsGrid, 256, 0, c->lmm, d->work, c->fromMapC.p, c->fromMapS.p, d->cellCount, d->cellOfPoint.p);
+    const int nTiles = vl_div_up(nCells, 1024);
+    VL_LAUNCH(lm_scan_tiles, nTiles, 256, 0, d->cellCount, nCells, d->tileSum);
+    VL_LAUNCH(lm_scan_sums, 1, 1024, 0, d->tileSum, nTiles);
+    VL_LAUNCH(lm_scan_apply, nTiles, 256, 0, d->cellCount, nCells, d->tileSum, d->cellStart);
+    VL_LAUNCH(lm_grid_fill, gsGrid, 256, 0, c->lmm, c->fromMapC.p, c->fromMapS.p, d->cellOfPoint.p, d->cellStart, d->cellFill, d->sortedPts.p);
+    VL_TRY(vl_reserve(c, c->knnIdx, (size_t)nq * 5));
+    VL_TRY(vl_reserve(c, c->knnD2, (size_t)nq * 5));
+    VL_TRY(vl_reserve(c, c->knnOk, (size_t)nq));
+    VL_TRY(vl_reserve(c, c->factors, (size_t)nq * 10));
+    VL_TRY(vl_reserve(c, c->factorValid, (size_t)nq));
+    for (int pass = 0; pass < 2; ++pass) {  // LM.cpp:526
+      VL_LAUNCH(lm_knn_fit, vl_div_up((long long)nq * 32, 256), 256, 0, c->lmm, d->work, c->stackC.p, c->stackS.p, c->fromMapC.p,
+                c->fromMapS.p, d->cellStart, d->sortedPts.p, c->knnIdx.p, c->knnD2.p, c->knnOk.p, c->factors.p, c->factorValid.p);
+      if (vl_debug_capture(c)) {
+        for (int kind = 0; kind < 2; ++kind) {
+          const int n = kind ? Qs : Qc, off = kind ? Qc : 0;
+          VL_TRY(vl_reserve(c, c->dbgKnnIdx[pass][kind], (size_t)max(n, 1) * 5));
+          VL_TRY(vl_reserve(c, c->dbgKnnD2[pass][kind], (size_t)max(n, 1) * 5));
+          VL_TRY(vl_reserve(c, c->dbgKnnOk[pass][kind], (size_t)max(n, 1)));
+          if (n == 0) continue;
+          VL_CUDA(cudaMemcpyAsync(c->dbgKnnIdx[pass][kind].p, c->knnIdx.p + (size_t)off * 5, sizeof(int) * 5 * n, cudaMemcpyDeviceToDevice, c->stream));
+          VL_CUDA(cudaMemcpyAsync(c->dbgKnnD2[pass][kind].p, c->knnD2.p + (size_t)off * 5, sizeof(float) * 5 * n, cudaMemcpyDeviceToDevice, c->stream));
+          VL_CUDA(cudaMemcpyAsync(c->dbgKnnOk[pass][kind].p, c->knnOk.p + off, sizeof(int) * n, cudaMemcpyDeviceToDevice, c->stream));
+        }
+      }
+      VL_TRY(vl_solve(c, nq, c->lmm->pose, vl_debug_capture(c) ? &c->dbgLmCost[pass * 2] : nullptr));
+    }
+  }
+  c->lm_optimized = optimized ? 1 : 0;
+  VL_LAUNCH(lm_transform_update, 1, 32, 0, c->lmm);  // LM.cpp:737 (runs even when the optimisation was skipped)
+  // ---- map update
+  const int nKeys = tailTotal + nq;
+  if (nKeys > 0) {
+    int P = 2; while (P < nKeys) P <<= 1;
+    VL_TRY(vl_reserve(c, c->tailKeys, (size_t)P));
+    VL_TRY(vl_reserve(c, d->newPts, (size_t)max(nq, 1)));
+    VL_TRY(vl_reserve(c, d->newCube, (size_t)max(nq, 1)));
+    VL_TRY(vl_reserve(c, d->unmatched, (size_t)nKeys + 2));
+    VL_TRY(vl_reserve(c, c->staging, (size_t)Mc + Ms + nKeys + 1));
+    VL_LAUNCH(rf_keys, vl_div_up(P, 256), 256, 0, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, c->stackC.p, c->stackS.p,
+              d->newPts.p, d->newCube.p, c->tailKeys.p, P);
+    VL_TRY(vl_sort_u64(c, c->tailKeys.p, P));
+    VL_LAUNCH(rf_segments, 1, 256, 0, c->tailKeys.p, P, d->work);
+    VL_LAUNCH(rf_match, vl_div_up(nKeys, 256), 256, 0, c->tailKeys.p, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, d->unmatched.p);
+    VL_LAUNCH(rf_scan_layout, 1, 1024, 0, d->unmatched.p, c->lmm, d->work, c->cubeC, c->cubeS);
+    VL_LAUNCH(rf_emit_new, vl_div_up(nKeys, 256), 256, 0, c->tailKeys.p, d->unmatched.p, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p,
+              c->poolS.p, d->newPts.p, c->staging.p);
+    VL_LAUNCH(rf_emit_prefix, gsGrid, 256, 0, c->tailKeys.p, d->unmatched.p, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p,
+              d->newPts.p, c->staging.p);
+    VL_LAUNCH(rf_alloc, 1, 32, 0, c->lmm, d->work, c->cubeC, c->cubeS, (int)c->poolC.cap, (int)c->poolS.cap);
+    VL_LAUNCH(rf_commit, gsGrid, 256, 0, c->staging.p, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p);
+    VL_LAUNCH(rf_finish, 1, 256, 0, c->lmm, d->work, c->cubeC, c->cubeS);
+    if (nq > 0)
+      VL_LAUNCH(rf_append_outside, 1, 1024, 0, c->lmm, d->newPts.p, d->newCube.p, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, (int)c->poolC.cap,
+                (int)c->poolS.cap);
+  }
+  d->hMapUpperC += Qc; d->hMapUpperS += Qs;
+  c->lm_frameCount++;
+  VL_CUDA(cudaGetLastError());
+  return VLOAM_OK;
+}
+
+int vl_lm_rescan_sorted(vloam_b200_ctx* c) {
+  VL_LAUNCH(lm_scan_sorted, VL_CUBE_NUM, 256, 0, c->lmm, c->prm, c->cubeC, c->poolC.p, 0);
+  VL_LAUNCH(lm_scan_sorted, VL_CUBE_NUM, 256, 0, c->lmm, c->prm, c->cubeS, c->poolS.p, 1);
+  VL_CUDA(cudaStreamSynchronize(c->stream));
+  return VLOAM_OK;
+}
+
+// blob = int32 counts[4851] followed by the points of all cubes in cube-index order
+int vl_lm_export_map(vloam_b200_ctx* c, int which, void* out, long cap, long* bytes) {
+  MapCubeTable h;
+  VL_CUDA(cudaStreamSynchronize(c->stream));
+  VL_CUDA(cudaMemcpy(&h, which ? c->cubeS : c->cubeC, sizeof h, cudaMemcpyDeviceToHost));
+  long total = 0;
+  for (int i = 0; i < VL_CUBE_NUM; ++i) total += h.count[i];
+  *bytes = (long)VL_CUBE_NUM * 4 + total * 16;
+  if (!out || cap < *bytes) return VLOAM_OK;
+  memcpy(out, h.count, (size_t)VL_CUBE_NUM * 4);
+  char* p = (char*)out + (size_t)VL_CUBE_NUM * 4;
+  const float4* pool = which ? c->poolS.p : c->poolC.p;
+  for (int i = 0; i < VL_CUBE_NUM; ++i) {
+    if (h.count[i] == 0) continue;
+    VL_CUDA(cudaMemcpy(p, pool + h.start[i], (size_t)h.count[i] * 16, cudaMemcpyDeviceToHost));
+    p += (size_t)h.count[i] * 16;
+  }
+  return VLOAM_OK;
+}
+
+int vl_lm_import_map(vloam_b200_ctx* c, int which, const void* data, long bytes) {
+  LmDevice* d = lmdev(c);
+  if (bytes < (long)VL_CUBE_NUM * 4) { snprintf(c->err, sizeof c->err, "map blob too short"); return VLOAM_E_INVALID; }
+  const int* counts = (const int*)data;
+  long long total = 0;
+  for (int i = 0; i < VL_CUBE_NUM; ++i) total += counts[i];
+  if (bytes != (long)VL_CUBE_NUM * 4 + total * 16) { snprintf(c->err, sizeof c->err, "map blob size mismatch"); return VLOAM_E_INVALID; }
+  DBuf<float4>& pool = which ? c->poolS : c->poolC;
+  // fresh layout: every cube gets 25 % head room (at least 256 points)
+  MapCubeTable h;
+  memset(&h, 0, sizeof h);
+  long long top = 0;
+  for (int i = 0; i < VL_CUBE_NUM; ++i) {
+    if (counts[i] == 0) continue;
+    h.start[i] = (int)top; h.count[i] = counts[i]; h.cap[i] = counts[i] + counts[i] / 4 + 256;
+    top += h.cap[i];
+  }
+  if (top > (long long)pool.cap) { snprintf(c->err, sizeof c->err, "map pool too small for import (%lld points)", top); return VLOAM_E_CAPACITY; }
+  VL_CUDA(cudaStreamSynchronize(c->stream));
+  const char* p = (const char*)data + (size_t)VL_CUBE_NUM * 4;
+  for (int i = 0; i < VL_CUBE_NUM; ++i) {
+    if (counts[i] == 0) continue;
+    VL_CUDA(cudaMemcpy(pool.p + h.start[i], p, (size_t)counts[i] * 16, cudaMemcpyHostToDevice));
+    p += (size_t)counts[i] * 16;
+  }
+  MapCubeTable* dt = which ? c->cubeS : c->cubeC;
+  VL_CUDA(cudaMemcpy(dt, &h, sizeof h, cudaMemcpyHostToDevice));
+  LmScalars hs;
+  VL_CUDA(cudaMemcpy(&hs, c->lmm, sizeof hs, cudaMemcpyDeviceToHost));
+  if (which) hs.poolTopS = (int)top; else hs.poolTopC = (int)top;
+  VL_CUDA(cudaMemcpy(c->lmm, &hs, sizeof hs, cudaMemcpyHostToDevice));
+  VL_LAUNCH(lm_scan_sorted, VL_CUBE_NUM, 256, 0, c->lmm, c->prm, dt, pool.p, which);
+  VL_CUDA(cudaStreamSynchronize(c->stream));
+  if (which) d->hMapUpperS = total; else d->hMapUpperC = total;
+  return VLOAM_OK;
+}

@@ -1,0 +1,632 @@
+// scan_registration.cu -- ScanRegistration::input (scan_registration.cpp:144-513) as CUDA.
+//
+// Data flow per sweep (all on c->stream, no host round trip inside):
+//   sr_find_bounds   first / last point surviving the NaN + range filter -> startOri / endOri
+//   sr_classify      per point: filter, ring id, -atan2f, first-half trigger, per-block ring histogram
+//   sr_ring_scan     per-ring exclusive scan over blocks (+ ring starts, last-block-done)
+//   sr_scatter       stable ring-major scatter + relTime / intensity (halfPassed == index > trigger)
+//   sr_curvature     11-tap literal left fold
+//   sr_pick          one CTA per ring: 6 sector sorts + greedy sharp / less-sharp / flat walks
+//   sr_ring_voxel    one CTA per ring: select label<=0, pcl::VoxelGrid(0.2) restated
+//   sr_offsets       prefix sums of the per-(ring,sector) pick counts and per-ring DS counts
+//   sr_gather        compaction into the four feature clouds in the reference's push order
+//
+// Parity notes: every f32 expression is evaluated with explicitly rounded ops in the
+// reference's order (the TU is also built with -fmad=false); atanf / atan2f are the
+// fdlibm routines of exact_math.h, bit-identical to glibc 2.39.
+#include <limits.h>
+#include <math_constants.h>
+#include "common.cuh"
+#include "exact_math.h"
+
+#define SR_BLOCK 256
+#define SR_SECT_CAP 1024   // sector keys sorted in shared memory up to this size
+#define SR_RING_CAP 8192   // picked flags kept in shared memory up to this ring length
+#define SR_VOX_CAP 4096    // ring voxel keys sorted in shared memory up to this size
+#define VL_PI 3.14159265358979323846
+
+__device__ __forceinline__ void sr_load(const float* in, int i, int stride, bool vec4, float& x, float& y, float& z) {
+  if (vec4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
+    x = v.x; y = v.y; z = v.z;
+  } else {
+    const float* p = in + (size_t)i * stride;
+    x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
+  }
+}
+
+// pcl::removeNaNFromPointCloud + removeClosedPointCloud (SR.cpp:107-141, 174-176)
+__device__ __forceinline__ bool sr_valid1(float x, float y, float z, float thres2) {
+  if (!isfinite(x) || !isfinite(y) || !isfinite(z)) return false;
+  const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+  return !(d2 < thres2);
+}
+
+// Ring id (SR.cpp:217-259) with the C++ promotion rules spelled out; -1 = rejected.
+__device__ __forceinline__ int sr_ring_of(float x, float y, float z, int nscans) {
+  const float h = __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)));
+  const float a180 = __fmul_rn(vlx::atanf_exact(__fdiv_rn(z, h)), 180.0f);
+  const float angle = (float)__ddiv_rn((double)a180, VL_PI);
+  int scanID;
+  if (nscans == 16) {
+    const float t = __fdiv_rn(__fadd_rn(angle, 15.0f), 2.0f);
+    scanID = (int)__dadd_rn((double)t, 0.5);
+    if (scanID > 15 || scanID < 0) return -1;
+  } else if (nscans == 32) {
+    const double t = __ddiv_rn(__dmul_rn(__dadd_rn((double)angle, 92.0 / 3.0), 3.0), 4.0);
+    scanID = (int)t;
+    if (scanID > 31 || scanID < 0) return -1;
+  } else if (nscans == 64) {
+    if ((double)angle >= -8.83) scanID = (int)__dadd_rn(__dmul_rn((double)__fsub_rn(2.0f, angle), 3.0), 0.5);
+    else scanID = 32 + (int)__dadd_rn(__dmul_rn(__dsub_rn(-8.83, (double)angle), 2.0), 0.5);
+    if (angle > 2.0f || (double)angle < -24.33 || scanID > 50 || scanID < 0) return -1;
+  } else {  // 128-beam builder extension (oracle_stages.cpp)
+    const double v = __dadd_rn(__ddiv_rn(__dadd_rn((double)angle, 22.5), 45.0 / 127.0), 0.5);
+    scanID = (int)v;
+    if (v < 0.0 || scanID > 127) return -1;
+  }
+  return scanID;
+}
+
+__device__ __forceinline__ float sr_ori_first(float ori, float startOri) {  // SR.cpp:267-274
+  if ((double)ori < __dsub_rn((double)startOri, VL_PI / 2)) ori = (float)__dadd_rn((double)ori, 2 * VL_PI);
+  else if ((double)ori > __dadd_rn((double)startOri, VL_PI * 3 / 2)) ori = (float)__dsub_rn((double)ori, 2 * VL_PI);
+  return ori;
+}
+
+__global__ void __launch_bounds__(1024) sr_find_bounds(const float* __restrict__ in, int n, int stride, int vec4, float thres2,
+                                                       SrScalars* __restrict__ s) {
+  __shared__ int found;
+  int first = -1, last = -1;
+  for (int base = 0; base < n; base += blockDim.x) {
+    if (threadIdx.x == 0) found = INT_MAX;
+    __syncthreads();
+    const int i = base + threadIdx.x;
+    if (i < n) { float x, y, z; sr_load(in, i, stride, vec4, x, y, z); if (sr_valid1(x, y, z, thres2)) atomicMin(&found, i); }
+    __syncthreads();
+    const int f = found;
+    __syncthreads();
+    if (f != INT_MAX) { first = f; break; }
+  }
+  for (int top = n; top > 0; top -= blockDim.x) {
+    if (threadIdx.x == 0) found = -1;
+    __syncthreads();
+    const int i = top - 1 - (int)threadIdx.x;
+    if (i >= 0) { float x, y, z; sr_load(in, i, stride, vec4, x, y, z); if (sr_valid1(x, y, z, thres2)) atomicMax(&found, i); }
+    __syncthreads();
+    const int f = found;
+    __syncthreads();
+    if (f >= 0) { last = f; break; }
+  }
+  if (threadIdx.x == 0) {
+    s->firstValid = first; s->lastValid = last; s->trigger = INT_MAX; s->blocksDone = 0;
+    s->count = 0; s->nSharp = s->nLessSharp = s->nFlat = s->nLessFlat = 0;
+    float so = 0.f, eo = 0.f;
+    if (first >= 0) {
+      float x, y, z;
+      sr_load(in, first, stride, vec4, x, y, z);
+      so = -vlx::atan2f_exact(y, x);                                       // SR.cpp:185
+      sr_load(in, last, stride, vec4, x, y, z);
+      eo = (float)__dadd_rn((double)(-vlx::atan2f_exact(y, x)), 2 * VL_PI);  // SR.cpp:187
+      if ((double)__fsub_rn(eo, so) > 3 * VL_PI) eo = (float)__dsub_rn((double)eo, 2 * VL_PI);
+      else if ((double)__fsub_rn(eo, so) < VL_PI) eo = (float)__dadd_rn((double)eo, 2 * VL_PI);
+    }
+    s->startOri = so; s->endOri = eo;
+  }
+}
+
+__global__ void __launch_bounds__(SR_BLOCK) sr_classify(const float* __restrict__ in, int n, int stride, int vec4, float thres2,
+                                                        int nscans, SrScalars* __restrict__ s, int* __restrict__ ring,
+                                                        float* __restrict__ oriOut, int* __restrict__ blockHist, int numBlocks) {
+  __shared__ int hist[VL_MAX_RINGS];
+  for (int t = threadIdx.x; t < VL_MAX_RINGS; t += blockDim.x) hist[t] = 0;
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int r = -1; float ori = 0.f; bool trig = false;
+  if (i < n) {
+    float x, y, z; sr_load(in, i, stride, vec4, x, y, z);
+    if (sr_valid1(x, y, z, thres2)) {
+      r = sr_ring_of(x, y, z, nscans);
+      if (r >= 0) {
+        ori = -vlx::atan2f_exact(y, x);  // SR.cpp:263
+        const float so = s->startOri;
+        const float o1 = sr_ori_first(ori, so);
+        trig = (double)__fsub_rn(o1, so) > VL_PI;  // SR.cpp:276
+        atomicAdd(&hist[r], 1);
+      }
+    }
+    ring[i] = r; oriOut[i] = ori;
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, trig);
+  if (b && (threadIdx.x & 31) == __ffs(b) - 1) atomicMin(&s->trigger, i);
+  __syncthreads();
+  for (int t = threadIdx.x; t < nscans; t += blockDim.x) blockHist[(size_t)t * numBlocks + blockIdx.x] = hist[t];
+}
+
+// One warp per ring: exclusive scan of that ring's per-block counts.  The last CTA
+// to finish turns the ring totals into ring starts (SR.cpp:308-315).
+__global__ void __launch_bounds__(256) sr_ring_scan(int* __restrict__ blockHist, int numBlocks, int nscans, int* __restrict__ ringCount,
+                                                    int* __restrict__ ringStart, SrScalars* __restrict__ s) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + warp;
+  if (r < nscans) {
+    int* h = blockHist + (size_t)r * numBlocks;
+    int carry = 0;
+    for (int base = 0; base < numBlocks; base += 32) {
+      const int b = base + lane;
+      const int v = b < numBlocks ? h[b] : 0;
+      int inc = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+      if (b < numBlocks) h[b] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) ringCount[r] = carry;
+  }
+  __shared__ int isLast;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) isLast = (atomicAdd(&s->blocksDone, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (isLast && warp == 0) {
+    __threadfence();
+    int carry = 0;
+    for (int base = 0; base < nscans; base += 32) {
+      const int rr = base + lane;
+      const int v = rr < nscans ? ((volatile int*)ringCount)[rr] : 0;
+      int inc = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+      if (rr < nscans) ringStart[rr] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) { ringStart[nscans] = carry; s->count = carry; }
+  }
+}
+
+__global__ void __launch_bounds__(SR_BLOCK) sr_scatter(const float* __restrict__ in, int n, int stride, int vec4, int nscans,
+                                                       const SrScalars* __restrict__ s, const int* __restrict__ ring,
+                                                       const float* __restrict__ oriIn, const int* __restrict__ blockOff, int numBlocks,
+                                                       const int* __restrict__ ringStart, float4* __restrict__ cloud) {
+  __shared__ int warpCnt[SR_BLOCK / 32][VL_MAX_RINGS];
+  for (int t = threadIdx.x; t < (SR_BLOCK / 32) * VL_MAX_RINGS; t += blockDim.x) (&warpCnt[0][0])[t] = 0;
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = i < n ? ring[i] : -1;
+  const int key = r >= 0 ? r : (-1 - lane);  // rejected lanes never match anyone
+  const unsigned m = __match_any_sync(0xffffffffu, key);
+  const int rankInWarp = __popc(m & ((1u << lane) - 1u));
+  if (r >= 0 && rankInWarp == 0) warpCnt[warp][r] = __popc(m);
+  __syncthreads();
+  if (r < 0) return;
+  int before = 0;
+  for (int w = 0; w < warp; ++w) before += warpCnt[w][r];
+  const int dst = ringStart[r] + blockOff[(size_t)r * numBlocks + blockIdx.x] + before + rankInWarp;
+  float x, y, z; sr_load(in, i, stride, vec4, x, y, z);
+  const float so = s->startOri, eo = s->endOri;
+  float ori = oriIn[i];
+  if (i <= s->trigger) {  // halfPassed still false when this point is processed (SR.cpp:265-280)
+    ori = sr_ori_first(ori, so);
+  } else {                // SR.cpp:281-292
+    ori = (float)__dadd_rn((double)ori, 2 * VL_PI);
+    if ((double)ori < __dsub_rn((double)eo, VL_PI * 3 / 2)) ori = (float)__dadd_rn((double)ori, 2 * VL_PI);
+    else if ((double)ori > __dadd_rn((double)eo, VL_PI / 2)) ori = (float)__dsub_rn((double)ori, 2 * VL_PI);
+  }
+  const float relTime = __fdiv_rn(__fsub_rn(ori, so), __fsub_rn(eo, so));       // SR.cpp:294
+  const float inten = (float)__dadd_rn((double)r, __dmul_rn(0.1, (double)relTime));  // SR.cpp:296
+  cloud[dst] = make_float4(x, y, z, inten);
+}
+
+__global__ void __launch_bounds__(SR_BLOCK) sr_curvature(const float4* __restrict__ cloud, const SrScalars* __restrict__ s,
+                                                         float* __restrict__ curv, int* __restrict__ label,
+                                                         unsigned char* __restrict__ picked) {
+  __shared__ float4 tile[SR_BLOCK + 10];
+  const int count = s->count;
+  const int base = blockIdx.x * blockDim.x;
+  if (base >= count) return;
+  for (int t = threadIdx.x; t < SR_BLOCK + 10; t += blockDim.x) {
+    const int g = base - 5 + t;
+    tile[t] = (g >= 0 && g < count) ? cloud[g] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  const int i = base + threadIdx.x;
+  if (i >= count) return;
+  float cv = 0.f;
+  if (i >= 5 && i < count - 5) {  // SR.cpp:323-339, strict left fold
+    const float4* p = &tile[threadIdx.x + 5];
+#define SR_FOLD(f)                                                                                         \
+  __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(     \
+      p[-5].f, p[-4].f), p[-3].f), p[-2].f), p[-1].f), __fmul_rn(10.0f, p[0].f)), p[1].f), p[2].f), p[3].f), p[4].f), p[5].f)
+    const float dx = SR_FOLD(x), dy = SR_FOLD(y), dz = SR_FOLD(z);
+#undef SR_FOLD
+    cv = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+  }
+  curv[i] = cv; label[i] = 0; picked[i] = 0;
+}
+
+__device__ __forceinline__ float sr_gap2(const float4* __restrict__ cloud, int a, int b) {  // SR.cpp:408-411
+  const float4 p = cloud[a], q = cloud[b];
+  const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// Mark ind and its +-5 neighbours until a gap > 0.05 (SR.cpp:403-429); warp-cooperative.
+__device__ __forceinline__ void sr_mark(const float4* __restrict__ cloud, unsigned char* pk, int ringBase, int ind, int lane) {
+  bool brk = false;
+  if (lane < 5) { const int l = lane + 1; brk = (double)sr_gap2(cloud, ind + l, ind + l - 1) > 0.05; }
+  else if (lane < 10) { const int l = -(lane - 4); brk = (double)sr_gap2(cloud, ind + l, ind + l + 1) > 0.05; }
+  const unsigned bb = __ballot_sync(0xffffffffu, brk);
+  const unsigned f = bb & 31u, w = (bb >> 5) & 31u;
+  const int nf = f ? __ffs(f) - 1 : 5, nb = w ? __ffs(w) - 1 : 5;
+  if (lane == 0) pk[ind - ringBase] = 1;
+  if (lane < nf) pk[ind + lane + 1 - ringBase] = 1;
+  if (lane >= 5 && lane - 5 < nb) pk[ind - (lane - 4) - ringBase] = 1;
+  __syncwarp();
+}
+
+__device__ __forceinline__ int sr_sp(int start, int end, int j) { return start + (end - start) * j / 6; }          // SR.cpp:360
+__device__ __forceinline__ int sr_ep(int start, int end, int j) { return start + (end - start) * (j + 1) / 6 - 1; }  // SR.cpp:361
+
+// One CTA per ring.  All six sectors are sorted together (batched bitonic on
+// (curvature bits, index) keys -- the canonical tie order of SURVEY Appendix B), then
+// warp 0 walks the sectors in order because +-5 marks spill into the next sector.
+__global__ void __launch_bounds__(SR_BLOCK) sr_pick(const float4* __restrict__ cloud, const float* __restrict__ curv,
+                                                    int* __restrict__ label, unsigned char* __restrict__ pickedG,
+                                                    unsigned long long* __restrict__ scratch, const int* __restrict__ ringStart,
+                                                    const int* __restrict__ ringCount, int* __restrict__ provSharp,
+                                                    int* __restrict__ provLess, int* __restrict__ provFlat, int* __restrict__ cntSharp,
+                                                    int* __restrict__ cntLess, int* __restrict__ cntFlat) {
+  extern __shared__ unsigned long long smem[];
+  const int r = blockIdx.x;
+  const int rs = ringStart[r], rc = ringCount[r];
+  const int start = rs + 5, end = rs + rc - 6;  // scanStartInd / scanEndInd (SR.cpp:310-314)
+  if (threadIdx.x < VL_SECTORS) { cntSharp[r * VL_SECTORS + threadIdx.x] = 0; cntLess[r * VL_SECTORS + threadIdx.x] = 0; cntFlat[r * VL_SECTORS + threadIdx.x] = 0; }
+  if (end - start < 6) return;  // SR.cpp:355-356
+  int maxLen = 0;
+#pragma unroll
+  for (int j = 0; j < VL_SECTORS; ++j) maxLen = max(maxLen, sr_ep(start, end, j) - sr_sp(start, end, j) + 1);
+  int P = 32; while (P < maxLen) P <<= 1;
+  const bool inSmem = P <= SR_SECT_CAP;
+  // sector j keys live at keys + j*P; the global fallback uses 2*count entries per ring (6P <= 12*len/6*... bounded by 2*rc+384)
+  unsigned long long* keys = inSmem ? smem : scratch + (size_t)2 * rs + (size_t)r * 6 * 64;
+  unsigned char* pk = (rc <= SR_RING_CAP) ? reinterpret_cast<unsigned char*>(smem + VL_SECTORS * SR_SECT_CAP) : pickedG + rs;
+  if (rc <= SR_RING_CAP) for (int t = threadIdx.x; t < rc; t += blockDim.x) pk[t] = 0;
+  for (int t = threadIdx.x; t < VL_SECTORS * P; t += blockDim.x) {
+    const int j = t / P, k = t - j * P;
+    const int idx = sr_sp(start, end, j) + k;
+    const int last = sr_ep(start, end, j);
+    keys[t] = (idx <= last) ? (((unsigned long long)__float_as_uint(curv[idx]) << 32) | (unsigned)idx) : ~0ull;
+  }
+  __syncthreads();
+  const int halfP = P >> 1;
+  for (int k = 2; k <= P; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < VL_SECTORS * halfP; t += blockDim.x) {
+        const int sct = t / halfP, u = t - sct * halfP;
+        const int i = ((u & ~(j - 1)) << 1) | (u & (j - 1));
+        const int l = i | j;
+        unsigned long long* ks = keys + sct * P;
+        const unsigned long long a = ks[i], b = ks[l];
+        const bool up = (i & k) == 0;
+        if ((a > b) == up) { ks[i] = b; ks[l] = a; }
+      }
+      __syncthreads();
+    }
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  for (int j = 0; j < VL_SECTORS; ++j) {
+    const int spj = sr_sp(start, end, j), epj = sr_ep(start, end, j);
+    const int m = epj - spj + 1;
+    const unsigned long long* ks = keys + j * P;
+    const int slot = r * VL_SECTORS + j;
+    // ---- descending walk: sharp (<=2) then less sharp (<=20 total), SR.cpp:371-431
+    int cnt = 0, pos = m - 1;
+    while (pos >= 0 && cnt < 20) {
+      const int k = pos - lane;
+      const bool valid = k >= 0;
+      const unsigned long long key = valid ? ks[k] : 0ull;
+      const int ind = (int)(unsigned)(key & 0xffffffffull);
+      const bool big = valid && (double)__uint_as_float((unsigned)(key >> 32)) > 0.1;
+      const bool cand = big && pk[ind - rs] == 0;
+      const unsigned bc = __ballot_sync(0xffffffffu, cand);
+      if (bc == 0) {
+        const unsigned bv = __ballot_sync(0xffffffffu, valid), bb = __ballot_sync(0xffffffffu, big);
+        if (bb != bv) break;  // reached curvature <= 0.1: nothing further can qualify
+        pos -= 32;
+        continue;
+      }
+      const int first = __ffs(bc) - 1;
+      const int pind = __shfl_sync(0xffffffffu, ind, first);
+      cnt++;
+      if (lane == 0) {
+        if (cnt <= 2) { label[pind] = 2; provSharp[slot * 2 + cnt - 1] = pind; }
+        else label[pind] = 1;
+        provLess[slot * 20 + cnt - 1] = pind;
+      }
+      sr_mark(cloud, pk, rs, pind, lane);
+      pos = pos - first - 1;
+    }
+    if (lane == 0) { cntSharp[slot] = min(cnt, 2); cntLess[slot] = cnt; }
+    // ---- ascending walk: flat (<=4; the 4th is not marked), SR.cpp:439-483
+    cnt = 0; pos = 0;
+    while (pos < m && cnt < 4) {
+      const int k = pos + lane;
+      const bool valid = k < m;
+      const unsigned long long key = valid ? ks[k] : 0ull;
+      const int ind = (int)(unsigned)(key & 0xffffffffull);
+      const bool small = valid && (double)__uint_as_float((unsigned)(key >> 32)) < 0.1;
+      const bool cand = small && pk[ind - rs] == 0;
+      const unsigned bc = __ballot_sync(0xffffffffu, cand);
+      if (bc == 0) {
+        const unsigned bv = __ballot_sync(0xffffffffu, valid), bs = __ballot_sync(0xffffffffu, small);
+        if (bs != bv) break;
+        pos += 32;
+        continue;
+      }
+      const int first = __ffs(bc) - 1;
+      const int pind = __shfl_sync(0xffffffffu, ind, first);
+      cnt++;
+      if (lane == 0) { label[pind] = -1; provFlat[slot * 4 + cnt - 1] = pind; }
+      if (cnt >= 4) break;
+      sr_mark(cloud, pk, rs, pind, lane);
+      pos = pos + first + 1;
+    }
+    if (lane == 0) cntFlat[slot] = cnt;
+    __syncwarp();
+  }
+}
+
+// ---- per-ring pcl::VoxelGrid(0.2) of the label<=0 points (SR.cpp:486-503) -------------
+struct VoxBox { int minb[3], mul1, mul2, guard; float inv; };
+
+__device__ __forceinline__ unsigned vox_idx(const float4 p, const VoxBox& b) {
+  const int i0 = (int)__fsub_rn(floorf(__fmul_rn(p.x, b.inv)), (float)b.minb[0]);
+  const int i1 = (int)__fsub_rn(floorf(__fmul_rn(p.y, b.inv)), (float)b.minb[1]);
+  const int i2 = (int)__fsub_rn(floorf(__fmul_rn(p.z, b.inv)), (float)b.minb[2]);
+  return (unsigned)(i0 + i1 * b.mul1 + i2 * b.mul2);
+}
+
+__device__ __forceinline__ void vox_make_box(const float mn[3], const float mx[3], float leaf, VoxBox* b) {
+  const float inv = __fdiv_rn(1.0f, leaf);
+  b->inv = inv;
+  const long long dx = (long long)__fmul_rn(__fsub_rn(mx[0], mn[0]), inv) + 1;
+  const long long dy = (long long)__fmul_rn(__fsub_rn(mx[1], mn[1]), inv) + 1;
+  const long long dz = (long long)__fmul_rn(__fsub_rn(mx[2], mn[2]), inv) + 1;
+  b->guard = (dx * dy * dz > (long long)INT_MAX) ? 1 : 0;
+  int maxb[3];
+  for (int a = 0; a < 3; ++a) {
+    b->minb[a] = (int)floorf(__fmul_rn(mn[a], inv));
+    maxb[a] = (int)floorf(__fmul_rn(mx[a], inv));
+  }
+  const int d0 = maxb[0] - b->minb[0] + 1, d1 = maxb[1] - b->minb[1] + 1;
+  b->mul1 = d0; b->mul2 = d0 * d1;
+}
+
+__global__ void __launch_bounds__(SR_BLOCK) sr_ring_voxel(const float4* __restrict__ cloud, const int* __restrict__ label,
+                                                          const int* __restrict__ ringStart, const int* __restrict__ ringCount,
+                                                          int* __restrict__ sel, unsigned long long* __restrict__ scratch,
+                                                          float4* __restrict__ outProv, int* __restrict__ dsCount, float leaf) {
+  __shared__ unsigned long long skeys[SR_VOX_CAP];
+  __shared__ int warpSum[SR_BLOCK / 32];
+  __shared__ float red[6][SR_BLOCK / 32];
+  __shared__ VoxBox box;
+  __shared__ int sTotal;
+  const int r = blockIdx.x;
+  const int rs = ringStart[r], rc = ringCount[r];
+  const int start = rs + 5, end = rs + rc - 6;
+  if (end - start < 6) { if (threadIdx.x == 0) dsCount[r] = 0; return; }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int* mySel = sel + rs;
+  // 1. ordered selection + bounding box
+  float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+  int total = 0;
+  for (int base = start; base < end; base += SR_BLOCK) {
+    const int k = base + threadIdx.x;
+    const bool f = k < end && label[k] <= 0;
+    const unsigned b = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) warpSum[warp] = __popc(b);
+    __syncthreads();
+    int before = 0, all = 0;
+    for (int w = 0; w < SR_BLOCK / 32; ++w) { const int v = warpSum[w]; if (w < warp) before += v; all += v; }
+    if (f) {
+      mySel[total + before + __popc(b & ((1u << lane) - 1u))] = k;
+      const float4 p = cloud[k];
+      mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
+      mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
+      mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+    }
+    total += all;
+    __syncthreads();
+  }
+  const int m = total;
+  if (m == 0) { if (threadIdx.x == 0) dsCount[r] = 0; return; }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float lo = mn[a], hi = mx[a];
+    for (int d = 16; d > 0; d >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, d)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, d)); }
+    if (lane == 0) { red[a][warp] = lo; red[3 + a][warp] = hi; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = red[a][0]; hi[a] = red[3 + a][0];
+      for (int w = 1; w < SR_BLOCK / 32; ++w) { lo[a] = fminf(lo[a], red[a][w]); hi[a] = fmaxf(hi[a], red[3 + a][w]); }
+    }
+    vox_make_box(lo, hi, leaf, &box);
+  }
+  __syncthreads();
+  float4* out = outProv + rs;
+  if (box.guard) {  // leaf too small for the extent: pcl returns the input unchanged
+    for (int t = threadIdx.x; t < m; t += SR_BLOCK) out[t] = cloud[mySel[t]];
+    if (threadIdx.x == 0) dsCount[r] = m;
+    return;
+  }
+  // 2. (voxel idx, local index) keys, bitonic sort
+  int P = 32; while (P < m) P <<= 1;
+  unsigned long long* keys = (P <= SR_VOX_CAP) ? skeys : scratch + (size_t)2 * rs + (size_t)r * 6 * 64;
+  for (int t = threadIdx.x; t < P; t += SR_BLOCK)
+    keys[t] = t < m ? (((unsigned long long)vox_idx(cloud[mySel[t]], box) << 32) | (unsigned)t) : ~0ull;
+  __syncthreads();
+  const int halfP = P >> 1;
+  for (int k = 2; k <= P; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int u = threadIdx.x; u < halfP; u += SR_BLOCK) {
+        const int i = ((u & ~(j - 1)) << 1) | (u & (j - 1));
+        const int l = i | j;
+        const unsigned long long a = keys[i], b = keys[l];
+        const bool up = (i & k) == 0;
+        if ((a > b) == up) { keys[i] = b; keys[l] = a; }
+      }
+      __syncthreads();
+    }
+  // 3. run heads -> ordered output slots; the head thread folds its run in f32, in index order
+  total = 0;
+  for (int base = 0; base < m; base += SR_BLOCK) {
+    const int t = base + threadIdx.x;
+    const bool head = t < m && (t == 0 || (unsigned)(keys[t] >> 32) != (unsigned)(keys[t - 1] >> 32));
+    const unsigned b = __ballot_sync(0xffffffffu, head);
+    if (lane == 0) warpSum[warp] = __popc(b);
+    __syncthreads();
+    int before = 0, all = 0;
+    for (int w = 0; w < SR_BLOCK / 32; ++w) { const int v = warpSum[w]; if (w < warp) before += v; all += v; }
+    if (head) {
+      const unsigned vox = (unsigned)(keys[t] >> 32);
+      float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f; int nrun = 0;
+      for (int q = t; q < m && (unsigned)(keys[q] >> 32) == vox; ++q) {
+        const float4 p = cloud[mySel[(int)(unsigned)(keys[q] & 0xffffffffull)]];
+        sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
+        ++nrun;
+      }
+      const float fn = (float)nrun;
+      out[total + before + __popc(b & ((1u << lane) - 1u))] =
+          make_float4(__fdiv_rn(sx, fn), __fdiv_rn(sy, fn), __fdiv_rn(sz, fn), __fdiv_rn(si, fn));
+    }
+    total += all;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) dsCount[r] = total;
+}
+
+// Exclusive scans of the pick counts (ring-major, sector, pick order = the reference's
+// push_back order) and of the per-ring DS counts.
+__global__ void __launch_bounds__(1024) sr_offsets(int nscans, const int* __restrict__ cntSharp, const int* __restrict__ cntLess,
+                                                   const int* __restrict__ cntFlat, const int* __restrict__ dsCount,
+                                                   int* __restrict__ offSharp, int* __restrict__ offLess, int* __restrict__ offFlat,
+                                                   int* __restrict__ dsOff, SrScalars* __restrict__ s) {
+  __shared__ int buf[4][1024];
+  const int t = threadIdx.x;
+  const int nslots = nscans * VL_SECTORS;
+  buf[0][t] = t < nslots ? cntSharp[t] : 0;
+  buf[1][t] = t < nslots ? cntLess[t] : 0;
+  buf[2][t] = t < nslots ? cntFlat[t] : 0;
+  buf[3][t] = t < nscans ? dsCount[t] : 0;
+  int own[4] = {buf[0][t], buf[1][t], buf[2][t], buf[3][t]};
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
+    int v[4];
+    for (int a = 0; a < 4; ++a) v[a] = t >= d ? buf[a][t - d] : 0;
+    __syncthreads();
+    for (int a = 0; a < 4; ++a) buf[a][t] += v[a];
+    __syncthreads();
+  }
+  if (t < nslots) { offSharp[t] = buf[0][t] - own[0]; offLess[t] = buf[1][t] - own[1]; offFlat[t] = buf[2][t] - own[2]; }
+  if (t < nscans) dsOff[t] = buf[3][t] - own[3];
+  if (t == 1023) { s->nSharp = buf[0][t]; s->nLessSharp = buf[1][t]; s->nFlat = buf[2][t]; s->nLessFlat = buf[3][t]; }
+}
+
+__global__ void __launch_bounds__(SR_BLOCK) sr_gather(const float4* __restrict__ cloud, int nscans, const SrScalars* __restrict__ s,
+                                                      const int* __restrict__ provSharp, const int* __restrict__ provLess,
+                                                      const int* __restrict__ provFlat, const int* __restrict__ cntSharp,
+                                                      const int* __restrict__ cntLess, const int* __restrict__ cntFlat,
+                                                      const int* __restrict__ offSharp, const int* __restrict__ offLess,
+                                                      const int* __restrict__ offFlat, const int* __restrict__ ringStart,
+                                                      const int* __restrict__ dsCount, const int* __restrict__ dsOff,
+                                                      const float4* __restrict__ lessFlatProv, float4* __restrict__ sharp,
+                                                      float4* __restrict__ lessSharp, float4* __restrict__ flat, float4* __restrict__ lessFlat) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nslots = nscans * VL_SECTORS;
+  if (t < nslots * 2) { const int sl = t / 2, k = t - sl * 2; if (k < cntSharp[sl]) sharp[offSharp[sl] + k] = cloud[provSharp[t]]; return; }
+  t -= nslots * 2;
+  if (t < nslots * 20) { const int sl = t / 20, k = t - sl * 20; if (k < cntLess[sl]) lessSharp[offLess[sl] + k] = cloud[provLess[t]]; return; }
+  t -= nslots * 20;
+  if (t < nslots * 4) { const int sl = t / 4, k = t - sl * 4; if (k < cntFlat[sl]) flat[offFlat[sl] + k] = cloud[provFlat[t]]; return; }
+  t -= nslots * 4;
+  if (t >= s->count) return;
+  int lo = 0, hi = nscans;  // ring of position t: largest r with ringStart[r] <= t
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ringStart[mid] <= t) lo = mid; else hi = mid; }
+  const int k = t - ringStart[lo];
+  if (k < dsCount[lo]) lessFlat[dsOff[lo] + k] = lessFlatProv[t];
+}
+
+// ---------------------------------------------------------------------------------
+int vl_sr_run(vloam_b200_ctx* c, const float* d_xyz, int n, int stride) {
+  const int R = c->prm.n_scans;
+  c->sr_counts_valid = false;
+  c->n_in = n; c->stride = stride;
+  c->cur ^= 1;  // this frame's lessSharp / lessFlat go to the buffer the "last" clouds do not occupy
+  if (n <= 0) {
+    VL_CUDA(cudaMemsetAsync(c->srs, 0, sizeof(SrScalars), c->stream));
+    VL_CUDA(cudaMemsetAsync(c->ringCount, 0, sizeof(int) * VL_MAX_RINGS, c->stream));
+    VL_CUDA(cudaMemsetAsync(c->ringStart, 0, sizeof(int) * (VL_MAX_RINGS + 1), c->stream));
+    return VLOAM_OK;
+  }
+  const int numBlocks = vl_div_up(n, SR_BLOCK);
+  VL_TRY(vl_reserve(c, c->ring, n));
+  VL_TRY(vl_reserve(c, c->ori, n));
+  VL_TRY(vl_reserve(c, c->blockHist, (size_t)R * numBlocks));
+  VL_TRY(vl_reserve(c, c->cloud, n));
+  VL_TRY(vl_reserve(c, c->curv, n));
+  VL_TRY(vl_reserve(c, c->label, n));
+  VL_TRY(vl_reserve(c, c->picked, n));
+  VL_TRY(vl_reserve(c, c->sortScratch, (size_t)2 * n + (size_t)VL_MAX_RINGS * 6 * 64 + 64));
+  VL_TRY(vl_reserve(c, c->lessFlatProv, n));
+  VL_TRY(vl_reserve(c, c->selIdx, n));
+  VL_TRY(vl_reserve(c, c->sharp, (size_t)R * VL_SECTORS * 2));
+  VL_TRY(vl_reserve(c, c->flat, (size_t)R * VL_SECTORS * 4));
+  VL_TRY(vl_reserve(c, c->lessSharp[c->cur], (size_t)R * VL_SECTORS * 20));
+  VL_TRY(vl_reserve(c, c->lessFlat[c->cur], n));
+  const int vec4 = (stride == 4 && (reinterpret_cast<uintptr_t>(d_xyz) & 15) == 0) ? 1 : 0;
+  const float thres = c->prm.minimum_range;
+  const float thres2 = thres * thres;
+
+  VL_LAUNCH(sr_find_bounds, 1, 1024, 0, d_xyz, n, stride, vec4, thres2, c->srs);
+  VL_LAUNCH(sr_classify, numBlocks, SR_BLOCK, 0, d_xyz, n, stride, vec4, thres2, R, c->srs, c->ring.p, c->ori.p, c->blockHist.p, numBlocks);
+  VL_LAUNCH(sr_ring_scan, vl_div_up(R, 8), 256, 0, c->blockHist.p, numBlocks, R, c->ringCount, c->ringStart, c->srs);
+  VL_LAUNCH(sr_scatter, numBlocks, SR_BLOCK, 0, d_xyz, n, stride, vec4, R, c->srs, c->ring.p, c->ori.p, c->blockHist.p, numBlocks,
+            c->ringStart, c->cloud.p);
+  VL_LAUNCH(sr_curvature, numBlocks, SR_BLOCK, 0, c->cloud.p, c->srs, c->curv.p, c->label.p, c->picked.p);
+  const size_t pickSmem = (size_t)VL_SECTORS * SR_SECT_CAP * sizeof(unsigned long long) + SR_RING_CAP;
+  static bool attrSet = false;
+  if (!attrSet) {
+    VL_CUDA(cudaFuncSetAttribute(sr_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pickSmem));
+    attrSet = true;
+  }
+  VL_LAUNCH(sr_pick, R, SR_BLOCK, pickSmem, c->cloud.p, c->curv.p, c->label.p, c->picked.p, c->sortScratch.p, c->ringStart, c->ringCount,
+            c->provSharp, c->provLess, c->provFlat, c->cntSharp, c->cntLess, c->cntFlat);
+  VL_LAUNCH(sr_ring_voxel, R, SR_BLOCK, 0, c->cloud.p, c->label.p, c->ringStart, c->ringCount, c->selIdx.p, c->sortScratch.p,
+            c->lessFlatProv.p, c->ringDsCount, 0.2f);
+  VL_LAUNCH(sr_offsets, 1, 1024, 0, R, c->cntSharp, c->cntLess, c->cntFlat, c->ringDsCount, c->offSharp, c->offLess, c->offFlat,
+            c->ringDsOff, c->srs);
+  const int gatherThreads = R * VL_SECTORS * 26 + n;
+  VL_LAUNCH(sr_gather, vl_div_up(gatherThreads, SR_BLOCK), SR_BLOCK, 0, c->cloud.p, R, c->srs, c->provSharp, c->provLess, c->provFlat,
+            c->cntSharp, c->cntLess, c->cntFlat, c->offSharp, c->offLess, c->offFlat, c->ringStart, c->ringDsCount, c->ringDsOff,
+            c->lessFlatProv.p, c->sharp.p, c->lessSharp[c->cur].p, c->flat.p, c->lessFlat[c->cur].p);
+  VL_CUDA(cudaMemcpyAsync(c->h_srs, c->srs, sizeof(SrScalars), cudaMemcpyDeviceToHost, c->stream));
+  VL_CUDA(cudaGetLastError());
+  return VLOAM_OK;
+}
+
+// Sync point S1: the host learns the feature counts (needed to size the LO / LM launches).
+int vl_sr_sync_counts(vloam_b200_ctx* c) {
+  if (c->sr_counts_valid) return VLOAM_OK;
+  VL_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->n_in <= 0) { c->nKept = c->nSharp = c->nLessSharp = c->nFlat = c->nLessFlat = 0; }
+  else {
+    c->nKept = c->h_srs->count; c->nSharp = c->h_srs->nSharp; c->nLessSharp = c->h_srs->nLessSharp;
+    c->nFlat = c->h_srs->nFlat; c->nLessFlat = c->h_srs->nLessFlat;
+  }
+  c->sr_counts_valid = true;
+  return VLOAM_OK;
+}

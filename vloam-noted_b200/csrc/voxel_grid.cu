@@ -1,0 +1,253 @@
+// voxel_grid.cu -- device-wide sort and pcl::VoxelGrid<PointXYZI> restated as CUDA.
+//
+// pcl::VoxelGrid (used at scan_registration.cpp:497-501, laser_mapping.cpp:492-500,
+// 795-808) is: bounding box -> linear voxel index per point -> sort (index, point)
+// pairs -> one f32 centroid per run, output in ascending voxel index.  The canonical
+// refinement of PCL's unstable sort is ascending point index
+// inside a voxel, so keys are (voxel idx << 32 | point index) and any correct sort
+// of those unique 64-bit keys reproduces the oracle bit for bit.
+//
+// Sort: bitonic network, tiles of 4096 keys sorted / merged in shared memory, the
+// strides above a tile as one global compare-exchange kernel each.  The arrays here
+// are <= a few hundred thousand keys (L2-resident), where this beats a radix sort's
+// fixed pass count and needs no scratch buffer.
+#include <limits.h>
+#include <math_constants.h>
+#include "common.cuh"
+
+#define BT_TILE 4096
+#define BT_THREADS 512
+#define VG_BLOCK 256
+
+__global__ void __launch_bounds__(BT_THREADS) bt_tile_sort(unsigned long long* __restrict__ keys, int tile) {
+  __shared__ unsigned long long s[BT_TILE];
+  const size_t base = (size_t)blockIdx.x * tile;
+  for (int t = threadIdx.x; t < tile; t += BT_THREADS) s[t] = keys[base + t];
+  __syncthreads();
+  const int half = tile >> 1;
+  for (int k = 2; k <= tile; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int u = threadIdx.x; u < half; u += BT_THREADS) {
+        const int i = ((u & ~(j - 1)) << 1) | (u & (j - 1));
+        const int l = i | j;
+        const unsigned long long a = s[i], b = s[l];
+        const bool up = ((base + i) & (size_t)k) == 0;
+        if ((a > b) == up) { s[i] = b; s[l] = a; }
+      }
+      __syncthreads();
+    }
+  for (int t = threadIdx.x; t < tile; t += BT_THREADS) keys[base + t] = s[t];
+}
+
+__global__ void __launch_bounds__(256) bt_global_step(unsigned long long* __restrict__ keys, int halfN, int j, int k) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= halfN) return;
+  const int i = ((u & ~(j - 1)) << 1) | (u & (j - 1));
+  const int l = i | j;
+  const unsigned long long a = keys[i], b = keys[l];
+  const bool up = (i & k) == 0;
+  if ((a > b) == up) { keys[i] = b; keys[l] = a; }
+}
+
+__global__ void __launch_bounds__(BT_THREADS) bt_tile_merge(unsigned long long* __restrict__ keys, int tile, int k) {
+  __shared__ unsigned long long s[BT_TILE];
+  const size_t base = (size_t)blockIdx.x * tile;
+  for (int t = threadIdx.x; t < tile; t += BT_THREADS) s[t] = keys[base + t];
+  __syncthreads();
+  const int half = tile >> 1;
+  const bool up = (base & (size_t)k) == 0;  // k > tile: the whole tile shares one direction
+  for (int j = tile >> 1; j > 0; j >>= 1) {
+    for (int u = threadIdx.x; u < half; u += BT_THREADS) {
+      const int i = ((u & ~(j - 1)) << 1) | (u & (j - 1));
+      const int l = i | j;
+      const unsigned long long a = s[i], b = s[l];
+      if ((a > b) == up) { s[i] = b; s[l] = a; }
+    }
+    __syncthreads();
+  }
+  for (int t = threadIdx.x; t < tile; t += BT_THREADS) keys[base + t] = s[t];
+}
+
+// Ascending sort of n_pow2 unique 64-bit keys in place (n_pow2 a power of two >= 2).
+int vl_sort_u64(vloam_b200_ctx* c, unsigned long long* d_keys, int n_pow2) {
+  if (n_pow2 < 2) return VLOAM_OK;
+  const int tile = n_pow2 < BT_TILE ? n_pow2 : BT_TILE;
+  VL_LAUNCH(bt_tile_sort, n_pow2 / tile, BT_THREADS, 0, d_keys, tile);
+  for (int k = tile << 1; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j >= tile; j >>= 1)
+      VL_LAUNCH(bt_global_step, vl_div_up(n_pow2 / 2, 256), 256, 0, d_keys, n_pow2 / 2, j, k);
+    VL_LAUNCH(bt_tile_merge, n_pow2 / tile, BT_THREADS, 0, d_keys, tile, k);
+  }
+  VL_CUDA(cudaGetLastError());
+  return VLOAM_OK;
+}
+
+// ---- voxel grid over one large cloud ------------------------------------------------
+struct VgBox { int minb[3], mul1, mul2, guard, n; float inv; };
+
+__device__ __forceinline__ unsigned vg_idx(const float4 p, const VgBox& b) {
+  const int i0 = (int)__fsub_rn(floorf(__fmul_rn(p.x, b.inv)), (float)b.minb[0]);
+  const int i1 = (int)__fsub_rn(floorf(__fmul_rn(p.y, b.inv)), (float)b.minb[1]);
+  const int i2 = (int)__fsub_rn(floorf(__fmul_rn(p.z, b.inv)), (float)b.minb[2]);
+  return (unsigned)(i0 + i1 * b.mul1 + i2 * b.mul2);
+}
+
+// getMinMax3D: per-block partial bounds -> partial[block*6 + {minx,miny,minz,maxx,maxy,maxz}]
+__global__ void __launch_bounds__(VG_BLOCK) vg_bbox(const float4* __restrict__ in, int nBound, const int* __restrict__ dN,
+                                                    float* __restrict__ partial) {
+  const int n = dN ? min(*dN, nBound) : nBound;
+  float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = in[i];
+    mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
+    mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
+    mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+  }
+  __shared__ float red[6][VG_BLOCK / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float lo = mn[a], hi = mx[a];
+    for (int d = 16; d > 0; d >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, d)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, d)); }
+    if (lane == 0) { red[a][warp] = lo; red[3 + a][warp] = hi; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    float v = red[threadIdx.x][0];
+    for (int w = 1; w < VG_BLOCK / 32; ++w) v = threadIdx.x < 3 ? fminf(v, red[threadIdx.x][w]) : fmaxf(v, red[threadIdx.x][w]);
+    partial[blockIdx.x * 6 + threadIdx.x] = v;
+  }
+}
+
+__global__ void vg_box(const float* __restrict__ partial, int nPartial, int nBound, const int* __restrict__ dN, float leaf,
+                       VgBox* __restrict__ box, int* __restrict__ dCount) {
+  if (threadIdx.x != 0) return;
+  const int n = dN ? min(*dN, nBound) : nBound;
+  float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+  for (int b = 0; b < nPartial; ++b)
+    for (int a = 0; a < 3; ++a) { mn[a] = fminf(mn[a], partial[b * 6 + a]); mx[a] = fmaxf(mx[a], partial[b * 6 + 3 + a]); }
+  VgBox bx;
+  bx.n = n;
+  const float inv = __fdiv_rn(1.0f, leaf);
+  bx.inv = inv;
+  bx.guard = 0; bx.mul1 = bx.mul2 = 0; bx.minb[0] = bx.minb[1] = bx.minb[2] = 0;
+  if (n > 0) {
+    const long long dx = (long long)__fmul_rn(__fsub_rn(mx[0], mn[0]), inv) + 1;
+    const long long dy = (long long)__fmul_rn(__fsub_rn(mx[1], mn[1]), inv) + 1;
+    const long long dz = (long long)__fmul_rn(__fsub_rn(mx[2], mn[2]), inv) + 1;
+    bx.guard = (dx * dy * dz > (long long)INT_MAX) ? 1 : 0;
+    int maxb[3];
+    for (int a = 0; a < 3; ++a) { bx.minb[a] = (int)floorf(__fmul_rn(mn[a], inv)); maxb[a] = (int)floorf(__fmul_rn(mx[a], inv)); }
+    const int d0 = maxb[0] - bx.minb[0] + 1, d1 = maxb[1] - bx.minb[1] + 1;
+    bx.mul1 = d0; bx.mul2 = d0 * d1;
+  }
+  *box = bx;
+  if (n == 0) *dCount = 0;
+}
+
+__global__ void __launch_bounds__(VG_BLOCK) vg_keys(const float4* __restrict__ in, const VgBox* __restrict__ box,
+                                                    unsigned long long* __restrict__ keys, int P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const VgBox b = *box;
+  keys[i] = (i < b.n && !b.guard) ? (((unsigned long long)vg_idx(in[i], b) << 32) | (unsigned)i) : ~0ull;
+}
+
+// Tile of 1024 sorted keys per block: count run heads.
+__global__ void __launch_bounds__(VG_BLOCK) vg_head_count(const unsigned long long* __restrict__ keys, const VgBox* __restrict__ box,
+                                                          int* __restrict__ blockCnt) {
+  const int n = box->guard ? 0 : box->n;
+  int cnt = 0;
+  const int base = blockIdx.x * 1024;
+  for (int q = 0; q < 4; ++q) {
+    const int t = base + q * VG_BLOCK + threadIdx.x;
+    if (t < n && (t == 0 || (unsigned)(keys[t] >> 32) != (unsigned)(keys[t - 1] >> 32))) ++cnt;
+  }
+  __shared__ int ws[VG_BLOCK / 32];
+  for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) { int s = 0; for (int w = 0; w < VG_BLOCK / 32; ++w) s += ws[w]; blockCnt[blockIdx.x] = s; }
+}
+
+__global__ void __launch_bounds__(1024) vg_block_scan(int* __restrict__ blockCnt, int nBlocks, const VgBox* __restrict__ box,
+                                                      int* __restrict__ dCount) {
+  __shared__ int buf[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nBlocks; base += 1024) {
+    const int b = base + threadIdx.x;
+    const int own = b < nBlocks ? blockCnt[b] : 0;
+    buf[threadIdx.x] = own;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+      const int v = threadIdx.x >= d ? buf[threadIdx.x - d] : 0;
+      __syncthreads();
+      buf[threadIdx.x] += v;
+      __syncthreads();
+    }
+    if (b < nBlocks) blockCnt[b] = carry + buf[threadIdx.x] - own;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += buf[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *dCount = box->guard ? box->n : carry;
+}
+
+__global__ void __launch_bounds__(VG_BLOCK) vg_centroid(const float4* __restrict__ in, const unsigned long long* __restrict__ keys,
+                                                        const VgBox* __restrict__ box, const int* __restrict__ blockOff,
+                                                        float4* __restrict__ out) {
+  const VgBox b = *box;
+  if (b.guard) {  // leaf too small for the extent: output = input
+    for (int i = blockIdx.x * 1024 + threadIdx.x; i < min(b.n, (int)(blockIdx.x + 1) * 1024); i += VG_BLOCK) out[i] = in[i];
+    return;
+  }
+  const int n = b.n;
+  __shared__ int ws[VG_BLOCK / 32];
+  int running = blockOff[blockIdx.x];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int q = 0; q < 4; ++q) {
+    const int t = blockIdx.x * 1024 + q * VG_BLOCK + threadIdx.x;
+    const bool head = t < n && (t == 0 || (unsigned)(keys[t] >> 32) != (unsigned)(keys[t - 1] >> 32));
+    const unsigned bal = __ballot_sync(0xffffffffu, head);
+    if (lane == 0) ws[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, all = 0;
+    for (int w = 0; w < VG_BLOCK / 32; ++w) { const int v = ws[w]; if (w < warp) before += v; all += v; }
+    if (head) {
+      const unsigned vox = (unsigned)(keys[t] >> 32);
+      float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f; int nrun = 0;
+      for (int r = t; r < n && (unsigned)(keys[r] >> 32) == vox; ++r) {
+        const float4 p = in[(int)(unsigned)(keys[r] & 0xffffffffull)];
+        sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
+        ++nrun;
+      }
+      const float fn = (float)nrun;
+      out[running + before + __popc(bal & ((1u << lane) - 1u))] =
+          make_float4(__fdiv_rn(sx, fn), __fdiv_rn(sy, fn), __fdiv_rn(sz, fn), __fdiv_rn(si, fn));
+    }
+    running += all;
+    __syncthreads();
+  }
+}
+
+int vl_voxel_grid_device(vloam_b200_ctx* c, const float4* d_in, int n, const int* d_n, float leaf, float4* d_out, int* d_count) {
+  if (n <= 0) { VL_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), c->stream)); return VLOAM_OK; }
+  int P = 2; while (P < n) P <<= 1;
+  const int nb = min(vl_div_up(n, VG_BLOCK), 256);
+  const int nTiles = vl_div_up(n, 1024);
+  VL_TRY(vl_reserve(c, c->vKeys, (size_t)P));
+  VL_TRY(vl_reserve(c, c->vScan, (size_t)nTiles + 256 * 6 + 64));
+  float* partial = reinterpret_cast<float*>(c->vScan.p + nTiles);
+  VgBox* box = reinterpret_cast<VgBox*>(c->vScalars);
+  VL_LAUNCH(vg_bbox, nb, VG_BLOCK, 0, d_in, n, d_n, partial);
+  VL_LAUNCH(vg_box, 1, 32, 0, partial, nb, n, d_n, leaf, box, d_count);
+  VL_LAUNCH(vg_keys, vl_div_up(P, VG_BLOCK), VG_BLOCK, 0, d_in, box, c->vKeys.p, P);
+  VL_TRY(vl_sort_u64(c, c->vKeys.p, P));
+  VL_LAUNCH(vg_head_count, nTiles, VG_BLOCK, 0, c->vKeys.p, box, c->vScan.p);
+  VL_LAUNCH(vg_block_scan, 1, 1024, 0, c->vScan.p, nTiles, box, d_count);
+  VL_LAUNCH(vg_centroid, nTiles, VG_BLOCK, 0, d_in, c->vKeys.p, box, c->vScan.p, d_out);
+  VL_CUDA(cudaGetLastError());
+  return VLOAM_OK;
+}
