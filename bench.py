@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py -- scans/sec of the lidar registration hot path (scanRegistration -> laserOdometry ->
+laserMapping) on synthetic HDL-64E sweeps against a planted ~1M-point cube map (BASELINE.json
+config C3: "HDL-64E scan-to-map laserMapping against ~1M-point local cube map").
+
+One "step" = one sweep through the whole per-frame chain (MAIN.cpp:143-144, 186-190).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          this repo's CUDA path
+  python bench.py --impl reference [...]                       the CPU restatement of the reference
+                                                               (oracle/, KD-tree mode) on the host cores
+
+Under torchrun (N > 1) every rank replays its own independent sequence (weak scaling, no data-path
+collective); poses and timings are gathered with one NCCL all_gather at the end.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SENSOR = 1  # HDL-64E
+WORKLOAD = "C3: synthetic HDL-64E sweeps (~118k pts), full scanRegistration+laserOdometry+laserMapping per sweep, planted ~1M-point cube map"
+
+
+def make_sequence(pkg, seq_id, n_frames, world_kind=1):
+    synth = pkg.synth
+    world = synth.World(1234, world_kind, 190.0)
+    traj = synth.trajectory(n_frames, seed=77 + seq_id)
+    scans = [world.scan(SENSOR, traj[k], 1000 + 7919 * seq_id + k) for k in range(n_frames)]
+    corner = world.plant(0, 0.4, seed=99)
+    surf = world.plant(1, 0.8, seed=98)
+    cblob, sblob = synth.cubes_blob(corner, 0.4), synth.cubes_blob(surf, 0.8)
+    return scans, traj, cblob, sblob
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def run_reference(args, rank, world_size):
+    """CPU arm: the oracle in baseline mode (KD-tree kNN, std::sort voxel grids, restated Ceres LM),
+    one single-threaded replica per host core like the reference (MAIN.cpp:277-282)."""
+    if rank != 0:
+        return
+    pkg = importlib.import_module("vloam-noted_b200")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as op
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    replicas = max(1, min(cores, 16))
+    budget_s = 200.0
+    n_frames = args.warmup + args.steps + 1
+    scans, traj, cblob, sblob = make_sequence(pkg, 0, min(n_frames, 64))
+
+    def replica(out, idx):
+        o = op.Oracle(n_scans=64, minimum_range=5.0, line_res=0.4, plane_res=0.8, knn_backend=1)
+        o.set("lm.cornerMap", cblob); o.set("lm.surfMap", sblob)
+        times = []
+        t_start = time.perf_counter()
+        for k in range(n_frames):
+            s = scans[k % len(scans)]
+            t0 = time.perf_counter()
+            o.process(s)
+            times.append(time.perf_counter() - t0)
+            if time.perf_counter() - t_start > budget_s:
+                break
+        out[idx] = times
+
+    results = [None] * replicas
+    th = [threading.Thread(target=replica, args=(results, i)) for i in range(replicas)]
+    t0 = time.perf_counter()
+    for t in th: t.start()
+    for t in th: t.join()
+    done = min(len(r) for r in results)
+    w = min(args.warmup + 1, max(done - 1, 0))
+    timed = done - w
+    per_rep = [sum(r[w:done]) for r in results]
+    wall = max(per_rep)
+    value = replicas * timed / wall if wall > 0 else 0.0
+    single = timed / float(np.mean(per_rep)) if timed else 0.0
+    line = {
+        "impl": "reference", "metric": "scans/sec", "value": value, "unit": "scans/s", "n_gpus": args.gpus, "steps": timed, "warmup": w,
+        "ms_per_step": 1e3 * wall / max(timed, 1) / replicas, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "map_points": int(pkg.synth.blob_counts(cblob).sum() + pkg.synth.blob_counts(sblob).sum())},
+        "cpu_baseline": {"value": value, "unit": "scans/s", "cores": replicas, "kind": "port",
+                         "sample": "%d frames x %d single-threaded replicas of oracle/ (KD-tree mode); one replica alone: %.3f scans/s; p50 %.1f ms/frame"
+                                   % (timed, replicas, single, 1e3 * float(np.median(np.concatenate([r[w:done] for r in results])))) if timed else "none"},
+        "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(pkg, scans, cblob, sblob, frames=4):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as op
+    o = op.Oracle(n_scans=64, minimum_range=5.0, line_res=0.4, plane_res=0.8, knn_backend=1)
+    o.set("lm.cornerMap", cblob); o.set("lm.surfMap", sblob)
+    times, stages = [], []
+    for k in range(frames + 1):
+        t0 = time.perf_counter()
+        o.process(scans[k])
+        times.append(time.perf_counter() - t0)
+        stages.append(o.get("timing")[:3])
+    t = times[1:]
+    st = np.mean(np.array(stages[1:]), axis=0)
+    return {"value": len(t) / sum(t), "unit": "scans/s", "cores": 1, "kind": "port",
+            "sample": "%d frames of the same workload after 1 warm-up frame, single thread like the reference; mean ms SR/LO/LM = %.1f/%.1f/%.1f"
+                      % (len(t), st[0], st[1], st[2])}
+
+
+def run_ours(args, rank, world_size, local_rank):
+    import torch
+    pkg = importlib.import_module("vloam-noted_b200")
+    pkg.load_lib()  # raises if the CUDA library is missing: there is no fallback
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    K, W = args.steps, max(args.warmup, 3)
+    n_frames = W + K + 1
+    scans, traj, cblob, sblob = make_sequence(pkg, rank, n_frames)
+    map_points = int(pkg.synth.blob_counts(cblob).sum() + pkg.synth.blob_counts(sblob).sum())
+
+    def fresh():
+        ctx = pkg.Context(n_scans=64, minimum_range=5.0, line_res=0.4, plane_res=0.8, device=local_rank)
+        ctx.set("lm.cornerMap", cblob); ctx.set("lm.surfMap", sblob)
+        return ctx
+
+    ext = None
+    # ---- leg 1: device-resident inputs (value) ------------------------------------------------
+    ctx = fresh()
+    ext = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+    dscans = [torch.from_numpy(s).cuda(local_rank) for s in scans]
+    torch.cuda.synchronize()
+    for k in range(W + 1):
+        ctx.process_frame_device(dscans[k].data_ptr(), dscans[k].shape[0], 4)
+    ctx.synchronize()
+    if dist: dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0: sampler.start()
+    l0 = ctx.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for k in range(W + 1, W + 1 + K):
+        ctx.process_frame_device(dscans[k].data_ptr(), dscans[k].shape[0], 4)
+    e1.record(ext)
+    ctx.synchronize(); torch.cuda.synchronize()
+    if dist: dist.barrier()
+    dev_ms = e0.elapsed_time(e1)
+    launches = ctx.kernel_launches - l0
+    # dominant-kernel timing (CUDA events around that kernel's launches, on the launching stream)
+    roof = None
+    if hasattr(ctx.L, "vloam_b200_profile_kernel"):
+        roof = profile_dominant(ctx, dscans, W + 1, K, map_points)
+    ctx.close()
+
+    # ---- leg 2: end to end through the C ABI with host buffers (e2e) --------------------------
+    ctx = fresh()
+    pinned = [torch.from_numpy(s).pin_memory() for s in scans]
+    pose = np.zeros(14)
+    lat = []
+    for k in range(W + 1):
+        ctx.process_frame_ptr(pinned[k].data_ptr(), pinned[k].shape[0], 4, pose.ctypes.data)
+    if dist: dist.barrier()
+    t0 = time.perf_counter()
+    poses = np.zeros((K, 14))
+    for i, k in enumerate(range(W + 1, W + 1 + K)):
+        t1 = time.perf_counter()
+        ctx.process_frame_ptr(pinned[k].data_ptr(), pinned[k].shape[0], 4, pose.ctypes.data)
+        lat.append(time.perf_counter() - t1)
+        poses[i] = pose
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    ctx.close()
+    h2d = float(np.mean([s.shape[0] * 16 for s in scans[W + 1:W + 1 + K]]))
+
+    # trajectory sanity against the generator's ground truth (frame W+K)
+    err = float(np.linalg.norm(poses[-1, 11:14] - traj[W + K][:3]))
+
+    # ---- max over ranks; one collective: gather of poses + timings ----------------------------
+    times = torch.tensor([dev_ms, e2e_s * 1e3, float(np.median(lat)) * 1e3, err], dtype=torch.float64, device="cuda")
+    if dist:
+        allt = [torch.zeros_like(times) for _ in range(world_size)]
+        dist.all_gather(allt, times)
+        gp = [torch.zeros(K, 14, dtype=torch.float64, device="cuda") for _ in range(world_size)]
+        dist.all_gather(gp, torch.from_numpy(poses).cuda())
+        allt = torch.stack(allt).cpu().numpy()
+    else:
+        allt = times.cpu().numpy()[None]
+    if rank != 0:
+        if dist: dist.destroy_process_group()
+        return
+    dev_ms_max, e2e_ms_max = float(allt[:, 0].max()), float(allt[:, 1].max())
+    value = world_size * K / (dev_ms_max * 1e-3)
+    e2e_value = world_size * K / (e2e_ms_max * 1e-3)
+    cpu = cpu_baseline_sample(pkg, scans, cblob, sblob) if world_size == 1 and not args.no_cpu_baseline else None
+    line = {
+        "metric": "scans/sec", "value": value, "unit": "scans/s", "n_gpus": world_size, "steps": K, "warmup": W,
+        "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "map_points": map_points, "points_per_sweep": int(np.mean([len(s) for s in scans])),
+                   "l2": "sub-map + sweep (~20 MB) fit the 126 MB L2 by design of the workload; every sweep is a new input",
+                   "parallelism": "independent sequences, one per GPU"},
+        "p50_ms_per_frame_e2e": float(np.max(allt[:, 2])), "final_pose_error_m": float(allt[:, 3].max()),
+        "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 14 * 8 + 352 + 712},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if roof: line["roofline"] = roof
+    if cpu: line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if dist: dist.destroy_process_group()
+
+
+def profile_dominant(ctx, dscans, first, K, map_points):
+    """Average duration of the dominant kernel, measured with CUDA events the library records around
+    that kernel's launches on its own stream, over a replay of the timed frames."""
+    import ctypes
+    L = ctx.L
+    L.vloam_b200_profile_kernel.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+    L.vloam_b200_profile_result.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    name = b"rf_emit_prefix"
+    L.vloam_b200_profile_kernel(ctx.h, name)
+    n = min(K, 20)
+    for k in range(first, first + n):
+        ctx.process_frame_device(dscans[k].data_ptr(), dscans[k].shape[0], 4)
+    ctx.synchronize()
+    cnt, ms, byt = ctypes.c_int(0), ctypes.c_double(0), ctypes.c_double(0)
+    L.vloam_b200_profile_result(ctx.h, ctypes.byref(cnt), ctypes.byref(ms), ctypes.byref(byt))
+    L.vloam_b200_profile_kernel(ctx.h, None)
+    if cnt.value == 0:
+        return None
+    peak, how = measured_peak()
+    per_launch_bytes = byt.value / cnt.value
+    achieved = per_launch_bytes / (ms.value / cnt.value * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": name.decode(), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": how, "launches_timed": cnt.value, "avg_us": 1e3 * ms.value / cnt.value,
+            "algorithmic_bytes_per_launch": per_launch_bytes}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local)
+
+
+if __name__ == "__main__":
+    main()

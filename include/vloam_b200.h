@@ -110,6 +110,12 @@ long long vloam_b200_kernel_launches(const vloam_b200_ctx* c);
 int vloam_b200_set_timing(vloam_b200_ctx* c, int enabled);
 int vloam_b200_stage_ms(vloam_b200_ctx* c, float* ms3);
 
+/* Measurement aid: record CUDA events around every launch of the kernel called `name`
+ * (NULL switches it off); profile_result returns how many launches were timed, their
+ * summed duration and the algorithmic bytes the launch sites declared for them. */
+int vloam_b200_profile_kernel(vloam_b200_ctx* c, const char* name);
+int vloam_b200_profile_result(vloam_b200_ctx* c, int* launches, double* total_ms, double* total_bytes);
+
 /* State export / import and stage-level inspection, keyed by name.  The
  * reference keeps this state in private members (LO.h:90-147, LM.h:102-203);
  * teacher-forced parity tests inject the oracle's state through these.

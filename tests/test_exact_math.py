@@ -1,0 +1,54 @@
+"""exact_math.h (the fdlibm atanf / atan2f the CUDA path uses) against the container's glibc:
+bit equality on a strided sweep of all binary32 inputs."""
+import os
+import subprocess
+import tempfile
+
+SRC = r'''
+#include <math.h>
+#include <stdio.h>
+#include <stdint.h>
+#include "exact_math.h"
+int main() {
+  long bad1 = 0, bad2 = 0, n1 = 0, n2 = 0;
+  for (uint64_t u = 3; u < (1ull << 32); u += 61) {  // ~70M inputs across every exponent
+    float x = vlx::u2f((uint32_t)u), a = atanf(x), c = vlx::atanf_exact(x);
+    if (vlx::f2u(a) != vlx::f2u(c) && !(a != a && c != c)) ++bad1;
+    ++n1;
+  }
+  uint64_t s = 88172645463325252ull;
+  for (long i = 0; i < 40000000L; ++i) {
+    s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+    float x, y;
+    if (i % 4 == 0) { x = vlx::u2f((uint32_t)s); y = vlx::u2f((uint32_t)(s >> 32)); }
+    else { x = (float)((double)(int32_t)(s & 0xffffffff) / 2147483648.0 * 120.0); y = (float)((double)(int32_t)(s >> 32) / 2147483648.0 * 120.0);
+           if (i % 4 == 2) x *= 1e-3f; if (i % 4 == 3) y *= 1e-4f; }
+    float a = atan2f(y, x), c = vlx::atan2f_exact(y, x);
+    if (vlx::f2u(a) != vlx::f2u(c) && !(a != a && c != c)) ++bad2;
+    ++n2;
+  }
+  // special values
+  const float sp[] = {0.f, -0.f, 1.f, -1.f, INFINITY, -INFINITY, NAN, 1e-40f, -1e-40f, 3e38f};
+  for (float y : sp) for (float x : sp) {
+    float a = atan2f(y, x), c = vlx::atan2f_exact(y, x);
+    if (vlx::f2u(a) != vlx::f2u(c) && !(a != a && c != c)) ++bad2;
+  }
+  printf("%ld %ld %ld %ld\n", bad1, n1, bad2, n2);
+  return 0;
+}
+'''
+
+
+def test_atan_bit_exact_vs_glibc():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    inc = os.path.join(root, "vloam-noted_b200", "csrc")
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "t.cpp")
+        open(src, "w").write(SRC)
+        exe = os.path.join(d, "t")
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-I", inc, src, "-o", exe], check=True)
+        out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
+    bad1, n1, bad2, n2 = map(int, out)
+    assert n1 > 60_000_000 and n2 == 40_000_000
+    assert bad1 == 0, "atanf differs from glibc on %d inputs" % bad1
+    assert bad2 == 0, "atan2f differs from glibc on %d inputs" % bad2

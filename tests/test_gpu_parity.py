@@ -1,0 +1,311 @@
+"""GPU parity tests proper (run on the B200 box): the CUDA path through the C ABI against the CPU
+oracle on identical inputs.  Bar (BASELINE.json north_star): feature clouds / labels / association
+and kNN indices bit-exact, poses within 1e-4 m and 1e-5 rad (quaternion components)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_bits_equal
+from test_oracle_math import make_factors
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL, ROT_TOL = 1e-4, 1e-5
+KW = {0: dict(n_scans=16, minimum_range=0.3, line_res=0.2, plane_res=0.4),
+      1: dict(n_scans=64, minimum_range=5.0, line_res=0.4, plane_res=0.8),
+      2: dict(n_scans=128, minimum_range=0.3, line_res=0.4, plane_res=0.8),
+      3: dict(n_scans=32, minimum_range=0.3, line_res=0.2, plane_res=0.4)}
+SR_NAMES = ("sr.laserCloud", "sr.curvature", "sr.label", "sr.scanStartInd", "sr.scanEndInd", "sr.sharp", "sr.lessSharp", "sr.flat", "sr.lessFlat")
+
+
+def check_sr(o, g):
+    for nm in SR_NAMES:
+        assert_bits_equal(o.get(nm), g.get(nm), nm)
+
+
+def pose_close(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    assert np.abs(a[4:7] - b[4:7]).max() < POS_TOL, (a[4:7], b[4:7])
+    assert np.abs(a[0:4] - b[0:4]).max() < ROT_TOL, (a[0:4], b[0:4])
+
+
+@pytest.mark.parametrize("sensor", [0, 1, 2, 3])
+@pytest.mark.parametrize("order", [0, 1])
+def test_scan_registration_bit_exact(pkg, op, synth, street, sensor, order):
+    """Azimuth-major (Velodyne driver) and ring-major (KITTI) emission orders, all four beam tables."""
+    scan = street.scan(sensor, [3.0, 0.5, 0.02, 0.03, 0.002, -0.001], 4242 + sensor, order=order)
+    o, g = op.Oracle(**KW[sensor]), pkg.Context(**KW[sensor])
+    o.scan_registration(scan)
+    g.begin_frame(); g.scan_registration(scan)
+    check_sr(o, g)
+    # packed XYZ (stride 3) gives the same result as KITTI stride 4
+    g.begin_frame(); g.scan_registration(np.ascontiguousarray(scan[:, :3]))
+    check_sr(o, g)
+    g.close()
+
+
+def test_scan_registration_adversarial_rings(pkg, op):
+    """Uniform random directions: every elevation, so thousands of points sit next to a ring boundary
+    (the atanf / atan2f parity trap of SURVEY section 0 item 6), with NaN / inf / near returns mixed in."""
+    rng = np.random.RandomState(7)
+    n = 200000
+    d = rng.randn(n, 3)
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    d[:, 2] *= 0.35
+    pts = (d * rng.uniform(0.2, 90.0, (n, 1))).astype(np.float32)
+    pts[rng.rand(n) < 0.02] = np.nan
+    pts[rng.rand(n) < 0.001, 0] = np.inf
+    for sensor in (0, 1, 2, 3):
+        o, g = op.Oracle(**KW[sensor]), pkg.Context(**KW[sensor])
+        o.scan_registration(pts)
+        g.begin_frame(); g.scan_registration(pts)
+        check_sr(o, g)
+        g.close()
+
+
+def test_scan_registration_edge_cases(pkg, op):
+    g, o = pkg.Context(**KW[0]), op.Oracle(**KW[0])
+    cases = [np.zeros((0, 3), np.float32), np.full((100, 3), np.nan, np.float32),
+             (np.random.RandomState(0).randn(100, 3) * 0.05).astype(np.float32),
+             np.array([[5, 0, 0.1], [5, 0.1, 0.1], [5, 0.2, 0.1]], np.float32),
+             np.tile(np.array([[4.0, 1.0, 0.2]], np.float32), (300, 1))]          # 300 identical points: all-tie sort keys
+    for c in cases:
+        o.scan_registration(c)
+        g.begin_frame(); g.scan_registration(c)
+        check_sr(o, g)
+    g.close()
+
+
+def test_dense_ring_uses_global_sort_path(pkg, op):
+    """One ring with 9000 points: sector > 1024 keys and ring > 4096 / 8192 -> the global-memory sort
+    and picked-flag fallbacks of sr_pick / sr_ring_voxel."""
+    rng = np.random.RandomState(3)
+    az = np.sort(rng.uniform(-np.pi, np.pi, 9000))[::-1]
+    r = 10 + 2 * np.sin(7 * az) + 0.05 * rng.randn(9000)
+    el = np.deg2rad(1.0)
+    pts = np.stack([r * np.cos(el) * np.cos(az), r * np.cos(el) * np.sin(az), r * np.sin(el) + 0 * az], 1).astype(np.float32)
+    o, g = op.Oracle(**KW[0]), pkg.Context(**KW[0])
+    o.scan_registration(pts)
+    g.begin_frame(); g.scan_registration(pts)
+    check_sr(o, g)
+    assert len(o.get("sr.lessFlat")) > 1000
+    g.close()
+
+
+@pytest.mark.parametrize("n,leaf,scale", [(0, 0.2, 1.0), (1, 0.2, 1.0), (777, 0.2, 3.0), (5000, 0.4, 20.0), (70000, 0.8, 40.0), (3, 0.2, 1e6)])
+def test_voxel_grid_bit_exact(pkg, op, n, leaf, scale):
+    rng = np.random.RandomState(n + 1)
+    c = (rng.randn(n, 4) * scale).astype(np.float32)
+    g = pkg.Context()
+    assert_bits_equal(op.voxel_grid(c, leaf), g.voxel_grid(c, leaf), "voxel_grid n=%d" % n)
+    g.close()
+
+
+def test_normal_equations_and_solver_match_oracle(pkg, op):
+    from scipy.spatial.transform import Rotation as R
+    rng = np.random.RandomState(23)
+    q = R.from_euler("xyz", [0.01, -0.02, 0.03]).as_quat()
+    t = np.array([0.8, -0.1, 0.05])
+    g = pkg.Context()
+    for noise, n in ((0.0, 40), (0.03, 300), (0.2, 3000)):
+        f = make_factors(rng, q, t, n, n, n, noise=noise)
+        x = np.concatenate([R.from_euler("xyz", [0.02, 0.0, 0.01]).as_quat(), [0.6, 0.0, 0.0]])
+        co, Ho, go = op.evaluate(f, x)
+        cg, Hg, gg = g.evaluate(f, x)
+        assert abs(co - cg) <= 1e-12 * max(1.0, abs(co))
+        assert np.abs(Ho - Hg).max() <= 1e-10 * np.abs(Ho).max()
+        assert np.abs(go - gg).max() <= 1e-10 * max(1.0, np.abs(go).max())
+        xo, lo = op.ceres_solve(f, x)
+        xg, lg = g.solve(f, x)
+        assert np.abs(xo - xg).max() < 1e-9, (xo, xg)
+        assert abs(lo[2] - lg[2]) <= 1e-12 * max(1.0, lo[2]) and abs(lo[3] - lg[3]) <= 1e-10 * max(1.0, lo[3])
+    xg, _ = g.solve(np.zeros((0, 10)), x)
+    assert (xg == x).all()
+    g.close()
+
+
+def teacher_force(o, g):
+    g.set_last(o.get("lo.cornerLast"), o.get("lo.surfLast"))
+    g.set("lo.pose", o.get("lo.pose"))
+    g.set("lm.state", o.get("lm.state")[:4])
+    g.set("lm.pose", o.get("lm.pose"))
+    g.set("lm.cornerMap", o.get("lm.cornerMap"))
+    g.set("lm.surfMap", o.get("lm.surfMap"))
+
+
+def check_frame(o, g, k):
+    check_sr(o, g)
+    if k > 0:
+        for nm in ("lo.assoc.corner0", "lo.assoc.surf0", "lo.assoc.corner1", "lo.assoc.surf1"):
+            assert_bits_equal(o.get(nm), g.get(nm), nm)
+    lo_o, lo_g = o.get("lo.pose"), g.get("lo.pose")
+    pose_close(lo_o[:7], lo_g[:7]); pose_close(lo_o[7:], lo_g[7:])
+    for nm in ("lm.cornerStack", "lm.surfStack", "lm.cornerFromMap", "lm.surfFromMap", "lm.validInd"):
+        assert_bits_equal(o.get(nm), g.get(nm), nm)
+    so, sg = o.get("lm.state"), g.get("lm.state")
+    assert (so == sg).all(), (so, sg)
+    if so[4]:
+        for p in (0, 1):
+            for kind in ("c", "s"):
+                oi, gi = o.get("lm.knn.%sidx%d" % (kind, p)), g.get("lm.knn.%sidx%d" % (kind, p))
+                od, gd = o.get("lm.knn.%sd2%d" % (kind, p)), g.get("lm.knn.%sd2%d" % (kind, p))
+                acc = od[:, 4] < 1.0   # parity contract: inside the acceptance ball
+                assert_bits_equal(oi[acc], gi[acc], "knn idx")
+                assert_bits_equal(od[acc], gd[acc], "knn d2")
+                assert_bits_equal(o.get("lm.knn.%sok%d" % (kind, p)), g.get("lm.knn.%sok%d" % (kind, p)), "fit accept flags")
+    lm_o, lm_g = o.get("lm.pose"), g.get("lm.pose")
+    pose_close(lm_o[:7], lm_g[:7]); pose_close(lm_o[7:], lm_g[7:])
+    assert o.get("lm.cornerMap") == g.get("lm.cornerMap"), "corner map bytes"
+    assert o.get("lm.surfMap") == g.get("lm.surfMap"), "surf map bytes"
+
+
+@pytest.mark.parametrize("sensor,frames", [(0, 4), (1, 4), (2, 2), (3, 3)])
+def test_teacher_forced_chain(pkg, op, synth, street, sensor, frames):
+    """Every frame the GPU context is loaded with the oracle's state, then both run SR -> LO -> LM; every
+    stage output must agree."""
+    traj = synth.trajectory(frames)
+    o, g = op.Oracle(**KW[sensor]), pkg.Context(**KW[sensor])
+    g.set_capture(True)
+    for k in range(frames):
+        scan = street.scan(sensor, traj[k], 1000 + k)
+        if k > 0:
+            teacher_force(o, g)
+        o.scan_registration(scan)
+        g.begin_frame(); g.scan_registration(scan)
+        o.laser_odometry(); g.laser_odometry()
+        o.laser_mapping(); g.laser_mapping()
+        check_frame(o, g, k)
+    g.close()
+
+
+def test_free_running_sequence_pose_tolerance(pkg, op, synth, street):
+    """No teacher forcing: 10 HDL-64 frames through process_frame; poses stay within tolerance."""
+    traj = synth.trajectory(10)
+    o, g = op.Oracle(**KW[1], knn_backend=1), pkg.Context(**KW[1])
+    for k in range(10):
+        scan = street.scan(1, traj[k], 1000 + k)
+        o.process(scan)
+        pose = g.process_frame(scan)
+        pose_close(o.get("lo.pose")[:7], pose[:7])
+        pose_close(o.get("lm.pose")[:7], pose[7:])
+    assert np.linalg.norm(pose[11:14] - traj[9][:3]) < 0.05
+    g.close()
+
+
+def test_vo_prior_path(pkg, op, synth, street):
+    """detach_VO_LO == false (LO.cpp:237-250): the prior overwrites para_q / para_t at the top of both passes."""
+    from scipy.spatial.transform import Rotation as R
+    traj = synth.trajectory(2)
+    o, g = op.Oracle(**KW[0]), pkg.Context(**KW[0])
+    pq, pt = R.from_euler("z", 0.004).as_quat(), np.array([0.95, 0.0, 0.0])
+    for k in range(2):
+        scan = street.scan(0, traj[k], 1000 + k)
+        o.scan_registration(scan); g.begin_frame(); g.scan_registration(scan)
+        o.laser_odometry(pq, pt); r = g.laser_odometry(pq, pt)
+    lo = o.get("lo.pose")
+    pose_close(lo[:7], np.concatenate([r["q_w_curr"], r["t_w_curr"]]))
+    pose_close(lo[7:], np.concatenate([r["q_last_curr"], r["t_last_curr"]]))
+    g.close()
+
+
+def test_mapping_skip_frame(pkg, op, synth, street):
+    """mapping_skip_frame = 2: odd frames only propagate the high-frequency pose (LM.cpp:197-201)."""
+    kw = dict(KW[0], mapping_skip_frame=2)
+    traj = synth.trajectory(4)
+    o, g = op.Oracle(**kw), pkg.Context(**kw)
+    for k in range(4):
+        scan = street.scan(0, traj[k], 1000 + k)
+        o.process(scan)
+        pose = g.process_frame(scan)
+        pose_close(o.get("lo.pose")[:7], pose[:7])
+    assert o.get("lm.surfMap") == g.get("lm.surfMap")
+    pose_close(o.get("lm.pose")[:7], g.get("lm.pose")[:7])
+    g.close()
+
+
+def test_cube_window_roll_and_outside_appends(pkg, op, synth, street):
+    """Jump the mapper 200+ m: the 21x21x11 window rolls (LM.cpp:252-444), the old cubes fall outside the
+    5x5x3 sub-map and fresh points land in cubes that were never filtered (raw tail path)."""
+    o, g = op.Oracle(**KW[1]), pkg.Context(**KW[1])
+    scan = street.scan(1, [0, 0, 0, 0, 0, 0], 1000)
+    o.process(scan); g.process_frame(scan)
+    for jump in ([480.0, -470.0, 0.0], [-520.0, 30.0, 20.0], [60.0, 60.0, 0.0]):
+        pose = o.get("lm.pose"); pose[11:14] = jump
+        o.set("lm.pose", pose); g.set("lm.pose", pose)
+        o.process(scan); g.process_frame(scan)
+        assert (o.get("lm.state")[:3] == g.get("lm.state")[:3]).all()
+        assert_bits_equal(o.get("lm.validInd"), g.get("lm.validInd"), "validInd")
+        assert o.get("lm.cornerMap") == g.get("lm.cornerMap") and o.get("lm.surfMap") == g.get("lm.surfMap")
+    g.close()
+
+
+def test_full_size_planted_map_frame(pkg, op, synth):
+    """BASELINE config C3 at full size: ~1M-point planted sub-map, one HDL-64 sweep.  kNN / fit parity
+    against the oracle (KD-tree backend, itself checked against brute force) and the size-independent
+    properties: re-filtering is idempotent on the planted cubes, map grows by <= Qc + Qs."""
+    world = synth.World(1234, 1, 190.0)
+    cb, sb = synth.cubes_blob(world.plant(0, 0.4, seed=99), 0.4), synth.cubes_blob(world.plant(1, 0.8, seed=98), 0.8)
+    assert synth.blob_counts(cb).sum() + synth.blob_counts(sb).sum() > 900_000
+    o, g = op.Oracle(**KW[1], knn_backend=1), pkg.Context(**KW[1])
+    g.set_capture(True)
+    for x in (o, g):
+        x.set("lm.cornerMap", cb); x.set("lm.surfMap", sb)
+    traj = synth.trajectory(2)
+    for k in range(2):
+        scan = world.scan(1, traj[k], 1000 + k)
+        if k > 0:
+            teacher_force(o, g)
+        o.scan_registration(scan); g.begin_frame(); g.scan_registration(scan)
+        o.laser_odometry(); g.laser_odometry()
+        o.laser_mapping(); g.laser_mapping()
+        check_frame(o, g, k)
+    n_before = synth.blob_counts(sb).sum()
+    n_after = synth.blob_counts(g.get("lm.surfMap")).sum()
+    assert n_before <= n_after <= n_before + 2 * len(g.get("lm.surfStack")) + 100000
+    g.close()
+
+
+def test_mirror_classes_follow_reference_call_sequence(pkg, op, synth, street):
+    """LidarOdometryMapping.reset / scanRegistrationIO / laserOdometryIO / laserMappingIO (MAIN.cpp:143-190)."""
+    lom = pkg.LidarOdometryMapping(**KW[0])
+    o = op.Oracle(**KW[0])
+    traj = synth.trajectory(2)
+    for k in range(2):
+        scan = street.scan(0, traj[k], 1000 + k)
+        lom.reset(); lom.scanRegistrationIO(scan); lom.laserOdometryIO(); lom.laserMappingIO()
+        o.process(scan)
+    full, sharp, less, flat, lessflat = lom.scan_registration.output()
+    assert_bits_equal(o.get("sr.sharp"), sharp, "sharp"); assert_bits_equal(o.get("sr.lessFlat"), lessflat, "lessFlat")
+    q, t, cl, sl, fr, skip = lom.laser_odometry.output()
+    assert not skip
+    assert_bits_equal(o.get("lo.cornerLast"), cl, "cornerLast")
+    pose_close(o.get("lm.pose")[:7], np.concatenate(lom.laser_mapping.pose))
+    lom.ctx.close()
+
+
+def test_golden_fixture_on_gpu(pkg):
+    """tests/golden/vlp16_pair.npz (oracle outputs, made by tests/make_golden.py) reproduced by the CUDA path."""
+    gold = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vlp16_pair.npz")))
+    g = pkg.Context(**KW[0])
+    g.set_capture(True)
+    for k in range(2):
+        pose = g.process_frame(gold["scan%d" % k])
+        for nm in ("sr.sharp", "sr.flat", "sr.lessSharp", "sr.lessFlat"):
+            assert_bits_equal(gold["f%d.%s" % (k, nm)], g.get(nm), nm)
+        assert (g.get("sr.label").astype(np.int8) == gold["f%d.label" % k]).all()
+        pose_close(gold["f%d.lo.pose" % k][:7], pose[:7]); pose_close(gold["f%d.lm.pose" % k][:7], pose[7:])
+    assert_bits_equal(gold["f1.assoc.corner0"], g.get("lo.assoc.corner0"), "assoc")
+    assert_bits_equal(gold["f1.assoc.surf0"], g.get("lo.assoc.surf0"), "assoc")
+    g.close()
+
+
+def test_errors_are_reported(pkg):
+    with pytest.raises(pkg.VloamError):
+        pkg.Context(n_scans=48)            # SR.cpp:58-61: only 16 / 32 / 64 (128 extension)
+    g = pkg.Context()
+    with pytest.raises(pkg.VloamError):
+        g.get("no.such.buffer")
+    with pytest.raises(pkg.VloamError):
+        g.set("lm.surfMap", b"123")
+    g.close()

@@ -40,11 +40,3 @@ def build_synth(force=False):
     if force or _stale(SYNTH_LIB, [src]):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", SYNTH_LIB, src], check=True)
     return SYNTH_LIB
-
-
-def build_oracle(force=False):
-    odir = os.path.join(ROOT, "oracle")
-    if force:
-        subprocess.run(["make", "-C", odir, "clean"], check=True, stdout=subprocess.DEVNULL)
-    subprocess.run(["make", "-C", odir], check=True, stdout=subprocess.DEVNULL)
-    return os.path.join(odir, "liboracle.so")

@@ -36,6 +36,7 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   c->cornerLastPtr = nullptr; c->surfLastPtr = nullptr;
   for (int k = 0; k < 4; ++k) c->dbgLoCost[k] = c->dbgLmCost[k] = 0;
   for (int k = 0; k < 3; ++k) c->stage_ms[k] = 0;
+  c->prof_name[0] = 0; c->prof_n = 0; c->prof_created = 0; c->prof_bytes = 0; c->prof_next_bytes = 0;
   cudaDeviceProp prop;
   VL_CUDA_CREATE(cudaGetDeviceProperties(&prop, device));
   c->num_sms = prop.multiProcessorCount;
@@ -215,6 +216,26 @@ int vloam_b200_stage_ms(vloam_b200_ctx* c, float* ms3) {
   if (!c->timing) { snprintf(c->err, sizeof c->err, "timing is off"); return VLOAM_E_INVALID; }
   VL_CUDA(cudaStreamSynchronize(c->stream));
   for (int k = 0; k < 3; ++k) VL_CUDA(cudaEventElapsedTime(&ms3[k], c->ev[k], c->ev[k + 1]));
+  return VLOAM_OK;
+}
+
+// Time one named kernel: CUDA events are recorded around each of its launches on the context's stream.
+int vloam_b200_profile_kernel(vloam_b200_ctx* c, const char* name) {
+  VL_CUDA(cudaStreamSynchronize(c->stream));
+  if (!c->prof_created) {
+    for (int k = 0; k < VL_PROF_MAX; ++k) { VL_CUDA(cudaEventCreate(&c->prof_ev[k][0])); VL_CUDA(cudaEventCreate(&c->prof_ev[k][1])); }
+    c->prof_created = 1;
+  }
+  c->prof_n = 0; c->prof_bytes = 0;
+  if (name) { strncpy(c->prof_name, name, sizeof c->prof_name - 1); c->prof_name[sizeof c->prof_name - 1] = 0; }
+  else c->prof_name[0] = 0;
+  return VLOAM_OK;
+}
+int vloam_b200_profile_result(vloam_b200_ctx* c, int* launches, double* total_ms, double* total_bytes) {
+  VL_CUDA(cudaStreamSynchronize(c->stream));
+  double ms = 0;
+  for (int k = 0; k < c->prof_n; ++k) { float t = 0; VL_CUDA(cudaEventElapsedTime(&t, c->prof_ev[k][0], c->prof_ev[k][1])); ms += t; }
+  *launches = c->prof_n; *total_ms = ms; *total_bytes = c->prof_bytes;
   return VLOAM_OK;
 }
 

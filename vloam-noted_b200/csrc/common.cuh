@@ -17,6 +17,7 @@
 #define VL_CUBE_D 11
 #define VL_CUBE_NUM (VL_CUBE_W * VL_CUBE_H * VL_CUBE_D)
 #define VL_MAX_VALID 125  // laserCloudValidInd[125], laser_mapping.h:127
+#define VL_PROF_MAX 512
 
 // ---- device-resident scalars (one struct per context, also mirrored in pinned host memory)
 struct SrScalars {
@@ -155,6 +156,11 @@ struct vloam_b200_ctx {
   // refilter scratch
   DBuf<unsigned long long> tailKeys; DBuf<float4> staging;
   DBuf<int> tmpI[4];
+  // per-kernel timing (vloam_b200_profile_kernel): CUDA events around the launches of one named kernel
+  char prof_name[64];
+  cudaEvent_t prof_ev[VL_PROF_MAX][2];
+  int prof_n, prof_created;
+  double prof_bytes, prof_next_bytes;
 };
 
 struct GridParams {
@@ -181,11 +187,24 @@ struct GridParams {
     if (r_ != VLOAM_OK) return r_; \
   } while (0)
 
-#define VL_LAUNCH(kernel, grid, block, smem, ...)                    \
-  do {                                                               \
-    kernel<<<(grid), (block), (smem), c->stream>>>(__VA_ARGS__);     \
-    c->launches++;                                                   \
+#define VL_LAUNCH(kernel, grid, block, smem, ...)                                              \
+  do {                                                                                         \
+    const bool prof_ = c->prof_name[0] && vl_prof_match(c, #kernel) && c->prof_n < VL_PROF_MAX; \
+    if (prof_) cudaEventRecord(c->prof_ev[c->prof_n][0], c->stream);                           \
+    kernel<<<(grid), (block), (smem), c->stream>>>(__VA_ARGS__);                               \
+    if (prof_) { cudaEventRecord(c->prof_ev[c->prof_n][1], c->stream); c->prof_n++; c->prof_bytes += c->prof_next_bytes; } \
+    c->prof_next_bytes = 0;                                                                    \
+    c->launches++;                                                                             \
   } while (0)
+
+// algorithmic bytes of the next launch (DESIGN.md roofline table), consumed by VL_LAUNCH when that kernel is profiled
+#define VL_BYTES(b) (c->prof_next_bytes = (double)(b))
+
+static inline bool vl_prof_match(const vloam_b200_ctx* c, const char* k) {
+  // template kernels show up as "lo_assoc<true>": compare the prefix
+  const size_t n = strlen(c->prof_name);
+  return strncmp(c->prof_name, k, n) == 0 && (k[n] == 0 || k[n] == '<');
+}
 
 template <typename T>
 static inline int vl_reserve(vloam_b200_ctx* c, DBuf<T>& b, size_t n, bool keep = false) {

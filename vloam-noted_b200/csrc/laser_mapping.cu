@@ -825,6 +825,7 @@ int vl_lm_run(vloam_b200_ctx* c) {
   const int gsGrid = c->num_sms * 8;
   VL_TRY(vl_reserve(c, c->fromMapC, (size_t)max(d->hMapUpperC, 1LL)));
   VL_TRY(vl_reserve(c, c->fromMapS, (size_t)max(d->hMapUpperS, 1LL)));
+  VL_BYTES(32.0 * (double)(d->hMapUpperC + d->hMapUpperS));  // upper bound until the S2 sync; refined below
   VL_LAUNCH(lm_gather, gsGrid, 256, 0, c->lmm, d->work, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, c->fromMapC.p, c->fromMapS.p);
   // LM.cpp:492-500: VoxelGrid of this frame's less-sharp / less-flat clouds
   VL_TRY(vl_reserve(c, c->stackC, (size_t)max(c->nCornerLast, 1)));
@@ -847,11 +848,15 @@ int vl_lm_run(vloam_b200_ctx* c) {
     VL_TRY(vl_reserve(c, d->sortedPts, (size_t)total));
     VL_CUDA(cudaMemsetAsync(d->cellCount, 0, sizeof(int) * (nCells + 1), c->stream));
     VL_CUDA(cudaMemsetAsync(d->cellFill, 0, sizeof(int) * (nCells + 1), c->stream));
+    VL_BYTES(24.0 * total);  // read point, write cell id, atomic on the cell counter
     VL_LAUNCH(lm_grid_count, gsGrid, 256, 0, c->lmm, d->work, c->fromMapC.p, c->fromMapS.p, d->cellCount, d->cellOfPoint.p);
     const int nTiles = vl_div_up(nCells, 1024);
+    VL_BYTES(4.0 * nCells);
     VL_LAUNCH(lm_scan_tiles, nTiles, 256, 0, d->cellCount, nCells, d->tileSum);
     VL_LAUNCH(lm_scan_sums, 1, 1024, 0, d->tileSum, nTiles);
+    VL_BYTES(8.0 * nCells);
     VL_LAUNCH(lm_scan_apply, nTiles, 256, 0, d->cellCount, nCells, d->tileSum, d->cellStart);
+    VL_BYTES(44.0 * total);  // read point + cell id + cell start, atomic, write sorted point
     VL_LAUNCH(lm_grid_fill, gsGrid, 256, 0, c->lmm, c->fromMapC.p, c->fromMapS.p, d->cellOfPoint.p, d->cellStart, d->cellFill, d->sortedPts.p);
     VL_TRY(vl_reserve(c, c->knnIdx, (size_t)nq * 5));
     VL_TRY(vl_reserve(c, c->knnD2, (size_t)nq * 5));
@@ -859,6 +864,7 @@ int vl_lm_run(vloam_b200_ctx* c) {
     VL_TRY(vl_reserve(c, c->factors, (size_t)nq * 10));
     VL_TRY(vl_reserve(c, c->factorValid, (size_t)nq));
     for (int pass = 0; pass < 2; ++pass) {  // LM.cpp:526
+      VL_BYTES(16.0 * nq * 6);  // query + 5 neighbours
       VL_LAUNCH(lm_knn_fit, vl_div_up((long long)nq * 32, 256), 256, 0, c->lmm, d->work, c->stackC.p, c->stackS.p, c->fromMapC.p,
                 c->fromMapS.p, d->cellStart, d->sortedPts.p, c->knnIdx.p, c->knnD2.p, c->knnOk.p, c->factors.p, c->factorValid.p);
       if (vl_debug_capture(c)) {
@@ -895,9 +901,11 @@ int vl_lm_run(vloam_b200_ctx* c) {
     VL_LAUNCH(rf_scan_layout, 1, 1024, 0, d->unmatched.p, c->lmm, d->work, c->cubeC, c->cubeS);
     VL_LAUNCH(rf_emit_new, vl_div_up(nKeys, 256), 256, 0, c->tailKeys.p, d->unmatched.p, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p,
               c->poolS.p, d->newPts.p, c->staging.p);
+    VL_BYTES(32.0 * (Mc + Ms));  // read every prefix point once, write it once to staging
     VL_LAUNCH(rf_emit_prefix, gsGrid, 256, 0, c->tailKeys.p, d->unmatched.p, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p,
               d->newPts.p, c->staging.p);
     VL_LAUNCH(rf_alloc, 1, 32, 0, c->lmm, d->work, c->cubeC, c->cubeS, (int)c->poolC.cap, (int)c->poolS.cap);
+    VL_BYTES(32.0 * (Mc + Ms + nq));  // staging -> pool copy
     VL_LAUNCH(rf_commit, gsGrid, 256, 0, c->staging.p, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p);
     VL_LAUNCH(rf_finish, 1, 256, 0, c->lmm, d->work, c->cubeC, c->cubeS);
     if (nq > 0)

@@ -136,7 +136,7 @@ void* vloam_synth_world_create(uint64_t seed, int kind, double extent) {
   w->zg = -1.8;
   const double pitch = kind == 0 ? 40.0 : 12.5;
   const double foot = kind == 0 ? 20.0 : 8.5;
-  const double hmin = kind == 0 ? 6.0 : (kind == 1 ? 20.0 : 60.0), hmax = kind == 0 ? 20.0 : (kind == 1 ? 62.0 : 110.0);
+  const double hmin = kind == 0 ? 6.0 : (kind == 1 ? 24.0 : 64.0), hmax = kind == 0 ? 20.0 : (kind == 1 ? 72.0 : 120.0);
   const double street_half = kind == 0 ? 8.0 : 3.0;
   for (double bx = -extent; bx < extent; bx += pitch)
     for (double by = -extent; by < extent; by += pitch) {
