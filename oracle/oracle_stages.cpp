@@ -42,7 +42,10 @@ void ScanRegistration::input(const float* xyz, int n, int stride) {  // SR.cpp:1
     in.push_back(x); in.push_back(y); in.push_back(z);
   }
   int cloudSize = (int)(in.size() / 3);
-  if (cloudSize == 0) return;  // the reference would index points[0]; defined here as "no output"
+  if (cloudSize == 0) {  // the reference would index points[0]; defined here as "no output"
+    for (int i = 0; i < N_SCANS; i++) { scanStartInd[i] = 5; scanEndInd[i] = -6; }  // what SR.cpp:308-315 yields for empty rings
+    return;
+  }
 
   // SR.cpp:183-197
   startOri = -atan2f(in[1], in[0]);

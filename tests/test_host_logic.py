@@ -19,9 +19,6 @@ def test_cubes_blob_layout_roundtrip(op, synth):
     assert o.get("lm.surfMap") == blob
     counts = synth.blob_counts(blob)
     cloud = np.frombuffer(blob[len(counts) * 4:], np.float32).reshape(-1, 4)
-    off = 0
-    for c in np.nonzero(counts)[0][:40]:
-        cube = cloud[off:off + counts[c]] if False else None
     # every cube is voxel-sorted and deduplicated: filtering it again is the identity
     off = 0
     checked = 0
