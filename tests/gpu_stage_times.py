@@ -6,7 +6,8 @@ sys.path.insert(0, ROOT)
 pkg = importlib.import_module("vloam-noted_b200")
 import bench
 import torch
-scans, traj, cb, sb = bench.make_sequence(pkg, 0, 40)
+N = int(os.environ.get('FRAMES', '40'))
+scans, traj, cb, sb = bench.make_sequence(pkg, 0, N)
 ctx = pkg.Context()
 ctx.set("lm.cornerMap", cb); ctx.set("lm.surfMap", sb)
 ctx.set_timing(True)
@@ -14,7 +15,7 @@ d = [torch.from_numpy(s).cuda() for s in scans]
 torch.cuda.synchronize()
 rows = []
 walls = []
-for k in range(40):
+for k in range(N):
     t0 = time.perf_counter()
     ctx.process_frame_device(d[k].data_ptr(), d[k].shape[0], 4)
     ctx.synchronize()
@@ -23,4 +24,6 @@ for k in range(40):
 rows = np.array(rows)[8:]
 print("stage ms median SR/LO/LM:", np.median(rows, 0).round(3), "sum", np.median(rows.sum(1)).round(3), "wall median", np.median(walls[8:]).round(3))
 print("stage ms mean   SR/LO/LM:", rows.mean(0).round(3))
-print("launches/frame", ctx.kernel_launches / 40)
+print("launches/frame", ctx.kernel_launches / N)
+allr = np.array(walls)
+print("wall ms per frame:", " ".join("%.1f" % v for v in allr))

@@ -336,3 +336,30 @@ def test_cpp_adapter_classes(pkg, op, synth, street, tmp_path):
     assert int(last[3]) == len(o.get("sr.laserCloud")) and int(last[5]) == len(o.get("sr.sharp")) and int(last[11]) == len(o.get("sr.lessFlat"))
     odom = np.array([float(v) for v in last[14:17]]); mapped = np.array([float(v) for v in last[19:22]])
     assert np.abs(odom - o.get("lo.pose")[4:7]).max() < POS_TOL and np.abs(mapped - o.get("lm.pose")[4:7]).max() < POS_TOL
+
+
+def test_lo_association_non_monotone_rings(pkg, op, synth, street):
+    """int(intensity) of the last clouds made non-monotone on purpose (what a negative relTime does,
+    SURVEY 7.2 item 3): the scans must still stop exactly where the reference's `break`s do."""
+    rng = np.random.RandomState(5)
+    traj = synth.trajectory(2)
+    o, g = op.Oracle(**KW[1]), pkg.Context(**KW[1])
+    for k in range(2):
+        scan = street.scan(1, traj[k], 1000 + k)
+        o.scan_registration(scan); g.begin_frame(); g.scan_registration(scan)
+        if k == 0:
+            o.laser_odometry(); g.laser_odometry()
+    corner, surf = o.get("lo.cornerLast").copy(), o.get("lo.surfLast").copy()
+    for cl in (corner, surf):
+        glitch = rng.rand(len(cl)) < 0.02
+        cl[glitch, 3] -= 1.0                       # ring - 1 in the middle of ring's block
+        cl[rng.rand(len(cl)) < 0.002, 3] += 3.0    # and a few early `break` triggers
+        cl[:, 3] = np.maximum(cl[:, 3], 0.0)
+    o.set_last(corner, surf); g.set_last(corner, surf)
+    x = np.array([0.0, 0.0, 0.002, 1.0, 0.9, 0.01, 0.0])
+    x[:4] /= np.linalg.norm(x[:4])
+    co, so = o.lo_associate(x)
+    cg_, sg = g.lo_associate(x)
+    assert_bits_equal(co, cg_, "corner association"); assert_bits_equal(so, sg, "surf association")
+    assert (so[:, 2] >= 0).sum() > 100
+    g.close()

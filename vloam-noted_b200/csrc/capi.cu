@@ -63,6 +63,7 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   LoScalars hl; memset(&hl, 0, sizeof hl); hl.para_q[3] = 1.0; hl.q_w[3] = 1.0;  // LO.cpp:81-91
   VL_CUDA_CREATE(cudaMemcpy(c->los, &hl, sizeof hl, cudaMemcpyHostToDevice));
   *c->h_los = hl;
+  VL_CUDA_CREATE(cudaMalloc(&c->loRingTbl, sizeof(int) * 2 * 160));
   VL_CUDA_CREATE(cudaMalloc(&c->evalOut, sizeof(EvalOut)));
   VL_CUDA_CREATE(cudaMalloc(&c->lms, sizeof(LmSolveState)));
   VL_CUDA_CREATE(cudaMemset(c->lms, 0, sizeof(LmSolveState)));

@@ -124,6 +124,7 @@ struct vloam_b200_ctx {
   int nCornerLast, nSurfLast;  // host counts of the "last" clouds (= other buffer of the pair)
   bool lo_inited; int lo_frameCount;
   float4* cornerLastPtr; float4* surfLastPtr;  // after solveLO's swap
+  int* loRingTbl;                     // 2 x (144 + 1) ints: ring-value -> first index tables of the last clouds
   DBuf<int> loCornerIdx, loSurfIdx;   // association results (2 / 3 ints per query)
   DBuf<double> factors;               // 10 doubles per factor slot
   DBuf<int> factorValid;
@@ -206,9 +207,12 @@ static inline bool vl_prof_match(const vloam_b200_ctx* c, const char* k) {
   return strncmp(c->prof_name, k, n) == 0 && (k[n] == 0 || k[n] == '<');
 }
 
+// Grows (never shrinks).  cudaMalloc / cudaFree stall the stream for milliseconds, so buffers whose
+// size follows the map ask for `slack` extra elements: growth then happens once per ~hundreds of frames.
 template <typename T>
-static inline int vl_reserve(vloam_b200_ctx* c, DBuf<T>& b, size_t n, bool keep = false) {
+static inline int vl_reserve(vloam_b200_ctx* c, DBuf<T>& b, size_t n, bool keep = false, size_t slack = 0) {
   if (n <= b.cap) return VLOAM_OK;
+  n += slack;
   size_t ncap = b.cap ? b.cap : 1024;
   while (ncap < n) ncap *= 2;
   T* np = nullptr;

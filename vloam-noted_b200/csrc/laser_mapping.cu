@@ -719,38 +719,81 @@ __global__ void rf_finish(LmScalars* __restrict__ s, const RfWork* __restrict__ 
 }
 
 // Points that land in a cube outside the 5x5x3 window are appended raw, in stack order (LM.cpp:762, 786).
+// One CTA walks the stacks in chunks of 1024: outside points are compacted in order, ranked among
+// the points of the same (kind, cube) inside the chunk, cube storage is grown where needed, and every
+// point is written to count + rank.  The common case (no outside point at all) is one pass of flags.
 __global__ void __launch_bounds__(1024) rf_append_outside(LmScalars* __restrict__ s, const float4* __restrict__ newPts,
                                                           const int* __restrict__ newCube, MapCubeTable* __restrict__ tc,
                                                           MapCubeTable* __restrict__ ts, float4* __restrict__ poolC, float4* __restrict__ poolS,
                                                           int poolCapC, int poolCapS) {
   const int Qc = s->Qc, total = s->Qc + s->Qs;
-  __shared__ int sNewStart, sOldStart, sCopy;
+  __shared__ int lIdx[1024], lKey[1024], lRank[1024], lTot[1024];
+  __shared__ int gKey[1024], gOld[1024], gNew[1024], gCnt[1024];
+  __shared__ int warpSum[32];
+  __shared__ int nGrow;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int any = 0;
+  for (int i = threadIdx.x; i < total; i += 1024) any |= (newCube[i] >= 0);
+  if (__syncthreads_or(any) == 0) return;
   for (int base = 0; base < total; base += 1024) {
     const int i = base + threadIdx.x;
     const int cb = i < total ? newCube[i] : -1;
-    if (__syncthreads_or(cb >= 0) == 0) continue;
-    // rare path: serialise the chunk in stack order
-    for (int k = 0; k < 1024 && base + k < total; ++k) {
-      const int cbk = newCube[base + k];
-      if (cbk < 0) continue;
-      const int kind = (base + k) >= Qc;
-      MapCubeTable* tb = kind ? ts : tc;
-      float4* pool = kind ? poolS : poolC;
-      if (threadIdx.x == 0) {
-        sCopy = 0;
-        if (tb->count[cbk] + 1 > tb->cap[cbk]) {
-          const int ncap = max(2 * (tb->count[cbk] + 1), 256);
-          int& top = kind ? s->poolTopS : s->poolTopC;
-          if (top + ncap > (kind ? poolCapS : poolCapC)) { s->overflow = 1; sCopy = -1; }
-          else { sOldStart = tb->start[cbk]; sNewStart = top; top += ncap; tb->start[cbk] = sNewStart; tb->cap[cbk] = ncap; sCopy = 1; }
-        }
+    const bool f = cb >= 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) warpSum[warp] = __popc(bal);
+    if (threadIdx.x == 0) nGrow = 0;
+    __syncthreads();
+    int before = 0, n = 0;
+    for (int w = 0; w < 32; ++w) { const int v = warpSum[w]; if (w < warp) before += v; n += v; }
+    if (f) { const int pos = before + __popc(bal & ((1u << lane) - 1u)); lIdx[pos] = i; lKey[pos] = (i >= Qc ? VL_CUBE_NUM : 0) + cb; }
+    __syncthreads();
+    if (n == 0) continue;
+    // rank inside the chunk among entries of the same (kind, cube); the first one is the leader
+    const int e = threadIdx.x;
+    int key = -1, rank = 0, tot = 0;
+    if (e < n) {
+      key = lKey[e];
+      for (int q = 0; q < n; ++q) { const bool same = lKey[q] == key; rank += (same && q < e); tot += same; }
+      lRank[e] = rank; lTot[e] = tot;
+      if (rank == 0) {
+        const int kind = key >= VL_CUBE_NUM, c2 = key - kind * VL_CUBE_NUM;
+        const MapCubeTable* tb = kind ? ts : tc;
+        if (tb->count[c2] + tot > tb->cap[c2]) { const int g = atomicAdd(&nGrow, 1); gKey[g] = key; gCnt[g] = tb->count[c2] + tot; }
       }
-      __syncthreads();
-      if (sCopy == 1) for (int q = threadIdx.x; q < tb->count[cbk]; q += 1024) pool[sNewStart + q] = pool[sOldStart + q];
-      __syncthreads();
-      if (threadIdx.x == 0 && sCopy >= 0) { pool[tb->start[cbk] + tb->count[cbk]] = newPts[base + k]; tb->count[cbk]++; }
-      __syncthreads();
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int g = 0; g < nGrow; ++g) {
+        const int kind = gKey[g] >= VL_CUBE_NUM, c2 = gKey[g] - kind * VL_CUBE_NUM;
+        MapCubeTable* tb = kind ? ts : tc;
+        const int ncap = max(2 * gCnt[g], 256);
+        int& top = kind ? s->poolTopS : s->poolTopC;
+        gOld[g] = tb->start[c2];
+        if (top + ncap > (kind ? poolCapS : poolCapC)) { s->overflow = 1; gNew[g] = -1; continue; }
+        gNew[g] = top; tb->start[c2] = top; tb->cap[c2] = ncap; top += ncap;
+      }
+    }
+    __syncthreads();
+    for (int g = 0; g < nGrow; ++g) {
+      if (gNew[g] < 0) continue;
+      const int kind = gKey[g] >= VL_CUBE_NUM, c2 = gKey[g] - kind * VL_CUBE_NUM;
+      float4* pool = kind ? poolS : poolC;
+      const int cnt = (kind ? ts : tc)->count[c2];
+      for (int q = threadIdx.x; q < cnt; q += 1024) pool[gNew[g] + q] = pool[gOld[g] + q];
+    }
+    __syncthreads();
+    if (e < n) {
+      const int kind = key >= VL_CUBE_NUM, c2 = key - kind * VL_CUBE_NUM;
+      MapCubeTable* tb = kind ? ts : tc;
+      if (tb->count[c2] + tot <= tb->cap[c2]) (kind ? poolS : poolC)[tb->start[c2] + tb->count[c2] + rank] = newPts[lIdx[e]];
+    }
+    __syncthreads();
+    if (e < n && rank == 0) {
+      const int kind = key >= VL_CUBE_NUM, c2 = key - kind * VL_CUBE_NUM;
+      MapCubeTable* tb = kind ? ts : tc;
+      if (tb->count[c2] + tot <= tb->cap[c2]) tb->count[c2] += tot;
+    }
+    __syncthreads();
   }
 }
 
@@ -823,8 +866,8 @@ int vl_lm_run(vloam_b200_ctx* c) {
   VL_LAUNCH(lm_prepare, 1, 1024, 0, c->lmm, c->los, c->cubeC, c->cubeS, d->work, skip);
   if (skip) { VL_CUDA(cudaGetLastError()); return VLOAM_OK; }
   const int gsGrid = c->num_sms * 8;
-  VL_TRY(vl_reserve(c, c->fromMapC, (size_t)max(d->hMapUpperC, 1LL)));
-  VL_TRY(vl_reserve(c, c->fromMapS, (size_t)max(d->hMapUpperS, 1LL)));
+  VL_TRY(vl_reserve(c, c->fromMapC, (size_t)max(d->hMapUpperC, 1LL), false, (size_t)d->hMapUpperC / 2 + (1 << 20)));
+  VL_TRY(vl_reserve(c, c->fromMapS, (size_t)max(d->hMapUpperS, 1LL), false, (size_t)d->hMapUpperS / 2 + (1 << 20)));
   VL_BYTES(32.0 * (double)(d->hMapUpperC + d->hMapUpperS));  // upper bound until the S2 sync; refined below
   VL_LAUNCH(lm_gather, gsGrid, 256, 0, c->lmm, d->work, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, c->fromMapC.p, c->fromMapS.p);
   // LM.cpp:492-500: VoxelGrid of this frame's less-sharp / less-flat clouds
@@ -844,8 +887,8 @@ int vl_lm_run(vloam_b200_ctx* c) {
     optimized = true;
     const int total = Mc + Ms;
     const int nCells = 2 * LM_NCELL;
-    VL_TRY(vl_reserve(c, d->cellOfPoint, (size_t)total));
-    VL_TRY(vl_reserve(c, d->sortedPts, (size_t)total));
+    VL_TRY(vl_reserve(c, d->cellOfPoint, (size_t)total, false, (size_t)total / 2 + (1 << 20)));
+    VL_TRY(vl_reserve(c, d->sortedPts, (size_t)total, false, (size_t)total / 2 + (1 << 20)));
     VL_CUDA(cudaMemsetAsync(d->cellCount, 0, sizeof(int) * (nCells + 1), c->stream));
     VL_CUDA(cudaMemsetAsync(d->cellFill, 0, sizeof(int) * (nCells + 1), c->stream));
     VL_BYTES(24.0 * total);  // read point, write cell id, atomic on the cell counter
@@ -888,11 +931,11 @@ int vl_lm_run(vloam_b200_ctx* c) {
   const int nKeys = tailTotal + nq;
   if (nKeys > 0) {
     int P = 2; while (P < nKeys) P <<= 1;
-    VL_TRY(vl_reserve(c, c->tailKeys, (size_t)P));
+    VL_TRY(vl_reserve(c, c->tailKeys, (size_t)P, false, (size_t)P));
     VL_TRY(vl_reserve(c, d->newPts, (size_t)max(nq, 1)));
     VL_TRY(vl_reserve(c, d->newCube, (size_t)max(nq, 1)));
-    VL_TRY(vl_reserve(c, d->unmatched, (size_t)nKeys + 2));
-    VL_TRY(vl_reserve(c, c->staging, (size_t)Mc + Ms + nKeys + 1));
+    VL_TRY(vl_reserve(c, d->unmatched, (size_t)nKeys + 2, false, (size_t)nKeys + (1 << 16)));
+    VL_TRY(vl_reserve(c, c->staging, (size_t)Mc + Ms + nKeys + 1, false, (size_t)(Mc + Ms) / 2 + (1 << 20)));
     VL_LAUNCH(rf_keys, vl_div_up(P, 256), 256, 0, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, c->stackC.p, c->stackS.p,
               d->newPts.p, d->newCube.p, c->tailKeys.p, P);
     VL_TRY(vl_sort_u64(c, c->tailKeys.p, P));

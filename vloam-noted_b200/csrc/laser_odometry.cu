@@ -39,9 +39,38 @@ __device__ __forceinline__ float lo_sqdis(const float4 t, float sx, float sy, fl
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+#define LO_TBL 144  // ring-value table: first index whose int(intensity) >= v, v in [0, LO_TBL)
+
+// int(intensity) is the ring id and the "last" clouds are ring-major, so the `break` positions of
+// the reference's scans are table look-ups -- provided the sequence really is non-decreasing.  This
+// kernel builds the table and verifies that; a cloud that fails the check (a negative relTime makes
+// int(intensity) = ring - 1) takes the ballot path that assumes nothing.
+// tbl layout per cloud: [0, LO_TBL) first-index table, [LO_TBL] = 1 if monotone.
+__global__ void __launch_bounds__(256) lo_ring_table(const float4* __restrict__ corner, int nc, const float4* __restrict__ surf, int ns,
+                                                     int* __restrict__ tbl) {
+  const int which = blockIdx.y;
+  const float4* cl = which ? surf : corner;
+  const int n = which ? ns : nc;
+  int* t = tbl + which * (LO_TBL + 1);
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n == 0) { if (j <= LO_TBL) t[j] = j == LO_TBL ? 1 : 0; return; }
+  if (j >= n) return;
+  const int v = min(max((int)cl[j].w, 0), LO_TBL - 1);
+  const int raw = (int)cl[j].w;
+  if (j == 0) { for (int q = 0; q <= v; ++q) t[q] = 0; }
+  else {
+    const int rawp = (int)cl[j - 1].w;
+    const int vp = min(max(rawp, 0), LO_TBL - 1);
+    if (raw < rawp || raw < 0) t[LO_TBL] = 0;  // not monotone (or negative): table unusable
+    for (int q = vp + 1; q <= v; ++q) t[q] = j;
+  }
+  if (j == n - 1) for (int q = v + 1; q < LO_TBL; ++q) t[q] = n;
+}
+__global__ void lo_ring_table_init(int* __restrict__ tbl) { if (threadIdx.x < 2) tbl[threadIdx.x * (LO_TBL + 1) + LO_TBL] = 1; }
+
 template <bool SURF>
 __global__ void __launch_bounds__(LO_QPB * 32) lo_assoc(const float4* __restrict__ query, int nq, const float4* __restrict__ target, int nt,
-                                                        const double* __restrict__ pose, int* __restrict__ outIdx,
+                                                        const double* __restrict__ pose, const int* __restrict__ tbl, int* __restrict__ outIdx,
                                                         double* __restrict__ factors, int* __restrict__ valid, int slotBase) {
   __shared__ float sq[LO_QPB][3];
   __shared__ Best sbest[LO_QPB][LO_QPB];
@@ -64,6 +93,7 @@ __global__ void __launch_bounds__(LO_QPB * 32) lo_assoc(const float4* __restrict
   Best b[LO_QPB];
 #pragma unroll
   for (int k = 0; k < LO_QPB; ++k) { qx[k] = sq[k][0]; qy[k] = sq[k][1]; qz[k] = sq[k][2]; b[k].d = 3.0e38f; b[k].j = -1; }
+#pragma unroll 4
   for (int j = threadIdx.x; j < nt; j += LO_QPB * 32) {
     const float4 t = __ldg(&target[j]);
 #pragma unroll
@@ -91,6 +121,32 @@ __global__ void __launch_bounds__(LO_QPB * 32) lo_assoc(const float4* __restrict
     closest = nn.j;
     const int id = (int)target[closest].w;  // closestPointScanID
     Best f2{25.0f, -1}, f3{25.0f, -1};
+    Best g2{25.0f, -1}, g3{25.0f, -1};
+    if (tbl[LO_TBL]) {
+      // monotone ring values: the scans stop at table positions, every point in between is visited
+      const int F = tbl[min(id + 3, LO_TBL - 1)];            // first j with int(intensity) >= id + 3  (> id + 2.5)
+      const int Bq = id - 2 <= 0 ? 0 : tbl[min(id - 2, LO_TBL - 1)];  // points below it have int(intensity) <= id - 3
+#pragma unroll 4
+      for (int j = closest + 1 + lane; j < F; j += 32) {   // LO.cpp:309-331, 407-430
+        const float4 t = __ldg(&target[j]);
+        const int v = (int)t.w;
+        const float d = lo_sqdis(t, sx, sy, sz);
+        if (SURF) {
+          if (v <= id) { if (d < f2.d) { f2.d = d; f2.j = j; } }
+          else if (d < f3.d) { f3.d = d; f3.j = j; }
+        } else if (v > id) { if (d < f2.d) { f2.d = d; f2.j = j; } }
+      }
+#pragma unroll 4
+      for (int j = closest - 1 - lane; j >= Bq; j -= 32) {  // LO.cpp:334-355, 433-456
+        const float4 t = __ldg(&target[j]);
+        const int v = (int)t.w;
+        const float d = lo_sqdis(t, sx, sy, sz);
+        if (SURF) {
+          if (v >= id) { if (d < g2.d) { g2.d = d; g2.j = j; } }
+          else if (d < g3.d) { g3.d = d; g3.j = j; }
+        } else if (v < id) { if (d < g2.d) { g2.d = d; g2.j = j; } }
+      }
+    } else {
     // forward: j = closest+1 .. ; break at the first int(intensity) > id + 2.5 (LO.cpp:309-331, 407-430)
     for (int base = closest + 1; base < nt; base += 128) {
       bool stop = false;
@@ -114,10 +170,7 @@ __global__ void __launch_bounds__(LO_QPB * 32) lo_assoc(const float4* __restrict
       }
       if (stop) break;
     }
-    f2 = warp_best(f2, true);
-    if (SURF) f3 = warp_best(f3, true);
     // backward: j = closest-1 .. 0 ; break at the first int(intensity) < id - 2.5 (LO.cpp:334-355, 433-456)
-    Best g2{25.0f, -1}, g3{25.0f, -1};
     for (int base = closest - 1; base >= 0; base -= 128) {
       bool stop = false;
 #pragma unroll
@@ -140,8 +193,10 @@ __global__ void __launch_bounds__(LO_QPB * 32) lo_assoc(const float4* __restrict
       }
       if (stop) break;
     }
+    }
+    f2 = warp_best(f2, true);
     g2 = warp_best(g2, false);
-    if (SURF) g3 = warp_best(g3, false);
+    if (SURF) { f3 = warp_best(f3, true); g3 = warp_best(g3, false); }
     // forward candidates were visited first: backward wins only when strictly nearer
     ind2 = (g2.j >= 0 && g2.d < f2.d) ? g2.j : f2.j;
     if (ind2 < 0 && g2.j >= 0) ind2 = g2.j;
@@ -192,6 +247,12 @@ __global__ void lo_set_prior(LoScalars* s, const double* __restrict__ prior) {  
   else if (threadIdx.x < 7) s->para_t[threadIdx.x - 4] = prior[threadIdx.x];
 }
 
+static int lo_ring_tables(vloam_b200_ctx* c, const float4* cornerLast, int nCL, const float4* surfLast, int nSL) {
+  VL_LAUNCH(lo_ring_table_init, 1, 32, 0, c->loRingTbl);
+  VL_LAUNCH(lo_ring_table, dim3(vl_div_up(max(max(nCL, nSL), LO_TBL + 1), 256), 2), 256, 0, cornerLast, nCL, surfLast, nSL, c->loRingTbl);
+  return VLOAM_OK;
+}
+
 static int lo_associate(vloam_b200_ctx* c, const double* d_pose, const float4* cornerLast, int nCL, const float4* surfLast, int nSL) {
   const int nS = c->nSharp, nF = c->nFlat;
   VL_TRY(vl_reserve(c, c->loCornerIdx, (size_t)max(nS, 1) * 2));
@@ -199,10 +260,10 @@ static int lo_associate(vloam_b200_ctx* c, const double* d_pose, const float4* c
   VL_TRY(vl_reserve(c, c->factors, (size_t)max(nS + nF, 1) * 10));
   VL_TRY(vl_reserve(c, c->factorValid, (size_t)max(nS + nF, 1)));
   if (nS > 0)
-    VL_LAUNCH(lo_assoc<false>, vl_div_up(nS, LO_QPB), LO_QPB * 32, 0, c->sharp.p, nS, cornerLast, nCL, d_pose, c->loCornerIdx.p,
+    VL_LAUNCH(lo_assoc<false>, vl_div_up(nS, LO_QPB), LO_QPB * 32, 0, c->sharp.p, nS, cornerLast, nCL, d_pose, c->loRingTbl, c->loCornerIdx.p,
               c->factors.p, c->factorValid.p, 0);
   if (nF > 0)
-    VL_LAUNCH(lo_assoc<true>, vl_div_up(nF, LO_QPB), LO_QPB * 32, 0, c->flat.p, nF, surfLast, nSL, d_pose, c->loSurfIdx.p,
+    VL_LAUNCH(lo_assoc<true>, vl_div_up(nF, LO_QPB), LO_QPB * 32, 0, c->flat.p, nF, surfLast, nSL, d_pose, c->loRingTbl + (LO_TBL + 1), c->loSurfIdx.p,
               c->factors.p, c->factorValid.p, nS);
   VL_CUDA(cudaGetLastError());
   return VLOAM_OK;
@@ -221,6 +282,7 @@ int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, i
       VL_CUDA(cudaMemcpyAsync(d_prior, h, sizeof h, cudaMemcpyHostToDevice, c->stream));
       VL_CUDA(cudaStreamSynchronize(c->stream));  // h is a stack buffer
     }
+    VL_TRY(lo_ring_tables(c, cornerLast, c->nCornerLast, surfLast, c->nSurfLast));
     for (int pass = 0; pass < 2; ++pass) {  // LO.cpp:224
       if (use_prior) VL_LAUNCH(lo_set_prior, 1, 32, 0, c->los, d_prior);
       VL_TRY(lo_associate(c, d_pose, cornerLast, c->nCornerLast, surfLast, c->nSurfLast));
@@ -250,6 +312,7 @@ int vl_lo_associate_only(vloam_b200_ctx* c, const double* x, int* corner_idx, in
   double* d_x = reinterpret_cast<double*>(c->vScalars + 32);
   VL_CUDA(cudaMemcpyAsync(d_x, x, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   VL_CUDA(cudaStreamSynchronize(c->stream));
+  VL_TRY(lo_ring_tables(c, c->cornerLastPtr, c->nCornerLast, c->surfLastPtr, c->nSurfLast));
   VL_TRY(lo_associate(c, d_x, c->cornerLastPtr, c->nCornerLast, c->surfLastPtr, c->nSurfLast));
   if (corner_idx && c->nSharp) VL_CUDA(cudaMemcpyAsync(corner_idx, c->loCornerIdx.p, sizeof(int) * 2 * c->nSharp, cudaMemcpyDeviceToHost, c->stream));
   if (surf_idx && c->nFlat) VL_CUDA(cudaMemcpyAsync(surf_idx, c->loSurfIdx.p, sizeof(int) * 3 * c->nFlat, cudaMemcpyDeviceToHost, c->stream));

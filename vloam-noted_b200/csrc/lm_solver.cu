@@ -11,7 +11,10 @@
 // tolerances) in one thread, leaving the next candidate in the state struct.  The host
 // never sees the 6x6 system; it only queues 1 + 4 evaluation kernels per solve.
 #include <float.h>
+#include <cooperative_groups.h>
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 #define LM_BLOCK 256
 #define LM_MAX_BLOCKS 512
@@ -246,6 +249,101 @@ __global__ void __launch_bounds__(LM_BLOCK) lm_eval(const double* __restrict__ f
   }
 }
 
+
+// ---- the whole ceres::Solve in ONE launch: a thread-block cluster keeps the iterate on chip ----
+// 8 CTAs (one cluster) evaluate the factors; per-CTA partial sums stay in shared memory and CTA 0
+// adds them through distributed shared memory in rank order (deterministic), runs the trust-region
+// bookkeeping and publishes the next evaluation point in its own shared memory, which the other
+// CTAs read back through DSMEM.  Two cluster barriers per evaluation replace the kernel boundary
+// (and the global-memory round trip) of the lm_eval chain: 1 launch instead of 7 per solve.
+#define LMC_CTAS 8
+#define LMC_THREADS 256
+
+__global__ void __cluster_dims__(LMC_CTAS, 1, 1) __launch_bounds__(LMC_THREADS)
+lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ valid, int nslots, double* __restrict__ x_inout,
+                 LmSolveState* __restrict__ st_out) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank();
+  __shared__ double part[28];
+  __shared__ double xs[8];
+  __shared__ int sdone;
+  __shared__ double total[28];
+  __shared__ LmSolveState st;
+  __shared__ double red[LMC_THREADS / 32][28];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (rank == 0 && threadIdx.x == 0) {
+    for (int k = 0; k < 7; ++k) { st.x[k] = x_inout[k]; st.xc[k] = x_inout[k]; st.best[k] = x_inout[k]; xs[k] = x_inout[k]; }
+    st.iter = 0; st.done = 0; st.nfactors = nslots; st.initial_cost = 0; st.final_cost = 0; st.cost = 0; st.min_cost = 0;
+    sdone = 0;
+  }
+  cluster.sync();
+  const double* xsrc = cluster.map_shared_rank(xs, 0);
+  const int* dsrc = cluster.map_shared_rank(&sdone, 0);
+  for (int it = 0; it < 5; ++it) {
+    if (*dsrc) break;  // uniform over the cluster: written before the last barrier
+    double x[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) x[k] = xsrc[k];
+    double acc[28];
+#pragma unroll
+    for (int k = 0; k < 28; ++k) acc[k] = 0.0;
+    for (int i = rank * LMC_THREADS + threadIdx.x; i < nslots; i += LMC_CTAS * LMC_THREADS) {
+      if (!valid[i]) continue;
+      FactorRow fr;
+      lm_factor(factors + (size_t)i * 10, x, fr);
+      double s = 0;
+      for (int k = 0; k < fr.nr; ++k) s += fr.r[k] * fr.r[k];
+      double rho0, rho1;  // ceres::HuberLoss(0.1)
+      if (s > 0.01) { const double r = sqrt(s); rho0 = 2.0 * 0.1 * r - 0.01; rho1 = fmax(DBL_MIN, 0.1 / r); }
+      else { rho0 = s; rho1 = 1.0; }
+      acc[27] += 0.5 * rho0;
+      for (int k = 0; k < fr.nr; ++k) {
+        int t = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          const double wa = rho1 * fr.J[k][a];
+#pragma unroll
+          for (int b = a; b < 6; ++b) acc[t++] += wa * fr.J[k][b];
+          acc[21 + a] += wa * fr.r[k];
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 28; ++k) {
+      double v = acc[k];
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+      if (lane == 0) red[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 28) {
+      double v = 0;
+      for (int w = 0; w < LMC_THREADS / 32; ++w) v += red[w][threadIdx.x];
+      part[threadIdx.x] = v;
+    }
+    cluster.sync();  // every CTA's partial is visible cluster-wide
+    if (rank == 0) {
+      if (threadIdx.x < 28) {
+        double v = 0;
+        for (unsigned r = 0; r < LMC_CTAS; ++r) v += cluster.map_shared_rank(part, r)[threadIdx.x];
+        total[threadIdx.x] = v;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        lm_logic(&st, total);
+        for (int k = 0; k < 7; ++k) xs[k] = st.xc[k];
+        sdone = st.done;
+      }
+    }
+    cluster.sync();  // the next evaluation point / done flag is published
+  }
+  cluster.sync();  // nobody may exit while another CTA can still read its shared memory (the done flag lives in CTA 0)
+  if (rank == 0 && threadIdx.x == 0) {
+    for (int k = 0; k < 7; ++k) x_inout[k] = st.best[k];
+    st.final_cost = st.min_cost;
+    if (st_out) *st_out = st;
+  }
+}
+
 __global__ void lm_begin(LmSolveState* st, const double* __restrict__ x, int nfactorsHint) {
   if (threadIdx.x != 0) return;
   for (int k = 0; k < 7; ++k) { st->x[k] = x[k]; st->xc[k] = x[k]; st->best[k] = x[k]; }
@@ -262,13 +360,8 @@ __global__ void lm_end(LmSolveState* st, double* __restrict__ x, const int* __re
 
 int vl_solve(vloam_b200_ctx* c, int nslots, double* d_x_inout, double* costs2) {
   if (nslots > 0) {
-    const int nb = min(vl_div_up(nslots, LM_BLOCK), LM_MAX_BLOCKS);
-    VL_TRY(vl_reserve(c, c->evalPartials, LM_MAX_BLOCKS));
-    unsigned int* counter = reinterpret_cast<unsigned int*>(c->vScalars + 60);
-    VL_LAUNCH(lm_begin, 1, 32, 0, c->lms, d_x_inout, nslots);
-    for (int it = 0; it < 5; ++it)
-      VL_LAUNCH(lm_eval, nb, LM_BLOCK, 0, c->factors.p, c->factorValid.p, nslots, c->lms, nullptr, c->evalPartials.p, c->evalOut, counter, 0);
-    VL_LAUNCH(lm_end, 1, 32, 0, c->lms, d_x_inout, c->factorValid.p, nslots);
+    VL_BYTES(84.0 * nslots * 5);
+    VL_LAUNCH(lm_solve_cluster, LMC_CTAS, LMC_THREADS, 0, c->factors.p, c->factorValid.p, nslots, d_x_inout, costs2 ? c->lms : nullptr);
     VL_CUDA(cudaGetLastError());
   }
   if (costs2) {

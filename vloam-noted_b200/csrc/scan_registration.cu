@@ -252,16 +252,17 @@ __device__ __forceinline__ float sr_gap2(const float4* __restrict__ cloud, int a
 }
 
 // Mark ind and its +-5 neighbours until a gap > 0.05 (SR.cpp:403-429); warp-cooperative.
-__device__ __forceinline__ void sr_mark(const float4* __restrict__ cloud, unsigned char* pk, int ringBase, int ind, int lane) {
+// gb[k] (ring-local) = squared gap between points k and k-1 exceeds 0.05, precomputed for the ring.
+__device__ __forceinline__ void sr_mark(const unsigned char* gb, unsigned char* pk, int loc, int lane) {
   bool brk = false;
-  if (lane < 5) { const int l = lane + 1; brk = (double)sr_gap2(cloud, ind + l, ind + l - 1) > 0.05; }
-  else if (lane < 10) { const int l = -(lane - 4); brk = (double)sr_gap2(cloud, ind + l, ind + l + 1) > 0.05; }
+  if (lane < 5) brk = gb[loc + lane + 1] != 0;            // l = lane+1: gap(ind+l, ind+l-1)
+  else if (lane < 10) brk = gb[loc - (lane - 4) + 1] != 0;  // l = -(lane-4): gap(ind+l, ind+l+1)
   const unsigned bb = __ballot_sync(0xffffffffu, brk);
   const unsigned f = bb & 31u, w = (bb >> 5) & 31u;
   const int nf = f ? __ffs(f) - 1 : 5, nb = w ? __ffs(w) - 1 : 5;
-  if (lane == 0) pk[ind - ringBase] = 1;
-  if (lane < nf) pk[ind + lane + 1 - ringBase] = 1;
-  if (lane >= 5 && lane - 5 < nb) pk[ind - (lane - 4) - ringBase] = 1;
+  if (lane == 0) pk[loc] = 1;
+  if (lane < nf) pk[loc + lane + 1] = 1;
+  if (lane >= 5 && lane - 5 < nb) pk[loc - (lane - 4)] = 1;
   __syncwarp();
 }
 
@@ -273,7 +274,7 @@ __device__ __forceinline__ int sr_ep(int start, int end, int j) { return start +
 // warp 0 walks the sectors in order because +-5 marks spill into the next sector.
 __global__ void __launch_bounds__(SR_BLOCK) sr_pick(const float4* __restrict__ cloud, const float* __restrict__ curv,
                                                     int* __restrict__ label, unsigned char* __restrict__ pickedG,
-                                                    unsigned long long* __restrict__ scratch, const int* __restrict__ ringStart,
+                                                    unsigned char* __restrict__ gapG, unsigned long long* __restrict__ scratch, const int* __restrict__ ringStart,
                                                     const int* __restrict__ ringCount, int* __restrict__ provSharp,
                                                     int* __restrict__ provLess, int* __restrict__ provFlat, int* __restrict__ cntSharp,
                                                     int* __restrict__ cntLess, int* __restrict__ cntFlat) {
@@ -291,7 +292,11 @@ __global__ void __launch_bounds__(SR_BLOCK) sr_pick(const float4* __restrict__ c
   // sector j keys live at keys + j*P; the global fallback uses 2*count entries per ring (6P <= 12*len/6*... bounded by 2*rc+384)
   unsigned long long* keys = inSmem ? smem : scratch + (size_t)2 * rs + (size_t)r * 6 * 64;
   unsigned char* pk = (rc <= SR_RING_CAP) ? reinterpret_cast<unsigned char*>(smem + VL_SECTORS * SR_SECT_CAP) : pickedG + rs;
-  if (rc <= SR_RING_CAP) for (int t = threadIdx.x; t < rc; t += blockDim.x) pk[t] = 0;
+  unsigned char* gb = (rc <= SR_RING_CAP) ? pk + SR_RING_CAP : gapG + rs;
+  for (int t = threadIdx.x; t < rc; t += blockDim.x) {
+    pk[t] = 0;
+    gb[t] = (t > 0 && (double)sr_gap2(cloud, rs + t, rs + t - 1) > 0.05) ? 1 : 0;  // SR.cpp:408-411
+  }
   for (int t = threadIdx.x; t < VL_SECTORS * P; t += blockDim.x) {
     const int j = t / P, k = t - j * P;
     const int idx = sr_sp(start, end, j) + k;
@@ -344,7 +349,7 @@ __global__ void __launch_bounds__(SR_BLOCK) sr_pick(const float4* __restrict__ c
         else label[pind] = 1;
         provLess[slot * 20 + cnt - 1] = pind;
       }
-      sr_mark(cloud, pk, rs, pind, lane);
+      sr_mark(gb, pk, pind - rs, lane);
       pos = pos - first - 1;
     }
     if (lane == 0) { cntSharp[slot] = min(cnt, 2); cntLess[slot] = cnt; }
@@ -369,7 +374,7 @@ __global__ void __launch_bounds__(SR_BLOCK) sr_pick(const float4* __restrict__ c
       cnt++;
       if (lane == 0) { label[pind] = -1; provFlat[slot * 4 + cnt - 1] = pind; }
       if (cnt >= 4) break;
-      sr_mark(cloud, pk, rs, pind, lane);
+      sr_mark(gb, pk, pind - rs, lane);
       pos = pos + first + 1;
     }
     if (lane == 0) cntFlat[slot] = cnt;
@@ -579,7 +584,7 @@ int vl_sr_run(vloam_b200_ctx* c, const float* d_xyz, int n, int stride) {
   VL_TRY(vl_reserve(c, c->cloud, n));
   VL_TRY(vl_reserve(c, c->curv, n));
   VL_TRY(vl_reserve(c, c->label, n));
-  VL_TRY(vl_reserve(c, c->picked, n));
+  VL_TRY(vl_reserve(c, c->picked, (size_t)2 * n));
   VL_TRY(vl_reserve(c, c->sortScratch, (size_t)2 * n + (size_t)VL_MAX_RINGS * 6 * 64 + 64));
   VL_TRY(vl_reserve(c, c->lessFlatProv, n));
   VL_TRY(vl_reserve(c, c->selIdx, n));
@@ -597,13 +602,13 @@ int vl_sr_run(vloam_b200_ctx* c, const float* d_xyz, int n, int stride) {
   VL_LAUNCH(sr_scatter, numBlocks, SR_BLOCK, 0, d_xyz, n, stride, vec4, R, c->srs, c->ring.p, c->ori.p, c->blockHist.p, numBlocks,
             c->ringStart, c->cloud.p);
   VL_LAUNCH(sr_curvature, numBlocks, SR_BLOCK, 0, c->cloud.p, c->srs, c->curv.p, c->label.p, c->picked.p);
-  const size_t pickSmem = (size_t)VL_SECTORS * SR_SECT_CAP * sizeof(unsigned long long) + SR_RING_CAP;
+  const size_t pickSmem = (size_t)VL_SECTORS * SR_SECT_CAP * sizeof(unsigned long long) + 2 * SR_RING_CAP;
   static bool attrSet = false;
   if (!attrSet) {
     VL_CUDA(cudaFuncSetAttribute(sr_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pickSmem));
     attrSet = true;
   }
-  VL_LAUNCH(sr_pick, R, SR_BLOCK, pickSmem, c->cloud.p, c->curv.p, c->label.p, c->picked.p, c->sortScratch.p, c->ringStart, c->ringCount,
+  VL_LAUNCH(sr_pick, R, SR_BLOCK, pickSmem, c->cloud.p, c->curv.p, c->label.p, c->picked.p, c->picked.p + n, c->sortScratch.p, c->ringStart, c->ringCount,
             c->provSharp, c->provLess, c->provFlat, c->cntSharp, c->cntLess, c->cntFlat);
   VL_LAUNCH(sr_ring_voxel, R, SR_BLOCK, 0, c->cloud.p, c->label.p, c->ringStart, c->ringCount, c->selIdx.p, c->sortScratch.p,
             c->lessFlatProv.p, c->ringDsCount, 0.2f);
