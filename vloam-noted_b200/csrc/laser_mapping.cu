@@ -68,6 +68,24 @@ __device__ __forceinline__ unsigned lm_vox_key_cube(const float4 p, float inv, i
   return lm_vox_key(p, inv, ci, cj, ck, s->cenW, s->cenH, s->cenD);
 }
 
+// exclusive scan of one int per thread over the first 256 threads of the block (all threads must call)
+__device__ __forceinline__ int lm_scan256(int v, int* buf, int* total) {
+  const int t = threadIdx.x;
+  if (t < 256) buf[t] = v;
+  __syncthreads();
+  for (int d = 1; d < 256; d <<= 1) {
+    int u = 0;
+    if (t < 256 && t >= d) u = buf[t - d];
+    __syncthreads();
+    if (t < 256) buf[t] += u;
+    __syncthreads();
+  }
+  const int incl = t < 256 ? buf[t] : 0;
+  if (total) *total = buf[255];
+  __syncthreads();
+  return incl - v;
+}
+
 // ---- LaserMapping::input (LM.cpp:178-209) + centre cube / roll / valid list (LM.cpp:228-466)
 __global__ void __launch_bounds__(1024) lm_prepare(LmScalars* __restrict__ s, const LoScalars* __restrict__ lo, MapCubeTable* __restrict__ tc,
                                                    MapCubeTable* __restrict__ ts, RfWork* __restrict__ w, int skip) {
@@ -135,6 +153,8 @@ __global__ void __launch_bounds__(1024) lm_prepare(LmScalars* __restrict__ s, co
     }
   }
   for (int d = threadIdx.x; d < VL_CUBE_NUM; d += 1024) w->slotOfCube[d] = -1;
+  __shared__ int sbuf[256];
+  __shared__ int snv;
   __syncthreads();
   if (threadIdx.x == 0) {
     const int cI = center[0], cJ = center[1], cK = center[2];
@@ -145,34 +165,39 @@ __global__ void __launch_bounds__(1024) lm_prepare(LmScalars* __restrict__ s, co
           if (i >= 0 && i < VL_CUBE_W && j >= 0 && j < VL_CUBE_H && k >= 0 && k < VL_CUBE_D && nv < VL_MAX_VALID)
             s->validInd[nv++] = i + VL_CUBE_W * j + VL_CUBE_W * VL_CUBE_H * k;
     s->validNum = nv;
-    int mc = 0, ms = 0, tailAcc = 0, prefAcc = 0;
-    for (int q = 0; q < nv; ++q) {
-      const int cb = s->validInd[q];
-      w->slotOfCube[cb] = q;
-      w->gatherOff[0][q] = mc; w->gatherOff[1][q] = ms;
-      mc += tc->count[cb]; ms += ts->count[cb];
-    }
-    w->gatherOff[0][nv] = mc; w->gatherOff[1][nv] = ms;
-    s->Mc = mc; s->Ms = ms;
-    int tC = 0, tS = 0;
-    for (int kind = 0; kind < 2; ++kind)
-      for (int q = 0; q < VL_MAX_VALID; ++q) {
-        const int sg = kind * VL_MAX_VALID + q;
-        w->tailOff[sg] = tailAcc; w->prefOff[sg] = prefAcc;
-        if (q < nv) {
-          const MapCubeTable* t = kind ? ts : tc;
-          const int cb = s->validInd[q];
-          const int tl = t->count[cb] - t->sorted[cb];
-          tailAcc += tl; prefAcc += t->sorted[cb];
-          if (kind) tS += tl; else tC += tl;
-        }
-      }
-    w->tailOff[LM_NSEG] = tailAcc; w->prefOff[LM_NSEG] = prefAcc;
-    s->tailC = tC; s->tailS = tS;
+    snv = nv;
     w->gridOrigin[0] = (float)(50 * (cI - 2 - s->cenW) - 25);
     w->gridOrigin[1] = (float)(50 * (cJ - 2 - s->cenH) - 25);
     w->gridOrigin[2] = (float)(50 * (cK - 1 - s->cenD) - 25);
   }
+  __syncthreads();
+  const int nv = snv;
+  const int t = threadIdx.x;
+  // thread t < 250 owns segment (kind, slot) = (t / 125, t % 125)
+  const int kind = t / VL_MAX_VALID, slot = t % VL_MAX_VALID;
+  int cnt = 0, srt = 0;
+  if (t < LM_NSEG && slot < nv) {
+    const int cb = s->validInd[slot];
+    const MapCubeTable* tb = kind ? ts : tc;
+    cnt = tb->count[cb]; srt = tb->sorted[cb];
+    if (kind == 0) w->slotOfCube[cb] = slot;
+  }
+  int total = 0;
+  const int offCnt = lm_scan256(cnt, sbuf, &total);          // corner segments first, then surf
+  __shared__ int sMc;
+  if (t == VL_MAX_VALID) sMc = offCnt;                        // exclusive offset of the first surf segment == Mc
+  __syncthreads();
+  if (t < LM_NSEG) w->gatherOff[kind][slot] = kind ? offCnt - sMc : offCnt;
+  if (t == 0) { s->Mc = sMc; s->Ms = total - sMc; w->gatherOff[0][VL_MAX_VALID] = sMc; w->gatherOff[1][VL_MAX_VALID] = total - sMc; }
+  int tailTotal = 0, prefTotal = 0;
+  const int tl = cnt - srt;
+  const int offTail = lm_scan256(tl, sbuf, &tailTotal);
+  const int offPref = lm_scan256(srt, sbuf, &prefTotal);
+  if (t < LM_NSEG) { w->tailOff[t] = offTail; w->prefOff[t] = offPref; }
+  __shared__ int sTailC;
+  if (t == VL_MAX_VALID) sTailC = offTail;
+  __syncthreads();
+  if (t == 0) { w->tailOff[LM_NSEG] = tailTotal; w->prefOff[LM_NSEG] = prefTotal; s->tailC = sTailC; s->tailS = tailTotal - sTailC; }
 }
 
 // LM.cpp:476-485: concatenate the valid cubes (loop order of LM.cpp:448-452) into the sub-map clouds
@@ -591,21 +616,22 @@ __global__ void __launch_bounds__(1024) rf_scan_layout(int* __restrict__ unmatch
     if (threadIdx.x == 1023) carry += buf[1023];
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    unmatched[n] = carry;
-    int acc = 0;
-    for (int sg = 0; sg < LM_NSEG; ++sg) {
-      const int kind = sg / VL_MAX_VALID, slot = sg % VL_MAX_VALID;
-      int cnt = 0;
-      if (slot < s->validNum) {
-        const int cb = s->validInd[slot];
-        cnt = (kind ? ts : tc)->sorted[cb] + (unmatched[w->tailBegin[sg + 1]] - unmatched[w->tailBegin[sg]]);
-      }
-      w->outOff[sg] = acc; w->outCount[sg] = cnt;
-      acc += cnt;
+  if (threadIdx.x == 0) unmatched[n] = carry;
+  __syncthreads();
+  __shared__ int sb2[256];
+  const int sg = threadIdx.x;
+  int cnt = 0;
+  if (sg < LM_NSEG) {
+    const int kind = sg / VL_MAX_VALID, slot = sg % VL_MAX_VALID;
+    if (slot < s->validNum) {
+      const int cb = s->validInd[slot];
+      cnt = (kind ? ts : tc)->sorted[cb] + (unmatched[w->tailBegin[sg + 1]] - unmatched[w->tailBegin[sg]]);
     }
-    w->outOff[LM_NSEG] = acc;
   }
+  int tot = 0;
+  const int off = lm_scan256(cnt, sb2, &tot);
+  if (sg < LM_NSEG) { w->outOff[sg] = off; w->outCount[sg] = cnt; }
+  if (sg == 0) w->outOff[LM_NSEG] = tot;
 }
 
 __device__ __forceinline__ float4 rf_fold(float4 acc, const float4 p) {
@@ -667,22 +693,31 @@ __global__ void __launch_bounds__(256) rf_emit_prefix(const unsigned long long* 
   }
 }
 
-// grow cube storage where the re-filtered cloud no longer fits (bump allocation from the pool top)
-__global__ void rf_alloc(LmScalars* __restrict__ s, const RfWork* __restrict__ w, MapCubeTable* __restrict__ tc, MapCubeTable* __restrict__ ts,
-                         int poolCapC, int poolCapS) {
-  if (threadIdx.x != 0) return;
-  for (int sg = 0; sg < LM_NSEG; ++sg) {
-    const int kind = sg / VL_MAX_VALID, slot = sg % VL_MAX_VALID;
-    if (slot >= s->validNum) continue;
-    const int cb = s->validInd[slot];
-    MapCubeTable* tb = kind ? ts : tc;
+// grow cube storage where the re-filtered cloud no longer fits (bump allocation from the pool top;
+// a block scan keeps the layout deterministic)
+__global__ void __launch_bounds__(256) rf_alloc(LmScalars* __restrict__ s, const RfWork* __restrict__ w, MapCubeTable* __restrict__ tc,
+                                                MapCubeTable* __restrict__ ts, int poolCapC, int poolCapS) {
+  __shared__ int sb[256];
+  const int sg = threadIdx.x;
+  const int kind = sg / VL_MAX_VALID, slot = sg % VL_MAX_VALID;
+  int ncapC = 0, ncapS = 0, cb = -1;
+  if (sg < LM_NSEG && slot < s->validNum) {
+    cb = s->validInd[slot];
+    const MapCubeTable* tb = kind ? ts : tc;
     const int need = w->outCount[sg];
-    if (need > tb->cap[cb]) {
-      const int ncap = max(2 * need, 256);
-      int& top = kind ? s->poolTopS : s->poolTopC;
-      if (top + ncap > (kind ? poolCapS : poolCapC)) { s->overflow = 1; continue; }
-      tb->start[cb] = top; tb->cap[cb] = ncap; top += ncap;
-    }
+    if (need > tb->cap[cb]) { if (kind) ncapS = max(2 * need, 256); else ncapC = max(2 * need, 256); }
+  }
+  int totC = 0, totS = 0;
+  const int offC = lm_scan256(ncapC, sb, &totC);
+  const int offS = lm_scan256(ncapS, sb, &totS);
+  const int topC = s->poolTopC, topS = s->poolTopS;
+  const bool okC = topC + totC <= poolCapC, okS = topS + totS <= poolCapS;
+  if (ncapC > 0 && okC) { tc->start[cb] = topC + offC; tc->cap[cb] = ncapC; }
+  if (ncapS > 0 && okS) { ts->start[cb] = topS + offS; ts->cap[cb] = ncapS; }
+  __syncthreads();
+  if (sg == 0) {
+    if (okC) s->poolTopC = topC + totC; else s->overflow = 1;
+    if (okS) s->poolTopS = topS + totS; else s->overflow = 1;
   }
 }
 
@@ -947,7 +982,7 @@ int vl_lm_run(vloam_b200_ctx* c) {
     VL_BYTES(32.0 * (Mc + Ms));  // read every prefix point once, write it once to staging
     VL_LAUNCH(rf_emit_prefix, gsGrid, 256, 0, c->tailKeys.p, d->unmatched.p, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p,
               d->newPts.p, c->staging.p);
-    VL_LAUNCH(rf_alloc, 1, 32, 0, c->lmm, d->work, c->cubeC, c->cubeS, (int)c->poolC.cap, (int)c->poolS.cap);
+    VL_LAUNCH(rf_alloc, 1, 256, 0, c->lmm, d->work, c->cubeC, c->cubeS, (int)c->poolC.cap, (int)c->poolS.cap);
     VL_BYTES(32.0 * (Mc + Ms + nq));  // staging -> pool copy
     VL_LAUNCH(rf_commit, gsGrid, 256, 0, c->staging.p, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p);
     VL_LAUNCH(rf_finish, 1, 256, 0, c->lmm, d->work, c->cubeC, c->cubeS);

@@ -100,6 +100,10 @@ __device__ bool lm_chol6(const double A[6][6], const double b[6], double y[6]) {
 }
 
 __device__ double lm_gmax(const double x[7], const double g[6]) {
+  // The translation part of x - Plus(x, -g) is g[3..5] itself; when that alone exceeds the gradient
+  // tolerance the max norm cannot pass the 1e-10 test and the quaternion part need not be formed.
+  const double gt = fmax(fabs(g[3]), fmax(fabs(g[4]), fabs(g[5])));
+  if (gt > 1e-6) return gt;
   double ng[6], xp[7];
   for (int k = 0; k < 6; ++k) ng[k] = -g[k];
   lm_plus(x, ng, xp);
@@ -139,7 +143,8 @@ __device__ void lm_logic(LmSolveState* st, const double* e) {
       for (int k = 0; k < 6; ++k) st->g[k] = e[21 + k];
       st->cost = cost;
       st->gmax = lm_gmax(st->x, st->g);
-      st->radius = fmin(max_radius, st->radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rho - 1.0, 3.0)));
+      const double tr = 2.0 * rho - 1.0;
+      st->radius = fmin(max_radius, st->radius / fmax(1.0 / 3.0, 1.0 - tr * tr * tr));
       st->decrease_factor = 2.0; st->reuse_diagonal = 0; st->last_successful = 1;
       if (st->cost < st->min_cost) { st->min_cost = st->cost; for (int k = 0; k < 7; ++k) st->best[k] = st->x[k]; }
     } else {  // HandleUnsuccessfulStep

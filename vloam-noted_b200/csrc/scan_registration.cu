@@ -412,7 +412,9 @@ __global__ void __launch_bounds__(SR_BLOCK) sr_ring_voxel(const float4* __restri
                                                           const int* __restrict__ ringStart, const int* __restrict__ ringCount,
                                                           int* __restrict__ sel, unsigned long long* __restrict__ scratch,
                                                           float4* __restrict__ outProv, int* __restrict__ dsCount, float leaf) {
-  __shared__ unsigned long long skeys[SR_VOX_CAP];
+  extern __shared__ unsigned long long vsm[];  // [SR_VOX_CAP] keys, then [SR_VOX_CAP] float4 points
+  unsigned long long* skeys = vsm;
+  float4* spts = reinterpret_cast<float4*>(vsm + SR_VOX_CAP);
   __shared__ int warpSum[SR_BLOCK / 32];
   __shared__ float red[6][SR_BLOCK / 32];
   __shared__ VoxBox box;
@@ -471,8 +473,16 @@ __global__ void __launch_bounds__(SR_BLOCK) sr_ring_voxel(const float4* __restri
   // 2. (voxel idx, local index) keys, bitonic sort
   int P = 32; while (P < m) P <<= 1;
   unsigned long long* keys = (P <= SR_VOX_CAP) ? skeys : scratch + (size_t)2 * rs + (size_t)r * 6 * 64;
-  for (int t = threadIdx.x; t < P; t += SR_BLOCK)
-    keys[t] = t < m ? (((unsigned long long)vox_idx(cloud[mySel[t]], box) << 32) | (unsigned)t) : ~0ull;
+  const bool ptsInSmem = m <= SR_VOX_CAP;
+  for (int t = threadIdx.x; t < P; t += SR_BLOCK) {
+    unsigned long long key = ~0ull;
+    if (t < m) {
+      const float4 p = cloud[mySel[t]];
+      if (ptsInSmem) spts[t] = p;
+      key = ((unsigned long long)vox_idx(p, box) << 32) | (unsigned)t;
+    }
+    keys[t] = key;
+  }
   __syncthreads();
   const int halfP = P >> 1;
   for (int k = 2; k <= P; k <<= 1)
@@ -500,7 +510,8 @@ __global__ void __launch_bounds__(SR_BLOCK) sr_ring_voxel(const float4* __restri
       const unsigned vox = (unsigned)(keys[t] >> 32);
       float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f; int nrun = 0;
       for (int q = t; q < m && (unsigned)(keys[q] >> 32) == vox; ++q) {
-        const float4 p = cloud[mySel[(int)(unsigned)(keys[q] & 0xffffffffull)]];
+        const int li = (int)(unsigned)(keys[q] & 0xffffffffull);
+        const float4 p = ptsInSmem ? spts[li] : cloud[mySel[li]];
         sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
         ++nrun;
       }
@@ -610,7 +621,10 @@ int vl_sr_run(vloam_b200_ctx* c, const float* d_xyz, int n, int stride) {
   }
   VL_LAUNCH(sr_pick, R, SR_BLOCK, pickSmem, c->cloud.p, c->curv.p, c->label.p, c->picked.p, c->picked.p + n, c->sortScratch.p, c->ringStart, c->ringCount,
             c->provSharp, c->provLess, c->provFlat, c->cntSharp, c->cntLess, c->cntFlat);
-  VL_LAUNCH(sr_ring_voxel, R, SR_BLOCK, 0, c->cloud.p, c->label.p, c->ringStart, c->ringCount, c->selIdx.p, c->sortScratch.p,
+  const size_t voxSmem = (size_t)SR_VOX_CAP * (sizeof(unsigned long long) + sizeof(float4));
+  static bool voxAttr = false;
+  if (!voxAttr) { VL_CUDA(cudaFuncSetAttribute(sr_ring_voxel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)voxSmem)); voxAttr = true; }
+  VL_LAUNCH(sr_ring_voxel, R, SR_BLOCK, voxSmem, c->cloud.p, c->label.p, c->ringStart, c->ringCount, c->selIdx.p, c->sortScratch.p,
             c->lessFlatProv.p, c->ringDsCount, 0.2f);
   VL_LAUNCH(sr_offsets, 1, 1024, 0, R, c->cntSharp, c->cntLess, c->cntFlat, c->ringDsCount, c->offSharp, c->offLess, c->offFlat,
             c->ringDsOff, c->srs);

@@ -13,7 +13,10 @@
 // fixed pass count and needs no scratch buffer.
 #include <limits.h>
 #include <math_constants.h>
+#include <cooperative_groups.h>
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 #define BT_TILE 4096
 #define BT_THREADS 512
@@ -68,9 +71,95 @@ __global__ void __launch_bounds__(BT_THREADS) bt_tile_merge(unsigned long long* 
   for (int t = threadIdx.x; t < tile; t += BT_THREADS) keys[base + t] = s[t];
 }
 
+// ---- single-launch sort: one thread-block cluster, tiles in distributed shared memory -----------
+// Up to 16 CTAs x 8192 keys.  Every CTA bitonic-sorts its tile in shared memory; the strides that
+// cross tiles read the partner tile through DSMEM (cluster.map_shared_rank) and write the result
+// into the second half of a double buffer, so a cross-tile stage costs one cluster barrier instead
+// of a kernel launch plus a global-memory round trip.
+#define CS_THREADS 1024
+
+__global__ void __launch_bounds__(CS_THREADS) bt_cluster_sort(unsigned long long* __restrict__ keys, int tile) {
+  extern __shared__ unsigned long long cs[];  // [2][tile]
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank();
+  const int n = tile * (int)cluster.num_blocks();
+  const size_t base = (size_t)rank * tile;
+  unsigned long long* cur = cs;
+  unsigned long long* alt = cs + tile;
+  for (int t = threadIdx.x; t < tile; t += CS_THREADS) cur[t] = keys[base + t];
+  __syncthreads();
+  const int half = tile >> 1;
+  for (int k = 2; k <= tile; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int u = threadIdx.x; u < half; u += CS_THREADS) {
+        const int i = ((u & ~(j - 1)) << 1) | (u & (j - 1));
+        const int l = i | j;
+        const unsigned long long a = cur[i], b = cur[l];
+        const bool up = ((base + i) & (size_t)k) == 0;
+        if ((a > b) == up) { cur[i] = b; cur[l] = a; }
+      }
+      __syncthreads();
+    }
+  for (int k = tile << 1; k <= n; k <<= 1) {
+    for (int j = k >> 1; j >= tile; j >>= 1) {
+      cluster.sync();  // partner tiles are complete in `cur`
+      const unsigned prank = rank ^ (unsigned)(j / tile);
+      const unsigned long long* rem = cluster.map_shared_rank(cur, prank);
+      const bool low = (base & (size_t)j) == 0;
+      const bool up = (base & (size_t)k) == 0;
+      const bool takeMin = (low == up);
+      for (int t = threadIdx.x; t < tile; t += CS_THREADS) {
+        const unsigned long long a = cur[t], b = rem[t];
+        alt[t] = takeMin ? (a < b ? a : b) : (a > b ? a : b);
+      }
+      unsigned long long* tmp = cur; cur = alt; alt = tmp;
+    }
+    // every CTA flipped buffers the same number of times, so `cur` means the same half everywhere;
+    // the barrier below also keeps a fast CTA from overwriting `alt` while a partner still reads it
+    cluster.sync();
+    const bool up = (base & (size_t)k) == 0;
+    for (int j = tile >> 1; j > 0; j >>= 1) {
+      for (int u = threadIdx.x; u < half; u += CS_THREADS) {
+        const int i = ((u & ~(j - 1)) << 1) | (u & (j - 1));
+        const int l = i | j;
+        const unsigned long long a = cur[i], b = cur[l];
+        if ((a > b) == up) { cur[i] = b; cur[l] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int t = threadIdx.x; t < tile; t += CS_THREADS) keys[base + t] = cur[t];
+  cluster.sync();  // no CTA exits while a partner may still read its shared memory
+}
+
+static int vl_sort_cluster(vloam_b200_ctx* c, unsigned long long* d_keys, int n_pow2) {
+  int tile = n_pow2 <= 4096 ? n_pow2 : 4096;
+  int nct = n_pow2 / tile;
+  if (nct > 16) { tile = 8192; nct = n_pow2 / tile; }
+  static bool attr = false;
+  if (!attr) {
+    VL_CUDA(cudaFuncSetAttribute(bt_cluster_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 8));
+    VL_CUDA(cudaFuncSetAttribute(bt_cluster_sort, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    attr = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nct); cfg.blockDim = dim3(CS_THREADS); cfg.dynamicSmemBytes = (size_t)2 * tile * 8; cfg.stream = c->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = nct; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  const bool prof = c->prof_name[0] && vl_prof_match(c, "bt_cluster_sort") && c->prof_n < VL_PROF_MAX;
+  if (prof) cudaEventRecord(c->prof_ev[c->prof_n][0], c->stream);
+  VL_CUDA(cudaLaunchKernelEx(&cfg, bt_cluster_sort, d_keys, tile));
+  if (prof) { cudaEventRecord(c->prof_ev[c->prof_n][1], c->stream); c->prof_n++; c->prof_bytes += 16.0 * n_pow2; }
+  c->launches++;
+  return VLOAM_OK;
+}
+
 // Ascending sort of n_pow2 unique 64-bit keys in place (n_pow2 a power of two >= 2).
 int vl_sort_u64(vloam_b200_ctx* c, unsigned long long* d_keys, int n_pow2) {
   if (n_pow2 < 2) return VLOAM_OK;
+  if (n_pow2 <= 16 * 8192) return vl_sort_cluster(c, d_keys, n_pow2);
   const int tile = n_pow2 < BT_TILE ? n_pow2 : BT_TILE;
   VL_LAUNCH(bt_tile_sort, n_pow2 / tile, BT_THREADS, 0, d_keys, tile);
   for (int k = tile << 1; k <= n_pow2; k <<= 1) {
@@ -204,25 +293,45 @@ __global__ void __launch_bounds__(VG_BLOCK) vg_centroid(const float4* __restrict
     return;
   }
   const int n = b.n;
+  // stage the tile's voxel ids and points in shared memory: the serial f32 folds below then run at
+  // shared-memory latency instead of chasing global loads (a run may continue past the tile; the tail
+  // is read from global, which is rare)
+  __shared__ unsigned svox[1024 + 1];
+  __shared__ float4 spt[1024];
   __shared__ int ws[VG_BLOCK / 32];
+  const int base = blockIdx.x * 1024;
+  for (int t = threadIdx.x; t < 1024; t += VG_BLOCK) {
+    const int g = base + t;
+    if (g < n) { const unsigned long long k = keys[g]; svox[t] = (unsigned)(k >> 32); spt[t] = in[(int)(unsigned)(k & 0xffffffffull)]; }
+    else svox[t] = 0xffffffffu;
+  }
+  __syncthreads();
   int running = blockOff[blockIdx.x];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int q = 0; q < 4; ++q) {
-    const int t = blockIdx.x * 1024 + q * VG_BLOCK + threadIdx.x;
-    const bool head = t < n && (t == 0 || (unsigned)(keys[t] >> 32) != (unsigned)(keys[t - 1] >> 32));
+    const int lt = q * VG_BLOCK + threadIdx.x;
+    const int t = base + lt;
+    const unsigned vox = svox[lt];
+    const bool head = t < n && (lt == 0 ? (t == 0 || (unsigned)(keys[t - 1] >> 32) != vox) : svox[lt - 1] != vox);
     const unsigned bal = __ballot_sync(0xffffffffu, head);
     if (lane == 0) ws[warp] = __popc(bal);
     __syncthreads();
     int before = 0, all = 0;
     for (int w = 0; w < VG_BLOCK / 32; ++w) { const int v = ws[w]; if (w < warp) before += v; all += v; }
     if (head) {
-      const unsigned vox = (unsigned)(keys[t] >> 32);
       float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f; int nrun = 0;
-      for (int r = t; r < n && (unsigned)(keys[r] >> 32) == vox; ++r) {
-        const float4 p = in[(int)(unsigned)(keys[r] & 0xffffffffull)];
+      int r = lt;
+      for (; r < 1024 && svox[r] == vox; ++r) {
+        const float4 p = spt[r];
         sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
         ++nrun;
       }
+      if (r == 1024)
+        for (int g = base + 1024; g < n && (unsigned)(keys[g] >> 32) == vox; ++g) {
+          const float4 p = in[(int)(unsigned)(keys[g] & 0xffffffffull)];
+          sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
+          ++nrun;
+        }
       const float fn = (float)nrun;
       out[running + before + __popc(bal & ((1u << lane) - 1u))] =
           make_float4(__fdiv_rn(sx, fn), __fdiv_rn(sy, fn), __fdiv_rn(sz, fn), __fdiv_rn(si, fn));
