@@ -42,38 +42,56 @@ def make_sequence(pkg, seq_id, n_frames, world_kind=1):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons sampled DURING the timed regions.  In-process NVML (nvidia_ml_py): a
+    spawned `nvidia-smi -lms` stalls CUDA calls for tens of ms every time it polls, which on a ~100 ms
+    timed region is the difference between 900 and 450 scans/s; NVML calls from a thread cost ~0.1 ms."""
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.idx, self.rows, self.stop_flag, self.thread, self.nv = gpu_index, [], False, None, None
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", os.environ.get("BENCH_SMI_MS", "500")],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.idx]) if vis and vis.split(",")[self.idx].isdigit() else self.idx
+            self.h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = nv
+            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.nv = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+    def _loop(self):
+        nv = self.nv
+        period = float(os.environ.get("BENCH_SMI_MS", "50")) / 1e3
+        while not self.stop_flag:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, reasons))
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            time.sleep(period)
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.nv or not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        seen = sorted(n for n, bit in names.items() if any(r & bit for _, r in self.rows))
+        return {"sm_mhz": float(np.median([r[0] for r in self.rows])), "sm_max_mhz": float(self.sm_max), "reasons": seen,
+                "samples": len(self.rows)}
 
 
 def measured_peak():
@@ -173,8 +191,8 @@ def run_ours(args, rank, world_size, local_rank):
         return ctx
 
     sampler = ClockSampler(local_rank)
-    if rank == 0 and os.environ.get("BENCH_SMI_MS", "500") != "0":
-        sampler.start()  # started before the warm-up: nvidia-smi's own start-up stalls CUDA calls for a moment
+    if rank == 0 and os.environ.get("BENCH_SMI_MS", "50") != "0":
+        sampler.start()
     # ---- leg 1: device-resident inputs (value) ------------------------------------------------
     ctx = fresh()
     ext = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
@@ -183,9 +201,6 @@ def run_ours(args, rank, world_size, local_rank):
     for k in range(W + 1):
         ctx.process_frame_device(dscans[k].data_ptr(), dscans[k].shape[0], 4)
     ctx.synchronize()
-    t_wait = time.time()
-    while rank == 0 and sampler.proc and len(sampler.rows) < 3 and time.time() - t_wait < 5.0:
-        time.sleep(0.05)
     if dist: dist.barrier()
     torch.cuda.synchronize()
     l0 = ctx.kernel_launches
@@ -290,8 +305,8 @@ def profile_dominant(ctx, dscans, first, K, map_points):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

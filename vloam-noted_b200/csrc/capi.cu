@@ -31,7 +31,7 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   VL_CUDA_CREATE(cudaSetDevice(device));
   vloam_b200_ctx* c = new vloam_b200_ctx();
   c->prm = *p; c->device = device; c->err[0] = 0; c->launches = 0; c->timing = false; c->cur = 0;
-  c->sr_counts_valid = false; c->n_in = 0; c->lo_inited = false; c->lo_frameCount = 0; c->lm_frameCount = 0; c->lm_optimized = 0; c->skip_frame = false;
+  c->sr_counts_valid = false; c->n_in = 0; c->lo_inited = false; c->lo_frameCount = 0; c->lm_frameCount = 0; c->lm_optimized = 0; c->loGridValid = false; c->skip_frame = false;
   c->nKept = c->nSharp = c->nLessSharp = c->nFlat = c->nLessFlat = 0; c->nCornerLast = c->nSurfLast = 0;
   c->cornerLastPtr = nullptr; c->surfLastPtr = nullptr;
   for (int k = 0; k < 4; ++k) c->dbgLoCost[k] = c->dbgLmCost[k] = 0;
@@ -333,6 +333,8 @@ int vloam_b200_debug_set(vloam_b200_ctx* c, const char* name, const void* data, 
     c->cornerLastPtr = c->lessSharp[o].p; c->surfLastPtr = c->lessFlat[o].p;
     c->nCornerLast = hdr[0]; c->nSurfLast = hdr[1];
     c->lo_inited = true;
+    VL_TRY(vl_lo_build_last(c));
+    VL_CUDA(cudaStreamSynchronize(c->stream));
     return VLOAM_OK;
   }
   if (n == "lo.pose") {

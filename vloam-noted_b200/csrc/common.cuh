@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "vloam_b200.h"
 
@@ -125,6 +126,7 @@ struct vloam_b200_ctx {
   bool lo_inited; int lo_frameCount;
   float4* cornerLastPtr; float4* surfLastPtr;  // after solveLO's swap
   int* loRingTbl;                     // 2 x (144 + 1) ints: ring-value -> first index tables of the last clouds
+  DBuf<int> loGridCells, loGridCellOf; DBuf<float4> loGridSorted; bool loGridValid;  // 5.12 m search grid over the last clouds
   DBuf<int> loCornerIdx, loSurfIdx;   // association results (2 / 3 ints per query)
   DBuf<double> factors;               // 10 doubles per factor slot
   DBuf<int> factorValid;
@@ -215,7 +217,10 @@ static inline int vl_reserve(vloam_b200_ctx* c, DBuf<T>& b, size_t n, bool keep 
   n += slack;
   size_t ncap = b.cap ? b.cap : 1024;
   while (ncap < n) ncap *= 2;
+  if (ncap * sizeof(T) <= ((size_t)32 << 20)) ncap *= 2;  // HBM is plentiful: head room so a count hovering at a power of two never regrows
   T* np = nullptr;
+  static const bool trace = getenv("VLOAM_TRACE_ALLOC") != nullptr;
+  if (trace) fprintf(stderr, "[vloam_b200] grow buffer to %zu x %zu B (frame %d)\n", ncap, sizeof(T), c->lo_frameCount);
   VL_CUDA(cudaMalloc(&np, ncap * sizeof(T)));
   if (keep && b.p && b.cap) VL_CUDA(cudaMemcpyAsync(np, b.p, b.cap * sizeof(T), cudaMemcpyDeviceToDevice, c->stream));
   if (b.p) { VL_CUDA(cudaStreamSynchronize(c->stream)); VL_CUDA(cudaFree(b.p)); }
@@ -230,11 +235,13 @@ int vl_sr_run(vloam_b200_ctx* c, const float* d_xyz, int n, int stride);
 int vl_sr_sync_counts(vloam_b200_ctx* c);
 int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, int use_prior);
 int vl_lo_associate_only(vloam_b200_ctx* c, const double* x, int* corner_idx, int* surf_idx);
+int vl_lo_build_last(vloam_b200_ctx* c);
 int vl_lm_run(vloam_b200_ctx* c);
 int vl_lm_init(vloam_b200_ctx* c);
 int vl_lm_export_map(vloam_b200_ctx* c, int which, void* out, long cap, long* bytes);
 int vl_lm_import_map(vloam_b200_ctx* c, int which, const void* data, long bytes);
 
+int vl_scan_exclusive(vloam_b200_ctx* c, const int* in, int n, int* tileSum, int* out);  // laser_mapping.cu
 // sort / voxel primitives (voxel_grid.cu)
 int vl_sort_u64(vloam_b200_ctx* c, unsigned long long* d_keys, int n_pow2);
 // pcl::VoxelGrid of d_in[0..n) -> d_out, count written to *d_count (device int); n is a host bound,

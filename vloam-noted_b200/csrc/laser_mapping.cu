@@ -288,6 +288,17 @@ __global__ void __launch_bounds__(256) lm_scan_apply(const int* __restrict__ in,
   }
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = running;  // total
 }
+// out[0..n] = exclusive scan of in[0..n) (out[n] = total); tileSum needs ceil(n/1024)+1 ints
+int vl_scan_exclusive(vloam_b200_ctx* c, const int* in, int n, int* tileSum, int* out) {
+  const int nTiles = vl_div_up(n, 1024);
+  VL_BYTES(4.0 * n);
+  VL_LAUNCH(lm_scan_tiles, nTiles, 256, 0, in, n, tileSum);
+  VL_LAUNCH(lm_scan_sums, 1, 1024, 0, tileSum, nTiles);
+  VL_BYTES(8.0 * n);
+  VL_LAUNCH(lm_scan_apply, nTiles, 256, 0, in, n, tileSum, out);
+  return VLOAM_OK;
+}
+
 __global__ void __launch_bounds__(256) lm_grid_fill(const LmScalars* __restrict__ s, const float4* __restrict__ mapC,
                                                     const float4* __restrict__ mapS, const int* __restrict__ cellOfPoint,
                                                     const int* __restrict__ cellStart, int* __restrict__ cellFill,
@@ -928,12 +939,7 @@ int vl_lm_run(vloam_b200_ctx* c) {
     VL_CUDA(cudaMemsetAsync(d->cellFill, 0, sizeof(int) * (nCells + 1), c->stream));
     VL_BYTES(24.0 * total);  // read point, write cell id, atomic on the cell counter
     VL_LAUNCH(lm_grid_count, gsGrid, 256, 0, c->lmm, d->work, c->fromMapC.p, c->fromMapS.p, d->cellCount, d->cellOfPoint.p);
-    const int nTiles = vl_div_up(nCells, 1024);
-    VL_BYTES(4.0 * nCells);
-    VL_LAUNCH(lm_scan_tiles, nTiles, 256, 0, d->cellCount, nCells, d->tileSum);
-    VL_LAUNCH(lm_scan_sums, 1, 1024, 0, d->tileSum, nTiles);
-    VL_BYTES(8.0 * nCells);
-    VL_LAUNCH(lm_scan_apply, nTiles, 256, 0, d->cellCount, nCells, d->tileSum, d->cellStart);
+    VL_TRY(vl_scan_exclusive(c, d->cellCount, nCells, d->tileSum, d->cellStart));
     VL_BYTES(44.0 * total);  // read point + cell id + cell start, atomic, write sorted point
     VL_LAUNCH(lm_grid_fill, gsGrid, 256, 0, c->lmm, c->fromMapC.p, c->fromMapS.p, d->cellOfPoint.p, d->cellStart, d->cellFill, d->sortedPts.p);
     VL_TRY(vl_reserve(c, c->knnIdx, (size_t)nq * 5));

@@ -57,11 +57,11 @@ __global__ void __launch_bounds__(256) lo_ring_table(const float4* __restrict__ 
   if (j >= n) return;
   const int v = min(max((int)cl[j].w, 0), LO_TBL - 1);
   const int raw = (int)cl[j].w;
-  if (j == 0) { for (int q = 0; q <= v; ++q) t[q] = 0; }
+  if (j == 0) { for (int q = 0; q <= v; ++q) t[q] = 0; if (raw < 0 || raw > 255) t[LO_TBL] = 0; }
   else {
     const int rawp = (int)cl[j - 1].w;
     const int vp = min(max(rawp, 0), LO_TBL - 1);
-    if (raw < rawp || raw < 0) t[LO_TBL] = 0;  // not monotone (or negative): table unusable
+    if (raw < rawp || raw < 0 || raw > 255) t[LO_TBL] = 0;  // not monotone (or outside the packed byte): tables unusable
     for (int q = vp + 1; q <= v; ++q) t[q] = j;
   }
   if (j == n - 1) for (int q = v + 1; q < LO_TBL; ++q) t[q] = n;
@@ -232,6 +232,202 @@ __global__ void __launch_bounds__(LO_QPB * 32) lo_assoc(const float4* __restrict
   }
 }
 
+
+// ---- uniform grid over the "last" clouds -----------------------------------------------------------
+// The reference rebuilds two KD-trees per frame (LO.cpp:573-574).  Here both last clouds are counting-
+// sorted once per frame into 2.56 m cells.  A search visits the 27 cells around the query first: they
+// contain every point closer than 2.56 m, so a minimum below (2.5 m)^2 is already the global one; only
+// otherwise the surrounding shell (5x5x5 cells, >= 5.12 m around the query, i.e. everything inside the
+// 5 m acceptance radius of LO.cpp:299/397) is visited too.  Entries are {x, y, z, bits(index |
+// int(intensity) << 24)}.  Coordinates outside the grid are clamped, which keeps neighbours neighbours
+// (clamping is monotone), so the search stays exact.
+#define LOG_NX 128
+#define LOG_NY 128
+#define LOG_NZ 32
+#define LOG_NCELL (LOG_NX * LOG_NY * LOG_NZ)
+#define LOG_INV 0.390625f    // 1 / 2.56
+#define LOG_NEAR2 6.25f      // (2.5 m)^2 < cell^2: a minimum below this found in the 27 cells is global
+#define LOG_OX (-163.84f)
+#define LOG_OZ (-40.96f)
+
+__device__ __forceinline__ int log_cx(float v) { return min(max((int)floorf((v - LOG_OX) * LOG_INV), 0), LOG_NX - 1); }
+__device__ __forceinline__ int log_cz(float v) { return min(max((int)floorf((v - LOG_OZ) * LOG_INV), 0), LOG_NZ - 1); }
+__device__ __forceinline__ int log_cell(float x, float y, float z) { return log_cx(x) + LOG_NX * (log_cx(y) + LOG_NY * log_cz(z)); }
+
+__global__ void __launch_bounds__(256) lo_grid_count(const float4* __restrict__ corner, int nc, const float4* __restrict__ surf, int ns,
+                                                     int* __restrict__ cellCount, int* __restrict__ cellOf) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nc + ns) return;
+  const int which = g >= nc;
+  const float4 p = which ? surf[g - nc] : corner[g];
+  const int cell = which * LOG_NCELL + log_cell(p.x, p.y, p.z);
+  cellOf[g] = cell;
+  atomicAdd(&cellCount[cell], 1);
+}
+__global__ void __launch_bounds__(256) lo_grid_fill(const float4* __restrict__ corner, int nc, const float4* __restrict__ surf, int ns,
+                                                    const int* __restrict__ cellOf, const int* __restrict__ cellStart,
+                                                    int* __restrict__ cellFill, float4* __restrict__ sorted) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nc + ns) return;
+  const int which = g >= nc;
+  const int j = which ? g - nc : g;
+  const float4 p = which ? surf[j] : corner[j];
+  const int cell = cellOf[g];
+  const int pos = cellStart[cell] + atomicAdd(&cellFill[cell], 1);
+  const unsigned v = (unsigned)min(max((int)p.w, 0), 255);
+  sorted[pos] = make_float4(p.x, p.y, p.z, __uint_as_float((unsigned)j | (v << 24)));
+}
+
+__device__ __forceinline__ Best warp_best_v(Best v, unsigned& tag, bool preferLow) {
+  for (int d = 16; d > 0; d >>= 1) {
+    Best o; o.d = __shfl_xor_sync(0xffffffffu, v.d, d); o.j = __shfl_xor_sync(0xffffffffu, v.j, d);
+    const unsigned ot = __shfl_xor_sync(0xffffffffu, tag, d);
+    const bool take = preferLow ? (o.d < v.d || (o.d == v.d && o.j < v.j)) : (o.d < v.d || (o.d == v.d && o.j > v.j));
+    if (take) { v = o; tag = ot; }
+  }
+  return v;
+}
+
+// Association over the grid (valid when int(intensity) of the target cloud is non-decreasing: the
+// reference's forward scan then visits exactly {j > closest : ring_j <= id + 2} and the backward scan
+// {j < closest : ring_j >= id - 2}; candidates farther than 5 m can never win because the running
+// minima start at DISTANCE_SQ_THRESHOLD = 25).  One warp per query, two passes over its 27 cells.
+// visit cells [xa, xb] of row (yy, zz); BODY sees float4 t
+#define LOG_ROW(xa, xb, yy, zz, BODY)                                                    \
+  do {                                                                                   \
+    const int c0_ = cellBase + (xa) + LOG_NX * ((yy) + LOG_NY * (zz));                   \
+    const int beg_ = cellStart[c0_], end_ = cellStart[c0_ + ((xb) - (xa)) + 1];          \
+    for (int p_ = beg_ + lane; p_ < end_; p_ += 32) { const float4 t = __ldg(&sorted[p_]); BODY } \
+  } while (0)
+// inner = the 3x3x3 block, shell = the 5x5x5 block minus the inner one
+#define LOG_VISIT(SHELL, BODY)                                                           \
+  do {                                                                                   \
+    const int rad_ = (SHELL) ? 2 : 1;                                                    \
+    for (int dz_ = -rad_; dz_ <= rad_; ++dz_) {                                          \
+      const int zz_ = cz + dz_;                                                          \
+      if (zz_ < 0 || zz_ >= LOG_NZ) continue;                                            \
+      for (int dy_ = -rad_; dy_ <= rad_; ++dy_) {                                        \
+        const int yy_ = cy + dy_;                                                        \
+        if (yy_ < 0 || yy_ >= LOG_NY) continue;                                          \
+        if (!(SHELL)) { LOG_ROW(max(cx - 1, 0), min(cx + 1, LOG_NX - 1), yy_, zz_, BODY); } \
+        else if (dz_ == -2 || dz_ == 2 || dy_ == -2 || dy_ == 2) { LOG_ROW(max(cx - 2, 0), min(cx + 2, LOG_NX - 1), yy_, zz_, BODY); } \
+        else {                                                                           \
+          if (cx - 2 >= 0) { LOG_ROW(cx - 2, cx - 2, yy_, zz_, BODY); }                  \
+          if (cx + 2 < LOG_NX) { LOG_ROW(cx + 2, cx + 2, yy_, zz_, BODY); }              \
+        }                                                                                \
+      }                                                                                  \
+    }                                                                                    \
+  } while (0)
+
+// Association over the grid (valid when int(intensity) of the target cloud is non-decreasing: the
+// reference's forward scan then visits exactly {j > closest : ring_j <= id + 2} and the backward scan
+// {j < closest : ring_j >= id - 2}; candidates farther than 5 m can never win because the running
+// minima start at DISTANCE_SQ_THRESHOLD = 25).  One warp per query.
+template <bool SURF>
+__global__ void __launch_bounds__(256) lo_assoc_grid(const float4* __restrict__ query, int nq, const float4* __restrict__ target,
+                                                     const float4* __restrict__ sorted, const int* __restrict__ cellStart,
+                                                     const double* __restrict__ pose, int* __restrict__ outIdx,
+                                                     double* __restrict__ factors, int* __restrict__ valid, int slotBase) {
+  const int lane = threadIdx.x & 31;
+  const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (qi >= nq) return;
+  const float4 cp = query[qi];
+  double r[3];
+  vl_qrot(pose, (double)cp.x, (double)cp.y, (double)cp.z, r);  // TransformToStart (LO.cpp:152-173)
+  const float sx = (float)(r[0] + pose[4]), sy = (float)(r[1] + pose[5]), sz = (float)(r[2] + pose[6]);
+  const int cx = log_cx(sx), cy = log_cx(sy), cz = log_cz(sz);
+  const int cellBase = SURF ? LOG_NCELL : 0;
+  // ---- pass A: exact nearest neighbour, ties by index
+  Best nn{3.0e38f, 0x7fffffff};
+  unsigned nnv = 0;
+#define LOG_NN_BODY                                                                      \
+  {                                                                                      \
+    const float d = vl_dist2(sx, sy, sz, t.x, t.y, t.z);                                 \
+    const unsigned bits = __float_as_uint(t.w);                                          \
+    const int j = (int)(bits & 0xffffffu);                                               \
+    if (d < nn.d || (d == nn.d && j < nn.j)) { nn.d = d; nn.j = j; nnv = bits >> 24; }   \
+  }
+  LOG_VISIT(false, LOG_NN_BODY);
+  nn = warp_best_v(nn, nnv, true);
+  if (!(nn.d < LOG_NEAR2)) {  // nothing within 2.5 m: look at the shell as well (warp-uniform branch)
+    LOG_VISIT(true, LOG_NN_BODY);
+    nn = warp_best_v(nn, nnv, true);
+  }
+  int closest = -1, ind2 = -1, ind3 = -1;
+  if (nn.j != 0x7fffffff && (double)nn.d < 25.0) {  // LO.cpp:299, 397
+    closest = nn.j;
+    const int id = (int)nnv;
+    Best f2{25.0f, 0x7fffffff}, f3{25.0f, 0x7fffffff}, g2{25.0f, -1}, g3{25.0f, -1};
+#define LOG_B_BODY                                                                                        \
+  {                                                                                                       \
+    const unsigned bits = __float_as_uint(t.w);                                                           \
+    const int j = (int)(bits & 0xffffffu);                                                                \
+    const int v = (int)(bits >> 24);                                                                      \
+    const float d = lo_sqdis(t, sx, sy, sz);                                                              \
+    if (d < 25.0f) { /* the running minima start at DISTANCE_SQ_THRESHOLD; only strict < replaces them */ \
+      if (j > closest) { /* forward scan LO.cpp:309-331 / 407-430 */                                      \
+        if (v <= id + 2) {                                                                                \
+          if (SURF) {                                                                                     \
+            if (v <= id) { if (d < f2.d || (d == f2.d && j < f2.j)) { f2.d = d; f2.j = j; } }             \
+            else if (d < f3.d || (d == f3.d && j < f3.j)) { f3.d = d; f3.j = j; }                         \
+          } else if (v > id) { if (d < f2.d || (d == f2.d && j < f2.j)) { f2.d = d; f2.j = j; } }         \
+        }                                                                                                 \
+      } else if (j < closest) { /* backward scan LO.cpp:334-355 / 433-456 */                              \
+        if (v >= id - 2) {                                                                                \
+          if (SURF) {                                                                                     \
+            if (v >= id) { if (d < g2.d || (d == g2.d && j > g2.j)) { g2.d = d; g2.j = j; } }             \
+            else if (d < g3.d || (d == g3.d && j > g3.j)) { g3.d = d; g3.j = j; }                         \
+          } else if (v < id) { if (d < g2.d || (d == g2.d && j > g2.j)) { g2.d = d; g2.j = j; } }         \
+        }                                                                                                 \
+      }                                                                                                   \
+    }                                                                                                     \
+  }
+    LOG_VISIT(false, LOG_B_BODY);
+    Best F2 = warp_best(f2, true), G2 = warp_best(g2, false), F3 = f3, G3 = g3;
+    if (SURF) { F3 = warp_best(f3, true); G3 = warp_best(g3, false); }
+    const bool need = !(fminf(F2.d, G2.d) < LOG_NEAR2) || (SURF && !(fminf(F3.d, G3.d) < LOG_NEAR2));
+    if (need) {  // some class has no candidate within 2.5 m yet: the shell may still hold one
+      LOG_VISIT(true, LOG_B_BODY);
+      F2 = warp_best(f2, true); G2 = warp_best(g2, false);
+      if (SURF) { F3 = warp_best(f3, true); G3 = warp_best(g3, false); }
+    }
+    // forward candidates were visited first: backward wins only when strictly nearer
+    if (F2.j == 0x7fffffff) F2.j = -1;
+    ind2 = (G2.j >= 0 && G2.d < F2.d) ? G2.j : F2.j;
+    if (SURF) {
+      if (F3.j == 0x7fffffff) F3.j = -1;
+      ind3 = (G3.j >= 0 && G3.d < F3.d) ? G3.j : F3.j;
+    }
+  }
+  if (lane != 0) return;
+  const int slot = slotBase + qi;
+  double* f = factors + (size_t)slot * 10;
+  if (SURF) {
+    outIdx[qi * 3] = closest; outIdx[qi * 3 + 1] = ind2; outIdx[qi * 3 + 2] = ind3;
+    const bool ok = closest >= 0 && ind2 >= 0 && ind3 >= 0;
+    valid[slot] = ok ? 1 : 0;
+    if (ok) {  // LidarPlaneFactor ctor (LF.hpp:73-74)
+      const float4 J = target[closest], L = target[ind2], M = target[ind3];
+      const double u[3] = {(double)J.x - (double)L.x, (double)J.y - (double)L.y, (double)J.z - (double)L.z};
+      const double w[3] = {(double)J.x - (double)M.x, (double)J.y - (double)M.y, (double)J.z - (double)M.z};
+      double n[3] = {u[1] * w[2] - u[2] * w[1], u[2] * w[0] - u[0] * w[2], u[0] * w[1] - u[1] * w[0]};
+      const double n2 = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+      if (n2 > 0.0) { const double nn2 = sqrt(n2); n[0] /= nn2; n[1] /= nn2; n[2] /= nn2; }
+      f[0] = 1.0; f[1] = cp.x; f[2] = cp.y; f[3] = cp.z;
+      f[4] = J.x; f[5] = J.y; f[6] = J.z; f[7] = n[0]; f[8] = n[1]; f[9] = n[2];
+    }
+  } else {
+    outIdx[qi * 2] = closest; outIdx[qi * 2 + 1] = ind2;
+    const bool ok = ind2 >= 0;
+    valid[slot] = ok ? 1 : 0;
+    if (ok) {  // LidarEdgeFactor (LO.cpp:360-381)
+      const float4 A = target[closest], B = target[ind2];
+      f[0] = 0.0; f[1] = cp.x; f[2] = cp.y; f[3] = cp.z;
+      f[4] = A.x; f[5] = A.y; f[6] = A.z; f[7] = B.x; f[8] = B.y; f[9] = B.z;
+    }
+  }
+}
+
 __global__ void lo_accumulate(LoScalars* s) {  // LO.cpp:524-525
   if (threadIdx.x != 0) return;
   double r[3];
@@ -247,9 +443,28 @@ __global__ void lo_set_prior(LoScalars* s, const double* __restrict__ prior) {  
   else if (threadIdx.x < 7) s->para_t[threadIdx.x - 4] = prior[threadIdx.x];
 }
 
-static int lo_ring_tables(vloam_b200_ctx* c, const float4* cornerLast, int nCL, const float4* surfLast, int nSL) {
+// Per-frame structures over the clouds that just became "last" (the reference rebuilds its KD-trees at
+// this point, LO.cpp:573-574): ring tables + monotonicity flags, and the search grid.  The two flags are
+// copied to pinned host memory; the next frame's first sync point makes them readable.
+int vl_lo_build_last(vloam_b200_ctx* c) {
+  const int nc = c->nCornerLast, ns = c->nSurfLast, n = nc + ns;
   VL_LAUNCH(lo_ring_table_init, 1, 32, 0, c->loRingTbl);
-  VL_LAUNCH(lo_ring_table, dim3(vl_div_up(max(max(nCL, nSL), LO_TBL + 1), 256), 2), 256, 0, cornerLast, nCL, surfLast, nSL, c->loRingTbl);
+  VL_LAUNCH(lo_ring_table, dim3(vl_div_up(max(max(nc, ns), LO_TBL + 1), 256), 2), 256, 0, c->cornerLastPtr, nc, c->surfLastPtr, ns, c->loRingTbl);
+  VL_CUDA(cudaMemcpyAsync(&c->h_vScalars[8], c->loRingTbl + LO_TBL, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VL_CUDA(cudaMemcpyAsync(&c->h_vScalars[9], c->loRingTbl + (LO_TBL + 1) + LO_TBL, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VL_TRY(vl_reserve(c, c->loGridCells, (size_t)3 * (2 * LOG_NCELL + 1) + 256));
+  VL_TRY(vl_reserve(c, c->loGridCellOf, (size_t)max(n, 1), false, (size_t)n / 2));
+  VL_TRY(vl_reserve(c, c->loGridSorted, (size_t)max(n, 1), false, (size_t)n / 2));
+  if (n > 0 && n < (1 << 24)) {
+    int* cnt = c->loGridCells.p; int* start = cnt + (2 * LOG_NCELL + 1); int* fill = start + (2 * LOG_NCELL + 1);
+    VL_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * (2 * LOG_NCELL + 1), c->stream));
+    VL_CUDA(cudaMemsetAsync(fill, 0, sizeof(int) * (2 * LOG_NCELL + 1), c->stream));
+    VL_LAUNCH(lo_grid_count, vl_div_up(n, 256), 256, 0, c->cornerLastPtr, nc, c->surfLastPtr, ns, cnt, c->loGridCellOf.p);
+    VL_TRY(vl_scan_exclusive(c, cnt, 2 * LOG_NCELL, fill + (2 * LOG_NCELL + 1), start));
+    VL_LAUNCH(lo_grid_fill, vl_div_up(n, 256), 256, 0, c->cornerLastPtr, nc, c->surfLastPtr, ns, c->loGridCellOf.p, start, fill, c->loGridSorted.p);
+    c->loGridValid = true;
+  } else c->loGridValid = false;
+  VL_CUDA(cudaGetLastError());
   return VLOAM_OK;
 }
 
@@ -259,12 +474,26 @@ static int lo_associate(vloam_b200_ctx* c, const double* d_pose, const float4* c
   VL_TRY(vl_reserve(c, c->loSurfIdx, (size_t)max(nF, 1) * 3));
   VL_TRY(vl_reserve(c, c->factors, (size_t)max(nS + nF, 1) * 10));
   VL_TRY(vl_reserve(c, c->factorValid, (size_t)max(nS + nF, 1)));
-  if (nS > 0)
-    VL_LAUNCH(lo_assoc<false>, vl_div_up(nS, LO_QPB), LO_QPB * 32, 0, c->sharp.p, nS, cornerLast, nCL, d_pose, c->loRingTbl, c->loCornerIdx.p,
-              c->factors.p, c->factorValid.p, 0);
-  if (nF > 0)
-    VL_LAUNCH(lo_assoc<true>, vl_div_up(nF, LO_QPB), LO_QPB * 32, 0, c->flat.p, nF, surfLast, nSL, d_pose, c->loRingTbl + (LO_TBL + 1), c->loSurfIdx.p,
-              c->factors.p, c->factorValid.p, nS);
+  // h_vScalars[8/9]: int(intensity) of the corner / surf cloud is non-decreasing (read after a sync point)
+  const bool gridC = c->loGridValid && c->h_vScalars[8] != 0, gridS = c->loGridValid && c->h_vScalars[9] != 0;
+  const int* start = c->loGridCells.p ? c->loGridCells.p + (2 * LOG_NCELL + 1) : nullptr;
+  if (nS > 0) {
+    if (gridC)
+      VL_LAUNCH(lo_assoc_grid<false>, vl_div_up((long long)nS * 32, 256), 256, 0, c->sharp.p, nS, cornerLast, c->loGridSorted.p, start, d_pose,
+                c->loCornerIdx.p, c->factors.p, c->factorValid.p, 0);
+    else
+      VL_LAUNCH(lo_assoc<false>, vl_div_up(nS, LO_QPB), LO_QPB * 32, 0, c->sharp.p, nS, cornerLast, nCL, d_pose, c->loRingTbl, c->loCornerIdx.p,
+                c->factors.p, c->factorValid.p, 0);
+  }
+  if (nF > 0) {
+    if (gridS) {
+      VL_BYTES(16.0 * nF * 2 * 1500);
+      VL_LAUNCH(lo_assoc_grid<true>, vl_div_up((long long)nF * 32, 256), 256, 0, c->flat.p, nF, surfLast, c->loGridSorted.p, start, d_pose,
+                c->loSurfIdx.p, c->factors.p, c->factorValid.p, nS);
+    } else
+      VL_LAUNCH(lo_assoc<true>, vl_div_up(nF, LO_QPB), LO_QPB * 32, 0, c->flat.p, nF, surfLast, nSL, d_pose, c->loRingTbl + (LO_TBL + 1), c->loSurfIdx.p,
+                c->factors.p, c->factorValid.p, nS);
+  }
   VL_CUDA(cudaGetLastError());
   return VLOAM_OK;
 }
@@ -282,7 +511,6 @@ int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, i
       VL_CUDA(cudaMemcpyAsync(d_prior, h, sizeof h, cudaMemcpyHostToDevice, c->stream));
       VL_CUDA(cudaStreamSynchronize(c->stream));  // h is a stack buffer
     }
-    VL_TRY(lo_ring_tables(c, cornerLast, c->nCornerLast, surfLast, c->nSurfLast));
     for (int pass = 0; pass < 2; ++pass) {  // LO.cpp:224
       if (use_prior) VL_LAUNCH(lo_set_prior, 1, 32, 0, c->los, d_prior);
       VL_TRY(lo_associate(c, d_pose, cornerLast, c->nCornerLast, surfLast, c->nSurfLast));
@@ -300,6 +528,7 @@ int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, i
   // LO.cpp:558-574: this frame's less-sharp / less-flat clouds become the "last" clouds
   c->cornerLastPtr = c->lessSharp[c->cur].p; c->surfLastPtr = c->lessFlat[c->cur].p;
   c->nCornerLast = c->nLessSharp; c->nSurfLast = c->nLessFlat;
+  VL_TRY(vl_lo_build_last(c));  // LO.cpp:573-574: setInputCloud on both KD-trees
   c->lo_frameCount++;
   c->skip_frame = (c->lo_frameCount % c->prm.mapping_skip_frame) != 0;  // LO.cpp:668-678
   VL_CUDA(cudaGetLastError());
@@ -312,7 +541,6 @@ int vl_lo_associate_only(vloam_b200_ctx* c, const double* x, int* corner_idx, in
   double* d_x = reinterpret_cast<double*>(c->vScalars + 32);
   VL_CUDA(cudaMemcpyAsync(d_x, x, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   VL_CUDA(cudaStreamSynchronize(c->stream));
-  VL_TRY(lo_ring_tables(c, c->cornerLastPtr, c->nCornerLast, c->surfLastPtr, c->nSurfLast));
   VL_TRY(lo_associate(c, d_x, c->cornerLastPtr, c->nCornerLast, c->surfLastPtr, c->nSurfLast));
   if (corner_idx && c->nSharp) VL_CUDA(cudaMemcpyAsync(corner_idx, c->loCornerIdx.p, sizeof(int) * 2 * c->nSharp, cudaMemcpyDeviceToHost, c->stream));
   if (surf_idx && c->nFlat) VL_CUDA(cudaMemcpyAsync(surf_idx, c->loSurfIdx.p, sizeof(int) * 3 * c->nFlat, cudaMemcpyDeviceToHost, c->stream));

@@ -73,8 +73,10 @@ __device__ __forceinline__ void lm_factor(const double* __restrict__ f, const do
 __device__ void lm_plus(const double x[7], const double d[6], double o[7]) {
   const double n = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
   if (n > 0.0) {
-    const double s = sin(n) / n;
-    const double dq[4] = {s * d[0], s * d[1], s * d[2], cos(n)};
+    double sn, cs;
+    sincos(n, &sn, &cs);
+    const double s = sn / n;
+    const double dq[4] = {s * d[0], s * d[1], s * d[2], cs};
     vl_qmul(dq, x, o);
   } else { o[0] = x[0]; o[1] = x[1]; o[2] = x[2]; o[3] = x[3]; }
   o[4] = x[4] + d[3]; o[5] = x[5] + d[4]; o[6] = x[6] + d[5];
@@ -82,21 +84,46 @@ __device__ void lm_plus(const double x[7], const double d[6], double o[7]) {
 
 __device__ __forceinline__ int tri(int i, int j) { return i <= j ? i * 6 - i * (i - 1) / 2 + (j - i) : j * 6 - j * (j - 1) / 2 + (i - j); }
 
-// Solve (A) y = b for symmetric positive definite 6x6 A (Cholesky); returns false on breakdown.
-__device__ bool lm_chol6(const double A[6][6], const double b[6], double y[6]) {
-  double L[6][6];
-  for (int i = 0; i < 6; ++i)
-    for (int j = 0; j <= i; ++j) {
-      double s = A[i][j];
-      for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
-      if (i == j) { if (!(s > 0.0)) return false; L[i][i] = sqrt(s); }
-      else L[i][j] = s / L[j][j];
+// Solve A y = b for symmetric positive definite 6x6 A (in-place Cholesky, fully unrolled so
+// every entry lives in a register); returns false on breakdown.
+__device__ __forceinline__ bool lm_chol6(double A[6][6], const double b[6], double y[6]) {
+  double inv[6];
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double s = A[j][j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) s -= A[j][k] * A[j][k];
+    ok = ok && (s > 0.0);
+    const double d = sqrt(s);
+    A[j][j] = d;
+    inv[j] = 1.0 / d;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      double t = A[i][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) t -= A[i][k] * A[j][k];
+      A[i][j] = t * inv[j];
     }
+  }
   double z[6];
-  for (int i = 0; i < 6; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= L[i][k] * z[k]; z[i] = s / L[i][i]; }
-  for (int i = 5; i >= 0; --i) { double s = z[i]; for (int k = i + 1; k < 6; ++k) s -= L[k][i] * y[k]; y[i] = s / L[i][i]; }
-  for (int i = 0; i < 6; ++i) if (!isfinite(y[i])) return false;
-  return true;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double t = b[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) t -= A[i][k] * z[k];
+    z[i] = t * inv[i];
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    double t = z[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) t -= A[k][i] * y[k];
+    y[i] = t * inv[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) ok = ok && isfinite(y[i]);
+  return ok;
 }
 
 __device__ double lm_gmax(const double x[7], const double g[6]) {
@@ -158,29 +185,48 @@ __device__ void lm_logic(LmSolveState* st, const double* e) {
     if (st->iter >= kMaxIter) { st->done = 1; return; }
     st->iter++;
     st->last_successful = 0;
-    double Hs[6][6], gs[6];
+    double Hs[6][6], gs[6], sc[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) sc[i] = st->scale[i];
+#pragma unroll
     for (int i = 0; i < 6; ++i) {
-      gs[i] = st->g[i] * st->scale[i];
-      for (int j = 0; j < 6; ++j) Hs[i][j] = st->H[tri(i, j)] * st->scale[i] * st->scale[j];
+      gs[i] = st->g[i] * sc[i];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) Hs[i][j] = st->H[i <= j ? i * 6 - i * (i - 1) / 2 + (j - i) : j * 6 - j * (j - 1) / 2 + (i - j)] * sc[i] * sc[j];
     }
-    if (!st->reuse_diagonal)
+    if (!st->reuse_diagonal) {
+#pragma unroll
       for (int k = 0; k < 6; ++k) st->diag[k] = fmin(fmax(Hs[k][k], min_diag), max_diag);
+    }
     double A[6][6];
-    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) A[i][j] = Hs[i][j];
-    for (int k = 0; k < 6; ++k) A[k][k] += st->diag[k] / st->radius;  // D^2 = diag / radius
+    const double invr = 1.0 / st->radius;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) A[i][j] = Hs[i][j];
+      A[i][i] += st->diag[i] * invr;  // D^2 = diag / radius
+    }
     double y[6];
     const bool ok = lm_chol6(A, gs, y);
     st->reuse_diagonal = 1;
     double mcc = 0;
     if (ok) {  // model_cost_change = -s'gs - s'Hs s / 2 with s = -y
       double sHs = 0, sg = 0;
-      for (int i = 0; i < 6; ++i) { sg += -y[i] * gs[i]; for (int j = 0; j < 6; ++j) sHs += y[i] * Hs[i][j] * y[j]; }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        sg += -y[i] * gs[i];
+        double row = 0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) row += Hs[i][j] * y[j];
+        sHs += y[i] * row;
+      }
       mcc = -sg - 0.5 * sHs;
     }
     if (!ok || !(mcc > 0.0)) { st->radius /= st->decrease_factor; st->decrease_factor *= 2.0; continue; }
     st->model_cost_change = mcc;
     double delta[6];
-    for (int k = 0; k < 6; ++k) delta[k] = -y[k] * st->scale[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) delta[k] = -y[k] * sc[k];
     lm_plus(st->x, delta, st->xc);
     return;
   }
@@ -202,13 +248,15 @@ __global__ void __launch_bounds__(LM_BLOCK) lm_eval(const double* __restrict__ f
     if (!valid[i]) continue;
     FactorRow fr;
     lm_factor(factors + (size_t)i * 10, x, fr);
-    double s = 0;
-    for (int k = 0; k < fr.nr; ++k) s += fr.r[k] * fr.r[k];
+    double s = fr.r[0] * fr.r[0];
+    if (fr.nr == 3) s = (s + fr.r[1] * fr.r[1]) + fr.r[2] * fr.r[2];
     double rho0, rho1;  // ceres::HuberLoss(0.1)
     if (s > 0.01) { const double r = sqrt(s); rho0 = 2.0 * 0.1 * r - 0.01; rho1 = fmax(DBL_MIN, 0.1 / r); }
     else { rho0 = s; rho1 = 1.0; }
     acc[27] += 0.5 * rho0;
-    for (int k = 0; k < fr.nr; ++k) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (k >= fr.nr) break;
       int t = 0;
 #pragma unroll
       for (int a = 0; a < 6; ++a) {
@@ -296,13 +344,15 @@ lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ val
       if (!valid[i]) continue;
       FactorRow fr;
       lm_factor(factors + (size_t)i * 10, x, fr);
-      double s = 0;
-      for (int k = 0; k < fr.nr; ++k) s += fr.r[k] * fr.r[k];
+      double s = fr.r[0] * fr.r[0];
+      if (fr.nr == 3) s = (s + fr.r[1] * fr.r[1]) + fr.r[2] * fr.r[2];
       double rho0, rho1;  // ceres::HuberLoss(0.1)
       if (s > 0.01) { const double r = sqrt(s); rho0 = 2.0 * 0.1 * r - 0.01; rho1 = fmax(DBL_MIN, 0.1 / r); }
       else { rho0 = s; rho1 = 1.0; }
       acc[27] += 0.5 * rho0;
-      for (int k = 0; k < fr.nr; ++k) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (k >= fr.nr) break;
         int t = 0;
 #pragma unroll
         for (int a = 0; a < 6; ++a) {
