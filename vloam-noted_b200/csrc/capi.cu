@@ -41,6 +41,9 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   VL_CUDA_CREATE(cudaGetDeviceProperties(&prop, device));
   c->num_sms = prop.multiProcessorCount;
   VL_CUDA_CREATE(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  VL_CUDA_CREATE(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evStacks, cudaEventDisableTiming));
+  c->stacksReady = false;
   for (int k = 0; k < 4; ++k) VL_CUDA_CREATE(cudaEventCreate(&c->ev[k]));
   const int R = VL_MAX_RINGS, S = VL_MAX_RINGS * VL_SECTORS;
   VL_CUDA_CREATE(cudaMalloc(&c->ringCount, sizeof(int) * R));
@@ -101,6 +104,9 @@ void vloam_b200_destroy(vloam_b200_ctx* c) {
   for (void* p : bufs) if (p) cudaFree(p);
   cudaFreeHost(c->h_srs); cudaFreeHost(c->h_los); cudaFreeHost(c->h_lms); cudaFreeHost(c->h_lmm); cudaFreeHost(c->h_vScalars);
   for (int k = 0; k < 4; ++k) cudaEventDestroy(c->ev[k]);
+  cudaStreamSynchronize(c->stream2);
+  cudaEventDestroy(c->evStacks);
+  cudaStreamDestroy(c->stream2);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -209,7 +215,7 @@ int vloam_b200_process_frame_device(vloam_b200_ctx* c, const float* d_xyz, int n
   return process_common(c, pose_out);
 }
 
-int vloam_b200_synchronize(vloam_b200_ctx* c) { VL_CUDA(cudaStreamSynchronize(c->stream)); return VLOAM_OK; }
+int vloam_b200_synchronize(vloam_b200_ctx* c) { VL_CUDA(cudaStreamSynchronize(c->stream2)); VL_CUDA(cudaStreamSynchronize(c->stream)); return VLOAM_OK; }
 void* vloam_b200_stream(vloam_b200_ctx* c) { return (void*)c->stream; }
 long long vloam_b200_kernel_launches(const vloam_b200_ctx* c) { return c->launches; }
 int vloam_b200_set_timing(vloam_b200_ctx* c, int enabled) { c->timing = enabled != 0; return VLOAM_OK; }

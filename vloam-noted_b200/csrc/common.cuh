@@ -87,6 +87,9 @@ struct vloam_b200_ctx {
   vloam_b200_params prm;
   int device;
   cudaStream_t stream;
+  cudaStream_t stream2;       // side stream: work that is independent of the odometry solve overlaps it
+  cudaEvent_t evStacks;       // this frame's downsampled stacks are ready
+  bool stacksReady;
   char err[512];
   long long launches;
   int num_sms;
@@ -237,6 +240,7 @@ int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, i
 int vl_lo_associate_only(vloam_b200_ctx* c, const double* x, int* corner_idx, int* surf_idx);
 int vl_lo_build_last(vloam_b200_ctx* c);
 int vl_lm_run(vloam_b200_ctx* c);
+int vl_lm_enqueue_stacks(vloam_b200_ctx* c, const float4* corner, int nc, const float4* surf, int ns);
 int vl_lm_init(vloam_b200_ctx* c);
 int vl_lm_export_map(vloam_b200_ctx* c, int which, void* out, long cap, long* bytes);
 int vl_lm_import_map(vloam_b200_ctx* c, int which, const void* data, long bytes);

@@ -906,6 +906,24 @@ int vl_lm_init(vloam_b200_ctx* c) {
 
 extern bool vl_debug_capture(const vloam_b200_ctx* c);
 
+// LM.cpp:492-500: VoxelGrid of this frame's less-sharp / less-flat clouds.  They depend on scan
+// registration only, so the odometry stage enqueues them on the side stream right after its first sync
+// point and they run underneath the odometry kernels; solveMapping waits on evStacks.
+int vl_lm_enqueue_stacks(vloam_b200_ctx* c, const float4* corner, int nc, const float4* surf, int ns) {
+  LmDevice* d = lmdev(c);
+  cudaStream_t main = c->stream;
+  c->stream = c->stream2;
+  int r = vl_reserve(c, c->stackC, (size_t)max(nc, 1));
+  if (r == VLOAM_OK) r = vl_reserve(c, c->stackS, (size_t)max(ns, 1));
+  if (r == VLOAM_OK) r = vl_voxel_grid_device(c, corner, nc, nullptr, c->prm.line_res, c->stackC.p, d->dQ);
+  if (r == VLOAM_OK) r = vl_voxel_grid_device(c, surf, ns, nullptr, c->prm.plane_res, c->stackS.p, d->dQ + 1);
+  c->stream = main;
+  if (r != VLOAM_OK) return r;
+  VL_CUDA(cudaEventRecord(c->evStacks, c->stream2));
+  c->stacksReady = true;
+  return VLOAM_OK;
+}
+
 int vl_lm_run(vloam_b200_ctx* c) {
   LmDevice* d = lmdev(c);
   const int skip = c->skip_frame ? 1 : 0;
@@ -916,11 +934,12 @@ int vl_lm_run(vloam_b200_ctx* c) {
   VL_TRY(vl_reserve(c, c->fromMapS, (size_t)max(d->hMapUpperS, 1LL), false, (size_t)d->hMapUpperS / 2 + (1 << 20)));
   VL_BYTES(32.0 * (double)(d->hMapUpperC + d->hMapUpperS));  // upper bound until the S2 sync; refined below
   VL_LAUNCH(lm_gather, gsGrid, 256, 0, c->lmm, d->work, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, c->fromMapC.p, c->fromMapS.p);
-  // LM.cpp:492-500: VoxelGrid of this frame's less-sharp / less-flat clouds
-  VL_TRY(vl_reserve(c, c->stackC, (size_t)max(c->nCornerLast, 1)));
-  VL_TRY(vl_reserve(c, c->stackS, (size_t)max(c->nSurfLast, 1)));
-  VL_TRY(vl_voxel_grid_device(c, c->cornerLastPtr, c->nCornerLast, nullptr, c->prm.line_res, c->stackC.p, d->dQ));
-  VL_TRY(vl_voxel_grid_device(c, c->surfLastPtr, c->nSurfLast, nullptr, c->prm.plane_res, c->stackS.p, d->dQ + 1));
+  if (!c->stacksReady) {  // laser_mapping called without this frame's laser_odometry having queued them
+    VL_CUDA(cudaStreamSynchronize(c->stream));
+    VL_TRY(vl_lm_enqueue_stacks(c, c->cornerLastPtr, c->nCornerLast, c->surfLastPtr, c->nSurfLast));
+  }
+  VL_CUDA(cudaStreamWaitEvent(c->stream, c->evStacks, 0));
+  c->stacksReady = false;
   VL_LAUNCH(lm_set_counts, 1, 32, 0, c->lmm, d->dQ, d->dQ + 1);
   // ---- sync point S2
   VL_CUDA(cudaMemcpyAsync(c->h_lmm, c->lmm, sizeof(LmScalars), cudaMemcpyDeviceToHost, c->stream));

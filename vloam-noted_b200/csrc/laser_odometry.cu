@@ -502,6 +502,8 @@ extern bool vl_debug_capture(const vloam_b200_ctx* c);
 
 int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, int use_prior) {
   VL_TRY(vl_sr_sync_counts(c));  // sync point S1
+  if (((c->lo_frameCount + 1) % c->prm.mapping_skip_frame) == 0)  // mapping will run on this frame (LO.cpp:668)
+    VL_TRY(vl_lm_enqueue_stacks(c, c->lessSharp[c->cur].p, c->nLessSharp, c->lessFlat[c->cur].p, c->nLessFlat));
   double* d_pose = c->los->para_q;  // para_q[4] + para_t[3] are contiguous
   if (c->lo_inited) {  // LO.cpp:209-217: the first frame only initialises
     const float4* cornerLast = c->cornerLastPtr; const float4* surfLast = c->surfLastPtr;

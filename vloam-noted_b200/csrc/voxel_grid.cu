@@ -71,6 +71,41 @@ __global__ void __launch_bounds__(BT_THREADS) bt_tile_merge(unsigned long long* 
   for (int t = threadIdx.x; t < tile; t += BT_THREADS) keys[base + t] = s[t];
 }
 
+
+// Strides j = jtop, jtop/2, ..., 1 of one bitonic merge level inside a shared-memory tile, two strides
+// per barrier: a thread owns the 4 elements {i, i+h, i+j, i+j+h} (h = j/2), which are closed under both
+// compare-exchange steps, so the pair of stages needs one __syncthreads instead of two.
+template <int THREADS>
+__device__ __forceinline__ void bt_smem_strides(unsigned long long* s, int tile, int jtop, size_t base, int k, bool uniformUp, bool upAll) {
+  int j = jtop;
+  while (j >= 2) {
+    const int h = j >> 1;
+    const int lh = __ffs(h) - 1;
+    for (int u = threadIdx.x; u < (tile >> 2); u += THREADS) {
+      const int i0 = ((u >> lh) << (lh + 2)) | (u & (h - 1));
+      const bool up = uniformUp ? upAll : (((base + i0) & (size_t)k) == 0);
+      unsigned long long a = s[i0], b = s[i0 + h], c = s[i0 + j], d = s[i0 + j + h];
+      unsigned long long t;
+      if ((a > c) == up) { t = a; a = c; c = t; }
+      if ((b > d) == up) { t = b; b = d; d = t; }
+      if ((a > b) == up) { t = a; a = b; b = t; }
+      if ((c > d) == up) { t = c; c = d; d = t; }
+      s[i0] = a; s[i0 + h] = b; s[i0 + j] = c; s[i0 + j + h] = d;
+    }
+    __syncthreads();
+    j >>= 2;
+  }
+  if (j == 1) {
+    for (int u = threadIdx.x; u < (tile >> 1); u += THREADS) {
+      const int i = u << 1;
+      const bool up = uniformUp ? upAll : (((base + i) & (size_t)k) == 0);
+      const unsigned long long a = s[i], b = s[i + 1];
+      if ((a > b) == up) { s[i] = b; s[i + 1] = a; }
+    }
+    __syncthreads();
+  }
+}
+
 // ---- single-launch sort: one thread-block cluster, tiles in distributed shared memory -----------
 // Up to 16 CTAs x 8192 keys.  Every CTA bitonic-sorts its tile in shared memory; the strides that
 // cross tiles read the partner tile through DSMEM (cluster.map_shared_rank) and write the result
@@ -88,18 +123,7 @@ __global__ void __launch_bounds__(CS_THREADS) bt_cluster_sort(unsigned long long
   unsigned long long* alt = cs + tile;
   for (int t = threadIdx.x; t < tile; t += CS_THREADS) cur[t] = keys[base + t];
   __syncthreads();
-  const int half = tile >> 1;
-  for (int k = 2; k <= tile; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int u = threadIdx.x; u < half; u += CS_THREADS) {
-        const int i = ((u & ~(j - 1)) << 1) | (u & (j - 1));
-        const int l = i | j;
-        const unsigned long long a = cur[i], b = cur[l];
-        const bool up = ((base + i) & (size_t)k) == 0;
-        if ((a > b) == up) { cur[i] = b; cur[l] = a; }
-      }
-      __syncthreads();
-    }
+  for (int k = 2; k <= tile; k <<= 1) bt_smem_strides<CS_THREADS>(cur, tile, k >> 1, base, k, false, false);
   for (int k = tile << 1; k <= n; k <<= 1) {
     for (int j = k >> 1; j >= tile; j >>= 1) {
       cluster.sync();  // partner tiles are complete in `cur`
@@ -117,16 +141,7 @@ __global__ void __launch_bounds__(CS_THREADS) bt_cluster_sort(unsigned long long
     // every CTA flipped buffers the same number of times, so `cur` means the same half everywhere;
     // the barrier below also keeps a fast CTA from overwriting `alt` while a partner still reads it
     cluster.sync();
-    const bool up = (base & (size_t)k) == 0;
-    for (int j = tile >> 1; j > 0; j >>= 1) {
-      for (int u = threadIdx.x; u < half; u += CS_THREADS) {
-        const int i = ((u & ~(j - 1)) << 1) | (u & (j - 1));
-        const int l = i | j;
-        const unsigned long long a = cur[i], b = cur[l];
-        if ((a > b) == up) { cur[i] = b; cur[l] = a; }
-      }
-      __syncthreads();
-    }
+    bt_smem_strides<CS_THREADS>(cur, tile, tile >> 1, base, k, true, (base & (size_t)k) == 0);
   }
   for (int t = threadIdx.x; t < tile; t += CS_THREADS) keys[base + t] = cur[t];
   cluster.sync();  // no CTA exits while a partner may still read its shared memory
