@@ -208,6 +208,7 @@ def run_ours(args, rank, world_size, local_rank):
     e0.record(ext)
     for k in range(W + 1, W + 1 + K):
         ctx.process_frame_device(dscans[k].data_ptr(), dscans[k].shape[0], 4)
+    ctx.synchronize()  # the last frame's map update runs on a side stream: include it
     e1.record(ext)
     ctx.synchronize(); torch.cuda.synchronize()
     if dist: dist.barrier()

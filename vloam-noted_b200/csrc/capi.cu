@@ -31,7 +31,7 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   VL_CUDA_CREATE(cudaSetDevice(device));
   vloam_b200_ctx* c = new vloam_b200_ctx();
   c->prm = *p; c->device = device; c->err[0] = 0; c->launches = 0; c->timing = false; c->cur = 0;
-  c->sr_counts_valid = false; c->n_in = 0; c->lo_inited = false; c->lo_frameCount = 0; c->lm_frameCount = 0; c->lm_optimized = 0; c->loGridValid = false; c->skip_frame = false;
+  c->sr_counts_valid = false; c->n_in = 0; c->lo_inited = false; c->lo_frameCount = 0; c->lm_frameCount = 0; c->lm_optimized = 0; c->skip_frame = false;
   c->nKept = c->nSharp = c->nLessSharp = c->nFlat = c->nLessFlat = 0; c->nCornerLast = c->nSurfLast = 0;
   c->cornerLastPtr = nullptr; c->surfLastPtr = nullptr;
   for (int k = 0; k < 4; ++k) c->dbgLoCost[k] = c->dbgLmCost[k] = 0;
@@ -42,8 +42,12 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   c->num_sms = prop.multiProcessorCount;
   VL_CUDA_CREATE(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   VL_CUDA_CREATE(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  VL_CUDA_CREATE(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evStacks, cudaEventDisableTiming));
-  c->stacksReady = false;
+  VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evLast, cudaEventDisableTiming));
+  VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evPose, cudaEventDisableTiming));
+  VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evMap, cudaEventDisableTiming));
+  c->stacksReady = false; c->lm_reset_pending = true; c->lastSet = 0; c->loGridValid[0] = c->loGridValid[1] = false;
   for (int k = 0; k < 4; ++k) VL_CUDA_CREATE(cudaEventCreate(&c->ev[k]));
   const int R = VL_MAX_RINGS, S = VL_MAX_RINGS * VL_SECTORS;
   VL_CUDA_CREATE(cudaMalloc(&c->ringCount, sizeof(int) * R));
@@ -66,7 +70,7 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   LoScalars hl; memset(&hl, 0, sizeof hl); hl.para_q[3] = 1.0; hl.q_w[3] = 1.0;  // LO.cpp:81-91
   VL_CUDA_CREATE(cudaMemcpy(c->los, &hl, sizeof hl, cudaMemcpyHostToDevice));
   *c->h_los = hl;
-  VL_CUDA_CREATE(cudaMalloc(&c->loRingTbl, sizeof(int) * 2 * 160));
+  VL_CUDA_CREATE(cudaMalloc(&c->loRingTbl, sizeof(int) * 4 * 160));
   VL_CUDA_CREATE(cudaMalloc(&c->evalOut, sizeof(EvalOut)));
   VL_CUDA_CREATE(cudaMalloc(&c->lms, sizeof(LmSolveState)));
   VL_CUDA_CREATE(cudaMemset(c->lms, 0, sizeof(LmSolveState)));
@@ -90,7 +94,7 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
 void vloam_b200_destroy(vloam_b200_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream3);
   // Device memory is released wholesale: contexts live for a whole replay (MAIN.cpp:118-124).
   void* singles[] = {c->ringCount, c->ringStart, c->srs, c->provSharp, c->provLess, c->provFlat, c->cntSharp, c->cntLess, c->cntFlat,
                      c->offSharp, c->offLess, c->offFlat, c->ringDsCount, c->ringDsOff, c->los, c->evalOut, c->lms, c->lmm, c->cubeC,
@@ -104,18 +108,16 @@ void vloam_b200_destroy(vloam_b200_ctx* c) {
   for (void* p : bufs) if (p) cudaFree(p);
   cudaFreeHost(c->h_srs); cudaFreeHost(c->h_los); cudaFreeHost(c->h_lms); cudaFreeHost(c->h_lmm); cudaFreeHost(c->h_vScalars);
   for (int k = 0; k < 4; ++k) cudaEventDestroy(c->ev[k]);
-  cudaStreamSynchronize(c->stream2);
-  cudaEventDestroy(c->evStacks);
-  cudaStreamDestroy(c->stream2);
+  cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream3);
+  cudaEventDestroy(c->evStacks); cudaEventDestroy(c->evLast); cudaEventDestroy(c->evPose); cudaEventDestroy(c->evMap);
+  cudaStreamDestroy(c->stream2); cudaStreamDestroy(c->stream3);
   cudaStreamDestroy(c->stream);
   delete c;
 }
 
-__global__ void k_begin_frame(LmScalars* s) { if (threadIdx.x == 0) s->validNum = 0; }  // LM.cpp:132-136
-
 int vloam_b200_begin_frame(vloam_b200_ctx* c) {
   VL_CUDA(cudaSetDevice(c->device));
-  VL_LAUNCH(k_begin_frame, 1, 32, 0, c->lmm);
+  c->lm_reset_pending = true;  // applied by the next solveMapping (the map update of the previous frame may still be reading the list)
   return VLOAM_OK;
 }
 
@@ -215,7 +217,10 @@ int vloam_b200_process_frame_device(vloam_b200_ctx* c, const float* d_xyz, int n
   return process_common(c, pose_out);
 }
 
-int vloam_b200_synchronize(vloam_b200_ctx* c) { VL_CUDA(cudaStreamSynchronize(c->stream2)); VL_CUDA(cudaStreamSynchronize(c->stream)); return VLOAM_OK; }
+int vloam_b200_synchronize(vloam_b200_ctx* c) {
+  VL_CUDA(cudaStreamSynchronize(c->stream)); VL_CUDA(cudaStreamSynchronize(c->stream2)); VL_CUDA(cudaStreamSynchronize(c->stream3));
+  return VLOAM_OK;
+}
 void* vloam_b200_stream(vloam_b200_ctx* c) { return (void*)c->stream; }
 long long vloam_b200_kernel_launches(const vloam_b200_ctx* c) { return c->launches; }
 int vloam_b200_set_timing(vloam_b200_ctx* c, int enabled) { c->timing = enabled != 0; return VLOAM_OK; }
@@ -262,7 +267,7 @@ static long put_host(const void* src, size_t bytes, void* out, long cap) { if (o
 long vloam_b200_debug_get(vloam_b200_ctx* c, const char* name, void* out, long cap) {
   const std::string n(name);
   if (n.rfind("sr.", 0) == 0 || n.rfind("lo.", 0) == 0) { if (vl_sr_sync_counts(c) != VLOAM_OK) return VLOAM_E_CUDA; }
-  if (cudaStreamSynchronize(c->stream) != cudaSuccess) return VLOAM_E_CUDA;
+  if (vloam_b200_synchronize(c) != VLOAM_OK) return VLOAM_E_CUDA;
   if (n == "sr.laserCloud") return put_dev(c, c->cloud.p, (size_t)c->nKept * 16, out, cap);
   if (n == "sr.sharp") return put_dev(c, c->sharp.p, (size_t)c->nSharp * 16, out, cap);
   if (n == "sr.lessSharp") return put_dev(c, c->lessSharp[c->cur].p, (size_t)c->nLessSharp * 16, out, cap);
@@ -323,7 +328,7 @@ long vloam_b200_debug_get(vloam_b200_ctx* c, const char* name, void* out, long c
 
 int vloam_b200_debug_set(vloam_b200_ctx* c, const char* name, const void* data, long bytes) {
   const std::string n(name);
-  VL_CUDA(cudaStreamSynchronize(c->stream));
+  VL_TRY(vloam_b200_synchronize(c));
   if (n == "debug.capture") { c->h_vScalars[0] = (bytes >= 4 && *(const int*)data) ? 1 : 0; return VLOAM_OK; }
   if (n == "lo.last") {  // blob: int nc, int ns, corner points, surf points  (the state solveLO swaps in, LO.cpp:558-574)
     const int* hdr = (const int*)data;
@@ -339,7 +344,7 @@ int vloam_b200_debug_set(vloam_b200_ctx* c, const char* name, const void* data, 
     c->cornerLastPtr = c->lessSharp[o].p; c->surfLastPtr = c->lessFlat[o].p;
     c->nCornerLast = hdr[0]; c->nSurfLast = hdr[1];
     c->lo_inited = true;
-    VL_TRY(vl_lo_build_last(c));
+    VL_TRY(vl_lo_build_last(c, c->lastSet, c->cornerLastPtr, c->nCornerLast, c->surfLastPtr, c->nSurfLast));
     VL_CUDA(cudaStreamSynchronize(c->stream));
     return VLOAM_OK;
   }

@@ -88,8 +88,13 @@ struct vloam_b200_ctx {
   int device;
   cudaStream_t stream;
   cudaStream_t stream2;       // side stream: work that is independent of the odometry solve overlaps it
+  cudaStream_t stream3;       // map update of frame k runs here while frame k+1's scan registration / odometry run on `stream`
   cudaEvent_t evStacks;       // this frame's downsampled stacks are ready
+  cudaEvent_t evLast;         // search structures over the next "last" clouds are built
+  cudaEvent_t evPose;         // solveMapping's pose is final (the map update may start)
+  cudaEvent_t evMap;          // the map update has finished (the next solveMapping may start)
   bool stacksReady;
+  bool lm_reset_pending;      // LaserMapping::reset was called since the last solveMapping
   char err[512];
   long long launches;
   int num_sms;
@@ -128,8 +133,11 @@ struct vloam_b200_ctx {
   int nCornerLast, nSurfLast;  // host counts of the "last" clouds (= other buffer of the pair)
   bool lo_inited; int lo_frameCount;
   float4* cornerLastPtr; float4* surfLastPtr;  // after solveLO's swap
-  int* loRingTbl;                     // 2 x (144 + 1) ints: ring-value -> first index tables of the last clouds
-  DBuf<int> loGridCells, loGridCellOf; DBuf<float4> loGridSorted; bool loGridValid;  // 5.12 m search grid over the last clouds
+  // search structures over the "last" clouds, double-buffered: set [lastSet] serves this frame's odometry
+  // while the side stream builds set [lastSet ^ 1] from this frame's clouds
+  int* loRingTbl;                     // 2 sets x 2 clouds x (144 + 1) ints: ring-value -> first index tables
+  DBuf<int> loGridCells[2], loGridCellOf; DBuf<float4> loGridSorted[2]; bool loGridValid[2];
+  int lastSet;
   DBuf<int> loCornerIdx, loSurfIdx;   // association results (2 / 3 ints per query)
   DBuf<double> factors;               // 10 doubles per factor slot
   DBuf<int> factorValid;
@@ -238,7 +246,7 @@ int vl_sr_run(vloam_b200_ctx* c, const float* d_xyz, int n, int stride);
 int vl_sr_sync_counts(vloam_b200_ctx* c);
 int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, int use_prior);
 int vl_lo_associate_only(vloam_b200_ctx* c, const double* x, int* corner_idx, int* surf_idx);
-int vl_lo_build_last(vloam_b200_ctx* c);
+int vl_lo_build_last(vloam_b200_ctx* c, int set, const float4* corner, int nc, const float4* surf, int ns);
 int vl_lm_run(vloam_b200_ctx* c);
 int vl_lm_enqueue_stacks(vloam_b200_ctx* c, const float4* corner, int nc, const float4* surf, int ns);
 int vl_lm_init(vloam_b200_ctx* c);

@@ -88,10 +88,11 @@ __device__ __forceinline__ int lm_scan256(int v, int* buf, int* total) {
 
 // ---- LaserMapping::input (LM.cpp:178-209) + centre cube / roll / valid list (LM.cpp:228-466)
 __global__ void __launch_bounds__(1024) lm_prepare(LmScalars* __restrict__ s, const LoScalars* __restrict__ lo, MapCubeTable* __restrict__ tc,
-                                                   MapCubeTable* __restrict__ ts, RfWork* __restrict__ w, int skip) {
+                                                   MapCubeTable* __restrict__ ts, RfWork* __restrict__ w, int skip, int resetValid) {
   __shared__ int shift[3];
   __shared__ int center[3];
   if (threadIdx.x == 0) {
+    if (resetValid) s->validNum = 0;  // LaserMapping::reset (LM.cpp:132-136)
     for (int k = 0; k < 4; ++k) s->q_wodom[k] = lo->q_w[k];
     for (int k = 0; k < 3; ++k) s->t_wodom[k] = lo->t_w[k];
     double r[3];
@@ -913,6 +914,7 @@ int vl_lm_enqueue_stacks(vloam_b200_ctx* c, const float4* corner, int nc, const 
   LmDevice* d = lmdev(c);
   cudaStream_t main = c->stream;
   c->stream = c->stream2;
+  cudaStreamWaitEvent(c->stream2, c->evMap, 0);  // the previous frame's map update still reads the previous stacks
   int r = vl_reserve(c, c->stackC, (size_t)max(nc, 1));
   if (r == VLOAM_OK) r = vl_reserve(c, c->stackS, (size_t)max(ns, 1));
   if (r == VLOAM_OK) r = vl_voxel_grid_device(c, corner, nc, nullptr, c->prm.line_res, c->stackC.p, d->dQ);
@@ -927,7 +929,9 @@ int vl_lm_enqueue_stacks(vloam_b200_ctx* c, const float4* corner, int nc, const 
 int vl_lm_run(vloam_b200_ctx* c) {
   LmDevice* d = lmdev(c);
   const int skip = c->skip_frame ? 1 : 0;
-  VL_LAUNCH(lm_prepare, 1, 1024, 0, c->lmm, c->los, c->cubeC, c->cubeS, d->work, skip);
+  VL_CUDA(cudaStreamWaitEvent(c->stream, c->evMap, 0));  // the previous frame's map update (stream3) must be complete
+  VL_LAUNCH(lm_prepare, 1, 1024, 0, c->lmm, c->los, c->cubeC, c->cubeS, d->work, skip, c->lm_reset_pending ? 1 : 0);
+  c->lm_reset_pending = false;
   if (skip) { VL_CUDA(cudaGetLastError()); return VLOAM_OK; }
   const int gsGrid = c->num_sms * 8;
   VL_TRY(vl_reserve(c, c->fromMapC, (size_t)max(d->hMapUpperC, 1LL), false, (size_t)d->hMapUpperC / 2 + (1 << 20)));
@@ -987,7 +991,13 @@ int vl_lm_run(vloam_b200_ctx* c) {
   }
   c->lm_optimized = optimized ? 1 : 0;
   VL_LAUNCH(lm_transform_update, 1, 32, 0, c->lmm);  // LM.cpp:737 (runs even when the optimisation was skipped)
-  // ---- map update
+  // ---- map update (LM.cpp:741-808).  The pose is final here; the update runs on stream3 so that the caller can
+  // read the pose, and the next frame's scan registration + odometry can start, while the map is brought up to date.
+  VL_CUDA(cudaEventRecord(c->evPose, c->stream));
+  cudaStream_t mainStream = c->stream;
+  c->stream = c->stream3;
+  const int rmap = [&]() -> int {
+  VL_CUDA(cudaStreamWaitEvent(c->stream3, c->evPose, 0));
   const int nKeys = tailTotal + nq;
   if (nKeys > 0) {
     int P = 2; while (P < nKeys) P <<= 1;
@@ -1015,6 +1025,11 @@ int vl_lm_run(vloam_b200_ctx* c) {
       VL_LAUNCH(rf_append_outside, 1, 1024, 0, c->lmm, d->newPts.p, d->newCube.p, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, (int)c->poolC.cap,
                 (int)c->poolS.cap);
   }
+  VL_CUDA(cudaEventRecord(c->evMap, c->stream3));
+  return VLOAM_OK;
+  }();
+  c->stream = mainStream;
+  if (rmap != VLOAM_OK) return rmap;
   d->hMapUpperC += Qc; d->hMapUpperS += Qs;
   c->lm_frameCount++;
   VL_CUDA(cudaGetLastError());

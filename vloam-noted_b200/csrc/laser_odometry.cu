@@ -446,24 +446,25 @@ __global__ void lo_set_prior(LoScalars* s, const double* __restrict__ prior) {  
 // Per-frame structures over the clouds that just became "last" (the reference rebuilds its KD-trees at
 // this point, LO.cpp:573-574): ring tables + monotonicity flags, and the search grid.  The two flags are
 // copied to pinned host memory; the next frame's first sync point makes them readable.
-int vl_lo_build_last(vloam_b200_ctx* c) {
-  const int nc = c->nCornerLast, ns = c->nSurfLast, n = nc + ns;
-  VL_LAUNCH(lo_ring_table_init, 1, 32, 0, c->loRingTbl);
-  VL_LAUNCH(lo_ring_table, dim3(vl_div_up(max(max(nc, ns), LO_TBL + 1), 256), 2), 256, 0, c->cornerLastPtr, nc, c->surfLastPtr, ns, c->loRingTbl);
-  VL_CUDA(cudaMemcpyAsync(&c->h_vScalars[8], c->loRingTbl + LO_TBL, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  VL_CUDA(cudaMemcpyAsync(&c->h_vScalars[9], c->loRingTbl + (LO_TBL + 1) + LO_TBL, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  VL_TRY(vl_reserve(c, c->loGridCells, (size_t)3 * (2 * LOG_NCELL + 1) + 256));
+int vl_lo_build_last(vloam_b200_ctx* c, int set, const float4* corner, int nc, const float4* surf, int ns) {
+  const int n = nc + ns;
+  int* tbl = c->loRingTbl + set * 2 * (LO_TBL + 1);
+  VL_LAUNCH(lo_ring_table_init, 1, 32, 0, tbl);
+  VL_LAUNCH(lo_ring_table, dim3(vl_div_up(max(max(nc, ns), LO_TBL + 1), 256), 2), 256, 0, corner, nc, surf, ns, tbl);
+  VL_CUDA(cudaMemcpyAsync(&c->h_vScalars[8 + 2 * set], tbl + LO_TBL, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VL_CUDA(cudaMemcpyAsync(&c->h_vScalars[9 + 2 * set], tbl + (LO_TBL + 1) + LO_TBL, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VL_TRY(vl_reserve(c, c->loGridCells[set], (size_t)3 * (2 * LOG_NCELL + 1) + 256));
   VL_TRY(vl_reserve(c, c->loGridCellOf, (size_t)max(n, 1), false, (size_t)n / 2));
-  VL_TRY(vl_reserve(c, c->loGridSorted, (size_t)max(n, 1), false, (size_t)n / 2));
+  VL_TRY(vl_reserve(c, c->loGridSorted[set], (size_t)max(n, 1), false, (size_t)n / 2));
   if (n > 0 && n < (1 << 24)) {
-    int* cnt = c->loGridCells.p; int* start = cnt + (2 * LOG_NCELL + 1); int* fill = start + (2 * LOG_NCELL + 1);
+    int* cnt = c->loGridCells[set].p; int* start = cnt + (2 * LOG_NCELL + 1); int* fill = start + (2 * LOG_NCELL + 1);
     VL_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * (2 * LOG_NCELL + 1), c->stream));
     VL_CUDA(cudaMemsetAsync(fill, 0, sizeof(int) * (2 * LOG_NCELL + 1), c->stream));
-    VL_LAUNCH(lo_grid_count, vl_div_up(n, 256), 256, 0, c->cornerLastPtr, nc, c->surfLastPtr, ns, cnt, c->loGridCellOf.p);
+    VL_LAUNCH(lo_grid_count, vl_div_up(n, 256), 256, 0, corner, nc, surf, ns, cnt, c->loGridCellOf.p);
     VL_TRY(vl_scan_exclusive(c, cnt, 2 * LOG_NCELL, fill + (2 * LOG_NCELL + 1), start));
-    VL_LAUNCH(lo_grid_fill, vl_div_up(n, 256), 256, 0, c->cornerLastPtr, nc, c->surfLastPtr, ns, c->loGridCellOf.p, start, fill, c->loGridSorted.p);
-    c->loGridValid = true;
-  } else c->loGridValid = false;
+    VL_LAUNCH(lo_grid_fill, vl_div_up(n, 256), 256, 0, corner, nc, surf, ns, c->loGridCellOf.p, start, fill, c->loGridSorted[set].p);
+    c->loGridValid[set] = true;
+  } else c->loGridValid[set] = false;
   VL_CUDA(cudaGetLastError());
   return VLOAM_OK;
 }
@@ -475,23 +476,26 @@ static int lo_associate(vloam_b200_ctx* c, const double* d_pose, const float4* c
   VL_TRY(vl_reserve(c, c->factors, (size_t)max(nS + nF, 1) * 10));
   VL_TRY(vl_reserve(c, c->factorValid, (size_t)max(nS + nF, 1)));
   // h_vScalars[8/9]: int(intensity) of the corner / surf cloud is non-decreasing (read after a sync point)
-  const bool gridC = c->loGridValid && c->h_vScalars[8] != 0, gridS = c->loGridValid && c->h_vScalars[9] != 0;
-  const int* start = c->loGridCells.p ? c->loGridCells.p + (2 * LOG_NCELL + 1) : nullptr;
+  const int set = c->lastSet;
+  const bool gridC = c->loGridValid[set] && c->h_vScalars[8 + 2 * set] != 0, gridS = c->loGridValid[set] && c->h_vScalars[9 + 2 * set] != 0;
+  const int* start = c->loGridCells[set].p ? c->loGridCells[set].p + (2 * LOG_NCELL + 1) : nullptr;
+  const float4* gsorted = c->loGridSorted[set].p;
+  const int* rtbl = c->loRingTbl + set * 2 * (LO_TBL + 1);
   if (nS > 0) {
     if (gridC)
-      VL_LAUNCH(lo_assoc_grid<false>, vl_div_up((long long)nS * 32, 256), 256, 0, c->sharp.p, nS, cornerLast, c->loGridSorted.p, start, d_pose,
+      VL_LAUNCH(lo_assoc_grid<false>, vl_div_up((long long)nS * 32, 256), 256, 0, c->sharp.p, nS, cornerLast, gsorted, start, d_pose,
                 c->loCornerIdx.p, c->factors.p, c->factorValid.p, 0);
     else
-      VL_LAUNCH(lo_assoc<false>, vl_div_up(nS, LO_QPB), LO_QPB * 32, 0, c->sharp.p, nS, cornerLast, nCL, d_pose, c->loRingTbl, c->loCornerIdx.p,
+      VL_LAUNCH(lo_assoc<false>, vl_div_up(nS, LO_QPB), LO_QPB * 32, 0, c->sharp.p, nS, cornerLast, nCL, d_pose, rtbl, c->loCornerIdx.p,
                 c->factors.p, c->factorValid.p, 0);
   }
   if (nF > 0) {
     if (gridS) {
       VL_BYTES(16.0 * nF * 2 * 1500);
-      VL_LAUNCH(lo_assoc_grid<true>, vl_div_up((long long)nF * 32, 256), 256, 0, c->flat.p, nF, surfLast, c->loGridSorted.p, start, d_pose,
+      VL_LAUNCH(lo_assoc_grid<true>, vl_div_up((long long)nF * 32, 256), 256, 0, c->flat.p, nF, surfLast, gsorted, start, d_pose,
                 c->loSurfIdx.p, c->factors.p, c->factorValid.p, nS);
     } else
-      VL_LAUNCH(lo_assoc<true>, vl_div_up(nF, LO_QPB), LO_QPB * 32, 0, c->flat.p, nF, surfLast, nSL, d_pose, c->loRingTbl + (LO_TBL + 1), c->loSurfIdx.p,
+      VL_LAUNCH(lo_assoc<true>, vl_div_up(nF, LO_QPB), LO_QPB * 32, 0, c->flat.p, nF, surfLast, nSL, d_pose, rtbl + (LO_TBL + 1), c->loSurfIdx.p,
                 c->factors.p, c->factorValid.p, nS);
   }
   VL_CUDA(cudaGetLastError());
@@ -502,8 +506,19 @@ extern bool vl_debug_capture(const vloam_b200_ctx* c);
 
 int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, int use_prior) {
   VL_TRY(vl_sr_sync_counts(c));  // sync point S1
+  VL_CUDA(cudaEventSynchronize(c->evLast));  // set [lastSet] (built underneath the previous frame) and its flags are complete
   if (((c->lo_frameCount + 1) % c->prm.mapping_skip_frame) == 0)  // mapping will run on this frame (LO.cpp:668)
     VL_TRY(vl_lm_enqueue_stacks(c, c->lessSharp[c->cur].p, c->nLessSharp, c->lessFlat[c->cur].p, c->nLessFlat));
+  {  // LO.cpp:573-574 (setInputCloud on both KD-trees) for the clouds that become "last" after this solve:
+     // they are this frame's less-sharp / less-flat clouds, final since scan registration, so the side
+     // stream builds them while the odometry below still searches the previous set
+    cudaStream_t mainStream = c->stream;
+    c->stream = c->stream2;
+    const int r = vl_lo_build_last(c, c->lastSet ^ 1, c->lessSharp[c->cur].p, c->nLessSharp, c->lessFlat[c->cur].p, c->nLessFlat);
+    c->stream = mainStream;
+    if (r != VLOAM_OK) return r;
+    VL_CUDA(cudaEventRecord(c->evLast, c->stream2));
+  }
   double* d_pose = c->los->para_q;  // para_q[4] + para_t[3] are contiguous
   if (c->lo_inited) {  // LO.cpp:209-217: the first frame only initialises
     const float4* cornerLast = c->cornerLastPtr; const float4* surfLast = c->surfLastPtr;
@@ -530,7 +545,7 @@ int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, i
   // LO.cpp:558-574: this frame's less-sharp / less-flat clouds become the "last" clouds
   c->cornerLastPtr = c->lessSharp[c->cur].p; c->surfLastPtr = c->lessFlat[c->cur].p;
   c->nCornerLast = c->nLessSharp; c->nSurfLast = c->nLessFlat;
-  VL_TRY(vl_lo_build_last(c));  // LO.cpp:573-574: setInputCloud on both KD-trees
+  c->lastSet ^= 1;
   c->lo_frameCount++;
   c->skip_frame = (c->lo_frameCount % c->prm.mapping_skip_frame) != 0;  // LO.cpp:668-678
   VL_CUDA(cudaGetLastError());
