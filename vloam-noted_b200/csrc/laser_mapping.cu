@@ -13,7 +13,7 @@
 //   vl_voxel_grid     current less-sharp / less-flat -> cornerStack / surfStack (LM.cpp:492-500)
 //   [sync S2: Mc, Ms, Qc, Qs, tail sizes]
 //   grid build        counting sort of both sub-maps into 2 m cells over the 250x250x150 m window
-//   2 x { lm_knn_fit (5-NN + PCA line / QR plane -> factor slots), vl_solve }
+//   2 x { lm_knn (5-NN), lm_fit (PCA line / QR plane -> factor slots), vl_solve }
 //   lm_transform_update, then the map update:
 //   rf_*              VoxelGrid re-filter of the valid cubes (LM.cpp:795-808) WITHOUT re-sorting the
 //                     map: only tails + this frame's points are sorted, then merged into the
@@ -391,7 +391,7 @@ __device__ void lm_qr_solve_5x3(double A[5][3], double b[5], double x[3]) {
 
 // One warp per downsampled feature: 5-NN in the 3x3x3 cell neighbourhood (exact inside the 1 m
 // acceptance ball), ordered by (d2, canonical id); then the line / plane fit.
-__global__ void __launch_bounds__(256) lm_knn_fit(const LmScalars* __restrict__ s, const RfWork* __restrict__ w,
+__global__ void __launch_bounds__(256) lm_knn(const LmScalars* __restrict__ s, const RfWork* __restrict__ w,
                                                   const float4* __restrict__ stackC, const float4* __restrict__ stackS,
                                                   const float4* __restrict__ mapC, const float4* __restrict__ mapS,
                                                   const int* __restrict__ cellStart, const float4* __restrict__ sortedPts,
@@ -454,14 +454,32 @@ __global__ void __launch_bounds__(256) lm_knn_fit(const LmScalars* __restrict__ 
     }
   }
   if (lane != 0) return;
-  const bool have5 = ni[4] != 0x7fffffff;
 #pragma unroll
   for (int k = 0; k < 5; ++k) { knnIdx[qi * 5 + k] = (ni[k] == 0x7fffffff) ? -1 : ni[k]; knnD2[qi * 5 + k] = nd[k]; }
+}
+
+// Line / plane fit of one feature per THREAD (the f64 eigen / QR work of 32 features shares a warp's
+// issue slots instead of idling 31 lanes behind lane 0 of the search kernel).
+__global__ void __launch_bounds__(128) lm_fit(const LmScalars* __restrict__ s, const float4* __restrict__ stackC, const float4* __restrict__ stackS,
+                                              const float4* __restrict__ mapC, const float4* __restrict__ mapS, const int* __restrict__ knnIdx,
+                                              const float* __restrict__ knnD2, int* __restrict__ knnOk, double* __restrict__ factors,
+                                              int* __restrict__ valid) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Qc = s->Qc, Qs = s->Qs;
+  if (qi >= Qc + Qs) return;
+  const int kind = qi >= Qc;
+  const float4 po = kind ? stackS[qi - Qc] : stackC[qi];
+  int ni[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) ni[k] = knnIdx[qi * 5 + k];
+  const bool have5 = ni[4] >= 0;
+  const float d4 = knnD2[qi * 5 + 4];
   bool ok = false;
   double* f = factors + (size_t)qi * 10;
-  if (have5 && (double)nd[4] < 1.0) {
+  if (have5 && (double)d4 < 1.0) {
     const float4* map = kind ? mapS : mapC;
     double P[5][3];
+#pragma unroll
     for (int j = 0; j < 5; ++j) { const float4 t = map[ni[j]]; P[j][0] = t.x; P[j][1] = t.y; P[j][2] = t.z; }
     if (!kind) {  // LM.cpp:559-603: PCA line test
       double cen[3] = {0, 0, 0};
@@ -972,8 +990,10 @@ int vl_lm_run(vloam_b200_ctx* c) {
     VL_TRY(vl_reserve(c, c->factorValid, (size_t)nq));
     for (int pass = 0; pass < 2; ++pass) {  // LM.cpp:526
       VL_BYTES(16.0 * nq * 6);  // query + 5 neighbours
-      VL_LAUNCH(lm_knn_fit, vl_div_up((long long)nq * 32, 256), 256, 0, c->lmm, d->work, c->stackC.p, c->stackS.p, c->fromMapC.p,
+      VL_LAUNCH(lm_knn, vl_div_up((long long)nq * 32, 256), 256, 0, c->lmm, d->work, c->stackC.p, c->stackS.p, c->fromMapC.p,
                 c->fromMapS.p, d->cellStart, d->sortedPts.p, c->knnIdx.p, c->knnD2.p, c->knnOk.p, c->factors.p, c->factorValid.p);
+      VL_LAUNCH(lm_fit, vl_div_up(nq, 128), 128, 0, c->lmm, c->stackC.p, c->stackS.p, c->fromMapC.p, c->fromMapS.p, c->knnIdx.p, c->knnD2.p,
+                c->knnOk.p, c->factors.p, c->factorValid.p);
       if (vl_debug_capture(c)) {
         for (int kind = 0; kind < 2; ++kind) {
           const int n = kind ? Qs : Qc, off = kind ? Qc : 0;

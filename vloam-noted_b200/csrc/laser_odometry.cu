@@ -324,13 +324,10 @@ __device__ __forceinline__ Best warp_best_v(Best v, unsigned& tag, bool preferLo
 // {j < closest : ring_j >= id - 2}; candidates farther than 5 m can never win because the running
 // minima start at DISTANCE_SQ_THRESHOLD = 25).  One warp per query.
 template <bool SURF>
-__global__ void __launch_bounds__(256) lo_assoc_grid(const float4* __restrict__ query, int nq, const float4* __restrict__ target,
-                                                     const float4* __restrict__ sorted, const int* __restrict__ cellStart,
-                                                     const double* __restrict__ pose, int* __restrict__ outIdx,
-                                                     double* __restrict__ factors, int* __restrict__ valid, int slotBase) {
-  const int lane = threadIdx.x & 31;
-  const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (qi >= nq) return;
+__device__ __forceinline__ void lo_assoc_grid_dev(int qi, int lane, const float4* __restrict__ query, const float4* __restrict__ target,
+                                                  const float4* __restrict__ sorted, const int* __restrict__ cellStart,
+                                                  const double* __restrict__ pose, int* __restrict__ outIdx,
+                                                  double* __restrict__ factors, int* __restrict__ valid, int slotBase) {
   const float4 cp = query[qi];
   double r[3];
   vl_qrot(pose, (double)cp.x, (double)cp.y, (double)cp.z, r);  // TransformToStart (LO.cpp:152-173)
@@ -428,6 +425,29 @@ __global__ void __launch_bounds__(256) lo_assoc_grid(const float4* __restrict__ 
   }
 }
 
+template <bool SURF>
+__global__ void __launch_bounds__(256) lo_assoc_grid(const float4* __restrict__ query, int nq, const float4* __restrict__ target,
+                                                     const float4* __restrict__ sorted, const int* __restrict__ cellStart,
+                                                     const double* __restrict__ pose, int* __restrict__ outIdx,
+                                                     double* __restrict__ factors, int* __restrict__ valid, int slotBase) {
+  const int lane = threadIdx.x & 31;
+  const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (qi >= nq) return;
+  lo_assoc_grid_dev<SURF>(qi, lane, query, target, sorted, cellStart, pose, outIdx, factors, valid, slotBase);
+}
+
+// sharp and flat queries in one launch: warps [0, nS) run the corner association, [nS, nS + nF) the surf one
+__global__ void __launch_bounds__(256) lo_assoc_grid_both(const float4* __restrict__ sharp, int nS, const float4* __restrict__ flat, int nF,
+                                                          const float4* __restrict__ cornerLast, const float4* __restrict__ surfLast,
+                                                          const float4* __restrict__ sorted, const int* __restrict__ cellStart,
+                                                          const double* __restrict__ pose, int* __restrict__ cornerIdx, int* __restrict__ surfIdx,
+                                                          double* __restrict__ factors, int* __restrict__ valid) {
+  const int lane = threadIdx.x & 31;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w < nS) lo_assoc_grid_dev<false>(w, lane, sharp, cornerLast, sorted, cellStart, pose, cornerIdx, factors, valid, 0);
+  else if (w < nS + nF) lo_assoc_grid_dev<true>(w - nS, lane, flat, surfLast, sorted, cellStart, pose, surfIdx, factors, valid, nS);
+}
+
 __global__ void lo_accumulate(LoScalars* s) {  // LO.cpp:524-525
   if (threadIdx.x != 0) return;
   double r[3];
@@ -481,6 +501,13 @@ static int lo_associate(vloam_b200_ctx* c, const double* d_pose, const float4* c
   const int* start = c->loGridCells[set].p ? c->loGridCells[set].p + (2 * LOG_NCELL + 1) : nullptr;
   const float4* gsorted = c->loGridSorted[set].p;
   const int* rtbl = c->loRingTbl + set * 2 * (LO_TBL + 1);
+  if (gridC && gridS && nS + nF > 0) {
+    VL_BYTES(16.0 * (nS + nF) * 2 * 600);
+    VL_LAUNCH(lo_assoc_grid_both, vl_div_up((long long)(nS + nF) * 32, 256), 256, 0, c->sharp.p, nS, c->flat.p, nF, cornerLast, surfLast, gsorted, start,
+              d_pose, c->loCornerIdx.p, c->loSurfIdx.p, c->factors.p, c->factorValid.p);
+    VL_CUDA(cudaGetLastError());
+    return VLOAM_OK;
+  }
   if (nS > 0) {
     if (gridC)
       VL_LAUNCH(lo_assoc_grid<false>, vl_div_up((long long)nS * 32, 256), 256, 0, c->sharp.p, nS, cornerLast, gsorted, start, d_pose,

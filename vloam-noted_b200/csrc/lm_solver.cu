@@ -323,6 +323,8 @@ lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ val
   __shared__ double total[28];
   __shared__ LmSolveState st;
   __shared__ double red[LMC_THREADS / 32][28];
+  __shared__ double gath[LMC_CTAS][28];
+  __shared__ double xloc[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (rank == 0 && threadIdx.x == 0) {
     for (int k = 0; k < 7; ++k) { st.x[k] = x_inout[k]; st.xc[k] = x_inout[k]; st.best[k] = x_inout[k]; xs[k] = x_inout[k]; }
@@ -333,10 +335,14 @@ lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ val
   const double* xsrc = cluster.map_shared_rank(xs, 0);
   const int* dsrc = cluster.map_shared_rank(&sdone, 0);
   for (int it = 0; it < 5; ++it) {
-    if (*dsrc) break;  // uniform over the cluster: written before the last barrier
+    // one round of remote reads: 7 coordinates + the done flag, then a local broadcast
+    if (threadIdx.x < 7) xloc[threadIdx.x] = xsrc[threadIdx.x];
+    else if (threadIdx.x == 7) xloc[7] = (double)*dsrc;
+    __syncthreads();
+    if (xloc[7] != 0.0) break;  // uniform over the cluster: written before the last barrier
     double x[7];
 #pragma unroll
-    for (int k = 0; k < 7; ++k) x[k] = xsrc[k];
+    for (int k = 0; k < 7; ++k) x[k] = xloc[k];
     double acc[28];
 #pragma unroll
     for (int k = 0; k < 28; ++k) acc[k] = 0.0;
@@ -377,9 +383,17 @@ lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ val
     }
     cluster.sync();  // every CTA's partial is visible cluster-wide
     if (rank == 0) {
+      // pull all 8 x 28 partials in one round of remote reads (one DSMEM latency, not eight), then add
+      // them in rank order so the sum is deterministic
+      if (threadIdx.x < 28 * LMC_CTAS) {
+        const int r = threadIdx.x / 28, k = threadIdx.x - r * 28;
+        gath[r][k] = cluster.map_shared_rank(part, r)[k];
+      }
+      __syncthreads();
       if (threadIdx.x < 28) {
         double v = 0;
-        for (unsigned r = 0; r < LMC_CTAS; ++r) v += cluster.map_shared_rank(part, r)[threadIdx.x];
+#pragma unroll
+        for (int r = 0; r < LMC_CTAS; ++r) v += gath[r][threadIdx.x];
         total[threadIdx.x] = v;
       }
       __syncthreads();

@@ -18,8 +18,10 @@
 #include <math_constants.h>
 #include "common.cuh"
 #include "exact_math.h"
+#include "bitonic.cuh"
 
 #define SR_BLOCK 256
+#define SR_PICK_THREADS 512  // sr_pick / sr_ring_voxel: one CTA per ring, the sorts want the threads
 #define SR_SECT_CAP 1024   // sector keys sorted in shared memory up to this size
 #define SR_RING_CAP 8192   // picked flags kept in shared memory up to this ring length
 #define SR_VOX_CAP 4096    // ring voxel keys sorted in shared memory up to this size
@@ -272,7 +274,7 @@ __device__ __forceinline__ int sr_ep(int start, int end, int j) { return start +
 // One CTA per ring.  All six sectors are sorted together (batched bitonic on
 // (curvature bits, index) keys -- the canonical tie order of SURVEY Appendix B), then
 // warp 0 walks the sectors in order because +-5 marks spill into the next sector.
-__global__ void __launch_bounds__(SR_BLOCK) sr_pick(const float4* __restrict__ cloud, const float* __restrict__ curv,
+__global__ void __launch_bounds__(SR_PICK_THREADS) sr_pick(const float4* __restrict__ cloud, const float* __restrict__ curv,
                                                     int* __restrict__ label, unsigned char* __restrict__ pickedG,
                                                     unsigned char* __restrict__ gapG, unsigned long long* __restrict__ scratch, const int* __restrict__ ringStart,
                                                     const int* __restrict__ ringCount, int* __restrict__ provSharp,
@@ -304,20 +306,7 @@ __global__ void __launch_bounds__(SR_BLOCK) sr_pick(const float4* __restrict__ c
     keys[t] = (idx <= last) ? (((unsigned long long)__float_as_uint(curv[idx]) << 32) | (unsigned)idx) : ~0ull;
   }
   __syncthreads();
-  const int halfP = P >> 1;
-  for (int k = 2; k <= P; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < VL_SECTORS * halfP; t += blockDim.x) {
-        const int sct = t / halfP, u = t - sct * halfP;
-        const int i = ((u & ~(j - 1)) << 1) | (u & (j - 1));
-        const int l = i | j;
-        unsigned long long* ks = keys + sct * P;
-        const unsigned long long a = ks[i], b = ks[l];
-        const bool up = (i & k) == 0;
-        if ((a > b) == up) { ks[i] = b; ks[l] = a; }
-      }
-      __syncthreads();
-    }
+  bt_sort_batched<SR_PICK_THREADS>(keys, P, VL_SECTORS);
   if (threadIdx.x >= 32) return;
   const int lane = threadIdx.x;
   for (int j = 0; j < VL_SECTORS; ++j) {
@@ -408,15 +397,15 @@ __device__ __forceinline__ void vox_make_box(const float mn[3], const float mx[3
   b->mul1 = d0; b->mul2 = d0 * d1;
 }
 
-__global__ void __launch_bounds__(SR_BLOCK) sr_ring_voxel(const float4* __restrict__ cloud, const int* __restrict__ label,
+__global__ void __launch_bounds__(SR_PICK_THREADS) sr_ring_voxel(const float4* __restrict__ cloud, const int* __restrict__ label,
                                                           const int* __restrict__ ringStart, const int* __restrict__ ringCount,
                                                           int* __restrict__ sel, unsigned long long* __restrict__ scratch,
                                                           float4* __restrict__ outProv, int* __restrict__ dsCount, float leaf) {
   extern __shared__ unsigned long long vsm[];  // [SR_VOX_CAP] keys, then [SR_VOX_CAP] float4 points
   unsigned long long* skeys = vsm;
   float4* spts = reinterpret_cast<float4*>(vsm + SR_VOX_CAP);
-  __shared__ int warpSum[SR_BLOCK / 32];
-  __shared__ float red[6][SR_BLOCK / 32];
+  __shared__ int warpSum[SR_PICK_THREADS / 32];
+  __shared__ float red[6][SR_PICK_THREADS / 32];
   __shared__ VoxBox box;
   __shared__ int sTotal;
   const int r = blockIdx.x;
@@ -428,14 +417,14 @@ __global__ void __launch_bounds__(SR_BLOCK) sr_ring_voxel(const float4* __restri
   // 1. ordered selection + bounding box
   float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
   int total = 0;
-  for (int base = start; base < end; base += SR_BLOCK) {
+  for (int base = start; base < end; base += SR_PICK_THREADS) {
     const int k = base + threadIdx.x;
     const bool f = k < end && label[k] <= 0;
     const unsigned b = __ballot_sync(0xffffffffu, f);
     if (lane == 0) warpSum[warp] = __popc(b);
     __syncthreads();
     int before = 0, all = 0;
-    for (int w = 0; w < SR_BLOCK / 32; ++w) { const int v = warpSum[w]; if (w < warp) before += v; all += v; }
+    for (int w = 0; w < SR_PICK_THREADS / 32; ++w) { const int v = warpSum[w]; if (w < warp) before += v; all += v; }
     if (f) {
       mySel[total + before + __popc(b & ((1u << lane) - 1u))] = k;
       const float4 p = cloud[k];
@@ -459,14 +448,14 @@ __global__ void __launch_bounds__(SR_BLOCK) sr_ring_voxel(const float4* __restri
     float lo[3], hi[3];
     for (int a = 0; a < 3; ++a) {
       lo[a] = red[a][0]; hi[a] = red[3 + a][0];
-      for (int w = 1; w < SR_BLOCK / 32; ++w) { lo[a] = fminf(lo[a], red[a][w]); hi[a] = fmaxf(hi[a], red[3 + a][w]); }
+      for (int w = 1; w < SR_PICK_THREADS / 32; ++w) { lo[a] = fminf(lo[a], red[a][w]); hi[a] = fmaxf(hi[a], red[3 + a][w]); }
     }
     vox_make_box(lo, hi, leaf, &box);
   }
   __syncthreads();
   float4* out = outProv + rs;
   if (box.guard) {  // leaf too small for the extent: pcl returns the input unchanged
-    for (int t = threadIdx.x; t < m; t += SR_BLOCK) out[t] = cloud[mySel[t]];
+    for (int t = threadIdx.x; t < m; t += SR_PICK_THREADS) out[t] = cloud[mySel[t]];
     if (threadIdx.x == 0) dsCount[r] = m;
     return;
   }
@@ -474,7 +463,7 @@ __global__ void __launch_bounds__(SR_BLOCK) sr_ring_voxel(const float4* __restri
   int P = 32; while (P < m) P <<= 1;
   unsigned long long* keys = (P <= SR_VOX_CAP) ? skeys : scratch + (size_t)2 * rs + (size_t)r * 6 * 64;
   const bool ptsInSmem = m <= SR_VOX_CAP;
-  for (int t = threadIdx.x; t < P; t += SR_BLOCK) {
+  for (int t = threadIdx.x; t < P; t += SR_PICK_THREADS) {
     unsigned long long key = ~0ull;
     if (t < m) {
       const float4 p = cloud[mySel[t]];
@@ -484,28 +473,17 @@ __global__ void __launch_bounds__(SR_BLOCK) sr_ring_voxel(const float4* __restri
     keys[t] = key;
   }
   __syncthreads();
-  const int halfP = P >> 1;
-  for (int k = 2; k <= P; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int u = threadIdx.x; u < halfP; u += SR_BLOCK) {
-        const int i = ((u & ~(j - 1)) << 1) | (u & (j - 1));
-        const int l = i | j;
-        const unsigned long long a = keys[i], b = keys[l];
-        const bool up = (i & k) == 0;
-        if ((a > b) == up) { keys[i] = b; keys[l] = a; }
-      }
-      __syncthreads();
-    }
+  bt_sort_batched<SR_PICK_THREADS>(keys, P, 1);
   // 3. run heads -> ordered output slots; the head thread folds its run in f32, in index order
   total = 0;
-  for (int base = 0; base < m; base += SR_BLOCK) {
+  for (int base = 0; base < m; base += SR_PICK_THREADS) {
     const int t = base + threadIdx.x;
     const bool head = t < m && (t == 0 || (unsigned)(keys[t] >> 32) != (unsigned)(keys[t - 1] >> 32));
     const unsigned b = __ballot_sync(0xffffffffu, head);
     if (lane == 0) warpSum[warp] = __popc(b);
     __syncthreads();
     int before = 0, all = 0;
-    for (int w = 0; w < SR_BLOCK / 32; ++w) { const int v = warpSum[w]; if (w < warp) before += v; all += v; }
+    for (int w = 0; w < SR_PICK_THREADS / 32; ++w) { const int v = warpSum[w]; if (w < warp) before += v; all += v; }
     if (head) {
       const unsigned vox = (unsigned)(keys[t] >> 32);
       float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f; int nrun = 0;
@@ -619,12 +597,12 @@ int vl_sr_run(vloam_b200_ctx* c, const float* d_xyz, int n, int stride) {
     VL_CUDA(cudaFuncSetAttribute(sr_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pickSmem));
     attrSet = true;
   }
-  VL_LAUNCH(sr_pick, R, SR_BLOCK, pickSmem, c->cloud.p, c->curv.p, c->label.p, c->picked.p, c->picked.p + n, c->sortScratch.p, c->ringStart, c->ringCount,
+  VL_LAUNCH(sr_pick, R, SR_PICK_THREADS, pickSmem, c->cloud.p, c->curv.p, c->label.p, c->picked.p, c->picked.p + n, c->sortScratch.p, c->ringStart, c->ringCount,
             c->provSharp, c->provLess, c->provFlat, c->cntSharp, c->cntLess, c->cntFlat);
   const size_t voxSmem = (size_t)SR_VOX_CAP * (sizeof(unsigned long long) + sizeof(float4));
   static bool voxAttr = false;
   if (!voxAttr) { VL_CUDA(cudaFuncSetAttribute(sr_ring_voxel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)voxSmem)); voxAttr = true; }
-  VL_LAUNCH(sr_ring_voxel, R, SR_BLOCK, voxSmem, c->cloud.p, c->label.p, c->ringStart, c->ringCount, c->selIdx.p, c->sortScratch.p,
+  VL_LAUNCH(sr_ring_voxel, R, SR_PICK_THREADS, voxSmem, c->cloud.p, c->label.p, c->ringStart, c->ringCount, c->selIdx.p, c->sortScratch.p,
             c->lessFlatProv.p, c->ringDsCount, 0.2f);
   VL_LAUNCH(sr_offsets, 1, 1024, 0, R, c->cntSharp, c->cntLess, c->cntFlat, c->ringDsCount, c->offSharp, c->offLess, c->offFlat,
             c->ringDsOff, c->srs);
