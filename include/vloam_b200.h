@@ -115,6 +115,8 @@ int vloam_b200_stage_ms(vloam_b200_ctx* c, float* ms3);
  * summed duration and the algorithmic bytes the launch sites declared for them. */
 int vloam_b200_profile_kernel(vloam_b200_ctx* c, const char* name);
 int vloam_b200_profile_result(vloam_b200_ctx* c, int* launches, double* total_ms, double* total_bytes);
+/* After profile_kernel(c, "*") (every launch timed): text table "name count total_ms total_bytes" per line. */
+int vloam_b200_profile_table(vloam_b200_ctx* c, char* buf, int cap);
 
 /* State export / import and stage-level inspection, keyed by name.  The
  * reference keeps this state in private members (LO.h:90-147, LM.h:102-203);

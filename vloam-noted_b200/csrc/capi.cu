@@ -43,6 +43,7 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   VL_CUDA_CREATE(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   VL_CUDA_CREATE(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
   VL_CUDA_CREATE(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
+  VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evSR, cudaEventDisableTiming));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evStacks, cudaEventDisableTiming));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evLast, cudaEventDisableTiming));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evPose, cudaEventDisableTiming));
@@ -109,7 +110,7 @@ void vloam_b200_destroy(vloam_b200_ctx* c) {
   cudaFreeHost(c->h_srs); cudaFreeHost(c->h_los); cudaFreeHost(c->h_lms); cudaFreeHost(c->h_lmm); cudaFreeHost(c->h_vScalars);
   for (int k = 0; k < 4; ++k) cudaEventDestroy(c->ev[k]);
   cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream3);
-  cudaEventDestroy(c->evStacks); cudaEventDestroy(c->evLast); cudaEventDestroy(c->evPose); cudaEventDestroy(c->evMap);
+  cudaEventDestroy(c->evSR); cudaEventDestroy(c->evStacks); cudaEventDestroy(c->evLast); cudaEventDestroy(c->evPose); cudaEventDestroy(c->evMap);
   cudaStreamDestroy(c->stream2); cudaStreamDestroy(c->stream3);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -249,6 +250,26 @@ int vloam_b200_profile_result(vloam_b200_ctx* c, int* launches, double* total_ms
   for (int k = 0; k < c->prof_n; ++k) { float t = 0; VL_CUDA(cudaEventElapsedTime(&t, c->prof_ev[k][0], c->prof_ev[k][1])); ms += t; }
   *launches = c->prof_n; *total_ms = ms; *total_bytes = c->prof_bytes;
   return VLOAM_OK;
+}
+
+// Per-kernel table of the launches timed since vloam_b200_profile_kernel(c, "*"): writes lines
+// "name count total_ms total_bytes\n" into buf (NUL-terminated); returns the number of distinct kernels.
+int vloam_b200_profile_table(vloam_b200_ctx* c, char* buf, int cap) {
+  VL_TRY(vloam_b200_synchronize(c));
+  std::vector<std::string> names; std::vector<int> cnt; std::vector<double> ms, by;
+  for (int k = 0; k < c->prof_n; ++k) {
+    float t = 0; VL_CUDA(cudaEventElapsedTime(&t, c->prof_ev[k][0], c->prof_ev[k][1]));
+    std::string nm(c->prof_kname[k]);
+    const size_t lt = nm.find('<'); if (lt != std::string::npos) nm = nm.substr(0, lt);
+    size_t i = 0; for (; i < names.size(); ++i) if (names[i] == nm) break;
+    if (i == names.size()) { names.push_back(nm); cnt.push_back(0); ms.push_back(0); by.push_back(0); }
+    cnt[i]++; ms[i] += t; by[i] += c->prof_kbytes[k];
+  }
+  std::string out;
+  for (size_t i = 0; i < names.size(); ++i) { char line[256]; snprintf(line, sizeof line, "%s %d %.6f %.1f\n", names[i].c_str(), cnt[i], ms[i], by[i]); out += line; }
+  if ((int)out.size() + 1 > cap) { snprintf(c->err, sizeof c->err, "profile table buffer too small"); return VLOAM_E_CAPACITY; }
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return (int)names.size();
 }
 
 int vloam_b200_lo_associate(vloam_b200_ctx* c, const double* x, int* corner_idx, int* surf_idx) { return vl_lo_associate_only(c, x, corner_idx, surf_idx); }
@@ -424,7 +445,7 @@ int vloam_b200_solve(vloam_b200_ctx* c, const double* factors, int nf, double* x
   double* d_x = reinterpret_cast<double*>(c->vScalars + 32);
   VL_CUDA(cudaMemcpyAsync(d_x, x, 56, cudaMemcpyHostToDevice, c->stream));
   double costs[2] = {0, 0};
-  VL_TRY(vl_solve(c, nf, d_x, costs));
+  VL_TRY(vl_solve(c, nf, nullptr, d_x, costs));
   VL_CUDA(cudaMemcpyAsync(x, d_x, 56, cudaMemcpyDeviceToHost, c->stream));
   VL_CUDA(cudaStreamSynchronize(c->stream));
   if (log4) { log4[0] = nf ? c->h_lms->iter : 0; log4[1] = 0; log4[2] = costs[0]; log4[3] = costs[1]; }

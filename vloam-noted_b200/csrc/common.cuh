@@ -18,7 +18,7 @@
 #define VL_CUBE_D 11
 #define VL_CUBE_NUM (VL_CUBE_W * VL_CUBE_H * VL_CUBE_D)
 #define VL_MAX_VALID 125  // laserCloudValidInd[125], laser_mapping.h:127
-#define VL_PROF_MAX 512
+#define VL_PROF_MAX 4096
 
 // ---- device-resident scalars (one struct per context, also mirrored in pinned host memory)
 struct SrScalars {
@@ -28,7 +28,7 @@ struct SrScalars {
   int count;                  // kept points == laserCloud size
   int nSharp, nLessSharp, nFlat, nLessFlat;
   int blocksDone;             // last-block-done counter for the ring scan
-  int pad;
+  int nQueries;               // nSharp + nFlat: odometry factor slots
 };
 
 struct LmSolveState {  // trust-region LM state, lives on the device (lm_solver.cu)
@@ -89,6 +89,7 @@ struct vloam_b200_ctx {
   cudaStream_t stream;
   cudaStream_t stream2;       // side stream: work that is independent of the odometry solve overlaps it
   cudaStream_t stream3;       // map update of frame k runs here while frame k+1's scan registration / odometry run on `stream`
+  cudaEvent_t evSR;           // scan registration of this frame finished and its counts are in h_srs
   cudaEvent_t evStacks;       // this frame's downsampled stacks are ready
   cudaEvent_t evLast;         // search structures over the next "last" clouds are built
   cudaEvent_t evPose;         // solveMapping's pose is final (the map update may start)
@@ -171,8 +172,10 @@ struct vloam_b200_ctx {
   DBuf<unsigned long long> tailKeys; DBuf<float4> staging;
   DBuf<int> tmpI[4];
   // per-kernel timing (vloam_b200_profile_kernel): CUDA events around the launches of one named kernel
-  char prof_name[64];
+  char prof_name[64];                 // kernel to time, or "*" for every launch
   cudaEvent_t prof_ev[VL_PROF_MAX][2];
+  const char* prof_kname[VL_PROF_MAX];
+  double prof_kbytes[VL_PROF_MAX];
   int prof_n, prof_created;
   double prof_bytes, prof_next_bytes;
 };
@@ -206,7 +209,8 @@ struct GridParams {
     const bool prof_ = c->prof_name[0] && vl_prof_match(c, #kernel) && c->prof_n < VL_PROF_MAX; \
     if (prof_) cudaEventRecord(c->prof_ev[c->prof_n][0], c->stream);                           \
     kernel<<<(grid), (block), (smem), c->stream>>>(__VA_ARGS__);                               \
-    if (prof_) { cudaEventRecord(c->prof_ev[c->prof_n][1], c->stream); c->prof_n++; c->prof_bytes += c->prof_next_bytes; } \
+    if (prof_) { cudaEventRecord(c->prof_ev[c->prof_n][1], c->stream); c->prof_kname[c->prof_n] = #kernel; c->prof_kbytes[c->prof_n] = c->prof_next_bytes; \
+                 c->prof_n++; c->prof_bytes += c->prof_next_bytes; } \
     c->prof_next_bytes = 0;                                                                    \
     c->launches++;                                                                             \
   } while (0)
@@ -216,6 +220,7 @@ struct GridParams {
 
 static inline bool vl_prof_match(const vloam_b200_ctx* c, const char* k) {
   // template kernels show up as "lo_assoc<true>": compare the prefix
+  if (c->prof_name[0] == '*') return true;
   const size_t n = strlen(c->prof_name);
   return strncmp(c->prof_name, k, n) == 0 && (k[n] == 0 || k[n] == '<');
 }
@@ -261,7 +266,8 @@ int vl_sort_u64(vloam_b200_ctx* c, unsigned long long* d_keys, int n_pow2);
 int vl_voxel_grid_device(vloam_b200_ctx* c, const float4* d_in, int n, const int* d_n, float leaf, float4* d_out, int* d_count);
 
 // solver (lm_solver.cu): evaluates factor slots [0, nslots) with validity flags.
-int vl_solve(vloam_b200_ctx* c, int nslots, double* d_x_inout, double* costs2 /* host, may be null */);
+// nslots: host bound on the factor slots; d_nslots (device, may be null): actual count, min() of both is used
+int vl_solve(vloam_b200_ctx* c, int nslots, const int* d_nslots, double* d_x_inout, double* costs2 /* host, may be null */);
 int vl_evaluate_once(vloam_b200_ctx* c, int nslots, const double* d_x, EvalOut* d_out);
 
 // ---- shared device helpers -----------------------------------------------------

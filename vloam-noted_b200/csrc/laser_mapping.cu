@@ -41,6 +41,7 @@ struct RfWork {
   int outCount[LM_NSEG];
   int firstViolation[LM_NSEG];
   int nKeysValid;
+  int nq;                               // Qc + Qs when the optimisation runs, else 0
   float gridOrigin[3];
   int Qc, Qs;
 };
@@ -398,9 +399,10 @@ __global__ void __launch_bounds__(256) lm_knn(const LmScalars* __restrict__ s, c
                                                   int* __restrict__ knnIdx, float* __restrict__ knnD2, int* __restrict__ knnOk,
                                                   double* __restrict__ factors, int* __restrict__ valid) {
   const int lane = threadIdx.x & 31;
-  const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int Qc = s->Qc, Qs = s->Qs;
-  if (qi >= Qc + Qs) return;
+  if (!s->optimized) return;
+  const int nWarps = (gridDim.x * blockDim.x) >> 5;
+  for (int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; qi < Qc + Qs; qi += nWarps) {
   const int kind = qi >= Qc;
   const float4 po = kind ? stackS[qi - Qc] : stackC[qi];
   double r[3];
@@ -453,9 +455,11 @@ __global__ void __launch_bounds__(256) lm_knn(const LmScalars* __restrict__ s, c
       bd[4] = CUDART_INF_F; bi[4] = 0x7fffffff;
     }
   }
-  if (lane != 0) return;
+  if (lane == 0) {
 #pragma unroll
-  for (int k = 0; k < 5; ++k) { knnIdx[qi * 5 + k] = (ni[k] == 0x7fffffff) ? -1 : ni[k]; knnD2[qi * 5 + k] = nd[k]; }
+    for (int k = 0; k < 5; ++k) { knnIdx[qi * 5 + k] = (ni[k] == 0x7fffffff) ? -1 : ni[k]; knnD2[qi * 5 + k] = nd[k]; }
+  }
+  }
 }
 
 // Line / plane fit of one feature per THREAD (the f64 eigen / QR work of 32 features shares a warp's
@@ -464,9 +468,9 @@ __global__ void __launch_bounds__(128) lm_fit(const LmScalars* __restrict__ s, c
                                               const float4* __restrict__ mapC, const float4* __restrict__ mapS, const int* __restrict__ knnIdx,
                                               const float* __restrict__ knnD2, int* __restrict__ knnOk, double* __restrict__ factors,
                                               int* __restrict__ valid) {
-  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
   const int Qc = s->Qc, Qs = s->Qs;
-  if (qi >= Qc + Qs) return;
+  if (!s->optimized) return;
+  for (int qi = blockIdx.x * blockDim.x + threadIdx.x; qi < Qc + Qs; qi += gridDim.x * blockDim.x) {
   const int kind = qi >= Qc;
   const float4 po = kind ? stackS[qi - Qc] : stackC[qi];
   int ni[5];
@@ -516,6 +520,7 @@ __global__ void __launch_bounds__(128) lm_fit(const LmScalars* __restrict__ s, c
   }
   valid[qi] = ok ? 1 : 0;
   knnOk[qi] = ok ? 1 : 0;
+  }
 }
 
 __global__ void lm_transform_update(LmScalars* s) {  // LM.cpp:147-151
@@ -878,7 +883,13 @@ __global__ void __launch_bounds__(256) lm_scan_sorted(const LmScalars* __restric
   if (threadIdx.x == 0) t->sorted[cb] = min(n, firstBad);
 }
 
-__global__ void lm_set_counts(LmScalars* s, const int* qc, const int* qs) { if (threadIdx.x == 0) { s->Qc = *qc; s->Qs = *qs; } }
+__global__ void lm_set_counts(LmScalars* s, RfWork* w, const int* qc, const int* qs) {
+  if (threadIdx.x != 0) return;
+  s->Qc = *qc; s->Qs = *qs;
+  // LM.cpp:514: optimise only against a sub-map with > 10 corner and > 50 surf points
+  s->optimized = (s->Mc > 10 && s->Ms > 50 && *qc + *qs > 0) ? 1 : 0;
+  w->nq = s->optimized ? *qc + *qs : 0;  // factor slots the solver looks at
+}
 
 // -----------------------------------------------------------------------------------------------
 #define LM_POOL_C (16 << 20)
@@ -962,39 +973,43 @@ int vl_lm_run(vloam_b200_ctx* c) {
   }
   VL_CUDA(cudaStreamWaitEvent(c->stream, c->evStacks, 0));
   c->stacksReady = false;
-  VL_LAUNCH(lm_set_counts, 1, 32, 0, c->lmm, d->dQ, d->dQ + 1);
-  // ---- sync point S2
-  VL_CUDA(cudaMemcpyAsync(c->h_lmm, c->lmm, sizeof(LmScalars), cudaMemcpyDeviceToHost, c->stream));
-  VL_CUDA(cudaStreamSynchronize(c->stream));
-  const int Mc = c->h_lmm->Mc, Ms = c->h_lmm->Ms, Qc = c->h_lmm->Qc, Qs = c->h_lmm->Qs;
-  const int tailTotal = c->h_lmm->tailC + c->h_lmm->tailS;
-  const int nq = Qc + Qs;
-  bool optimized = false;
-  if (Mc > 10 && Ms > 50 && nq > 0) {  // LM.cpp:514
-    optimized = true;
-    const int total = Mc + Ms;
+  VL_LAUNCH(lm_set_counts, 1, 32, 0, c->lmm, d->work, d->dQ, d->dQ + 1);
+  // The search / fit / solve kernels read the sizes (Mc, Ms, Qc, Qs) and the LM.cpp:514 decision on the
+  // device, so they are queued without waiting for the host; sync point S2 sits after the solve, where
+  // the pose has to be final anyway.  (Debug snapshots need host counts first and sync here.)
+  const bool capture = vl_debug_capture(c);
+  int Qc = 0, Qs = 0;
+  if (capture) {
+    VL_CUDA(cudaMemcpyAsync(c->h_lmm, c->lmm, sizeof(LmScalars), cudaMemcpyDeviceToHost, c->stream));
+    VL_CUDA(cudaStreamSynchronize(c->stream));
+    Qc = c->h_lmm->Qc; Qs = c->h_lmm->Qs;
+  }
+  const long long totalBound = d->hMapUpperC + d->hMapUpperS;
+  const int nqBound = max(c->nCornerLast + c->nSurfLast, 1);  // a voxel filter never grows a cloud
+  {
     const int nCells = 2 * LM_NCELL;
-    VL_TRY(vl_reserve(c, d->cellOfPoint, (size_t)total, false, (size_t)total / 2 + (1 << 20)));
-    VL_TRY(vl_reserve(c, d->sortedPts, (size_t)total, false, (size_t)total / 2 + (1 << 20)));
+    VL_TRY(vl_reserve(c, d->cellOfPoint, (size_t)max(totalBound, 1LL), false, (size_t)totalBound / 2 + (1 << 20)));
+    VL_TRY(vl_reserve(c, d->sortedPts, (size_t)max(totalBound, 1LL), false, (size_t)totalBound / 2 + (1 << 20)));
     VL_CUDA(cudaMemsetAsync(d->cellCount, 0, sizeof(int) * (nCells + 1), c->stream));
     VL_CUDA(cudaMemsetAsync(d->cellFill, 0, sizeof(int) * (nCells + 1), c->stream));
-    VL_BYTES(24.0 * total);  // read point, write cell id, atomic on the cell counter
+    VL_BYTES(24.0 * (double)totalBound);  // read point, write cell id, atomic on the cell counter
     VL_LAUNCH(lm_grid_count, gsGrid, 256, 0, c->lmm, d->work, c->fromMapC.p, c->fromMapS.p, d->cellCount, d->cellOfPoint.p);
     VL_TRY(vl_scan_exclusive(c, d->cellCount, nCells, d->tileSum, d->cellStart));
-    VL_BYTES(44.0 * total);  // read point + cell id + cell start, atomic, write sorted point
+    VL_BYTES(44.0 * (double)totalBound);  // read point + cell id + cell start, atomic, write sorted point
     VL_LAUNCH(lm_grid_fill, gsGrid, 256, 0, c->lmm, c->fromMapC.p, c->fromMapS.p, d->cellOfPoint.p, d->cellStart, d->cellFill, d->sortedPts.p);
-    VL_TRY(vl_reserve(c, c->knnIdx, (size_t)nq * 5));
-    VL_TRY(vl_reserve(c, c->knnD2, (size_t)nq * 5));
-    VL_TRY(vl_reserve(c, c->knnOk, (size_t)nq));
-    VL_TRY(vl_reserve(c, c->factors, (size_t)nq * 10));
-    VL_TRY(vl_reserve(c, c->factorValid, (size_t)nq));
+    VL_TRY(vl_reserve(c, c->knnIdx, (size_t)nqBound * 5));
+    VL_TRY(vl_reserve(c, c->knnD2, (size_t)nqBound * 5));
+    VL_TRY(vl_reserve(c, c->knnOk, (size_t)nqBound));
+    VL_TRY(vl_reserve(c, c->factors, (size_t)nqBound * 10));
+    VL_TRY(vl_reserve(c, c->factorValid, (size_t)nqBound));
     for (int pass = 0; pass < 2; ++pass) {  // LM.cpp:526
-      VL_BYTES(16.0 * nq * 6);  // query + 5 neighbours
-      VL_LAUNCH(lm_knn, vl_div_up((long long)nq * 32, 256), 256, 0, c->lmm, d->work, c->stackC.p, c->stackS.p, c->fromMapC.p,
+      VL_BYTES(16.0 * 7000 * 6);  // query + 5 neighbours, typical Qc + Qs
+      VL_LAUNCH(lm_knn, c->num_sms * 8, 256, 0, c->lmm, d->work, c->stackC.p, c->stackS.p, c->fromMapC.p,
                 c->fromMapS.p, d->cellStart, d->sortedPts.p, c->knnIdx.p, c->knnD2.p, c->knnOk.p, c->factors.p, c->factorValid.p);
-      VL_LAUNCH(lm_fit, vl_div_up(nq, 128), 128, 0, c->lmm, c->stackC.p, c->stackS.p, c->fromMapC.p, c->fromMapS.p, c->knnIdx.p, c->knnD2.p,
+      VL_BYTES((16.0 * 6 + 24.0 + 84.0) * 7000);
+      VL_LAUNCH(lm_fit, c->num_sms, 128, 0, c->lmm, c->stackC.p, c->stackS.p, c->fromMapC.p, c->fromMapS.p, c->knnIdx.p, c->knnD2.p,
                 c->knnOk.p, c->factors.p, c->factorValid.p);
-      if (vl_debug_capture(c)) {
+      if (capture) {
         for (int kind = 0; kind < 2; ++kind) {
           const int n = kind ? Qs : Qc, off = kind ? Qc : 0;
           VL_TRY(vl_reserve(c, c->dbgKnnIdx[pass][kind], (size_t)max(n, 1) * 5));
@@ -1006,14 +1021,21 @@ int vl_lm_run(vloam_b200_ctx* c) {
           VL_CUDA(cudaMemcpyAsync(c->dbgKnnOk[pass][kind].p, c->knnOk.p + off, sizeof(int) * n, cudaMemcpyDeviceToDevice, c->stream));
         }
       }
-      VL_TRY(vl_solve(c, nq, c->lmm->pose, vl_debug_capture(c) ? &c->dbgLmCost[pass * 2] : nullptr));
+      VL_TRY(vl_solve(c, nqBound, &d->work->nq, c->lmm->pose, capture ? &c->dbgLmCost[pass * 2] : nullptr));
     }
   }
-  c->lm_optimized = optimized ? 1 : 0;
   VL_LAUNCH(lm_transform_update, 1, 32, 0, c->lmm);  // LM.cpp:737 (runs even when the optimisation was skipped)
   // ---- map update (LM.cpp:741-808).  The pose is final here; the update runs on stream3 so that the caller can
   // read the pose, and the next frame's scan registration + odometry can start, while the map is brought up to date.
   VL_CUDA(cudaEventRecord(c->evPose, c->stream));
+  // ---- sync point S2: sizes for the map update (and the pose, which is final now)
+  VL_CUDA(cudaMemcpyAsync(c->h_lmm, c->lmm, sizeof(LmScalars), cudaMemcpyDeviceToHost, c->stream));
+  VL_CUDA(cudaStreamSynchronize(c->stream));
+  const int Mc = c->h_lmm->Mc, Ms = c->h_lmm->Ms;
+  Qc = c->h_lmm->Qc; Qs = c->h_lmm->Qs;
+  const int tailTotal = c->h_lmm->tailC + c->h_lmm->tailS;
+  const int nq = Qc + Qs;
+  c->lm_optimized = c->h_lmm->optimized;
   cudaStream_t mainStream = c->stream;
   c->stream = c->stream3;
   const int rmap = [&]() -> int {

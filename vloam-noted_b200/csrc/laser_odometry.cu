@@ -437,13 +437,15 @@ __global__ void __launch_bounds__(256) lo_assoc_grid(const float4* __restrict__ 
 }
 
 // sharp and flat queries in one launch: warps [0, nS) run the corner association, [nS, nS + nF) the surf one
-__global__ void __launch_bounds__(256) lo_assoc_grid_both(const float4* __restrict__ sharp, int nS, const float4* __restrict__ flat, int nF,
-                                                          const float4* __restrict__ cornerLast, const float4* __restrict__ surfLast,
+__global__ void __launch_bounds__(256) lo_assoc_grid_both(const float4* __restrict__ sharp, const float4* __restrict__ flat, int slotBound,
+                                                          const SrScalars* __restrict__ srs, const float4* __restrict__ cornerLast, const float4* __restrict__ surfLast,
                                                           const float4* __restrict__ sorted, const int* __restrict__ cellStart,
                                                           const double* __restrict__ pose, int* __restrict__ cornerIdx, int* __restrict__ surfIdx,
                                                           double* __restrict__ factors, int* __restrict__ valid) {
   const int lane = threadIdx.x & 31;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nS = srs->nSharp, nF = srs->nFlat;  // device-side counts: the host may not know them yet
+  if (w >= nS + nF) { if (w < slotBound && lane == 0) valid[w] = 0; return; }
   if (w < nS) lo_assoc_grid_dev<false>(w, lane, sharp, cornerLast, sorted, cellStart, pose, cornerIdx, factors, valid, 0);
   else if (w < nS + nF) lo_assoc_grid_dev<true>(w - nS, lane, flat, surfLast, sorted, cellStart, pose, surfIdx, factors, valid, nS);
 }
@@ -489,8 +491,12 @@ int vl_lo_build_last(vloam_b200_ctx* c, int set, const float4* corner, int nc, c
   return VLOAM_OK;
 }
 
+// upper bounds on the query counts that hold before the host has read them (SR.cpp:386-400, 452)
+static inline int lo_sharp_bound(const vloam_b200_ctx* c) { return c->prm.n_scans * VL_SECTORS * 2; }
+static inline int lo_flat_bound(const vloam_b200_ctx* c) { return c->prm.n_scans * VL_SECTORS * 4; }
+
 static int lo_associate(vloam_b200_ctx* c, const double* d_pose, const float4* cornerLast, int nCL, const float4* surfLast, int nSL) {
-  const int nS = c->nSharp, nF = c->nFlat;
+  const int nS = c->sr_counts_valid ? c->nSharp : lo_sharp_bound(c), nF = c->sr_counts_valid ? c->nFlat : lo_flat_bound(c);
   VL_TRY(vl_reserve(c, c->loCornerIdx, (size_t)max(nS, 1) * 2));
   VL_TRY(vl_reserve(c, c->loSurfIdx, (size_t)max(nF, 1) * 3));
   VL_TRY(vl_reserve(c, c->factors, (size_t)max(nS + nF, 1) * 10));
@@ -503,8 +509,8 @@ static int lo_associate(vloam_b200_ctx* c, const double* d_pose, const float4* c
   const int* rtbl = c->loRingTbl + set * 2 * (LO_TBL + 1);
   if (gridC && gridS && nS + nF > 0) {
     VL_BYTES(16.0 * (nS + nF) * 2 * 600);
-    VL_LAUNCH(lo_assoc_grid_both, vl_div_up((long long)(nS + nF) * 32, 256), 256, 0, c->sharp.p, nS, c->flat.p, nF, cornerLast, surfLast, gsorted, start,
-              d_pose, c->loCornerIdx.p, c->loSurfIdx.p, c->factors.p, c->factorValid.p);
+    VL_LAUNCH(lo_assoc_grid_both, vl_div_up((long long)(nS + nF) * 32, 256), 256, 0, c->sharp.p, c->flat.p, nS + nF, c->srs, cornerLast, surfLast,
+              gsorted, start, d_pose, c->loCornerIdx.p, c->loSurfIdx.p, c->factors.p, c->factorValid.p);
     VL_CUDA(cudaGetLastError());
     return VLOAM_OK;
   }
@@ -532,20 +538,13 @@ static int lo_associate(vloam_b200_ctx* c, const double* d_pose, const float4* c
 extern bool vl_debug_capture(const vloam_b200_ctx* c);
 
 int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, int use_prior) {
-  VL_TRY(vl_sr_sync_counts(c));  // sync point S1
   VL_CUDA(cudaEventSynchronize(c->evLast));  // set [lastSet] (built underneath the previous frame) and its flags are complete
-  if (((c->lo_frameCount + 1) % c->prm.mapping_skip_frame) == 0)  // mapping will run on this frame (LO.cpp:668)
-    VL_TRY(vl_lm_enqueue_stacks(c, c->lessSharp[c->cur].p, c->nLessSharp, c->lessFlat[c->cur].p, c->nLessFlat));
-  {  // LO.cpp:573-574 (setInputCloud on both KD-trees) for the clouds that become "last" after this solve:
-     // they are this frame's less-sharp / less-flat clouds, final since scan registration, so the side
-     // stream builds them while the odometry below still searches the previous set
-    cudaStream_t mainStream = c->stream;
-    c->stream = c->stream2;
-    const int r = vl_lo_build_last(c, c->lastSet ^ 1, c->lessSharp[c->cur].p, c->nLessSharp, c->lessFlat[c->cur].p, c->nLessFlat);
-    c->stream = mainStream;
-    if (r != VLOAM_OK) return r;
-    VL_CUDA(cudaEventRecord(c->evLast, c->stream2));
-  }
+  // The grid kernels read the query counts on the device, so the odometry can be queued before the host
+  // has them (sync point S1 then costs no GPU idle time).  The ballot fallback and the debug snapshots
+  // need host counts first.
+  const int set = c->lastSet;
+  const bool early = c->loGridValid[set] && c->h_vScalars[8 + 2 * set] != 0 && c->h_vScalars[9 + 2 * set] != 0 && !vl_debug_capture(c);
+  if (!early) VL_TRY(vl_sr_sync_counts(c));
   double* d_pose = c->los->para_q;  // para_q[4] + para_t[3] are contiguous
   if (c->lo_inited) {  // LO.cpp:209-217: the first frame only initialises
     const float4* cornerLast = c->cornerLastPtr; const float4* surfLast = c->surfLastPtr;
@@ -564,9 +563,23 @@ int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, i
         VL_CUDA(cudaMemcpyAsync(c->dbgLoCorner[pass].p, c->loCornerIdx.p, sizeof(int) * 2 * c->nSharp, cudaMemcpyDeviceToDevice, c->stream));
         VL_CUDA(cudaMemcpyAsync(c->dbgLoSurf[pass].p, c->loSurfIdx.p, sizeof(int) * 3 * c->nFlat, cudaMemcpyDeviceToDevice, c->stream));
       }
-      VL_TRY(vl_solve(c, c->nSharp + c->nFlat, d_pose, vl_debug_capture(c) ? &c->dbgLoCost[pass * 2] : nullptr));
+      const int nslots = c->sr_counts_valid ? c->nSharp + c->nFlat : lo_sharp_bound(c) + lo_flat_bound(c);
+      VL_TRY(vl_solve(c, nslots, &c->srs->nQueries, d_pose, vl_debug_capture(c) ? &c->dbgLoCost[pass * 2] : nullptr));
     }
     VL_LAUNCH(lo_accumulate, 1, 32, 0, c->los);
+  }
+  VL_TRY(vl_sr_sync_counts(c));  // sync point S1 (event after scan registration; the odometry above is already queued)
+  if (((c->lo_frameCount + 1) % c->prm.mapping_skip_frame) == 0)  // mapping will run on this frame (LO.cpp:668)
+    VL_TRY(vl_lm_enqueue_stacks(c, c->lessSharp[c->cur].p, c->nLessSharp, c->lessFlat[c->cur].p, c->nLessFlat));
+  {  // LO.cpp:573-574 (setInputCloud on both KD-trees) for the clouds that become "last" after this solve:
+     // they are this frame's less-sharp / less-flat clouds, final since scan registration, so the side
+     // stream builds them while the odometry still searches the previous set
+    cudaStream_t mainStream = c->stream;
+    c->stream = c->stream2;
+    const int r = vl_lo_build_last(c, c->lastSet ^ 1, c->lessSharp[c->cur].p, c->nLessSharp, c->lessFlat[c->cur].p, c->nLessFlat);
+    c->stream = mainStream;
+    if (r != VLOAM_OK) return r;
+    VL_CUDA(cudaEventRecord(c->evLast, c->stream2));
   }
   c->lo_inited = true;
   // LO.cpp:558-574: this frame's less-sharp / less-flat clouds become the "last" clouds

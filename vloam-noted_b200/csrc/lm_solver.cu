@@ -38,19 +38,17 @@ __device__ __forceinline__ void lm_factor(const double* __restrict__ f, const do
     o.nr = 3;
     o.r[0] = nu[0] / n; o.r[1] = nu[1] / n; o.r[2] = nu[2] / n;
     // d r / d lp = [w]x with w = (b - a) / n;  d lp / d delta = -2 [rp]x;  d lp / d t = I
+    // => J_rot = -2 [w]x [rp]x = -2 (rp w^T - (w . rp) I),  J_t = [w]x
     const double w[3] = {-de[0] / n, -de[1] / n, -de[2] / n};
+    const double wr = w[0] * rp[0] + w[1] * rp[1] + w[2] * rp[2];
 #pragma unroll
-    for (int cidx = 0; cidx < 3; ++cidx) {
-      double e[3] = {0, 0, 0}; e[cidx] = 1.0;
-      // m = -2 (rp x e_c)
-      const double m[3] = {-2.0 * (rp[1] * e[2] - rp[2] * e[1]), -2.0 * (rp[2] * e[0] - rp[0] * e[2]), -2.0 * (rp[0] * e[1] - rp[1] * e[0])};
-      o.J[0][cidx] = w[1] * m[2] - w[2] * m[1];
-      o.J[1][cidx] = w[2] * m[0] - w[0] * m[2];
-      o.J[2][cidx] = w[0] * m[1] - w[1] * m[0];
-      o.J[0][3 + cidx] = w[1] * e[2] - w[2] * e[1];
-      o.J[1][3 + cidx] = w[2] * e[0] - w[0] * e[2];
-      o.J[2][3 + cidx] = w[0] * e[1] - w[1] * e[0];
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int cidx = 0; cidx < 3; ++cidx) o.J[i][cidx] = -2.0 * (i == cidx ? rp[i] * w[cidx] - wr : rp[i] * w[cidx]);
     }
+    o.J[0][3] = 0.0;   o.J[0][4] = -w[2]; o.J[0][5] = w[1];
+    o.J[1][3] = w[2];  o.J[1][4] = 0.0;   o.J[1][5] = -w[0];
+    o.J[2][3] = -w[1]; o.J[2][4] = w[0];  o.J[2][5] = 0.0;
   } else {
     double n[3];
     o.nr = 1;
@@ -312,18 +310,22 @@ __global__ void __launch_bounds__(LM_BLOCK) lm_eval(const double* __restrict__ f
 #define LMC_CTAS 8
 #define LMC_THREADS 256
 
-__global__ void __cluster_dims__(LMC_CTAS, 1, 1) __launch_bounds__(LMC_THREADS)
-lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ valid, int nslots, double* __restrict__ x_inout,
-                 LmSolveState* __restrict__ st_out) {
+#define LMC_MAX_CTAS 16
+__global__ void __launch_bounds__(LMC_THREADS)
+lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ valid, int nslotsBound, const int* __restrict__ d_nslots,
+                 double* __restrict__ x_inout, LmSolveState* __restrict__ st_out) {
+  const int nslots = d_nslots ? min(nslotsBound, *d_nslots) : nslotsBound;
+  if (nslots <= 0) return;  // no residual blocks: Ceres leaves the parameters untouched (uniform over the cluster)
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank();
+  const int nct = (int)cluster.num_blocks();
   __shared__ double part[28];
   __shared__ double xs[8];
   __shared__ int sdone;
   __shared__ double total[28];
   __shared__ LmSolveState st;
   __shared__ double red[LMC_THREADS / 32][28];
-  __shared__ double gath[LMC_CTAS][28];
+  __shared__ double gath[LMC_MAX_CTAS][28];
   __shared__ double xloc[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (rank == 0 && threadIdx.x == 0) {
@@ -346,7 +348,7 @@ lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ val
     double acc[28];
 #pragma unroll
     for (int k = 0; k < 28; ++k) acc[k] = 0.0;
-    for (int i = rank * LMC_THREADS + threadIdx.x; i < nslots; i += LMC_CTAS * LMC_THREADS) {
+    for (int i = rank * LMC_THREADS + threadIdx.x; i < nslots; i += nct * LMC_THREADS) {
       if (!valid[i]) continue;
       FactorRow fr;
       lm_factor(factors + (size_t)i * 10, x, fr);
@@ -385,15 +387,14 @@ lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ val
     if (rank == 0) {
       // pull all 8 x 28 partials in one round of remote reads (one DSMEM latency, not eight), then add
       // them in rank order so the sum is deterministic
-      if (threadIdx.x < 28 * LMC_CTAS) {
-        const int r = threadIdx.x / 28, k = threadIdx.x - r * 28;
+      for (int t = threadIdx.x; t < 28 * nct; t += LMC_THREADS) {
+        const int r = t / 28, k = t - r * 28;
         gath[r][k] = cluster.map_shared_rank(part, r)[k];
       }
       __syncthreads();
       if (threadIdx.x < 28) {
         double v = 0;
-#pragma unroll
-        for (int r = 0; r < LMC_CTAS; ++r) v += gath[r][threadIdx.x];
+        for (int r = 0; r < nct; ++r) v += gath[r][threadIdx.x];
         total[threadIdx.x] = v;
       }
       __syncthreads();
@@ -427,11 +428,25 @@ __global__ void lm_end(LmSolveState* st, double* __restrict__ x, const int* __re
   st->final_cost = st->min_cost;
 }
 
-int vl_solve(vloam_b200_ctx* c, int nslots, double* d_x_inout, double* costs2) {
+int vl_solve(vloam_b200_ctx* c, int nslots, const int* d_nslots, double* d_x_inout, double* costs2) {
   if (nslots > 0) {
-    VL_BYTES(84.0 * nslots * 5);
-    VL_LAUNCH(lm_solve_cluster, LMC_CTAS, LMC_THREADS, 0, c->factors.p, c->factorValid.p, nslots, d_x_inout, costs2 ? c->lms : nullptr);
-    VL_CUDA(cudaGetLastError());
+    // one cluster: 8 CTAs for the small odometry problems, 16 (non-portable size) for the mapping ones
+    const int nct = nslots > 4096 ? LMC_MAX_CTAS : LMC_CTAS;
+    static bool attr = false;
+    if (!attr) { VL_CUDA(cudaFuncSetAttribute(lm_solve_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)); attr = true; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nct); cfg.blockDim = dim3(LMC_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = nct; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    const bool prof = c->prof_name[0] && vl_prof_match(c, "lm_solve_cluster") && c->prof_n < VL_PROF_MAX;
+    if (prof) cudaEventRecord(c->prof_ev[c->prof_n][0], c->stream);
+    const double* cf = c->factors.p; const int* cv = c->factorValid.p; LmSolveState* so = costs2 ? c->lms : nullptr;
+    VL_CUDA(cudaLaunchKernelEx(&cfg, lm_solve_cluster, cf, cv, nslots, d_nslots, d_x_inout, so));
+    if (prof) { cudaEventRecord(c->prof_ev[c->prof_n][1], c->stream); c->prof_kname[c->prof_n] = "lm_solve_cluster"; c->prof_kbytes[c->prof_n] = 84.0 * nslots * 5;
+                c->prof_n++; c->prof_bytes += 84.0 * nslots * 5; }
+    c->launches++;
   }
   if (costs2) {
     if (nslots > 0) {

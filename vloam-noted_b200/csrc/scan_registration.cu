@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(1024) sr_find_bounds(const float* __restrict__
   }
   if (threadIdx.x == 0) {
     s->firstValid = first; s->lastValid = last; s->trigger = INT_MAX; s->blocksDone = 0;
-    s->count = 0; s->nSharp = s->nLessSharp = s->nFlat = s->nLessFlat = 0;
+    s->count = 0; s->nSharp = s->nLessSharp = s->nFlat = s->nLessFlat = 0; s->nQueries = 0;
     float so = 0.f, eo = 0.f;
     if (first >= 0) {
       float x, y, z;
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(1024) sr_offsets(int nscans, const int* __rest
   }
   if (t < nslots) { offSharp[t] = buf[0][t] - own[0]; offLess[t] = buf[1][t] - own[1]; offFlat[t] = buf[2][t] - own[2]; }
   if (t < nscans) dsOff[t] = buf[3][t] - own[3];
-  if (t == 1023) { s->nSharp = buf[0][t]; s->nLessSharp = buf[1][t]; s->nFlat = buf[2][t]; s->nLessFlat = buf[3][t]; }
+  if (t == 1023) { s->nSharp = buf[0][t]; s->nLessSharp = buf[1][t]; s->nFlat = buf[2][t]; s->nLessFlat = buf[3][t]; s->nQueries = buf[0][t] + buf[2][t]; }
 }
 
 __global__ void __launch_bounds__(SR_BLOCK) sr_gather(const float4* __restrict__ cloud, int nscans, const SrScalars* __restrict__ s,
@@ -564,6 +564,7 @@ int vl_sr_run(vloam_b200_ctx* c, const float* d_xyz, int n, int stride) {
     VL_CUDA(cudaMemsetAsync(c->srs, 0, sizeof(SrScalars), c->stream));
     VL_CUDA(cudaMemsetAsync(c->ringCount, 0, sizeof(int) * VL_MAX_RINGS, c->stream));
     VL_CUDA(cudaMemsetAsync(c->ringStart, 0, sizeof(int) * (VL_MAX_RINGS + 1), c->stream));
+    VL_CUDA(cudaEventRecord(c->evSR, c->stream));
     return VLOAM_OK;
   }
   const int numBlocks = vl_div_up(n, SR_BLOCK);
@@ -586,10 +587,13 @@ int vl_sr_run(vloam_b200_ctx* c, const float* d_xyz, int n, int stride) {
   const float thres2 = thres * thres;
 
   VL_LAUNCH(sr_find_bounds, 1, 1024, 0, d_xyz, n, stride, vec4, thres2, c->srs);
+  VL_BYTES((4.0 * stride + 8.0) * n);
   VL_LAUNCH(sr_classify, numBlocks, SR_BLOCK, 0, d_xyz, n, stride, vec4, thres2, R, c->srs, c->ring.p, c->ori.p, c->blockHist.p, numBlocks);
   VL_LAUNCH(sr_ring_scan, vl_div_up(R, 8), 256, 0, c->blockHist.p, numBlocks, R, c->ringCount, c->ringStart, c->srs);
+  VL_BYTES((4.0 * stride + 8.0 + 16.0) * n);
   VL_LAUNCH(sr_scatter, numBlocks, SR_BLOCK, 0, d_xyz, n, stride, vec4, R, c->srs, c->ring.p, c->ori.p, c->blockHist.p, numBlocks,
             c->ringStart, c->cloud.p);
+  VL_BYTES(25.0 * n);
   VL_LAUNCH(sr_curvature, numBlocks, SR_BLOCK, 0, c->cloud.p, c->srs, c->curv.p, c->label.p, c->picked.p);
   const size_t pickSmem = (size_t)VL_SECTORS * SR_SECT_CAP * sizeof(unsigned long long) + 2 * SR_RING_CAP;
   static bool attrSet = false;
@@ -597,11 +601,13 @@ int vl_sr_run(vloam_b200_ctx* c, const float* d_xyz, int n, int stride) {
     VL_CUDA(cudaFuncSetAttribute(sr_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pickSmem));
     attrSet = true;
   }
+  VL_BYTES(40.0 * n);  // 2 points + curvature per ring point in, labels + picks out (upper bound: n kept)
   VL_LAUNCH(sr_pick, R, SR_PICK_THREADS, pickSmem, c->cloud.p, c->curv.p, c->label.p, c->picked.p, c->picked.p + n, c->sortScratch.p, c->ringStart, c->ringCount,
             c->provSharp, c->provLess, c->provFlat, c->cntSharp, c->cntLess, c->cntFlat);
   const size_t voxSmem = (size_t)SR_VOX_CAP * (sizeof(unsigned long long) + sizeof(float4));
   static bool voxAttr = false;
   if (!voxAttr) { VL_CUDA(cudaFuncSetAttribute(sr_ring_voxel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)voxSmem)); voxAttr = true; }
+  VL_BYTES(36.0 * n);
   VL_LAUNCH(sr_ring_voxel, R, SR_PICK_THREADS, voxSmem, c->cloud.p, c->label.p, c->ringStart, c->ringCount, c->selIdx.p, c->sortScratch.p,
             c->lessFlatProv.p, c->ringDsCount, 0.2f);
   VL_LAUNCH(sr_offsets, 1, 1024, 0, R, c->cntSharp, c->cntLess, c->cntFlat, c->ringDsCount, c->offSharp, c->offLess, c->offFlat,
@@ -611,14 +617,16 @@ int vl_sr_run(vloam_b200_ctx* c, const float* d_xyz, int n, int stride) {
             c->cntSharp, c->cntLess, c->cntFlat, c->offSharp, c->offLess, c->offFlat, c->ringStart, c->ringDsCount, c->ringDsOff,
             c->lessFlatProv.p, c->sharp.p, c->lessSharp[c->cur].p, c->flat.p, c->lessFlat[c->cur].p);
   VL_CUDA(cudaMemcpyAsync(c->h_srs, c->srs, sizeof(SrScalars), cudaMemcpyDeviceToHost, c->stream));
+  VL_CUDA(cudaEventRecord(c->evSR, c->stream));
   VL_CUDA(cudaGetLastError());
   return VLOAM_OK;
 }
 
-// Sync point S1: the host learns the feature counts (needed to size the LO / LM launches).
+// Sync point S1: the host learns the feature counts.  It waits on the event recorded right after scan
+// registration, not on the stream, so odometry kernels queued behind it keep the GPU busy meanwhile.
 int vl_sr_sync_counts(vloam_b200_ctx* c) {
   if (c->sr_counts_valid) return VLOAM_OK;
-  VL_CUDA(cudaStreamSynchronize(c->stream));
+  VL_CUDA(cudaEventSynchronize(c->evSR));
   if (c->n_in <= 0) { c->nKept = c->nSharp = c->nLessSharp = c->nFlat = c->nLessFlat = 0; }
   else {
     c->nKept = c->h_srs->count; c->nSharp = c->h_srs->nSharp; c->nLessSharp = c->h_srs->nLessSharp;

@@ -166,7 +166,8 @@ static int vl_sort_cluster(vloam_b200_ctx* c, unsigned long long* d_keys, int n_
   const bool prof = c->prof_name[0] && vl_prof_match(c, "bt_cluster_sort") && c->prof_n < VL_PROF_MAX;
   if (prof) cudaEventRecord(c->prof_ev[c->prof_n][0], c->stream);
   VL_CUDA(cudaLaunchKernelEx(&cfg, bt_cluster_sort, d_keys, tile));
-  if (prof) { cudaEventRecord(c->prof_ev[c->prof_n][1], c->stream); c->prof_n++; c->prof_bytes += 16.0 * n_pow2; }
+  if (prof) { cudaEventRecord(c->prof_ev[c->prof_n][1], c->stream); c->prof_kname[c->prof_n] = "bt_cluster_sort"; c->prof_kbytes[c->prof_n] = 16.0 * n_pow2;
+              c->prof_n++; c->prof_bytes += 16.0 * n_pow2; }
   c->launches++;
   return VLOAM_OK;
 }
@@ -371,6 +372,7 @@ int vl_voxel_grid_device(vloam_b200_ctx* c, const float4* d_in, int n, const int
   VL_TRY(vl_sort_u64(c, c->vKeys.p, P));
   VL_LAUNCH(vg_head_count, nTiles, VG_BLOCK, 0, c->vKeys.p, box, c->vScan.p);
   VL_LAUNCH(vg_block_scan, 1, 1024, 0, c->vScan.p, nTiles, box, d_count);
+  VL_BYTES(40.0 * n);  // key + gathered point in, centroid out
   VL_LAUNCH(vg_centroid, nTiles, VG_BLOCK, 0, d_in, c->vKeys.p, box, c->vScan.p, d_out);
   VL_CUDA(cudaGetLastError());
   return VLOAM_OK;
