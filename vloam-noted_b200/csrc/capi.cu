@@ -43,6 +43,8 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   VL_CUDA_CREATE(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   VL_CUDA_CREATE(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
   VL_CUDA_CREATE(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
+  VL_CUDA_CREATE(cudaStreamCreateWithFlags(&c->stream4, cudaStreamNonBlocking));
+  VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evStacksC, cudaEventDisableTiming));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evSR, cudaEventDisableTiming));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evStacks, cudaEventDisableTiming));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evLast, cudaEventDisableTiming));
@@ -95,7 +97,7 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
 void vloam_b200_destroy(vloam_b200_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream3);
+  cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream3); cudaStreamSynchronize(c->stream4);
   // Device memory is released wholesale: contexts live for a whole replay (MAIN.cpp:118-124).
   void* singles[] = {c->ringCount, c->ringStart, c->srs, c->provSharp, c->provLess, c->provFlat, c->cntSharp, c->cntLess, c->cntFlat,
                      c->offSharp, c->offLess, c->offFlat, c->ringDsCount, c->ringDsOff, c->los, c->evalOut, c->lms, c->lmm, c->cubeC,
@@ -105,13 +107,14 @@ void vloam_b200_destroy(vloam_b200_ctx* c) {
                   c->lessFlatProv.p, c->selIdx.p, c->sharp.p, c->lessSharp[0].p, c->lessSharp[1].p, c->flat.p, c->lessFlat[0].p,
                   c->lessFlat[1].p, c->loCornerIdx.p, c->loSurfIdx.p, c->factors.p, c->factorValid.p, c->evalPartials.p,
                   c->poolC.p, c->poolS.p, c->stackC.p, c->stackS.p, c->fromMapC.p, c->fromMapS.p, c->knnIdx.p, c->knnD2.p, c->knnOk.p,
-                  c->vKeys.p, c->vHead.p, c->vScan.p, c->vOut.p, c->vIn.p, c->tailKeys.p, c->staging.p};
+                  c->vKeys.p, c->vKeys2.p, c->vHead.p, c->vScan.p, c->vScan2.p, c->vOut.p, c->vIn.p, c->tailKeys.p, c->staging.p};
   for (void* p : bufs) if (p) cudaFree(p);
   cudaFreeHost(c->h_srs); cudaFreeHost(c->h_los); cudaFreeHost(c->h_lms); cudaFreeHost(c->h_lmm); cudaFreeHost(c->h_vScalars);
   for (int k = 0; k < 4; ++k) cudaEventDestroy(c->ev[k]);
   cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream3);
   cudaEventDestroy(c->evSR); cudaEventDestroy(c->evStacks); cudaEventDestroy(c->evLast); cudaEventDestroy(c->evPose); cudaEventDestroy(c->evMap);
-  cudaStreamDestroy(c->stream2); cudaStreamDestroy(c->stream3);
+  cudaEventDestroy(c->evStacksC);
+  cudaStreamDestroy(c->stream2); cudaStreamDestroy(c->stream3); cudaStreamDestroy(c->stream4);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -220,6 +223,7 @@ int vloam_b200_process_frame_device(vloam_b200_ctx* c, const float* d_xyz, int n
 
 int vloam_b200_synchronize(vloam_b200_ctx* c) {
   VL_CUDA(cudaStreamSynchronize(c->stream)); VL_CUDA(cudaStreamSynchronize(c->stream2)); VL_CUDA(cudaStreamSynchronize(c->stream3));
+  VL_CUDA(cudaStreamSynchronize(c->stream4));
   return VLOAM_OK;
 }
 void* vloam_b200_stream(vloam_b200_ctx* c) { return (void*)c->stream; }

@@ -88,6 +88,8 @@ struct vloam_b200_ctx {
   int device;
   cudaStream_t stream;
   cudaStream_t stream2;       // side stream: work that is independent of the odometry solve overlaps it
+  cudaStream_t stream4;       // second side stream: the corner stack filter runs beside the surf one
+  cudaEvent_t evStacksC;
   cudaStream_t stream3;       // map update of frame k runs here while frame k+1's scan registration / odometry run on `stream`
   cudaEvent_t evSR;           // scan registration of this frame finished and its counts are in h_srs
   cudaEvent_t evStacks;       // this frame's downsampled stacks are ready
@@ -164,7 +166,7 @@ struct vloam_b200_ctx {
   DBuf<int> gridCellStart[2]; DBuf<int> gridPointIdx[2]; DBuf<int> gridCellOfPoint[2];
   struct GridParams* gridPrm;  // device [2]
   // voxel filter scratch
-  DBuf<unsigned long long> vKeys; DBuf<int> vHead; DBuf<int> vScan;
+  DBuf<unsigned long long> vKeys, vKeys2; DBuf<int> vHead; DBuf<int> vScan, vScan2;  // two scratch lanes: the corner and surf filters run concurrently
   DBuf<float4> vOut; DBuf<float4> vIn;
   int* vScalars;  // device scratch ints
   int* h_vScalars;
@@ -263,7 +265,7 @@ int vl_scan_exclusive(vloam_b200_ctx* c, const int* in, int n, int* tileSum, int
 int vl_sort_u64(vloam_b200_ctx* c, unsigned long long* d_keys, int n_pow2);
 // pcl::VoxelGrid of d_in[0..n) -> d_out, count written to *d_count (device int); n is a host bound,
 // d_n (device int, may be null) is the actual count.
-int vl_voxel_grid_device(vloam_b200_ctx* c, const float4* d_in, int n, const int* d_n, float leaf, float4* d_out, int* d_count);
+int vl_voxel_grid_device(vloam_b200_ctx* c, const float4* d_in, int n, const int* d_n, float leaf, float4* d_out, int* d_count, int lane = 0);
 
 // solver (lm_solver.cu): evaluates factor slots [0, nslots) with validity flags.
 // nslots: host bound on the factor slots; d_nslots (device, may be null): actual count, min() of both is used

@@ -942,15 +942,19 @@ extern bool vl_debug_capture(const vloam_b200_ctx* c);
 int vl_lm_enqueue_stacks(vloam_b200_ctx* c, const float4* corner, int nc, const float4* surf, int ns) {
   LmDevice* d = lmdev(c);
   cudaStream_t main = c->stream;
+  // surf filter on stream2 (scratch lane 0), corner filter beside it on stream4 (scratch lane 1)
   c->stream = c->stream2;
   cudaStreamWaitEvent(c->stream2, c->evMap, 0);  // the previous frame's map update still reads the previous stacks
-  int r = vl_reserve(c, c->stackC, (size_t)max(nc, 1));
-  if (r == VLOAM_OK) r = vl_reserve(c, c->stackS, (size_t)max(ns, 1));
-  if (r == VLOAM_OK) r = vl_voxel_grid_device(c, corner, nc, nullptr, c->prm.line_res, c->stackC.p, d->dQ);
-  if (r == VLOAM_OK) r = vl_voxel_grid_device(c, surf, ns, nullptr, c->prm.plane_res, c->stackS.p, d->dQ + 1);
+  int r = vl_reserve(c, c->stackS, (size_t)max(ns, 1));
+  if (r == VLOAM_OK) r = vl_voxel_grid_device(c, surf, ns, nullptr, c->prm.plane_res, c->stackS.p, d->dQ + 1, 0);
+  c->stream = c->stream4;
+  cudaStreamWaitEvent(c->stream4, c->evMap, 0);
+  if (r == VLOAM_OK) r = vl_reserve(c, c->stackC, (size_t)max(nc, 1));
+  if (r == VLOAM_OK) r = vl_voxel_grid_device(c, corner, nc, nullptr, c->prm.line_res, c->stackC.p, d->dQ, 1);
   c->stream = main;
   if (r != VLOAM_OK) return r;
   VL_CUDA(cudaEventRecord(c->evStacks, c->stream2));
+  VL_CUDA(cudaEventRecord(c->evStacksC, c->stream4));
   c->stacksReady = true;
   return VLOAM_OK;
 }
@@ -971,19 +975,12 @@ int vl_lm_run(vloam_b200_ctx* c) {
     VL_CUDA(cudaStreamSynchronize(c->stream));
     VL_TRY(vl_lm_enqueue_stacks(c, c->cornerLastPtr, c->nCornerLast, c->surfLastPtr, c->nSurfLast));
   }
-  VL_CUDA(cudaStreamWaitEvent(c->stream, c->evStacks, 0));
   c->stacksReady = false;
-  VL_LAUNCH(lm_set_counts, 1, 32, 0, c->lmm, d->work, d->dQ, d->dQ + 1);
   // The search / fit / solve kernels read the sizes (Mc, Ms, Qc, Qs) and the LM.cpp:514 decision on the
   // device, so they are queued without waiting for the host; sync point S2 sits after the solve, where
   // the pose has to be final anyway.  (Debug snapshots need host counts first and sync here.)
   const bool capture = vl_debug_capture(c);
   int Qc = 0, Qs = 0;
-  if (capture) {
-    VL_CUDA(cudaMemcpyAsync(c->h_lmm, c->lmm, sizeof(LmScalars), cudaMemcpyDeviceToHost, c->stream));
-    VL_CUDA(cudaStreamSynchronize(c->stream));
-    Qc = c->h_lmm->Qc; Qs = c->h_lmm->Qs;
-  }
   const long long totalBound = d->hMapUpperC + d->hMapUpperS;
   const int nqBound = max(c->nCornerLast + c->nSurfLast, 1);  // a voxel filter never grows a cloud
   {
@@ -997,6 +994,15 @@ int vl_lm_run(vloam_b200_ctx* c) {
     VL_TRY(vl_scan_exclusive(c, d->cellCount, nCells, d->tileSum, d->cellStart));
     VL_BYTES(44.0 * (double)totalBound);  // read point + cell id + cell start, atomic, write sorted point
     VL_LAUNCH(lm_grid_fill, gsGrid, 256, 0, c->lmm, c->fromMapC.p, c->fromMapS.p, d->cellOfPoint.p, d->cellStart, d->cellFill, d->sortedPts.p);
+    // only now are this frame's downsampled stacks needed (they were filtered on the side streams)
+    VL_CUDA(cudaStreamWaitEvent(c->stream, c->evStacks, 0));
+    VL_CUDA(cudaStreamWaitEvent(c->stream, c->evStacksC, 0));
+    VL_LAUNCH(lm_set_counts, 1, 32, 0, c->lmm, d->work, d->dQ, d->dQ + 1);
+    if (capture) {
+      VL_CUDA(cudaMemcpyAsync(c->h_lmm, c->lmm, sizeof(LmScalars), cudaMemcpyDeviceToHost, c->stream));
+      VL_CUDA(cudaStreamSynchronize(c->stream));
+      Qc = c->h_lmm->Qc; Qs = c->h_lmm->Qs;
+    }
     VL_TRY(vl_reserve(c, c->knnIdx, (size_t)nqBound * 5));
     VL_TRY(vl_reserve(c, c->knnD2, (size_t)nqBound * 5));
     VL_TRY(vl_reserve(c, c->knnOk, (size_t)nqBound));

@@ -357,23 +357,25 @@ __global__ void __launch_bounds__(VG_BLOCK) vg_centroid(const float4* __restrict
   }
 }
 
-int vl_voxel_grid_device(vloam_b200_ctx* c, const float4* d_in, int n, const int* d_n, float leaf, float4* d_out, int* d_count) {
+int vl_voxel_grid_device(vloam_b200_ctx* c, const float4* d_in, int n, const int* d_n, float leaf, float4* d_out, int* d_count, int lane) {
   if (n <= 0) { VL_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), c->stream)); return VLOAM_OK; }
   int P = 2; while (P < n) P <<= 1;
   const int nb = min(vl_div_up(n, VG_BLOCK), 256);
   const int nTiles = vl_div_up(n, 1024);
-  VL_TRY(vl_reserve(c, c->vKeys, (size_t)P));
-  VL_TRY(vl_reserve(c, c->vScan, (size_t)nTiles + 256 * 6 + 64));
-  float* partial = reinterpret_cast<float*>(c->vScan.p + nTiles);
-  VgBox* box = reinterpret_cast<VgBox*>(c->vScalars);
+  DBuf<unsigned long long>& vKeys = lane ? c->vKeys2 : c->vKeys;
+  DBuf<int>& vScan = lane ? c->vScan2 : c->vScan;
+  VL_TRY(vl_reserve(c, vKeys, (size_t)P));
+  VL_TRY(vl_reserve(c, vScan, (size_t)nTiles + 256 * 6 + 64));
+  float* partial = reinterpret_cast<float*>(vScan.p + nTiles);
+  VgBox* box = reinterpret_cast<VgBox*>(c->vScalars + (lane ? 96 : 0));
   VL_LAUNCH(vg_bbox, nb, VG_BLOCK, 0, d_in, n, d_n, partial);
   VL_LAUNCH(vg_box, 1, 32, 0, partial, nb, n, d_n, leaf, box, d_count);
-  VL_LAUNCH(vg_keys, vl_div_up(P, VG_BLOCK), VG_BLOCK, 0, d_in, box, c->vKeys.p, P);
-  VL_TRY(vl_sort_u64(c, c->vKeys.p, P));
-  VL_LAUNCH(vg_head_count, nTiles, VG_BLOCK, 0, c->vKeys.p, box, c->vScan.p);
-  VL_LAUNCH(vg_block_scan, 1, 1024, 0, c->vScan.p, nTiles, box, d_count);
+  VL_LAUNCH(vg_keys, vl_div_up(P, VG_BLOCK), VG_BLOCK, 0, d_in, box, vKeys.p, P);
+  VL_TRY(vl_sort_u64(c, vKeys.p, P));
+  VL_LAUNCH(vg_head_count, nTiles, VG_BLOCK, 0, vKeys.p, box, vScan.p);
+  VL_LAUNCH(vg_block_scan, 1, 1024, 0, vScan.p, nTiles, box, d_count);
   VL_BYTES(40.0 * n);  // key + gathered point in, centroid out
-  VL_LAUNCH(vg_centroid, nTiles, VG_BLOCK, 0, d_in, c->vKeys.p, box, c->vScan.p, d_out);
+  VL_LAUNCH(vg_centroid, nTiles, VG_BLOCK, 0, d_in, vKeys.p, box, vScan.p, d_out);
   VL_CUDA(cudaGetLastError());
   return VLOAM_OK;
 }
