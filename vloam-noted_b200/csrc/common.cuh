@@ -297,6 +297,26 @@ __device__ __forceinline__ void vl_qmul(const double a[4], const double b[4], do
   const double z = aw * bz + az * bw + ax * by - ay * bx;
   o[0] = x; o[1] = y; o[2] = z; o[3] = w;
 }
+// Visit every index of up to 32 ranges with all lanes busy.  Lane r owns range [myBeg, myBeg + myLen)
+// (myLen = 0 when it has none); the cell-start look-ups of all ranges are therefore issued together
+// (one memory latency instead of one per row) and short rows no longer leave lanes idle.  soff / sbeg:
+// 32 ints of shared memory each, private to the warp.  BODY sees `const int p`.
+#define VL_WARP_VISIT_RANGES(myBeg, myLen, lane, soff, sbeg, BODY)                                  \
+  do {                                                                                              \
+    int inc_ = (myLen);                                                                             \
+    for (int d_ = 1; d_ < 32; d_ <<= 1) { const int t_ = __shfl_up_sync(0xffffffffu, inc_, d_); if ((lane) >= d_) inc_ += t_; } \
+    __syncwarp();                                                                                   \
+    (soff)[lane] = inc_ - (myLen); (sbeg)[lane] = (myBeg);                                          \
+    __syncwarp();                                                                                   \
+    const int total_ = __shfl_sync(0xffffffffu, inc_, 31);                                          \
+    for (int idx_ = (lane); idx_ < total_; idx_ += 32) {                                            \
+      int lo_ = 0, hi_ = 32;                                                                        \
+      while (hi_ - lo_ > 1) { const int mid_ = (lo_ + hi_) >> 1; if ((soff)[mid_] <= idx_) lo_ = mid_; else hi_ = mid_; } \
+      const int p = (sbeg)[lo_] + (idx_ - (soff)[lo_]);                                             \
+      BODY                                                                                          \
+    }                                                                                               \
+  } while (0)
+
 // FLANN L2_Simple<float>: acc = 0; acc += d*d over x, y, z (f32, no FMA: -fmad=false).
 __device__ __forceinline__ float vl_dist2(float qx, float qy, float qz, float px, float py, float pz) {
   float acc = 0.f, d;

@@ -399,6 +399,9 @@ __global__ void __launch_bounds__(256) lm_knn(const LmScalars* __restrict__ s, c
                                                   int* __restrict__ knnIdx, float* __restrict__ knnD2, int* __restrict__ knnOk,
                                                   double* __restrict__ factors, int* __restrict__ valid) {
   const int lane = threadIdx.x & 31;
+  __shared__ int srange[8][64];
+  int* soff = srange[threadIdx.x >> 5];
+  int* sbeg = soff + 32;
   const int Qc = s->Qc, Qs = s->Qs;
   if (!s->optimized) return;
   const int nWarps = (gridDim.x * blockDim.x) >> 5;
@@ -415,14 +418,18 @@ __global__ void __launch_bounds__(256) lm_knn(const LmScalars* __restrict__ s, c
   float bd[5]; int bi[5];
 #pragma unroll
   for (int k = 0; k < 5; ++k) { bd[k] = CUDART_INF_F; bi[k] = 0x7fffffff; }
-  for (int row = 0; row < 9; ++row) {  // 9 (y,z) rows; the 3 x-adjacent cells of a row are contiguous
-    const int yy = cy - 1 + row % 3, zz = cz - 1 + row / 3;
-    if (yy < 0 || yy >= LM_GY || zz < 0 || zz >= LM_GZ) continue;
-    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, LM_GX - 1);
-    if (x0 > x1) continue;
-    const int c0 = kind * LM_NCELL + x0 + LM_GX * (yy + LM_GY * zz);
-    const int beg = cellStart[c0], end = cellStart[c0 + (x1 - x0) + 1];
-    for (int p = beg + lane; p < end; p += 32) {
+  {  // 9 (y,z) rows; the 3 x-adjacent cells of a row are contiguous.  Lane r < 9 looks up row r.
+    int rb = 0, rl = 0;
+    if (lane < 9) {
+      const int yy = cy - 1 + lane % 3, zz = cz - 1 + lane / 3;
+      const int x0 = max(cx - 1, 0), x1 = min(cx + 1, LM_GX - 1);
+      if (yy >= 0 && yy < LM_GY && zz >= 0 && zz < LM_GZ && x0 <= x1) {
+        const int c0 = kind * LM_NCELL + x0 + LM_GX * (yy + LM_GY * zz);
+        rb = cellStart[c0];
+        rl = cellStart[c0 + (x1 - x0) + 1] - rb;
+      }
+    }
+    VL_WARP_VISIT_RANGES(rb, rl, lane, soff, sbeg, {
       const float4 t = __ldg(&sortedPts[p]);
       const float d = vl_dist2(sx, sy, sz, t.x, t.y, t.z);
       const int id = __float_as_int(t.w);
@@ -435,7 +442,7 @@ __global__ void __launch_bounds__(256) lm_knn(const LmScalars* __restrict__ s, c
             const int ti = bi[k]; bi[k] = bi[k - 1]; bi[k - 1] = ti;
           }
       }
-    }
+    });
   }
   // merge the 32 lane-local lists: pop the global minimum five times
   float nd[5]; int ni[5];

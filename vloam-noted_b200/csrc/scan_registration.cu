@@ -407,7 +407,6 @@ __global__ void __launch_bounds__(SR_PICK_THREADS) sr_ring_voxel(const float4* _
   __shared__ int warpSum[SR_PICK_THREADS / 32];
   __shared__ float red[6][SR_PICK_THREADS / 32];
   __shared__ VoxBox box;
-  __shared__ int sTotal;
   const int r = blockIdx.x;
   const int rs = ringStart[r], rc = ringCount[r];
   const int start = rs + 5, end = rs + rc - 6;
