@@ -306,7 +306,11 @@ def profile_dominant(ctx, dscans, first, K, map_points):
               "achieved_gbs": (byt / (ms * 1e-3) / 1e9) if byt > 0 and ms > 0 else None} for nm, cnt, ms, byt in rows[:12]]
     nm, cnt, ms, byt = rows[0]
     achieved = byt / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-    roof = {"bound": "hbm", "kernel": nm, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(nm)
+    roof = {"bound": "hbm", "kernel": nm, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "peak_source": how, "launches_timed": cnt, "avg_us": 1e3 * ms / cnt, "algorithmic_bytes_per_launch": byt / cnt,
             "share_of_kernel_time": ms / total,
             "note": "the frame is launch/dependency-latency bound (SURVEY 8d): ~60 MB of algorithmic traffic per frame in ~0.7 ms"}
