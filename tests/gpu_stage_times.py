@@ -7,9 +7,24 @@ pkg = importlib.import_module("vloam-noted_b200")
 import bench
 import torch
 N = int(os.environ.get('FRAMES', '40'))
-scans, traj, cb, sb = bench.make_sequence(pkg, 0, N)
-ctx = pkg.Context()
-ctx.set("lm.cornerMap", cb); ctx.set("lm.surfMap", sb)
+WL = os.environ.get('WORKLOAD', 'c3')
+if WL == 'c4':  # OS1-128 sweeps against a ~1.9M-point map
+    world = pkg.synth.World(1234, 2, 190.0)
+    traj = pkg.synth.trajectory(N)
+    scans = [world.scan(2, traj[k], 1000 + k) for k in range(N)]
+    cb, sb = pkg.synth.cubes_blob(world.plant(0, 0.4, seed=99), 0.4), pkg.synth.cubes_blob(world.plant(1, 0.8, seed=98), 0.8)
+    ctx = pkg.Context(n_scans=128, minimum_range=0.3)
+elif WL == 'c1':  # VLP-16 sweeps, no planted map
+    world = pkg.synth.World(1234, 0, 160.0)
+    traj = pkg.synth.trajectory(N)
+    scans = [world.scan(0, traj[k], 1000 + k) for k in range(N)]
+    cb = sb = None
+    ctx = pkg.Context(n_scans=16, minimum_range=0.3, line_res=0.2, plane_res=0.4)
+else:
+    scans, traj, cb, sb = bench.make_sequence(pkg, 0, N)
+    ctx = pkg.Context()
+if cb is not None:
+    ctx.set("lm.cornerMap", cb); ctx.set("lm.surfMap", sb)
 ctx.set_timing(True)
 d = [torch.from_numpy(s).cuda() for s in scans]
 torch.cuda.synchronize()

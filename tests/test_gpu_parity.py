@@ -363,3 +363,39 @@ def test_lo_association_non_monotone_rings(pkg, op, synth, street):
     assert_bits_equal(co, cg_, "corner association"); assert_bits_equal(so, sg, "surf association")
     assert (so[:, 2] >= 0).sum() > 100
     g.close()
+
+
+def test_config_c4_os1_128_against_2m_map(pkg, op, synth):
+    """BASELINE config C4: OS1-128 dense sweeps (~257k points, 128-beam extension) against a ~1.9M-point
+    planted map; two teacher-forced frames, every stage compared."""
+    world = synth.World(1234, 2, 190.0)
+    cb, sb = synth.cubes_blob(world.plant(0, 0.4, seed=99), 0.4), synth.cubes_blob(world.plant(1, 0.8, seed=98), 0.8)
+    assert synth.blob_counts(cb).sum() + synth.blob_counts(sb).sum() > 1_800_000
+    o, g = op.Oracle(**KW[2], knn_backend=1), pkg.Context(**KW[2])
+    g.set_capture(True)
+    for x in (o, g):
+        x.set("lm.cornerMap", cb); x.set("lm.surfMap", sb)
+    for k in range(2):
+        scan = world.scan(2, [1.0 * k, 0.0, 0.0, 0.0, 0.0, 0.0], 1000 + k)
+        assert len(scan) > 240_000
+        if k > 0:
+            teacher_force(o, g)
+        o.scan_registration(scan); g.begin_frame(); g.scan_registration(scan)
+        o.laser_odometry(); g.laser_odometry()
+        o.laser_mapping(); g.laser_mapping()
+        check_frame(o, g, k)
+    g.close()
+
+
+def test_process_frame_is_deterministic(pkg, synth, street):
+    """Two contexts fed the same sweeps give bit-identical poses and maps (fixed reduction orders)."""
+    traj = synth.trajectory(5)
+    scans = [street.scan(1, traj[k], 1000 + k) for k in range(5)]
+    outs = []
+    for _ in range(2):
+        g = pkg.Context(**KW[1])
+        poses = [g.process_frame(s).copy() for s in scans]
+        outs.append((np.array(poses), g.get("lm.surfMap"), g.get("lm.cornerMap")))
+        g.close()
+    assert (outs[0][0] == outs[1][0]).all()
+    assert outs[0][1] == outs[1][1] and outs[0][2] == outs[1][2]
