@@ -206,11 +206,21 @@ struct GridParams {
     if (r_ != VLOAM_OK) return r_; \
   } while (0)
 
+// Every kernel is launched with programmatic stream serialisation allowed and starts with VL_PDL_WAIT()
+// (griddepcontrol.wait): the next grid of a dependent chain is already resident when its predecessor
+// drains, which removes most of the launch gap between the ~45 dependent kernels of a frame.
+#define VL_PDL_WAIT() cudaGridDependencySynchronize()
 #define VL_LAUNCH(kernel, grid, block, smem, ...)                                              \
   do {                                                                                         \
     const bool prof_ = c->prof_name[0] && vl_prof_match(c, #kernel) && c->prof_n < VL_PROF_MAX; \
     if (prof_) cudaEventRecord(c->prof_ev[c->prof_n][0], c->stream);                           \
-    kernel<<<(grid), (block), (smem), c->stream>>>(__VA_ARGS__);                               \
+    cudaLaunchConfig_t cfg_ = {};                                                              \
+    cfg_.gridDim = dim3(grid); cfg_.blockDim = dim3(block); cfg_.dynamicSmemBytes = (smem); cfg_.stream = c->stream; \
+    cudaLaunchAttribute at_[1];                                                                \
+    at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                            \
+    at_[0].val.programmaticStreamSerializationAllowed = 1;                                     \
+    cfg_.attrs = at_; cfg_.numAttrs = 1;                                                       \
+    cudaLaunchKernelEx(&cfg_, kernel, __VA_ARGS__);                                            \
     if (prof_) { cudaEventRecord(c->prof_ev[c->prof_n][1], c->stream); c->prof_kname[c->prof_n] = #kernel; c->prof_kbytes[c->prof_n] = c->prof_next_bytes; \
                  c->prof_n++; c->prof_bytes += c->prof_next_bytes; } \
     c->prof_next_bytes = 0;                                                                    \

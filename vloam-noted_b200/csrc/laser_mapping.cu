@@ -90,6 +90,8 @@ __device__ __forceinline__ int lm_scan256(int v, int* buf, int* total) {
 // ---- LaserMapping::input (LM.cpp:178-209) + centre cube / roll / valid list (LM.cpp:228-466)
 __global__ void __launch_bounds__(1024) lm_prepare(LmScalars* __restrict__ s, const LoScalars* __restrict__ lo, MapCubeTable* __restrict__ tc,
                                                    MapCubeTable* __restrict__ ts, RfWork* __restrict__ w, int skip, int resetValid) {
+  VL_PDL_WAIT();
+
   __shared__ int shift[3];
   __shared__ int center[3];
   if (threadIdx.x == 0) {
@@ -207,6 +209,8 @@ __global__ void __launch_bounds__(256) lm_gather(const LmScalars* __restrict__ s
                                                  const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts,
                                                  const float4* __restrict__ poolC, const float4* __restrict__ poolS,
                                                  float4* __restrict__ outC, float4* __restrict__ outS) {
+  VL_PDL_WAIT();
+
   const int nv = s->validNum, mc = s->Mc, total = s->Mc + s->Ms;
   for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
     const int kind = g >= mc;
@@ -228,6 +232,8 @@ __device__ __forceinline__ int lm_cell_coord(float v, float o, int n) {
 __global__ void __launch_bounds__(256) lm_grid_count(const LmScalars* __restrict__ s, const RfWork* __restrict__ w,
                                                      const float4* __restrict__ mapC, const float4* __restrict__ mapS,
                                                      int* __restrict__ cellCount, int* __restrict__ cellOfPoint) {
+  VL_PDL_WAIT();
+
   const int mc = s->Mc, total = s->Mc + s->Ms;
   const float ox = w->gridOrigin[0], oy = w->gridOrigin[1], oz = w->gridOrigin[2];
   for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
@@ -240,6 +246,8 @@ __global__ void __launch_bounds__(256) lm_grid_count(const LmScalars* __restrict
 }
 // exclusive scan over 2*LM_NCELL counts: tile sums (1024 per block) -> scan of tile sums -> apply
 __global__ void __launch_bounds__(256) lm_scan_tiles(const int* __restrict__ in, int n, int* __restrict__ tileSum) {
+  VL_PDL_WAIT();
+
   int acc = 0;
   const int base = blockIdx.x * 1024;
   for (int q = 0; q < 4; ++q) { const int t = base + q * 256 + threadIdx.x; if (t < n) acc += in[t]; }
@@ -250,6 +258,8 @@ __global__ void __launch_bounds__(256) lm_scan_tiles(const int* __restrict__ in,
   if (threadIdx.x == 0) { int v = 0; for (int k = 0; k < 8; ++k) v += ws[k]; tileSum[blockIdx.x] = v; }
 }
 __global__ void __launch_bounds__(1024) lm_scan_sums(int* __restrict__ tileSum, int nTiles) {
+  VL_PDL_WAIT();
+
   __shared__ int buf[1024];
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
@@ -272,6 +282,8 @@ __global__ void __launch_bounds__(1024) lm_scan_sums(int* __restrict__ tileSum, 
   }
 }
 __global__ void __launch_bounds__(256) lm_scan_apply(const int* __restrict__ in, int n, const int* __restrict__ tileSum, int* __restrict__ out) {
+  VL_PDL_WAIT();
+
   __shared__ int ws[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int running = tileSum[blockIdx.x];
@@ -305,6 +317,8 @@ __global__ void __launch_bounds__(256) lm_grid_fill(const LmScalars* __restrict_
                                                     const float4* __restrict__ mapS, const int* __restrict__ cellOfPoint,
                                                     const int* __restrict__ cellStart, int* __restrict__ cellFill,
                                                     float4* __restrict__ sortedPts) {
+  VL_PDL_WAIT();
+
   const int mc = s->Mc, total = s->Mc + s->Ms;
   for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
     const int kind = g >= mc;
@@ -398,6 +412,8 @@ __global__ void __launch_bounds__(256) lm_knn(const LmScalars* __restrict__ s, c
                                                   const int* __restrict__ cellStart, const float4* __restrict__ sortedPts,
                                                   int* __restrict__ knnIdx, float* __restrict__ knnD2, int* __restrict__ knnOk,
                                                   double* __restrict__ factors, int* __restrict__ valid) {
+  VL_PDL_WAIT();
+
   const int lane = threadIdx.x & 31;
   __shared__ int srange[8][64];
   int* soff = srange[threadIdx.x >> 5];
@@ -475,6 +491,8 @@ __global__ void __launch_bounds__(128) lm_fit(const LmScalars* __restrict__ s, c
                                               const float4* __restrict__ mapC, const float4* __restrict__ mapS, const int* __restrict__ knnIdx,
                                               const float* __restrict__ knnD2, int* __restrict__ knnOk, double* __restrict__ factors,
                                               int* __restrict__ valid) {
+  VL_PDL_WAIT();
+
   const int Qc = s->Qc, Qs = s->Qs;
   if (!s->optimized) return;
   for (int qi = blockIdx.x * blockDim.x + threadIdx.x; qi < Qc + Qs; qi += gridDim.x * blockDim.x) {
@@ -530,7 +548,9 @@ __global__ void __launch_bounds__(128) lm_fit(const LmScalars* __restrict__ s, c
   }
 }
 
-__global__ void lm_transform_update(LmScalars* s) {  // LM.cpp:147-151
+__global__ void lm_transform_update(LmScalars* s) {
+  VL_PDL_WAIT();
+  // LM.cpp:147-151
   if (threadIdx.x != 0) return;
   const double* q = s->q_wodom;
   const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
@@ -552,6 +572,8 @@ __global__ void __launch_bounds__(256) rf_keys(const LmScalars* __restrict__ s, 
                                                const float4* __restrict__ stackC, const float4* __restrict__ stackS,
                                                float4* __restrict__ newPts, int* __restrict__ newCube,
                                                unsigned long long* __restrict__ keys, int P) {
+  VL_PDL_WAIT();
+
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= P) return;
   const int tailTotal = w->tailOff[LM_NSEG];
@@ -599,6 +621,8 @@ __device__ __forceinline__ float4 rf_key_point(unsigned long long key, const LmS
 #define RF_VOX(key) ((unsigned)(((key) >> 26) & 0x3fffffffull))
 
 __global__ void __launch_bounds__(256) rf_segments(const unsigned long long* __restrict__ keys, int P, RfWork* __restrict__ w) {
+  VL_PDL_WAIT();
+
   const int sg = threadIdx.x;
   if (sg > LM_NSEG) return;
   const unsigned long long target = (unsigned long long)sg << 56;
@@ -614,6 +638,8 @@ __global__ void __launch_bounds__(256) rf_match(const unsigned long long* __rest
                                                 const RfWork* __restrict__ w, vloam_b200_params prm, const MapCubeTable* __restrict__ tc,
                                                 const MapCubeTable* __restrict__ ts, const float4* __restrict__ poolC,
                                                 const float4* __restrict__ poolS, int* __restrict__ unmatchedHead) {
+  VL_PDL_WAIT();
+
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= w->nKeysValid) return;
   const unsigned long long key = keys[t];
@@ -636,6 +662,8 @@ __global__ void __launch_bounds__(256) rf_match(const unsigned long long* __rest
 
 __global__ void __launch_bounds__(1024) rf_scan_layout(int* __restrict__ unmatched, const LmScalars* __restrict__ s, RfWork* __restrict__ w,
                                                        const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts) {
+  VL_PDL_WAIT();
+
   // exclusive scan of unmatched[0..n) in place, unmatched[n] = total
   __shared__ int buf[1024];
   __shared__ int carry;
@@ -690,6 +718,8 @@ __global__ void __launch_bounds__(256) rf_emit_new(const unsigned long long* __r
                                                    const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts,
                                                    const float4* __restrict__ poolC, const float4* __restrict__ poolS,
                                                    const float4* __restrict__ newPts, float4* __restrict__ staging) {
+  VL_PDL_WAIT();
+
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = w->nKeysValid;
   if (t >= n) return;
@@ -716,6 +746,8 @@ __global__ void __launch_bounds__(256) rf_emit_prefix(const unsigned long long* 
                                                       const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts,
                                                       const float4* __restrict__ poolC, const float4* __restrict__ poolS,
                                                       const float4* __restrict__ newPts, float4* __restrict__ staging) {
+  VL_PDL_WAIT();
+
   const int total = w->prefOff[LM_NSEG];
   for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
     int lo = 0, hi = LM_NSEG;
@@ -739,6 +771,8 @@ __global__ void __launch_bounds__(256) rf_emit_prefix(const unsigned long long* 
 // a block scan keeps the layout deterministic)
 __global__ void __launch_bounds__(256) rf_alloc(LmScalars* __restrict__ s, const RfWork* __restrict__ w, MapCubeTable* __restrict__ tc,
                                                 MapCubeTable* __restrict__ ts, int poolCapC, int poolCapS) {
+  VL_PDL_WAIT();
+
   __shared__ int sb[256];
   const int sg = threadIdx.x;
   const int kind = sg / VL_MAX_VALID, slot = sg % VL_MAX_VALID;
@@ -766,6 +800,8 @@ __global__ void __launch_bounds__(256) rf_alloc(LmScalars* __restrict__ s, const
 __global__ void __launch_bounds__(256) rf_commit(const float4* __restrict__ staging, LmScalars* __restrict__ s, RfWork* __restrict__ w,
                                                  vloam_b200_params prm, MapCubeTable* __restrict__ tc, MapCubeTable* __restrict__ ts,
                                                  float4* __restrict__ poolC, float4* __restrict__ poolS) {
+  VL_PDL_WAIT();
+
   const int total = w->outOff[LM_NSEG];
   for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
     int lo = 0, hi = LM_NSEG;
@@ -784,6 +820,8 @@ __global__ void __launch_bounds__(256) rf_commit(const float4* __restrict__ stag
 }
 
 __global__ void rf_finish(LmScalars* __restrict__ s, const RfWork* __restrict__ w, MapCubeTable* __restrict__ tc, MapCubeTable* __restrict__ ts) {
+  VL_PDL_WAIT();
+
   const int sg = threadIdx.x;
   if (sg >= LM_NSEG) return;
   const int kind = sg / VL_MAX_VALID, slot = sg % VL_MAX_VALID;
@@ -803,6 +841,8 @@ __global__ void __launch_bounds__(1024) rf_append_outside(LmScalars* __restrict_
                                                           const int* __restrict__ newCube, MapCubeTable* __restrict__ tc,
                                                           MapCubeTable* __restrict__ ts, float4* __restrict__ poolC, float4* __restrict__ poolS,
                                                           int poolCapC, int poolCapS) {
+  VL_PDL_WAIT();
+
   const int Qc = s->Qc, total = s->Qc + s->Qs;
   __shared__ int lIdx[1024], lKey[1024], lRank[1024], lTot[1024];
   __shared__ int gKey[1024], gOld[1024], gNew[1024], gCnt[1024];
@@ -877,6 +917,8 @@ __global__ void __launch_bounds__(1024) rf_append_outside(LmScalars* __restrict_
 // after an import: longest strictly increasing voxel-key prefix of every cube
 __global__ void __launch_bounds__(256) lm_scan_sorted(const LmScalars* __restrict__ s, vloam_b200_params prm, MapCubeTable* __restrict__ t,
                                                       const float4* __restrict__ pool, int kind) {
+  VL_PDL_WAIT();
+
   const int cb = blockIdx.x;
   __shared__ int firstBad;
   if (threadIdx.x == 0) firstBad = INT_MAX;
@@ -891,6 +933,8 @@ __global__ void __launch_bounds__(256) lm_scan_sorted(const LmScalars* __restric
 }
 
 __global__ void lm_set_counts(LmScalars* s, RfWork* w, const int* qc, const int* qs) {
+  VL_PDL_WAIT();
+
   if (threadIdx.x != 0) return;
   s->Qc = *qc; s->Qs = *qs;
   // LM.cpp:514: optimise only against a sub-map with > 10 corner and > 50 surf points

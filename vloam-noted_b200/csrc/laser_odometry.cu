@@ -48,6 +48,8 @@ __device__ __forceinline__ float lo_sqdis(const float4 t, float sx, float sy, fl
 // tbl layout per cloud: [0, LO_TBL) first-index table, [LO_TBL] = 1 if monotone.
 __global__ void __launch_bounds__(256) lo_ring_table(const float4* __restrict__ corner, int nc, const float4* __restrict__ surf, int ns,
                                                      int* __restrict__ tbl) {
+  VL_PDL_WAIT();
+
   const int which = blockIdx.y;
   const float4* cl = which ? surf : corner;
   const int n = which ? ns : nc;
@@ -66,12 +68,16 @@ __global__ void __launch_bounds__(256) lo_ring_table(const float4* __restrict__ 
   }
   if (j == n - 1) for (int q = v + 1; q < LO_TBL; ++q) t[q] = n;
 }
-__global__ void lo_ring_table_init(int* __restrict__ tbl) { if (threadIdx.x < 2) tbl[threadIdx.x * (LO_TBL + 1) + LO_TBL] = 1; }
+__global__ void lo_ring_table_init(int* __restrict__ tbl) {
+  VL_PDL_WAIT();
+ if (threadIdx.x < 2) tbl[threadIdx.x * (LO_TBL + 1) + LO_TBL] = 1; }
 
 template <bool SURF>
 __global__ void __launch_bounds__(LO_QPB * 32) lo_assoc(const float4* __restrict__ query, int nq, const float4* __restrict__ target, int nt,
                                                         const double* __restrict__ pose, const int* __restrict__ tbl, int* __restrict__ outIdx,
                                                         double* __restrict__ factors, int* __restrict__ valid, int slotBase) {
+  VL_PDL_WAIT();
+
   __shared__ float sq[LO_QPB][3];
   __shared__ Best sbest[LO_QPB][LO_QPB];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -256,6 +262,8 @@ __device__ __forceinline__ int log_cell(float x, float y, float z) { return log_
 
 __global__ void __launch_bounds__(256) lo_grid_count(const float4* __restrict__ corner, int nc, const float4* __restrict__ surf, int ns,
                                                      int* __restrict__ cellCount, int* __restrict__ cellOf) {
+  VL_PDL_WAIT();
+
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= nc + ns) return;
   const int which = g >= nc;
@@ -267,6 +275,8 @@ __global__ void __launch_bounds__(256) lo_grid_count(const float4* __restrict__ 
 __global__ void __launch_bounds__(256) lo_grid_fill(const float4* __restrict__ corner, int nc, const float4* __restrict__ surf, int ns,
                                                     const int* __restrict__ cellOf, const int* __restrict__ cellStart,
                                                     int* __restrict__ cellFill, float4* __restrict__ sorted) {
+  VL_PDL_WAIT();
+
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= nc + ns) return;
   const int which = g >= nc;
@@ -430,6 +440,8 @@ __global__ void __launch_bounds__(256) lo_assoc_grid(const float4* __restrict__ 
                                                      const float4* __restrict__ sorted, const int* __restrict__ cellStart,
                                                      const double* __restrict__ pose, int* __restrict__ outIdx,
                                                      double* __restrict__ factors, int* __restrict__ valid, int slotBase) {
+  VL_PDL_WAIT();
+
   const int lane = threadIdx.x & 31;
   const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (qi >= nq) return;
@@ -442,6 +454,8 @@ __global__ void __launch_bounds__(256) lo_assoc_grid_both(const float4* __restri
                                                           const float4* __restrict__ sorted, const int* __restrict__ cellStart,
                                                           const double* __restrict__ pose, int* __restrict__ cornerIdx, int* __restrict__ surfIdx,
                                                           double* __restrict__ factors, int* __restrict__ valid) {
+  VL_PDL_WAIT();
+
   const int lane = threadIdx.x & 31;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nS = srs->nSharp, nF = srs->nFlat;  // device-side counts: the host may not know them yet
@@ -450,7 +464,9 @@ __global__ void __launch_bounds__(256) lo_assoc_grid_both(const float4* __restri
   else if (w < nS + nF) lo_assoc_grid_dev<true>(w - nS, lane, flat, surfLast, sorted, cellStart, pose, surfIdx, factors, valid, nS);
 }
 
-__global__ void lo_accumulate(LoScalars* s) {  // LO.cpp:524-525
+__global__ void lo_accumulate(LoScalars* s) {
+  VL_PDL_WAIT();
+  // LO.cpp:524-525
   if (threadIdx.x != 0) return;
   double r[3];
   vl_qrot(s->q_w, s->para_t[0], s->para_t[1], s->para_t[2], r);
@@ -460,7 +476,9 @@ __global__ void lo_accumulate(LoScalars* s) {  // LO.cpp:524-525
   for (int k = 0; k < 4; ++k) s->q_w[k] = qn[k];
 }
 
-__global__ void lo_set_prior(LoScalars* s, const double* __restrict__ prior) {  // LO.cpp:237-250
+__global__ void lo_set_prior(LoScalars* s, const double* __restrict__ prior) {
+  VL_PDL_WAIT();
+  // LO.cpp:237-250
   if (threadIdx.x < 4) s->para_q[threadIdx.x] = prior[threadIdx.x];
   else if (threadIdx.x < 7) s->para_t[threadIdx.x - 4] = prior[threadIdx.x];
 }

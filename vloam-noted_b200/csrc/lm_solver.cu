@@ -234,6 +234,8 @@ __device__ void lm_logic(LmSolveState* st, const double* e) {
 __global__ void __launch_bounds__(LM_BLOCK) lm_eval(const double* __restrict__ factors, const int* __restrict__ valid, int nslots,
                                                     LmSolveState* st, const double* __restrict__ xEval, EvalOut* __restrict__ partials,
                                                     EvalOut* __restrict__ evalOut, unsigned int* __restrict__ counter, int mode) {
+  VL_PDL_WAIT();
+
   if (mode == 0 && st->done) return;
   double x[7];
   const double* xs = mode == 1 ? xEval : (st->iter == 0 ? st->x : st->xc);
@@ -314,6 +316,8 @@ __global__ void __launch_bounds__(LM_BLOCK) lm_eval(const double* __restrict__ f
 __global__ void __launch_bounds__(LMC_THREADS)
 lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ valid, int nslotsBound, const int* __restrict__ d_nslots,
                  double* __restrict__ x_inout, LmSolveState* __restrict__ st_out) {
+  VL_PDL_WAIT();
+
   const int nslots = d_nslots ? min(nslotsBound, *d_nslots) : nslotsBound;
   if (nslots <= 0) return;  // no residual blocks: Ceres leaves the parameters untouched (uniform over the cluster)
   cg::cluster_group cluster = cg::this_cluster();
@@ -415,6 +419,8 @@ lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ val
 }
 
 __global__ void lm_begin(LmSolveState* st, const double* __restrict__ x, int nfactorsHint) {
+  VL_PDL_WAIT();
+
   if (threadIdx.x != 0) return;
   for (int k = 0; k < 7; ++k) { st->x[k] = x[k]; st->xc[k] = x[k]; st->best[k] = x[k]; }
   st->iter = 0; st->done = 0; st->nfactors = nfactorsHint;
@@ -423,6 +429,8 @@ __global__ void lm_begin(LmSolveState* st, const double* __restrict__ x, int nfa
 
 // No residual blocks: Ceres removes the parameter blocks and returns without touching x.
 __global__ void lm_end(LmSolveState* st, double* __restrict__ x, const int* __restrict__ valid, int nslots) {
+  VL_PDL_WAIT();
+
   if (threadIdx.x != 0) return;
   for (int k = 0; k < 7; ++k) x[k] = st->best[k];
   st->final_cost = st->min_cost;
@@ -436,10 +444,12 @@ int vl_solve(vloam_b200_ctx* c, int nslots, const int* d_nslots, double* d_x_ino
     if (!attr) { VL_CUDA(cudaFuncSetAttribute(lm_solve_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)); attr = true; }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nct); cfg.blockDim = dim3(LMC_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = nct; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 2;
     const bool prof = c->prof_name[0] && vl_prof_match(c, "lm_solve_cluster") && c->prof_n < VL_PROF_MAX;
     if (prof) cudaEventRecord(c->prof_ev[c->prof_n][0], c->stream);
     const double* cf = c->factors.p; const int* cv = c->factorValid.p; LmSolveState* so = costs2 ? c->lms : nullptr;

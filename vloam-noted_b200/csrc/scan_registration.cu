@@ -78,6 +78,8 @@ __device__ __forceinline__ float sr_ori_first(float ori, float startOri) {  // S
 
 __global__ void __launch_bounds__(1024) sr_find_bounds(const float* __restrict__ in, int n, int stride, int vec4, float thres2,
                                                        SrScalars* __restrict__ s) {
+  VL_PDL_WAIT();
+
   __shared__ int found;
   int first = -1, last = -1;
   for (int base = 0; base < n; base += blockDim.x) {
@@ -120,6 +122,8 @@ __global__ void __launch_bounds__(1024) sr_find_bounds(const float* __restrict__
 __global__ void __launch_bounds__(SR_BLOCK) sr_classify(const float* __restrict__ in, int n, int stride, int vec4, float thres2,
                                                         int nscans, SrScalars* __restrict__ s, int* __restrict__ ring,
                                                         float* __restrict__ oriOut, int* __restrict__ blockHist, int numBlocks) {
+  VL_PDL_WAIT();
+
   __shared__ int hist[VL_MAX_RINGS];
   for (int t = threadIdx.x; t < VL_MAX_RINGS; t += blockDim.x) hist[t] = 0;
   __syncthreads();
@@ -149,6 +153,8 @@ __global__ void __launch_bounds__(SR_BLOCK) sr_classify(const float* __restrict_
 // to finish turns the ring totals into ring starts (SR.cpp:308-315).
 __global__ void __launch_bounds__(256) sr_ring_scan(int* __restrict__ blockHist, int numBlocks, int nscans, int* __restrict__ ringCount,
                                                     int* __restrict__ ringStart, SrScalars* __restrict__ s) {
+  VL_PDL_WAIT();
+
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + warp;
   if (r < nscans) {
@@ -190,6 +196,8 @@ __global__ void __launch_bounds__(SR_BLOCK) sr_scatter(const float* __restrict__
                                                        const SrScalars* __restrict__ s, const int* __restrict__ ring,
                                                        const float* __restrict__ oriIn, const int* __restrict__ blockOff, int numBlocks,
                                                        const int* __restrict__ ringStart, float4* __restrict__ cloud) {
+  VL_PDL_WAIT();
+
   __shared__ int warpCnt[SR_BLOCK / 32][VL_MAX_RINGS];
   for (int t = threadIdx.x; t < (SR_BLOCK / 32) * VL_MAX_RINGS; t += blockDim.x) (&warpCnt[0][0])[t] = 0;
   __syncthreads();
@@ -223,6 +231,8 @@ __global__ void __launch_bounds__(SR_BLOCK) sr_scatter(const float* __restrict__
 __global__ void __launch_bounds__(SR_BLOCK) sr_curvature(const float4* __restrict__ cloud, const SrScalars* __restrict__ s,
                                                          float* __restrict__ curv, int* __restrict__ label,
                                                          unsigned char* __restrict__ picked) {
+  VL_PDL_WAIT();
+
   __shared__ float4 tile[SR_BLOCK + 10];
   const int count = s->count;
   const int base = blockIdx.x * blockDim.x;
@@ -280,6 +290,8 @@ __global__ void __launch_bounds__(SR_PICK_THREADS) sr_pick(const float4* __restr
                                                     const int* __restrict__ ringCount, int* __restrict__ provSharp,
                                                     int* __restrict__ provLess, int* __restrict__ provFlat, int* __restrict__ cntSharp,
                                                     int* __restrict__ cntLess, int* __restrict__ cntFlat) {
+  VL_PDL_WAIT();
+
   extern __shared__ unsigned long long smem[];
   const int r = blockIdx.x;
   const int rs = ringStart[r], rc = ringCount[r];
@@ -401,6 +413,8 @@ __global__ void __launch_bounds__(SR_PICK_THREADS) sr_ring_voxel(const float4* _
                                                           const int* __restrict__ ringStart, const int* __restrict__ ringCount,
                                                           int* __restrict__ sel, unsigned long long* __restrict__ scratch,
                                                           float4* __restrict__ outProv, int* __restrict__ dsCount, float leaf) {
+  VL_PDL_WAIT();
+
   extern __shared__ unsigned long long vsm[];  // [SR_VOX_CAP] keys, then [SR_VOX_CAP] float4 points
   unsigned long long* skeys = vsm;
   float4* spts = reinterpret_cast<float4*>(vsm + SR_VOX_CAP);
@@ -508,6 +522,8 @@ __global__ void __launch_bounds__(1024) sr_offsets(int nscans, const int* __rest
                                                    const int* __restrict__ cntFlat, const int* __restrict__ dsCount,
                                                    int* __restrict__ offSharp, int* __restrict__ offLess, int* __restrict__ offFlat,
                                                    int* __restrict__ dsOff, SrScalars* __restrict__ s) {
+  VL_PDL_WAIT();
+
   __shared__ int buf[4][1024];
   const int t = threadIdx.x;
   const int nslots = nscans * VL_SECTORS;
@@ -538,6 +554,8 @@ __global__ void __launch_bounds__(SR_BLOCK) sr_gather(const float4* __restrict__
                                                       const int* __restrict__ dsCount, const int* __restrict__ dsOff,
                                                       const float4* __restrict__ lessFlatProv, float4* __restrict__ sharp,
                                                       float4* __restrict__ lessSharp, float4* __restrict__ flat, float4* __restrict__ lessFlat) {
+  VL_PDL_WAIT();
+
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int nslots = nscans * VL_SECTORS;
   if (t < nslots * 2) { const int sl = t / 2, k = t - sl * 2; if (k < cntSharp[sl]) sharp[offSharp[sl] + k] = cloud[provSharp[t]]; return; }

@@ -23,6 +23,8 @@ namespace cg = cooperative_groups;
 #define VG_BLOCK 256
 
 __global__ void __launch_bounds__(BT_THREADS) bt_tile_sort(unsigned long long* __restrict__ keys, int tile) {
+  VL_PDL_WAIT();
+
   __shared__ unsigned long long s[BT_TILE];
   const size_t base = (size_t)blockIdx.x * tile;
   for (int t = threadIdx.x; t < tile; t += BT_THREADS) s[t] = keys[base + t];
@@ -43,6 +45,8 @@ __global__ void __launch_bounds__(BT_THREADS) bt_tile_sort(unsigned long long* _
 }
 
 __global__ void __launch_bounds__(256) bt_global_step(unsigned long long* __restrict__ keys, int halfN, int j, int k) {
+  VL_PDL_WAIT();
+
   const int u = blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= halfN) return;
   const int i = ((u & ~(j - 1)) << 1) | (u & (j - 1));
@@ -53,6 +57,8 @@ __global__ void __launch_bounds__(256) bt_global_step(unsigned long long* __rest
 }
 
 __global__ void __launch_bounds__(BT_THREADS) bt_tile_merge(unsigned long long* __restrict__ keys, int tile, int k) {
+  VL_PDL_WAIT();
+
   __shared__ unsigned long long s[BT_TILE];
   const size_t base = (size_t)blockIdx.x * tile;
   for (int t = threadIdx.x; t < tile; t += BT_THREADS) s[t] = keys[base + t];
@@ -114,6 +120,8 @@ __device__ __forceinline__ void bt_smem_strides(unsigned long long* s, int tile,
 #define CS_THREADS 1024
 
 __global__ void __launch_bounds__(CS_THREADS) bt_cluster_sort(unsigned long long* __restrict__ keys, int tile) {
+  VL_PDL_WAIT();
+
   extern __shared__ unsigned long long cs[];  // [2][tile]
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank();
@@ -159,10 +167,12 @@ static int vl_sort_cluster(vloam_b200_ctx* c, unsigned long long* d_keys, int n_
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(nct); cfg.blockDim = dim3(CS_THREADS); cfg.dynamicSmemBytes = (size_t)2 * tile * 8; cfg.stream = c->stream;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = nct; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 2;
   const bool prof = c->prof_name[0] && vl_prof_match(c, "bt_cluster_sort") && c->prof_n < VL_PROF_MAX;
   if (prof) cudaEventRecord(c->prof_ev[c->prof_n][0], c->stream);
   VL_CUDA(cudaLaunchKernelEx(&cfg, bt_cluster_sort, d_keys, tile));
@@ -200,6 +210,8 @@ __device__ __forceinline__ unsigned vg_idx(const float4 p, const VgBox& b) {
 // getMinMax3D: per-block partial bounds -> partial[block*6 + {minx,miny,minz,maxx,maxy,maxz}]
 __global__ void __launch_bounds__(VG_BLOCK) vg_bbox(const float4* __restrict__ in, int nBound, const int* __restrict__ dN,
                                                     float* __restrict__ partial) {
+  VL_PDL_WAIT();
+
   const int n = dN ? min(*dN, nBound) : nBound;
   float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -226,6 +238,8 @@ __global__ void __launch_bounds__(VG_BLOCK) vg_bbox(const float4* __restrict__ i
 
 __global__ void vg_box(const float* __restrict__ partial, int nPartial, int nBound, const int* __restrict__ dN, float leaf,
                        VgBox* __restrict__ box, int* __restrict__ dCount) {
+  VL_PDL_WAIT();
+
   if (threadIdx.x != 0) return;
   const int n = dN ? min(*dN, nBound) : nBound;
   float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
@@ -252,6 +266,8 @@ __global__ void vg_box(const float* __restrict__ partial, int nPartial, int nBou
 
 __global__ void __launch_bounds__(VG_BLOCK) vg_keys(const float4* __restrict__ in, const VgBox* __restrict__ box,
                                                     unsigned long long* __restrict__ keys, int P) {
+  VL_PDL_WAIT();
+
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
   const VgBox b = *box;
@@ -261,6 +277,8 @@ __global__ void __launch_bounds__(VG_BLOCK) vg_keys(const float4* __restrict__ i
 // Tile of 1024 sorted keys per block: count run heads.
 __global__ void __launch_bounds__(VG_BLOCK) vg_head_count(const unsigned long long* __restrict__ keys, const VgBox* __restrict__ box,
                                                           int* __restrict__ blockCnt) {
+  VL_PDL_WAIT();
+
   const int n = box->guard ? 0 : box->n;
   int cnt = 0;
   const int base = blockIdx.x * 1024;
@@ -277,6 +295,8 @@ __global__ void __launch_bounds__(VG_BLOCK) vg_head_count(const unsigned long lo
 
 __global__ void __launch_bounds__(1024) vg_block_scan(int* __restrict__ blockCnt, int nBlocks, const VgBox* __restrict__ box,
                                                       int* __restrict__ dCount) {
+  VL_PDL_WAIT();
+
   __shared__ int buf[1024];
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
@@ -303,6 +323,8 @@ __global__ void __launch_bounds__(1024) vg_block_scan(int* __restrict__ blockCnt
 __global__ void __launch_bounds__(VG_BLOCK) vg_centroid(const float4* __restrict__ in, const unsigned long long* __restrict__ keys,
                                                         const VgBox* __restrict__ box, const int* __restrict__ blockOff,
                                                         float4* __restrict__ out) {
+  VL_PDL_WAIT();
+
   const VgBox b = *box;
   if (b.guard) {  // leaf too small for the extent: output = input
     for (int i = blockIdx.x * 1024 + threadIdx.x; i < min(b.n, (int)(blockIdx.x + 1) * 1024); i += VG_BLOCK) out[i] = in[i];
