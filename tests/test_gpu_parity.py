@@ -125,6 +125,36 @@ def test_normal_equations_and_solver_match_oracle(pkg, op):
     g.close()
 
 
+@pytest.mark.gpu
+def test_solver_trust_region_paths_and_sizes(pkg, op):
+    """Far starting points (rejected steps, shrinking radius), Huber-dominated problems and factor counts
+    that select every register-resident variant of lm_solve_cluster (1 / 2 / 4 slots per thread, and the
+    memory-streaming fallback above 16384 slots): same iterate and the same number of iterations as the
+    restated Ceres trust-region loop."""
+    from scipy.spatial.transform import Rotation as R
+    rng = np.random.RandomState(5)
+    q = R.from_euler("xyz", [0.05, -0.02, 0.1]).as_quat()
+    t = np.array([1.0, 0.3, -0.2])
+    g = pkg.Context()
+    starts = [
+        np.concatenate([R.from_euler("xyz", [0.6, -0.4, 0.9]).as_quat(), [6.0, -4.0, 3.0]]),   # far: steps get rejected
+        np.concatenate([R.from_euler("xyz", [0.0, 0.0, 0.0]).as_quat(), [0.0, 0.0, 0.0]]),
+        np.concatenate([q, t]),                                                                  # already at the optimum
+    ]
+    iters = set()
+    for n_each, noise in ((30, 0.0), (1400, 0.05), (2800, 0.3), (5500, 0.05), (6000, 0.02)):
+        f = make_factors(rng, q, t, n_each, n_each, n_each, noise=noise)
+        for x in starts:
+            xo, lo = op.ceres_solve(f, x)
+            xg, lg = g.solve(f, x)
+            assert int(lo[0]) == int(lg[0]), ("iterations", n_each, lo, lg)
+            assert np.abs(xo - xg).max() < 1e-8, (n_each, xo, xg)
+            assert abs(lo[2] - lg[2]) <= 1e-11 * max(1.0, lo[2]) and abs(lo[3] - lg[3]) <= 1e-9 * max(1.0, lo[3])
+            iters.add(int(lg[0]))
+    assert len(iters) > 1  # early termination and full-length runs were both exercised
+    g.close()
+
+
 def teacher_force(o, g):
     g.set_last(o.get("lo.cornerLast"), o.get("lo.surfLast"))
     g.set("lo.pose", o.get("lo.pose"))

@@ -8,6 +8,7 @@ static bool g_capture_default = false;
 // stage files ask through this hook whether to keep per-pass association snapshots
 bool vl_debug_capture(const vloam_b200_ctx* c) { return c->h_vScalars && c->h_vScalars[0] != 0; }
 int vl_lm_rescan_sorted(vloam_b200_ctx* c);
+int vl_solver_trace(vloam_b200_ctx* c, long long* out16);
 
 extern "C" {
 
@@ -329,6 +330,11 @@ long vloam_b200_debug_get(vloam_b200_ctx* c, const char* name, void* out, long c
       if (kind == "cok") return put_dev(c, c->dbgKnnOk[k][0].p, (size_t)Qc * 4, out, cap);
       if (kind == "sok") return put_dev(c, c->dbgKnnOk[k][1].p, (size_t)Qs * 4, out, cap);
     }
+  }
+  if (n == "solver.trace") {  // clock64 stamps of the last lm_solve_cluster launch (first call arms the trace)
+    long long v[16];
+    if (vl_solver_trace(c, v) != VLOAM_OK) return VLOAM_E_CUDA;
+    return put_host(v, sizeof v, out, cap);
   }
   if (n == "lo.costs") return put_host(c->dbgLoCost, sizeof c->dbgLoCost, out, cap);
   if (n == "lm.costs") return put_host(c->dbgLmCost, sizeof c->dbgLmCost, out, cap);

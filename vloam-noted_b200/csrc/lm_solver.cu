@@ -34,12 +34,12 @@ __device__ __forceinline__ void lm_factor(const double* __restrict__ f, const do
     const double u[3] = {lp[0] - a[0], lp[1] - a[1], lp[2] - a[2]}, v[3] = {lp[0] - b[0], lp[1] - b[1], lp[2] - b[2]};
     const double nu[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
     const double de[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};
-    const double n = sqrt(de[0] * de[0] + de[1] * de[1] + de[2] * de[2]);
+    const double inv = 1.0 / sqrt(de[0] * de[0] + de[1] * de[1] + de[2] * de[2]);
     o.nr = 3;
-    o.r[0] = nu[0] / n; o.r[1] = nu[1] / n; o.r[2] = nu[2] / n;
-    // d r / d lp = [w]x with w = (b - a) / n;  d lp / d delta = -2 [rp]x;  d lp / d t = I
+    o.r[0] = nu[0] * inv; o.r[1] = nu[1] * inv; o.r[2] = nu[2] * inv;
+    // d r / d lp = [w]x with w = (b - a) / |a - b|;  d lp / d delta = -2 [rp]x;  d lp / d t = I
     // => J_rot = -2 [w]x [rp]x = -2 (rp w^T - (w . rp) I),  J_t = [w]x
-    const double w[3] = {-de[0] / n, -de[1] / n, -de[2] / n};
+    const double w[3] = {-de[0] * inv, -de[1] * inv, -de[2] * inv};
     const double wr = w[0] * rp[0] + w[1] * rp[1] + w[2] * rp[2];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -82,27 +82,27 @@ __device__ void lm_plus(const double x[7], const double d[6], double o[7]) {
 
 __device__ __forceinline__ int tri(int i, int j) { return i <= j ? i * 6 - i * (i - 1) / 2 + (j - i) : j * 6 - j * (j - 1) / 2 + (i - j); }
 
-// Solve A y = b for symmetric positive definite 6x6 A (in-place Cholesky, fully unrolled so
-// every entry lives in a register); returns false on breakdown.
-__device__ __forceinline__ bool lm_chol6(double A[6][6], const double b[6], double y[6]) {
+// Solve A y = b for symmetric positive definite 6x6 A by a right-looking, fully unrolled L D L^T
+// (unit lower L): no square roots, and the six reciprocals are the only long-latency operations on
+// the dependent chain (f64 sqrt ~ 90 and div ~ 130 cycles on B200, measured).  Returns false on breakdown.
+__device__ __forceinline__ bool lm_ldl6(double A[6][6], const double b[6], double y[6]) {
   double inv[6];
   bool ok = true;
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
-    double s = A[j][j];
+    const double d = A[j][j];
+    ok = ok && (d > 0.0);
+    inv[j] = __drcp_rn(d);
+    double l[6];
 #pragma unroll
-    for (int k = 0; k < j; ++k) s -= A[j][k] * A[j][k];
-    ok = ok && (s > 0.0);
-    const double d = sqrt(s);
-    A[j][j] = d;
-    inv[j] = 1.0 / d;
+    for (int i = j + 1; i < 6; ++i) l[i] = A[i][j] * inv[j];
 #pragma unroll
     for (int i = j + 1; i < 6; ++i) {
-      double t = A[i][j];
 #pragma unroll
-      for (int k = 0; k < j; ++k) t -= A[i][k] * A[j][k];
-      A[i][j] = t * inv[j];
+      for (int k = j + 1; k <= i; ++k) A[i][k] -= l[i] * A[k][j];  // A[k][j] still holds L[k][j] * d
     }
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) A[i][j] = l[i];
   }
   double z[6];
 #pragma unroll
@@ -110,14 +110,14 @@ __device__ __forceinline__ bool lm_chol6(double A[6][6], const double b[6], doub
     double t = b[i];
 #pragma unroll
     for (int k = 0; k < i; ++k) t -= A[i][k] * z[k];
-    z[i] = t * inv[i];
+    z[i] = t;
   }
 #pragma unroll
   for (int i = 5; i >= 0; --i) {
-    double t = z[i];
+    double t = z[i] * inv[i];
 #pragma unroll
     for (int k = i + 1; k < 6; ++k) t -= A[k][i] * y[k];
-    y[i] = t * inv[i];
+    y[i] = t;
   }
 #pragma unroll
   for (int i = 0; i < 6; ++i) ok = ok && isfinite(y[i]);
@@ -130,117 +130,179 @@ __device__ double lm_gmax(const double x[7], const double g[6]) {
   const double gt = fmax(fabs(g[3]), fmax(fabs(g[4]), fabs(g[5])));
   if (gt > 1e-6) return gt;
   double ng[6], xp[7];
+#pragma unroll
   for (int k = 0; k < 6; ++k) ng[k] = -g[k];
   lm_plus(x, ng, xp);
   double m = 0;
+#pragma unroll
   for (int k = 0; k < 7; ++k) m = fmax(m, fabs(x[k] - xp[k]));
   return m;
 }
 
-// TrustRegionMinimizer bookkeeping after an evaluation `e` (at st->x when iter == 0, at st->xc otherwise).
-__device__ void lm_logic(LmSolveState* st, const double* e) {
+#define LG_TRACE(slot) do { if (tr && lane == 0) tr[slot] = clock64(); } while (0)
+// ---- TrustRegionMinimizer bookkeeping, warp-cooperative -------------------------------------------------
+// Runs on warp 0 of every CTA after each evaluation.  f64 sqrt / div are ~90 / ~130-cycle dependent
+// sequences on B200 and a lone thread issues a dependent f64 op only every 8 cycles, so a one-thread
+// version of this costs ~3 us per evaluation -- as much as the evaluation itself.  Here the 21 + 6
+// entries of the normal equations stay distributed over the lanes that summed them (lane t < 21 owns
+// entry t = tri(i, j), lane 21 + k owns g[k], lane 27 the cost): Jacobi scales, the scaled system, the
+// LM diagonal and the model cost change are computed one entry per lane; only the 6x6 L D L^T itself
+// (a strictly dependent chain) is replicated on every lane.  Scalars are replicated: every lane takes
+// the same branches, and every CTA of the cluster computes the same bits.
+struct LmWarp {
+  double x[7], xc[7];
+  double sc[6];                      // Jacobi scaling, fixed at iteration 0
+  double cost, min_cost, initial_cost, model_cost_change, radius, decrease_factor, x_norm, gmax;
+  int reuse_diagonal, done, iter, last_successful;
+  double H, Hs, diag;                // this lane's entry: accepted-point system (unscaled, scaled), LM diagonal
+  int li, lj;                        // this lane's (row, column); vector lanes: (k, -1)
+};
+
+__device__ __forceinline__ double lm_sel6(const double (&v)[6], int k) {
+  double r = v[0];
+#pragma unroll
+  for (int q = 1; q < 6; ++q) r = (k == q) ? v[q] : r;
+  return r;
+}
+
+__device__ __forceinline__ double lm_gmax_warp(const LmWarp& S) {
+  double g[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) g[k] = __shfl_sync(0xffffffffu, S.H, 21 + k);
+  return lm_gmax(S.x, g);
+}
+
+// e: this lane's entry of the evaluation (at S.x when iter == 0, at S.xc otherwise).  best[7]: shared memory.
+__device__ __forceinline__ void lm_logic_warp(LmWarp& S, const double e, const int lane, double* __restrict__ best, long long* tr) {
   const double ftol = 1e-6, gtol = 1e-10, ptol = 1e-8, min_rel = 1e-3;
   const double min_radius = 1e-32, max_radius = 1e16, min_diag = 1e-6, max_diag = 1e32;
   const int kMaxIter = 4;
-  const double cost = e[27];
-  if (st->iter == 0) {  // IterationZero
-    for (int k = 0; k < 21; ++k) st->H[k] = e[k];
-    for (int k = 0; k < 6; ++k) st->g[k] = e[21 + k];
-    st->cost = cost; st->min_cost = cost; st->initial_cost = cost;
-    for (int k = 0; k < 6; ++k) st->scale[k] = 1.0 / (1.0 + sqrt(st->H[tri(k, k)]));
-    double xn = 0; for (int k = 0; k < 7; ++k) { xn += st->x[k] * st->x[k]; st->best[k] = st->x[k]; }
-    st->x_norm = sqrt(xn);
-    st->gmax = lm_gmax(st->x, st->g);
-    st->radius = 1e4; st->decrease_factor = 2.0; st->reuse_diagonal = 0; st->last_successful = 0;
+  const double cost = __shfl_sync(0xffffffffu, e, 27);
+  const bool isDiag = S.li == S.lj;
+  if (S.iter == 0) {  // IterationZero
+    S.H = e;
+    S.cost = cost; S.min_cost = cost; S.initial_cost = cost;
+    const double s = 1.0 / (1.0 + sqrt(fabs(e)));  // meaningful on the six diagonal lanes (0, 6, 11, 15, 18, 20)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) S.sc[k] = __shfl_sync(0xffffffffu, s, tri(k, k));
+    double xn = 0;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) xn += S.x[k] * S.x[k];
+    S.x_norm = sqrt(xn);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) best[k] = S.x[k];
+    }
+    S.gmax = lm_gmax_warp(S);
+    S.radius = 1e4; S.decrease_factor = 2.0; S.reuse_diagonal = 0; S.last_successful = 0;
+    S.Hs = (S.H * lm_sel6(S.sc, S.li)) * (S.lj >= 0 ? lm_sel6(S.sc, S.lj) : 1.0);
   } else {
-    st->cand_cost = cost;
-    double sn = 0; for (int k = 0; k < 7; ++k) sn += (st->x[k] - st->xc[k]) * (st->x[k] - st->xc[k]);
+    double sn = 0, xn = 0;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { sn += (S.x[k] - S.xc[k]) * (S.x[k] - S.xc[k]); xn += S.xc[k] * S.xc[k]; }
+    // the four long operations of this branch are independent of each other up to the radius update
     sn = sqrt(sn);
-    if (sn <= ptol * (st->x_norm + ptol)) { st->done = 1; return; }     // ParameterToleranceReached
-    const double cost_change = st->cost - cost;
-    if (fabs(cost_change) <= ftol * st->cost) { st->done = 1; return; }  // FunctionToleranceReached
-    const double rho = cost_change / st->model_cost_change;
+    const double xcn = sqrt(xn);
+    const double cost_change = S.cost - cost;
+    const double rho = cost_change / S.model_cost_change;
+    if (sn <= ptol * (S.x_norm + ptol)) { S.done = 1; return; }       // ParameterToleranceReached
+    if (fabs(cost_change) <= ftol * S.cost) { S.done = 1; return; }   // FunctionToleranceReached
     if (rho > min_rel) {  // HandleSuccessfulStep
-      double xn = 0;
-      for (int k = 0; k < 7; ++k) { st->x[k] = st->xc[k]; xn += st->x[k] * st->x[k]; }
-      st->x_norm = sqrt(xn);
-      for (int k = 0; k < 21; ++k) st->H[k] = e[k];
-      for (int k = 0; k < 6; ++k) st->g[k] = e[21 + k];
-      st->cost = cost;
-      st->gmax = lm_gmax(st->x, st->g);
-      const double tr = 2.0 * rho - 1.0;
-      st->radius = fmin(max_radius, st->radius / fmax(1.0 / 3.0, 1.0 - tr * tr * tr));
-      st->decrease_factor = 2.0; st->reuse_diagonal = 0; st->last_successful = 1;
-      if (st->cost < st->min_cost) { st->min_cost = st->cost; for (int k = 0; k < 7; ++k) st->best[k] = st->x[k]; }
+#pragma unroll
+      for (int k = 0; k < 7; ++k) S.x[k] = S.xc[k];
+      S.x_norm = xcn;
+      S.H = e;
+      S.Hs = (S.H * lm_sel6(S.sc, S.li)) * (S.lj >= 0 ? lm_sel6(S.sc, S.lj) : 1.0);
+      S.cost = cost;
+      S.gmax = lm_gmax_warp(S);
+      const double t3 = 2.0 * rho - 1.0;
+      S.radius = fmin(max_radius, S.radius / fmax(1.0 / 3.0, 1.0 - t3 * t3 * t3));
+      S.decrease_factor = 2.0; S.reuse_diagonal = 0; S.last_successful = 1;
+      if (S.cost < S.min_cost) {
+        S.min_cost = S.cost;
+        if (lane == 0) {
+#pragma unroll
+          for (int k = 0; k < 7; ++k) best[k] = S.x[k];
+        }
+      }
     } else {  // HandleUnsuccessfulStep
-      st->radius /= st->decrease_factor; st->decrease_factor *= 2.0; st->last_successful = 0;
+      S.radius /= S.decrease_factor; S.decrease_factor *= 2.0; S.last_successful = 0;
     }
   }
+  LG_TRACE(9);
   // next trust-region step(s); an invalid step consumes an iteration without an evaluation
   while (true) {
-    if (st->last_successful && st->gmax <= gtol) { st->done = 1; return; }
-    if (st->radius < min_radius) { st->done = 1; return; }
-    if (st->iter >= kMaxIter) { st->done = 1; return; }
-    st->iter++;
-    st->last_successful = 0;
-    double Hs[6][6], gs[6], sc[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) sc[i] = st->scale[i];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      gs[i] = st->g[i] * sc[i];
-#pragma unroll
-      for (int j = 0; j < 6; ++j) Hs[i][j] = st->H[i <= j ? i * 6 - i * (i - 1) / 2 + (j - i) : j * 6 - j * (j - 1) / 2 + (i - j)] * sc[i] * sc[j];
-    }
-    if (!st->reuse_diagonal) {
-#pragma unroll
-      for (int k = 0; k < 6; ++k) st->diag[k] = fmin(fmax(Hs[k][k], min_diag), max_diag);
-    }
-    double A[6][6];
-    const double invr = 1.0 / st->radius;
+    if (S.last_successful && S.gmax <= gtol) { S.done = 1; return; }
+    if (S.radius < min_radius) { S.done = 1; return; }
+    if (S.iter >= kMaxIter) { S.done = 1; return; }
+    S.iter++;
+    S.last_successful = 0;
+    if (!S.reuse_diagonal) S.diag = fmin(fmax(S.Hs, min_diag), max_diag);  // used on the diagonal lanes only
+    const double invr = 1.0 / S.radius;
+    const double a = isDiag ? S.Hs + S.diag * invr : S.Hs;  // D^2 = diag / radius
+    double A[6][6], gs[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
 #pragma unroll
-      for (int j = 0; j < 6; ++j) A[i][j] = Hs[i][j];
-      A[i][i] += st->diag[i] * invr;  // D^2 = diag / radius
+      for (int j = i; j < 6; ++j) { const double v = __shfl_sync(0xffffffffu, a, tri(i, j)); A[i][j] = v; A[j][i] = v; }
+      gs[i] = __shfl_sync(0xffffffffu, a, 21 + i);
     }
+    LG_TRACE(10);
     double y[6];
-    const bool ok = lm_chol6(A, gs, y);
-    st->reuse_diagonal = 1;
-    double mcc = 0;
-    if (ok) {  // model_cost_change = -s'gs - s'Hs s / 2 with s = -y
-      double sHs = 0, sg = 0;
+    const bool ok = lm_ldl6(A, gs, y);
+    LG_TRACE(11);
+    S.reuse_diagonal = 1;
+    // model_cost_change = -s'gs - s'Hs s / 2 with s = -y  =  y'gs - y'Hs y / 2, one term per lane
+    double term = 0.0;
+    if (lane < 21) term = ((isDiag ? -0.5 : -1.0) * S.Hs) * (lm_sel6(y, S.li) * lm_sel6(y, S.lj));
+    else if (lane < 27) term = lm_sel6(y, S.li) * S.Hs;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        sg += -y[i] * gs[i];
-        double row = 0;
-#pragma unroll
-        for (int j = 0; j < 6; ++j) row += Hs[i][j] * y[j];
-        sHs += y[i] * row;
-      }
-      mcc = -sg - 0.5 * sHs;
-    }
-    if (!ok || !(mcc > 0.0)) { st->radius /= st->decrease_factor; st->decrease_factor *= 2.0; continue; }
-    st->model_cost_change = mcc;
+    for (int d = 16; d >= 1; d >>= 1) term += __shfl_xor_sync(0xffffffffu, term, d);  // commutative pairs: the same bits on every lane
+    const double mcc = ok ? term : 0.0;
+    if (!ok || !(mcc > 0.0)) { S.radius /= S.decrease_factor; S.decrease_factor *= 2.0; continue; }
+    S.model_cost_change = mcc;
     double delta[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) delta[k] = -y[k] * sc[k];
-    lm_plus(st->x, delta, st->xc);
+    for (int k = 0; k < 6; ++k) delta[k] = -y[k] * S.sc[k];
+    LG_TRACE(12);
+    lm_plus(S.x, delta, S.xc);
+    LG_TRACE(13);
     return;
   }
 }
 
-// mode 0: solver step on st; mode 1: evaluate at xEval only, sums to evalOut.
+// Huber-corrected contribution of one factor to the 21 + 6 + 1 sums
+__device__ __forceinline__ void lm_accumulate(const FactorRow& fr, double* __restrict__ acc) {
+  double s = fr.r[0] * fr.r[0];
+  if (fr.nr == 3) s = (s + fr.r[1] * fr.r[1]) + fr.r[2] * fr.r[2];
+  double rho0, rho1;  // ceres::HuberLoss(0.1)
+  if (s > 0.01) { const double r = sqrt(s); rho0 = 2.0 * 0.1 * r - 0.01; rho1 = fmax(DBL_MIN, 0.1 / r); }
+  else { rho0 = s; rho1 = 1.0; }
+  acc[27] += 0.5 * rho0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (k >= fr.nr) break;
+    int t = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      const double wa = rho1 * fr.J[k][a];
+#pragma unroll
+      for (int b = a; b < 6; ++b) { acc[t] = fma(wa, fr.J[k][b], acc[t]); ++t; }  // explicit DFMA: the library is built with -fmad=false
+      acc[21 + a] = fma(wa, fr.r[k], acc[21 + a]);
+    }
+  }
+}
+
+// One robustified evaluation at xEval (vloam_b200_evaluate: the parity tests compare the normal
+// equations themselves with the oracle's).  The last CTA to finish adds the per-CTA partials in order.
 __global__ void __launch_bounds__(LM_BLOCK) lm_eval(const double* __restrict__ factors, const int* __restrict__ valid, int nslots,
-                                                    LmSolveState* st, const double* __restrict__ xEval, EvalOut* __restrict__ partials,
-                                                    EvalOut* __restrict__ evalOut, unsigned int* __restrict__ counter, int mode) {
+                                                    const double* __restrict__ xEval, EvalOut* __restrict__ partials,
+                                                    EvalOut* __restrict__ evalOut, unsigned int* __restrict__ counter) {
   VL_PDL_WAIT();
 
-  if (mode == 0 && st->done) return;
   double x[7];
-  const double* xs = mode == 1 ? xEval : (st->iter == 0 ? st->x : st->xc);
 #pragma unroll
-  for (int k = 0; k < 7; ++k) x[k] = xs[k];
+  for (int k = 0; k < 7; ++k) x[k] = xEval[k];
   double acc[28];
 #pragma unroll
   for (int k = 0; k < 28; ++k) acc[k] = 0.0;
@@ -248,24 +310,7 @@ __global__ void __launch_bounds__(LM_BLOCK) lm_eval(const double* __restrict__ f
     if (!valid[i]) continue;
     FactorRow fr;
     lm_factor(factors + (size_t)i * 10, x, fr);
-    double s = fr.r[0] * fr.r[0];
-    if (fr.nr == 3) s = (s + fr.r[1] * fr.r[1]) + fr.r[2] * fr.r[2];
-    double rho0, rho1;  // ceres::HuberLoss(0.1)
-    if (s > 0.01) { const double r = sqrt(s); rho0 = 2.0 * 0.1 * r - 0.01; rho1 = fmax(DBL_MIN, 0.1 / r); }
-    else { rho0 = s; rho1 = 1.0; }
-    acc[27] += 0.5 * rho0;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      if (k >= fr.nr) break;
-      int t = 0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) {
-        const double wa = rho1 * fr.J[k][a];
-#pragma unroll
-        for (int b = a; b < 6; ++b) acc[t++] += wa * fr.J[k][b];
-        acc[21 + a] += wa * fr.r[k];
-      }
-    }
+    lm_accumulate(fr, acc);
   }
   __shared__ double red[LM_BLOCK / 32][28];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -288,174 +333,265 @@ __global__ void __launch_bounds__(LM_BLOCK) lm_eval(const double* __restrict__ f
   __syncthreads();
   if (!isLast) return;
   __threadfence();
-  __shared__ double total[28];
   if (threadIdx.x < 28) {
     double v = 0;
     for (unsigned b = 0; b < gridDim.x; ++b) v += ((volatile EvalOut*)partials)[b].v[threadIdx.x];
-    total[threadIdx.x] = v;
+    evalOut->v[threadIdx.x] = v;
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    *counter = 0;
-    if (mode == 1) { for (int k = 0; k < 28; ++k) evalOut->v[k] = total[k]; }
-    else lm_logic(st, total);
-  }
+  if (threadIdx.x == 0) *counter = 0;
 }
 
 
 // ---- the whole ceres::Solve in ONE launch: a thread-block cluster keeps the iterate on chip ----
-// 8 CTAs (one cluster) evaluate the factors; per-CTA partial sums stay in shared memory and CTA 0
-// adds them through distributed shared memory in rank order (deterministic), runs the trust-region
-// bookkeeping and publishes the next evaluation point in its own shared memory, which the other
-// CTAs read back through DSMEM.  Two cluster barriers per evaluation replace the kernel boundary
-// (and the global-memory round trip) of the lm_eval chain: 1 launch instead of 7 per solve.
-#define LMC_CTAS 8
-#define LMC_THREADS 256
+// One cluster of 8 (odometry) or 16 (mapping) CTAs.  Every thread loads its <= FPT factors ONCE into
+// registers together with their pose-independent parts (|a-b|, (b-a)/|a-b|): cluster.sync invalidates
+// L1D, so re-reading the factors at each of the 5 evaluations costs an L2 round trip every time.
+// Per evaluation: residuals + Jacobians from registers, a transposed butterfly reduction (31 double
+// shuffles per warp instead of 28 x 5), per-CTA partials in shared memory, ONE cluster barrier, then
+// EVERY CTA pulls all partials through distributed shared memory, adds them in rank order and runs the
+// trust-region bookkeeping redundantly (same inputs, same instructions => the same candidate in every
+// CTA).  Nothing has to be published back, so the second cluster barrier and the remote read of the
+// next evaluation point of the previous design are gone; the partials are double-buffered by
+// evaluation parity, which the single barrier is enough to protect.
+#define LMC_CTAS 16  // one cluster of the non-portable maximum size: the f64 pipes of 16 SMs
 
-#define LMC_MAX_CTAS 16
-__global__ void __launch_bounds__(LMC_THREADS)
+struct LmFactorReg {  // one factor with its pose-independent parts hoisted
+  int type;           // -1: empty / invalid slot
+  double p[3];        // current point
+  double a[3];        // edge: a; plane: j; plane-norm: n
+  double b[3];        // edge: b; plane: ljm_norm; plane-norm: {d, -, -}
+  double inv;         // edge: 1 / |a - b|
+  double w[3];        // edge: (b - a) / |a - b|
+};
+
+__device__ __forceinline__ void lm_factor_load(const double* __restrict__ f, bool ok, LmFactorReg& o) {
+  o.type = -1;
+  if (!ok) return;
+  o.type = (int)f[0];
+  o.p[0] = f[1]; o.p[1] = f[2]; o.p[2] = f[3];
+  o.a[0] = f[4]; o.a[1] = f[5]; o.a[2] = f[6];
+  o.b[0] = f[7]; o.b[1] = f[8]; o.b[2] = f[9];
+  if (o.type == 0) {
+    const double de[3] = {o.a[0] - o.b[0], o.a[1] - o.b[1], o.a[2] - o.b[2]};
+    o.inv = 1.0 / sqrt(de[0] * de[0] + de[1] * de[1] + de[2] * de[2]);
+    o.w[0] = -de[0] * o.inv; o.w[1] = -de[1] * o.inv; o.w[2] = -de[2] * o.inv;
+  }
+}
+
+// same arithmetic, in the same order, as lm_factor
+__device__ __forceinline__ void lm_factor_eval(const LmFactorReg& f, const double* __restrict__ x, FactorRow& o) {
+  double rp[3];
+  vl_qrot(x, f.p[0], f.p[1], f.p[2], rp);
+  const double lp[3] = {rp[0] + x[4], rp[1] + x[5], rp[2] + x[6]};
+  if (f.type == 0) {
+    const double u[3] = {lp[0] - f.a[0], lp[1] - f.a[1], lp[2] - f.a[2]}, v[3] = {lp[0] - f.b[0], lp[1] - f.b[1], lp[2] - f.b[2]};
+    const double nu[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+    o.nr = 3;
+    o.r[0] = nu[0] * f.inv; o.r[1] = nu[1] * f.inv; o.r[2] = nu[2] * f.inv;
+    const double wr = f.w[0] * rp[0] + f.w[1] * rp[1] + f.w[2] * rp[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int cidx = 0; cidx < 3; ++cidx) o.J[i][cidx] = -2.0 * (i == cidx ? rp[i] * f.w[cidx] - wr : rp[i] * f.w[cidx]);
+    }
+    o.J[0][3] = 0.0;     o.J[0][4] = -f.w[2]; o.J[0][5] = f.w[1];
+    o.J[1][3] = f.w[2];  o.J[1][4] = 0.0;     o.J[1][5] = -f.w[0];
+    o.J[2][3] = -f.w[1]; o.J[2][4] = f.w[0];  o.J[2][5] = 0.0;
+  } else {
+    double n[3];
+    o.nr = 1;
+    if (f.type == 1) {
+      n[0] = f.b[0]; n[1] = f.b[1]; n[2] = f.b[2];
+      o.r[0] = (lp[0] - f.a[0]) * n[0] + (lp[1] - f.a[1]) * n[1] + (lp[2] - f.a[2]) * n[2];
+    } else {
+      n[0] = f.a[0]; n[1] = f.a[1]; n[2] = f.a[2];
+      o.r[0] = (n[0] * lp[0] + n[1] * lp[1] + n[2] * lp[2]) + f.b[0];
+    }
+    o.J[0][0] = -2.0 * (n[1] * rp[2] - n[2] * rp[1]);
+    o.J[0][1] = -2.0 * (n[2] * rp[0] - n[0] * rp[2]);
+    o.J[0][2] = -2.0 * (n[0] * rp[1] - n[1] * rp[0]);
+    o.J[0][3] = n[0]; o.J[0][4] = n[1]; o.J[0][5] = n[2];
+  }
+}
+
+// Sum v[0..32) over the warp; afterwards v[0] of lane L holds the total of entry L.  Each level halves
+// the entries a lane is responsible for: 16 + 8 + 4 + 2 + 1 = 31 double shuffles.
+__device__ __forceinline__ void lm_warp_transpose_reduce(double (&v)[32], int lane) {
+#pragma unroll
+  for (int h = 16; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int k = 0; k < h; ++k) {
+      const double lo = v[k], hi = v[k + h];
+      const double send = up ? lo : hi, keep = up ? hi : lo;
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+}
+
+#ifndef LM_TRACE_IT
+#define LM_TRACE_IT 1  // which evaluation the phase stamps describe (0 = the first, which also waits for the factor loads)
+#endif
+#define LM_TRACE(slot) do { if (trace && rank == 0 && threadIdx.x == 0) trace[slot] = clock64(); } while (0)
+
+// FPT: factor slots held in registers per thread (0 = read them from memory at every evaluation).
+// Slot i belongs to CTA i % 16 (thread (i / 16) % THREADS): the edge factors, which cost three times a
+// plane factor and sit at the front of the slot array, are spread evenly over the CTAs.
+template <int FPT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ valid, int nslotsBound, const int* __restrict__ d_nslots,
-                 double* __restrict__ x_inout, LmSolveState* __restrict__ st_out) {
+                 double* __restrict__ x_inout, LmSolveState* __restrict__ st_out, long long* __restrict__ trace) {
   VL_PDL_WAIT();
 
   const int nslots = d_nslots ? min(nslotsBound, *d_nslots) : nslotsBound;
   if (nslots <= 0) return;  // no residual blocks: Ceres leaves the parameters untouched (uniform over the cluster)
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank();
-  const int nct = (int)cluster.num_blocks();
-  __shared__ double part[28];
-  __shared__ double xs[8];
-  __shared__ int sdone;
-  __shared__ double total[28];
-  __shared__ LmSolveState st;
-  __shared__ double red[LMC_THREADS / 32][28];
-  __shared__ double gath[LMC_MAX_CTAS][28];
-  __shared__ double xloc[8];
+  __shared__ double part[2][28];
+  __shared__ double red[THREADS / 32][28];
+  __shared__ double gath[LMC_CTAS][28];
+  __shared__ double xnext[8];
+  __shared__ double best[7];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (rank == 0 && threadIdx.x == 0) {
-    for (int k = 0; k < 7; ++k) { st.x[k] = x_inout[k]; st.xc[k] = x_inout[k]; st.best[k] = x_inout[k]; xs[k] = x_inout[k]; }
-    st.iter = 0; st.done = 0; st.nfactors = nslots; st.initial_cost = 0; st.final_cost = 0; st.cost = 0; st.min_cost = 0;
-    sdone = 0;
+  LM_TRACE(0);
+  double x[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) x[k] = x_inout[k];
+  LmWarp S;  // live in warp 0 only
+#pragma unroll
+  for (int k = 0; k < 7; ++k) { S.x[k] = x[k]; S.xc[k] = x[k]; }
+  S.iter = 0; S.done = 0; S.initial_cost = 0; S.cost = 0; S.min_cost = 0; S.reuse_diagonal = 0; S.last_successful = 0;
+  S.model_cost_change = 0; S.radius = 1e4; S.decrease_factor = 2.0; S.x_norm = 0; S.gmax = 0; S.H = 0; S.Hs = 0; S.diag = 0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) S.sc[k] = 1.0;
+  S.li = 0; S.lj = -1;
+  if (lane < 21) { int t = lane, i = 0; while (t >= 6 - i) { t -= 6 - i; ++i; } S.li = i; S.lj = i + t; }
+  else if (lane < 27) S.li = lane - 21;
+  LmFactorReg fr_[FPT > 0 ? FPT : 1];
+  if (FPT > 0) {
+#pragma unroll
+    for (int j = 0; j < FPT; ++j) {
+      const int i = (j * THREADS + threadIdx.x) * LMC_CTAS + (int)rank;
+      const bool ok = i < nslots && valid[i] != 0;
+      lm_factor_load(factors + (size_t)(ok ? i : 0) * 10, ok, fr_[j]);
+    }
   }
-  cluster.sync();
-  const double* xsrc = cluster.map_shared_rank(xs, 0);
-  const int* dsrc = cluster.map_shared_rank(&sdone, 0);
+  LM_TRACE(14);
   for (int it = 0; it < 5; ++it) {
-    // one round of remote reads: 7 coordinates + the done flag, then a local broadcast
-    if (threadIdx.x < 7) xloc[threadIdx.x] = xsrc[threadIdx.x];
-    else if (threadIdx.x == 7) xloc[7] = (double)*dsrc;
-    __syncthreads();
-    if (xloc[7] != 0.0) break;  // uniform over the cluster: written before the last barrier
-    double x[7];
+    if (it == LM_TRACE_IT) LM_TRACE(1);
+    double acc[32];
 #pragma unroll
-    for (int k = 0; k < 7; ++k) x[k] = xloc[k];
-    double acc[28];
+    for (int k = 0; k < 32; ++k) acc[k] = 0.0;
+    if (FPT > 0) {
 #pragma unroll
-    for (int k = 0; k < 28; ++k) acc[k] = 0.0;
-    for (int i = rank * LMC_THREADS + threadIdx.x; i < nslots; i += nct * LMC_THREADS) {
-      if (!valid[i]) continue;
-      FactorRow fr;
-      lm_factor(factors + (size_t)i * 10, x, fr);
-      double s = fr.r[0] * fr.r[0];
-      if (fr.nr == 3) s = (s + fr.r[1] * fr.r[1]) + fr.r[2] * fr.r[2];
-      double rho0, rho1;  // ceres::HuberLoss(0.1)
-      if (s > 0.01) { const double r = sqrt(s); rho0 = 2.0 * 0.1 * r - 0.01; rho1 = fmax(DBL_MIN, 0.1 / r); }
-      else { rho0 = s; rho1 = 1.0; }
-      acc[27] += 0.5 * rho0;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        if (k >= fr.nr) break;
-        int t = 0;
-#pragma unroll
-        for (int a = 0; a < 6; ++a) {
-          const double wa = rho1 * fr.J[k][a];
-#pragma unroll
-          for (int b = a; b < 6; ++b) acc[t++] += wa * fr.J[k][b];
-          acc[21 + a] += wa * fr.r[k];
-        }
+      for (int j = 0; j < FPT; ++j) {
+        if (fr_[j].type < 0) continue;
+        FactorRow fr;
+        lm_factor_eval(fr_[j], x, fr);
+        lm_accumulate(fr, acc);
+      }
+    } else {
+      for (int i = threadIdx.x * LMC_CTAS + (int)rank; i < nslots; i += THREADS * LMC_CTAS) {
+        if (!valid[i]) continue;
+        FactorRow fr;
+        lm_factor(factors + (size_t)i * 10, x, fr);
+        lm_accumulate(fr, acc);
       }
     }
-#pragma unroll
-    for (int k = 0; k < 28; ++k) {
-      double v = acc[k];
-      for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
-      if (lane == 0) red[warp][k] = v;
-    }
+    if (it == LM_TRACE_IT) LM_TRACE(2);
+    lm_warp_transpose_reduce(acc, lane);
+    if (lane < 28) red[warp][lane] = acc[0];
     __syncthreads();
+    double* mine = part[it & 1];
     if (threadIdx.x < 28) {
       double v = 0;
-      for (int w = 0; w < LMC_THREADS / 32; ++w) v += red[w][threadIdx.x];
-      part[threadIdx.x] = v;
+#pragma unroll
+      for (int w = 0; w < THREADS / 32; ++w) v += red[w][threadIdx.x];
+      mine[threadIdx.x] = v;
     }
-    cluster.sync();  // every CTA's partial is visible cluster-wide
-    if (rank == 0) {
-      // pull all 8 x 28 partials in one round of remote reads (one DSMEM latency, not eight), then add
-      // them in rank order so the sum is deterministic
-      for (int t = threadIdx.x; t < 28 * nct; t += LMC_THREADS) {
-        const int r = t / 28, k = t - r * 28;
-        gath[r][k] = cluster.map_shared_rank(part, r)[k];
+    if (it == LM_TRACE_IT) LM_TRACE(3);
+    cluster.sync();  // every CTA's partial of this evaluation is visible cluster-wide
+    if (it == LM_TRACE_IT) LM_TRACE(4);
+    for (int t = threadIdx.x; t < 28 * LMC_CTAS; t += THREADS) {
+      const int r = t / 28, k = t - r * 28;
+      gath[r][k] = cluster.map_shared_rank(mine, r)[k];
+    }
+    __syncthreads();
+    if (it == LM_TRACE_IT) LM_TRACE(5);
+    if (warp == 0) {
+      double v = 0;
+      if (lane < 28) {
+#pragma unroll
+        for (int r = 0; r < LMC_CTAS; ++r) v += gath[r][lane];  // rank order: deterministic
       }
-      __syncthreads();
-      if (threadIdx.x < 28) {
-        double v = 0;
-        for (int r = 0; r < nct; ++r) v += gath[r][threadIdx.x];
-        total[threadIdx.x] = v;
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        lm_logic(&st, total);
-        for (int k = 0; k < 7; ++k) xs[k] = st.xc[k];
-        sdone = st.done;
+      lm_logic_warp(S, v, lane, best, (it == LM_TRACE_IT && rank == 0) ? trace : nullptr);
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) xnext[k] = S.xc[k];
+        xnext[7] = (double)S.done;
       }
     }
-    cluster.sync();  // the next evaluation point / done flag is published
+    __syncthreads();
+    if (it == LM_TRACE_IT) LM_TRACE(6);
+    if (xnext[7] != 0.0) break;  // identical in every CTA
+#pragma unroll
+    for (int k = 0; k < 7; ++k) x[k] = xnext[k];
   }
-  cluster.sync();  // nobody may exit while another CTA can still read its shared memory (the done flag lives in CTA 0)
-  if (rank == 0 && threadIdx.x == 0) {
-    for (int k = 0; k < 7; ++k) x_inout[k] = st.best[k];
-    st.final_cost = st.min_cost;
-    if (st_out) *st_out = st;
+  LM_TRACE(7);
+  cluster.sync();  // nobody may exit while another CTA can still read its partials
+  if (rank == 0 && warp == 0) {
+    __syncwarp();
+    if (lane < 7) x_inout[lane] = best[lane];
+    if (lane == 0 && st_out) {  // what the debug getters read (costs, iterations)
+      st_out->initial_cost = S.initial_cost; st_out->final_cost = S.min_cost; st_out->min_cost = S.min_cost; st_out->cost = S.cost;
+      st_out->iter = S.iter; st_out->done = S.done; st_out->nfactors = nslots; st_out->radius = S.radius;
+    }
   }
+  LM_TRACE(8);
 }
 
-__global__ void lm_begin(LmSolveState* st, const double* __restrict__ x, int nfactorsHint) {
-  VL_PDL_WAIT();
-
-  if (threadIdx.x != 0) return;
-  for (int k = 0; k < 7; ++k) { st->x[k] = x[k]; st->xc[k] = x[k]; st->best[k] = x[k]; }
-  st->iter = 0; st->done = 0; st->nfactors = nfactorsHint;
-  st->initial_cost = 0; st->final_cost = 0; st->cost = 0; st->min_cost = 0;
+static long long* g_solver_trace = nullptr;  // device buffer of 16 clock64 stamps, allocated on first request
+int vl_solver_trace(vloam_b200_ctx* c, long long* out16) {
+  if (!g_solver_trace) { VL_CUDA(cudaMalloc(&g_solver_trace, 16 * sizeof(long long))); VL_CUDA(cudaMemset(g_solver_trace, 0, 16 * sizeof(long long))); }
+  VL_CUDA(cudaStreamSynchronize(c->stream));
+  VL_CUDA(cudaMemcpy(out16, g_solver_trace, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return VLOAM_OK;
 }
 
-// No residual blocks: Ceres removes the parameter blocks and returns without touching x.
-__global__ void lm_end(LmSolveState* st, double* __restrict__ x, const int* __restrict__ valid, int nslots) {
-  VL_PDL_WAIT();
-
-  if (threadIdx.x != 0) return;
-  for (int k = 0; k < 7; ++k) x[k] = st->best[k];
-  st->final_cost = st->min_cost;
+template <int FPT, int THREADS>
+static cudaError_t lm_launch(cudaLaunchConfig_t& cfg, const double* cf, const int* cv, int nslots, const int* d_nslots, double* x,
+                             LmSolveState* so, long long* trace) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(lm_solve_cluster<FPT, THREADS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  cfg.blockDim = dim3(THREADS);
+  return cudaLaunchKernelEx(&cfg, lm_solve_cluster<FPT, THREADS>, cf, cv, nslots, d_nslots, x, so, trace);
 }
 
 int vl_solve(vloam_b200_ctx* c, int nslots, const int* d_nslots, double* d_x_inout, double* costs2) {
   if (nslots > 0) {
-    // one cluster: 8 CTAs for the small odometry problems, 16 (non-portable size) for the mapping ones
-    const int nct = nslots > 4096 ? LMC_MAX_CTAS : LMC_CTAS;
-    static bool attr = false;
-    if (!attr) { VL_CUDA(cudaFuncSetAttribute(lm_solve_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)); attr = true; }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(nct); cfg.blockDim = dim3(LMC_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+    cfg.gridDim = dim3(LMC_CTAS); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
     cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = nct; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[0].val.clusterDim.x = LMC_CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 2;
     const bool prof = c->prof_name[0] && vl_prof_match(c, "lm_solve_cluster") && c->prof_n < VL_PROF_MAX;
     if (prof) cudaEventRecord(c->prof_ev[c->prof_n][0], c->stream);
     const double* cf = c->factors.p; const int* cv = c->factorValid.p; LmSolveState* so = costs2 ? c->lms : nullptr;
-    VL_CUDA(cudaLaunchKernelEx(&cfg, lm_solve_cluster, cf, cv, nslots, d_nslots, d_x_inout, so));
-    if (prof) { cudaEventRecord(c->prof_ev[c->prof_n][1], c->stream); c->prof_kname[c->prof_n] = "lm_solve_cluster"; c->prof_kbytes[c->prof_n] = 84.0 * nslots * 5;
-                c->prof_n++; c->prof_bytes += 84.0 * nslots * 5; }
+    long long* tr = g_solver_trace;
+    if (nslots <= LMC_CTAS * 256) VL_CUDA((lm_launch<1, 256>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr)));
+    else if (nslots <= LMC_CTAS * 512) VL_CUDA((lm_launch<2, 256>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr)));
+    else if (nslots <= LMC_CTAS * 1024) VL_CUDA((lm_launch<4, 256>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr)));
+    else VL_CUDA((lm_launch<0, 256>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr)));
+    // algorithmic bytes: the factor slots (80 B + flag) are read once; the 5 evaluations run from registers
+    if (prof) { cudaEventRecord(c->prof_ev[c->prof_n][1], c->stream); c->prof_kname[c->prof_n] = "lm_solve_cluster"; c->prof_kbytes[c->prof_n] = 84.0 * nslots;
+                c->prof_n++; c->prof_bytes += 84.0 * nslots; }
     c->launches++;
   }
   if (costs2) {
@@ -472,7 +608,7 @@ int vl_evaluate_once(vloam_b200_ctx* c, int nslots, const double* d_x, EvalOut* 
   const int nb = max(1, min(vl_div_up(nslots, LM_BLOCK), LM_MAX_BLOCKS));
   VL_TRY(vl_reserve(c, c->evalPartials, LM_MAX_BLOCKS));
   unsigned int* counter = reinterpret_cast<unsigned int*>(c->vScalars + 60);
-  VL_LAUNCH(lm_eval, nb, LM_BLOCK, 0, c->factors.p, c->factorValid.p, nslots, c->lms, d_x, c->evalPartials.p, d_out, counter, 1);
+  VL_LAUNCH(lm_eval, nb, LM_BLOCK, 0, c->factors.p, c->factorValid.p, nslots, d_x, c->evalPartials.p, d_out, counter);
   VL_CUDA(cudaGetLastError());
   return VLOAM_OK;
 }
