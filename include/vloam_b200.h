@@ -117,6 +117,8 @@ int vloam_b200_profile_kernel(vloam_b200_ctx* c, const char* name);
 int vloam_b200_profile_result(vloam_b200_ctx* c, int* launches, double* total_ms, double* total_bytes);
 /* After profile_kernel(c, "*") (every launch timed): text table "name count total_ms total_bytes" per line. */
 int vloam_b200_profile_table(vloam_b200_ctx* c, char* buf, int cap);
+/* Same launches as a timeline: "name stream start_us end_us" per line (stream 0 = main .. 3), relative to the first. */
+int vloam_b200_profile_timeline(vloam_b200_ctx* c, char* buf, int cap);
 
 /* State export / import and stage-level inspection, keyed by name.  The
  * reference keeps this state in private members (LO.h:90-147, LM.h:102-203);

@@ -15,7 +15,7 @@ EXPORTS = [
     "vloam_b200_scan_registration", "vloam_b200_scan_registration_device", "vloam_b200_get_cloud", "vloam_b200_laser_odometry",
     "vloam_b200_laser_mapping", "vloam_b200_process_frame", "vloam_b200_process_frame_device", "vloam_b200_synchronize",
     "vloam_b200_stream", "vloam_b200_kernel_launches", "vloam_b200_set_timing", "vloam_b200_stage_ms", "vloam_b200_debug_get",
-    "vloam_b200_debug_set", "vloam_b200_profile_kernel", "vloam_b200_profile_result", "vloam_b200_profile_table", "vloam_b200_lo_associate", "vloam_b200_voxel_grid", "vloam_b200_evaluate", "vloam_b200_solve",
+    "vloam_b200_debug_set", "vloam_b200_profile_kernel", "vloam_b200_profile_result", "vloam_b200_profile_table", "vloam_b200_profile_timeline", "vloam_b200_lo_associate", "vloam_b200_voxel_grid", "vloam_b200_evaluate", "vloam_b200_solve",
 ]
 
 

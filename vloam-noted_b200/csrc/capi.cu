@@ -81,6 +81,7 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   VL_CUDA_CREATE(cudaMallocHost(&c->h_lms, sizeof(LmSolveState)));
   VL_CUDA_CREATE(cudaMalloc(&c->lmm, sizeof(LmScalars)));
   VL_CUDA_CREATE(cudaMallocHost(&c->h_lmm, sizeof(LmScalars)));
+  memset(c->h_lmm, 0, sizeof(LmScalars));
   VL_CUDA_CREATE(cudaMalloc(&c->cubeC, sizeof(MapCubeTable)));
   VL_CUDA_CREATE(cudaMalloc(&c->cubeS, sizeof(MapCubeTable)));
   VL_CUDA_CREATE(cudaMalloc(&c->vScalars, sizeof(int) * 256));
@@ -275,6 +276,27 @@ int vloam_b200_profile_table(vloam_b200_ctx* c, char* buf, int cap) {
   if ((int)out.size() + 1 > cap) { snprintf(c->err, sizeof c->err, "profile table buffer too small"); return VLOAM_E_CAPACITY; }
   memcpy(buf, out.c_str(), out.size() + 1);
   return (int)names.size();
+}
+
+// Timeline of the launches timed since vloam_b200_profile_kernel(c, "*"): lines "name stream start_us end_us\n",
+// times relative to the first recorded launch, stream = 0 (main) .. 3.  Event pairs around every launch
+// serialise neighbouring launches a little (no programmatic overlap across an event), so this shows the
+// dependency structure and the gaps, not the exact production schedule.
+int vloam_b200_profile_timeline(vloam_b200_ctx* c, char* buf, int cap) {
+  VL_TRY(vloam_b200_synchronize(c));
+  std::string out;
+  const cudaStream_t ss[4] = {c->stream, c->stream2, c->stream3, c->stream4};
+  for (int k = 0; k < c->prof_n; ++k) {
+    float t0 = 0, t1 = 0;
+    VL_CUDA(cudaEventElapsedTime(&t0, c->prof_ev[0][0], c->prof_ev[k][0]));
+    VL_CUDA(cudaEventElapsedTime(&t1, c->prof_ev[0][0], c->prof_ev[k][1]));
+    int si = 0; for (int q = 0; q < 4; ++q) if (ss[q] == c->prof_kstream[k]) si = q;
+    char line[256]; snprintf(line, sizeof line, "%s %d %.3f %.3f\n", c->prof_kname[k], si, t0 * 1e3, t1 * 1e3);
+    out += line;
+  }
+  if ((int)out.size() + 1 > cap) { snprintf(c->err, sizeof c->err, "timeline buffer too small"); return VLOAM_E_CAPACITY; }
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return c->prof_n;
 }
 
 int vloam_b200_lo_associate(vloam_b200_ctx* c, const double* x, int* corner_idx, int* surf_idx) { return vl_lo_associate_only(c, x, corner_idx, surf_idx); }

@@ -178,6 +178,7 @@ struct vloam_b200_ctx {
   cudaEvent_t prof_ev[VL_PROF_MAX][2];
   const char* prof_kname[VL_PROF_MAX];
   double prof_kbytes[VL_PROF_MAX];
+  cudaStream_t prof_kstream[VL_PROF_MAX];
   int prof_n, prof_created;
   double prof_bytes, prof_next_bytes;
 };
@@ -221,7 +222,7 @@ struct GridParams {
     at_[0].val.programmaticStreamSerializationAllowed = 1;                                     \
     cfg_.attrs = at_; cfg_.numAttrs = 1;                                                       \
     cudaLaunchKernelEx(&cfg_, kernel, __VA_ARGS__);                                            \
-    if (prof_) { cudaEventRecord(c->prof_ev[c->prof_n][1], c->stream); c->prof_kname[c->prof_n] = #kernel; c->prof_kbytes[c->prof_n] = c->prof_next_bytes; \
+    if (prof_) { cudaEventRecord(c->prof_ev[c->prof_n][1], c->stream); c->prof_kname[c->prof_n] = #kernel; c->prof_kbytes[c->prof_n] = c->prof_next_bytes; c->prof_kstream[c->prof_n] = c->stream; \
                  c->prof_n++; c->prof_bytes += c->prof_next_bytes; } \
     c->prof_next_bytes = 0;                                                                    \
     c->launches++;                                                                             \
@@ -279,7 +280,8 @@ int vl_voxel_grid_device(vloam_b200_ctx* c, const float4* d_in, int n, const int
 
 // solver (lm_solver.cu): evaluates factor slots [0, nslots) with validity flags.
 // nslots: host bound on the factor slots; d_nslots (device, may be null): actual count, min() of both is used
-int vl_solve(vloam_b200_ctx* c, int nslots, const int* d_nslots, double* d_x_inout, double* costs2 /* host, may be null */);
+int vl_solve(vloam_b200_ctx* c, int nslots, const int* d_nslots, double* d_x_inout, double* costs2 /* host, may be null */,
+             int hint = 0 /* last known actual slot count, 0 = none */);
 int vl_evaluate_once(vloam_b200_ctx* c, int nslots, const double* d_x, EvalOut* d_out);
 
 // ---- shared device helpers -----------------------------------------------------

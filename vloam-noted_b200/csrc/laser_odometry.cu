@@ -582,7 +582,7 @@ int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, i
         VL_CUDA(cudaMemcpyAsync(c->dbgLoSurf[pass].p, c->loSurfIdx.p, sizeof(int) * 3 * c->nFlat, cudaMemcpyDeviceToDevice, c->stream));
       }
       const int nslots = c->sr_counts_valid ? c->nSharp + c->nFlat : lo_sharp_bound(c) + lo_flat_bound(c);
-      VL_TRY(vl_solve(c, nslots, &c->srs->nQueries, d_pose, vl_debug_capture(c) ? &c->dbgLoCost[pass * 2] : nullptr));
+      VL_TRY(vl_solve(c, nslots, &c->srs->nQueries, d_pose, vl_debug_capture(c) ? &c->dbgLoCost[pass * 2] : nullptr, c->nSharp + c->nFlat));
     }
     VL_LAUNCH(lo_accumulate, 1, 32, 0, c->los);
   }

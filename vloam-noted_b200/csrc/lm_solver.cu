@@ -365,12 +365,14 @@ struct LmFactorReg {  // one factor with its pose-independent parts hoisted
 };
 
 __device__ __forceinline__ void lm_factor_load(const double* __restrict__ f, bool ok, LmFactorReg& o) {
-  o.type = -1;
-  if (!ok) return;
-  o.type = (int)f[0];
+  // the ten loads are issued unconditionally (the slot array is allocated up to the host bound), so they overlap
+  // the loads of the slot count and of the validity flag instead of waiting for them
+  const double t = f[0];
   o.p[0] = f[1]; o.p[1] = f[2]; o.p[2] = f[3];
   o.a[0] = f[4]; o.a[1] = f[5]; o.a[2] = f[6];
   o.b[0] = f[7]; o.b[1] = f[8]; o.b[2] = f[9];
+  o.type = ok ? (int)t : -1;
+  o.inv = 0; o.w[0] = o.w[1] = o.w[2] = 0;
   if (o.type == 0) {
     const double de[3] = {o.a[0] - o.b[0], o.a[1] - o.b[1], o.a[2] - o.b[2]};
     o.inv = 1.0 / sqrt(de[0] * de[0] + de[1] * de[1] + de[2] * de[2]);
@@ -443,10 +445,23 @@ lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ val
                  double* __restrict__ x_inout, LmSolveState* __restrict__ st_out, long long* __restrict__ trace) {
   VL_PDL_WAIT();
 
-  const int nslots = d_nslots ? min(nslotsBound, *d_nslots) : nslotsBound;
-  if (nslots <= 0) return;  // no residual blocks: Ceres leaves the parameters untouched (uniform over the cluster)
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank();
+  // raw slots first: these loads do not depend on the slot count or the validity flags
+  double raw[FPT > 0 ? FPT : 1][10];
+  int vflag[FPT > 0 ? FPT : 1];
+  if (FPT > 0) {
+#pragma unroll
+    for (int j = 0; j < FPT; ++j) {
+      const int i = (j * THREADS + threadIdx.x) * LMC_CTAS + (int)rank;
+      const bool inb = i < nslotsBound;
+      vflag[j] = inb ? valid[i] : 0;
+#pragma unroll
+      for (int q = 0; q < 10; ++q) raw[j][q] = inb ? factors[(size_t)i * 10 + q] : 0.0;
+    }
+  }
+  const int nslots = d_nslots ? min(nslotsBound, *d_nslots) : nslotsBound;
+  if (nslots <= 0) return;  // no residual blocks: Ceres leaves the parameters untouched (uniform over the cluster)
   __shared__ double part[2][28];
   __shared__ double red[THREADS / 32][28];
   __shared__ double gath[LMC_CTAS][28];
@@ -467,13 +482,14 @@ lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ val
   S.li = 0; S.lj = -1;
   if (lane < 21) { int t = lane, i = 0; while (t >= 6 - i) { t -= 6 - i; ++i; } S.li = i; S.lj = i + t; }
   else if (lane < 27) S.li = lane - 21;
+  // the host picks FPT from a hint (last frame's count); the actual count decides here, uniformly over the cluster
+  const bool inreg = FPT > 0 && nslots <= FPT * THREADS * LMC_CTAS;
   LmFactorReg fr_[FPT > 0 ? FPT : 1];
-  if (FPT > 0) {
+  if (inreg) {
 #pragma unroll
     for (int j = 0; j < FPT; ++j) {
       const int i = (j * THREADS + threadIdx.x) * LMC_CTAS + (int)rank;
-      const bool ok = i < nslots && valid[i] != 0;
-      lm_factor_load(factors + (size_t)(ok ? i : 0) * 10, ok, fr_[j]);
+      lm_factor_load(raw[j], i < nslots && vflag[j] != 0, fr_[j]);
     }
   }
   LM_TRACE(14);
@@ -482,7 +498,7 @@ lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ val
     double acc[32];
 #pragma unroll
     for (int k = 0; k < 32; ++k) acc[k] = 0.0;
-    if (FPT > 0) {
+    if (inreg) {
 #pragma unroll
       for (int j = 0; j < FPT; ++j) {
         if (fr_[j].type < 0) continue;
@@ -571,7 +587,7 @@ static cudaError_t lm_launch(cudaLaunchConfig_t& cfg, const double* cf, const in
   return cudaLaunchKernelEx(&cfg, lm_solve_cluster<FPT, THREADS>, cf, cv, nslots, d_nslots, x, so, trace);
 }
 
-int vl_solve(vloam_b200_ctx* c, int nslots, const int* d_nslots, double* d_x_inout, double* costs2) {
+int vl_solve(vloam_b200_ctx* c, int nslots, const int* d_nslots, double* d_x_inout, double* costs2, int hint) {
   if (nslots > 0) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(LMC_CTAS); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
@@ -585,12 +601,16 @@ int vl_solve(vloam_b200_ctx* c, int nslots, const int* d_nslots, double* d_x_ino
     if (prof) cudaEventRecord(c->prof_ev[c->prof_n][0], c->stream);
     const double* cf = c->factors.p; const int* cv = c->factorValid.p; LmSolveState* so = costs2 ? c->lms : nullptr;
     long long* tr = g_solver_trace;
-    if (nslots <= LMC_CTAS * 256) VL_CUDA((lm_launch<1, 256>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr)));
-    else if (nslots <= LMC_CTAS * 512) VL_CUDA((lm_launch<2, 256>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr)));
-    else if (nslots <= LMC_CTAS * 1024) VL_CUDA((lm_launch<4, 256>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr)));
+    // nslots is a host BOUND (buffer capacity when the count still lives on the device); `hint` is the last known
+    // actual count.  The variant only decides how many slots a thread can keep in registers: a solve whose
+    // actual count exceeds it streams the factors from memory at every evaluation instead.
+    const int est = hint > 0 ? min(nslots, hint + hint / 8 + 64) : nslots;
+    if (est <= LMC_CTAS * 256) VL_CUDA((lm_launch<1, 256>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr)));
+    else if (est <= LMC_CTAS * 512) VL_CUDA((lm_launch<2, 256>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr)));
+    else if (est <= LMC_CTAS * 1024) VL_CUDA((lm_launch<4, 256>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr)));
     else VL_CUDA((lm_launch<0, 256>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr)));
     // algorithmic bytes: the factor slots (80 B + flag) are read once; the 5 evaluations run from registers
-    if (prof) { cudaEventRecord(c->prof_ev[c->prof_n][1], c->stream); c->prof_kname[c->prof_n] = "lm_solve_cluster"; c->prof_kbytes[c->prof_n] = 84.0 * nslots;
+    if (prof) { cudaEventRecord(c->prof_ev[c->prof_n][1], c->stream); c->prof_kname[c->prof_n] = "lm_solve_cluster"; c->prof_kbytes[c->prof_n] = 84.0 * nslots; c->prof_kstream[c->prof_n] = c->stream;
                 c->prof_n++; c->prof_bytes += 84.0 * nslots; }
     c->launches++;
   }

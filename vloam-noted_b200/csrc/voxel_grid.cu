@@ -176,7 +176,7 @@ static int vl_sort_cluster(vloam_b200_ctx* c, unsigned long long* d_keys, int n_
   const bool prof = c->prof_name[0] && vl_prof_match(c, "bt_cluster_sort") && c->prof_n < VL_PROF_MAX;
   if (prof) cudaEventRecord(c->prof_ev[c->prof_n][0], c->stream);
   VL_CUDA(cudaLaunchKernelEx(&cfg, bt_cluster_sort, d_keys, tile));
-  if (prof) { cudaEventRecord(c->prof_ev[c->prof_n][1], c->stream); c->prof_kname[c->prof_n] = "bt_cluster_sort"; c->prof_kbytes[c->prof_n] = 16.0 * n_pow2;
+  if (prof) { cudaEventRecord(c->prof_ev[c->prof_n][1], c->stream); c->prof_kname[c->prof_n] = "bt_cluster_sort"; c->prof_kbytes[c->prof_n] = 16.0 * n_pow2; c->prof_kstream[c->prof_n] = c->stream;
               c->prof_n++; c->prof_bytes += 16.0 * n_pow2; }
   c->launches++;
   return VLOAM_OK;
