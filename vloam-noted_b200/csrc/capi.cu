@@ -9,6 +9,7 @@ static bool g_capture_default = false;
 bool vl_debug_capture(const vloam_b200_ctx* c) { return c->h_vScalars && c->h_vScalars[0] != 0; }
 int vl_lm_rescan_sorted(vloam_b200_ctx* c);
 int vl_solver_trace(vloam_b200_ctx* c, long long* out16);
+int vl_lo_trace(vloam_b200_ctx* c, int* out, int n);
 
 extern "C" {
 
@@ -352,6 +353,11 @@ long vloam_b200_debug_get(vloam_b200_ctx* c, const char* name, void* out, long c
       if (kind == "cok") return put_dev(c, c->dbgKnnOk[k][0].p, (size_t)Qc * 4, out, cap);
       if (kind == "sok") return put_dev(c, c->dbgKnnOk[k][1].p, (size_t)Qs * 4, out, cap);
     }
+  }
+  if (n == "lo.trace") {  // per query warp of the last grid association: {cycles, flags}
+    static int v[2 * 8192];
+    if (vl_lo_trace(c, v, 2 * 8192) != VLOAM_OK) return VLOAM_E_CUDA;
+    return put_host(v, sizeof v, out, cap);
   }
   if (n == "solver.trace") {  // clock64 stamps of the last lm_solve_cluster launch (first call arms the trace)
     long long v[16];

@@ -65,6 +65,7 @@ struct LmScalars {
   int poolTopC, poolTopS;
   int overflow;                     // set when a pool / buffer bound was hit
   int optimized;
+  int totalC, totalS;               // points in all 4851 cubes before this frame's update (bounds the next sub-map)
   double pose[7];                   // q_w_curr, t_w_curr (parameters[7], laser_mapping.h:156)
   double q_wmap_wodom[4], t_wmap_wodom[3];
   double q_wodom[4], t_wodom[3];
@@ -244,7 +245,7 @@ template <typename T>
 static inline int vl_reserve(vloam_b200_ctx* c, DBuf<T>& b, size_t n, bool keep = false, size_t slack = 0) {
   if (n <= b.cap) return VLOAM_OK;
   n += slack;
-  size_t ncap = b.cap ? b.cap : 1024;
+  size_t ncap = b.cap ? b.cap : ((size_t)1 << 17);  // a regrow stalls the pipeline for ~1 ms: start above any per-sweep feature count
   while (ncap < n) ncap *= 2;
   if (ncap * sizeof(T) <= ((size_t)32 << 20)) ncap *= 2;  // HBM is plentiful: head room so a count hovering at a power of two never regrows
   T* np = nullptr;
@@ -309,24 +310,47 @@ __device__ __forceinline__ void vl_qmul(const double a[4], const double b[4], do
   const double z = aw * bz + az * bw + ax * by - ay * bx;
   o[0] = x; o[1] = y; o[2] = z; o[3] = w;
 }
-// Visit every index of up to 32 ranges with all lanes busy.  Lane r owns range [myBeg, myBeg + myLen)
-// (myLen = 0 when it has none); the cell-start look-ups of all ranges are therefore issued together
-// (one memory latency instead of one per row) and short rows no longer leave lanes idle.  soff / sbeg:
-// 32 ints of shared memory each, private to the warp.  BODY sees `const int p`.
-#define VL_WARP_VISIT_RANGES(myBeg, myLen, lane, soff, sbeg, BODY)                                  \
-  do {                                                                                              \
-    int inc_ = (myLen);                                                                             \
+// Visit every element of up to 32 index ranges of ARRAY (float4) with all lanes busy, 128 elements per step.
+// Lane r owns range [myBeg, myBeg + myLen) (myLen = 0 when it has none), so the look-ups that produced
+// the ranges were issued together (one memory latency, not one per range).  Non-empty ranges are compacted
+// onto lanes 0..nr-1 with their exclusive prefix; the range owning each of the 32 consecutive flattened
+// positions of a sub-step then follows from one ballot (ranges starting at or before the sub-step) and
+// one warp OR-reduction (bit i: a range starts at position base + i) -- registers only, no search.  The
+// four loads of a step are issued before any is used: a query warp has few sibling warps to hide the L2
+// latency behind.  BODY sees `const float4 t` and `const int p` (its index in ARRAY).
+#define VL_WARP_VISIT_FLAT(myBeg, myLen, lane, ARRAY, BODY)                                                    \
+  do {                                                                                                         \
+    int inc_ = (myLen);                                                                                        \
     for (int d_ = 1; d_ < 32; d_ <<= 1) { const int t_ = __shfl_up_sync(0xffffffffu, inc_, d_); if ((lane) >= d_) inc_ += t_; } \
-    __syncwarp();                                                                                   \
-    (soff)[lane] = inc_ - (myLen); (sbeg)[lane] = (myBeg);                                          \
-    __syncwarp();                                                                                   \
-    const int total_ = __shfl_sync(0xffffffffu, inc_, 31);                                          \
-    for (int idx_ = (lane); idx_ < total_; idx_ += 32) {                                            \
-      int lo_ = 0, hi_ = 32;                                                                        \
-      while (hi_ - lo_ > 1) { const int mid_ = (lo_ + hi_) >> 1; if ((soff)[mid_] <= idx_) lo_ = mid_; else hi_ = mid_; } \
-      const int p = (sbeg)[lo_] + (idx_ - (soff)[lo_]);                                             \
-      BODY                                                                                          \
-    }                                                                                               \
+    const int total_ = __shfl_sync(0xffffffffu, inc_, 31);                                                     \
+    if (total_ <= 0) break;                                                                                    \
+    const unsigned ne_ = __ballot_sync(0xffffffffu, (myLen) > 0);                                              \
+    const int nr_ = __popc(ne_);                                                                               \
+    const int src_ = (lane) < nr_ ? (int)__fns(ne_, 0, (lane) + 1) : 0;                                        \
+    const int cbeg_ = __shfl_sync(0xffffffffu, (myBeg), src_);                                                 \
+    int cexc_ = __shfl_sync(0xffffffffu, inc_ - (myLen), src_);                                                \
+    if ((lane) >= nr_) cexc_ = 0x7fffffff;                                                                     \
+    const int safe_ = __shfl_sync(0xffffffffu, cbeg_, 0);                                                      \
+    for (int base_ = 0; base_ < total_; base_ += 128) {                                                        \
+      int p4_[4]; bool ok4_[4];                                                                                \
+      _Pragma("unroll")                                                                                        \
+      for (int u_ = 0; u_ < 4; ++u_) {                                                                         \
+        const int b_ = base_ + 32 * u_;                                                                        \
+        const int cnt0_ = __popc(__ballot_sync(0xffffffffu, cexc_ <= b_));                                     \
+        const unsigned st_ = __reduce_or_sync(0xffffffffu, (cexc_ > b_ && cexc_ < b_ + 32) ? (1u << (cexc_ - b_)) : 0u); \
+        const int k_ = max(cnt0_ - 1 + __popc(st_ & ((2u << (lane)) - 1u)), 0) & 31;                           \
+        const int rb_ = __shfl_sync(0xffffffffu, cbeg_, k_), ro_ = __shfl_sync(0xffffffffu, cexc_, k_);        \
+        const int idx_ = b_ + (lane);                                                                          \
+        ok4_[u_] = idx_ < total_;                                                                              \
+        p4_[u_] = ok4_[u_] ? rb_ + (idx_ - ro_) : safe_;                                                       \
+      }                                                                                                        \
+      const float4 t0_ = __ldg(&(ARRAY)[p4_[0]]), t1_ = __ldg(&(ARRAY)[p4_[1]]);                               \
+      const float4 t2_ = __ldg(&(ARRAY)[p4_[2]]), t3_ = __ldg(&(ARRAY)[p4_[3]]);                               \
+      if (ok4_[0]) { const float4 t = t0_; const int p = p4_[0]; (void)p; BODY }                               \
+      if (ok4_[1]) { const float4 t = t1_; const int p = p4_[1]; (void)p; BODY }                               \
+      if (ok4_[2]) { const float4 t = t2_; const int p = p4_[2]; (void)p; BODY }                               \
+      if (ok4_[3]) { const float4 t = t3_; const int p = p4_[3]; (void)p; BODY }                               \
+    }                                                                                                          \
   } while (0)
 
 // FLANN L2_Simple<float>: acc = 0; acc += d*d over x, y, z (f32, no FMA: -fmad=false).

@@ -156,10 +156,17 @@ __global__ void __launch_bounds__(1024) lm_prepare(LmScalars* __restrict__ s, co
       ts->start[d] = v[q][4]; ts->count[d] = wrap[q] ? 0 : v[q][5]; ts->cap[d] = v[q][6]; ts->sorted[d] = wrap[q] ? 0 : v[q][7];
     }
   }
-  for (int d = threadIdx.x; d < VL_CUBE_NUM; d += 1024) w->slotOfCube[d] = -1;
+  __shared__ int sTot[2];
+  if (threadIdx.x < 2) sTot[threadIdx.x] = 0;
+  __syncthreads();
+  int myC = 0, myS = 0;
+  for (int d = threadIdx.x; d < VL_CUBE_NUM; d += 1024) { w->slotOfCube[d] = -1; myC += tc->count[d]; myS += ts->count[d]; }
+  for (int o = 16; o > 0; o >>= 1) { myC += __shfl_xor_sync(0xffffffffu, myC, o); myS += __shfl_xor_sync(0xffffffffu, myS, o); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&sTot[0], myC); atomicAdd(&sTot[1], myS); }
   __shared__ int sbuf[256];
   __shared__ int snv;
   __syncthreads();
+  if (threadIdx.x == 0) { s->totalC = sTot[0]; s->totalS = sTot[1]; }
   if (threadIdx.x == 0) {
     const int cI = center[0], cJ = center[1], cK = center[2];
     int nv = s->validNum;  // LaserMapping::reset zeroes it once per frame (LM.cpp:132-136)
@@ -415,9 +422,6 @@ __global__ void __launch_bounds__(256) lm_knn(const LmScalars* __restrict__ s, c
   VL_PDL_WAIT();
 
   const int lane = threadIdx.x & 31;
-  __shared__ int srange[8][64];
-  int* soff = srange[threadIdx.x >> 5];
-  int* sbeg = soff + 32;
   const int Qc = s->Qc, Qs = s->Qs;
   if (!s->optimized) return;
   const int nWarps = (gridDim.x * blockDim.x) >> 5;
@@ -445,8 +449,7 @@ __global__ void __launch_bounds__(256) lm_knn(const LmScalars* __restrict__ s, c
         rl = cellStart[c0 + (x1 - x0) + 1] - rb;
       }
     }
-    VL_WARP_VISIT_RANGES(rb, rl, lane, soff, sbeg, {
-      const float4 t = __ldg(&sortedPts[p]);
+    VL_WARP_VISIT_FLAT(rb, rl, lane, sortedPts, {
       const float d = vl_dist2(sx, sy, sz, t.x, t.y, t.z);
       const int id = __float_as_int(t.w);
       if (d < bd[4] || (d == bd[4] && id < bi[4])) {  // insertion into the lane-local sorted top-5
@@ -1129,7 +1132,8 @@ int vl_lm_run(vloam_b200_ctx* c) {
   }();
   c->stream = mainStream;
   if (rmap != VLOAM_OK) return rmap;
-  d->hMapUpperC += Qc; d->hMapUpperS += Qs;
+  // the map after this frame's update holds at most the points it held before plus this frame's inserts
+  d->hMapUpperC = (long long)c->h_lmm->totalC + Qc; d->hMapUpperS = (long long)c->h_lmm->totalS + Qs;
   c->lm_frameCount++;
   VL_CUDA(cudaGetLastError());
   return VLOAM_OK;

@@ -241,20 +241,23 @@ __global__ void __launch_bounds__(LO_QPB * 32) lo_assoc(const float4* __restrict
 
 // ---- uniform grid over the "last" clouds -----------------------------------------------------------
 // The reference rebuilds two KD-trees per frame (LO.cpp:573-574).  Here both last clouds are counting-
-// sorted once per frame into 2.56 m cells.  A search visits the 27 cells around the query first: they
-// contain every point closer than 2.56 m, so a minimum below (2.5 m)^2 is already the global one; only
-// otherwise the surrounding shell (5x5x5 cells, >= 5.12 m around the query, i.e. everything inside the
-// 5 m acceptance radius of LO.cpp:299/397) is visited too.  Entries are {x, y, z, bits(index |
+// sorted once per frame into 1.28 m cells (256 x 256 x 32 cells per cloud).  A search visits the 27 cells
+// around the query first: they contain every point closer than 1.28 m, so a minimum below (1.25 m)^2 is
+// already the global one; otherwise the 5x5x5 block (everything within 2.56 m) and, failing that, the
+// 9x9x9 block (>= 5.12 m around the query, i.e. everything inside the 5 m acceptance radius of
+// LO.cpp:299/397) are visited.  The less-flat cloud puts ~150 points into a 2.56 m cell near the sensor:
+// with cells that large a query warp spent 20 us filtering ~4000 candidates per pass.  Entries are {x, y, z, bits(index |
 // int(intensity) << 24)}.  Coordinates outside the grid are clamped, which keeps neighbours neighbours
 // (clamping is monotone), so the search stays exact.
-#define LOG_NX 128
-#define LOG_NY 128
+#define LOG_NX 256
+#define LOG_NY 256
 #define LOG_NZ 32
 #define LOG_NCELL (LOG_NX * LOG_NY * LOG_NZ)
-#define LOG_INV 0.390625f    // 1 / 2.56
-#define LOG_NEAR2 6.25f      // (2.5 m)^2 < cell^2: a minimum below this found in the 27 cells is global
+#define LOG_INV 0.78125f     // 1 / 1.28
+#define LOG_NEAR1 1.5625f    // (1.25 m)^2 < cell^2: a minimum below this found in the 3x3x3 block is global
+#define LOG_NEAR2 6.25f      // (2.5 m)^2 < (2 cells)^2: same for the 5x5x5 block; the 9x9x9 block covers the 5 m gate
 #define LOG_OX (-163.84f)
-#define LOG_OZ (-40.96f)
+#define LOG_OZ (-10.24f)
 
 __device__ __forceinline__ int log_cx(float v) { return min(max((int)floorf((v - LOG_OX) * LOG_INV), 0), LOG_NX - 1); }
 __device__ __forceinline__ int log_cz(float v) { return min(max((int)floorf((v - LOG_OZ) * LOG_INV), 0), LOG_NZ - 1); }
@@ -302,42 +305,42 @@ __device__ __forceinline__ Best warp_best_v(Best v, unsigned& tag, bool preferLo
 // reference's forward scan then visits exactly {j > closest : ring_j <= id + 2} and the backward scan
 // {j < closest : ring_j >= id - 2}; candidates farther than 5 m can never win because the running
 // minima start at DISTANCE_SQ_THRESHOLD = 25).  One warp per query, two passes over its 27 cells.
-// visit cells [xa, xb] of row (yy, zz); BODY sees float4 t
-#define LOG_ROW(xa, xb, yy, zz, BODY)                                                    \
-  do {                                                                                   \
-    const int c0_ = cellBase + (xa) + LOG_NX * ((yy) + LOG_NY * (zz));                   \
-    const int beg_ = cellStart[c0_], end_ = cellStart[c0_ + ((xb) - (xa)) + 1];          \
-    for (int p_ = beg_ + lane; p_ < end_; p_ += 32) { const float4 t = __ldg(&sorted[p_]); BODY } \
-  } while (0)
-// inner = the 3x3x3 block, shell = the 5x5x5 block minus the inner one
-#define LOG_VISIT(SHELL, BODY)                                                           \
-  do {                                                                                   \
-    const int rad_ = (SHELL) ? 2 : 1;                                                    \
-    for (int dz_ = -rad_; dz_ <= rad_; ++dz_) {                                          \
-      const int zz_ = cz + dz_;                                                          \
-      if (zz_ < 0 || zz_ >= LOG_NZ) continue;                                            \
-      for (int dy_ = -rad_; dy_ <= rad_; ++dy_) {                                        \
-        const int yy_ = cy + dy_;                                                        \
-        if (yy_ < 0 || yy_ >= LOG_NY) continue;                                          \
-        if (!(SHELL)) { LOG_ROW(max(cx - 1, 0), min(cx + 1, LOG_NX - 1), yy_, zz_, BODY); } \
-        else if (dz_ == -2 || dz_ == 2 || dy_ == -2 || dy_ == 2) { LOG_ROW(max(cx - 2, 0), min(cx + 2, LOG_NX - 1), yy_, zz_, BODY); } \
-        else {                                                                           \
-          if (cx - 2 >= 0) { LOG_ROW(cx - 2, cx - 2, yy_, zz_, BODY); }                  \
-          if (cx + 2 < LOG_NX) { LOG_ROW(cx + 2, cx + 2, yy_, zz_, BODY); }              \
-        }                                                                                \
-      }                                                                                  \
-    }                                                                                    \
+// Visit the (2R+1)^3 block of cells around (cx, cy, cz), R = 1, 2 or 4.  A block is (2R+1)^2 rows of
+// contiguous cells; lane r looks up the point range of row r (all cell-start reads in one memory latency;
+// the 81 rows of R = 4 take three rounds) and VL_WARP_VISIT_FLAT spreads the candidates of all rows over
+// the lanes.  A larger block simply revisits the smaller one: every update in the bodies below is an
+// idempotent minimum, and escalation only happens where the inner block was nearly empty.  BODY sees float4 t.
+#define LOG_VISIT(R, BODY)                                                                                   \
+  do {                                                                                                       \
+    const int side_ = 2 * (R) + 1;                                                                           \
+    for (int r0_ = 0; r0_ < side_ * side_; r0_ += 32) {                                                      \
+      const int rr_ = r0_ + lane;                                                                            \
+      int beg_ = 0, len_ = 0;                                                                                \
+      if (rr_ < side_ * side_) {                                                                             \
+        const int zz_ = cz + rr_ / side_ - (R), yy_ = cy + rr_ % side_ - (R);                                \
+        if (zz_ >= 0 && zz_ < LOG_NZ && yy_ >= 0 && yy_ < LOG_NY) {                                          \
+          const int row_ = cellBase + LOG_NX * (yy_ + LOG_NY * zz_);                                         \
+          beg_ = cellStart[row_ + max(cx - (R), 0)];                                                         \
+          len_ = cellStart[row_ + min(cx + (R), LOG_NX - 1) + 1] - beg_;                                     \
+        }                                                                                                    \
+      }                                                                                                      \
+      VL_WARP_VISIT_FLAT(beg_, len_, lane, sorted, BODY);                                                    \
+    }                                                                                                        \
   } while (0)
 
 // Association over the grid (valid when int(intensity) of the target cloud is non-decreasing: the
 // reference's forward scan then visits exactly {j > closest : ring_j <= id + 2} and the backward scan
 // {j < closest : ring_j >= id - 2}; candidates farther than 5 m can never win because the running
 // minima start at DISTANCE_SQ_THRESHOLD = 25).  One warp per query.
+__device__ int* g_lo_trace = nullptr;  // debug: per query warp {cycles, flags: 1 = shell in the NN pass, 2 = shell in the second pass}
+
 template <bool SURF>
 __device__ __forceinline__ void lo_assoc_grid_dev(int qi, int lane, const float4* __restrict__ query, const float4* __restrict__ target,
                                                   const float4* __restrict__ sorted, const int* __restrict__ cellStart,
                                                   const double* __restrict__ pose, int* __restrict__ outIdx,
                                                   double* __restrict__ factors, int* __restrict__ valid, int slotBase) {
+  const long long tr0 = g_lo_trace ? clock64() : 0;
+  int trFlags = 0;
   const float4 cp = query[qi];
   double r[3];
   vl_qrot(pose, (double)cp.x, (double)cp.y, (double)cp.z, r);  // TransformToStart (LO.cpp:152-173)
@@ -354,11 +357,17 @@ __device__ __forceinline__ void lo_assoc_grid_dev(int qi, int lane, const float4
     const int j = (int)(bits & 0xffffffu);                                               \
     if (d < nn.d || (d == nn.d && j < nn.j)) { nn.d = d; nn.j = j; nnv = bits >> 24; }   \
   }
-  LOG_VISIT(false, LOG_NN_BODY);
+  LOG_VISIT(1, LOG_NN_BODY);
   nn = warp_best_v(nn, nnv, true);
-  if (!(nn.d < LOG_NEAR2)) {  // nothing within 2.5 m: look at the shell as well (warp-uniform branch)
-    LOG_VISIT(true, LOG_NN_BODY);
+  if (!(nn.d < LOG_NEAR1)) {  // nothing within 1.25 m: widen the block (warp-uniform branches)
+    trFlags |= 1;
+    LOG_VISIT(2, LOG_NN_BODY);
     nn = warp_best_v(nn, nnv, true);
+    if (!(nn.d < LOG_NEAR2)) {
+      trFlags |= 8;
+      LOG_VISIT(4, LOG_NN_BODY);
+      nn = warp_best_v(nn, nnv, true);
+    }
   }
   int closest = -1, ind2 = -1, ind3 = -1;
   if (nn.j != 0x7fffffff && (double)nn.d < 25.0) {  // LO.cpp:299, 397
@@ -389,14 +398,21 @@ __device__ __forceinline__ void lo_assoc_grid_dev(int qi, int lane, const float4
       }                                                                                                   \
     }                                                                                                     \
   }
-    LOG_VISIT(false, LOG_B_BODY);
+    LOG_VISIT(1, LOG_B_BODY);
     Best F2 = warp_best(f2, true), G2 = warp_best(g2, false), F3 = f3, G3 = g3;
     if (SURF) { F3 = warp_best(f3, true); G3 = warp_best(g3, false); }
-    const bool need = !(fminf(F2.d, G2.d) < LOG_NEAR2) || (SURF && !(fminf(F3.d, G3.d) < LOG_NEAR2));
-    if (need) {  // some class has no candidate within 2.5 m yet: the shell may still hold one
-      LOG_VISIT(true, LOG_B_BODY);
+    // a class whose best candidate is nearer than the radius the visited block guarantees is settled
+    if (!(fminf(F2.d, G2.d) < LOG_NEAR1) || (SURF && !(fminf(F3.d, G3.d) < LOG_NEAR1))) {
+      trFlags |= 2;
+      LOG_VISIT(2, LOG_B_BODY);
       F2 = warp_best(f2, true); G2 = warp_best(g2, false);
       if (SURF) { F3 = warp_best(f3, true); G3 = warp_best(g3, false); }
+      if (!(fminf(F2.d, G2.d) < LOG_NEAR2) || (SURF && !(fminf(F3.d, G3.d) < LOG_NEAR2))) {
+        trFlags |= 16;
+        LOG_VISIT(4, LOG_B_BODY);
+        F2 = warp_best(f2, true); G2 = warp_best(g2, false);
+        if (SURF) { F3 = warp_best(f3, true); G3 = warp_best(g3, false); }
+      }
     }
     // forward candidates were visited first: backward wins only when strictly nearer
     if (F2.j == 0x7fffffff) F2.j = -1;
@@ -408,6 +424,7 @@ __device__ __forceinline__ void lo_assoc_grid_dev(int qi, int lane, const float4
   }
   if (lane != 0) return;
   const int slot = slotBase + qi;
+  if (g_lo_trace) { g_lo_trace[2 * slot] = (int)(clock64() - tr0); g_lo_trace[2 * slot + 1] = trFlags | (SURF ? 4 : 0); }
   double* f = factors + (size_t)slot * 10;
   if (SURF) {
     outIdx[qi * 3] = closest; outIdx[qi * 3 + 1] = ind2; outIdx[qi * 3 + 2] = ind3;
@@ -493,7 +510,7 @@ int vl_lo_build_last(vloam_b200_ctx* c, int set, const float4* corner, int nc, c
   VL_LAUNCH(lo_ring_table, dim3(vl_div_up(max(max(nc, ns), LO_TBL + 1), 256), 2), 256, 0, corner, nc, surf, ns, tbl);
   VL_CUDA(cudaMemcpyAsync(&c->h_vScalars[8 + 2 * set], tbl + LO_TBL, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   VL_CUDA(cudaMemcpyAsync(&c->h_vScalars[9 + 2 * set], tbl + (LO_TBL + 1) + LO_TBL, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  VL_TRY(vl_reserve(c, c->loGridCells[set], (size_t)3 * (2 * LOG_NCELL + 1) + 256));
+  VL_TRY(vl_reserve(c, c->loGridCells[set], (size_t)3 * (2 * LOG_NCELL + 1) + (2 * LOG_NCELL) / 1024 + 8));  // counts, starts, fill, tile sums
   VL_TRY(vl_reserve(c, c->loGridCellOf, (size_t)max(n, 1), false, (size_t)n / 2));
   VL_TRY(vl_reserve(c, c->loGridSorted[set], (size_t)max(n, 1), false, (size_t)n / 2));
   if (n > 0 && n < (1 << 24)) {
@@ -554,6 +571,20 @@ static int lo_associate(vloam_b200_ctx* c, const double* d_pose, const float4* c
 }
 
 extern bool vl_debug_capture(const vloam_b200_ctx* c);
+
+// debug: the first call arms the per-warp trace of the grid association; later calls copy it out (n ints)
+int vl_lo_trace(vloam_b200_ctx* c, int* out, int n) {
+  static int* d_buf = nullptr;
+  const int cap = 2 * 8192;
+  if (!d_buf) {
+    VL_CUDA(cudaMalloc(&d_buf, sizeof(int) * cap));
+    VL_CUDA(cudaMemset(d_buf, 0, sizeof(int) * cap));
+    VL_CUDA(cudaMemcpyToSymbol(g_lo_trace, &d_buf, sizeof(int*)));
+  }
+  VL_CUDA(cudaStreamSynchronize(c->stream));
+  VL_CUDA(cudaMemcpy(out, d_buf, sizeof(int) * min(n, cap), cudaMemcpyDeviceToHost));
+  return VLOAM_OK;
+}
 
 int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, int use_prior) {
   VL_CUDA(cudaEventSynchronize(c->evLast));  // set [lastSet] (built underneath the previous frame) and its flags are complete

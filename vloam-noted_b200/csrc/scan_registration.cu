@@ -265,7 +265,9 @@ __device__ __forceinline__ float sr_gap2(const float4* __restrict__ cloud, int a
 
 // Mark ind and its +-5 neighbours until a gap > 0.05 (SR.cpp:403-429); warp-cooperative.
 // gb[k] (ring-local) = squared gap between points k and k-1 exceeds 0.05, precomputed for the ring.
-__device__ __forceinline__ void sr_mark(const unsigned char* gb, unsigned char* pk, int loc, int lane) {
+// Only positions in [lo, hi] are written; forward marks beyond hi are returned as a bit mask
+// (bit b = position hi + 1 + b), backward marks below lo are dropped (that sector is already final).
+__device__ __forceinline__ unsigned sr_mark(const unsigned char* gb, unsigned char* pk, int loc, int lane, int lo, int hi) {
   bool brk = false;
   if (lane < 5) brk = gb[loc + lane + 1] != 0;            // l = lane+1: gap(ind+l, ind+l-1)
   else if (lane < 10) brk = gb[loc - (lane - 4) + 1] != 0;  // l = -(lane-4): gap(ind+l, ind+l+1)
@@ -273,13 +275,88 @@ __device__ __forceinline__ void sr_mark(const unsigned char* gb, unsigned char* 
   const unsigned f = bb & 31u, w = (bb >> 5) & 31u;
   const int nf = f ? __ffs(f) - 1 : 5, nb = w ? __ffs(w) - 1 : 5;
   if (lane == 0) pk[loc] = 1;
-  if (lane < nf) pk[loc + lane + 1] = 1;
-  if (lane >= 5 && lane - 5 < nb) pk[loc - (lane - 4)] = 1;
+  if (lane < nf && loc + lane + 1 <= hi) pk[loc + lane + 1] = 1;
+  if (lane >= 5 && lane - 5 < nb && loc - (lane - 4) >= lo) pk[loc - (lane - 4)] = 1;
+  unsigned spill = 0;
+  const int over = loc + nf - hi;  // forward marks that land beyond hi: positions hi+1 .. loc+nf
+  if (over > 0) spill = ((1u << over) - 1u) << max(loc + 1 - (hi + 1), 0);
   __syncwarp();
+  return spill;
 }
 
 __device__ __forceinline__ int sr_sp(int start, int end, int j) { return start + (end - start) * j / 6; }          // SR.cpp:360
 __device__ __forceinline__ int sr_ep(int start, int end, int j) { return start + (end - start) * (j + 1) / 6 - 1; }  // SR.cpp:361
+
+// Greedy walks of one sector (SR.cpp:371-483), warp-cooperative: 32 sorted candidates per ballot.
+// pre: marks already present on the first five points of the sector (bit b = point sp + b);
+// [lo, hi]: ring-local range this walk may mark.  Returns the forward spill of its marks beyond hi.
+__device__ __forceinline__ unsigned sr_walk_sector(int j, int r, int start, int end, int rs, const unsigned long long* __restrict__ ks,
+                                                   const unsigned char* gb, unsigned char* pk, int* __restrict__ label,
+                                                   int* __restrict__ provSharp, int* __restrict__ provLess, int* __restrict__ provFlat,
+                                                   int* __restrict__ cntSharp, int* __restrict__ cntLess, int* __restrict__ cntFlat, int lane,
+                                                   unsigned pre, int lo, int hi) {
+  const int spj = sr_sp(start, end, j), epj = sr_ep(start, end, j);
+  const int m = epj - spj + 1;
+  const int slot = r * VL_SECTORS + j;
+  unsigned spill = 0;
+  if (lane < 5 && ((pre >> lane) & 1u) && lane < m) pk[spj - rs + lane] = 1;
+  __syncwarp();
+  // ---- descending walk: sharp (<=2) then less sharp (<=20 total), SR.cpp:371-431
+  int cnt = 0, pos = m - 1;
+  while (pos >= 0 && cnt < 20) {
+    const int k = pos - lane;
+    const bool valid = k >= 0;
+    const unsigned long long key = valid ? ks[k] : 0ull;
+    const int ind = (int)(unsigned)(key & 0xffffffffull);
+    const bool big = valid && (double)__uint_as_float((unsigned)(key >> 32)) > 0.1;
+    const bool cand = big && pk[ind - rs] == 0;
+    const unsigned bc = __ballot_sync(0xffffffffu, cand);
+    if (bc == 0) {
+      const unsigned bv = __ballot_sync(0xffffffffu, valid), bb = __ballot_sync(0xffffffffu, big);
+      if (bb != bv) break;  // reached curvature <= 0.1: nothing further can qualify
+      pos -= 32;
+      continue;
+    }
+    const int first = __ffs(bc) - 1;
+    const int pind = __shfl_sync(0xffffffffu, ind, first);
+    cnt++;
+    if (lane == 0) {
+      if (cnt <= 2) { label[pind] = 2; provSharp[slot * 2 + cnt - 1] = pind; }
+      else label[pind] = 1;
+      provLess[slot * 20 + cnt - 1] = pind;
+    }
+    spill |= sr_mark(gb, pk, pind - rs, lane, lo, hi);
+    pos = pos - first - 1;
+  }
+  if (lane == 0) { cntSharp[slot] = min(cnt, 2); cntLess[slot] = cnt; }
+  // ---- ascending walk: flat (<=4; the 4th is not marked), SR.cpp:439-483
+  cnt = 0; pos = 0;
+  while (pos < m && cnt < 4) {
+    const int k = pos + lane;
+    const bool valid = k < m;
+    const unsigned long long key = valid ? ks[k] : 0ull;
+    const int ind = (int)(unsigned)(key & 0xffffffffull);
+    const bool small = valid && (double)__uint_as_float((unsigned)(key >> 32)) < 0.1;
+    const bool cand = small && pk[ind - rs] == 0;
+    const unsigned bc = __ballot_sync(0xffffffffu, cand);
+    if (bc == 0) {
+      const unsigned bv = __ballot_sync(0xffffffffu, valid), bs = __ballot_sync(0xffffffffu, small);
+      if (bs != bv) break;
+      pos += 32;
+      continue;
+    }
+    const int first = __ffs(bc) - 1;
+    const int pind = __shfl_sync(0xffffffffu, ind, first);
+    cnt++;
+    if (lane == 0) { label[pind] = -1; provFlat[slot * 4 + cnt - 1] = pind; }
+    if (cnt >= 4) break;
+    spill |= sr_mark(gb, pk, pind - rs, lane, lo, hi);
+    pos = pos + first + 1;
+  }
+  if (lane == 0) cntFlat[slot] = cnt;
+  __syncwarp();
+  return spill;
+}
 
 // One CTA per ring.  All six sectors are sorted together (batched bitonic on
 // (curvature bits, index) keys -- the canonical tie order of SURVEY Appendix B), then
@@ -319,66 +396,47 @@ __global__ void __launch_bounds__(SR_PICK_THREADS) sr_pick(const float4* __restr
   }
   __syncthreads();
   bt_sort_batched<SR_PICK_THREADS>(keys, P, VL_SECTORS);
-  if (threadIdx.x >= 32) return;
-  const int lane = threadIdx.x;
-  for (int j = 0; j < VL_SECTORS; ++j) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int minLen = INT_MAX;
+#pragma unroll
+  for (int j = 0; j < VL_SECTORS; ++j) minLen = min(minLen, sr_ep(start, end, j) - sr_sp(start, end, j) + 1);
+  if (minLen < 6) {  // tiny ring: marks may cross more than one sector boundary -- walk the sectors in order
+    if (warp != 0) return;
+    for (int j = 0; j < VL_SECTORS; ++j)
+      sr_walk_sector(j, r, start, end, rs, keys + j * P, gb, pk, label, provSharp, provLess, provFlat, cntSharp, cntLess, cntFlat, lane, 0u, 0, INT_MAX);
+    return;
+  }
+  // The sectors only interact through the <= 5 marks a pick near the end of sector j leaves on the first
+  // points of sector j+1 (SR.cpp:403-417).  Six warps walk the six sectors at once, each confined to its
+  // own range and reporting that spill as a bit mask; a pre-marked point changes a sector's walk only if
+  // the walk had picked that very point (a mark does nothing but veto a pick), so afterwards warp 0 checks
+  // the sectors in order and re-walks the few whose picks collide with the final spill of their predecessor.
+  __shared__ unsigned spillOut[VL_SECTORS];
+  if (warp < VL_SECTORS) {
+    const int j = warp;
+    const unsigned so = sr_walk_sector(j, r, start, end, rs, keys + j * P, gb, pk, label, provSharp, provLess, provFlat, cntSharp, cntLess, cntFlat, lane, 0u,
+                                       sr_sp(start, end, j) - rs, sr_ep(start, end, j) - rs);
+    if (lane == 0) spillOut[j] = so;
+  }
+  __syncthreads();
+  if (warp != 0) return;
+  for (int j = 1; j < VL_SECTORS; ++j) {
+    const unsigned in = spillOut[j - 1];
+    if (in == 0) continue;
     const int spj = sr_sp(start, end, j), epj = sr_ep(start, end, j);
-    const int m = epj - spj + 1;
-    const unsigned long long* ks = keys + j * P;
     const int slot = r * VL_SECTORS + j;
-    // ---- descending walk: sharp (<=2) then less sharp (<=20 total), SR.cpp:371-431
-    int cnt = 0, pos = m - 1;
-    while (pos >= 0 && cnt < 20) {
-      const int k = pos - lane;
-      const bool valid = k >= 0;
-      const unsigned long long key = valid ? ks[k] : 0ull;
-      const int ind = (int)(unsigned)(key & 0xffffffffull);
-      const bool big = valid && (double)__uint_as_float((unsigned)(key >> 32)) > 0.1;
-      const bool cand = big && pk[ind - rs] == 0;
-      const unsigned bc = __ballot_sync(0xffffffffu, cand);
-      if (bc == 0) {
-        const unsigned bv = __ballot_sync(0xffffffffu, valid), bb = __ballot_sync(0xffffffffu, big);
-        if (bb != bv) break;  // reached curvature <= 0.1: nothing further can qualify
-        pos -= 32;
-        continue;
-      }
-      const int first = __ffs(bc) - 1;
-      const int pind = __shfl_sync(0xffffffffu, ind, first);
-      cnt++;
-      if (lane == 0) {
-        if (cnt <= 2) { label[pind] = 2; provSharp[slot * 2 + cnt - 1] = pind; }
-        else label[pind] = 1;
-        provLess[slot * 20 + cnt - 1] = pind;
-      }
-      sr_mark(gb, pk, pind - rs, lane);
-      pos = pos - first - 1;
-    }
-    if (lane == 0) { cntSharp[slot] = min(cnt, 2); cntLess[slot] = cnt; }
-    // ---- ascending walk: flat (<=4; the 4th is not marked), SR.cpp:439-483
-    cnt = 0; pos = 0;
-    while (pos < m && cnt < 4) {
-      const int k = pos + lane;
-      const bool valid = k < m;
-      const unsigned long long key = valid ? ks[k] : 0ull;
-      const int ind = (int)(unsigned)(key & 0xffffffffull);
-      const bool small = valid && (double)__uint_as_float((unsigned)(key >> 32)) < 0.1;
-      const bool cand = small && pk[ind - rs] == 0;
-      const unsigned bc = __ballot_sync(0xffffffffu, cand);
-      if (bc == 0) {
-        const unsigned bv = __ballot_sync(0xffffffffu, valid), bs = __ballot_sync(0xffffffffu, small);
-        if (bs != bv) break;
-        pos += 32;
-        continue;
-      }
-      const int first = __ffs(bc) - 1;
-      const int pind = __shfl_sync(0xffffffffu, ind, first);
-      cnt++;
-      if (lane == 0) { label[pind] = -1; provFlat[slot * 4 + cnt - 1] = pind; }
-      if (cnt >= 4) break;
-      sr_mark(gb, pk, pind - rs, lane);
-      pos = pos + first + 1;
-    }
-    if (lane == 0) cntFlat[slot] = cnt;
+    const int nl = cntLess[slot], nfl = cntFlat[slot];
+    int pind = -1;
+    if (lane < nl) pind = provLess[slot * 20 + lane];
+    else if (lane >= 20 && lane - 20 < nfl) pind = provFlat[slot * 4 + lane - 20];
+    const bool hit = pind >= 0 && pind - spj < 5 && ((in >> (pind - spj)) & 1u);
+    if (__ballot_sync(0xffffffffu, hit) == 0) continue;  // the spill vetoes nothing this sector picked
+    if (pind >= 0) label[pind] = 0;                       // undo the speculative walk of sector j ...
+    for (int t = spj - rs + lane; t <= epj - rs; t += 32) pk[t] = 0;
+    __syncwarp();
+    const unsigned so = sr_walk_sector(j, r, start, end, rs, keys + j * P, gb, pk, label, provSharp, provLess, provFlat, cntSharp, cntLess, cntFlat, lane, in,
+                                       spj - rs, epj - rs);  // ... and repeat it with the incoming marks in place
+    if (lane == 0) spillOut[j] = so;
     __syncwarp();
   }
 }
