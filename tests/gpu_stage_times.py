@@ -29,6 +29,7 @@ ctx.set_timing(True)
 d = [torch.from_numpy(s).cuda() for s in scans]
 torch.cuda.synchronize()
 rows = []
+detail = []
 walls = []
 for k in range(N):
     t0 = time.perf_counter()
@@ -36,9 +37,13 @@ for k in range(N):
     ctx.synchronize()
     walls.append((time.perf_counter() - t0) * 1e3)
     rows.append(ctx.stage_ms())
+    detail.append(np.frombuffer(ctx.get_raw("timing.detail"), np.float32).copy())
 rows = np.array(rows)[8:]
 print("stage ms median SR/LO/LM:", np.median(rows, 0).round(3), "sum", np.median(rows.sum(1)).round(3), "wall median", np.median(walls[8:]).round(3))
 print("stage ms mean   SR/LO/LM:", rows.mean(0).round(3))
+dm = np.median(np.array(detail)[8:], 0)
+print("ms since frame start (median): SR end %.3f | LO end %.3f | sub-map build end %.3f | stacks awaited %.3f | solve 1 end %.3f | LM end %.3f" % (dm[0], dm[1], dm[3], dm[4], dm[5], dm[2]))
+print("   side streams: surf stack ready %.3f | corner stack ready %.3f | next LO grid ready %.3f" % (dm[6], dm[7], dm[8]))
 print("launches/frame", ctx.kernel_launches / N)
 allr = np.array(walls)
 print("wall ms per frame:", " ".join("%.1f" % v for v in allr))

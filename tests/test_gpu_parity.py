@@ -429,3 +429,46 @@ def test_process_frame_is_deterministic(pkg, synth, street):
         g.close()
     assert (outs[0][0] == outs[1][0]).all()
     assert outs[0][1] == outs[1][1] and outs[0][2] == outs[1][2]
+
+
+@pytest.mark.gpu
+def test_speculative_submap_equals_inline_build(pkg, op, synth, street):
+    """The sub-map of frame k+1 is gathered and cell-sorted right after frame k's map update, for the window
+    frame k used; lm_prepare lets the in-line build run instead when the window moved.  A 28 m drive (the
+    centre cube changes at x = 25 m), a mapping_skip_frame = 2 run and a run whose map offset is edited from
+    outside so that the window moves two frames later must give bit-identical poses and maps with the
+    speculation switched off (VLOAM_NO_SPECULATION); the long drive is also checked against the oracle."""
+    import os
+    def run(spec, kw, sensor, poses, check_oracle, shift_after=None):
+        if spec: os.environ.pop("VLOAM_NO_SPECULATION", None)
+        else: os.environ["VLOAM_NO_SPECULATION"] = "1"
+        try:
+            g = pkg.Context(**kw)
+        finally:
+            os.environ.pop("VLOAM_NO_SPECULATION", None)
+        o = op.Oracle(**kw) if check_oracle else None
+        out, centres = [], []
+        for k, p in enumerate(poses):
+            scan = street.scan(sensor, [p[0], p[1], 0, p[2], 0, 0], 3000 + k)
+            out.append(g.process_frame(scan).copy())
+            centres.append(tuple(g.get("lm.validInd")[:1]))
+            if o is not None:
+                o.process(scan)
+            if shift_after is not None and k == shift_after:
+                pose = g.get("lm.pose"); pose[11] += 23.0   # t_wmap_wodom: the mapper now sits 2 m from a cube face
+                g.set("lm.pose", pose)
+        maps = (g.get("lm.cornerMap"), g.get("lm.surfMap"))
+        if o is not None:
+            assert o.get("lm.cornerMap") == maps[0] and o.get("lm.surfMap") == maps[1]
+            pose_close(o.get("lm.pose")[:7], g.get("lm.pose")[:7])
+        g.close()
+        return np.array(out), maps, centres
+    drive = [(1.1 * k, 0.05 * k, 0.002 * k) for k in range(27)]
+    cases = ((KW[0], 0, drive, True, None), (dict(KW[0], mapping_skip_frame=2), 0, drive[:8], False, None), (KW[1], 1, drive[:7], False, 2))
+    for i, (kw, sensor, poses, chk, shift) in enumerate(cases):
+        pa, ma, ca = run(True, kw, sensor, poses, chk, shift)
+        pb, mb, cb = run(False, kw, sensor, poses, False, shift)
+        assert (pa == pb).all(), "poses differ with / without the speculative sub-map"
+        assert ma[0] == mb[0] and ma[1] == mb[1], "maps differ with / without the speculative sub-map"
+        if i != 1:
+            assert len(set(ca)) > 1, "the window never moved: the mismatch path was not exercised"

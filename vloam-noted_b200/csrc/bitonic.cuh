@@ -40,3 +40,72 @@ __device__ __forceinline__ void bt_sort_batched(unsigned long long* s, int P, in
     }
   }
 }
+
+
+// ---- single array in SHARED memory, tuned rounds ---------------------------------------------------------
+// Call these with a pointer the compiler can see is shared memory (derived from the __shared__ array in the
+// calling kernel, not selected at run time between shared and global): the accesses then compile to LDS / STS.
+// Strides 2 and 1 of every merge level -- and the whole k = 2, k = 4 levels -- are done on four CONSECUTIVE
+// keys held in registers (two 128-bit accesses per thread, conflict-free), strides >= 8 in pairs per barrier
+// ({i, i+h, i+j, i+j+h} is closed under strides j and h = j/2), a left-over stride 4 on its own.
+// Direction of element i at level k: ascending iff ((gbase + i) & k) == 0 (gbase: global index of s[0]).
+__device__ __forceinline__ void bt_cswap(unsigned long long& a, unsigned long long& b, bool up) {
+  if ((a > b) == up) { const unsigned long long t = a; a = b; b = t; }
+}
+
+template <int THREADS>
+__device__ __forceinline__ void bt_smem_init4(unsigned long long* s, int n) {  // levels k = 2 and k = 4
+  for (int u = threadIdx.x; u < (n >> 2); u += THREADS) {
+    ulonglong2* p = reinterpret_cast<ulonglong2*>(s + (u << 2));
+    ulonglong2 v0 = p[0], v1 = p[1];
+    bt_cswap(v0.x, v0.y, true); bt_cswap(v1.x, v1.y, false);           // k = 2: (i & 2) == 0 ascending
+    const bool up = ((u << 2) & 4) == 0;                                // k = 4 (gbase is a multiple of 4)
+    bt_cswap(v0.x, v1.x, up); bt_cswap(v0.y, v1.y, up);
+    bt_cswap(v0.x, v0.y, up); bt_cswap(v1.x, v1.y, up);
+    p[0] = v0; p[1] = v1;
+  }
+  __syncthreads();
+}
+
+template <int THREADS>
+__device__ __forceinline__ void bt_smem_level(unsigned long long* s, int n, int jtop, size_t gbase, int k) {  // k >= 8, strides jtop .. 1
+  int j = jtop;
+  while (j >= 8) {
+    const int h = j >> 1, lh = __ffs(h) - 1;
+    for (int u = threadIdx.x; u < (n >> 2); u += THREADS) {
+      const int i0 = ((u >> lh) << (lh + 2)) | (u & (h - 1));
+      const bool up = ((gbase + i0) & (size_t)k) == 0;
+      unsigned long long a = s[i0], b = s[i0 + h], c = s[i0 + j], d = s[i0 + j + h];
+      bt_cswap(a, c, up); bt_cswap(b, d, up); bt_cswap(a, b, up); bt_cswap(c, d, up);
+      s[i0] = a; s[i0 + h] = b; s[i0 + j] = c; s[i0 + j + h] = d;
+    }
+    __syncthreads();
+    j >>= 2;
+  }
+  if (j == 4) {
+    for (int u = threadIdx.x; u < (n >> 1); u += THREADS) {
+      const int i = ((u & ~3) << 1) | (u & 3);
+      const bool up = ((gbase + i) & (size_t)k) == 0;
+      unsigned long long a = s[i], b = s[i + 4];
+      bt_cswap(a, b, up);
+      s[i] = a; s[i + 4] = b;
+    }
+    __syncthreads();
+  }
+  for (int u = threadIdx.x; u < (n >> 2); u += THREADS) {  // strides 2 and 1 in registers
+    ulonglong2* p = reinterpret_cast<ulonglong2*>(s + (u << 2));
+    ulonglong2 v0 = p[0], v1 = p[1];
+    const bool up = ((gbase + (size_t)(u << 2)) & (size_t)k) == 0;
+    bt_cswap(v0.x, v1.x, up); bt_cswap(v0.y, v1.y, up);
+    bt_cswap(v0.x, v0.y, up); bt_cswap(v1.x, v1.y, up);
+    p[0] = v0; p[1] = v1;
+  }
+  __syncthreads();
+}
+
+// ascending sort of n keys (power of two >= 8) in shared memory
+template <int THREADS>
+__device__ __forceinline__ void bt_smem_sort(unsigned long long* s, int n) {
+  bt_smem_init4<THREADS>(s, n);
+  for (int k = 8; k <= n; k <<= 1) bt_smem_level<THREADS>(s, n, k >> 1, 0, k);
+}

@@ -10,6 +10,7 @@ bool vl_debug_capture(const vloam_b200_ctx* c) { return c->h_vScalars && c->h_vS
 int vl_lm_rescan_sorted(vloam_b200_ctx* c);
 int vl_solver_trace(vloam_b200_ctx* c, long long* out16);
 int vl_lo_trace(vloam_b200_ctx* c, int* out, int n);
+int vl_sr_trace(vloam_b200_ctx* c, long long* out, int n);
 
 extern "C" {
 
@@ -32,7 +33,7 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   if (!(p->line_res >= 0.05f) || !(p->plane_res >= 0.05f) || p->mapping_skip_frame < 1) return VLOAM_E_INVALID;
   VL_CUDA_CREATE(cudaSetDevice(device));
   vloam_b200_ctx* c = new vloam_b200_ctx();
-  c->prm = *p; c->device = device; c->err[0] = 0; c->launches = 0; c->timing = false; c->cur = 0;
+  c->prm = *p; c->device = device; c->err[0] = 0; c->launches = 0; c->worker = nullptr; c->timing = false; c->cur = 0;
   c->sr_counts_valid = false; c->n_in = 0; c->lo_inited = false; c->lo_frameCount = 0; c->lm_frameCount = 0; c->lm_optimized = 0; c->skip_frame = false;
   c->nKept = c->nSharp = c->nLessSharp = c->nFlat = c->nLessFlat = 0; c->nCornerLast = c->nSurfLast = 0;
   c->cornerLastPtr = nullptr; c->surfLastPtr = nullptr;
@@ -54,6 +55,7 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evMap, cudaEventDisableTiming));
   c->stacksReady = false; c->lm_reset_pending = true; c->lastSet = 0; c->loGridValid[0] = c->loGridValid[1] = false;
   for (int k = 0; k < 4; ++k) VL_CUDA_CREATE(cudaEventCreate(&c->ev[k]));
+  for (int k = 0; k < 8; ++k) { VL_CUDA_CREATE(cudaEventCreate(&c->evx[k])); VL_CUDA_CREATE(cudaEventRecord(c->evx[k], c->stream)); }
   const int R = VL_MAX_RINGS, S = VL_MAX_RINGS * VL_SECTORS;
   VL_CUDA_CREATE(cudaMalloc(&c->ringCount, sizeof(int) * R));
   VL_CUDA_CREATE(cudaMalloc(&c->ringStart, sizeof(int) * (R + 1)));
@@ -100,6 +102,7 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
 void vloam_b200_destroy(vloam_b200_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  vl_lm_shutdown(c);
   cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream3); cudaStreamSynchronize(c->stream4);
   // Device memory is released wholesale: contexts live for a whole replay (MAIN.cpp:118-124).
   void* singles[] = {c->ringCount, c->ringStart, c->srs, c->provSharp, c->provLess, c->provFlat, c->cntSharp, c->cntLess, c->cntFlat,
@@ -114,6 +117,7 @@ void vloam_b200_destroy(vloam_b200_ctx* c) {
   for (void* p : bufs) if (p) cudaFree(p);
   cudaFreeHost(c->h_srs); cudaFreeHost(c->h_los); cudaFreeHost(c->h_lms); cudaFreeHost(c->h_lmm); cudaFreeHost(c->h_vScalars);
   for (int k = 0; k < 4; ++k) cudaEventDestroy(c->ev[k]);
+  for (int k = 0; k < 8; ++k) cudaEventDestroy(c->evx[k]);
   cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream3);
   cudaEventDestroy(c->evSR); cudaEventDestroy(c->evStacks); cudaEventDestroy(c->evLast); cudaEventDestroy(c->evPose); cudaEventDestroy(c->evMap);
   cudaEventDestroy(c->evStacksC);
@@ -225,6 +229,7 @@ int vloam_b200_process_frame_device(vloam_b200_ctx* c, const float* d_xyz, int n
 }
 
 int vloam_b200_synchronize(vloam_b200_ctx* c) {
+  VL_TRY(vl_lm_join(c));
   VL_CUDA(cudaStreamSynchronize(c->stream)); VL_CUDA(cudaStreamSynchronize(c->stream2)); VL_CUDA(cudaStreamSynchronize(c->stream3));
   VL_CUDA(cudaStreamSynchronize(c->stream4));
   return VLOAM_OK;
@@ -241,6 +246,7 @@ int vloam_b200_stage_ms(vloam_b200_ctx* c, float* ms3) {
 
 // Time one named kernel: CUDA events are recorded around each of its launches on the context's stream.
 int vloam_b200_profile_kernel(vloam_b200_ctx* c, const char* name) {
+  VL_TRY(vl_lm_join(c));
   VL_CUDA(cudaStreamSynchronize(c->stream));
   if (!c->prof_created) {
     for (int k = 0; k < VL_PROF_MAX; ++k) { VL_CUDA(cudaEventCreate(&c->prof_ev[k][0])); VL_CUDA(cudaEventCreate(&c->prof_ev[k][1])); }
@@ -353,6 +359,19 @@ long vloam_b200_debug_get(vloam_b200_ctx* c, const char* name, void* out, long c
       if (kind == "cok") return put_dev(c, c->dbgKnnOk[k][0].p, (size_t)Qc * 4, out, cap);
       if (kind == "sok") return put_dev(c, c->dbgKnnOk[k][1].p, (size_t)Qs * 4, out, cap);
     }
+  }
+  if (n == "timing.detail") {  // timing mode: ms since the start of the frame's scan registration
+    // {SR end, LO end, LM end, sub-map build end, stacks awaited + counts set, first solve end, surf stack ready, corner stack ready, next LO grid ready}
+    float v[9] = {0};
+    if (!c->timing) { snprintf(c->err, sizeof c->err, "timing is off"); return VLOAM_E_INVALID; }
+    for (int k = 0; k < 3; ++k) cudaEventElapsedTime(&v[k], c->ev[0], c->ev[k + 1]);
+    for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&v[3 + k], c->ev[0], c->evx[k]);
+    return put_host(v, sizeof v, out, cap);
+  }
+  if (n == "sr.trace") {  // clock64 phase stamps of the last sr_pick (CTAs 0..127) and sr_ring_voxel (128..255) launches
+    static long long v[256 * 8];
+    if (vl_sr_trace(c, v, 256 * 8) != VLOAM_OK) return VLOAM_E_CUDA;
+    return put_host(v, sizeof v, out, cap);
   }
   if (n == "lo.trace") {  // per query warp of the last grid association: {cycles, flags}
     static int v[2 * 8192];

@@ -84,6 +84,13 @@ struct DBuf {  // growable device buffer
   size_t cap = 0;  // elements
 };
 
+// Launch helpers take their stream from here: the map update of a frame is issued by a helper thread
+// (laser_mapping.cu) while the calling thread already queues the next sweep, so "the current stream" is a
+// per-thread notion.  Non-null: this thread's launches go there instead of c->stream.
+extern thread_local cudaStream_t vl_tls_stream;
+#define VL_STREAM(c) (vl_tls_stream ? vl_tls_stream : (c)->stream)
+struct VlWorker;
+
 struct vloam_b200_ctx {
   vloam_b200_params prm;
   int device;
@@ -100,10 +107,12 @@ struct vloam_b200_ctx {
   bool stacksReady;
   bool lm_reset_pending;      // LaserMapping::reset was called since the last solveMapping
   char err[512];
-  long long launches;
+  long long launches;         // updated with __atomic_fetch_add (two issuing threads)
+  VlWorker* worker;           // helper thread that issues the map update (created on first use)
   int num_sms;
   bool timing;
   cudaEvent_t ev[4];
+  cudaEvent_t evx[8];  // timing mode only: finer marks (see "timing.detail" in capi.cu)
   float stage_ms[3];
 
   // ---- scan registration
@@ -215,18 +224,18 @@ struct GridParams {
 #define VL_LAUNCH(kernel, grid, block, smem, ...)                                              \
   do {                                                                                         \
     const bool prof_ = c->prof_name[0] && vl_prof_match(c, #kernel) && c->prof_n < VL_PROF_MAX; \
-    if (prof_) cudaEventRecord(c->prof_ev[c->prof_n][0], c->stream);                           \
+    if (prof_) cudaEventRecord(c->prof_ev[c->prof_n][0], VL_STREAM(c));                        \
     cudaLaunchConfig_t cfg_ = {};                                                              \
-    cfg_.gridDim = dim3(grid); cfg_.blockDim = dim3(block); cfg_.dynamicSmemBytes = (smem); cfg_.stream = c->stream; \
+    cfg_.gridDim = dim3(grid); cfg_.blockDim = dim3(block); cfg_.dynamicSmemBytes = (smem); cfg_.stream = VL_STREAM(c); \
     cudaLaunchAttribute at_[1];                                                                \
     at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                            \
     at_[0].val.programmaticStreamSerializationAllowed = 1;                                     \
     cfg_.attrs = at_; cfg_.numAttrs = 1;                                                       \
     cudaLaunchKernelEx(&cfg_, kernel, __VA_ARGS__);                                            \
-    if (prof_) { cudaEventRecord(c->prof_ev[c->prof_n][1], c->stream); c->prof_kname[c->prof_n] = #kernel; c->prof_kbytes[c->prof_n] = c->prof_next_bytes; c->prof_kstream[c->prof_n] = c->stream; \
+    if (prof_) { cudaEventRecord(c->prof_ev[c->prof_n][1], VL_STREAM(c)); c->prof_kname[c->prof_n] = #kernel; c->prof_kbytes[c->prof_n] = c->prof_next_bytes; c->prof_kstream[c->prof_n] = VL_STREAM(c); \
                  c->prof_n++; c->prof_bytes += c->prof_next_bytes; } \
     c->prof_next_bytes = 0;                                                                    \
-    c->launches++;                                                                             \
+    __atomic_fetch_add(&c->launches, 1LL, __ATOMIC_RELAXED);                                   \
   } while (0)
 
 // algorithmic bytes of the next launch (DESIGN.md roofline table), consumed by VL_LAUNCH when that kernel is profiled
@@ -252,8 +261,8 @@ static inline int vl_reserve(vloam_b200_ctx* c, DBuf<T>& b, size_t n, bool keep 
   static const bool trace = getenv("VLOAM_TRACE_ALLOC") != nullptr;
   if (trace) fprintf(stderr, "[vloam_b200] grow buffer to %zu x %zu B (frame %d)\n", ncap, sizeof(T), c->lo_frameCount);
   VL_CUDA(cudaMalloc(&np, ncap * sizeof(T)));
-  if (keep && b.p && b.cap) VL_CUDA(cudaMemcpyAsync(np, b.p, b.cap * sizeof(T), cudaMemcpyDeviceToDevice, c->stream));
-  if (b.p) { VL_CUDA(cudaStreamSynchronize(c->stream)); VL_CUDA(cudaFree(b.p)); }
+  if (keep && b.p && b.cap) VL_CUDA(cudaMemcpyAsync(np, b.p, b.cap * sizeof(T), cudaMemcpyDeviceToDevice, VL_STREAM(c)));
+  if (b.p) { VL_CUDA(cudaStreamSynchronize(VL_STREAM(c))); VL_CUDA(cudaFree(b.p)); }
   b.p = np; b.cap = ncap;
   return VLOAM_OK;
 }
@@ -269,10 +278,12 @@ int vl_lo_build_last(vloam_b200_ctx* c, int set, const float4* corner, int nc, c
 int vl_lm_run(vloam_b200_ctx* c);
 int vl_lm_enqueue_stacks(vloam_b200_ctx* c, const float4* corner, int nc, const float4* surf, int ns);
 int vl_lm_init(vloam_b200_ctx* c);
+int vl_lm_join(vloam_b200_ctx* c);      // wait until the helper thread has issued the pending map update; returns its status
+void vl_lm_shutdown(vloam_b200_ctx* c);  // stop the helper thread
 int vl_lm_export_map(vloam_b200_ctx* c, int which, void* out, long cap, long* bytes);
 int vl_lm_import_map(vloam_b200_ctx* c, int which, const void* data, long bytes);
 
-int vl_scan_exclusive(vloam_b200_ctx* c, const int* in, int n, int* tileSum, int* out);  // laser_mapping.cu
+int vl_scan_exclusive(vloam_b200_ctx* c, const int* in, int n, int* tileSum, int* out, const int* d_skip = nullptr);  // laser_mapping.cu; d_skip: device flag, non-zero = do nothing
 // sort / voxel primitives (voxel_grid.cu)
 int vl_sort_u64(vloam_b200_ctx* c, unsigned long long* d_keys, int n_pow2);
 // pcl::VoxelGrid of d_in[0..n) -> d_out, count written to *d_count (device int); n is a host bound,

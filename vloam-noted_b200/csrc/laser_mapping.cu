@@ -23,6 +23,96 @@
 #include <float.h>
 #include <math_constants.h>
 #include "common.cuh"
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+
+// ---- helper thread ------------------------------------------------------------------------------------
+// After sync point S2 the caller has its pose; what remains of the frame is issuing ~25 launches of the map
+// update and of the next frame's speculative sub-map on stream3 -- ~100 us of host time during which neither
+// the caller nor the next sweep's scan registration made progress.  One helper thread per context issues
+// them instead.  It spins for a millisecond after each task (a replay hands it work every ~0.4 ms) and
+// sleeps on a condition variable otherwise (a live 10 Hz feed must not burn a core).
+thread_local cudaStream_t vl_tls_stream = nullptr;
+
+struct VlWorker {
+  std::thread th;
+  std::mutex m;
+  std::condition_variable cv;
+  std::function<int()> task;
+  std::atomic<int> state{0};   // 0 idle, 1 task posted, 2 running
+  std::atomic<bool> sleeping{false};
+  bool quit = false;
+  int rc = VLOAM_OK;
+  int device = 0;
+};
+
+static void lm_worker_main(VlWorker* w) {
+  cudaSetDevice(w->device);
+  for (;;) {
+    const auto t0 = std::chrono::steady_clock::now();
+    while (w->state.load(std::memory_order_acquire) != 1) {
+      if (std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(1)) {
+        std::unique_lock<std::mutex> lk(w->m);
+        w->sleeping.store(true);
+        w->cv.wait(lk, [&] { return w->state.load(std::memory_order_acquire) == 1 || w->quit; });
+        w->sleeping.store(false);
+        if (w->quit) return;
+        break;
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    w->state.store(2, std::memory_order_relaxed);
+    w->rc = w->task();
+    w->state.store(0, std::memory_order_release);
+  }
+}
+
+int vl_lm_join(vloam_b200_ctx* c) {
+  VlWorker* w = c->worker;
+  if (!w) return VLOAM_OK;
+  while (w->state.load(std::memory_order_acquire) != 0) {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+  const int rc = w->rc;
+  w->rc = VLOAM_OK;
+  return rc;
+}
+
+void vl_lm_shutdown(vloam_b200_ctx* c) {
+  VlWorker* w = c->worker;
+  if (!w) return;
+  vl_lm_join(c);
+  { std::lock_guard<std::mutex> lk(w->m); w->quit = true; }
+  w->cv.notify_all();
+  // a spinning worker notices quit only through the condition variable path: post nothing, it falls asleep within 1 ms
+  w->th.join();
+  delete w;
+  c->worker = nullptr;
+}
+
+static int lm_submit(vloam_b200_ctx* c, std::function<int()> f) {
+  if (!c->worker) {
+    VlWorker* w = new VlWorker();
+    w->device = c->device;
+    w->th = std::thread(lm_worker_main, w);
+    c->worker = w;
+  }
+  VlWorker* w = c->worker;
+  VL_TRY(vl_lm_join(c));
+  w->task = std::move(f);
+  w->state.store(1, std::memory_order_release);
+  if (w->sleeping.load()) { std::lock_guard<std::mutex> lk(w->m); w->cv.notify_all(); }
+  return VLOAM_OK;
+}
+
 
 #define LM_CELL 2.0f
 #define LM_GX 125
@@ -44,6 +134,18 @@ struct RfWork {
   int nq;                               // Qc + Qs when the optimisation runs, else 0
   float gridOrigin[3];
   int Qc, Qs;
+};
+
+// Everything the sub-map gather and the search grid need to know about one valid-cube window.  Two
+// copies live on the device: `real`, written by lm_prepare from this frame's pose, and `spec`, written
+// right after the previous frame's map update for the window that frame used (lm_spec_prepare).
+struct LmSub {
+  int validNum, Mc, Ms;
+  int cI, cJ, cK, cenW, cenH, cenD;     // window centre and laserCloudCen* it was built for
+  int ok;                               // spec: the descriptor (and the structures built from it) is complete
+  float gridOrigin[3];
+  int validInd[VL_MAX_VALID];
+  int gatherOff[2][VL_MAX_VALID + 1];
 };
 
 __device__ __forceinline__ int lm_cube_of(float v, int cen) {  // LM.cpp:747-756
@@ -89,13 +191,16 @@ __device__ __forceinline__ int lm_scan256(int v, int* buf, int* total) {
 
 // ---- LaserMapping::input (LM.cpp:178-209) + centre cube / roll / valid list (LM.cpp:228-466)
 __global__ void __launch_bounds__(1024) lm_prepare(LmScalars* __restrict__ s, const LoScalars* __restrict__ lo, MapCubeTable* __restrict__ tc,
-                                                   MapCubeTable* __restrict__ ts, RfWork* __restrict__ w, int skip, int resetValid) {
+                                                   MapCubeTable* __restrict__ ts, RfWork* __restrict__ w, int skip, int resetValid,
+                                                   LmSub* __restrict__ real, const LmSub* __restrict__ spec, int specQueued, int* __restrict__ specOK) {
   VL_PDL_WAIT();
 
   __shared__ int shift[3];
   __shared__ int center[3];
+  __shared__ int sFresh;
   if (threadIdx.x == 0) {
     if (resetValid) s->validNum = 0;  // LaserMapping::reset (LM.cpp:132-136)
+    sFresh = s->validNum == 0;
     for (int k = 0; k < 4; ++k) s->q_wodom[k] = lo->q_w[k];
     for (int k = 0; k < 3; ++k) s->t_wodom[k] = lo->t_w[k];
     double r[3];
@@ -129,7 +234,7 @@ __global__ void __launch_bounds__(1024) lm_prepare(LmScalars* __restrict__ s, co
     center[0] = cI; center[1] = cJ; center[2] = cK;
   }
   __syncthreads();
-  if (skip) return;
+  if (skip) return;  // (a skipped frame neither consumes nor invalidates the speculative sub-map)
   const int sI = shift[0], sJ = shift[1], sK = shift[2];
   if (sI != 0 || sJ != 0 || sK != 0) {
     // new[i,j,k] = old[i-sI, j-sJ, k-sK]; entries whose source wrapped are the cleared slabs (they
@@ -180,6 +285,8 @@ __global__ void __launch_bounds__(1024) lm_prepare(LmScalars* __restrict__ s, co
     w->gridOrigin[0] = (float)(50 * (cI - 2 - s->cenW) - 25);
     w->gridOrigin[1] = (float)(50 * (cJ - 2 - s->cenH) - 25);
     w->gridOrigin[2] = (float)(50 * (cK - 1 - s->cenD) - 25);
+    real->validNum = nv; real->cI = cI; real->cJ = cJ; real->cK = cK; real->cenW = s->cenW; real->cenH = s->cenH; real->cenD = s->cenD;
+    for (int k = 0; k < 3; ++k) real->gridOrigin[k] = w->gridOrigin[k];
   }
   __syncthreads();
   const int nv = snv;
@@ -198,8 +305,18 @@ __global__ void __launch_bounds__(1024) lm_prepare(LmScalars* __restrict__ s, co
   __shared__ int sMc;
   if (t == VL_MAX_VALID) sMc = offCnt;                        // exclusive offset of the first surf segment == Mc
   __syncthreads();
-  if (t < LM_NSEG) w->gatherOff[kind][slot] = kind ? offCnt - sMc : offCnt;
-  if (t == 0) { s->Mc = sMc; s->Ms = total - sMc; w->gatherOff[0][VL_MAX_VALID] = sMc; w->gatherOff[1][VL_MAX_VALID] = total - sMc; }
+  if (t < LM_NSEG) { w->gatherOff[kind][slot] = kind ? offCnt - sMc : offCnt; real->gatherOff[kind][slot] = kind ? offCnt - sMc : offCnt; }
+  if (t < VL_MAX_VALID) real->validInd[t] = t < nv ? s->validInd[t] : 0;
+  if (t == 0) {
+    s->Mc = sMc; s->Ms = total - sMc; w->gatherOff[0][VL_MAX_VALID] = sMc; w->gatherOff[1][VL_MAX_VALID] = total - sMc;
+    real->Mc = sMc; real->Ms = total - sMc; real->gatherOff[0][VL_MAX_VALID] = sMc; real->gatherOff[1][VL_MAX_VALID] = total - sMc; real->ok = 1;
+    // The sub-map gathered and cell-sorted after the previous map update is this frame's sub-map when the
+    // window did not move: same centre cube, no roll, a freshly reset valid list.  The cube tables have not
+    // changed since, so equal windows mean equal offsets; the sizes are compared as a last line of defence.
+    *specOK = (specQueued && spec->ok && sFresh && shift[0] == 0 && shift[1] == 0 && shift[2] == 0 && spec->cI == center[0] &&
+               spec->cJ == center[1] && spec->cK == center[2] && spec->cenW == s->cenW && spec->cenH == s->cenH && spec->cenD == s->cenD &&
+               spec->validNum == nv && spec->Mc == sMc && spec->Ms == total - sMc) ? 1 : 0;
+  }
   int tailTotal = 0, prefTotal = 0;
   const int tl = cnt - srt;
   const int offTail = lm_scan256(tl, sbuf, &tailTotal);
@@ -211,21 +328,67 @@ __global__ void __launch_bounds__(1024) lm_prepare(LmScalars* __restrict__ s, co
   if (t == 0) { w->tailOff[LM_NSEG] = tailTotal; w->prefOff[LM_NSEG] = prefTotal; s->tailC = sTailC; s->tailS = tailTotal - sTailC; }
 }
 
-// LM.cpp:476-485: concatenate the valid cubes (loop order of LM.cpp:448-452) into the sub-map clouds
-__global__ void __launch_bounds__(256) lm_gather(const LmScalars* __restrict__ s, const RfWork* __restrict__ w,
+// The window the next frame will most likely use is the one this frame used (a cube is 50 m wide): right
+// after the map update, on the update's stream, its descriptor is rebuilt from the updated cube tables.
+__global__ void __launch_bounds__(256) lm_spec_prepare(const LmSub* __restrict__ last, const MapCubeTable* __restrict__ tc,
+                                                       const MapCubeTable* __restrict__ ts, LmSub* __restrict__ spec) {
+  VL_PDL_WAIT();
+
+  __shared__ int sbuf[256];
+  __shared__ int snv;
+  if (threadIdx.x == 0) {
+    const int cI = last->cI, cJ = last->cJ, cK = last->cK;
+    int nv = 0;
+    for (int i = cI - 2; i <= cI + 2; i++)  // LM.cpp:448-466, on a freshly reset list
+      for (int j = cJ - 2; j <= cJ + 2; j++)
+        for (int k = cK - 1; k <= cK + 1; k++)
+          if (i >= 0 && i < VL_CUBE_W && j >= 0 && j < VL_CUBE_H && k >= 0 && k < VL_CUBE_D && nv < VL_MAX_VALID)
+            spec->validInd[nv++] = i + VL_CUBE_W * j + VL_CUBE_W * VL_CUBE_H * k;
+    spec->validNum = nv; snv = nv;
+    spec->cI = cI; spec->cJ = cJ; spec->cK = cK; spec->cenW = last->cenW; spec->cenH = last->cenH; spec->cenD = last->cenD;
+    spec->gridOrigin[0] = (float)(50 * (cI - 2 - last->cenW) - 25);
+    spec->gridOrigin[1] = (float)(50 * (cJ - 2 - last->cenH) - 25);
+    spec->gridOrigin[2] = (float)(50 * (cK - 1 - last->cenD) - 25);
+  }
+  __syncthreads();
+  const int nv = snv, t = threadIdx.x;
+  const int kind = t / VL_MAX_VALID, slot = t % VL_MAX_VALID;
+  int cnt = 0;
+  if (t < LM_NSEG && slot < nv) cnt = (kind ? ts : tc)->count[spec->validInd[slot]];
+  int total = 0;
+  const int offCnt = lm_scan256(cnt, sbuf, &total);
+  __shared__ int sMc;
+  if (t == VL_MAX_VALID) sMc = offCnt;
+  __syncthreads();
+  if (t < LM_NSEG) spec->gatherOff[kind][slot] = kind ? offCnt - sMc : offCnt;
+  if (t == 0) { spec->Mc = sMc; spec->Ms = total - sMc; spec->gatherOff[0][VL_MAX_VALID] = sMc; spec->gatherOff[1][VL_MAX_VALID] = total - sMc; spec->ok = 1; }
+}
+
+// zero the two cell-counter arrays of the search grid (a kernel, not a memset, so that it can be skipped)
+__global__ void __launch_bounds__(256) lm_grid_zero(int* __restrict__ a, int* __restrict__ b, int n, const int* __restrict__ skip) {
+  VL_PDL_WAIT();
+
+  if (skip && *skip) return;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) { a[g] = 0; b[g] = 0; }
+}
+
+// LM.cpp:476-485: concatenate the valid cubes (loop order of LM.cpp:448-452) into the sub-map clouds.
+// skip (may be null): device flag "the speculative build already produced exactly this" -> nothing to do.
+__global__ void __launch_bounds__(256) lm_gather(const LmSub* __restrict__ sub, const int* __restrict__ skip,
                                                  const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts,
                                                  const float4* __restrict__ poolC, const float4* __restrict__ poolS,
                                                  float4* __restrict__ outC, float4* __restrict__ outS) {
   VL_PDL_WAIT();
 
-  const int nv = s->validNum, mc = s->Mc, total = s->Mc + s->Ms;
+  if (skip && *skip) return;
+  const int nv = sub->validNum, mc = sub->Mc, total = sub->Mc + sub->Ms;
   for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
     const int kind = g >= mc;
     const int e = kind ? g - mc : g;
-    const int* off = w->gatherOff[kind];
+    const int* off = sub->gatherOff[kind];
     int lo = 0, hi = nv;
     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid] <= e) lo = mid; else hi = mid; }
-    const int cb = s->validInd[lo];
+    const int cb = sub->validInd[lo];
     if (kind) outS[e] = poolS[ts->start[cb] + (e - off[lo])];
     else outC[e] = poolC[tc->start[cb] + (e - off[lo])];
   }
@@ -236,13 +399,14 @@ __device__ __forceinline__ int lm_cell_coord(float v, float o, int n) {
   const int cidx = (int)floorf(__fmul_rn(__fsub_rn(v, o), 1.0f / LM_CELL));
   return min(max(cidx, 0), n - 1);
 }
-__global__ void __launch_bounds__(256) lm_grid_count(const LmScalars* __restrict__ s, const RfWork* __restrict__ w,
+__global__ void __launch_bounds__(256) lm_grid_count(const LmSub* __restrict__ sub, const int* __restrict__ skip,
                                                      const float4* __restrict__ mapC, const float4* __restrict__ mapS,
                                                      int* __restrict__ cellCount, int* __restrict__ cellOfPoint) {
   VL_PDL_WAIT();
 
-  const int mc = s->Mc, total = s->Mc + s->Ms;
-  const float ox = w->gridOrigin[0], oy = w->gridOrigin[1], oz = w->gridOrigin[2];
+  if (skip && *skip) return;
+  const int mc = sub->Mc, total = sub->Mc + sub->Ms;
+  const float ox = sub->gridOrigin[0], oy = sub->gridOrigin[1], oz = sub->gridOrigin[2];
   for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
     const int kind = g >= mc;
     const float4 p = kind ? mapS[g - mc] : mapC[g];
@@ -252,9 +416,10 @@ __global__ void __launch_bounds__(256) lm_grid_count(const LmScalars* __restrict
   }
 }
 // exclusive scan over 2*LM_NCELL counts: tile sums (1024 per block) -> scan of tile sums -> apply
-__global__ void __launch_bounds__(256) lm_scan_tiles(const int* __restrict__ in, int n, int* __restrict__ tileSum) {
+__global__ void __launch_bounds__(256) lm_scan_tiles(const int* __restrict__ in, int n, int* __restrict__ tileSum, const int* __restrict__ skip) {
   VL_PDL_WAIT();
 
+  if (skip && *skip) return;
   int acc = 0;
   const int base = blockIdx.x * 1024;
   for (int q = 0; q < 4; ++q) { const int t = base + q * 256 + threadIdx.x; if (t < n) acc += in[t]; }
@@ -264,9 +429,10 @@ __global__ void __launch_bounds__(256) lm_scan_tiles(const int* __restrict__ in,
   __syncthreads();
   if (threadIdx.x == 0) { int v = 0; for (int k = 0; k < 8; ++k) v += ws[k]; tileSum[blockIdx.x] = v; }
 }
-__global__ void __launch_bounds__(1024) lm_scan_sums(int* __restrict__ tileSum, int nTiles) {
+__global__ void __launch_bounds__(1024) lm_scan_sums(int* __restrict__ tileSum, int nTiles, const int* __restrict__ skip) {
   VL_PDL_WAIT();
 
+  if (skip && *skip) return;
   __shared__ int buf[1024];
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
@@ -288,9 +454,11 @@ __global__ void __launch_bounds__(1024) lm_scan_sums(int* __restrict__ tileSum, 
     __syncthreads();
   }
 }
-__global__ void __launch_bounds__(256) lm_scan_apply(const int* __restrict__ in, int n, const int* __restrict__ tileSum, int* __restrict__ out) {
+__global__ void __launch_bounds__(256) lm_scan_apply(const int* __restrict__ in, int n, const int* __restrict__ tileSum, int* __restrict__ out,
+                                                     const int* __restrict__ skip) {
   VL_PDL_WAIT();
 
+  if (skip && *skip) return;
   __shared__ int ws[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int running = tileSum[blockIdx.x];
@@ -310,23 +478,24 @@ __global__ void __launch_bounds__(256) lm_scan_apply(const int* __restrict__ in,
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = running;  // total
 }
 // out[0..n] = exclusive scan of in[0..n) (out[n] = total); tileSum needs ceil(n/1024)+1 ints
-int vl_scan_exclusive(vloam_b200_ctx* c, const int* in, int n, int* tileSum, int* out) {
+int vl_scan_exclusive(vloam_b200_ctx* c, const int* in, int n, int* tileSum, int* out, const int* d_skip) {
   const int nTiles = vl_div_up(n, 1024);
   VL_BYTES(4.0 * n);
-  VL_LAUNCH(lm_scan_tiles, nTiles, 256, 0, in, n, tileSum);
-  VL_LAUNCH(lm_scan_sums, 1, 1024, 0, tileSum, nTiles);
+  VL_LAUNCH(lm_scan_tiles, nTiles, 256, 0, in, n, tileSum, d_skip);
+  VL_LAUNCH(lm_scan_sums, 1, 1024, 0, tileSum, nTiles, d_skip);
   VL_BYTES(8.0 * n);
-  VL_LAUNCH(lm_scan_apply, nTiles, 256, 0, in, n, tileSum, out);
+  VL_LAUNCH(lm_scan_apply, nTiles, 256, 0, in, n, tileSum, out, d_skip);
   return VLOAM_OK;
 }
 
-__global__ void __launch_bounds__(256) lm_grid_fill(const LmScalars* __restrict__ s, const float4* __restrict__ mapC,
+__global__ void __launch_bounds__(256) lm_grid_fill(const LmSub* __restrict__ sub, const int* __restrict__ skip, const float4* __restrict__ mapC,
                                                     const float4* __restrict__ mapS, const int* __restrict__ cellOfPoint,
                                                     const int* __restrict__ cellStart, int* __restrict__ cellFill,
                                                     float4* __restrict__ sortedPts) {
   VL_PDL_WAIT();
 
-  const int mc = s->Mc, total = s->Mc + s->Ms;
+  if (skip && *skip) return;
+  const int mc = sub->Mc, total = sub->Mc + sub->Ms;
   for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
     const int kind = g >= mc;
     const int id = kind ? g - mc : g;  // canonical index inside its own sub-map cloud
@@ -961,6 +1130,10 @@ struct LmDevice {  // extra device state owned by this file
   DBuf<int> unmatched;
   int* dQ;          // two device ints: Qc, Qs from the voxel filters
   long long hMapUpperC, hMapUpperS;  // host upper bounds on the total map size
+  LmSub* subReal; LmSub* subSpec;    // sub-map window descriptors (this frame's / the speculative one)
+  int* specOK;                       // device flag written by lm_prepare: the speculative sub-map is this frame's
+  bool specQueued;                   // host: a speculative build was queued after the last map update and nothing touched the map since
+  bool specEnabled;
 };
 static LmDevice* lmdev(vloam_b200_ctx* c) { return reinterpret_cast<LmDevice*>(c->gridPrm); }
 
@@ -974,6 +1147,11 @@ int vl_lm_init(vloam_b200_ctx* c) {
   VL_CUDA(cudaMalloc(&d->cellFill, sizeof(int) * (2 * LM_NCELL + 1)));
   VL_CUDA(cudaMalloc(&d->tileSum, sizeof(int) * (vl_div_up(2 * LM_NCELL, 1024) + 1)));
   VL_CUDA(cudaMalloc(&d->dQ, sizeof(int) * 2));
+  VL_CUDA(cudaMalloc(&d->subReal, sizeof(LmSub))); VL_CUDA(cudaMemset(d->subReal, 0, sizeof(LmSub)));
+  VL_CUDA(cudaMalloc(&d->subSpec, sizeof(LmSub))); VL_CUDA(cudaMemset(d->subSpec, 0, sizeof(LmSub)));
+  VL_CUDA(cudaMalloc(&d->specOK, sizeof(int))); VL_CUDA(cudaMemset(d->specOK, 0, sizeof(int)));
+  d->specQueued = false;
+  d->specEnabled = getenv("VLOAM_NO_SPECULATION") == nullptr;
   d->hMapUpperC = d->hMapUpperS = 0;
   VL_TRY(vl_reserve(c, c->poolC, LM_POOL_C));
   VL_TRY(vl_reserve(c, c->poolS, LM_POOL_S));
@@ -995,16 +1173,19 @@ extern bool vl_debug_capture(const vloam_b200_ctx* c);
 // point and they run underneath the odometry kernels; solveMapping waits on evStacks.
 int vl_lm_enqueue_stacks(vloam_b200_ctx* c, const float4* corner, int nc, const float4* surf, int ns) {
   LmDevice* d = lmdev(c);
+  VL_TRY(vl_lm_join(c));  // evMap of the previous frame must have been recorded before it is waited on below
   cudaStream_t main = c->stream;
   // surf filter on stream2 (scratch lane 0), corner filter beside it on stream4 (scratch lane 1)
   c->stream = c->stream2;
   cudaStreamWaitEvent(c->stream2, c->evMap, 0);  // the previous frame's map update still reads the previous stacks
   int r = vl_reserve(c, c->stackS, (size_t)max(ns, 1));
   if (r == VLOAM_OK) r = vl_voxel_grid_device(c, surf, ns, nullptr, c->prm.plane_res, c->stackS.p, d->dQ + 1, 0);
+  if (c->timing) cudaEventRecord(c->evx[3], c->stream2);
   c->stream = c->stream4;
   cudaStreamWaitEvent(c->stream4, c->evMap, 0);
   if (r == VLOAM_OK) r = vl_reserve(c, c->stackC, (size_t)max(nc, 1));
   if (r == VLOAM_OK) r = vl_voxel_grid_device(c, corner, nc, nullptr, c->prm.line_res, c->stackC.p, d->dQ, 1);
+  if (c->timing) cudaEventRecord(c->evx[4], c->stream4);
   c->stream = main;
   if (r != VLOAM_OK) return r;
   VL_CUDA(cudaEventRecord(c->evStacks, c->stream2));
@@ -1013,18 +1194,35 @@ int vl_lm_enqueue_stacks(vloam_b200_ctx* c, const float4* corner, int nc, const 
   return VLOAM_OK;
 }
 
+// search grid over the gathered sub-map (LM.cpp:519-520's two KD-tree builds): counting sort into 2 m cells
+static int lm_build_grid(vloam_b200_ctx* c, LmDevice* d, const LmSub* sub, const int* d_skip, long long totalBound) {
+  const int nCells = 2 * LM_NCELL;
+  const int gsGrid = c->num_sms * 8;
+  VL_BYTES(8.0 * (nCells + 1));
+  VL_LAUNCH(lm_grid_zero, gsGrid, 256, 0, d->cellCount, d->cellFill, nCells + 1, d_skip);
+  VL_BYTES(24.0 * (double)totalBound);  // read point, write cell id, atomic on the cell counter
+  VL_LAUNCH(lm_grid_count, gsGrid, 256, 0, sub, d_skip, c->fromMapC.p, c->fromMapS.p, d->cellCount, d->cellOfPoint.p);
+  VL_TRY(vl_scan_exclusive(c, d->cellCount, nCells, d->tileSum, d->cellStart, d_skip));
+  VL_BYTES(44.0 * (double)totalBound);  // read point + cell id + cell start, atomic, write sorted point
+  VL_LAUNCH(lm_grid_fill, gsGrid, 256, 0, sub, d_skip, c->fromMapC.p, c->fromMapS.p, d->cellOfPoint.p, d->cellStart, d->cellFill, d->sortedPts.p);
+  return VLOAM_OK;
+}
+
 int vl_lm_run(vloam_b200_ctx* c) {
   LmDevice* d = lmdev(c);
+  VL_TRY(vl_lm_join(c));  // the previous frame's map update has been issued (evMap recorded, host bounds updated)
   const int skip = c->skip_frame ? 1 : 0;
   VL_CUDA(cudaStreamWaitEvent(c->stream, c->evMap, 0));  // the previous frame's map update (stream3) must be complete
-  VL_LAUNCH(lm_prepare, 1, 1024, 0, c->lmm, c->los, c->cubeC, c->cubeS, d->work, skip, c->lm_reset_pending ? 1 : 0);
+  VL_LAUNCH(lm_prepare, 1, 1024, 0, c->lmm, c->los, c->cubeC, c->cubeS, d->work, skip, c->lm_reset_pending ? 1 : 0, d->subReal, d->subSpec,
+            d->specQueued ? 1 : 0, d->specOK);
   c->lm_reset_pending = false;
   if (skip) { VL_CUDA(cudaGetLastError()); return VLOAM_OK; }
   const int gsGrid = c->num_sms * 8;
   VL_TRY(vl_reserve(c, c->fromMapC, (size_t)max(d->hMapUpperC, 1LL), false, (size_t)d->hMapUpperC / 2 + (1 << 20)));
   VL_TRY(vl_reserve(c, c->fromMapS, (size_t)max(d->hMapUpperS, 1LL), false, (size_t)d->hMapUpperS / 2 + (1 << 20)));
   VL_BYTES(32.0 * (double)(d->hMapUpperC + d->hMapUpperS));  // upper bound until the S2 sync; refined below
-  VL_LAUNCH(lm_gather, gsGrid, 256, 0, c->lmm, d->work, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, c->fromMapC.p, c->fromMapS.p);
+  // Every kernel of the sub-map build returns at once when lm_prepare found the speculative build valid.
+  VL_LAUNCH(lm_gather, gsGrid, 256, 0, d->subReal, d->specOK, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, c->fromMapC.p, c->fromMapS.p);
   if (!c->stacksReady) {  // laser_mapping called without this frame's laser_odometry having queued them
     VL_CUDA(cudaStreamSynchronize(c->stream));
     VL_TRY(vl_lm_enqueue_stacks(c, c->cornerLastPtr, c->nCornerLast, c->surfLastPtr, c->nSurfLast));
@@ -1038,20 +1236,15 @@ int vl_lm_run(vloam_b200_ctx* c) {
   const long long totalBound = d->hMapUpperC + d->hMapUpperS;
   const int nqBound = max(c->nCornerLast + c->nSurfLast, 1);  // a voxel filter never grows a cloud
   {
-    const int nCells = 2 * LM_NCELL;
     VL_TRY(vl_reserve(c, d->cellOfPoint, (size_t)max(totalBound, 1LL), false, (size_t)totalBound / 2 + (1 << 20)));
     VL_TRY(vl_reserve(c, d->sortedPts, (size_t)max(totalBound, 1LL), false, (size_t)totalBound / 2 + (1 << 20)));
-    VL_CUDA(cudaMemsetAsync(d->cellCount, 0, sizeof(int) * (nCells + 1), c->stream));
-    VL_CUDA(cudaMemsetAsync(d->cellFill, 0, sizeof(int) * (nCells + 1), c->stream));
-    VL_BYTES(24.0 * (double)totalBound);  // read point, write cell id, atomic on the cell counter
-    VL_LAUNCH(lm_grid_count, gsGrid, 256, 0, c->lmm, d->work, c->fromMapC.p, c->fromMapS.p, d->cellCount, d->cellOfPoint.p);
-    VL_TRY(vl_scan_exclusive(c, d->cellCount, nCells, d->tileSum, d->cellStart));
-    VL_BYTES(44.0 * (double)totalBound);  // read point + cell id + cell start, atomic, write sorted point
-    VL_LAUNCH(lm_grid_fill, gsGrid, 256, 0, c->lmm, c->fromMapC.p, c->fromMapS.p, d->cellOfPoint.p, d->cellStart, d->cellFill, d->sortedPts.p);
+    VL_TRY(lm_build_grid(c, d, d->subReal, d->specOK, totalBound));
+    if (c->timing) VL_CUDA(cudaEventRecord(c->evx[0], c->stream));
     // only now are this frame's downsampled stacks needed (they were filtered on the side streams)
     VL_CUDA(cudaStreamWaitEvent(c->stream, c->evStacks, 0));
     VL_CUDA(cudaStreamWaitEvent(c->stream, c->evStacksC, 0));
     VL_LAUNCH(lm_set_counts, 1, 32, 0, c->lmm, d->work, d->dQ, d->dQ + 1);
+    if (c->timing) VL_CUDA(cudaEventRecord(c->evx[1], c->stream));
     if (capture) {
       VL_CUDA(cudaMemcpyAsync(c->h_lmm, c->lmm, sizeof(LmScalars), cudaMemcpyDeviceToHost, c->stream));
       VL_CUDA(cudaStreamSynchronize(c->stream));
@@ -1082,6 +1275,7 @@ int vl_lm_run(vloam_b200_ctx* c) {
         }
       }
       VL_TRY(vl_solve(c, nqBound, &d->work->nq, c->lmm->pose, capture ? &c->dbgLmCost[pass * 2] : nullptr, c->h_lmm->Qc + c->h_lmm->Qs));
+      if (c->timing && pass == 0) VL_CUDA(cudaEventRecord(c->evx[2], c->stream));
     }
   }
   VL_LAUNCH(lm_transform_update, 1, 32, 0, c->lmm);  // LM.cpp:737 (runs even when the optimisation was skipped)
@@ -1096,9 +1290,10 @@ int vl_lm_run(vloam_b200_ctx* c) {
   const int tailTotal = c->h_lmm->tailC + c->h_lmm->tailS;
   const int nq = Qc + Qs;
   c->lm_optimized = c->h_lmm->optimized;
-  cudaStream_t mainStream = c->stream;
-  c->stream = c->stream3;
-  const int rmap = [&]() -> int {
+  const long long totalC = c->h_lmm->totalC, totalS = c->h_lmm->totalS;
+  auto update = [=]() -> int {
+  vl_tls_stream = c->stream3;  // every launch helper below issues on the update's stream, whichever thread runs this
+  struct Restore { ~Restore() { vl_tls_stream = nullptr; } } restore;
   VL_CUDA(cudaStreamWaitEvent(c->stream3, c->evPose, 0));
   const int nKeys = tailTotal + nq;
   if (nKeys > 0) {
@@ -1127,19 +1322,42 @@ int vl_lm_run(vloam_b200_ctx* c) {
       VL_LAUNCH(rf_append_outside, 1, 1024, 0, c->lmm, d->newPts.p, d->newCube.p, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, (int)c->poolC.cap,
                 (int)c->poolS.cap);
   }
+  // the map after this frame's update holds at most the points it held before plus this frame's inserts
+  d->hMapUpperC = totalC + Qc; d->hMapUpperS = totalS + Qs;
+  // ---- speculative sub-map of the NEXT frame.  Gathering the 75 valid cubes and cell-sorting ~1M points is
+  // ~80 us of dependent kernels that only depend on the pose through the window centre, and the window moves
+  // once per 50 m.  So the work is done here, behind the map update on its side stream (underneath the next
+  // sweep's scan registration and odometry), for the window this frame used; the next lm_prepare checks the
+  // window and lets the in-line build run only when it moved.  Debug snapshots read this frame's sub-map
+  // after the call returns, so capture mode keeps the in-line build.
+  d->specQueued = false;
+  if (d->specEnabled && !capture) {
+    const long long tb = d->hMapUpperC + d->hMapUpperS;
+    VL_TRY(vl_reserve(c, c->fromMapC, (size_t)max(d->hMapUpperC, 1LL), false, (size_t)d->hMapUpperC / 2 + (1 << 20)));
+    VL_TRY(vl_reserve(c, c->fromMapS, (size_t)max(d->hMapUpperS, 1LL), false, (size_t)d->hMapUpperS / 2 + (1 << 20)));
+    VL_TRY(vl_reserve(c, d->cellOfPoint, (size_t)max(tb, 1LL), false, (size_t)tb / 2 + (1 << 20)));
+    VL_TRY(vl_reserve(c, d->sortedPts, (size_t)max(tb, 1LL), false, (size_t)tb / 2 + (1 << 20)));
+    VL_LAUNCH(lm_spec_prepare, 1, 256, 0, d->subReal, c->cubeC, c->cubeS, d->subSpec);
+    VL_BYTES(32.0 * (double)tb);
+    VL_LAUNCH(lm_gather, gsGrid, 256, 0, d->subSpec, (const int*)nullptr, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, c->fromMapC.p, c->fromMapS.p);
+    VL_TRY(lm_build_grid(c, d, d->subSpec, nullptr, tb));
+    d->specQueued = true;
+  }
   VL_CUDA(cudaEventRecord(c->evMap, c->stream3));
   return VLOAM_OK;
-  }();
-  c->stream = mainStream;
-  if (rmap != VLOAM_OK) return rmap;
-  // the map after this frame's update holds at most the points it held before plus this frame's inserts
-  d->hMapUpperC = (long long)c->h_lmm->totalC + Qc; d->hMapUpperS = (long long)c->h_lmm->totalS + Qs;
+  };
   c->lm_frameCount++;
+  // profiling and debug snapshots serialise everything; otherwise the helper thread issues the update while
+  // the caller returns with its pose (whoever needs the map next joins it first: vl_lm_join)
+  static const bool noWorker = getenv("VLOAM_NO_WORKER") != nullptr;
+  if (noWorker || capture || c->prof_name[0]) { const int rmap = update(); if (rmap != VLOAM_OK) return rmap; }
+  else VL_TRY(lm_submit(c, update));
   VL_CUDA(cudaGetLastError());
   return VLOAM_OK;
 }
 
 int vl_lm_rescan_sorted(vloam_b200_ctx* c) {
+  lmdev(c)->specQueued = false;  // the state behind the speculative sub-map was edited from outside
   VL_LAUNCH(lm_scan_sorted, VL_CUBE_NUM, 256, 0, c->lmm, c->prm, c->cubeC, c->poolC.p, 0);
   VL_LAUNCH(lm_scan_sorted, VL_CUBE_NUM, 256, 0, c->lmm, c->prm, c->cubeS, c->poolS.p, 1);
   VL_CUDA(cudaStreamSynchronize(c->stream));
@@ -1168,6 +1386,7 @@ int vl_lm_export_map(vloam_b200_ctx* c, int which, void* out, long cap, long* by
 
 int vl_lm_import_map(vloam_b200_ctx* c, int which, const void* data, long bytes) {
   LmDevice* d = lmdev(c);
+  d->specQueued = false;  // the map behind the speculative sub-map is replaced
   if (bytes < (long)VL_CUBE_NUM * 4) { snprintf(c->err, sizeof c->err, "map blob too short"); return VLOAM_E_INVALID; }
   const int* counts = (const int*)data;
   long long total = 0;

@@ -629,6 +629,7 @@ int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, i
     c->stream = mainStream;
     if (r != VLOAM_OK) return r;
     VL_CUDA(cudaEventRecord(c->evLast, c->stream2));
+    if (c->timing) VL_CUDA(cudaEventRecord(c->evx[5], c->stream2));
   }
   c->lo_inited = true;
   // LO.cpp:558-574: this frame's less-sharp / less-flat clouds become the "last" clouds

@@ -612,7 +612,7 @@ int vl_solve(vloam_b200_ctx* c, int nslots, const int* d_nslots, double* d_x_ino
     // algorithmic bytes: the factor slots (80 B + flag) are read once; the 5 evaluations run from registers
     if (prof) { cudaEventRecord(c->prof_ev[c->prof_n][1], c->stream); c->prof_kname[c->prof_n] = "lm_solve_cluster"; c->prof_kbytes[c->prof_n] = 84.0 * nslots; c->prof_kstream[c->prof_n] = c->stream;
                 c->prof_n++; c->prof_bytes += 84.0 * nslots; }
-    c->launches++;
+    __atomic_fetch_add(&c->launches, 1LL, __ATOMIC_RELAXED);
   }
   if (costs2) {
     if (nslots > 0) {

@@ -358,6 +358,105 @@ __device__ __forceinline__ unsigned sr_walk_sector(int j, int r, int start, int 
   return spill;
 }
 
+// ---- sort-free sector walk ---------------------------------------------------------------------------
+// The greedy walks only ever need "the largest (smallest) curvature among the points not yet vetoed", at
+// most 20 + 4 times per sector.  A sector of up to 32 * SR_REG_SLOTS points fits in the registers of one
+// warp (element e lives in lane e % 32, slot e / 32), so each pick is a lane-local scan over the slots plus
+// one warp arg-max on (curvature bits, index) keys -- the same total order the sorted walk uses (SURVEY
+// Appendix B: ties go to the larger index when walking down, to the smaller one when walking up) -- and the
+// +-5 marks are bit clears in the owning lanes.  No sort, no shared-memory candidate list: ~4 us per sector
+// instead of an 18 us bitonic sort of all six sectors followed by a 10 us walk.
+#define SR_REG_SLOTS 16
+__device__ __forceinline__ unsigned sr_walk_sector_reg(int j, int r, int start, int end, int rs, const float* __restrict__ curv,
+                                                       const unsigned char* gb, int* __restrict__ label, int* __restrict__ provSharp,
+                                                       int* __restrict__ provLess, int* __restrict__ provFlat, int* __restrict__ cntSharp,
+                                                       int* __restrict__ cntLess, int* __restrict__ cntFlat, int lane, unsigned pre) {
+  const int spj = sr_sp(start, end, j), epj = sr_ep(start, end, j);
+  const int m = epj - spj + 1;
+  const int slot = r * VL_SECTORS + j;
+  float cv[SR_REG_SLOTS];
+  unsigned alive = 0, big = 0, small = 0;
+#pragma unroll
+  for (int q = 0; q < SR_REG_SLOTS; ++q) {
+    const int e = q * 32 + lane;
+    cv[q] = 0.f;
+    if (e < m) {
+      cv[q] = curv[spj + e];
+      alive |= 1u << q;
+      if ((double)cv[q] > 0.1) big |= 1u << q;    // SR.cpp:375
+      if ((double)cv[q] < 0.1) small |= 1u << q;  // SR.cpp:443
+    }
+  }
+  if (lane < 5 && ((pre >> lane) & 1u)) alive &= ~1u;  // incoming marks sit on elements 0..4 = slot 0 of lanes 0..4
+  unsigned spill = 0;
+  // mark element e and its +-5 neighbours until a gap > 0.05 (SR.cpp:403-429).  The marked window
+  // [e - nb, e + nf] is at most 11 elements long, so every lane owns at most one element of it.
+  auto mark = [&](int e) {
+    const int loc = spj - rs + e;
+    bool brk = false;
+    if (lane < 5) brk = gb[loc + lane + 1] != 0;
+    else if (lane < 10) brk = gb[loc - (lane - 4) + 1] != 0;
+    const unsigned bb = __ballot_sync(0xffffffffu, brk);
+    const unsigned f = bb & 31u, w = (bb >> 5) & 31u;
+    const int nf = f ? __ffs(f) - 1 : 5, nb = w ? __ffs(w) - 1 : 5;
+    const int first = e - nb;
+    const int d = (lane - first) & 31;  // offset of this lane's element inside the window, if it has one
+    const int pos = first + d;
+    if (d <= nb + nf && pos >= 0 && pos < m) alive &= ~(1u << (pos >> 5));
+    const int over = e + nf - (m - 1);  // forward marks beyond the sector: elements m .. e + nf
+    if (over > 0) spill |= (1u << over) - 1u;
+  };
+  // ---- descending walk: sharp (<=2) then less sharp (<=20 total), SR.cpp:371-431.  Arg-max on (curvature
+  // bits, element) in two hardware warp reductions: the largest curvature, then the largest element holding it.
+  int cnt = 0;
+  while (cnt < 20) {
+    unsigned lb = 0u; int lq = 0;
+    const unsigned cand = alive & big;
+#pragma unroll
+    for (int q = 0; q < SR_REG_SLOTS; ++q) {
+      const unsigned bits = __float_as_uint(cv[q]);
+      if (((cand >> q) & 1u) && bits >= lb) { lb = bits; lq = q; }  // >= : the later (larger) element wins a tie
+    }
+    const unsigned gmax = __reduce_max_sync(0xffffffffu, lb);
+    if (gmax == 0u) break;  // curvature > 0.1 has non-zero bits
+    const int e = (int)__reduce_max_sync(0xffffffffu, (lb == gmax) ? (unsigned)(lq * 32 + lane + 1) : 0u) - 1;
+    const int pind = spj + e;
+    cnt++;
+    if (lane == 0) {
+      if (cnt <= 2) { label[pind] = 2; provSharp[slot * 2 + cnt - 1] = pind; }
+      else label[pind] = 1;
+      provLess[slot * 20 + cnt - 1] = pind;
+    }
+    mark(e);
+  }
+  if (lane == 0) { cntSharp[slot] = min(cnt, 2); cntLess[slot] = cnt; }
+  // ---- ascending walk: flat (<=4; the 4th is not marked), SR.cpp:439-483
+  cnt = 0;
+  while (cnt < 4) {
+    unsigned lb = 0xffffffffu; int lq = 0;
+    const unsigned cand = alive & small;
+#pragma unroll
+    for (int q = 0; q < SR_REG_SLOTS; ++q) {
+      const unsigned bits = __float_as_uint(cv[q]);
+      if (((cand >> q) & 1u) && bits < lb) { lb = bits; lq = q; }  // < : the earlier (smaller) element wins a tie
+    }
+    const unsigned gmin = __reduce_min_sync(0xffffffffu, lb);
+    if (gmin == 0xffffffffu) break;
+    const int e = (int)__reduce_min_sync(0xffffffffu, (lb == gmin) ? (unsigned)(lq * 32 + lane) : 0xffffffffu);
+    const int pind = spj + e;
+    cnt++;
+    if (lane == 0) { label[pind] = -1; provFlat[slot * 4 + cnt - 1] = pind; }
+    if (cnt >= 4) break;
+    mark(e);
+  }
+  if (lane == 0) cntFlat[slot] = cnt;
+  __syncwarp();
+  return spill;
+}
+
+__device__ long long* g_sr_trace = nullptr;  // debug: clock64 phase stamps, 8 per CTA of sr_pick then 8 per CTA of sr_ring_voxel
+#define SR_TRACE(slot) do { if (g_sr_trace && threadIdx.x == 0) g_sr_trace[(TRACE_BASE + blockIdx.x) * 8 + (slot)] = clock64(); } while (0)
+
 // One CTA per ring.  All six sectors are sorted together (batched bitonic on
 // (curvature bits, index) keys -- the canonical tie order of SURVEY Appendix B), then
 // warp 0 walks the sectors in order because +-5 marks spill into the next sector.
@@ -370,14 +469,56 @@ __global__ void __launch_bounds__(SR_PICK_THREADS) sr_pick(const float4* __restr
   VL_PDL_WAIT();
 
   extern __shared__ unsigned long long smem[];
+#define TRACE_BASE 0
+  SR_TRACE(0);
   const int r = blockIdx.x;
   const int rs = ringStart[r], rc = ringCount[r];
   const int start = rs + 5, end = rs + rc - 6;  // scanStartInd / scanEndInd (SR.cpp:310-314)
   if (threadIdx.x < VL_SECTORS) { cntSharp[r * VL_SECTORS + threadIdx.x] = 0; cntLess[r * VL_SECTORS + threadIdx.x] = 0; cntFlat[r * VL_SECTORS + threadIdx.x] = 0; }
   if (end - start < 6) return;  // SR.cpp:355-356
-  int maxLen = 0;
+  int maxLen = 0, minLen0 = INT_MAX;
 #pragma unroll
-  for (int j = 0; j < VL_SECTORS; ++j) maxLen = max(maxLen, sr_ep(start, end, j) - sr_sp(start, end, j) + 1);
+  for (int j = 0; j < VL_SECTORS; ++j) {
+    const int len = sr_ep(start, end, j) - sr_sp(start, end, j) + 1;
+    maxLen = max(maxLen, len); minLen0 = min(minLen0, len);
+  }
+  if (maxLen <= 32 * SR_REG_SLOTS && minLen0 >= 6 && rc <= SR_RING_CAP) {
+    // ---- register path (every sensor of the reference: <= 512 points per sector) ----
+    unsigned char* gbs = reinterpret_cast<unsigned char*>(smem);
+    for (int t = threadIdx.x; t < rc; t += blockDim.x)
+      gbs[t] = (t > 0 && (double)sr_gap2(cloud, rs + t, rs + t - 1) > 0.05) ? 1 : 0;  // SR.cpp:408-411
+    __syncthreads();
+    SR_TRACE(1); SR_TRACE(2);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ unsigned spillReg[VL_SECTORS];
+    if (warp < VL_SECTORS) {  // six warps, six sectors, each blind to the others' marks (see the resolution loop below)
+      const unsigned so = sr_walk_sector_reg(warp, r, start, end, rs, curv, gbs, label, provSharp, provLess, provFlat, cntSharp, cntLess, cntFlat, lane, 0u);
+      if (lane == 0) spillReg[warp] = so;
+    }
+    SR_TRACE(3);
+    __syncthreads();
+    SR_TRACE(4);
+    if (warp != 0) return;
+    for (int j = 1; j < VL_SECTORS; ++j) {
+      const unsigned in = spillReg[j - 1];
+      if (in == 0) continue;
+      const int spj = sr_sp(start, end, j);
+      const int slot = r * VL_SECTORS + j;
+      const int nl = cntLess[slot], nfl = cntFlat[slot];
+      int pind = -1;
+      if (lane < nl) pind = provLess[slot * 20 + lane];
+      else if (lane >= 20 && lane - 20 < nfl) pind = provFlat[slot * 4 + lane - 20];
+      const bool hit = pind >= 0 && pind - spj < 5 && ((in >> (pind - spj)) & 1u);
+      if (__ballot_sync(0xffffffffu, hit) == 0) continue;  // the spill vetoes nothing this sector picked
+      if (pind >= 0) label[pind] = 0;                       // undo the speculative walk of sector j and repeat it
+      __syncwarp();
+      const unsigned so = sr_walk_sector_reg(j, r, start, end, rs, curv, gbs, label, provSharp, provLess, provFlat, cntSharp, cntLess, cntFlat, lane, in);
+      if (lane == 0) spillReg[j] = so;
+      __syncwarp();
+    }
+    SR_TRACE(5);
+    return;
+  }
   int P = 32; while (P < maxLen) P <<= 1;
   const bool inSmem = P <= SR_SECT_CAP;
   // sector j keys live at keys + j*P; the global fallback uses 2*count entries per ring (6P <= 12*len/6*... bounded by 2*rc+384)
@@ -395,7 +536,9 @@ __global__ void __launch_bounds__(SR_PICK_THREADS) sr_pick(const float4* __restr
     keys[t] = (idx <= last) ? (((unsigned long long)__float_as_uint(curv[idx]) << 32) | (unsigned)idx) : ~0ull;
   }
   __syncthreads();
+  SR_TRACE(1);
   bt_sort_batched<SR_PICK_THREADS>(keys, P, VL_SECTORS);
+  SR_TRACE(2);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int minLen = INT_MAX;
 #pragma unroll
@@ -418,7 +561,9 @@ __global__ void __launch_bounds__(SR_PICK_THREADS) sr_pick(const float4* __restr
                                        sr_sp(start, end, j) - rs, sr_ep(start, end, j) - rs);
     if (lane == 0) spillOut[j] = so;
   }
+  SR_TRACE(3);
   __syncthreads();
+  SR_TRACE(4);
   if (warp != 0) return;
   for (int j = 1; j < VL_SECTORS; ++j) {
     const unsigned in = spillOut[j - 1];
@@ -439,6 +584,8 @@ __global__ void __launch_bounds__(SR_PICK_THREADS) sr_pick(const float4* __restr
     if (lane == 0) spillOut[j] = so;
     __syncwarp();
   }
+  SR_TRACE(5);
+#undef TRACE_BASE
 }
 
 // ---- per-ring pcl::VoxelGrid(0.2) of the label<=0 points (SR.cpp:486-503) -------------
@@ -473,6 +620,8 @@ __global__ void __launch_bounds__(SR_PICK_THREADS) sr_ring_voxel(const float4* _
                                                           float4* __restrict__ outProv, int* __restrict__ dsCount, float leaf) {
   VL_PDL_WAIT();
 
+#define TRACE_BASE 128
+  SR_TRACE(0);
   extern __shared__ unsigned long long vsm[];  // [SR_VOX_CAP] keys, then [SR_VOX_CAP] float4 points
   unsigned long long* skeys = vsm;
   float4* spts = reinterpret_cast<float4*>(vsm + SR_VOX_CAP);
@@ -530,6 +679,7 @@ __global__ void __launch_bounds__(SR_PICK_THREADS) sr_ring_voxel(const float4* _
     if (threadIdx.x == 0) dsCount[r] = m;
     return;
   }
+  SR_TRACE(1);
   // 2. (voxel idx, local index) keys, bitonic sort
   int P = 32; while (P < m) P <<= 1;
   unsigned long long* keys = (P <= SR_VOX_CAP) ? skeys : scratch + (size_t)2 * rs + (size_t)r * 6 * 64;
@@ -544,7 +694,10 @@ __global__ void __launch_bounds__(SR_PICK_THREADS) sr_ring_voxel(const float4* _
     keys[t] = key;
   }
   __syncthreads();
-  bt_sort_batched<SR_PICK_THREADS>(keys, P, 1);
+  SR_TRACE(2);
+  if (P <= SR_VOX_CAP) bt_smem_sort<SR_PICK_THREADS>(skeys, P);  // (P >= 32) the usual case: LDS / STS, register rounds
+  else bt_sort_batched<SR_PICK_THREADS>(keys, P, 1);
+  SR_TRACE(3);
   // 3. run heads -> ordered output slots; the head thread folds its run in f32, in index order
   total = 0;
   for (int base = 0; base < m; base += SR_PICK_THREADS) {
@@ -572,6 +725,8 @@ __global__ void __launch_bounds__(SR_PICK_THREADS) sr_ring_voxel(const float4* _
     __syncthreads();
   }
   if (threadIdx.x == 0) dsCount[r] = total;
+  SR_TRACE(4);
+#undef TRACE_BASE
 }
 
 // Exclusive scans of the pick counts (ring-major, sector, pick order = the reference's
@@ -699,6 +854,20 @@ int vl_sr_run(vloam_b200_ctx* c, const float* d_xyz, int n, int stride) {
 
 // Sync point S1: the host learns the feature counts.  It waits on the event recorded right after scan
 // registration, not on the stream, so odometry kernels queued behind it keep the GPU busy meanwhile.
+// debug: the first call arms the phase trace of sr_pick / sr_ring_voxel; later calls copy it out (256 x 8 stamps)
+int vl_sr_trace(vloam_b200_ctx* c, long long* out, int n) {
+  static long long* d_buf = nullptr;
+  const int cap = 256 * 8;
+  if (!d_buf) {
+    VL_CUDA(cudaMalloc(&d_buf, sizeof(long long) * cap));
+    VL_CUDA(cudaMemset(d_buf, 0, sizeof(long long) * cap));
+    VL_CUDA(cudaMemcpyToSymbol(g_sr_trace, &d_buf, sizeof(long long*)));
+  }
+  VL_CUDA(cudaStreamSynchronize(c->stream));
+  VL_CUDA(cudaMemcpy(out, d_buf, sizeof(long long) * min(n, cap), cudaMemcpyDeviceToHost));
+  return VLOAM_OK;
+}
+
 int vl_sr_sync_counts(vloam_b200_ctx* c) {
   if (c->sr_counts_valid) return VLOAM_OK;
   VL_CUDA(cudaEventSynchronize(c->evSR));

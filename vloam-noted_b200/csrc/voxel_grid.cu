@@ -15,6 +15,7 @@
 #include <math_constants.h>
 #include <cooperative_groups.h>
 #include "common.cuh"
+#include "bitonic.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -131,7 +132,12 @@ __global__ void __launch_bounds__(CS_THREADS) bt_cluster_sort(unsigned long long
   unsigned long long* alt = cs + tile;
   for (int t = threadIdx.x; t < tile; t += CS_THREADS) cur[t] = keys[base + t];
   __syncthreads();
-  for (int k = 2; k <= tile; k <<= 1) bt_smem_strides<CS_THREADS>(cur, tile, k >> 1, base, k, false, false);
+  if (tile >= 8) {
+    bt_smem_init4<CS_THREADS>(cur, tile);
+    for (int k = 8; k <= tile; k <<= 1) bt_smem_level<CS_THREADS>(cur, tile, k >> 1, base, k);
+  } else {  // 2 or 4 keys in all (a single CTA)
+    for (int k = 2; k <= tile; k <<= 1) bt_smem_strides<CS_THREADS>(cur, tile, k >> 1, base, k, false, false);
+  }
   for (int k = tile << 1; k <= n; k <<= 1) {
     for (int j = k >> 1; j >= tile; j >>= 1) {
       cluster.sync();  // partner tiles are complete in `cur`
@@ -149,7 +155,7 @@ __global__ void __launch_bounds__(CS_THREADS) bt_cluster_sort(unsigned long long
     // every CTA flipped buffers the same number of times, so `cur` means the same half everywhere;
     // the barrier below also keeps a fast CTA from overwriting `alt` while a partner still reads it
     cluster.sync();
-    bt_smem_strides<CS_THREADS>(cur, tile, tile >> 1, base, k, true, (base & (size_t)k) == 0);
+    bt_smem_level<CS_THREADS>(cur, tile, tile >> 1, base, k);
   }
   for (int t = threadIdx.x; t < tile; t += CS_THREADS) keys[base + t] = cur[t];
   cluster.sync();  // no CTA exits while a partner may still read its shared memory
@@ -166,7 +172,7 @@ static int vl_sort_cluster(vloam_b200_ctx* c, unsigned long long* d_keys, int n_
     attr = true;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(nct); cfg.blockDim = dim3(CS_THREADS); cfg.dynamicSmemBytes = (size_t)2 * tile * 8; cfg.stream = c->stream;
+  cfg.gridDim = dim3(nct); cfg.blockDim = dim3(CS_THREADS); cfg.dynamicSmemBytes = (size_t)2 * tile * 8; cfg.stream = VL_STREAM(c);
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = nct; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -174,11 +180,11 @@ static int vl_sort_cluster(vloam_b200_ctx* c, unsigned long long* d_keys, int n_
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = 2;
   const bool prof = c->prof_name[0] && vl_prof_match(c, "bt_cluster_sort") && c->prof_n < VL_PROF_MAX;
-  if (prof) cudaEventRecord(c->prof_ev[c->prof_n][0], c->stream);
+  if (prof) cudaEventRecord(c->prof_ev[c->prof_n][0], VL_STREAM(c));
   VL_CUDA(cudaLaunchKernelEx(&cfg, bt_cluster_sort, d_keys, tile));
-  if (prof) { cudaEventRecord(c->prof_ev[c->prof_n][1], c->stream); c->prof_kname[c->prof_n] = "bt_cluster_sort"; c->prof_kbytes[c->prof_n] = 16.0 * n_pow2; c->prof_kstream[c->prof_n] = c->stream;
+  if (prof) { cudaEventRecord(c->prof_ev[c->prof_n][1], VL_STREAM(c)); c->prof_kname[c->prof_n] = "bt_cluster_sort"; c->prof_kbytes[c->prof_n] = 16.0 * n_pow2; c->prof_kstream[c->prof_n] = VL_STREAM(c);
               c->prof_n++; c->prof_bytes += 16.0 * n_pow2; }
-  c->launches++;
+  __atomic_fetch_add(&c->launches, 1LL, __ATOMIC_RELAXED);
   return VLOAM_OK;
 }
 
@@ -320,6 +326,7 @@ __global__ void __launch_bounds__(1024) vg_block_scan(int* __restrict__ blockCnt
   if (threadIdx.x == 0) *dCount = box->guard ? box->n : carry;
 }
 
+#define VG_HALO 256
 __global__ void __launch_bounds__(VG_BLOCK) vg_centroid(const float4* __restrict__ in, const unsigned long long* __restrict__ keys,
                                                         const VgBox* __restrict__ box, const int* __restrict__ blockOff,
                                                         float4* __restrict__ out) {
@@ -334,11 +341,13 @@ __global__ void __launch_bounds__(VG_BLOCK) vg_centroid(const float4* __restrict
   // stage the tile's voxel ids and points in shared memory: the serial f32 folds below then run at
   // shared-memory latency instead of chasing global loads (a run may continue past the tile; the tail
   // is read from global, which is rare)
-  __shared__ unsigned svox[1024 + 1];
-  __shared__ float4 spt[1024];
+  // VG_HALO entries beyond the tile are staged too: the last run of nearly every tile continues into the next
+  // one, and finishing it from global memory is a chain of dependent key -> point loads (~1 us per 2 points).
+  __shared__ unsigned svox[1024 + VG_HALO + 1];
+  __shared__ float4 spt[1024 + VG_HALO];
   __shared__ int ws[VG_BLOCK / 32];
   const int base = blockIdx.x * 1024;
-  for (int t = threadIdx.x; t < 1024; t += VG_BLOCK) {
+  for (int t = threadIdx.x; t < 1024 + VG_HALO; t += VG_BLOCK) {
     const int g = base + t;
     if (g < n) { const unsigned long long k = keys[g]; svox[t] = (unsigned)(k >> 32); spt[t] = in[(int)(unsigned)(k & 0xffffffffull)]; }
     else svox[t] = 0xffffffffu;
@@ -359,13 +368,13 @@ __global__ void __launch_bounds__(VG_BLOCK) vg_centroid(const float4* __restrict
     if (head) {
       float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f; int nrun = 0;
       int r = lt;
-      for (; r < 1024 && svox[r] == vox; ++r) {
+      for (; r < 1024 + VG_HALO && svox[r] == vox; ++r) {
         const float4 p = spt[r];
         sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
         ++nrun;
       }
-      if (r == 1024)
-        for (int g = base + 1024; g < n && (unsigned)(keys[g] >> 32) == vox; ++g) {
+      if (r == 1024 + VG_HALO)
+        for (int g = base + 1024 + VG_HALO; g < n && (unsigned)(keys[g] >> 32) == vox; ++g) {
           const float4 p = in[(int)(unsigned)(keys[g] & 0xffffffffull)];
           sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
           ++nrun;
