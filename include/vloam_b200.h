@@ -93,6 +93,12 @@ int vloam_b200_laser_odometry(vloam_b200_ctx* c, const double* prior_q, const do
  * on skipped frames, LM.cpp:197-201). */
 int vloam_b200_laser_mapping(vloam_b200_ctx* c, double* q_w_curr, double* t_w_curr);
 
+/* The full-resolution cloud of this sweep registered into the map frame: LaserMapping::publish's loop
+ * over laserCloudFullRes with pointAssociateToMap (LM.cpp:901-905; q_w_curr / t_w_curr after
+ * solveMapping, the propagated pose on skipped frames).  out_xyzi: HOST buffer of cap_points points (NULL
+ * to query the size).  Returns the number of points or a negative error. */
+int vloam_b200_register_full_cloud(vloam_b200_ctx* c, float* out_xyzi, int cap_points);
+
 /* MAIN.cpp:143-144, 186-190 in one call: begin_frame, scan_registration,
  * laser_odometry, laser_mapping.  pose_out (may be NULL): 14 doubles
  * {odom q[4], odom t[3], mapped q[4], mapped t[3]}.  Synchronises the stream

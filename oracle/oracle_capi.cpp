@@ -111,6 +111,11 @@ int vloam_oracle_get(void* h, const char* name, void* out, long cap) {
     return put(v, sizeof v, out, cap);
   }
   if (n == "lm.state") { int v[5] = {p->lm.cenW, p->lm.cenH, p->lm.cenD, p->lm.frameCount, p->lm.optimized ? 1 : 0}; return put(v, sizeof v, out, cap); }
+  if (n == "lm.fullResRegistered") {  // LM.cpp:901-905: laserCloudFullRes through pointAssociateToMap (publish path)
+    Cloud reg = p->lo.fullRes;
+    lm_register_full_cloud(reg, p->lm.parameters);
+    return putv(reg, out, cap);
+  }
   if (n == "lm.cornerStack") return putv(p->lm.cornerStack, out, cap);
   if (n == "lm.surfStack") return putv(p->lm.surfStack, out, cap);
   if (n == "lm.cornerFromMap") return putv(p->lm.cornerFromMap, out, cap);

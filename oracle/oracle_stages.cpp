@@ -365,6 +365,11 @@ static inline P4 associate_to_map(const P4& pi, const double pose[7]) {  // LM.c
   return po;
 }
 
+// LM.cpp:901-905: every point of laserCloudFullRes through pointAssociateToMap, in place (LaserMapping::publish)
+void lm_register_full_cloud(Cloud& cloud, const double pose[7]) {
+  for (auto& pt : cloud) pt = associate_to_map(pt, pose);
+}
+
 void LaserMapping::associate(const double pose[7], std::vector<Factor>* fs, int pass) {  // LM.cpp:545-681
   KdTree* kc = kdCornerMap; KdTree* ks = kdSurfMap;
   const int nc = (int)cornerStack.size(), ns = (int)surfStack.size();

@@ -67,6 +67,7 @@ struct SolveLog {
   double initial_cost = 0, final_cost = 0;
   std::vector<double> cost_trace;  // cost after each attempt
 };
+void lm_register_full_cloud(Cloud& cloud, const double pose[7]);  // LM.cpp:901-905
 // ceres::Solve as configured at LO.cpp:500-509 / LM.cpp:710-717.  x = {qx,qy,qz,qw,tx,ty,tz}.
 void ceres_solve(const std::vector<Factor>& f, double x[7], SolveLog* log);
 // One evaluation (robustified): cost, 6x6 J^T J (row-major), 6 J^T r.  For tests.

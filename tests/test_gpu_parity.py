@@ -472,3 +472,19 @@ def test_speculative_submap_equals_inline_build(pkg, op, synth, street):
         assert ma[0] == mb[0] and ma[1] == mb[1], "maps differ with / without the speculative sub-map"
         if i != 1:
             assert len(set(ca)) > 1, "the window never moved: the mismatch path was not exercised"
+
+
+@pytest.mark.gpu
+def test_full_resolution_cloud_registration(pkg, op, synth, street):
+    """LaserMapping::publish's loop over laserCloudFullRes (LM.cpp:901-905): every kept point of the sweep through
+    pointAssociateToMap with the mapped pose -- bit-exact against the oracle given the same pose."""
+    o, g = op.Oracle(**KW[1]), pkg.Context(**KW[1])
+    traj = synth.trajectory(3)
+    for k in range(3):
+        scan = street.scan(1, traj[k], 1000 + k)
+        o.process(scan); g.process_frame(scan)
+        g.set("lm.pose", o.get("lm.pose"))           # same pose on both sides: the comparison is about the transform
+        reg_o, reg_g = o.get("lm.fullResRegistered"), g.register_full_cloud()
+        assert len(reg_g) == len(o.get("sr.laserCloud")) > 50000
+        assert_bits_equal(reg_o, reg_g, "registered full-resolution cloud")
+    g.close()

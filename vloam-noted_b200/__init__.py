@@ -9,3 +9,4 @@ from .api import (Context, Params, VloamError, load_lib, EXPORTS, ScanRegistrati
                   LidarOdometryMapping, CLOUD_FULL, CLOUD_SHARP, CLOUD_LESS_SHARP, CLOUD_FLAT, CLOUD_LESS_FLAT,
                   CLOUD_CORNER_LAST, CLOUD_SURF_LAST)
 from . import synth  # noqa: F401
+from . import kitti_io  # noqa: F401

@@ -15,7 +15,7 @@ EXPORTS = [
     "vloam_b200_scan_registration", "vloam_b200_scan_registration_device", "vloam_b200_get_cloud", "vloam_b200_laser_odometry",
     "vloam_b200_laser_mapping", "vloam_b200_process_frame", "vloam_b200_process_frame_device", "vloam_b200_synchronize",
     "vloam_b200_stream", "vloam_b200_kernel_launches", "vloam_b200_set_timing", "vloam_b200_stage_ms", "vloam_b200_debug_get",
-    "vloam_b200_debug_set", "vloam_b200_profile_kernel", "vloam_b200_profile_result", "vloam_b200_profile_table", "vloam_b200_profile_timeline", "vloam_b200_lo_associate", "vloam_b200_voxel_grid", "vloam_b200_evaluate", "vloam_b200_solve",
+    "vloam_b200_debug_set", "vloam_b200_profile_kernel", "vloam_b200_profile_result", "vloam_b200_profile_table", "vloam_b200_profile_timeline", "vloam_b200_register_full_cloud", "vloam_b200_lo_associate", "vloam_b200_voxel_grid", "vloam_b200_evaluate", "vloam_b200_solve",
 ]
 
 
@@ -70,6 +70,7 @@ def load_lib(build=False):
     L.vloam_b200_voxel_grid.argtypes = [vp, vp, ci, ctypes.c_float, vp, ci]
     L.vloam_b200_evaluate.argtypes = [vp, vp, ci, vp, vp, vp, vp]
     L.vloam_b200_solve.argtypes = [vp, vp, ci, vp, vp]
+    L.vloam_b200_register_full_cloud.argtypes = [vp, vp, ci]
     _lib = L
     return L
 
@@ -144,6 +145,14 @@ class Context:
         out = np.empty((n, 4), np.float32)
         if n:
             self._chk(self.L.vloam_b200_get_cloud(self.h, which, out.ctypes.data, n))
+        return out
+
+    def register_full_cloud(self):
+        """LaserMapping::publish's registration of laserCloudFullRes into the map frame (LM.cpp:901-905)."""
+        n = self._chk(self.L.vloam_b200_register_full_cloud(self.h, None, 0))
+        out = np.empty((n, 4), np.float32)
+        if n:
+            self._chk(self.L.vloam_b200_register_full_cloud(self.h, out.ctypes.data, n))
         return out
 
     def laser_odometry(self, prior_q=None, prior_t=None, want_pose=True):

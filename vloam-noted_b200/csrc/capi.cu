@@ -113,7 +113,7 @@ void vloam_b200_destroy(vloam_b200_ctx* c) {
                   c->lessFlatProv.p, c->selIdx.p, c->sharp.p, c->lessSharp[0].p, c->lessSharp[1].p, c->flat.p, c->lessFlat[0].p,
                   c->lessFlat[1].p, c->loCornerIdx.p, c->loSurfIdx.p, c->factors.p, c->factorValid.p, c->evalPartials.p,
                   c->poolC.p, c->poolS.p, c->stackC.p, c->stackS.p, c->fromMapC.p, c->fromMapS.p, c->knnIdx.p, c->knnD2.p, c->knnOk.p,
-                  c->vKeys.p, c->vKeys2.p, c->vHead.p, c->vScan.p, c->vScan2.p, c->vOut.p, c->vIn.p, c->tailKeys.p, c->staging.p};
+                  c->vKeys.p, c->vKeys2.p, c->vHead.p, c->vScan.p, c->vScan2.p, c->vOut.p, c->vIn.p, c->regOut.p, c->tailKeys.p, c->staging.p};
   for (void* p : bufs) if (p) cudaFree(p);
   cudaFreeHost(c->h_srs); cudaFreeHost(c->h_los); cudaFreeHost(c->h_lms); cudaFreeHost(c->h_lmm); cudaFreeHost(c->h_vScalars);
   for (int k = 0; k < 4; ++k) cudaEventDestroy(c->ev[k]);
@@ -198,6 +198,18 @@ int vloam_b200_laser_mapping(vloam_b200_ctx* c, double* q_w, double* t_w) {
     if (t_w) memcpy(t_w, t, 24);
   }
   return VLOAM_OK;
+}
+
+int vloam_b200_register_full_cloud(vloam_b200_ctx* c, float* out, int cap_points) {
+  VL_TRY(vl_sr_sync_counts(c));
+  const int n = c->nKept;
+  if (!out || n == 0) return n;
+  if (cap_points < n) { snprintf(c->err, sizeof c->err, "cloud buffer too small (%d < %d)", cap_points, n); return VLOAM_E_CAPACITY; }
+  VL_TRY(vl_reserve(c, c->regOut, (size_t)n));
+  VL_TRY(vl_lm_register_full(c, c->cloud.p, n, c->regOut.p));
+  VL_CUDA(cudaMemcpyAsync(out, c->regOut.p, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+  VL_CUDA(cudaStreamSynchronize(c->stream));
+  return n;
 }
 
 static int process_common(vloam_b200_ctx* c, double* pose_out) {

@@ -178,6 +178,7 @@ struct vloam_b200_ctx {
   // voxel filter scratch
   DBuf<unsigned long long> vKeys, vKeys2; DBuf<int> vHead; DBuf<int> vScan, vScan2;  // two scratch lanes: the corner and surf filters run concurrently
   DBuf<float4> vOut; DBuf<float4> vIn;
+  DBuf<float4> regOut;  // full-resolution cloud registered into the map frame
   int* vScalars;  // device scratch ints
   int* h_vScalars;
   // refilter scratch
@@ -278,6 +279,7 @@ int vl_lo_build_last(vloam_b200_ctx* c, int set, const float4* corner, int nc, c
 int vl_lm_run(vloam_b200_ctx* c);
 int vl_lm_enqueue_stacks(vloam_b200_ctx* c, const float4* corner, int nc, const float4* surf, int ns);
 int vl_lm_init(vloam_b200_ctx* c);
+int vl_lm_register_full(vloam_b200_ctx* c, const float4* d_in, int n, float4* d_out);
 int vl_lm_join(vloam_b200_ctx* c);      // wait until the helper thread has issued the pending map update; returns its status
 void vl_lm_shutdown(vloam_b200_ctx* c);  // stop the helper thread
 int vl_lm_export_map(vloam_b200_ctx* c, int which, void* out, long cap, long* bytes);

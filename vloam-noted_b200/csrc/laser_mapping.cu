@@ -1356,6 +1356,29 @@ int vl_lm_run(vloam_b200_ctx* c) {
   return VLOAM_OK;
 }
 
+// LM.cpp:901-905 (LaserMapping::publish): laserCloudFullRes through pointAssociateToMap
+__global__ void __launch_bounds__(256) lm_register_full(const float4* __restrict__ in, int n, const LmScalars* __restrict__ s, int skip,
+                                                        float4* __restrict__ out) {
+  VL_PDL_WAIT();
+
+  const double* q = skip ? s->q_hf : s->pose;
+  const double* t = skip ? s->t_hf : s->pose + 4;
+  const double pose[7] = {q[0], q[1], q[2], q[3], t[0], t[1], t[2]};
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) {
+    const float4 p = in[g];
+    double r[3];
+    vl_qrot(pose, (double)p.x, (double)p.y, (double)p.z, r);  // LM.cpp:154-164
+    out[g] = make_float4((float)(r[0] + pose[4]), (float)(r[1] + pose[5]), (float)(r[2] + pose[6]), p.w);
+  }
+}
+
+int vl_lm_register_full(vloam_b200_ctx* c, const float4* d_in, int n, float4* d_out) {
+  VL_BYTES(32.0 * n);
+  VL_LAUNCH(lm_register_full, c->num_sms * 4, 256, 0, d_in, n, c->lmm, c->skip_frame ? 1 : 0, d_out);
+  VL_CUDA(cudaGetLastError());
+  return VLOAM_OK;
+}
+
 int vl_lm_rescan_sorted(vloam_b200_ctx* c) {
   lmdev(c)->specQueued = false;  // the state behind the speculative sub-map was edited from outside
   VL_LAUNCH(lm_scan_sorted, VL_CUBE_NUM, 256, 0, c->lmm, c->prm, c->cubeC, c->poolC.p, 0);
