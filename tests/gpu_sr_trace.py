@@ -25,3 +25,8 @@ for name, base, labels in (("sr_pick", 0, ["init(gap,keys)", "sort", "walk", "ba
     print("%s: %d CTAs, per-CTA total median %.1f max %.1f us" % (name, len(rows), np.median(tot), tot.max()))
     for i, l in enumerate(labels):
         print("   %-16s median %6.2f  max %6.2f us" % (l, np.median(dt[:, i]), dt[:, i].max()))
+    if base == 0:
+        a, b, c2, d2 = rows[:, 2], rows[:, 6], rows[:, 7], rows[:, 3]
+        ok = (b > a) & (c2 > b)
+        print("   walk of sector 0: load+lane sort %.2f | descending walk %.2f | ascending walk %.2f us (medians; stamps of the first walk only when no re-walk overwrote them)" % (
+            np.median((b - a)[ok]) / 1965.0, np.median((c2 - b)[ok]) / 1965.0, np.median((d2 - c2)[ok]) / 1965.0))

@@ -92,7 +92,10 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   VL_CUDA_CREATE(cudaMallocHost(&c->h_vScalars, sizeof(int) * 256));
   memset(c->h_vScalars, 0, sizeof(int) * 256);
   c->h_vScalars[0] = g_capture_default ? 1 : 0;
-  const int r = vl_lm_init(c);
+  int r = vl_lm_init(c);
+  if (r == VLOAM_OK) r = vl_sr_set_attrs(c);
+  if (r == VLOAM_OK) r = vl_sort_set_attrs(c);
+  if (r == VLOAM_OK) r = vl_solver_set_attrs(c);
   if (r != VLOAM_OK) { fprintf(stderr, "vloam_b200_create: %s\n", c->err); return r; }
   VL_CUDA_CREATE(cudaDeviceSynchronize());
   *out = c;

@@ -279,6 +279,9 @@ int vl_lo_build_last(vloam_b200_ctx* c, int set, const float4* corner, int nc, c
 int vl_lm_run(vloam_b200_ctx* c);
 int vl_lm_enqueue_stacks(vloam_b200_ctx* c, const float4* corner, int nc, const float4* surf, int ns);
 int vl_lm_init(vloam_b200_ctx* c);
+int vl_sr_set_attrs(vloam_b200_ctx* c);
+int vl_sort_set_attrs(vloam_b200_ctx* c);
+int vl_solver_set_attrs(vloam_b200_ctx* c);
 int vl_lm_register_full(vloam_b200_ctx* c, const float4* d_in, int n, float4* d_out);
 int vl_lm_join(vloam_b200_ctx* c);      // wait until the helper thread has issued the pending map update; returns its status
 void vl_lm_shutdown(vloam_b200_ctx* c);  // stop the helper thread

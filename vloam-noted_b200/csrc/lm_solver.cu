@@ -577,14 +577,17 @@ int vl_solver_trace(vloam_b200_ctx* c, long long* out16) {
 template <int FPT, int THREADS>
 static cudaError_t lm_launch(cudaLaunchConfig_t& cfg, const double* cf, const int* cv, int nslots, const int* d_nslots, double* x,
                              LmSolveState* so, long long* trace) {
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(lm_solve_cluster<FPT, THREADS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
   cfg.blockDim = dim3(THREADS);
   return cudaLaunchKernelEx(&cfg, lm_solve_cluster<FPT, THREADS>, cf, cv, nslots, d_nslots, x, so, trace);
+}
+
+// function attributes are per device: set when a context is created on it (vloam_b200_create)
+int vl_solver_set_attrs(vloam_b200_ctx* c) {
+  VL_CUDA(cudaFuncSetAttribute(lm_solve_cluster<1, 256>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  VL_CUDA(cudaFuncSetAttribute(lm_solve_cluster<2, 256>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  VL_CUDA(cudaFuncSetAttribute(lm_solve_cluster<4, 256>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  VL_CUDA(cudaFuncSetAttribute(lm_solve_cluster<0, 256>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  return VLOAM_OK;
 }
 
 int vl_solve(vloam_b200_ctx* c, int nslots, const int* d_nslots, double* d_x_inout, double* costs2, int hint) {

@@ -358,36 +358,73 @@ __device__ __forceinline__ unsigned sr_walk_sector(int j, int r, int start, int 
   return spill;
 }
 
-// ---- sort-free sector walk ---------------------------------------------------------------------------
+__device__ long long* g_sr_trace = nullptr;  // debug: clock64 phase stamps, 8 per CTA of sr_pick then 8 per CTA of sr_ring_voxel
+#define SR_TRACE(slot) do { if (g_sr_trace && threadIdx.x == 0) g_sr_trace[(TRACE_BASE + blockIdx.x) * 8 + (slot)] = clock64(); } while (0)
+#define TRACE_BASE 0
+// ---- sector walk on per-lane sorted lists ------------------------------------------------------------
 // The greedy walks only ever need "the largest (smallest) curvature among the points not yet vetoed", at
-// most 20 + 4 times per sector.  A sector of up to 32 * SR_REG_SLOTS points fits in the registers of one
-// warp (element e lives in lane e % 32, slot e / 32), so each pick is a lane-local scan over the slots plus
-// one warp arg-max on (curvature bits, index) keys -- the same total order the sorted walk uses (SURVEY
-// Appendix B: ties go to the larger index when walking down, to the smaller one when walking up) -- and the
-// +-5 marks are bit clears in the owning lanes.  No sort, no shared-memory candidate list: ~4 us per sector
-// instead of an 18 us bitonic sort of all six sectors followed by a 10 us walk.
+// most 20 + 4 times per sector.  A sector of up to 32 * SR_REG_SLOTS points is dealt out to one warp
+// (element e lives in lane e % 32, slot e / 32).  Every lane sorts its <= 16 (curvature bits, slot) keys
+// once in registers (bitonic network, compile-time indices) and parks the sorted list in shared memory
+// together with the inverse permutation; `live` is a bit mask over SORTED positions.  A pick is then: the
+// highest (lowest) live position of each lane (one clz / ffs and one shared-memory read), the largest
+// curvature over the warp and the largest element holding it (two hardware warp reductions: the
+// (curvature, index) order of SURVEY Appendix B), and the +-5 marks as bit clears in the owning lanes
+// (the marked window is <= 11 elements, so each lane owns at most one).  No global sort, no candidate
+// list: ~3 us per sector instead of an 18 us bitonic sort of all six sectors followed by a 10 us walk.
 #define SR_REG_SLOTS 16
+struct SrLaneLists {                       // per warp
+  unsigned bits[SR_REG_SLOTS][32];         // [sorted position][lane]: curvature bits, ascending
+  unsigned char slot[SR_REG_SLOTS][32];    // [sorted position][lane]: element slot held there
+  unsigned char pos[SR_REG_SLOTS][32];     // [slot][lane]: sorted position of that slot
+};
+
 __device__ __forceinline__ unsigned sr_walk_sector_reg(int j, int r, int start, int end, int rs, const float* __restrict__ curv,
-                                                       const unsigned char* gb, int* __restrict__ label, int* __restrict__ provSharp,
+                                                       const unsigned char* gb, SrLaneLists& L, int* __restrict__ label, int* __restrict__ provSharp,
                                                        int* __restrict__ provLess, int* __restrict__ provFlat, int* __restrict__ cntSharp,
                                                        int* __restrict__ cntLess, int* __restrict__ cntFlat, int lane, unsigned pre) {
   const int spj = sr_sp(start, end, j), epj = sr_ep(start, end, j);
   const int m = epj - spj + 1;
   const int slot = r * VL_SECTORS + j;
-  float cv[SR_REG_SLOTS];
-  unsigned alive = 0, big = 0, small = 0;
+  // per-lane ascending sort of (curvature bits, slot); absent elements sort to the top and stay dead
+  unsigned long long key[SR_REG_SLOTS];
 #pragma unroll
   for (int q = 0; q < SR_REG_SLOTS; ++q) {
     const int e = q * 32 + lane;
-    cv[q] = 0.f;
-    if (e < m) {
-      cv[q] = curv[spj + e];
-      alive |= 1u << q;
-      if ((double)cv[q] > 0.1) big |= 1u << q;    // SR.cpp:375
-      if ((double)cv[q] < 0.1) small |= 1u << q;  // SR.cpp:443
+    key[q] = e < m ? (((unsigned long long)__float_as_uint(curv[spj + e]) << 32) | (unsigned)q) : (0xffffffff00000000ull | (unsigned)q);
+  }
+#pragma unroll
+  for (int k = 2; k <= SR_REG_SLOTS; k <<= 1) {
+#pragma unroll
+    for (int jj = k >> 1; jj > 0; jj >>= 1) {
+#pragma unroll
+      for (int i = 0; i < SR_REG_SLOTS; ++i) {
+        const int l = i ^ jj;
+        if (l > i) {
+          const bool up = (i & k) == 0;
+          const unsigned long long a = key[i], b = key[l];
+          const bool sw = (a > b) == up;
+          key[i] = sw ? b : a; key[l] = sw ? a : b;
+        }
+      }
     }
   }
-  if (lane < 5 && ((pre >> lane) & 1u)) alive &= ~1u;  // incoming marks sit on elements 0..4 = slot 0 of lanes 0..4
+  unsigned live = 0, big = 0, small = 0;  // over sorted positions
+#pragma unroll
+  for (int p = 0; p < SR_REG_SLOTS; ++p) {
+    const unsigned bits = (unsigned)(key[p] >> 32);
+    const int q = (int)(key[p] & 0xffu);
+    L.bits[p][lane] = bits; L.slot[p][lane] = (unsigned char)q; L.pos[q][lane] = (unsigned char)p;
+    if (q * 32 + lane < m) {
+      live |= 1u << p;
+      const float cv = __uint_as_float(bits);
+      if ((double)cv > 0.1) big |= 1u << p;    // SR.cpp:375
+      if ((double)cv < 0.1) small |= 1u << p;  // SR.cpp:443
+    }
+  }
+  __syncwarp();
+  SR_TRACE(6);
+  if (lane < 5 && ((pre >> lane) & 1u)) live &= ~(1u << L.pos[0][lane]);  // incoming marks sit on elements 0..4 = slot 0 of lanes 0..4
   unsigned spill = 0;
   // mark element e and its +-5 neighbours until a gap > 0.05 (SR.cpp:403-429).  The marked window
   // [e - nb, e + nf] is at most 11 elements long, so every lane owns at most one element of it.
@@ -401,25 +438,24 @@ __device__ __forceinline__ unsigned sr_walk_sector_reg(int j, int r, int start, 
     const int nf = f ? __ffs(f) - 1 : 5, nb = w ? __ffs(w) - 1 : 5;
     const int first = e - nb;
     const int d = (lane - first) & 31;  // offset of this lane's element inside the window, if it has one
-    const int pos = first + d;
-    if (d <= nb + nf && pos >= 0 && pos < m) alive &= ~(1u << (pos >> 5));
+    const int pe = first + d;
+    if (d <= nb + nf && pe >= 0 && pe < m) live &= ~(1u << L.pos[pe >> 5][lane]);
     const int over = e + nf - (m - 1);  // forward marks beyond the sector: elements m .. e + nf
     if (over > 0) spill |= (1u << over) - 1u;
   };
-  // ---- descending walk: sharp (<=2) then less sharp (<=20 total), SR.cpp:371-431.  Arg-max on (curvature
-  // bits, element) in two hardware warp reductions: the largest curvature, then the largest element holding it.
+  // ---- descending walk: sharp (<=2) then less sharp (<=20 total), SR.cpp:371-431
   int cnt = 0;
   while (cnt < 20) {
-    unsigned lb = 0u; int lq = 0;
-    const unsigned cand = alive & big;
-#pragma unroll
-    for (int q = 0; q < SR_REG_SLOTS; ++q) {
-      const unsigned bits = __float_as_uint(cv[q]);
-      if (((cand >> q) & 1u) && bits >= lb) { lb = bits; lq = q; }  // >= : the later (larger) element wins a tie
+    const unsigned cand = live & big;
+    unsigned lb = 0u, le = 0u;
+    if (cand) {
+      const int p = 31 - __clz(cand);  // ascending lists: the highest live position is this lane's largest (curvature, element)
+      lb = L.bits[p][lane];
+      le = (unsigned)(L.slot[p][lane] * 32 + lane + 1);
     }
     const unsigned gmax = __reduce_max_sync(0xffffffffu, lb);
     if (gmax == 0u) break;  // curvature > 0.1 has non-zero bits
-    const int e = (int)__reduce_max_sync(0xffffffffu, (lb == gmax) ? (unsigned)(lq * 32 + lane + 1) : 0u) - 1;
+    const int e = (int)__reduce_max_sync(0xffffffffu, (lb == gmax) ? le : 0u) - 1;
     const int pind = spj + e;
     cnt++;
     if (lane == 0) {
@@ -430,19 +466,20 @@ __device__ __forceinline__ unsigned sr_walk_sector_reg(int j, int r, int start, 
     mark(e);
   }
   if (lane == 0) { cntSharp[slot] = min(cnt, 2); cntLess[slot] = cnt; }
+  SR_TRACE(7);
   // ---- ascending walk: flat (<=4; the 4th is not marked), SR.cpp:439-483
   cnt = 0;
   while (cnt < 4) {
-    unsigned lb = 0xffffffffu; int lq = 0;
-    const unsigned cand = alive & small;
-#pragma unroll
-    for (int q = 0; q < SR_REG_SLOTS; ++q) {
-      const unsigned bits = __float_as_uint(cv[q]);
-      if (((cand >> q) & 1u) && bits < lb) { lb = bits; lq = q; }  // < : the earlier (smaller) element wins a tie
+    const unsigned cand = live & small;
+    unsigned lb = 0xffffffffu, le = 0xffffffffu;
+    if (cand) {
+      const int p = __ffs(cand) - 1;  // the lowest live position: smallest (curvature, element)
+      lb = L.bits[p][lane];
+      le = (unsigned)(L.slot[p][lane] * 32 + lane);
     }
     const unsigned gmin = __reduce_min_sync(0xffffffffu, lb);
     if (gmin == 0xffffffffu) break;
-    const int e = (int)__reduce_min_sync(0xffffffffu, (lb == gmin) ? (unsigned)(lq * 32 + lane) : 0xffffffffu);
+    const int e = (int)__reduce_min_sync(0xffffffffu, (lb == gmin) ? le : 0xffffffffu);
     const int pind = spj + e;
     cnt++;
     if (lane == 0) { label[pind] = -1; provFlat[slot * 4 + cnt - 1] = pind; }
@@ -454,8 +491,6 @@ __device__ __forceinline__ unsigned sr_walk_sector_reg(int j, int r, int start, 
   return spill;
 }
 
-__device__ long long* g_sr_trace = nullptr;  // debug: clock64 phase stamps, 8 per CTA of sr_pick then 8 per CTA of sr_ring_voxel
-#define SR_TRACE(slot) do { if (g_sr_trace && threadIdx.x == 0) g_sr_trace[(TRACE_BASE + blockIdx.x) * 8 + (slot)] = clock64(); } while (0)
 
 // One CTA per ring.  All six sectors are sorted together (batched bitonic on
 // (curvature bits, index) keys -- the canonical tie order of SURVEY Appendix B), then
@@ -469,7 +504,6 @@ __global__ void __launch_bounds__(SR_PICK_THREADS) sr_pick(const float4* __restr
   VL_PDL_WAIT();
 
   extern __shared__ unsigned long long smem[];
-#define TRACE_BASE 0
   SR_TRACE(0);
   const int r = blockIdx.x;
   const int rs = ringStart[r], rc = ringCount[r];
@@ -491,30 +525,44 @@ __global__ void __launch_bounds__(SR_PICK_THREADS) sr_pick(const float4* __restr
     SR_TRACE(1); SR_TRACE(2);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ unsigned spillReg[VL_SECTORS];
-    if (warp < VL_SECTORS) {  // six warps, six sectors, each blind to the others' marks (see the resolution loop below)
-      const unsigned so = sr_walk_sector_reg(warp, r, start, end, rs, curv, gbs, label, provSharp, provLess, provFlat, cntSharp, cntLess, cntFlat, lane, 0u);
+    __shared__ SrLaneLists lists[VL_SECTORS];
+    // Six warps, six sectors.  Round 0: every sector is walked blind to its predecessor's marks.  A pre-marked
+    // point changes a walk only if that walk had picked it (a mark does nothing but veto a pick), so in the
+    // following rounds sector j keeps its result while (a) every mark it was walked with is still in its
+    // predecessor's spill and (b) no NEW spill mark sits on one of its picks; otherwise it is walked again with
+    // the current spill.  Sector j is final after round j at the latest (sector 0 never changes); nearly always
+    // one round with one or two re-walks, all of them in parallel.
+    unsigned used = 0u;  // marks this warp's sector was last walked with
+    if (warp < VL_SECTORS) {
+      const unsigned so = sr_walk_sector_reg(warp, r, start, end, rs, curv, gbs, lists[warp], label, provSharp, provLess, provFlat, cntSharp, cntLess, cntFlat, lane, 0u);
       if (lane == 0) spillReg[warp] = so;
     }
     SR_TRACE(3);
-    __syncthreads();
-    SR_TRACE(4);
-    if (warp != 0) return;
-    for (int j = 1; j < VL_SECTORS; ++j) {
-      const unsigned in = spillReg[j - 1];
-      if (in == 0) continue;
-      const int spj = sr_sp(start, end, j);
-      const int slot = r * VL_SECTORS + j;
-      const int nl = cntLess[slot], nfl = cntFlat[slot];
+    for (int round = 1; round < VL_SECTORS; ++round) {
+      __syncthreads();
+      if (round == 1) SR_TRACE(4);
+      bool need = false;
+      unsigned in = 0u;
       int pind = -1;
-      if (lane < nl) pind = provLess[slot * 20 + lane];
-      else if (lane >= 20 && lane - 20 < nfl) pind = provFlat[slot * 4 + lane - 20];
-      const bool hit = pind >= 0 && pind - spj < 5 && ((in >> (pind - spj)) & 1u);
-      if (__ballot_sync(0xffffffffu, hit) == 0) continue;  // the spill vetoes nothing this sector picked
-      if (pind >= 0) label[pind] = 0;                       // undo the speculative walk of sector j and repeat it
-      __syncwarp();
-      const unsigned so = sr_walk_sector_reg(j, r, start, end, rs, curv, gbs, label, provSharp, provLess, provFlat, cntSharp, cntLess, cntFlat, lane, in);
-      if (lane == 0) spillReg[j] = so;
-      __syncwarp();
+      if (warp >= 1 && warp < VL_SECTORS) {
+        in = spillReg[warp - 1];
+        const int spj = sr_sp(start, end, warp);
+        const int slot = r * VL_SECTORS + warp;
+        const int nl = cntLess[slot], nfl = cntFlat[slot];
+        if (lane < nl) pind = provLess[slot * 20 + lane];
+        else if (lane >= 20 && lane - 20 < nfl) pind = provFlat[slot * 4 + lane - 20];
+        const unsigned fresh = in & ~used;
+        const bool hit = pind >= 0 && pind - spj < 5 && ((fresh >> (pind - spj)) & 1u);
+        need = (used & ~in) != 0u || __ballot_sync(0xffffffffu, hit) != 0u;
+      }
+      if (!__syncthreads_or(need ? 1 : 0)) break;  // (also orders the reads of spillReg above before the writes below)
+      if (need) {
+        if (pind >= 0) label[pind] = 0;  // undo this sector's previous walk
+        __syncwarp();
+        const unsigned so = sr_walk_sector_reg(warp, r, start, end, rs, curv, gbs, lists[warp], label, provSharp, provLess, provFlat, cntSharp, cntLess, cntFlat, lane, in);
+        used = in;
+        if (lane == 0) spillReg[warp] = so;
+      }
     }
     SR_TRACE(5);
     return;
@@ -585,8 +633,8 @@ __global__ void __launch_bounds__(SR_PICK_THREADS) sr_pick(const float4* __restr
     __syncwarp();
   }
   SR_TRACE(5);
-#undef TRACE_BASE
 }
+#undef TRACE_BASE
 
 // ---- per-ring pcl::VoxelGrid(0.2) of the label<=0 points (SR.cpp:486-503) -------------
 struct VoxBox { int minb[3], mul1, mul2, guard; float inv; };
@@ -826,17 +874,10 @@ int vl_sr_run(vloam_b200_ctx* c, const float* d_xyz, int n, int stride) {
   VL_BYTES(25.0 * n);
   VL_LAUNCH(sr_curvature, numBlocks, SR_BLOCK, 0, c->cloud.p, c->srs, c->curv.p, c->label.p, c->picked.p);
   const size_t pickSmem = (size_t)VL_SECTORS * SR_SECT_CAP * sizeof(unsigned long long) + 2 * SR_RING_CAP;
-  static bool attrSet = false;
-  if (!attrSet) {
-    VL_CUDA(cudaFuncSetAttribute(sr_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pickSmem));
-    attrSet = true;
-  }
   VL_BYTES(40.0 * n);  // 2 points + curvature per ring point in, labels + picks out (upper bound: n kept)
   VL_LAUNCH(sr_pick, R, SR_PICK_THREADS, pickSmem, c->cloud.p, c->curv.p, c->label.p, c->picked.p, c->picked.p + n, c->sortScratch.p, c->ringStart, c->ringCount,
             c->provSharp, c->provLess, c->provFlat, c->cntSharp, c->cntLess, c->cntFlat);
   const size_t voxSmem = (size_t)SR_VOX_CAP * (sizeof(unsigned long long) + sizeof(float4));
-  static bool voxAttr = false;
-  if (!voxAttr) { VL_CUDA(cudaFuncSetAttribute(sr_ring_voxel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)voxSmem)); voxAttr = true; }
   VL_BYTES(36.0 * n);
   VL_LAUNCH(sr_ring_voxel, R, SR_PICK_THREADS, voxSmem, c->cloud.p, c->label.p, c->ringStart, c->ringCount, c->selIdx.p, c->sortScratch.p,
             c->lessFlatProv.p, c->ringDsCount, 0.2f);
@@ -854,6 +895,15 @@ int vl_sr_run(vloam_b200_ctx* c, const float* d_xyz, int n, int stride) {
 
 // Sync point S1: the host learns the feature counts.  It waits on the event recorded right after scan
 // registration, not on the stream, so odometry kernels queued behind it keep the GPU busy meanwhile.
+// function attributes are per device: set when a context is created on it (vloam_b200_create)
+int vl_sr_set_attrs(vloam_b200_ctx* c) {
+  VL_CUDA(cudaFuncSetAttribute(sr_pick, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)((size_t)VL_SECTORS * SR_SECT_CAP * sizeof(unsigned long long) + 2 * SR_RING_CAP)));
+  VL_CUDA(cudaFuncSetAttribute(sr_ring_voxel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)((size_t)SR_VOX_CAP * (sizeof(unsigned long long) + sizeof(float4)))));
+  return VLOAM_OK;
+}
+
 // debug: the first call arms the phase trace of sr_pick / sr_ring_voxel; later calls copy it out (256 x 8 stamps)
 int vl_sr_trace(vloam_b200_ctx* c, long long* out, int n) {
   static long long* d_buf = nullptr;

@@ -161,16 +161,17 @@ __global__ void __launch_bounds__(CS_THREADS) bt_cluster_sort(unsigned long long
   cluster.sync();  // no CTA exits while a partner may still read its shared memory
 }
 
+// function attributes are per device: set when a context is created on it (vloam_b200_create)
+int vl_sort_set_attrs(vloam_b200_ctx* c) {
+  VL_CUDA(cudaFuncSetAttribute(bt_cluster_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 8));
+  VL_CUDA(cudaFuncSetAttribute(bt_cluster_sort, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  return VLOAM_OK;
+}
+
 static int vl_sort_cluster(vloam_b200_ctx* c, unsigned long long* d_keys, int n_pow2) {
   int tile = n_pow2 <= 4096 ? n_pow2 : 4096;
   int nct = n_pow2 / tile;
   if (nct > 16) { tile = 8192; nct = n_pow2 / tile; }
-  static bool attr = false;
-  if (!attr) {
-    VL_CUDA(cudaFuncSetAttribute(bt_cluster_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 8));
-    VL_CUDA(cudaFuncSetAttribute(bt_cluster_sort, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    attr = true;
-  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(nct); cfg.blockDim = dim3(CS_THREADS); cfg.dynamicSmemBytes = (size_t)2 * tile * 8; cfg.stream = VL_STREAM(c);
   cudaLaunchAttribute at[2];
