@@ -22,7 +22,9 @@
 #include <limits.h>
 #include <float.h>
 #include <math_constants.h>
+#include <cooperative_groups.h>
 #include "common.cuh"
+namespace cg = cooperative_groups;
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -365,22 +367,21 @@ __global__ void __launch_bounds__(256) lm_spec_prepare(const LmSub* __restrict__
 }
 
 // zero the two cell-counter arrays of the search grid (a kernel, not a memset, so that it can be skipped)
+__device__ __forceinline__ void lm_dev_zero(int* __restrict__ a, int* __restrict__ b, int n) {
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) { a[g] = 0; b[g] = 0; }
+}
 __global__ void __launch_bounds__(256) lm_grid_zero(int* __restrict__ a, int* __restrict__ b, int n, const int* __restrict__ skip) {
   VL_PDL_WAIT();
 
   if (skip && *skip) return;
-  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) { a[g] = 0; b[g] = 0; }
+  lm_dev_zero(a, b, n);
 }
 
 // LM.cpp:476-485: concatenate the valid cubes (loop order of LM.cpp:448-452) into the sub-map clouds.
 // skip (may be null): device flag "the speculative build already produced exactly this" -> nothing to do.
-__global__ void __launch_bounds__(256) lm_gather(const LmSub* __restrict__ sub, const int* __restrict__ skip,
-                                                 const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts,
-                                                 const float4* __restrict__ poolC, const float4* __restrict__ poolS,
-                                                 float4* __restrict__ outC, float4* __restrict__ outS) {
-  VL_PDL_WAIT();
-
-  if (skip && *skip) return;
+__device__ __forceinline__ void lm_dev_gather(const LmSub* __restrict__ sub, const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts,
+                                              const float4* __restrict__ poolC, const float4* __restrict__ poolS,
+                                              float4* __restrict__ outC, float4* __restrict__ outS) {
   const int nv = sub->validNum, mc = sub->Mc, total = sub->Mc + sub->Ms;
   for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
     const int kind = g >= mc;
@@ -393,18 +394,23 @@ __global__ void __launch_bounds__(256) lm_gather(const LmSub* __restrict__ sub, 
     else outC[e] = poolC[tc->start[cb] + (e - off[lo])];
   }
 }
+__global__ void __launch_bounds__(256) lm_gather(const LmSub* __restrict__ sub, const int* __restrict__ skip,
+                                                 const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts,
+                                                 const float4* __restrict__ poolC, const float4* __restrict__ poolS,
+                                                 float4* __restrict__ outC, float4* __restrict__ outS) {
+  VL_PDL_WAIT();
+
+  if (skip && *skip) return;
+  lm_dev_gather(sub, tc, ts, poolC, poolS, outC, outS);
+}
 
 // ---- search grid: counting sort of both sub-maps into 2 m cells --------------------------------
 __device__ __forceinline__ int lm_cell_coord(float v, float o, int n) {
   const int cidx = (int)floorf(__fmul_rn(__fsub_rn(v, o), 1.0f / LM_CELL));
   return min(max(cidx, 0), n - 1);
 }
-__global__ void __launch_bounds__(256) lm_grid_count(const LmSub* __restrict__ sub, const int* __restrict__ skip,
-                                                     const float4* __restrict__ mapC, const float4* __restrict__ mapS,
-                                                     int* __restrict__ cellCount, int* __restrict__ cellOfPoint) {
-  VL_PDL_WAIT();
-
-  if (skip && *skip) return;
+__device__ __forceinline__ void lm_dev_count(const LmSub* __restrict__ sub, const float4* __restrict__ mapC, const float4* __restrict__ mapS,
+                                             int* __restrict__ cellCount, int* __restrict__ cellOfPoint) {
   const int mc = sub->Mc, total = sub->Mc + sub->Ms;
   const float ox = sub->gridOrigin[0], oy = sub->gridOrigin[1], oz = sub->gridOrigin[2];
   for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
@@ -415,34 +421,45 @@ __global__ void __launch_bounds__(256) lm_grid_count(const LmSub* __restrict__ s
     atomicAdd(&cellCount[cell], 1);
   }
 }
+__global__ void __launch_bounds__(256) lm_grid_count(const LmSub* __restrict__ sub, const int* __restrict__ skip,
+                                                     const float4* __restrict__ mapC, const float4* __restrict__ mapS,
+                                                     int* __restrict__ cellCount, int* __restrict__ cellOfPoint) {
+  VL_PDL_WAIT();
+
+  if (skip && *skip) return;
+  lm_dev_count(sub, mapC, mapS, cellCount, cellOfPoint);
+}
 // exclusive scan over 2*LM_NCELL counts: tile sums (1024 per block) -> scan of tile sums -> apply
+__device__ __forceinline__ void lm_dev_scan_tile(const int* __restrict__ in, int n, int* __restrict__ tileSum, int tile) {  // 256 threads
+  int acc = 0;
+  const int base = tile * 1024;
+  for (int q = 0; q < 4; ++q) { const int t = base + q * 256 + threadIdx.x; if (t < n) acc += in[t]; }
+  __shared__ int ws[8];
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+  __syncthreads();  // (ws may still be read by the previous tile of a looping caller)
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) { int v = 0; for (int k = 0; k < 8; ++k) v += ws[k]; tileSum[tile] = v; }
+}
 __global__ void __launch_bounds__(256) lm_scan_tiles(const int* __restrict__ in, int n, int* __restrict__ tileSum, const int* __restrict__ skip) {
   VL_PDL_WAIT();
 
   if (skip && *skip) return;
-  int acc = 0;
-  const int base = blockIdx.x * 1024;
-  for (int q = 0; q < 4; ++q) { const int t = base + q * 256 + threadIdx.x; if (t < n) acc += in[t]; }
-  __shared__ int ws[8];
-  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) { int v = 0; for (int k = 0; k < 8; ++k) v += ws[k]; tileSum[blockIdx.x] = v; }
+  lm_dev_scan_tile(in, n, tileSum, blockIdx.x);
 }
-__global__ void __launch_bounds__(1024) lm_scan_sums(int* __restrict__ tileSum, int nTiles, const int* __restrict__ skip) {
-  VL_PDL_WAIT();
-
-  if (skip && *skip) return;
-  __shared__ int buf[1024];
+// exclusive scan of the tile sums in place by ONE block of T threads (T a power of two <= 1024)
+template <int T>
+__device__ __forceinline__ void lm_dev_scan_sums(int* __restrict__ tileSum, int nTiles) {
+  __shared__ int buf[T];
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
-  for (int base = 0; base < nTiles; base += 1024) {
+  for (int base = 0; base < nTiles; base += T) {
     const int b = base + threadIdx.x;
     const int own = b < nTiles ? tileSum[b] : 0;
     buf[threadIdx.x] = own;
     __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {
+    for (int d = 1; d < T; d <<= 1) {
       const int v = threadIdx.x >= d ? buf[threadIdx.x - d] : 0;
       __syncthreads();
       buf[threadIdx.x] += v;
@@ -450,32 +467,42 @@ __global__ void __launch_bounds__(1024) lm_scan_sums(int* __restrict__ tileSum, 
     }
     if (b < nTiles) tileSum[b] = carry + buf[threadIdx.x] - own;
     __syncthreads();
-    if (threadIdx.x == 1023) carry += buf[1023];
+    if (threadIdx.x == T - 1) carry += buf[T - 1];
     __syncthreads();
   }
 }
-__global__ void __launch_bounds__(256) lm_scan_apply(const int* __restrict__ in, int n, const int* __restrict__ tileSum, int* __restrict__ out,
-                                                     const int* __restrict__ skip) {
+__global__ void __launch_bounds__(1024) lm_scan_sums(int* __restrict__ tileSum, int nTiles, const int* __restrict__ skip) {
   VL_PDL_WAIT();
 
   if (skip && *skip) return;
+  lm_dev_scan_sums<1024>(tileSum, nTiles);
+}
+__device__ __forceinline__ void lm_dev_scan_apply(const int* __restrict__ in, int n, const int* __restrict__ tileSum, int* __restrict__ out,
+                                                  int tile, int nTiles) {  // 256 threads
   __shared__ int ws[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int running = tileSum[blockIdx.x];
+  int running = tileSum[tile];
   for (int q = 0; q < 4; ++q) {
-    const int t = blockIdx.x * 1024 + q * 256 + threadIdx.x;
+    const int t = tile * 1024 + q * 256 + threadIdx.x;
     const int v = t < n ? in[t] : 0;
     int inc = v;
     for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+    __syncthreads();  // (ws may still be read by the previous round / tile)
     if (lane == 31) ws[warp] = inc;
     __syncthreads();
     int before = 0, all = 0;
     for (int k = 0; k < 8; ++k) { if (k < warp) before += ws[k]; all += ws[k]; }
     if (t < n) out[t] = running + before + inc - v;
     running += all;
-    __syncthreads();
   }
-  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = running;  // total
+  if (tile == nTiles - 1 && threadIdx.x == 0) out[n] = running;  // total
+}
+__global__ void __launch_bounds__(256) lm_scan_apply(const int* __restrict__ in, int n, const int* __restrict__ tileSum, int* __restrict__ out,
+                                                     const int* __restrict__ skip) {
+  VL_PDL_WAIT();
+
+  if (skip && *skip) return;
+  lm_dev_scan_apply(in, n, tileSum, out, blockIdx.x, gridDim.x);
 }
 // out[0..n] = exclusive scan of in[0..n) (out[n] = total); tileSum needs ceil(n/1024)+1 ints
 int vl_scan_exclusive(vloam_b200_ctx* c, const int* in, int n, int* tileSum, int* out, const int* d_skip) {
@@ -488,13 +515,9 @@ int vl_scan_exclusive(vloam_b200_ctx* c, const int* in, int n, int* tileSum, int
   return VLOAM_OK;
 }
 
-__global__ void __launch_bounds__(256) lm_grid_fill(const LmSub* __restrict__ sub, const int* __restrict__ skip, const float4* __restrict__ mapC,
-                                                    const float4* __restrict__ mapS, const int* __restrict__ cellOfPoint,
-                                                    const int* __restrict__ cellStart, int* __restrict__ cellFill,
-                                                    float4* __restrict__ sortedPts) {
-  VL_PDL_WAIT();
-
-  if (skip && *skip) return;
+__device__ __forceinline__ void lm_dev_fill(const LmSub* __restrict__ sub, const float4* __restrict__ mapC, const float4* __restrict__ mapS,
+                                            const int* __restrict__ cellOfPoint, const int* __restrict__ cellStart, int* __restrict__ cellFill,
+                                            float4* __restrict__ sortedPts) {
   const int mc = sub->Mc, total = sub->Mc + sub->Ms;
   for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
     const int kind = g >= mc;
@@ -504,6 +527,41 @@ __global__ void __launch_bounds__(256) lm_grid_fill(const LmSub* __restrict__ su
     const int pos = cellStart[cell] + atomicAdd(&cellFill[cell], 1);
     sortedPts[pos] = make_float4(p.x, p.y, p.z, __int_as_float(id));
   }
+}
+__global__ void __launch_bounds__(256) lm_grid_fill(const LmSub* __restrict__ sub, const int* __restrict__ skip, const float4* __restrict__ mapC,
+                                                    const float4* __restrict__ mapS, const int* __restrict__ cellOfPoint,
+                                                    const int* __restrict__ cellStart, int* __restrict__ cellFill,
+                                                    float4* __restrict__ sortedPts) {
+  VL_PDL_WAIT();
+
+  if (skip && *skip) return;
+  lm_dev_fill(sub, mapC, mapS, cellOfPoint, cellStart, cellFill, sortedPts);
+}
+
+// The whole in-line sub-map build (gather, zero, count, scan, fill) as ONE cooperative launch.  It runs every
+// frame on the main stream but does real work only when the window moved: with the speculative build valid it
+// is a single grid that returns at once, where eight separately launched early-exit kernels cost ~20 us of
+// dependent launch latency.  Grid barriers separate the phases when it does run.
+struct LmInlineArgs {
+  const LmSub* sub; const int* skip; const MapCubeTable* tc; const MapCubeTable* ts; const float4* poolC; const float4* poolS;
+  float4* outC; float4* outS; int* cellCount; int* cellFill; int* cellStart; int* tileSum; int* cellOfPoint; float4* sortedPts; int nCells;
+};
+__global__ void __launch_bounds__(256) lm_inline_build(LmInlineArgs a) {
+  if (*a.skip) return;  // uniform over the grid
+  cg::grid_group grid = cg::this_grid();
+  lm_dev_gather(a.sub, a.tc, a.ts, a.poolC, a.poolS, a.outC, a.outS);
+  lm_dev_zero(a.cellCount, a.cellFill, a.nCells + 1);
+  grid.sync();
+  lm_dev_count(a.sub, a.outC, a.outS, a.cellCount, a.cellOfPoint);
+  grid.sync();
+  const int nTiles = (a.nCells + 1023) / 1024;
+  for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) lm_dev_scan_tile(a.cellCount, a.nCells, a.tileSum, tile);
+  grid.sync();
+  if (blockIdx.x == 0) lm_dev_scan_sums<256>(a.tileSum, nTiles);
+  grid.sync();
+  for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) lm_dev_scan_apply(a.cellCount, a.nCells, a.tileSum, a.cellStart, tile, nTiles);
+  grid.sync();
+  lm_dev_fill(a.sub, a.outC, a.outS, a.cellOfPoint, a.cellStart, a.cellFill, a.sortedPts);
 }
 
 // ---- fits -------------------------------------------------------------------------------------
@@ -1134,6 +1192,7 @@ struct LmDevice {  // extra device state owned by this file
   int* specOK;                       // device flag written by lm_prepare: the speculative sub-map is this frame's
   bool specQueued;                   // host: a speculative build was queued after the last map update and nothing touched the map since
   bool specEnabled;
+  int inlineGrid;                    // co-resident grid of lm_inline_build (cooperative launch)
 };
 static LmDevice* lmdev(vloam_b200_ctx* c) { return reinterpret_cast<LmDevice*>(c->gridPrm); }
 
@@ -1152,6 +1211,9 @@ int vl_lm_init(vloam_b200_ctx* c) {
   VL_CUDA(cudaMalloc(&d->specOK, sizeof(int))); VL_CUDA(cudaMemset(d->specOK, 0, sizeof(int)));
   d->specQueued = false;
   d->specEnabled = getenv("VLOAM_NO_SPECULATION") == nullptr;
+  int perSm = 0;
+  VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, lm_inline_build, 256, 0));
+  d->inlineGrid = c->num_sms * max(1, min(perSm, 4));
   d->hMapUpperC = d->hMapUpperS = 0;
   VL_TRY(vl_reserve(c, c->poolC, LM_POOL_C));
   VL_TRY(vl_reserve(c, c->poolS, LM_POOL_S));
@@ -1208,6 +1270,26 @@ static int lm_build_grid(vloam_b200_ctx* c, LmDevice* d, const LmSub* sub, const
   return VLOAM_OK;
 }
 
+// in-line sub-map build of this frame (one cooperative launch; returns at once on the device when *specOK)
+static int lm_inline_launch(vloam_b200_ctx* c, LmDevice* d, long long totalBound) {
+  LmInlineArgs a;
+  a.sub = d->subReal; a.skip = d->specOK; a.tc = c->cubeC; a.ts = c->cubeS; a.poolC = c->poolC.p; a.poolS = c->poolS.p;
+  a.outC = c->fromMapC.p; a.outS = c->fromMapS.p; a.cellCount = d->cellCount; a.cellFill = d->cellFill; a.cellStart = d->cellStart;
+  a.tileSum = d->tileSum; a.cellOfPoint = d->cellOfPoint.p; a.sortedPts = d->sortedPts.p; a.nCells = 2 * LM_NCELL;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(d->inlineGrid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = VL_STREAM(c);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  const bool prof = c->prof_name[0] && vl_prof_match(c, "lm_inline_build") && c->prof_n < VL_PROF_MAX;
+  if (prof) cudaEventRecord(c->prof_ev[c->prof_n][0], VL_STREAM(c));
+  VL_CUDA(cudaLaunchKernelEx(&cfg, lm_inline_build, a));
+  if (prof) { cudaEventRecord(c->prof_ev[c->prof_n][1], VL_STREAM(c)); c->prof_kname[c->prof_n] = "lm_inline_build";
+              c->prof_kbytes[c->prof_n] = 100.0 * (double)totalBound; c->prof_kstream[c->prof_n] = VL_STREAM(c); c->prof_n++; }
+  __atomic_fetch_add(&c->launches, 1LL, __ATOMIC_RELAXED);
+  return VLOAM_OK;
+}
+
 int vl_lm_run(vloam_b200_ctx* c) {
   LmDevice* d = lmdev(c);
   VL_TRY(vl_lm_join(c));  // the previous frame's map update has been issued (evMap recorded, host bounds updated)
@@ -1220,9 +1302,6 @@ int vl_lm_run(vloam_b200_ctx* c) {
   const int gsGrid = c->num_sms * 8;
   VL_TRY(vl_reserve(c, c->fromMapC, (size_t)max(d->hMapUpperC, 1LL), false, (size_t)d->hMapUpperC / 2 + (1 << 20)));
   VL_TRY(vl_reserve(c, c->fromMapS, (size_t)max(d->hMapUpperS, 1LL), false, (size_t)d->hMapUpperS / 2 + (1 << 20)));
-  VL_BYTES(32.0 * (double)(d->hMapUpperC + d->hMapUpperS));  // upper bound until the S2 sync; refined below
-  // Every kernel of the sub-map build returns at once when lm_prepare found the speculative build valid.
-  VL_LAUNCH(lm_gather, gsGrid, 256, 0, d->subReal, d->specOK, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, c->fromMapC.p, c->fromMapS.p);
   if (!c->stacksReady) {  // laser_mapping called without this frame's laser_odometry having queued them
     VL_CUDA(cudaStreamSynchronize(c->stream));
     VL_TRY(vl_lm_enqueue_stacks(c, c->cornerLastPtr, c->nCornerLast, c->surfLastPtr, c->nSurfLast));
@@ -1238,7 +1317,7 @@ int vl_lm_run(vloam_b200_ctx* c) {
   {
     VL_TRY(vl_reserve(c, d->cellOfPoint, (size_t)max(totalBound, 1LL), false, (size_t)totalBound / 2 + (1 << 20)));
     VL_TRY(vl_reserve(c, d->sortedPts, (size_t)max(totalBound, 1LL), false, (size_t)totalBound / 2 + (1 << 20)));
-    VL_TRY(lm_build_grid(c, d, d->subReal, d->specOK, totalBound));
+    VL_TRY(lm_inline_launch(c, d, totalBound));  // returns at once on the device when lm_prepare found the speculative build valid
     if (c->timing) VL_CUDA(cudaEventRecord(c->evx[0], c->stream));
     // only now are this frame's downsampled stacks needed (they were filtered on the side streams)
     VL_CUDA(cudaStreamWaitEvent(c->stream, c->evStacks, 0));

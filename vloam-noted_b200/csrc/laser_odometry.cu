@@ -379,6 +379,9 @@ __device__ __forceinline__ void lo_assoc_grid_dev(int qi, int lane, const float4
     const unsigned bits = __float_as_uint(t.w);                                                           \
     const int j = (int)(bits & 0xffffffu);                                                                \
     const int v = (int)(bits >> 24);                                                                      \
+    /* ring band first: with non-decreasing rings every class below lies in [id - 2, id + 2], and ~90 % */ \
+    /* of the candidates of a 64-beam cloud fail this two-instruction test before any distance is formed */ \
+    if (v >= id - 2 && v <= id + 2) {                                                                     \
     const float d = lo_sqdis(t, sx, sy, sz);                                                              \
     if (d < 25.0f) { /* the running minima start at DISTANCE_SQ_THRESHOLD; only strict < replaces them */ \
       if (j > closest) { /* forward scan LO.cpp:309-331 / 407-430 */                                      \
@@ -396,6 +399,7 @@ __device__ __forceinline__ void lo_assoc_grid_dev(int qi, int lane, const float4
           } else if (v < id) { if (d < g2.d || (d == g2.d && j > g2.j)) { g2.d = d; g2.j = j; } }         \
         }                                                                                                 \
       }                                                                                                   \
+    }                                                                                                     \
     }                                                                                                     \
   }
     LOG_VISIT(1, LOG_B_BODY);
