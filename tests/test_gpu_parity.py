@@ -488,3 +488,33 @@ def test_full_resolution_cloud_registration(pkg, op, synth, street):
         assert len(reg_g) == len(o.get("sr.laserCloud")) > 50000
         assert_bits_equal(reg_o, reg_g, "registered full-resolution cloud")
     g.close()
+
+
+@pytest.mark.gpu
+def test_concurrent_sequences_match_sequential_runs(pkg, synth, street):
+    """BASELINE config C5 on one GPU: independent sequences, one context and one host thread each, replayed
+    concurrently (every context owns four streams and a helper thread).  Poses and final maps must be bit-identical
+    to the same sequences replayed one after the other."""
+    import threading
+    nseq, frames = 3, 6
+    seqs = []
+    for q in range(nseq):
+        traj = synth.trajectory(frames, seed=300 + q)
+        seqs.append([street.scan(0, traj[k], 7000 + 100 * q + k) for k in range(frames)])
+
+    def replay(q, out):
+        g = pkg.Context(**KW[0])
+        poses = [g.process_frame(s).copy() for s in seqs[q]]
+        out[q] = (np.array(poses), g.get("lm.cornerMap"), g.get("lm.surfMap"))
+        g.close()
+
+    alone, together = [None] * nseq, [None] * nseq
+    for q in range(nseq):
+        replay(q, alone)
+    th = [threading.Thread(target=replay, args=(q, together)) for q in range(nseq)]
+    for t in th: t.start()
+    for t in th: t.join()
+    for q in range(nseq):
+        assert together[q] is not None, "a replay thread died"
+        assert (alone[q][0] == together[q][0]).all(), "poses differ when sequences share the GPU"
+        assert alone[q][1] == together[q][1] and alone[q][2] == together[q][2], "maps differ when sequences share the GPU"
