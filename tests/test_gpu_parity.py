@@ -518,3 +518,37 @@ def test_concurrent_sequences_match_sequential_runs(pkg, synth, street):
         assert together[q] is not None, "a replay thread died"
         assert (alone[q][0] == together[q][0]).all(), "poses differ when sequences share the GPU"
         assert alone[q][1] == together[q][1] and alone[q][2] == together[q][2], "maps differ when sequences share the GPU"
+
+
+@pytest.mark.gpu
+def test_map_pools_grow_instead_of_failing(pkg, synth, street):
+    """The cube pools are bump-allocated; when one is half full it is doubled at sync point S2.  A context that
+    starts with tiny pools (VLOAM_POOL_POINTS) must replay a sequence with the same poses and map bytes as one
+    with the default 16M / 48M-point pools, and importing a map larger than the pool must grow it too."""
+    import os
+    traj = synth.trajectory(8)
+    scans = [street.scan(1, traj[k], 1000 + k) for k in range(8)]
+
+    def replay():
+        g = pkg.Context(**KW[1])
+        poses = [g.process_frame(s).copy() for s in scans]
+        maps = (g.get("lm.cornerMap"), g.get("lm.surfMap"))
+        return g, np.array(poses), maps
+
+    g0, p0, m0 = replay()
+    os.environ["VLOAM_POOL_POINTS"] = "4096"
+    try:
+        g1, p1, m1 = replay()
+    finally:
+        os.environ.pop("VLOAM_POOL_POINTS", None)
+    assert (p0 == p1).all() and m0 == m1
+    assert len(m0[1]) > 4851 * 4 + 3 * 4096 * 16, "the surf map never outgrew the tiny pool: growth was not exercised"
+    os.environ["VLOAM_POOL_POINTS"] = "4096"
+    try:
+        g2 = pkg.Context(**KW[1])
+    finally:
+        os.environ.pop("VLOAM_POOL_POINTS", None)
+    g2.set("lm.cornerMap", m0[0]); g2.set("lm.surfMap", m0[1])   # import into pools that are too small
+    assert g2.get("lm.surfMap") == m0[1] and g2.get("lm.cornerMap") == m0[0]
+    for g in (g0, g1, g2):
+        g.close()

@@ -1215,8 +1215,18 @@ int vl_lm_init(vloam_b200_ctx* c) {
   VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, lm_inline_build, 256, 0));
   d->inlineGrid = c->num_sms * max(1, min(perSm, 4));
   d->hMapUpperC = d->hMapUpperS = 0;
-  VL_TRY(vl_reserve(c, c->poolC, LM_POOL_C));
-  VL_TRY(vl_reserve(c, c->poolS, LM_POOL_S));
+  // Map pools: bump allocation with doubling per cube; when a pool is half full it is doubled (copy) at sync point
+  // S2, so a long drive degrades into a rare ~ms stall instead of VLOAM_E_CAPACITY.  VLOAM_POOL_POINTS: initial
+  // size of the corner pool in points (the surf pool gets 3x), for tests of the growth path.
+  const char* pp = getenv("VLOAM_POOL_POINTS");
+  if (pp) {  // exact sizes (vl_reserve rounds small requests up)
+    const size_t pc = (size_t)max(atoll(pp), 4096LL);
+    VL_CUDA(cudaMalloc(&c->poolC.p, pc * sizeof(float4))); c->poolC.cap = pc;
+    VL_CUDA(cudaMalloc(&c->poolS.p, 3 * pc * sizeof(float4))); c->poolS.cap = 3 * pc;
+  } else {
+    VL_TRY(vl_reserve(c, c->poolC, LM_POOL_C));
+    VL_TRY(vl_reserve(c, c->poolS, LM_POOL_S));
+  }
   VL_CUDA(cudaMemset(c->cubeC, 0, sizeof(MapCubeTable)));
   VL_CUDA(cudaMemset(c->cubeS, 0, sizeof(MapCubeTable)));
   LmScalars h;
@@ -1366,6 +1376,17 @@ int vl_lm_run(vloam_b200_ctx* c) {
   VL_CUDA(cudaStreamSynchronize(c->stream));
   const int Mc = c->h_lmm->Mc, Ms = c->h_lmm->Ms;
   Qc = c->h_lmm->Qc; Qs = c->h_lmm->Qs;
+  if (c->h_lmm->overflow) { snprintf(c->err, sizeof c->err, "map pool exhausted"); return VLOAM_E_CAPACITY; }
+  // Pool head room for this frame's update: a cube that outgrows its segment gets a new one of twice its new size,
+  // so the update allocates at most 2 x (points in the map + inserts) + 256 per touched cube.  When that no longer
+  // fits, the pool is doubled (copy) now: the previous update is complete (this stream waited on evMap), the next
+  // one has not been issued, and the copy keeps every cube's offset valid.
+  {
+    const size_t needC = 2 * ((size_t)c->h_lmm->totalC + Qc) + 256 * (size_t)(VL_MAX_VALID + min(Qc, VL_CUBE_NUM));
+    const size_t needS = 2 * ((size_t)c->h_lmm->totalS + Qs) + 256 * (size_t)(VL_MAX_VALID + min(Qs, VL_CUBE_NUM));
+    if ((size_t)c->h_lmm->poolTopC + needC > c->poolC.cap) VL_TRY(vl_reserve(c, c->poolC, 2 * ((size_t)c->h_lmm->poolTopC + needC), true));
+    if ((size_t)c->h_lmm->poolTopS + needS > c->poolS.cap) VL_TRY(vl_reserve(c, c->poolS, 2 * ((size_t)c->h_lmm->poolTopS + needS), true));
+  }
   const int tailTotal = c->h_lmm->tailC + c->h_lmm->tailS;
   const int nq = Qc + Qs;
   c->lm_optimized = c->h_lmm->optimized;
@@ -1504,8 +1525,8 @@ int vl_lm_import_map(vloam_b200_ctx* c, int which, const void* data, long bytes)
     h.start[i] = (int)top; h.count[i] = counts[i]; h.cap[i] = counts[i] + counts[i] / 4 + 256;
     top += h.cap[i];
   }
-  if (top > (long long)pool.cap) { snprintf(c->err, sizeof c->err, "map pool too small for import (%lld points)", top); return VLOAM_E_CAPACITY; }
   VL_CUDA(cudaStreamSynchronize(c->stream));
+  if ((size_t)top * 2 > pool.cap) VL_TRY(vl_reserve(c, pool, (size_t)top * 2));  // (contents are replaced below)
   const char* p = (const char*)data + (size_t)VL_CUBE_NUM * 4;
   for (int i = 0; i < VL_CUBE_NUM; ++i) {
     if (counts[i] == 0) continue;
