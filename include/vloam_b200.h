@@ -71,6 +71,14 @@ int vloam_b200_begin_frame(vloam_b200_ctx* c);
  * `stride` floats apart (3 for packed XYZ, 4 for KITTI x,y,z,r).  Asynchronous
  * with respect to the host unless a getter is called. */
 int vloam_b200_scan_registration(vloam_b200_ctx* c, const float* xyz, int n, int stride);
+/* Optional look-ahead for replays: register the NEXT sweep (host pointer -- pinned for an asynchronous copy -- or
+ * device pointer).  Its scan registration is queued on a side stream from inside the processing of the current
+ * sweep and runs underneath that sweep's odometry and mapping; the following scan_registration / process_frame
+ * call with the same (pointer, n, stride) finds the work done, any other call ignores it.  The buffer must stay
+ * unchanged until then.  Results are bit-identical with or without it.  No reference counterpart: the bag player
+ * hands over one sweep at a time (MAIN.cpp:143). */
+int vloam_b200_prefetch_scan(vloam_b200_ctx* c, const float* xyz, int n, int stride);
+int vloam_b200_prefetch_scan_device(vloam_b200_ctx* c, const float* d_xyz, int n, int stride);
 /* Same, but xyz is a DEVICE pointer already resident in HBM. */
 int vloam_b200_scan_registration_device(vloam_b200_ctx* c, const float* d_xyz, int n, int stride);
 

@@ -31,10 +31,14 @@ torch.cuda.synchronize()
 rows = []
 detail = []
 walls = []
+LOOKAHEAD = os.environ.get("LOOKAHEAD") == "1"   # replay mode: register the next sweep, no full synchronize between sweeps
+host = []
 for k in range(N):
     t0 = time.perf_counter()
+    if LOOKAHEAD and k + 1 < N: ctx.prefetch_device(d[k + 1].data_ptr(), d[k + 1].shape[0], 4)
     ctx.process_frame_device(d[k].data_ptr(), d[k].shape[0], 4)
-    ctx.synchronize()
+    if not LOOKAHEAD: ctx.synchronize()
+    host.append(np.frombuffer(ctx.get_raw("timing.host"), np.float64).copy()) if LOOKAHEAD else None
     walls.append((time.perf_counter() - t0) * 1e3)
     rows.append(ctx.stage_ms())
     detail.append(np.frombuffer(ctx.get_raw("timing.detail"), np.float32).copy())
@@ -44,6 +48,9 @@ print("stage ms mean   SR/LO/LM:", rows.mean(0).round(3))
 dm = np.median(np.array(detail)[8:], 0)
 print("ms since frame start (median): SR end %.3f | LO end %.3f | sub-map build end %.3f | stacks awaited %.3f | solve 1 end %.3f | LM end %.3f" % (dm[0], dm[1], dm[3], dm[4], dm[5], dm[2]))
 print("   side streams: surf stack ready %.3f | corner stack ready %.3f | next LO grid ready %.3f" % (dm[6], dm[7], dm[8]))
+if LOOKAHEAD:
+    hm = np.median(np.array(host)[8:], 0)
+    print("host clock inside process_frame, us (median): SR adopted %.0f | odometry + look-ahead queued %.0f | S1 + side streams queued %.0f | helper joined %.0f | mapping queued %.0f | S2 passed %.0f | update submitted %.0f" % tuple(hm))
 print("launches/frame", ctx.kernel_launches / N)
 allr = np.array(walls)
 print("wall ms per frame:", " ".join("%.1f" % v for v in allr))

@@ -552,3 +552,41 @@ def test_map_pools_grow_instead_of_failing(pkg, synth, street):
     assert g2.get("lm.surfMap") == m0[1] and g2.get("lm.cornerMap") == m0[0]
     for g in (g0, g1, g2):
         g.close()
+
+
+@pytest.mark.gpu
+def test_lookahead_scan_registration_gives_identical_results(pkg, synth, street):
+    """vloam_b200_prefetch_scan[_device]: the next sweep's scan registration runs on a side stream, into a spare set
+    of buffers, underneath the current sweep's odometry and mapping, and is adopted by the next process_frame call with
+    the same buffer.  Poses and maps must equal the plain replay bit for bit -- with device and host buffers, when a
+    registered sweep is never processed, and when another sweep is processed in between."""
+    import torch
+    traj = synth.trajectory(8)
+    scans = [street.scan(1, traj[k], 1000 + k) for k in range(8)]
+    a = pkg.Context(**KW[1])
+    ref = [a.process_frame(s).copy() for s in scans]
+    ref_maps = (a.get("lm.cornerMap"), a.get("lm.surfMap"))
+    ref_sharp = a.get("sr.sharp")
+    a.close()
+    pinned = [torch.from_numpy(s).pin_memory() for s in scans]
+    dev = [torch.from_numpy(s).cuda() for s in scans]
+    for mode in ("device", "host", "mixed"):
+        b = pkg.Context(**KW[1])
+        pose = np.zeros(14)
+        for k in range(8):
+            if mode == "device":
+                if k + 1 < 8: b.prefetch_device(dev[k + 1].data_ptr(), dev[k + 1].shape[0], 4)
+                b.process_frame_device(dev[k].data_ptr(), dev[k].shape[0], 4, pose.ctypes.data)
+            elif mode == "host":
+                if k + 1 < 8: b.prefetch_ptr(pinned[k + 1].data_ptr(), pinned[k + 1].shape[0], 4)
+                b.process_frame_ptr(pinned[k].data_ptr(), pinned[k].shape[0], 4, pose.ctypes.data)
+            else:  # registrations that are skipped, stale or for the wrong sweep
+                if k in (0, 1, 4): b.prefetch_ptr(pinned[k + 1].data_ptr(), pinned[k + 1].shape[0], 4)
+                if k == 2: b.prefetch_ptr(pinned[7].data_ptr(), pinned[7].shape[0], 4)   # far-ahead sweep: stale by the time it comes
+                if k == 5: b.prefetch_device(dev[0].data_ptr(), dev[0].shape[0], 4)        # never processed
+                if k % 2: b.process_frame_device(dev[k].data_ptr(), dev[k].shape[0], 4, pose.ctypes.data)
+                else: b.process_frame_ptr(pinned[k].data_ptr(), pinned[k].shape[0], 4, pose.ctypes.data)
+            assert (pose == ref[k]).all(), "%s: frame %d differs with the look-ahead" % (mode, k)
+        assert (b.get("lm.cornerMap"), b.get("lm.surfMap")) == ref_maps, mode
+        assert_bits_equal(ref_sharp, b.get("sr.sharp"), "sr.sharp of the last sweep (%s)" % mode)
+        b.close()

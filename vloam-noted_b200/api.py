@@ -12,7 +12,7 @@ CLOUD_FULL, CLOUD_SHARP, CLOUD_LESS_SHARP, CLOUD_FLAT, CLOUD_LESS_FLAT, CLOUD_CO
 
 EXPORTS = [
     "vloam_b200_default_params", "vloam_b200_create", "vloam_b200_destroy", "vloam_b200_last_error", "vloam_b200_begin_frame",
-    "vloam_b200_scan_registration", "vloam_b200_scan_registration_device", "vloam_b200_get_cloud", "vloam_b200_laser_odometry",
+    "vloam_b200_scan_registration", "vloam_b200_prefetch_scan", "vloam_b200_prefetch_scan_device", "vloam_b200_scan_registration_device", "vloam_b200_get_cloud", "vloam_b200_laser_odometry",
     "vloam_b200_laser_mapping", "vloam_b200_process_frame", "vloam_b200_process_frame_device", "vloam_b200_synchronize",
     "vloam_b200_stream", "vloam_b200_kernel_launches", "vloam_b200_set_timing", "vloam_b200_stage_ms", "vloam_b200_debug_get",
     "vloam_b200_debug_set", "vloam_b200_profile_kernel", "vloam_b200_profile_result", "vloam_b200_profile_table", "vloam_b200_profile_timeline", "vloam_b200_register_full_cloud", "vloam_b200_lo_associate", "vloam_b200_voxel_grid", "vloam_b200_evaluate", "vloam_b200_solve",
@@ -51,6 +51,8 @@ def load_lib(build=False):
     L.vloam_b200_begin_frame.argtypes = [vp]
     L.vloam_b200_scan_registration.argtypes = [vp, vp, ci, ci]
     L.vloam_b200_scan_registration_device.argtypes = [vp, vp, ci, ci]
+    L.vloam_b200_prefetch_scan.argtypes = [vp, vp, ci, ci]
+    L.vloam_b200_prefetch_scan_device.argtypes = [vp, vp, ci, ci]
     L.vloam_b200_get_cloud.argtypes = [vp, ci, vp, ci]
     L.vloam_b200_laser_odometry.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp, vp]
     L.vloam_b200_laser_mapping.argtypes = [vp, vp, vp]
@@ -178,6 +180,13 @@ class Context:
         pose = np.zeros(14)
         self._chk(self.L.vloam_b200_process_frame(self.h, a.ctypes.data, a.shape[0], a.shape[1], pose.ctypes.data if want_pose else None))
         return pose
+
+    def prefetch_ptr(self, host_ptr, n, stride):
+        """Register the next sweep (pinned host pointer): its scan registration runs underneath the current sweep."""
+        return self._chk(self.L.vloam_b200_prefetch_scan(self.h, host_ptr, n, stride))
+
+    def prefetch_device(self, dptr, n, stride):
+        return self._chk(self.L.vloam_b200_prefetch_scan_device(self.h, dptr, n, stride))
 
     def process_frame_ptr(self, host_ptr, n, stride, pose_ptr):
         return self._chk(self.L.vloam_b200_process_frame(self.h, host_ptr, n, stride, pose_ptr))

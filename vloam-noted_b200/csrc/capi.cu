@@ -26,6 +26,37 @@ const char* vloam_b200_last_error(const vloam_b200_ctx* c) { return c ? c->err :
     if (e_ != cudaSuccess) { fprintf(stderr, "vloam_b200_create: %s: %s\n", #call, cudaGetErrorString(e_)); return VLOAM_E_CUDA; } \
   } while (0)
 
+// fixed-size arrays, counters and the completion event of one scan-registration field set (VL_SR_FIELDS)
+static int alloc_sr_fixed(vloam_b200_ctx* c) {
+  const int R = VL_MAX_RINGS, S = VL_MAX_RINGS * VL_SECTORS;
+  VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evSR, cudaEventDisableTiming));
+  VL_CUDA_CREATE(cudaMalloc(&c->ringCount, sizeof(int) * R));
+  VL_CUDA_CREATE(cudaMalloc(&c->ringStart, sizeof(int) * (R + 1)));
+  VL_CUDA_CREATE(cudaMemset(c->ringCount, 0, sizeof(int) * R));
+  VL_CUDA_CREATE(cudaMemset(c->ringStart, 0, sizeof(int) * (R + 1)));
+  VL_CUDA_CREATE(cudaMalloc(&c->srs, sizeof(SrScalars)));
+  VL_CUDA_CREATE(cudaMemset(c->srs, 0, sizeof(SrScalars)));
+  VL_CUDA_CREATE(cudaMallocHost(&c->h_srs, sizeof(SrScalars)));
+  memset(c->h_srs, 0, sizeof(SrScalars));
+  VL_CUDA_CREATE(cudaMalloc(&c->provSharp, sizeof(int) * S * 2));
+  VL_CUDA_CREATE(cudaMalloc(&c->provLess, sizeof(int) * S * 20));
+  VL_CUDA_CREATE(cudaMalloc(&c->provFlat, sizeof(int) * S * 4));
+  int** smalls[] = {&c->cntSharp, &c->cntLess, &c->cntFlat, &c->offSharp, &c->offLess, &c->offFlat};
+  for (int** q : smalls) { VL_CUDA_CREATE(cudaMalloc(q, sizeof(int) * S)); VL_CUDA_CREATE(cudaMemset(*q, 0, sizeof(int) * S)); }
+  VL_CUDA_CREATE(cudaMalloc(&c->ringDsCount, sizeof(int) * R));
+  VL_CUDA_CREATE(cudaMalloc(&c->ringDsOff, sizeof(int) * R));
+  c->sr_counts_valid = false; c->n_in = 0; c->nKept = c->nSharp = c->nLessSharp = c->nFlat = c->nLessFlat = 0;
+  return VLOAM_OK;
+}
+static void free_sr_set(vloam_b200_ctx* c) {  // the set currently swapped into the context
+  void* dev[] = {c->ringCount, c->ringStart, c->srs, c->provSharp, c->provLess, c->provFlat, c->cntSharp, c->cntLess, c->cntFlat, c->offSharp,
+                 c->offLess, c->offFlat, c->ringDsCount, c->ringDsOff, c->in.p, c->ring.p, c->ori.p, c->blockHist.p, c->cloud.p, c->curv.p,
+                 c->label.p, c->picked.p, c->sortScratch.p, c->lessFlatProv.p, c->selIdx.p, c->sharp.p, c->flat.p};
+  for (void* p : dev) if (p) cudaFree(p);
+  if (c->h_srs) cudaFreeHost(c->h_srs);
+  if (c->evSR) cudaEventDestroy(c->evSR);
+}
+
 int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** out) {
   if (!p || !out) return VLOAM_E_INVALID;
   // SR.cpp:58-61, 255-259: only 16 / 32 / 64 beams (128 = builder extension)
@@ -48,7 +79,10 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   VL_CUDA_CREATE(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
   VL_CUDA_CREATE(cudaStreamCreateWithFlags(&c->stream4, cudaStreamNonBlocking));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evStacksC, cudaEventDisableTiming));
-  VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evSR, cudaEventDisableTiming));
+  VL_CUDA_CREATE(cudaStreamCreateWithFlags(&c->streamAux, cudaStreamNonBlocking));
+  VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evAux, cudaEventDisableTiming));
+  VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evAuxZero, cudaEventDisableTiming));
+  VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evUpd, cudaEventDisableTiming));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evStacks, cudaEventDisableTiming));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evLast, cudaEventDisableTiming));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evPose, cudaEventDisableTiming));
@@ -56,22 +90,12 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   c->stacksReady = false; c->lm_reset_pending = true; c->lastSet = 0; c->loGridValid[0] = c->loGridValid[1] = false;
   for (int k = 0; k < 4; ++k) VL_CUDA_CREATE(cudaEventCreate(&c->ev[k]));
   for (int k = 0; k < 8; ++k) { VL_CUDA_CREATE(cudaEventCreate(&c->evx[k])); VL_CUDA_CREATE(cudaEventRecord(c->evx[k], c->stream)); }
-  const int R = VL_MAX_RINGS, S = VL_MAX_RINGS * VL_SECTORS;
-  VL_CUDA_CREATE(cudaMalloc(&c->ringCount, sizeof(int) * R));
-  VL_CUDA_CREATE(cudaMalloc(&c->ringStart, sizeof(int) * (R + 1)));
-  VL_CUDA_CREATE(cudaMemset(c->ringCount, 0, sizeof(int) * R));
-  VL_CUDA_CREATE(cudaMemset(c->ringStart, 0, sizeof(int) * (R + 1)));
-  VL_CUDA_CREATE(cudaMalloc(&c->srs, sizeof(SrScalars)));
-  VL_CUDA_CREATE(cudaMemset(c->srs, 0, sizeof(SrScalars)));
-  VL_CUDA_CREATE(cudaMallocHost(&c->h_srs, sizeof(SrScalars)));
-  memset(c->h_srs, 0, sizeof(SrScalars));
-  VL_CUDA_CREATE(cudaMalloc(&c->provSharp, sizeof(int) * S * 2));
-  VL_CUDA_CREATE(cudaMalloc(&c->provLess, sizeof(int) * S * 20));
-  VL_CUDA_CREATE(cudaMalloc(&c->provFlat, sizeof(int) * S * 4));
-  int** smalls[] = {&c->cntSharp, &c->cntLess, &c->cntFlat, &c->offSharp, &c->offLess, &c->offFlat};
-  for (int** q : smalls) { VL_CUDA_CREATE(cudaMalloc(q, sizeof(int) * S)); VL_CUDA_CREATE(cudaMemset(*q, 0, sizeof(int) * S)); }
-  VL_CUDA_CREATE(cudaMalloc(&c->ringDsCount, sizeof(int) * R));
-  VL_CUDA_CREATE(cudaMalloc(&c->ringDsOff, sizeof(int) * R));
+  VL_TRY(alloc_sr_fixed(c));
+  c->srNext = new SrSet();
+  vl_sr_swap(c, *c->srNext);      // the spare set gets its own fixed-size arrays, counters and event
+  { const int r_ = alloc_sr_fixed(c); vl_sr_swap(c, *c->srNext); if (r_ != VLOAM_OK) return r_; }
+  c->srNextKey = nullptr; c->srNextValid = false; c->srPendKey = nullptr; c->srPendDevice = false;
+  VL_CUDA_CREATE(cudaStreamCreateWithFlags(&c->streamSR, cudaStreamNonBlocking));
   VL_CUDA_CREATE(cudaMalloc(&c->los, sizeof(LoScalars)));
   VL_CUDA_CREATE(cudaMallocHost(&c->h_los, sizeof(LoScalars)));
   LoScalars hl; memset(&hl, 0, sizeof hl); hl.para_q[3] = 1.0; hl.q_w[3] = 1.0;  // LO.cpp:81-91
@@ -108,22 +132,23 @@ void vloam_b200_destroy(vloam_b200_ctx* c) {
   vl_lm_shutdown(c);
   cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream3); cudaStreamSynchronize(c->stream4);
   // Device memory is released wholesale: contexts live for a whole replay (MAIN.cpp:118-124).
-  void* singles[] = {c->ringCount, c->ringStart, c->srs, c->provSharp, c->provLess, c->provFlat, c->cntSharp, c->cntLess, c->cntFlat,
-                     c->offSharp, c->offLess, c->offFlat, c->ringDsCount, c->ringDsOff, c->los, c->evalOut, c->lms, c->lmm, c->cubeC,
-                     c->cubeS, c->vScalars};
+  cudaStreamSynchronize(c->streamSR);
+  free_sr_set(c);
+  if (c->srNext) { vl_sr_swap(c, *c->srNext); free_sr_set(c); delete c->srNext; c->srNext = nullptr; }
+  cudaStreamDestroy(c->streamSR);
+  void* singles[] = {c->los, c->evalOut, c->lms, c->lmm, c->cubeC, c->cubeS, c->vScalars};
   for (void* p : singles) if (p) cudaFree(p);
-  void* bufs[] = {c->in.p, c->ring.p, c->ori.p, c->blockHist.p, c->cloud.p, c->curv.p, c->label.p, c->picked.p, c->sortScratch.p,
-                  c->lessFlatProv.p, c->selIdx.p, c->sharp.p, c->lessSharp[0].p, c->lessSharp[1].p, c->flat.p, c->lessFlat[0].p,
-                  c->lessFlat[1].p, c->loCornerIdx.p, c->loSurfIdx.p, c->factors.p, c->factorValid.p, c->evalPartials.p,
+  void* bufs[] = {c->lessSharp[0].p, c->lessSharp[1].p, c->lessSharp[2].p, c->lessFlat[0].p, c->lessFlat[1].p, c->lessFlat[2].p, c->loCornerIdx.p, c->loSurfIdx.p, c->factors.p, c->factorValid.p, c->evalPartials.p,
                   c->poolC.p, c->poolS.p, c->stackC.p, c->stackS.p, c->fromMapC.p, c->fromMapS.p, c->knnIdx.p, c->knnD2.p, c->knnOk.p,
                   c->vKeys.p, c->vKeys2.p, c->vHead.p, c->vScan.p, c->vScan2.p, c->vOut.p, c->vIn.p, c->regOut.p, c->tailKeys.p, c->staging.p};
   for (void* p : bufs) if (p) cudaFree(p);
-  cudaFreeHost(c->h_srs); cudaFreeHost(c->h_los); cudaFreeHost(c->h_lms); cudaFreeHost(c->h_lmm); cudaFreeHost(c->h_vScalars);
+  cudaFreeHost(c->h_los); cudaFreeHost(c->h_lms); cudaFreeHost(c->h_lmm); cudaFreeHost(c->h_vScalars);
   for (int k = 0; k < 4; ++k) cudaEventDestroy(c->ev[k]);
   for (int k = 0; k < 8; ++k) cudaEventDestroy(c->evx[k]);
   cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream3);
-  cudaEventDestroy(c->evSR); cudaEventDestroy(c->evStacks); cudaEventDestroy(c->evLast); cudaEventDestroy(c->evPose); cudaEventDestroy(c->evMap);
+  cudaEventDestroy(c->evStacks); cudaEventDestroy(c->evLast); cudaEventDestroy(c->evPose); cudaEventDestroy(c->evMap);
   cudaEventDestroy(c->evStacksC);
+  cudaStreamSynchronize(c->streamAux); cudaEventDestroy(c->evAux); cudaEventDestroy(c->evAuxZero); cudaEventDestroy(c->evUpd); cudaStreamDestroy(c->streamAux);
   cudaStreamDestroy(c->stream2); cudaStreamDestroy(c->stream3); cudaStreamDestroy(c->stream4);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -135,19 +160,78 @@ int vloam_b200_begin_frame(vloam_b200_ctx* c) {
   return VLOAM_OK;
 }
 
+// Look-ahead for replays: register the NEXT sweep (device or host pointer).  Its scan registration is queued on a side
+// stream from inside the processing of the current sweep, into the spare field set, so it runs underneath this sweep's
+// odometry and mapping; the following scan_registration / process_frame call with the same (pointer, n, stride)
+// finds the work done.  Any other call ignores (and later overwrites) it.  The buffer must stay valid and unchanged
+// until that call.  No reference counterpart: the bag player hands over one sweep at a time (MAIN.cpp:143).
+int vloam_b200_prefetch_scan_device(vloam_b200_ctx* c, const float* d_xyz, int n, int stride) {
+  if (n <= 0 || stride < 3 || !d_xyz) { snprintf(c->err, sizeof c->err, "bad cloud shape"); return VLOAM_E_INVALID; }
+  c->srPendKey = d_xyz; c->srPendN = n; c->srPendStride = stride; c->srPendDevice = true;
+  return VLOAM_OK;
+}
+int vloam_b200_prefetch_scan(vloam_b200_ctx* c, const float* xyz, int n, int stride) {
+  if (n <= 0 || stride < 3 || !xyz) { snprintf(c->err, sizeof c->err, "bad cloud shape"); return VLOAM_E_INVALID; }
+  c->srPendKey = xyz; c->srPendN = n; c->srPendStride = stride; c->srPendDevice = false;
+  return VLOAM_OK;
+}
+
+// queue the registered look-ahead: spare set swapped in, scan registration on streamSR, set swapped back out.
+// Called by the odometry stage once its own kernels are queued (the host would only wait at S1 otherwise): issuing
+// these ~10 launches before the odometry delays the sweep that is being processed.
+int vl_launch_lookahead(vloam_b200_ctx* c) {
+  if (!c->srPendKey) return VLOAM_OK;
+  const float* key = c->srPendKey; const int n = c->srPendN, stride = c->srPendStride; const bool dev = c->srPendDevice;
+  c->srPendKey = nullptr;
+  const int curNow = c->cur;
+  vl_sr_swap(c, *c->srNext);
+  c->cur = curNow;  // vl_sr_run advances it: the look-ahead writes the generation after this sweep's
+  vl_tls_stream = c->streamSR;
+  int r = VLOAM_OK;
+  const float* d_xyz = key;
+  if (!dev) {
+    r = vl_reserve(c, c->in, (size_t)n * stride);
+    if (r == VLOAM_OK && cudaMemcpyAsync(c->in.p, key, (size_t)n * stride * sizeof(float), cudaMemcpyHostToDevice, c->streamSR) != cudaSuccess) r = VLOAM_E_CUDA;
+    d_xyz = c->in.p;
+  }
+  if (r == VLOAM_OK) r = vl_sr_run(c, d_xyz, n, stride);
+  vl_tls_stream = nullptr;
+  vl_sr_swap(c, *c->srNext);
+  c->srNextValid = r == VLOAM_OK; c->srNextKey = key; c->srNextN = n; c->srNextStride = stride;
+  return r;
+}
+
+// this sweep was registered ahead: adopt the spare set (its kernels may still be running on streamSR)
+static bool adopt_lookahead(vloam_b200_ctx* c, const float* key, int n, int stride) {
+  if (!c->srNextValid || key != c->srNextKey || n != c->srNextN || stride != c->srNextStride) return false;
+  vl_sr_swap(c, *c->srNext);
+  c->srNextValid = false;
+  cudaStreamWaitEvent(c->stream, c->evSR, 0);
+  return true;
+}
+
 int vloam_b200_scan_registration_device(vloam_b200_ctx* c, const float* d_xyz, int n, int stride) {
   if (n < 0 || stride < 3) { snprintf(c->err, sizeof c->err, "bad cloud shape"); return VLOAM_E_INVALID; }
   if (c->timing) VL_CUDA(cudaEventRecord(c->ev[0], c->stream));
-  VL_TRY(vl_sr_run(c, d_xyz, n, stride));
+  if (!adopt_lookahead(c, d_xyz, n, stride)) {
+    c->srNextValid = false;  // a look-ahead result for another sweep targets the generation this run is about to write
+    VL_TRY(vl_sr_run(c, d_xyz, n, stride));
+  }
   if (c->timing) VL_CUDA(cudaEventRecord(c->ev[1], c->stream));
   return VLOAM_OK;
 }
 
 int vloam_b200_scan_registration(vloam_b200_ctx* c, const float* xyz, int n, int stride) {
   if (n < 0 || stride < 3 || (n > 0 && !xyz)) { snprintf(c->err, sizeof c->err, "bad cloud shape"); return VLOAM_E_INVALID; }
-  VL_TRY(vl_reserve(c, c->in, (size_t)max(n, 1) * stride));
-  if (n > 0) VL_CUDA(cudaMemcpyAsync(c->in.p, xyz, (size_t)n * stride * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  return vloam_b200_scan_registration_device(c, c->in.p, n, stride);
+  if (c->timing) VL_CUDA(cudaEventRecord(c->ev[0], c->stream));
+  if (!adopt_lookahead(c, xyz, n, stride)) {
+    c->srNextValid = false;
+    VL_TRY(vl_reserve(c, c->in, (size_t)max(n, 1) * stride));
+    if (n > 0) VL_CUDA(cudaMemcpyAsync(c->in.p, xyz, (size_t)n * stride * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    VL_TRY(vl_sr_run(c, c->in.p, n, stride));
+  }
+  if (c->timing) VL_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  return VLOAM_OK;
 }
 
 int vloam_b200_get_cloud(vloam_b200_ctx* c, int which, float* out, int cap_points) {
@@ -216,6 +300,7 @@ int vloam_b200_register_full_cloud(vloam_b200_ctx* c, float* out, int cap_points
 }
 
 static int process_common(vloam_b200_ctx* c, double* pose_out) {
+  VL_HOST_MARK(1);
   VL_TRY(vloam_b200_laser_odometry(c, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr));
   if (pose_out) {
     VL_TRY(vl_lm_run(c));
@@ -233,11 +318,13 @@ static int process_common(vloam_b200_ctx* c, double* pose_out) {
 }
 
 int vloam_b200_process_frame(vloam_b200_ctx* c, const float* xyz, int n, int stride, double* pose_out) {
+  VL_HOST_MARK(0);
   VL_TRY(vloam_b200_begin_frame(c));
   VL_TRY(vloam_b200_scan_registration(c, xyz, n, stride));
   return process_common(c, pose_out);
 }
 int vloam_b200_process_frame_device(vloam_b200_ctx* c, const float* d_xyz, int n, int stride, double* pose_out) {
+  VL_HOST_MARK(0);
   VL_TRY(vloam_b200_begin_frame(c));
   VL_TRY(vloam_b200_scan_registration_device(c, d_xyz, n, stride));
   return process_common(c, pose_out);
@@ -245,6 +332,8 @@ int vloam_b200_process_frame_device(vloam_b200_ctx* c, const float* d_xyz, int n
 
 int vloam_b200_synchronize(vloam_b200_ctx* c) {
   VL_TRY(vl_lm_join(c));
+  VL_CUDA(cudaStreamSynchronize(c->streamSR));
+  VL_CUDA(cudaStreamSynchronize(c->streamAux));
   VL_CUDA(cudaStreamSynchronize(c->stream)); VL_CUDA(cudaStreamSynchronize(c->stream2)); VL_CUDA(cudaStreamSynchronize(c->stream3));
   VL_CUDA(cudaStreamSynchronize(c->stream4));
   return VLOAM_OK;
@@ -307,12 +396,12 @@ int vloam_b200_profile_table(vloam_b200_ctx* c, char* buf, int cap) {
 int vloam_b200_profile_timeline(vloam_b200_ctx* c, char* buf, int cap) {
   VL_TRY(vloam_b200_synchronize(c));
   std::string out;
-  const cudaStream_t ss[4] = {c->stream, c->stream2, c->stream3, c->stream4};
+  const cudaStream_t ss[6] = {c->stream, c->stream2, c->stream3, c->stream4, c->streamSR, c->streamAux};
   for (int k = 0; k < c->prof_n; ++k) {
     float t0 = 0, t1 = 0;
     VL_CUDA(cudaEventElapsedTime(&t0, c->prof_ev[0][0], c->prof_ev[k][0]));
     VL_CUDA(cudaEventElapsedTime(&t1, c->prof_ev[0][0], c->prof_ev[k][1]));
-    int si = 0; for (int q = 0; q < 4; ++q) if (ss[q] == c->prof_kstream[k]) si = q;
+    int si = 0; for (int q = 0; q < 6; ++q) if (ss[q] == c->prof_kstream[k]) si = q;
     char line[256]; snprintf(line, sizeof line, "%s %d %.3f %.3f\n", c->prof_kname[k], si, t0 * 1e3, t1 * 1e3);
     out += line;
   }
@@ -375,6 +464,12 @@ long vloam_b200_debug_get(vloam_b200_ctx* c, const char* name, void* out, long c
       if (kind == "sok") return put_dev(c, c->dbgKnnOk[k][1].p, (size_t)Qs * 4, out, cap);
     }
   }
+  if (n == "timing.host") {  // timing mode: host clock in us since process_frame was entered
+    // {SR queued / adopted, odometry queued (+ look-ahead), S1 passed + side streams queued, helper joined, mapping queued, S2 passed}
+    double v[7];
+    for (int k = 0; k < 7; ++k) v[k] = c->hostT[k + 1] - c->hostT[0];
+    return put_host(v, sizeof v, out, cap);
+  }
   if (n == "timing.detail") {  // timing mode: ms since the start of the frame's scan registration
     // {SR end, LO end, LM end, sub-map build end, stacks awaited + counts set, first solve end, surf stack ready, corner stack ready, next LO grid ready}
     float v[9] = {0};
@@ -426,7 +521,8 @@ int vloam_b200_debug_set(vloam_b200_ctx* c, const char* name, const void* data, 
   if (n == "lo.last") {  // blob: int nc, int ns, corner points, surf points  (the state solveLO swaps in, LO.cpp:558-574)
     const int* hdr = (const int*)data;
     if (bytes < 8 || bytes != 8 + ((long)hdr[0] + hdr[1]) * 16) { snprintf(c->err, sizeof c->err, "lo.last blob size mismatch"); return VLOAM_E_INVALID; }
-    const int o = c->cur ^ 1;  // the buffer the next frame will not write
+    const int o = (c->cur + 1) % 3;  // (cur becomes o below, so the next sweep's scan registration writes (o + 1) % 3)
+    c->srNextValid = false;        // a look-ahead result was computed into buffer o: drop it
     VL_TRY(vl_reserve(c, c->lessSharp[o], (size_t)max(hdr[0], 1)));
     VL_TRY(vl_reserve(c, c->lessFlat[o], (size_t)max(hdr[1], 1)));
     const char* p = (const char*)data + 8;

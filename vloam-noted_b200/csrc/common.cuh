@@ -87,6 +87,9 @@ struct DBuf {  // growable device buffer
 // Launch helpers take their stream from here: the map update of a frame is issued by a helper thread
 // (laser_mapping.cu) while the calling thread already queues the next sweep, so "the current stream" is a
 // per-thread notion.  Non-null: this thread's launches go there instead of c->stream.
+#include <chrono>
+static inline double vl_now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+#define VL_HOST_MARK(k) do { if (c->timing) c->hostT[k] = vl_now_us(); } while (0)
 extern thread_local cudaStream_t vl_tls_stream;
 #define VL_STREAM(c) (vl_tls_stream ? vl_tls_stream : (c)->stream)
 struct VlWorker;
@@ -98,6 +101,8 @@ struct vloam_b200_ctx {
   cudaStream_t stream2;       // side stream: work that is independent of the odometry solve overlaps it
   cudaStream_t stream4;       // second side stream: the corner stack filter runs beside the surf one
   cudaEvent_t evStacksC;
+  cudaStream_t streamAux;     // map-update work that is off the chain update -> speculative sub-map (zeroing, outside appends)
+  cudaEvent_t evAux, evAuxZero, evUpd;
   cudaStream_t stream3;       // map update of frame k runs here while frame k+1's scan registration / odometry run on `stream`
   cudaEvent_t evSR;           // scan registration of this frame finished and its counts are in h_srs
   cudaEvent_t evStacks;       // this frame's downsampled stacks are ready
@@ -112,6 +117,7 @@ struct vloam_b200_ctx {
   int num_sms;
   bool timing;
   cudaEvent_t ev[4];
+  double hostT[8];     // timing mode only: host clock (us) at marks inside a frame (see "timing.host" in capi.cu)
   cudaEvent_t evx[8];  // timing mode only: finer marks (see "timing.detail" in capi.cu)
   float stage_ms[3];
 
@@ -136,10 +142,16 @@ struct vloam_b200_ctx {
   DBuf<float4> lessFlatProv;  // per-ring downsampled points at ringStart[r]
   int* ringDsCount; int* ringDsOff;
   DBuf<int> selIdx;           // per-ring compacted selection (original indices)
-  DBuf<float4> sharp, lessSharp[2], flat, lessFlat[2];  // [cur] of the double-buffered pair is this frame
+  DBuf<float4> sharp, flat;
+  DBuf<float4> lessSharp[3], lessFlat[3];  // three generations: the "last" clouds, this frame's ([cur]) and the look-ahead's
   int cur;                    // index of this frame's lessSharp / lessFlat buffer
   int nKept, nSharp, nLessSharp, nFlat, nLessFlat;  // host copies (valid after the SR sync point)
   bool sr_counts_valid;
+  // look-ahead scan registration (vloam_b200_prefetch_scan[_device]): a second set of every field above (VL_SR_FIELDS)
+  struct SrSet* srNext;       // spare set; holds the results for srNextKey when srNextValid
+  const float* srNextKey; int srNextN, srNextStride; bool srNextValid;
+  const float* srPendKey; int srPendN, srPendStride; bool srPendDevice;  // registered, not yet launched
+  cudaStream_t streamSR;
 
   // ---- laser odometry
   LoScalars* los; LoScalars* h_los;
@@ -193,6 +205,29 @@ struct vloam_b200_ctx {
   int prof_n, prof_created;
   double prof_bytes, prof_next_bytes;
 };
+
+// Every per-sweep field of the scan-registration stage (names as in vloam_b200_ctx).  The look-ahead keeps a second
+// set: it is swapped into the context while its kernels are queued and swapped back afterwards, and swapped in for
+// good when the sweep it belongs to is processed.  (The kernels captured the pointers at launch; swapping is host
+// bookkeeping only.)
+#define VL_SR_FIELDS(X)                                                                                              \
+  X(DBuf<float>, in) X(int, n_in) X(int, stride) X(DBuf<int>, ring) X(DBuf<float>, ori) X(DBuf<int>, blockHist)        \
+  X(int*, ringCount) X(int*, ringStart) X(SrScalars*, srs) X(SrScalars*, h_srs) X(DBuf<float4>, cloud) X(DBuf<float>, curv) \
+  X(DBuf<int>, label) X(DBuf<unsigned char>, picked) X(DBuf<unsigned long long>, sortScratch)                        \
+  X(int*, provSharp) X(int*, provLess) X(int*, provFlat) X(int*, cntSharp) X(int*, cntLess) X(int*, cntFlat)          \
+  X(int*, offSharp) X(int*, offLess) X(int*, offFlat) X(DBuf<float4>, lessFlatProv) X(int*, ringDsCount) X(int*, ringDsOff) \
+  X(DBuf<int>, selIdx) X(DBuf<float4>, sharp) X(DBuf<float4>, flat) X(int, cur)                                      \
+  X(int, nKept) X(int, nSharp) X(int, nLessSharp) X(int, nFlat) X(int, nLessFlat) X(bool, sr_counts_valid) X(cudaEvent_t, evSR)
+struct SrSet {
+#define VL_X(type, name) type name{};
+  VL_SR_FIELDS(VL_X)
+#undef VL_X
+};
+static inline void vl_sr_swap(vloam_b200_ctx* c, SrSet& s) {
+#define VL_X(type, name) { type t_ = c->name; c->name = s.name; s.name = t_; }
+  VL_SR_FIELDS(VL_X)
+#undef VL_X
+}
 
 struct GridParams {
   float ox, oy, oz;   // origin (min corner)
@@ -279,6 +314,7 @@ int vl_lo_build_last(vloam_b200_ctx* c, int set, const float4* corner, int nc, c
 int vl_lm_run(vloam_b200_ctx* c);
 int vl_lm_enqueue_stacks(vloam_b200_ctx* c, const float4* corner, int nc, const float4* surf, int ns);
 int vl_lm_init(vloam_b200_ctx* c);
+extern "C" int vl_launch_lookahead(vloam_b200_ctx* c);  // capi.cu: queue the registered look-ahead scan registration (no-op without one)
 int vl_sr_set_attrs(vloam_b200_ctx* c);
 int vl_sort_set_attrs(vloam_b200_ctx* c);
 int vl_solver_set_attrs(vloam_b200_ctx* c);

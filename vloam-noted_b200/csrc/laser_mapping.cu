@@ -1267,11 +1267,13 @@ int vl_lm_enqueue_stacks(vloam_b200_ctx* c, const float4* corner, int nc, const 
 }
 
 // search grid over the gathered sub-map (LM.cpp:519-520's two KD-tree builds): counting sort into 2 m cells
-static int lm_build_grid(vloam_b200_ctx* c, LmDevice* d, const LmSub* sub, const int* d_skip, long long totalBound) {
+static int lm_build_grid(vloam_b200_ctx* c, LmDevice* d, const LmSub* sub, const int* d_skip, long long totalBound, bool zeroed = false) {
   const int nCells = 2 * LM_NCELL;
   const int gsGrid = c->num_sms * 8;
-  VL_BYTES(8.0 * (nCells + 1));
-  VL_LAUNCH(lm_grid_zero, gsGrid, 256, 0, d->cellCount, d->cellFill, nCells + 1, d_skip);
+  if (!zeroed) {
+    VL_BYTES(8.0 * (nCells + 1));
+    VL_LAUNCH(lm_grid_zero, gsGrid, 256, 0, d->cellCount, d->cellFill, nCells + 1, d_skip);
+  }
   VL_BYTES(24.0 * (double)totalBound);  // read point, write cell id, atomic on the cell counter
   VL_LAUNCH(lm_grid_count, gsGrid, 256, 0, sub, d_skip, c->fromMapC.p, c->fromMapS.p, d->cellCount, d->cellOfPoint.p);
   VL_TRY(vl_scan_exclusive(c, d->cellCount, nCells, d->tileSum, d->cellStart, d_skip));
@@ -1302,9 +1304,12 @@ static int lm_inline_launch(vloam_b200_ctx* c, LmDevice* d, long long totalBound
 
 int vl_lm_run(vloam_b200_ctx* c) {
   LmDevice* d = lmdev(c);
+  VL_HOST_MARK(3);
   VL_TRY(vl_lm_join(c));  // the previous frame's map update has been issued (evMap recorded, host bounds updated)
+  VL_HOST_MARK(4);
   const int skip = c->skip_frame ? 1 : 0;
   VL_CUDA(cudaStreamWaitEvent(c->stream, c->evMap, 0));  // the previous frame's map update (stream3) must be complete
+  VL_CUDA(cudaStreamWaitEvent(c->stream, c->evAux, 0));  // ... including its outside appends (streamAux)
   VL_LAUNCH(lm_prepare, 1, 1024, 0, c->lmm, c->los, c->cubeC, c->cubeS, d->work, skip, c->lm_reset_pending ? 1 : 0, d->subReal, d->subSpec,
             d->specQueued ? 1 : 0, d->specOK);
   c->lm_reset_pending = false;
@@ -1373,7 +1378,9 @@ int vl_lm_run(vloam_b200_ctx* c) {
   VL_CUDA(cudaEventRecord(c->evPose, c->stream));
   // ---- sync point S2: sizes for the map update (and the pose, which is final now)
   VL_CUDA(cudaMemcpyAsync(c->h_lmm, c->lmm, sizeof(LmScalars), cudaMemcpyDeviceToHost, c->stream));
+  VL_HOST_MARK(5);
   VL_CUDA(cudaStreamSynchronize(c->stream));
+  VL_HOST_MARK(6);
   const int Mc = c->h_lmm->Mc, Ms = c->h_lmm->Ms;
   Qc = c->h_lmm->Qc; Qs = c->h_lmm->Qs;
   if (c->h_lmm->overflow) { snprintf(c->err, sizeof c->err, "map pool exhausted"); return VLOAM_E_CAPACITY; }
@@ -1395,6 +1402,15 @@ int vl_lm_run(vloam_b200_ctx* c) {
   vl_tls_stream = c->stream3;  // every launch helper below issues on the update's stream, whichever thread runs this
   struct Restore { ~Restore() { vl_tls_stream = nullptr; } } restore;
   VL_CUDA(cudaStreamWaitEvent(c->stream3, c->evPose, 0));
+  const bool spec = d->specEnabled && !capture;
+  if (spec) {  // the cell counters of the speculative grid are zeroed beside the update, not behind it
+    VL_CUDA(cudaStreamWaitEvent(c->streamAux, c->evPose, 0));
+    vl_tls_stream = c->streamAux;
+    VL_BYTES(8.0 * (2 * LM_NCELL + 1));
+    VL_LAUNCH(lm_grid_zero, gsGrid, 256, 0, d->cellCount, d->cellFill, 2 * LM_NCELL + 1, (const int*)nullptr);
+    vl_tls_stream = c->stream3;
+    VL_CUDA(cudaEventRecord(c->evAuxZero, c->streamAux));
+  }
   const int nKeys = tailTotal + nq;
   if (nKeys > 0) {
     int P = 2; while (P < nKeys) P <<= 1;
@@ -1418,10 +1434,18 @@ int vl_lm_run(vloam_b200_ctx* c) {
     VL_BYTES(32.0 * (Mc + Ms + nq));  // staging -> pool copy
     VL_LAUNCH(rf_commit, gsGrid, 256, 0, c->staging.p, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p);
     VL_LAUNCH(rf_finish, 1, 256, 0, c->lmm, d->work, c->cubeC, c->cubeS);
-    if (nq > 0)
+    if (nq > 0) {
+      // Points that fell outside the 5x5x3 window go to cubes the speculative sub-map never reads: this single-CTA
+      // kernel (~20 us) runs beside the sub-map build; the next solveMapping waits on both (evMap, evAux).
+      VL_CUDA(cudaEventRecord(c->evUpd, c->stream3));
+      VL_CUDA(cudaStreamWaitEvent(c->streamAux, c->evUpd, 0));
+      vl_tls_stream = c->streamAux;
       VL_LAUNCH(rf_append_outside, 1, 1024, 0, c->lmm, d->newPts.p, d->newCube.p, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, (int)c->poolC.cap,
                 (int)c->poolS.cap);
+      vl_tls_stream = c->stream3;
+    }
   }
+  VL_CUDA(cudaEventRecord(c->evAux, c->streamAux));
   // the map after this frame's update holds at most the points it held before plus this frame's inserts
   d->hMapUpperC = totalC + Qc; d->hMapUpperS = totalS + Qs;
   // ---- speculative sub-map of the NEXT frame.  Gathering the 75 valid cubes and cell-sorting ~1M points is
@@ -1431,7 +1455,7 @@ int vl_lm_run(vloam_b200_ctx* c) {
   // window and lets the in-line build run only when it moved.  Debug snapshots read this frame's sub-map
   // after the call returns, so capture mode keeps the in-line build.
   d->specQueued = false;
-  if (d->specEnabled && !capture) {
+  if (spec) {
     const long long tb = d->hMapUpperC + d->hMapUpperS;
     VL_TRY(vl_reserve(c, c->fromMapC, (size_t)max(d->hMapUpperC, 1LL), false, (size_t)d->hMapUpperC / 2 + (1 << 20)));
     VL_TRY(vl_reserve(c, c->fromMapS, (size_t)max(d->hMapUpperS, 1LL), false, (size_t)d->hMapUpperS / 2 + (1 << 20)));
@@ -1440,7 +1464,8 @@ int vl_lm_run(vloam_b200_ctx* c) {
     VL_LAUNCH(lm_spec_prepare, 1, 256, 0, d->subReal, c->cubeC, c->cubeS, d->subSpec);
     VL_BYTES(32.0 * (double)tb);
     VL_LAUNCH(lm_gather, gsGrid, 256, 0, d->subSpec, (const int*)nullptr, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, c->fromMapC.p, c->fromMapS.p);
-    VL_TRY(lm_build_grid(c, d, d->subSpec, nullptr, tb));
+    VL_CUDA(cudaStreamWaitEvent(c->stream3, c->evAuxZero, 0));
+    VL_TRY(lm_build_grid(c, d, d->subSpec, nullptr, tb, true));
     d->specQueued = true;
   }
   VL_CUDA(cudaEventRecord(c->evMap, c->stream3));
@@ -1452,6 +1477,7 @@ int vl_lm_run(vloam_b200_ctx* c) {
   static const bool noWorker = getenv("VLOAM_NO_WORKER") != nullptr;
   if (noWorker || capture || c->prof_name[0]) { const int rmap = update(); if (rmap != VLOAM_OK) return rmap; }
   else VL_TRY(lm_submit(c, update));
+  VL_HOST_MARK(7);
   VL_CUDA(cudaGetLastError());
   return VLOAM_OK;
 }

@@ -621,6 +621,8 @@ int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, i
     }
     VL_LAUNCH(lo_accumulate, 1, 32, 0, c->los);
   }
+  VL_TRY(vl_launch_lookahead(c));  // the next sweep's scan registration, if one is registered, goes to its side stream now
+  VL_HOST_MARK(2);
   VL_TRY(vl_sr_sync_counts(c));  // sync point S1 (event after scan registration; the odometry above is already queued)
   if (((c->lo_frameCount + 1) % c->prm.mapping_skip_frame) == 0)  // mapping will run on this frame (LO.cpp:668)
     VL_TRY(vl_lm_enqueue_stacks(c, c->lessSharp[c->cur].p, c->nLessSharp, c->lessFlat[c->cur].p, c->nLessFlat));

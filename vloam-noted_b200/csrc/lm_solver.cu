@@ -353,6 +353,9 @@ __global__ void __launch_bounds__(LM_BLOCK) lm_eval(const double* __restrict__ f
 // CTA).  Nothing has to be published back, so the second cluster barrier and the remote read of the
 // next evaluation point of the previous design are gone; the partials are double-buffered by
 // evaluation parity, which the single barrier is enough to protect.
+#ifndef LMC_MIN_CTAS
+#define LMC_MIN_CTAS 1  // (2 caps the kernel at 128 registers so that a solver CTA fits beside another stream's resident CTA; the spills
+#endif                  // cost more -- 130 -> 160 us of solves per frame -- than the co-residency gains)
 #define LMC_CTAS 16  // one cluster of the non-portable maximum size: the f64 pipes of 16 SMs
 
 struct LmFactorReg {  // one factor with its pose-independent parts hoisted
@@ -440,7 +443,7 @@ __device__ __forceinline__ void lm_warp_transpose_reduce(double (&v)[32], int la
 // Slot i belongs to CTA i % 16 (thread (i / 16) % THREADS): the edge factors, which cost three times a
 // plane factor and sit at the front of the slot array, are spread evenly over the CTAs.
 template <int FPT, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, LMC_MIN_CTAS)
 lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ valid, int nslotsBound, const int* __restrict__ d_nslots,
                  double* __restrict__ x_inout, LmSolveState* __restrict__ st_out, long long* __restrict__ trace) {
   VL_PDL_WAIT();

@@ -837,12 +837,12 @@ int vl_sr_run(vloam_b200_ctx* c, const float* d_xyz, int n, int stride) {
   const int R = c->prm.n_scans;
   c->sr_counts_valid = false;
   c->n_in = n; c->stride = stride;
-  c->cur ^= 1;  // this frame's lessSharp / lessFlat go to the buffer the "last" clouds do not occupy
+  c->cur = (c->cur + 1) % 3;  // this sweep's lessSharp / lessFlat: neither the "last" clouds' buffer nor the sweep before that
   if (n <= 0) {
-    VL_CUDA(cudaMemsetAsync(c->srs, 0, sizeof(SrScalars), c->stream));
-    VL_CUDA(cudaMemsetAsync(c->ringCount, 0, sizeof(int) * VL_MAX_RINGS, c->stream));
-    VL_CUDA(cudaMemsetAsync(c->ringStart, 0, sizeof(int) * (VL_MAX_RINGS + 1), c->stream));
-    VL_CUDA(cudaEventRecord(c->evSR, c->stream));
+    VL_CUDA(cudaMemsetAsync(c->srs, 0, sizeof(SrScalars), VL_STREAM(c)));
+    VL_CUDA(cudaMemsetAsync(c->ringCount, 0, sizeof(int) * VL_MAX_RINGS, VL_STREAM(c)));
+    VL_CUDA(cudaMemsetAsync(c->ringStart, 0, sizeof(int) * (VL_MAX_RINGS + 1), VL_STREAM(c)));
+    VL_CUDA(cudaEventRecord(c->evSR, VL_STREAM(c)));
     return VLOAM_OK;
   }
   const int numBlocks = vl_div_up(n, SR_BLOCK);
@@ -887,8 +887,8 @@ int vl_sr_run(vloam_b200_ctx* c, const float* d_xyz, int n, int stride) {
   VL_LAUNCH(sr_gather, vl_div_up(gatherThreads, SR_BLOCK), SR_BLOCK, 0, c->cloud.p, R, c->srs, c->provSharp, c->provLess, c->provFlat,
             c->cntSharp, c->cntLess, c->cntFlat, c->offSharp, c->offLess, c->offFlat, c->ringStart, c->ringDsCount, c->ringDsOff,
             c->lessFlatProv.p, c->sharp.p, c->lessSharp[c->cur].p, c->flat.p, c->lessFlat[c->cur].p);
-  VL_CUDA(cudaMemcpyAsync(c->h_srs, c->srs, sizeof(SrScalars), cudaMemcpyDeviceToHost, c->stream));
-  VL_CUDA(cudaEventRecord(c->evSR, c->stream));
+  VL_CUDA(cudaMemcpyAsync(c->h_srs, c->srs, sizeof(SrScalars), cudaMemcpyDeviceToHost, VL_STREAM(c)));
+  VL_CUDA(cudaEventRecord(c->evSR, VL_STREAM(c)));
   VL_CUDA(cudaGetLastError());
   return VLOAM_OK;
 }
