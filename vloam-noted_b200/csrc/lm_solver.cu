@@ -610,7 +610,7 @@ int vl_solve(vloam_b200_ctx* c, int nslots, const int* d_nslots, double* d_x_ino
     // nslots is a host BOUND (buffer capacity when the count still lives on the device); `hint` is the last known
     // actual count.  The variant only decides how many slots a thread can keep in registers: a solve whose
     // actual count exceeds it streams the factors from memory at every evaluation instead.
-    const int est = hint > 0 ? min(nslots, hint + hint / 8 + 64) : nslots;
+    const int est = hint > 0 ? min(nslots, hint + hint / 32 + 64) : nslots;  // counts move by a few per cent between sweeps; a miss only costs speed
     if (est <= LMC_CTAS * 256) VL_CUDA((lm_launch<1, 256>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr)));
     else if (est <= LMC_CTAS * 512) VL_CUDA((lm_launch<2, 256>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr)));
     else if (est <= LMC_CTAS * 1024) VL_CUDA((lm_launch<4, 256>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr)));
