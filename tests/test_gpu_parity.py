@@ -590,3 +590,30 @@ def test_lookahead_scan_registration_gives_identical_results(pkg, synth, street)
         assert (b.get("lm.cornerMap"), b.get("lm.surfMap")) == ref_maps, mode
         assert_bits_equal(ref_sharp, b.get("sr.sharp"), "sr.sharp of the last sweep (%s)" % mode)
         b.close()
+
+
+@pytest.mark.gpu
+def test_segmented_update_sort_global_fallback(pkg, synth, street):
+    """The map update buckets its (segment | voxel | order) keys by cube segment and sorts every bucket in shared
+    memory; buckets above the capacity are sorted in a global scratch area.  With the capacity forced down to 64
+    keys (VLOAM_SEG_CAP, read once per process: run in a subprocess) nearly every bucket takes that path and the maps
+    must not change."""
+    import os, subprocess, sys, hashlib
+    code = (
+        "import importlib, sys, hashlib, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "pkg = importlib.import_module('vloam-noted_b200')\n"
+        "w = pkg.synth.World(1234, 0, 160.0); traj = pkg.synth.trajectory(5)\n"
+        "g = pkg.Context(n_scans=64, minimum_range=5.0, line_res=0.4, plane_res=0.8)\n"
+        "poses = [g.process_frame(w.scan(1, traj[k], 1000 + k)).copy() for k in range(5)]\n"
+        "h = hashlib.sha256(np.array(poses).tobytes() + g.get('lm.cornerMap') + g.get('lm.surfMap')).hexdigest()\n"
+        "print('HASH', h)\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = {}
+    for cap in ("", "64"):
+        env = dict(os.environ)
+        env.pop("VLOAM_SEG_CAP", None)
+        if cap: env["VLOAM_SEG_CAP"] = cap
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[cap] = [l for l in r.stdout.splitlines() if l.startswith("HASH")][0]
+    assert out[""] == out["64"]

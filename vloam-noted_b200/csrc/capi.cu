@@ -136,7 +136,12 @@ void vloam_b200_destroy(vloam_b200_ctx* c) {
   free_sr_set(c);
   if (c->srNext) { vl_sr_swap(c, *c->srNext); free_sr_set(c); delete c->srNext; c->srNext = nullptr; }
   cudaStreamDestroy(c->streamSR);
-  void* singles[] = {c->los, c->evalOut, c->lms, c->lmm, c->cubeC, c->cubeS, c->vScalars};
+  vl_lm_free(c);
+  void* singles[] = {c->los, c->evalOut, c->lms, c->lmm, c->cubeC, c->cubeS, c->vScalars, c->loRingTbl, c->loGridCells[0].p, c->loGridCells[1].p,
+                     c->loGridCellOf.p, c->loGridSorted[0].p, c->loGridSorted[1].p, c->dbgLoCorner[0].p, c->dbgLoCorner[1].p, c->dbgLoSurf[0].p,
+                     c->dbgLoSurf[1].p, c->dbgKnnIdx[0][0].p, c->dbgKnnIdx[0][1].p, c->dbgKnnIdx[1][0].p, c->dbgKnnIdx[1][1].p, c->dbgKnnD2[0][0].p,
+                     c->dbgKnnD2[0][1].p, c->dbgKnnD2[1][0].p, c->dbgKnnD2[1][1].p, c->dbgKnnOk[0][0].p, c->dbgKnnOk[0][1].p, c->dbgKnnOk[1][0].p,
+                     c->dbgKnnOk[1][1].p};
   for (void* p : singles) if (p) cudaFree(p);
   void* bufs[] = {c->lessSharp[0].p, c->lessSharp[1].p, c->lessSharp[2].p, c->lessFlat[0].p, c->lessFlat[1].p, c->lessFlat[2].p, c->loCornerIdx.p, c->loSurfIdx.p, c->factors.p, c->factorValid.p, c->evalPartials.p,
                   c->poolC.p, c->poolS.p, c->stackC.p, c->stackS.p, c->fromMapC.p, c->fromMapS.p, c->knnIdx.p, c->knnD2.p, c->knnOk.p,

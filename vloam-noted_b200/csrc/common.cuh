@@ -314,6 +314,7 @@ int vl_lo_build_last(vloam_b200_ctx* c, int set, const float4* corner, int nc, c
 int vl_lm_run(vloam_b200_ctx* c);
 int vl_lm_enqueue_stacks(vloam_b200_ctx* c, const float4* corner, int nc, const float4* surf, int ns);
 int vl_lm_init(vloam_b200_ctx* c);
+void vl_lm_free(vloam_b200_ctx* c);
 extern "C" int vl_launch_lookahead(vloam_b200_ctx* c);  // capi.cu: queue the registered look-ahead scan registration (no-op without one)
 int vl_sr_set_attrs(vloam_b200_ctx* c);
 int vl_sort_set_attrs(vloam_b200_ctx* c);

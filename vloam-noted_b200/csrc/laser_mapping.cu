@@ -24,6 +24,7 @@
 #include <math_constants.h>
 #include <cooperative_groups.h>
 #include "common.cuh"
+#include "bitonic.cuh"
 namespace cg = cooperative_groups;
 #include <atomic>
 #include <chrono>
@@ -129,6 +130,8 @@ struct RfWork {
   int tailOff[LM_NSEG + 1];             // exclusive offsets of existing-tail keys
   int prefOff[LM_NSEG + 1];             // exclusive offsets of prefix points
   int tailBegin[LM_NSEG + 1];           // per segment range in the sorted key array
+  int segCount[LM_NSEG + 1];            // keys per segment (histogram of rf_keys; zeroed by lm_prepare)
+  int segFill[LM_NSEG + 1];             // scatter cursors
   int outOff[LM_NSEG + 1];              // staging offsets
   int outCount[LM_NSEG];
   int firstViolation[LM_NSEG];
@@ -266,6 +269,7 @@ __global__ void __launch_bounds__(1024) lm_prepare(LmScalars* __restrict__ s, co
   __shared__ int sTot[2];
   if (threadIdx.x < 2) sTot[threadIdx.x] = 0;
   __syncthreads();
+  if (threadIdx.x <= LM_NSEG) w->segCount[threadIdx.x] = 0;  // histogram of this frame's update keys (rf_keys)
   int myC = 0, myS = 0;
   for (int d = threadIdx.x; d < VL_CUBE_NUM; d += 1024) { w->slotOfCube[d] = -1; myC += tc->count[d]; myS += ts->count[d]; }
   for (int o = 16; o > 0; o >>= 1) { myC += __shfl_xor_sync(0xffffffffu, myC, o); myS += __shfl_xor_sync(0xffffffffu, myS, o); }
@@ -796,7 +800,7 @@ __global__ void lm_transform_update(LmScalars* s) {
 // order: existing tail point -> its position in the cube; new point -> 2^25 + stack index.
 __device__ __forceinline__ float lm_leaf_inv(const vloam_b200_params& p, int kind) { return __fdiv_rn(1.0f, kind ? p.plane_res : p.line_res); }
 
-__global__ void __launch_bounds__(256) rf_keys(const LmScalars* __restrict__ s, const RfWork* __restrict__ w, vloam_b200_params prm,
+__global__ void __launch_bounds__(256) rf_keys(const LmScalars* __restrict__ s, RfWork* __restrict__ w, vloam_b200_params prm,
                                                const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts,
                                                const float4* __restrict__ poolC, const float4* __restrict__ poolS,
                                                const float4* __restrict__ stackC, const float4* __restrict__ stackS,
@@ -838,6 +842,59 @@ __global__ void __launch_bounds__(256) rf_keys(const LmScalars* __restrict__ s, 
     }
   }
   keys[g] = key;
+  if (key != ~0ull) atomicAdd(&w->segCount[(int)(key >> 56)], 1);
+}
+
+// ---- segmented sort of the update keys ----------------------------------------------------------------
+// The keys are (segment | voxel | order) and every later step works per segment (one segment = one valid cube
+// of one kind).  Instead of one bitonic network over all keys (37 us for 8k keys: ~48 barrier rounds of a
+// 1024-thread CTA pair), the keys are bucketed by segment -- histogram in rf_keys, a 250-entry scan that IS the
+// per-segment range table, one scatter -- and each bucket is sorted by its own CTA in shared memory.
+__global__ void __launch_bounds__(256) rf_seg_scan(RfWork* __restrict__ w) {
+  VL_PDL_WAIT();
+
+  __shared__ int sb[256];
+  const int t = threadIdx.x;
+  const int cnt = t < LM_NSEG ? w->segCount[t] : 0;
+  int total = 0;
+  const int off = lm_scan256(cnt, sb, &total);
+  if (t < LM_NSEG) { w->tailBegin[t] = off; w->segFill[t] = 0; w->firstViolation[t] = INT_MAX; }
+  if (t == 0) { w->tailBegin[LM_NSEG] = total; w->nKeysValid = total; }
+}
+__global__ void __launch_bounds__(256) rf_seg_scatter(const unsigned long long* __restrict__ in, int n, RfWork* __restrict__ w,
+                                                      unsigned long long* __restrict__ out) {
+  VL_PDL_WAIT();
+
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const unsigned long long key = in[g];
+  if (key == ~0ull) return;
+  const int sg = (int)(key >> 56);
+  out[w->tailBegin[sg] + atomicAdd(&w->segFill[sg], 1)] = key;
+}
+#define RF_SEG_THREADS 512
+#define RF_SEG_CAP 8192  // keys of one segment sorted in shared memory; larger segments use `scratch` (global)
+__global__ void __launch_bounds__(RF_SEG_THREADS) rf_seg_sort(unsigned long long* __restrict__ keys, const RfWork* __restrict__ w,
+                                                              unsigned long long* __restrict__ scratch, int cap) {
+  VL_PDL_WAIT();
+
+  extern __shared__ unsigned long long sk[];
+  const int sg = blockIdx.x;
+  const int beg = w->tailBegin[sg], n = w->tailBegin[sg + 1] - beg;
+  if (n <= 1) return;
+  int P = 8; while (P < n) P <<= 1;
+  if (P <= cap) {
+    for (int t = threadIdx.x; t < P; t += RF_SEG_THREADS) sk[t] = t < n ? keys[beg + t] : ~0ull;
+    __syncthreads();
+    bt_smem_sort<RF_SEG_THREADS>(sk, P);
+    for (int t = threadIdx.x; t < n; t += RF_SEG_THREADS) keys[beg + t] = sk[t];
+  } else {  // P <= 2 n - 1: the segments' scratch areas [2 beg, 2 beg + P) do not overlap
+    unsigned long long* g = scratch + (size_t)2 * beg;
+    for (int t = threadIdx.x; t < P; t += RF_SEG_THREADS) g[t] = t < n ? keys[beg + t] : ~0ull;
+    __syncthreads();
+    bt_sort_batched<RF_SEG_THREADS>(g, P, 1);
+    for (int t = threadIdx.x; t < n; t += RF_SEG_THREADS) keys[beg + t] = g[t];
+  }
 }
 
 __device__ __forceinline__ float4 rf_key_point(unsigned long long key, const LmScalars* s, const MapCubeTable* tc, const MapCubeTable* ts,
@@ -849,19 +906,6 @@ __device__ __forceinline__ float4 rf_key_point(unsigned long long key, const LmS
   return (kind ? poolS : poolC)[(kind ? ts : tc)->start[cb] + (int)ord];
 }
 #define RF_VOX(key) ((unsigned)(((key) >> 26) & 0x3fffffffull))
-
-__global__ void __launch_bounds__(256) rf_segments(const unsigned long long* __restrict__ keys, int P, RfWork* __restrict__ w) {
-  VL_PDL_WAIT();
-
-  const int sg = threadIdx.x;
-  if (sg > LM_NSEG) return;
-  const unsigned long long target = (unsigned long long)sg << 56;
-  int lo = 0, hi = P;  // first index with key >= target
-  while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < target) lo = mid + 1; else hi = mid; }
-  w->tailBegin[sg] = lo;
-  if (sg == LM_NSEG) w->nKeysValid = lo;
-  if (sg < LM_NSEG) w->firstViolation[sg] = INT_MAX;
-}
 
 // For each sorted tail key: is it the head of a run that no prefix point owns?
 __global__ void __launch_bounds__(256) rf_match(const unsigned long long* __restrict__ keys, const LmScalars* __restrict__ s,
@@ -1211,6 +1255,7 @@ int vl_lm_init(vloam_b200_ctx* c) {
   VL_CUDA(cudaMalloc(&d->specOK, sizeof(int))); VL_CUDA(cudaMemset(d->specOK, 0, sizeof(int)));
   d->specQueued = false;
   d->specEnabled = getenv("VLOAM_NO_SPECULATION") == nullptr;
+  VL_CUDA(cudaFuncSetAttribute(rf_seg_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, RF_SEG_CAP * 8));
   int perSm = 0;
   VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, lm_inline_build, 256, 0));
   d->inlineGrid = c->num_sms * max(1, min(perSm, 4));
@@ -1236,6 +1281,16 @@ int vl_lm_init(vloam_b200_ctx* c) {
   VL_CUDA(cudaMemcpy(c->lmm, &h, sizeof h, cudaMemcpyHostToDevice));
   *c->h_lmm = h;
   return VLOAM_OK;
+}
+
+void vl_lm_free(vloam_b200_ctx* c) {  // everything vl_lm_init and this file's reserves own (the pools are freed by capi.cu)
+  LmDevice* d = lmdev(c);
+  if (!d) return;
+  void* dev[] = {d->work, d->cellCount, d->cellStart, d->cellFill, d->tileSum, d->dQ, d->subReal, d->subSpec, d->specOK,
+                 d->cellOfPoint.p, d->sortedPts.p, d->newPts.p, d->newCube.p, d->unmatched.p};
+  for (void* p : dev) if (p) cudaFree(p);
+  delete d;
+  c->gridPrm = nullptr;
 }
 
 extern bool vl_debug_capture(const vloam_b200_ctx* c);
@@ -1413,22 +1468,27 @@ int vl_lm_run(vloam_b200_ctx* c) {
   }
   const int nKeys = tailTotal + nq;
   if (nKeys > 0) {
-    int P = 2; while (P < nKeys) P <<= 1;
-    VL_TRY(vl_reserve(c, c->tailKeys, (size_t)P, false, (size_t)P));
+    const size_t N = ((size_t)nKeys + 255) & ~(size_t)255;
+    VL_TRY(vl_reserve(c, c->tailKeys, 4 * N, false, 4 * N));  // [0, N) unsorted keys | [N, 2N) bucketed + sorted | [2N, 4N) scratch for oversize segments
+    unsigned long long* keysIn = c->tailKeys.p;
+    unsigned long long* keysSorted = c->tailKeys.p + N;
     VL_TRY(vl_reserve(c, d->newPts, (size_t)max(nq, 1)));
     VL_TRY(vl_reserve(c, d->newCube, (size_t)max(nq, 1)));
     VL_TRY(vl_reserve(c, d->unmatched, (size_t)nKeys + 2, false, (size_t)nKeys + (1 << 16)));
     VL_TRY(vl_reserve(c, c->staging, (size_t)Mc + Ms + nKeys + 1, false, (size_t)(Mc + Ms) / 2 + (1 << 20)));
-    VL_LAUNCH(rf_keys, vl_div_up(P, 256), 256, 0, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, c->stackC.p, c->stackS.p,
-              d->newPts.p, d->newCube.p, c->tailKeys.p, P);
-    VL_TRY(vl_sort_u64(c, c->tailKeys.p, P));
-    VL_LAUNCH(rf_segments, 1, 256, 0, c->tailKeys.p, P, d->work);
-    VL_LAUNCH(rf_match, vl_div_up(nKeys, 256), 256, 0, c->tailKeys.p, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, d->unmatched.p);
+    VL_LAUNCH(rf_keys, vl_div_up(nKeys, 256), 256, 0, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, c->stackC.p, c->stackS.p,
+              d->newPts.p, d->newCube.p, keysIn, nKeys);
+    VL_LAUNCH(rf_seg_scan, 1, 256, 0, d->work);
+    VL_LAUNCH(rf_seg_scatter, vl_div_up(nKeys, 256), 256, 0, keysIn, nKeys, d->work, keysSorted);
+    VL_BYTES(16.0 * nKeys);
+    static const int segCap = getenv("VLOAM_SEG_CAP") ? max(8, min(atoi(getenv("VLOAM_SEG_CAP")), RF_SEG_CAP)) : RF_SEG_CAP;  // tests force the global path
+    VL_LAUNCH(rf_seg_sort, LM_NSEG, RF_SEG_THREADS, (size_t)RF_SEG_CAP * 8, keysSorted, d->work, c->tailKeys.p + 2 * N, segCap);
+    VL_LAUNCH(rf_match, vl_div_up(nKeys, 256), 256, 0, keysSorted, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, d->unmatched.p);
     VL_LAUNCH(rf_scan_layout, 1, 1024, 0, d->unmatched.p, c->lmm, d->work, c->cubeC, c->cubeS);
-    VL_LAUNCH(rf_emit_new, vl_div_up(nKeys, 256), 256, 0, c->tailKeys.p, d->unmatched.p, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p,
+    VL_LAUNCH(rf_emit_new, vl_div_up(nKeys, 256), 256, 0, keysSorted, d->unmatched.p, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p,
               c->poolS.p, d->newPts.p, c->staging.p);
     VL_BYTES(32.0 * (Mc + Ms));  // read every prefix point once, write it once to staging
-    VL_LAUNCH(rf_emit_prefix, gsGrid, 256, 0, c->tailKeys.p, d->unmatched.p, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p,
+    VL_LAUNCH(rf_emit_prefix, gsGrid, 256, 0, keysSorted, d->unmatched.p, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p,
               d->newPts.p, c->staging.p);
     VL_LAUNCH(rf_alloc, 1, 256, 0, c->lmm, d->work, c->cubeC, c->cubeS, (int)c->poolC.cap, (int)c->poolS.cap);
     VL_BYTES(32.0 * (Mc + Ms + nq));  // staging -> pool copy
