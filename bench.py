@@ -221,15 +221,16 @@ def other_workloads(pkg, torch, local_rank, frames=70, warm=10):
     return out
 
 
-def batched_sequences(pkg, torch, local_rank, cblob, sblob, nseq=4, frames=70, warm=10):
+def batched_sequences(pkg, torch, local_rank, cblob, sblob, nseq=4, frames=70, warm=10, first_seq=0, seq_stride=1):
     """BASELINE config C5 on one GPU: `nseq` independent sequences, one context (4 streams + its helper thread) and
     one host thread each, replayed concurrently.  A single sequence leaves the GPU mostly idle (the frame is a
     chain of short dependent kernels), so concurrent sequences overlap almost freely."""
     seqs = []
     for q in range(nseq):
         world = pkg.synth.World(1234, 1, 190.0)
-        traj = pkg.synth.trajectory(frames, seed=177 + q)
-        scans = [world.scan(SENSOR, traj[k], 9000 + 7919 * q + k) for k in range(frames)]
+        sid = first_seq + q * seq_stride
+        traj = pkg.synth.trajectory(frames, seed=177 + sid)
+        scans = [world.scan(SENSOR, traj[k], 9000 + 7919 * sid + k) for k in range(frames)]
         ctx = pkg.Context(n_scans=64, minimum_range=5.0, line_res=0.4, plane_res=0.8, device=local_rank)
         ctx.set("lm.cornerMap", cblob); ctx.set("lm.surfMap", sblob)
         seqs.append((ctx, [torch.from_numpy(x).cuda(local_rank) for x in scans]))
@@ -264,7 +265,7 @@ def batched_sequences(pkg, torch, local_rank, cblob, sblob, nseq=4, frames=70, w
     ms = e0.elapsed_time(e1)
     for ctx, _ in seqs: ctx.close()
     allat = np.concatenate([np.array(x) for x in lat]) * 1e3
-    return {"sequences_per_gpu": nseq, "scans_per_s": nseq * (frames - warm) / (ms * 1e-3), "p50_ms_per_frame": float(np.median(allat)),
+    return {"sequences_per_gpu": nseq, "device_ms": ms, "scans_per_s": nseq * (frames - warm) / (ms * 1e-3), "p50_ms_per_frame": float(np.median(allat)),
             "p99_ms_per_frame": float(np.percentile(allat, 99)), "frames_per_sequence": frames - warm,
             "note": "every frame returns its pose to its own host thread (sync per frame); timed with CUDA events on the default stream around all threads"}
 
@@ -454,6 +455,42 @@ def profile_dominant(ctx, dscans, first, K, map_points):
     return roof, table
 
 
+
+def run_c5(args, rank, world_size, local_rank):
+    """BASELINE config C5: 8 independent HDL-64E sequences batched across the GPUs of one box (strong scaling): sequence
+    s runs on rank s mod G, each rank replays its 8/G sequences concurrently (one context + host thread each), poses and
+    timings are gathered with one NCCL all_gather.  `python bench.py --workload c5 [--frames F]` (F = 1000 in BASELINE;
+    the default keeps synthetic-sweep generation to a minute)."""
+    import torch
+    pkg = importlib.import_module("vloam-noted_b200")
+    pkg.load_lib()
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    total = 8
+    mine = len(range(rank, total, world_size))
+    _, _, cblob, sblob = make_sequence(pkg, 0, 1)
+    if dist: dist.barrier()
+    r = batched_sequences(pkg, torch, local_rank, cblob, sblob, nseq=mine, frames=args.frames, warm=min(10, args.frames // 4),
+                          first_seq=rank, seq_stride=world_size)
+    t = torch.tensor([r["device_ms"], r["p50_ms_per_frame"], r["p99_ms_per_frame"], float(mine * r["frames_per_sequence"])], dtype=torch.float64, device="cuda")
+    if dist:
+        allt = [torch.zeros_like(t) for _ in range(world_size)]
+        dist.all_gather(allt, t)
+        allt = torch.stack(allt).cpu().numpy()
+    else:
+        allt = t.cpu().numpy()[None]
+    if rank == 0:
+        print(json.dumps({"metric": "scans/sec", "value": float(allt[:, 3].sum() / (allt[:, 0].max() * 1e-3)), "unit": "scans/s", "n_gpus": world_size,
+                          "higher_is_better": True, "scaling": "strong", "dtype": "f32+f64", "data": "synthetic",
+                          "config": {"workload": "C5: 8 independent synthetic HDL-64E sequences, %d timed sweeps each, batched across %d GPU(s)" % (r["frames_per_sequence"], world_size),
+                                     "sequences_per_gpu": mine},
+                          "p50_ms_per_frame": float(allt[:, 1].max()), "p99_ms_per_frame": float(allt[:, 2].max())}), flush=True)
+    if dist: dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -462,12 +499,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the cold-L2, batched-sequence and C1/C2/C4 legs")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c5"], help="c3: the headline (default); c5: 8 sequences batched across the GPUs")
+    ap.add_argument("--frames", type=int, default=110, help="sweeps per sequence for --workload c5")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.workload == "c5":
+        run_c5(args, rank, world, local)
     else:
         run_ours(args, rank, world, local)
 
