@@ -35,7 +35,11 @@ def main():
     hdr = rows[h]
     ia, isrc, isamp = hdr.index("Address"), hdr.index("Source"), hdr.index("# Samples")
     stalls = [i for i, n in enumerate(hdr) if n.startswith("stall_") and "Not Issued" not in n]
-    data = [r for r in rows[h + 1:] if len(r) > max(stalls)]
+    data = []
+    for r in rows[h + 1:]:  # the first matching launch only (a regex that matches several kernels yields several sections)
+        if len(r) <= max(stalls): continue
+        if r[ia] == "Address": break
+        data.append(r)
     I = lambda x: int(x) if x.strip().lstrip("-").isdigit() else 0
     base = int(data[0][ia], 16)
     maps = line_map(lib, kernel)

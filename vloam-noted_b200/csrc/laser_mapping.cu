@@ -653,16 +653,19 @@ __global__ void __launch_bounds__(256) lm_knn(const LmScalars* __restrict__ s, c
   VL_PDL_WAIT();
 
   const int lane = threadIdx.x & 31;
-  const int Qc = s->Qc, Qs = s->Qs;
-  if (!s->optimized) return;
+  const int Qc = s->Qc, Qs = s->Qs, opt = s->optimized;
+  double pose[7];  // loaded with the counts: one memory latency instead of two
+#pragma unroll
+  for (int k = 0; k < 7; ++k) pose[k] = s->pose[k];
+  const float ox = w->gridOrigin[0], oy = w->gridOrigin[1], oz = w->gridOrigin[2];
+  if (!opt) return;
   const int nWarps = (gridDim.x * blockDim.x) >> 5;
   for (int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; qi < Qc + Qs; qi += nWarps) {
   const int kind = qi >= Qc;
   const float4 po = kind ? stackS[qi - Qc] : stackC[qi];
   double r[3];
-  vl_qrot(s->pose, (double)po.x, (double)po.y, (double)po.z, r);  // pointAssociateToMap (LM.cpp:154-164)
-  const float sx = (float)(r[0] + s->pose[4]), sy = (float)(r[1] + s->pose[5]), sz = (float)(r[2] + s->pose[6]);
-  const float ox = w->gridOrigin[0], oy = w->gridOrigin[1], oz = w->gridOrigin[2];
+  vl_qrot(pose, (double)po.x, (double)po.y, (double)po.z, r);  // pointAssociateToMap (LM.cpp:154-164)
+  const float sx = (float)(r[0] + pose[4]), sy = (float)(r[1] + pose[5]), sz = (float)(r[2] + pose[6]);
   const int cx = (int)floorf(__fmul_rn(__fsub_rn(sx, ox), 1.0f / LM_CELL));
   const int cy = (int)floorf(__fmul_rn(__fsub_rn(sy, oy), 1.0f / LM_CELL));
   const int cz = (int)floorf(__fmul_rn(__fsub_rn(sz, oz), 1.0f / LM_CELL));
@@ -694,19 +697,16 @@ __global__ void __launch_bounds__(256) lm_knn(const LmScalars* __restrict__ s, c
       }
     });
   }
-  // merge the 32 lane-local lists: pop the global minimum five times
+  // merge the 32 lane-local lists: pop the global minimum of (d2, id) five times.  d2 >= 0, so its bit pattern
+  // orders like the value: two hardware warp reductions per pop (smallest d2, then the smallest id holding it)
   float nd[5]; int ni[5];
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
-    float d = bd[0]; int id = bi[0]; int src = lane;
-    for (int off = 16; off > 0; off >>= 1) {
-      const float od = __shfl_xor_sync(0xffffffffu, d, off);
-      const int oi = __shfl_xor_sync(0xffffffffu, id, off);
-      const int os = __shfl_xor_sync(0xffffffffu, src, off);
-      if (od < d || (od == d && oi < id)) { d = od; id = oi; src = os; }
-    }
-    nd[k] = d; ni[k] = id;
-    if (lane == src && id != 0x7fffffff) {
+    const unsigned hb = __float_as_uint(bd[0]);  // +inf (empty list) sorts last
+    const unsigned gmin = __reduce_min_sync(0xffffffffu, hb);
+    const unsigned imin = __reduce_min_sync(0xffffffffu, hb == gmin ? (unsigned)bi[0] : 0x7fffffffu);
+    nd[k] = __uint_as_float(gmin); ni[k] = (int)imin;
+    if (hb == gmin && (unsigned)bi[0] == imin && imin != 0x7fffffffu) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) { bd[q] = bd[q + 1]; bi[q] = bi[q + 1]; }
       bd[4] = CUDART_INF_F; bi[4] = 0x7fffffff;
