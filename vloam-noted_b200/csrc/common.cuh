@@ -184,8 +184,6 @@ struct vloam_b200_ctx {
   DBuf<int> knnIdx; DBuf<float> knnD2; DBuf<int> knnOk;
   DBuf<int> dbgKnnIdx[2][2]; DBuf<float> dbgKnnD2[2][2]; DBuf<int> dbgKnnOk[2][2];
   double dbgLmCost[4];
-  // search grid over the sub-map
-  DBuf<int> gridCellStart[2]; DBuf<int> gridPointIdx[2]; DBuf<int> gridCellOfPoint[2];
   struct GridParams* gridPrm;  // device [2]
   // voxel filter scratch
   DBuf<unsigned long long> vKeys, vKeys2; DBuf<int> vHead; DBuf<int> vScan, vScan2;  // two scratch lanes: the corner and surf filters run concurrently
@@ -195,7 +193,6 @@ struct vloam_b200_ctx {
   int* h_vScalars;
   // refilter scratch
   DBuf<unsigned long long> tailKeys; DBuf<float4> staging;
-  DBuf<int> tmpI[4];
   // per-kernel timing (vloam_b200_profile_kernel): CUDA events around the launches of one named kernel
   char prof_name[64];                 // kernel to time, or "*" for every launch
   cudaEvent_t prof_ev[VL_PROF_MAX][2];
