@@ -66,8 +66,11 @@ static void lm_worker_main(VlWorker* w) {
         if (w->quit) return;
         break;
       }
+      // busy-wait briefly, then give the core away between polls: with one process per GPU on a 16-core box the
+      // helper threads of eight ranks must not starve the threads that feed them
+      if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(50)) std::this_thread::yield();
 #if defined(__x86_64__)
-      __builtin_ia32_pause();
+      else __builtin_ia32_pause();
 #endif
     }
     w->state.store(2, std::memory_order_relaxed);
