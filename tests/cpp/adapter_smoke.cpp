@@ -2,7 +2,9 @@
 // vloam_main_node.cpp:143-144, 186-190 drives the reference, on sweeps read from a raw float file.
 // usage: adapter_smoke <scan0.bin> <scan1.bin>   (float32 x,y,z,r per point, KITTI layout)
 #include <stdio.h>
+#include <math.h>
 #include <stdlib.h>
+#include <string.h>
 #include <vector>
 #include "vloam_adapter.hpp"
 
@@ -36,6 +38,28 @@ int main(int argc, char** argv) {
       loam.laser_odometry.output(q, t, cl, sl, fr, skip);
       vloam::Quat qm; vloam::Vec3 tm;
       loam.laser_mapping.output(qm, tm);
+      // the per-point helpers of the reference's public interface against the device path
+      vloam::CloudPtr reg;
+      loam.laser_mapping.registeredFullCloud(reg);                       // LM.cpp:901-905 on the device
+      if (reg->size() != full->size()) { printf("ERROR: registered cloud size\n"); return 1; }
+      for (size_t i = 0; i < full->size(); i += 97) {
+        vloam::PointType m, back, st, en;
+        loam.laser_mapping.pointAssociateToMap(&full->points[i], &m);     // LM.cpp:154-164 on the host
+        if (memcmp(&m, &reg->points[i], sizeof m) != 0) { printf("ERROR: pointAssociateToMap differs from the device at %zu\n", i); return 1; }
+        loam.laser_mapping.pointAssociateTobeMapped(&m, &back);
+        loam.laser_odometry.TransformToStart(&full->points[i], &st);
+        loam.laser_odometry.TransformToEnd(&full->points[i], &en);
+        const float tol = 1e-4f * (1.0f + fabsf(full->points[i].x) + fabsf(full->points[i].y) + fabsf(full->points[i].z));
+        if (fabsf(back.x - full->points[i].x) > tol || fabsf(back.y - full->points[i].y) > tol || fabsf(back.z - full->points[i].z) > tol ||
+            fabsf(en.x - full->points[i].x) > tol || fabsf(en.y - full->points[i].y) > tol || fabsf(en.z - full->points[i].z) > tol ||
+            en.intensity != (float)(int)full->points[i].intensity || st.intensity != full->points[i].intensity) {
+          printf("ERROR: per-point helper round trip at %zu\n", i); return 1;
+        }
+      }
+      vloam::CloudXYZI near_far, kept;
+      near_far.points = full->points;
+      vloam::ScanRegistration::removeClosedPointCloud(near_far, kept, 10.0f);   // SR.cpp:107-141
+      for (const auto& p : kept.points) if (p.x * p.x + p.y * p.y + p.z * p.z < 100.0f) { printf("ERROR: removeClosedPointCloud\n"); return 1; }
       printf("frame %d kept %zu sharp %zu less %zu flat %zu lessflat %zu | odom %.9f %.9f %.9f | map %.9f %.9f %.9f\n", k - 1, full->size(),
              sharp->size(), less->size(), flat->size(), lessflat->size(), t.x, t.y, t.z, tm.x, tm.y, tm.z);
     }

@@ -60,6 +60,22 @@ namespace vloam {
 // The reference aborts (ROS_BREAK) on a missing parameter or a bad scan_line; the adapter throws.
 struct AdapterError : std::runtime_error { using std::runtime_error::runtime_error; };
 
+// Eigen's Quaterniond * Vector3d (uv = 2 u x v; v + w uv + u x uv), as the device code evaluates it.  Used only by
+// the per-point helpers the reference exposes publicly (TransformToStart, pointAssociateToMap, ...): callers
+// outside the pipeline may use them, the pipeline itself transforms whole clouds on the device.
+inline void quat_rotate(const double q[4], const double v[3], double o[3]) {
+  const double ux = q[0], uy = q[1], uz = q[2], w = q[3];
+  double a = uy * v[2] - uz * v[1], b = uz * v[0] - ux * v[2], c = ux * v[1] - uy * v[0];
+  a += a; b += b; c += c;
+  o[0] = (v[0] + w * a) + (uy * c - uz * b);
+  o[1] = (v[1] + w * b) + (uz * a - ux * c);
+  o[2] = (v[2] + w * c) + (ux * b - uy * a);
+}
+inline void quat_inverse(const double q[4], double o[4]) {  // Eigen: conjugate / squaredNorm
+  const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  o[0] = -q[0] / n2; o[1] = -q[1] / n2; o[2] = -q[2] / n2; o[3] = q[3] / n2;
+}
+
 class Engine {  // one vloam_b200_ctx shared by the three stage objects (they share it in LOM.h:78-80 too)
 public:
   explicit Engine(const vloam_b200_params& p, int device = 0) {
@@ -94,6 +110,18 @@ public:
     for (size_t i = 0; i < laserCloudIn_.points.size(); ++i) { xyz_[i * 3] = laserCloudIn_.points[i].x; xyz_[i * 3 + 1] = laserCloudIn_.points[i].y; xyz_[i * 3 + 2] = laserCloudIn_.points[i].z; }
     e_->check(vloam_b200_scan_registration(e_->ctx(), xyz_.data(), (int)laserCloudIn_.points.size(), 3));
   }
+  // SR.cpp:107-141 (public template of the reference): order-preserving removal of points closer than thres
+  template <typename CloudT>
+  static void removeClosedPointCloud(const CloudT& cloud_in, CloudT& cloud_out, float thres) {
+    if (&cloud_in != &cloud_out) cloud_out.points.resize(cloud_in.points.size());
+    size_t j = 0;
+    for (size_t i = 0; i < cloud_in.points.size(); ++i) {
+      const auto& p = cloud_in.points[i];
+      if (p.x * p.x + p.y * p.y + p.z * p.z < thres * thres) continue;
+      cloud_out.points[j++] = p;
+    }
+    cloud_out.points.resize(j);
+  }
   void publish() {}
   void output(CloudPtr& laserCloud_, CloudPtr& cornerPointsSharp_, CloudPtr& cornerPointsLessSharp_, CloudPtr& surfPointsFlat_,
               CloudPtr& surfPointsLessFlat_) {  // SR.cpp:566-577
@@ -126,6 +154,19 @@ public:
     if (!skip_frame) { e_->fetch(VLOAM_CLOUD_CORNER_LAST, laserCloudCornerLast_); e_->fetch(VLOAM_CLOUD_SURF_LAST, laserCloudSurfLast_); e_->fetch(VLOAM_CLOUD_FULL, laserCloudFullRes_); }
   }
   void lastMotion(Quat& q_last_curr, Vec3& t_last_curr) const { quat_set(q_last_curr, ql_); vec_set(t_last_curr, tl_); }
+  // LO.cpp:152-173 with DISTORTION == false (s = 1): the point of this sweep in the frame of the sweep's start
+  void TransformToStart(PointType const* const pi, PointType* const po) const {
+    const double v[3] = {pi->x, pi->y, pi->z};
+    double r[3]; quat_rotate(ql_, v, r);
+    po->x = (float)(r[0] + tl_[0]); po->y = (float)(r[1] + tl_[1]); po->z = (float)(r[2] + tl_[2]); po->intensity = pi->intensity;
+  }
+  // LO.cpp:176-193: into the frame of the sweep's end (dead in the reference: only called under `if (0)`, LO.cpp:537)
+  void TransformToEnd(PointType const* const pi, PointType* const po) const {
+    PointType un; TransformToStart(pi, &un);
+    const double v[3] = {un.x - tl_[0], un.y - tl_[1], un.z - tl_[2]};
+    double qi[4], r[3]; quat_inverse(ql_, qi); quat_rotate(qi, v, r);
+    po->x = (float)r[0]; po->y = (float)r[1]; po->z = (float)r[2]; po->intensity = (float)(int)pi->intensity;
+  }
 private:
   std::shared_ptr<Engine> e_;
   double pq_[4] = {0, 0, 0, 1}, pt_[3] = {0, 0, 0}, qw_[4] = {0, 0, 0, 1}, tw_[3] = {0, 0, 0}, ql_[4] = {0, 0, 0, 1}, tl_[3] = {0, 0, 0};
@@ -143,6 +184,29 @@ public:
   void solveMapping() { e_->check(vloam_b200_laser_mapping(e_->ctx(), q_, t_)); }  // LM.cpp:212-814 (skip frames: LM.cpp:197-201)
   void publish() {}
   void output(Quat& q_w_curr, Vec3& t_w_curr) const { quat_set(q_w_curr, q_); vec_set(t_w_curr, t_); }
+  void transformUpdate() {}          // LM.cpp:147-151: already applied on the device at the end of solveMapping
+  void transformAssociateToMap() {}  // declared in LM.h:87, its definition is commented out in the reference (LM.cpp:138-143)
+  // LM.cpp:154-164 / 166-175 with the mapped pose of the last solveMapping
+  void pointAssociateToMap(PointType const* const pi, PointType* const po) const {
+    const double v[3] = {pi->x, pi->y, pi->z};
+    double r[3]; quat_rotate(q_, v, r);
+    po->x = (float)(r[0] + t_[0]); po->y = (float)(r[1] + t_[1]); po->z = (float)(r[2] + t_[2]); po->intensity = pi->intensity;
+  }
+  void pointAssociateTobeMapped(PointType const* const pi, PointType* const po) const {
+    const double v[3] = {pi->x - t_[0], pi->y - t_[1], pi->z - t_[2]};
+    double qi[4], r[3]; quat_inverse(q_, qi); quat_rotate(qi, v, r);
+    po->x = (float)r[0]; po->y = (float)r[1]; po->z = (float)r[2]; po->intensity = pi->intensity;
+  }
+  // LM.cpp:901-905: the full-resolution cloud of this sweep in the map frame (on the device)
+  void registeredFullCloud(CloudPtr& out) const {
+    const int n = vloam_b200_register_full_cloud(e_->ctx(), nullptr, 0);
+    e_->check(n);
+    std::vector<float> buf((size_t)n * 4);
+    if (n) e_->check(vloam_b200_register_full_cloud(e_->ctx(), buf.data(), n));
+    if (!out) out = make_cloud();
+    out->points.resize(n);
+    for (int i = 0; i < n; ++i) { PointType p; p.x = buf[i * 4]; p.y = buf[i * 4 + 1]; p.z = buf[i * 4 + 2]; p.intensity = buf[i * 4 + 3]; out->points[i] = p; }
+  }
 private:
   std::shared_ptr<Engine> e_;
   double q_[4] = {0, 0, 0, 1}, t_[3] = {0, 0, 0};
