@@ -32,8 +32,9 @@ for c0 in range(0, N, CH):
     lat = np.array(lat); lat_all.append(lat)
     k = min(c0 + CH, N) - 1
     err = np.linalg.norm(pose[11:14] - (np.array(traj[k][:3]) - np.array(traj[0][:3])))
-    print("sweeps %4d-%4d: %.0f scans/s, p50 %.3f p99 %.3f max %.3f ms | mapped t = %s, |t - truth| = %.3f m" % (
-        c0, k, len(scans) / dt, np.median(lat), np.percentile(lat, 99), lat.max(), np.round(pose[11:14], 2), err), flush=True)
+    print("sweeps %4d-%4d: %.0f scans/s, p50 %.3f p99 %.3f max %.3f ms (sweep %d) | mapped t = %s, |t - truth| = %.3f m" % (
+        c0, k, len(scans) / dt, np.median(lat), np.percentile(lat, 99), lat.max(), c0 + int(lat.argmax()), np.round(pose[11:14], 2), err), flush=True)
+    if c0 == 0: print("   first sweeps, ms:", " ".join("%.2f" % v for v in lat[:8]))
 lat = np.concatenate(lat_all)
 print("total: %d sweeps, %.0f scans/s, p50 %.3f p99 %.3f p99.9 %.3f max %.3f ms" % (N, N / t_all, np.median(lat), np.percentile(lat, 99), np.percentile(lat, 99.9), lat.max()))
 print("map bytes corner/surf:", len(ctx.get("lm.cornerMap")), len(ctx.get("lm.surfMap")))

@@ -120,6 +120,9 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   if (r == VLOAM_OK) r = vl_sr_set_attrs(c);
   if (r == VLOAM_OK) r = vl_sort_set_attrs(c);
   if (r == VLOAM_OK) r = vl_solver_set_attrs(c);
+  if (r == VLOAM_OK) r = vl_lo_preload(c);
+  if (r == VLOAM_OK) r = vl_vg_preload(c);
+  if (r == VLOAM_OK) r = vl_lm_preload(c);
   if (r != VLOAM_OK) { fprintf(stderr, "vloam_b200_create: %s\n", c->err); return r; }
   VL_CUDA_CREATE(cudaDeviceSynchronize());
   *out = c;

@@ -316,6 +316,9 @@ extern "C" int vl_launch_lookahead(vloam_b200_ctx* c);  // capi.cu: queue the re
 int vl_sr_set_attrs(vloam_b200_ctx* c);
 int vl_sort_set_attrs(vloam_b200_ctx* c);
 int vl_solver_set_attrs(vloam_b200_ctx* c);
+int vl_lo_preload(vloam_b200_ctx* c);
+int vl_vg_preload(vloam_b200_ctx* c);
+int vl_lm_preload(vloam_b200_ctx* c);
 int vl_lm_register_full(vloam_b200_ctx* c, const float4* d_in, int n, float4* d_out);
 int vl_lm_join(vloam_b200_ctx* c);      // wait until the helper thread has issued the pending map update; returns its status
 void vl_lm_shutdown(vloam_b200_ctx* c);  // stop the helper thread

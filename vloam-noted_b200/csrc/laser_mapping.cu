@@ -1633,3 +1633,36 @@ int vl_lm_import_map(vloam_b200_ctx* c, int which, const void* data, long bytes)
   if (which) d->hMapUpperS = total; else d->hMapUpperC = total;
   return VLOAM_OK;
 }
+
+int vl_lm_preload(vloam_b200_ctx* c) {  // see vl_sr_set_attrs: load every kernel of this file when a context is created
+  cudaFuncAttributes fa_;
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_prepare));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_spec_prepare));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_grid_zero));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_gather));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_grid_count));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_scan_tiles));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_scan_sums));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_scan_apply));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_grid_fill));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_inline_build));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_knn));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_fit));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_transform_update));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, rf_keys));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, rf_seg_scan));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, rf_seg_scatter));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, rf_seg_sort));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, rf_match));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, rf_scan_layout));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, rf_emit_new));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, rf_emit_prefix));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, rf_alloc));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, rf_commit));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, rf_finish));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, rf_append_outside));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_scan_sorted));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_set_counts));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_register_full));
+  return VLOAM_OK;
+}

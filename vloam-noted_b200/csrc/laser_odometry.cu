@@ -574,6 +574,17 @@ static int lo_associate(vloam_b200_ctx* c, const double* d_pose, const float4* c
   return VLOAM_OK;
 }
 
+int vl_lo_preload(vloam_b200_ctx* c) {  // see vl_sr_set_attrs: load every kernel of this file when a context is created
+  cudaFuncAttributes fa_;
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lo_ring_table)); VL_CUDA(cudaFuncGetAttributes(&fa_, lo_ring_table_init));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lo_assoc<false>)); VL_CUDA(cudaFuncGetAttributes(&fa_, lo_assoc<true>));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lo_grid_count)); VL_CUDA(cudaFuncGetAttributes(&fa_, lo_grid_fill));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lo_assoc_grid<false>)); VL_CUDA(cudaFuncGetAttributes(&fa_, lo_assoc_grid<true>));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lo_assoc_grid_both)); VL_CUDA(cudaFuncGetAttributes(&fa_, lo_accumulate));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lo_set_prior));
+  return VLOAM_OK;
+}
+
 extern bool vl_debug_capture(const vloam_b200_ctx* c);
 
 // debug: the first call arms the per-warp trace of the grid association; later calls copy it out (n ints)

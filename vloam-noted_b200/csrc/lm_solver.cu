@@ -590,6 +590,13 @@ int vl_solver_set_attrs(vloam_b200_ctx* c) {
   VL_CUDA(cudaFuncSetAttribute(lm_solve_cluster<2, 256>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   VL_CUDA(cudaFuncSetAttribute(lm_solve_cluster<4, 256>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   VL_CUDA(cudaFuncSetAttribute(lm_solve_cluster<0, 256>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  // lazy module loading would otherwise charge each kernel's first launch (~1 ms apiece) to the first sweeps
+  cudaFuncAttributes fa_;
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_eval));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, (lm_solve_cluster<1, 256>)));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, (lm_solve_cluster<2, 256>)));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, (lm_solve_cluster<4, 256>)));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, (lm_solve_cluster<0, 256>)));
   return VLOAM_OK;
 }
 

@@ -901,6 +901,17 @@ int vl_sr_set_attrs(vloam_b200_ctx* c) {
                                (int)((size_t)VL_SECTORS * SR_SECT_CAP * sizeof(unsigned long long) + 2 * SR_RING_CAP)));
   VL_CUDA(cudaFuncSetAttribute(sr_ring_voxel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)((size_t)SR_VOX_CAP * (sizeof(unsigned long long) + sizeof(float4)))));
+  // lazy module loading would otherwise charge each kernel's first launch (~1 ms apiece) to the first sweeps
+  cudaFuncAttributes fa_;
+  VL_CUDA(cudaFuncGetAttributes(&fa_, sr_find_bounds));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, sr_classify));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, sr_ring_scan));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, sr_scatter));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, sr_curvature));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, sr_pick));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, sr_ring_voxel));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, sr_offsets));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, sr_gather));
   return VLOAM_OK;
 }
 

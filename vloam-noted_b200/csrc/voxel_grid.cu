@@ -165,6 +165,12 @@ __global__ void __launch_bounds__(CS_THREADS) bt_cluster_sort(unsigned long long
 int vl_sort_set_attrs(vloam_b200_ctx* c) {
   VL_CUDA(cudaFuncSetAttribute(bt_cluster_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 8));
   VL_CUDA(cudaFuncSetAttribute(bt_cluster_sort, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  // lazy module loading would otherwise charge each kernel's first launch (~1 ms apiece) to the first sweeps
+  cudaFuncAttributes fa_;
+  VL_CUDA(cudaFuncGetAttributes(&fa_, bt_tile_sort));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, bt_global_step));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, bt_tile_merge));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, bt_cluster_sort));
   return VLOAM_OK;
 }
 
@@ -409,5 +415,12 @@ int vl_voxel_grid_device(vloam_b200_ctx* c, const float4* d_in, int n, const int
   VL_BYTES(40.0 * n);  // key + gathered point in, centroid out
   VL_LAUNCH(vg_centroid, nTiles, VG_BLOCK, 0, d_in, vKeys.p, box, vScan.p, d_out);
   VL_CUDA(cudaGetLastError());
+  return VLOAM_OK;
+}
+
+int vl_vg_preload(vloam_b200_ctx* c) {  // see vl_sr_set_attrs: load the voxel-filter kernels when a context is created
+  cudaFuncAttributes fa_;
+  VL_CUDA(cudaFuncGetAttributes(&fa_, vg_bbox)); VL_CUDA(cudaFuncGetAttributes(&fa_, vg_box)); VL_CUDA(cudaFuncGetAttributes(&fa_, vg_keys));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, vg_head_count)); VL_CUDA(cudaFuncGetAttributes(&fa_, vg_block_scan)); VL_CUDA(cudaFuncGetAttributes(&fa_, vg_centroid));
   return VLOAM_OK;
 }
