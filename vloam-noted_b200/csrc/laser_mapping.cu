@@ -401,16 +401,6 @@ __device__ __forceinline__ void lm_dev_gather(const LmSub* __restrict__ sub, con
     else outC[e] = poolC[tc->start[cb] + (e - off[lo])];
   }
 }
-__global__ void __launch_bounds__(256) lm_gather(const LmSub* __restrict__ sub, const int* __restrict__ skip,
-                                                 const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts,
-                                                 const float4* __restrict__ poolC, const float4* __restrict__ poolS,
-                                                 float4* __restrict__ outC, float4* __restrict__ outS) {
-  VL_PDL_WAIT();
-
-  if (skip && *skip) return;
-  lm_dev_gather(sub, tc, ts, poolC, poolS, outC, outS);
-}
-
 // ---- search grid: counting sort of both sub-maps into 2 m cells --------------------------------
 __device__ __forceinline__ int lm_cell_coord(float v, float o, int n) {
   const int cidx = (int)floorf(__fmul_rn(__fsub_rn(v, o), 1.0f / LM_CELL));
@@ -428,13 +418,29 @@ __device__ __forceinline__ void lm_dev_count(const LmSub* __restrict__ sub, cons
     atomicAdd(&cellCount[cell], 1);
   }
 }
-__global__ void __launch_bounds__(256) lm_grid_count(const LmSub* __restrict__ sub, const int* __restrict__ skip,
-                                                     const float4* __restrict__ mapC, const float4* __restrict__ mapS,
-                                                     int* __restrict__ cellCount, int* __restrict__ cellOfPoint) {
+// Speculative path: gather and cell count in one pass -- each point is read from the pool once, written to the
+// sub-map cloud and binned (one launch and one re-read of the gathered cloud less on the update -> sub-map chain).
+__global__ void __launch_bounds__(256) lm_gather_count(const LmSub* __restrict__ sub, const MapCubeTable* __restrict__ tc,
+                                                       const MapCubeTable* __restrict__ ts, const float4* __restrict__ poolC,
+                                                       const float4* __restrict__ poolS, float4* __restrict__ outC, float4* __restrict__ outS,
+                                                       int* __restrict__ cellCount, int* __restrict__ cellOfPoint) {
   VL_PDL_WAIT();
 
-  if (skip && *skip) return;
-  lm_dev_count(sub, mapC, mapS, cellCount, cellOfPoint);
+  const int nv = sub->validNum, mc = sub->Mc, total = sub->Mc + sub->Ms;
+  const float ox = sub->gridOrigin[0], oy = sub->gridOrigin[1], oz = sub->gridOrigin[2];
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
+    const int kind = g >= mc;
+    const int e = kind ? g - mc : g;
+    const int* off = sub->gatherOff[kind];
+    int lo = 0, hi = nv;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid] <= e) lo = mid; else hi = mid; }
+    const int cb = sub->validInd[lo];
+    const float4 p = kind ? poolS[ts->start[cb] + (e - off[lo])] : poolC[tc->start[cb] + (e - off[lo])];
+    if (kind) outS[e] = p; else outC[e] = p;
+    const int cell = kind * LM_NCELL + lm_cell_coord(p.x, ox, LM_GX) + LM_GX * (lm_cell_coord(p.y, oy, LM_GY) + LM_GY * lm_cell_coord(p.z, oz, LM_GZ));
+    cellOfPoint[g] = cell;
+    atomicAdd(&cellCount[cell], 1);
+  }
 }
 // exclusive scan over 2*LM_NCELL counts: tile sums (1024 per block) -> scan of tile sums -> apply
 __device__ __forceinline__ void lm_dev_scan_tile(const int* __restrict__ in, int n, int* __restrict__ tileSum, int tile) {  // 256 threads
@@ -1324,22 +1330,6 @@ int vl_lm_enqueue_stacks(vloam_b200_ctx* c, const float4* corner, int nc, const 
   return VLOAM_OK;
 }
 
-// search grid over the gathered sub-map (LM.cpp:519-520's two KD-tree builds): counting sort into 2 m cells
-static int lm_build_grid(vloam_b200_ctx* c, LmDevice* d, const LmSub* sub, const int* d_skip, long long totalBound, bool zeroed = false) {
-  const int nCells = 2 * LM_NCELL;
-  const int gsGrid = c->num_sms * 8;
-  if (!zeroed) {
-    VL_BYTES(8.0 * (nCells + 1));
-    VL_LAUNCH(lm_grid_zero, gsGrid, 256, 0, d->cellCount, d->cellFill, nCells + 1, d_skip);
-  }
-  VL_BYTES(24.0 * (double)totalBound);  // read point, write cell id, atomic on the cell counter
-  VL_LAUNCH(lm_grid_count, gsGrid, 256, 0, sub, d_skip, c->fromMapC.p, c->fromMapS.p, d->cellCount, d->cellOfPoint.p);
-  VL_TRY(vl_scan_exclusive(c, d->cellCount, nCells, d->tileSum, d->cellStart, d_skip));
-  VL_BYTES(44.0 * (double)totalBound);  // read point + cell id + cell start, atomic, write sorted point
-  VL_LAUNCH(lm_grid_fill, gsGrid, 256, 0, sub, d_skip, c->fromMapC.p, c->fromMapS.p, d->cellOfPoint.p, d->cellStart, d->cellFill, d->sortedPts.p);
-  return VLOAM_OK;
-}
-
 // in-line sub-map build of this frame (one cooperative launch; returns at once on the device when *specOK)
 static int lm_inline_launch(vloam_b200_ctx* c, LmDevice* d, long long totalBound) {
   LmInlineArgs a;
@@ -1525,10 +1515,14 @@ int vl_lm_run(vloam_b200_ctx* c) {
     VL_TRY(vl_reserve(c, d->cellOfPoint, (size_t)max(tb, 1LL), false, (size_t)tb / 2 + (1 << 20)));
     VL_TRY(vl_reserve(c, d->sortedPts, (size_t)max(tb, 1LL), false, (size_t)tb / 2 + (1 << 20)));
     VL_LAUNCH(lm_spec_prepare, 1, 256, 0, d->subReal, c->cubeC, c->cubeS, d->subSpec);
-    VL_BYTES(32.0 * (double)tb);
-    VL_LAUNCH(lm_gather, gsGrid, 256, 0, d->subSpec, (const int*)nullptr, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, c->fromMapC.p, c->fromMapS.p);
-    VL_CUDA(cudaStreamWaitEvent(c->stream3, c->evAuxZero, 0));
-    VL_TRY(lm_build_grid(c, d, d->subSpec, nullptr, tb, true));
+    VL_CUDA(cudaStreamWaitEvent(c->stream3, c->evAuxZero, 0));  // the cell counters were zeroed on streamAux
+    VL_BYTES(56.0 * (double)tb);
+    VL_LAUNCH(lm_gather_count, gsGrid, 256, 0, d->subSpec, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, c->fromMapC.p, c->fromMapS.p, d->cellCount,
+              d->cellOfPoint.p);
+    VL_TRY(vl_scan_exclusive(c, d->cellCount, 2 * LM_NCELL, d->tileSum, d->cellStart, nullptr));
+    VL_BYTES(44.0 * (double)tb);
+    VL_LAUNCH(lm_grid_fill, gsGrid, 256, 0, d->subSpec, (const int*)nullptr, c->fromMapC.p, c->fromMapS.p, d->cellOfPoint.p, d->cellStart, d->cellFill,
+              d->sortedPts.p);
     d->specQueued = true;
   }
   VL_CUDA(cudaEventRecord(c->evMap, c->stream3));
@@ -1639,8 +1633,7 @@ int vl_lm_preload(vloam_b200_ctx* c) {  // see vl_sr_set_attrs: load every kerne
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_prepare));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_spec_prepare));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_grid_zero));
-  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_gather));
-  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_grid_count));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_gather_count));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_scan_tiles));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_scan_sums));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_scan_apply));
