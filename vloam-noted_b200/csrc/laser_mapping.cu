@@ -181,20 +181,19 @@ __device__ __forceinline__ unsigned lm_vox_key_cube(const float4 p, float inv, i
 
 // exclusive scan of one int per thread over the first 256 threads of the block (all threads must call)
 __device__ __forceinline__ int lm_scan256(int v, int* buf, int* total) {
-  const int t = threadIdx.x;
-  if (t < 256) buf[t] = v;
+  // exclusive scan over threads 0..255 (block of 256 or 1024 threads; every thread must call): warp shuffles, then
+  // the eight warp totals through shared memory -- two barriers instead of the eighteen of a Hillis-Steele ladder
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  int inc = t < 256 ? v : 0;
+  for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+  if (t < 256 && lane == 31) buf[warp] = inc;
   __syncthreads();
-  for (int d = 1; d < 256; d <<= 1) {
-    int u = 0;
-    if (t < 256 && t >= d) u = buf[t - d];
-    __syncthreads();
-    if (t < 256) buf[t] += u;
-    __syncthreads();
-  }
-  const int incl = t < 256 ? buf[t] : 0;
-  if (total) *total = buf[255];
+  int before = 0, all = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { const int sw = buf[w]; if (w < warp) before += sw; all += sw; }
+  if (total) *total = all;
   __syncthreads();
-  return incl - v;
+  return t < 256 ? before + inc - v : 0;
 }
 
 // ---- LaserMapping::input (LM.cpp:178-209) + centre cube / roll / valid list (LM.cpp:228-466)
