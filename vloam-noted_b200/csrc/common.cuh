@@ -406,6 +406,30 @@ __device__ __forceinline__ void vl_qmul(const double a[4], const double b[4], do
     }                                                                                                          \
   } while (0)
 
+// Exclusive scan of one int per thread over a block of T threads (T a multiple of 32, <= 1024; every thread calls):
+// warp shuffles, the T/32 warp totals through `ws` (>= 32 ints of shared memory) and a second shuffle scan by warp 0:
+// three barriers, where a Hillis-Steele ladder over 1024 entries takes twenty.  *total (may be null) = block sum.
+template <int T>
+__device__ __forceinline__ int vl_block_excl_scan(int v, int* ws, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+  if (lane == 31) ws[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int x = lane < T / 32 ? ws[lane] : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += u; }
+    ws[lane] = x;
+  }
+  __syncthreads();
+  const int before = warp > 0 ? ws[warp - 1] : 0;
+  if (total) *total = ws[T / 32 - 1];
+  __syncthreads();
+  return before + inc - v;
+}
+
 // FLANN L2_Simple<float>: acc = 0; acc += d*d over x, y, z (f32, no FMA: -fmad=false).
 __device__ __forceinline__ float vl_dist2(float qx, float qy, float qz, float px, float py, float pz) {
   float acc = 0.f, d;

@@ -462,25 +462,15 @@ __global__ void __launch_bounds__(256) lm_scan_tiles(const int* __restrict__ in,
 // exclusive scan of the tile sums in place by ONE block of T threads (T a power of two <= 1024)
 template <int T>
 __device__ __forceinline__ void lm_dev_scan_sums(int* __restrict__ tileSum, int nTiles) {
-  __shared__ int buf[T];
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
+  __shared__ int ws[32];
+  int carry = 0;  // the same value in every thread
   for (int base = 0; base < nTiles; base += T) {
     const int b = base + threadIdx.x;
     const int own = b < nTiles ? tileSum[b] : 0;
-    buf[threadIdx.x] = own;
-    __syncthreads();
-    for (int d = 1; d < T; d <<= 1) {
-      const int v = threadIdx.x >= d ? buf[threadIdx.x - d] : 0;
-      __syncthreads();
-      buf[threadIdx.x] += v;
-      __syncthreads();
-    }
-    if (b < nTiles) tileSum[b] = carry + buf[threadIdx.x] - own;
-    __syncthreads();
-    if (threadIdx.x == T - 1) carry += buf[T - 1];
-    __syncthreads();
+    int tot = 0;
+    const int ex = vl_block_excl_scan<T>(own, ws, &tot);
+    if (b < nTiles) tileSum[b] = carry + ex;
+    carry += tot;
   }
 }
 __global__ void __launch_bounds__(1024) lm_scan_sums(int* __restrict__ tileSum, int nTiles, const int* __restrict__ skip) {
@@ -947,26 +937,16 @@ __global__ void __launch_bounds__(1024) rf_scan_layout(int* __restrict__ unmatch
   VL_PDL_WAIT();
 
   // exclusive scan of unmatched[0..n) in place, unmatched[n] = total
-  __shared__ int buf[1024];
-  __shared__ int carry;
+  __shared__ int ws[32];
   const int n = w->nKeysValid;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
+  int carry = 0;  // the same value in every thread
   for (int base = 0; base < n; base += 1024) {
     const int b = base + threadIdx.x;
     const int own = b < n ? unmatched[b] : 0;
-    buf[threadIdx.x] = own;
-    __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {
-      const int v = threadIdx.x >= d ? buf[threadIdx.x - d] : 0;
-      __syncthreads();
-      buf[threadIdx.x] += v;
-      __syncthreads();
-    }
-    if (b < n) unmatched[b] = carry + buf[threadIdx.x] - own;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry += buf[1023];
-    __syncthreads();
+    int tot = 0;
+    const int ex = vl_block_excl_scan<1024>(own, ws, &tot);
+    if (b < n) unmatched[b] = carry + ex;
+    carry += tot;
   }
   if (threadIdx.x == 0) unmatched[n] = carry;
   __syncthreads();

@@ -785,25 +785,16 @@ __global__ void __launch_bounds__(1024) sr_offsets(int nscans, const int* __rest
                                                    int* __restrict__ dsOff, SrScalars* __restrict__ s) {
   VL_PDL_WAIT();
 
-  __shared__ int buf[4][1024];
+  __shared__ int ws[32];
   const int t = threadIdx.x;
   const int nslots = nscans * VL_SECTORS;
-  buf[0][t] = t < nslots ? cntSharp[t] : 0;
-  buf[1][t] = t < nslots ? cntLess[t] : 0;
-  buf[2][t] = t < nslots ? cntFlat[t] : 0;
-  buf[3][t] = t < nscans ? dsCount[t] : 0;
-  int own[4] = {buf[0][t], buf[1][t], buf[2][t], buf[3][t]};
-  __syncthreads();
-  for (int d = 1; d < 1024; d <<= 1) {
-    int v[4];
-    for (int a = 0; a < 4; ++a) v[a] = t >= d ? buf[a][t - d] : 0;
-    __syncthreads();
-    for (int a = 0; a < 4; ++a) buf[a][t] += v[a];
-    __syncthreads();
-  }
-  if (t < nslots) { offSharp[t] = buf[0][t] - own[0]; offLess[t] = buf[1][t] - own[1]; offFlat[t] = buf[2][t] - own[2]; }
-  if (t < nscans) dsOff[t] = buf[3][t] - own[3];
-  if (t == 1023) { s->nSharp = buf[0][t]; s->nLessSharp = buf[1][t]; s->nFlat = buf[2][t]; s->nLessFlat = buf[3][t]; s->nQueries = buf[0][t] + buf[2][t]; }
+  const int own[4] = {t < nslots ? cntSharp[t] : 0, t < nslots ? cntLess[t] : 0, t < nslots ? cntFlat[t] : 0, t < nscans ? dsCount[t] : 0};
+  int ex[4], tot[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) ex[a] = vl_block_excl_scan<1024>(own[a], ws, &tot[a]);
+  if (t < nslots) { offSharp[t] = ex[0]; offLess[t] = ex[1]; offFlat[t] = ex[2]; }
+  if (t < nscans) dsOff[t] = ex[3];
+  if (t == 0) { s->nSharp = tot[0]; s->nLessSharp = tot[1]; s->nFlat = tot[2]; s->nLessFlat = tot[3]; s->nQueries = tot[0] + tot[2]; }
 }
 
 __global__ void __launch_bounds__(SR_BLOCK) sr_gather(const float4* __restrict__ cloud, int nscans, const SrScalars* __restrict__ s,

@@ -310,25 +310,15 @@ __global__ void __launch_bounds__(1024) vg_block_scan(int* __restrict__ blockCnt
                                                       int* __restrict__ dCount) {
   VL_PDL_WAIT();
 
-  __shared__ int buf[1024];
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
+  __shared__ int ws[32];
+  int carry = 0;  // the same value in every thread
   for (int base = 0; base < nBlocks; base += 1024) {
     const int b = base + threadIdx.x;
     const int own = b < nBlocks ? blockCnt[b] : 0;
-    buf[threadIdx.x] = own;
-    __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {
-      const int v = threadIdx.x >= d ? buf[threadIdx.x - d] : 0;
-      __syncthreads();
-      buf[threadIdx.x] += v;
-      __syncthreads();
-    }
-    if (b < nBlocks) blockCnt[b] = carry + buf[threadIdx.x] - own;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry += buf[1023];
-    __syncthreads();
+    int tot = 0;
+    const int ex = vl_block_excl_scan<1024>(own, ws, &tot);
+    if (b < nBlocks) blockCnt[b] = carry + ex;
+    carry += tot;
   }
   if (threadIdx.x == 0) *dCount = box->guard ? box->n : carry;
 }
