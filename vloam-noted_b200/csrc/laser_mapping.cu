@@ -1106,7 +1106,7 @@ __global__ void __launch_bounds__(1024) rf_append_outside(LmScalars* __restrict_
   VL_PDL_WAIT();
 
   const int Qc = s->Qc, total = s->Qc + s->Qs;
-  __shared__ int lIdx[1024], lKey[1024], lRank[1024], lTot[1024];
+  __shared__ int lIdx[1024], lKey[1024];
   __shared__ int gKey[1024], gOld[1024], gNew[1024], gCnt[1024];
   __shared__ int warpSum[32];
   __shared__ int nGrow;
@@ -1133,7 +1133,6 @@ __global__ void __launch_bounds__(1024) rf_append_outside(LmScalars* __restrict_
     if (e < n) {
       key = lKey[e];
       for (int q = 0; q < n; ++q) { const bool same = lKey[q] == key; rank += (same && q < e); tot += same; }
-      lRank[e] = rank; lTot[e] = tot;
       if (rank == 0) {
         const int kind = key >= VL_CUBE_NUM, c2 = key - kind * VL_CUBE_NUM;
         const MapCubeTable* tb = kind ? ts : tc;
