@@ -74,12 +74,20 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   cudaDeviceProp prop;
   VL_CUDA_CREATE(cudaGetDeviceProperties(&prop, device));
   c->num_sms = prop.multiProcessorCount;
-  VL_CUDA_CREATE(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  VL_CUDA_CREATE(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-  VL_CUDA_CREATE(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
-  VL_CUDA_CREATE(cudaStreamCreateWithFlags(&c->stream4, cudaStreamNonBlocking));
+  // Stream priorities: the pose chain (main stream) goes first, the stack filters it waits on next, and the work
+  // that only has to be ready for the NEXT sweep (map update, speculative sub-map, look-ahead scan registration)
+  // last -- when SMs free up, blocks of the solver's 16-CTA cluster are placed before the streaming grids' blocks.
+  // VLOAM_NO_PRIORITIES=1: all streams at the default priority.
+  int prLow = 0, prHigh = 0;
+  VL_CUDA_CREATE(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
+  if (getenv("VLOAM_NO_PRIORITIES")) prHigh = prLow;
+  const int prMid = prHigh < prLow ? prHigh + 1 : prLow;
+  VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prHigh));
+  VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prMid));
+  VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, prLow));
+  VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->stream4, cudaStreamNonBlocking, prMid));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evStacksC, cudaEventDisableTiming));
-  VL_CUDA_CREATE(cudaStreamCreateWithFlags(&c->streamAux, cudaStreamNonBlocking));
+  VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->streamAux, cudaStreamNonBlocking, prLow));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evAux, cudaEventDisableTiming));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evAuxZero, cudaEventDisableTiming));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evUpd, cudaEventDisableTiming));
@@ -87,6 +95,7 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evLast, cudaEventDisableTiming));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evPose, cudaEventDisableTiming));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evMap, cudaEventDisableTiming));
+  VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evKeys, cudaEventDisableTiming));
   c->stacksReady = false; c->lm_reset_pending = true; c->lastSet = 0; c->loGridValid[0] = c->loGridValid[1] = false;
   for (int k = 0; k < 4; ++k) VL_CUDA_CREATE(cudaEventCreate(&c->ev[k]));
   for (int k = 0; k < 8; ++k) { VL_CUDA_CREATE(cudaEventCreate(&c->evx[k])); VL_CUDA_CREATE(cudaEventRecord(c->evx[k], c->stream)); }
@@ -95,7 +104,7 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   vl_sr_swap(c, *c->srNext);      // the spare set gets its own fixed-size arrays, counters and event
   { const int r_ = alloc_sr_fixed(c); vl_sr_swap(c, *c->srNext); if (r_ != VLOAM_OK) return r_; }
   c->srNextKey = nullptr; c->srNextValid = false; c->srPendKey = nullptr; c->srPendDevice = false;
-  VL_CUDA_CREATE(cudaStreamCreateWithFlags(&c->streamSR, cudaStreamNonBlocking));
+  VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->streamSR, cudaStreamNonBlocking, prLow));
   VL_CUDA_CREATE(cudaMalloc(&c->los, sizeof(LoScalars)));
   VL_CUDA_CREATE(cudaMallocHost(&c->h_los, sizeof(LoScalars)));
   LoScalars hl; memset(&hl, 0, sizeof hl); hl.para_q[3] = 1.0; hl.q_w[3] = 1.0;  // LO.cpp:81-91
@@ -140,6 +149,7 @@ void vloam_b200_destroy(vloam_b200_ctx* c) {
   if (c->srNext) { vl_sr_swap(c, *c->srNext); free_sr_set(c); delete c->srNext; c->srNext = nullptr; }
   cudaStreamDestroy(c->streamSR);
   vl_lm_free(c);
+  vl_scan_free(&c->loScan[0]); vl_scan_free(&c->loScan[1]);
   void* singles[] = {c->los, c->evalOut, c->lms, c->lmm, c->cubeC, c->cubeS, c->vScalars, c->loRingTbl, c->loGridCells[0].p, c->loGridCells[1].p,
                      c->loGridCellOf.p, c->loGridSorted[0].p, c->loGridSorted[1].p, c->dbgLoCorner[0].p, c->dbgLoCorner[1].p, c->dbgLoSurf[0].p,
                      c->dbgLoSurf[1].p, c->dbgKnnIdx[0][0].p, c->dbgKnnIdx[0][1].p, c->dbgKnnIdx[1][0].p, c->dbgKnnIdx[1][1].p, c->dbgKnnD2[0][0].p,
@@ -154,7 +164,7 @@ void vloam_b200_destroy(vloam_b200_ctx* c) {
   for (int k = 0; k < 4; ++k) cudaEventDestroy(c->ev[k]);
   for (int k = 0; k < 8; ++k) cudaEventDestroy(c->evx[k]);
   cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream3);
-  cudaEventDestroy(c->evStacks); cudaEventDestroy(c->evLast); cudaEventDestroy(c->evPose); cudaEventDestroy(c->evMap);
+  cudaEventDestroy(c->evStacks); cudaEventDestroy(c->evLast); cudaEventDestroy(c->evPose); cudaEventDestroy(c->evMap); cudaEventDestroy(c->evKeys);
   cudaEventDestroy(c->evStacksC);
   cudaStreamSynchronize(c->streamAux); cudaEventDestroy(c->evAux); cudaEventDestroy(c->evAuxZero); cudaEventDestroy(c->evUpd); cudaStreamDestroy(c->streamAux);
   cudaStreamDestroy(c->stream2); cudaStreamDestroy(c->stream3); cudaStreamDestroy(c->stream4);

@@ -94,6 +94,9 @@ extern thread_local cudaStream_t vl_tls_stream;
 #define VL_STREAM(c) (vl_tls_stream ? vl_tls_stream : (c)->stream)
 struct VlWorker;
 
+// status words of one single-launch scan: tiles x (epoch | status | value) and the tile ticket counter
+struct VlScan { unsigned long long* state = nullptr; int tiles = 0; unsigned epoch = 0; };
+
 struct vloam_b200_ctx {
   vloam_b200_params prm;
   int device;
@@ -109,6 +112,7 @@ struct vloam_b200_ctx {
   cudaEvent_t evLast;         // search structures over the next "last" clouds are built
   cudaEvent_t evPose;         // solveMapping's pose is final (the map update may start)
   cudaEvent_t evMap;          // the map update has finished (the next solveMapping may start)
+  cudaEvent_t evKeys;         // the map update has read the stacks (rf_keys): the next sweep's stack filters may start
   bool stacksReady;
   bool lm_reset_pending;      // LaserMapping::reset was called since the last solveMapping
   char err[512];
@@ -161,6 +165,7 @@ struct vloam_b200_ctx {
   // search structures over the "last" clouds, double-buffered: set [lastSet] serves this frame's odometry
   // while the side stream builds set [lastSet ^ 1] from this frame's clouds
   int* loRingTbl;                     // 2 sets x 2 clouds x (144 + 1) ints: ring-value -> first index tables
+  VlScan loScan[2];
   DBuf<int> loGridCells[2], loGridCellOf; DBuf<float4> loGridSorted[2]; bool loGridValid[2];
   int lastSet;
   DBuf<int> loCornerIdx, loSurfIdx;   // association results (2 / 3 ints per query)
@@ -309,7 +314,7 @@ int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, i
 int vl_lo_associate_only(vloam_b200_ctx* c, const double* x, int* corner_idx, int* surf_idx);
 int vl_lo_build_last(vloam_b200_ctx* c, int set, const float4* corner, int nc, const float4* surf, int ns);
 int vl_lm_run(vloam_b200_ctx* c);
-int vl_lm_enqueue_stacks(vloam_b200_ctx* c, const float4* corner, int nc, const float4* surf, int ns);
+int vl_lm_enqueue_stacks(vloam_b200_ctx* c, const float4* corner, int nc, const float4* surf, int ns, bool early = false);
 int vl_lm_init(vloam_b200_ctx* c);
 void vl_lm_free(vloam_b200_ctx* c);
 extern "C" int vl_launch_lookahead(vloam_b200_ctx* c);  // capi.cu: queue the registered look-ahead scan registration (no-op without one)
@@ -325,7 +330,11 @@ void vl_lm_shutdown(vloam_b200_ctx* c);  // stop the helper thread
 int vl_lm_export_map(vloam_b200_ctx* c, int which, void* out, long cap, long* bytes);
 int vl_lm_import_map(vloam_b200_ctx* c, int which, const void* data, long bytes);
 
-int vl_scan_exclusive(vloam_b200_ctx* c, const int* in, int n, int* tileSum, int* out, const int* d_skip = nullptr);  // laser_mapping.cu; d_skip: device flag, non-zero = do nothing
+// out[0..n] = exclusive scan of in[0..n) in ONE launch (chained scan with look-back, laser_mapping.cu).  `in` and `out`
+// must be 16-byte aligned; d_skip: device flag, non-zero = do nothing.  A VlScan holds the per-tile status words.
+int vl_scan_alloc(VlScan* sc, int n);
+void vl_scan_free(VlScan* sc);
+int vl_scan_exclusive(vloam_b200_ctx* c, const int* in, int n, VlScan* sc, int* out, const int* d_skip = nullptr);
 // sort / voxel primitives (voxel_grid.cu)
 int vl_sort_u64(vloam_b200_ctx* c, unsigned long long* d_keys, int n_pow2);
 // pcl::VoxelGrid of d_in[0..n) -> d_out, count written to *d_count (device int); n is a host bound,

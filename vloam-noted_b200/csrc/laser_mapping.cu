@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(1024) lm_prepare(LmScalars* __restrict__ s, co
   __shared__ int sTot[2];
   if (threadIdx.x < 2) sTot[threadIdx.x] = 0;
   __syncthreads();
-  if (threadIdx.x <= LM_NSEG) w->segCount[threadIdx.x] = 0;  // histogram of this frame's update keys (rf_keys)
+  if (threadIdx.x <= LM_NSEG) { w->segCount[threadIdx.x] = 0; w->segFill[threadIdx.x] = 0; }  // histogram / bucket cursors of this frame's update keys
   int myC = 0, myS = 0;
   for (int d = threadIdx.x; d < VL_CUBE_NUM; d += 1024) { w->slotOfCube[d] = -1; myC += tc->count[d]; myS += ts->count[d]; }
   for (int o = 16; o > 0; o >>= 1) { myC += __shfl_xor_sync(0xffffffffu, myC, o); myS += __shfl_xor_sync(0xffffffffu, myS, o); }
@@ -441,7 +441,8 @@ __global__ void __launch_bounds__(256) lm_gather_count(const LmSub* __restrict__
     atomicAdd(&cellCount[cell], 1);
   }
 }
-// exclusive scan over 2*LM_NCELL counts: tile sums (1024 per block) -> scan of tile sums -> apply
+// exclusive scan over 2*LM_NCELL counts, three-phase form for the cooperative in-line build: tile sums (1024 per
+// block) -> scan of tile sums -> apply
 __device__ __forceinline__ void lm_dev_scan_tile(const int* __restrict__ in, int n, int* __restrict__ tileSum, int tile) {  // 256 threads
   int acc = 0;
   const int base = tile * 1024;
@@ -452,12 +453,6 @@ __device__ __forceinline__ void lm_dev_scan_tile(const int* __restrict__ in, int
   if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x == 0) { int v = 0; for (int k = 0; k < 8; ++k) v += ws[k]; tileSum[tile] = v; }
-}
-__global__ void __launch_bounds__(256) lm_scan_tiles(const int* __restrict__ in, int n, int* __restrict__ tileSum, const int* __restrict__ skip) {
-  VL_PDL_WAIT();
-
-  if (skip && *skip) return;
-  lm_dev_scan_tile(in, n, tileSum, blockIdx.x);
 }
 // exclusive scan of the tile sums in place by ONE block of T threads (T a power of two <= 1024)
 template <int T>
@@ -472,12 +467,6 @@ __device__ __forceinline__ void lm_dev_scan_sums(int* __restrict__ tileSum, int 
     if (b < nTiles) tileSum[b] = carry + ex;
     carry += tot;
   }
-}
-__global__ void __launch_bounds__(1024) lm_scan_sums(int* __restrict__ tileSum, int nTiles, const int* __restrict__ skip) {
-  VL_PDL_WAIT();
-
-  if (skip && *skip) return;
-  lm_dev_scan_sums<1024>(tileSum, nTiles);
 }
 __device__ __forceinline__ void lm_dev_scan_apply(const int* __restrict__ in, int n, const int* __restrict__ tileSum, int* __restrict__ out,
                                                   int tile, int nTiles) {  // 256 threads
@@ -499,21 +488,90 @@ __device__ __forceinline__ void lm_dev_scan_apply(const int* __restrict__ in, in
   }
   if (tile == nTiles - 1 && threadIdx.x == 0) out[n] = running;  // total
 }
-__global__ void __launch_bounds__(256) lm_scan_apply(const int* __restrict__ in, int n, const int* __restrict__ tileSum, int* __restrict__ out,
-                                                     const int* __restrict__ skip) {
+// ---- single-launch exclusive scan (chained tiles with look-back) --------------------------------------
+// out[0..n] = exclusive scan of in[0..n) (out[n] = total).  A tile is 1024 counts (4 consecutive per thread, one
+// 128-bit load and store each).  Tiles take their index from a ticket counter, so every predecessor of a running
+// tile is itself running or done; a tile publishes its own sum at once ("aggregate"), warp 0 then walks the status
+// words of the tiles before it, 32 at a time, until it meets one that already knows its inclusive prefix, and
+// publishes its own.  Status word: [63:34] epoch of this launch | [33:32] 1 aggregate / 2 inclusive | [31:0] value --
+// written and read as one 64-bit word, and stale words of earlier launches simply read as "not ready", so nothing
+// has to be cleared between launches.  The three-kernel version (tile sums, scan of sums, apply) cost two more
+// dependent launches and a second read of the counts on the update -> sub-map chain.
+#define SCAN_TILE 1024
+__global__ void __launch_bounds__(256) lm_scan_chained(const int* __restrict__ in, int n, unsigned long long* __restrict__ state,
+                                                       unsigned epoch, int* __restrict__ out, const int* __restrict__ skip) {
   VL_PDL_WAIT();
 
   if (skip && *skip) return;
-  lm_dev_scan_apply(in, n, tileSum, out, blockIdx.x, gridDim.x);
+  __shared__ int sTile, sPrefix;
+  __shared__ int ws[32];
+  int* ticket = reinterpret_cast<int*>(state + gridDim.x);
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(ticket, 1);
+    if (t == (int)gridDim.x - 1) *ticket = 0;  // every tile has its ticket: ready for the next launch
+    sTile = t;
+  }
+  __syncthreads();
+  const int tile = sTile;
+  const int base = tile * SCAN_TILE + threadIdx.x * 4;
+  int4 v = make_int4(0, 0, 0, 0);
+  if (base + 3 < n) v = *reinterpret_cast<const int4*>(in + base);
+  else { if (base < n) v.x = in[base]; if (base + 1 < n) v.y = in[base + 1]; if (base + 2 < n) v.z = in[base + 2]; }
+  int tot = 0;
+  const int ex = vl_block_excl_scan<256>(v.x + v.y + v.z + v.w, ws, &tot);
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const unsigned long long tag = (unsigned long long)epoch << 34;
+    volatile unsigned long long* st = state;
+    int excl = 0;
+    if (tile > 0) {
+      if (lane == 0) st[tile] = tag | (1ull << 32) | (unsigned)tot;
+      int look = tile - 1;
+      for (;;) {
+        const int idx = look - lane;
+        const unsigned long long wd = idx >= 0 ? st[idx] : (tag | (2ull << 32));  // before tile 0: inclusive prefix 0
+        const int status = (wd >> 34) == (unsigned long long)epoch ? (int)((wd >> 32) & 3) : 0;
+        const unsigned notReady = __ballot_sync(0xffffffffu, status == 0);
+        const unsigned incl = __ballot_sync(0xffffffffu, status == 2);
+        const int f = incl ? __ffs(incl) - 1 : 32;                                  // nearest tile with an inclusive prefix
+        const unsigned need = f >= 31 ? 0xffffffffu : ((2u << f) - 1u);           // lanes 0..f (all 32 when there is none)
+        if (notReady & need) continue;                                             // a tile in between has not published yet
+        int val = lane <= f ? (int)(unsigned)wd : 0;
+        for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+        excl += val;
+        if (f < 32) break;
+        look -= 32;
+      }
+    }
+    if (lane == 0) { st[tile] = tag | (2ull << 32) | (unsigned)(excl + tot); sPrefix = excl; }
+  }
+  __syncthreads();
+  const int p0 = sPrefix + ex;
+  const int4 o = make_int4(p0, p0 + v.x, p0 + v.x + v.y, p0 + v.x + v.y + v.z);
+  if (base + 3 < n) *reinterpret_cast<int4*>(out + base) = o;
+  else { if (base < n) out[base] = o.x; if (base + 1 < n) out[base + 1] = o.y; if (base + 2 < n) out[base + 2] = o.z; }
+  if (tile == (int)gridDim.x - 1 && threadIdx.x == 0) out[n] = sPrefix + tot;
 }
-// out[0..n] = exclusive scan of in[0..n) (out[n] = total); tileSum needs ceil(n/1024)+1 ints
-int vl_scan_exclusive(vloam_b200_ctx* c, const int* in, int n, int* tileSum, int* out, const int* d_skip) {
-  const int nTiles = vl_div_up(n, 1024);
-  VL_BYTES(4.0 * n);
-  VL_LAUNCH(lm_scan_tiles, nTiles, 256, 0, in, n, tileSum, d_skip);
-  VL_LAUNCH(lm_scan_sums, 1, 1024, 0, tileSum, nTiles, d_skip);
+int vl_scan_alloc(VlScan* sc, int n) {
+  const int tiles = vl_div_up(n, SCAN_TILE);
+  if (sc->state && sc->tiles == tiles) return VLOAM_OK;
+  vl_scan_free(sc);
+  if (cudaMalloc(&sc->state, sizeof(unsigned long long) * (tiles + 1)) != cudaSuccess) return VLOAM_E_CUDA;
+  if (cudaMemset(sc->state, 0, sizeof(unsigned long long) * (tiles + 1)) != cudaSuccess) return VLOAM_E_CUDA;  // epoch 0 = never used
+  if (cudaDeviceSynchronize() != cudaSuccess) return VLOAM_E_CUDA;  // (first use only) the memset is not ordered with the non-blocking streams
+  sc->tiles = tiles; sc->epoch = 0;
+  return VLOAM_OK;
+}
+void vl_scan_free(VlScan* sc) { if (sc->state) cudaFree(sc->state); sc->state = nullptr; sc->tiles = 0; }
+int vl_scan_exclusive(vloam_b200_ctx* c, const int* in, int n, VlScan* sc, int* out, const int* d_skip) {
+  if (!sc->state || sc->tiles != vl_div_up(n, SCAN_TILE) || (((uintptr_t)in | (uintptr_t)out) & 15)) return VLOAM_E_INVALID;
+  if (sc->epoch >= (1u << 30) - 1) {  // the 30-bit epoch wraps: forget every old status word first
+    VL_CUDA(cudaMemsetAsync(sc->state, 0, sizeof(unsigned long long) * (sc->tiles + 1), VL_STREAM(c)));
+    sc->epoch = 0;
+  }
+  ++sc->epoch;
   VL_BYTES(8.0 * n);
-  VL_LAUNCH(lm_scan_apply, nTiles, 256, 0, in, n, tileSum, out, d_skip);
+  VL_LAUNCH(lm_scan_chained, sc->tiles, 256, 0, in, n, sc->state, sc->epoch, out, d_skip);
   return VLOAM_OK;
 }
 
@@ -848,27 +906,30 @@ __global__ void __launch_bounds__(256) rf_keys(const LmScalars* __restrict__ s, 
 // of one kind).  Instead of one bitonic network over all keys (37 us for 8k keys: ~48 barrier rounds of a
 // 1024-thread CTA pair), the keys are bucketed by segment -- histogram in rf_keys, a 250-entry scan that IS the
 // per-segment range table, one scatter -- and each bucket is sorted by its own CTA in shared memory.
-__global__ void __launch_bounds__(256) rf_seg_scan(RfWork* __restrict__ w) {
-  VL_PDL_WAIT();
-
-  __shared__ int sb[256];
-  const int t = threadIdx.x;
-  const int cnt = t < LM_NSEG ? w->segCount[t] : 0;
-  int total = 0;
-  const int off = lm_scan256(cnt, sb, &total);
-  if (t < LM_NSEG) { w->tailBegin[t] = off; w->segFill[t] = 0; w->firstViolation[t] = INT_MAX; }
-  if (t == 0) { w->tailBegin[LM_NSEG] = total; w->nKeysValid = total; }
-}
+// Every block of the scatter scans the 250 counts for itself (one 256-thread scan, ~1 us) instead of waiting for a
+// separate single-block launch; block 0 publishes the range table for the later steps.  segFill is zeroed by lm_prepare.
 __global__ void __launch_bounds__(256) rf_seg_scatter(const unsigned long long* __restrict__ in, int n, RfWork* __restrict__ w,
                                                       unsigned long long* __restrict__ out) {
   VL_PDL_WAIT();
 
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ int sb[256];
+  __shared__ int sBegin[256];
+  const int t = threadIdx.x;
+  const int cnt = t < LM_NSEG ? w->segCount[t] : 0;
+  int total = 0;
+  const int off = lm_scan256(cnt, sb, &total);
+  sBegin[t] = off;
+  if (blockIdx.x == 0) {
+    if (t < LM_NSEG) { w->tailBegin[t] = off; w->firstViolation[t] = INT_MAX; }
+    if (t == 0) { w->tailBegin[LM_NSEG] = total; w->nKeysValid = total; }
+  }
+  __syncthreads();
+  const int g = blockIdx.x * blockDim.x + t;
   if (g >= n) return;
   const unsigned long long key = in[g];
   if (key == ~0ull) return;
   const int sg = (int)(key >> 56);
-  out[w->tailBegin[sg] + atomicAdd(&w->segFill[sg], 1)] = key;
+  out[sBegin[sg] + atomicAdd(&w->segFill[sg], 1)] = key;
 }
 #define RF_SEG_THREADS 512
 #define RF_SEG_CAP 8192  // keys of one segment sorted in shared memory; larger segments use `scratch` (global)
@@ -936,16 +997,34 @@ __global__ void __launch_bounds__(1024) rf_scan_layout(int* __restrict__ unmatch
                                                        const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts) {
   VL_PDL_WAIT();
 
-  // exclusive scan of unmatched[0..n) in place, unmatched[n] = total
+  // exclusive scan of unmatched[0..n) in place, unmatched[n] = total; 8 consecutive flags per thread and round
   __shared__ int ws[32];
   const int n = w->nKeysValid;
   int carry = 0;  // the same value in every thread
-  for (int base = 0; base < n; base += 1024) {
-    const int b = base + threadIdx.x;
-    const int own = b < n ? unmatched[b] : 0;
+  for (int base = 0; base < n; base += 8192) {
+    const int b = base + threadIdx.x * 8;
+    int v[8];
+    if (b + 7 < n) {
+      const int4 lo = *reinterpret_cast<const int4*>(unmatched + b), hi = *reinterpret_cast<const int4*>(unmatched + b + 4);
+      v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = b + k < n ? unmatched[b + k] : 0;
+    }
+    int own = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) own += v[k];
     int tot = 0;
-    const int ex = vl_block_excl_scan<1024>(own, ws, &tot);
-    if (b < n) unmatched[b] = carry + ex;
+    int run = carry + vl_block_excl_scan<1024>(own, ws, &tot);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const int t = v[k]; v[k] = run; run += t; }
+    if (b + 7 < n) {
+      *reinterpret_cast<int4*>(unmatched + b) = make_int4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<int4*>(unmatched + b + 4) = make_int4(v[4], v[5], v[6], v[7]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) if (b + k < n) unmatched[b + k] = v[k];
+    }
     carry += tot;
   }
   if (threadIdx.x == 0) unmatched[n] = carry;
@@ -975,14 +1054,12 @@ __device__ __forceinline__ float4 rf_centroid(const float4 acc, int n) {
 }
 
 // new voxels: runs of tail keys that no prefix point owns
-__global__ void __launch_bounds__(256) rf_emit_new(const unsigned long long* __restrict__ keys, const int* __restrict__ uScan,
-                                                   const LmScalars* __restrict__ s, const RfWork* __restrict__ w, vloam_b200_params prm,
-                                                   const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts,
-                                                   const float4* __restrict__ poolC, const float4* __restrict__ poolS,
-                                                   const float4* __restrict__ newPts, float4* __restrict__ staging) {
-  VL_PDL_WAIT();
-
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void rf_dev_emit_new(int blk, const unsigned long long* __restrict__ keys, const int* __restrict__ uScan,
+                                                const LmScalars* __restrict__ s, const RfWork* __restrict__ w, const vloam_b200_params& prm,
+                                                const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts,
+                                                const float4* __restrict__ poolC, const float4* __restrict__ poolS,
+                                                const float4* __restrict__ newPts, float4* __restrict__ staging) {
+  const int t = blk * blockDim.x + threadIdx.x;
   const int n = w->nKeysValid;
   if (t >= n) return;
   if (uScan[t + 1] == uScan[t]) return;  // not an unmatched head
@@ -1003,15 +1080,13 @@ __global__ void __launch_bounds__(256) rf_emit_new(const unsigned long long* __r
 }
 
 // prefix points: shifted by the new voxels that sort before them; absorb a matching tail run
-__global__ void __launch_bounds__(256) rf_emit_prefix(const unsigned long long* __restrict__ keys, const int* __restrict__ uScan,
-                                                      const LmScalars* __restrict__ s, const RfWork* __restrict__ w, vloam_b200_params prm,
-                                                      const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts,
-                                                      const float4* __restrict__ poolC, const float4* __restrict__ poolS,
-                                                      const float4* __restrict__ newPts, float4* __restrict__ staging) {
-  VL_PDL_WAIT();
-
+__device__ __forceinline__ void rf_dev_emit_prefix(int blk, int nblk, const unsigned long long* __restrict__ keys, const int* __restrict__ uScan,
+                                                   const LmScalars* __restrict__ s, const RfWork* __restrict__ w, const vloam_b200_params& prm,
+                                                   const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts,
+                                                   const float4* __restrict__ poolC, const float4* __restrict__ poolS,
+                                                   const float4* __restrict__ newPts, float4* __restrict__ staging) {
   const int total = w->prefOff[LM_NSEG];
-  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
+  for (int g = blk * blockDim.x + threadIdx.x; g < total; g += nblk * blockDim.x) {
     int lo = 0, hi = LM_NSEG;
     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (w->prefOff[mid] <= g) lo = mid; else hi = mid; }
     const int sg = lo, i = g - w->prefOff[sg];
@@ -1027,6 +1102,19 @@ __global__ void __launch_bounds__(256) rf_emit_prefix(const unsigned long long* 
     for (int q = a; q < segEnd && RF_VOX(keys[q]) == vk; ++q) { acc = rf_fold(acc, rf_key_point(keys[q], s, tc, ts, poolC, poolS, newPts)); ++cnt; }
     staging[w->outOff[sg] + i + (uScan[a] - uScan[segBegin])] = rf_centroid(acc, cnt);
   }
+}
+
+// Both emitters in one launch: they write disjoint staging entries and neither reads what the other writes, so the
+// first nbNew blocks handle the new voxels (a few long per-run loops) while the rest stream the prefix points.
+__global__ void __launch_bounds__(256) rf_emit(int nbNew, const unsigned long long* __restrict__ keys, const int* __restrict__ uScan,
+                                               const LmScalars* __restrict__ s, const RfWork* __restrict__ w, vloam_b200_params prm,
+                                               const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts,
+                                               const float4* __restrict__ poolC, const float4* __restrict__ poolS,
+                                               const float4* __restrict__ newPts, float4* __restrict__ staging) {
+  VL_PDL_WAIT();
+
+  if ((int)blockIdx.x < nbNew) rf_dev_emit_new(blockIdx.x, keys, uScan, s, w, prm, tc, ts, poolC, poolS, newPts, staging);
+  else rf_dev_emit_prefix(blockIdx.x - nbNew, gridDim.x - nbNew, keys, uScan, s, w, prm, tc, ts, poolC, poolS, newPts, staging);
 }
 
 // grow cube storage where the re-filtered cloud no longer fits (bump allocation from the pool top;
@@ -1212,7 +1300,8 @@ struct LmDevice {  // extra device state owned by this file
   int* cellCount;   // 2*LM_NCELL + 1 (scan output in place: cellStart)
   int* cellStart;
   int* cellFill;
-  int* tileSum;
+  int* tileSum;  // in-line (cooperative) build only
+  VlScan scan;   // speculative build: single-launch scan
   DBuf<int> cellOfPoint;
   DBuf<float4> sortedPts;
   DBuf<float4> newPts; DBuf<int> newCube;
@@ -1236,6 +1325,7 @@ int vl_lm_init(vloam_b200_ctx* c) {
   VL_CUDA(cudaMalloc(&d->cellStart, sizeof(int) * (2 * LM_NCELL + 1)));
   VL_CUDA(cudaMalloc(&d->cellFill, sizeof(int) * (2 * LM_NCELL + 1)));
   VL_CUDA(cudaMalloc(&d->tileSum, sizeof(int) * (vl_div_up(2 * LM_NCELL, 1024) + 1)));
+  VL_TRY(vl_scan_alloc(&d->scan, 2 * LM_NCELL));
   VL_CUDA(cudaMalloc(&d->dQ, sizeof(int) * 2));
   VL_CUDA(cudaMalloc(&d->subReal, sizeof(LmSub))); VL_CUDA(cudaMemset(d->subReal, 0, sizeof(LmSub)));
   VL_CUDA(cudaMalloc(&d->subSpec, sizeof(LmSub))); VL_CUDA(cudaMemset(d->subSpec, 0, sizeof(LmSub)));
@@ -1276,6 +1366,7 @@ void vl_lm_free(vloam_b200_ctx* c) {  // everything vl_lm_init and this file's r
   void* dev[] = {d->work, d->cellCount, d->cellStart, d->cellFill, d->tileSum, d->dQ, d->subReal, d->subSpec, d->specOK,
                  d->cellOfPoint.p, d->sortedPts.p, d->newPts.p, d->newCube.p, d->unmatched.p};
   for (void* p : dev) if (p) cudaFree(p);
+  vl_scan_free(&d->scan);
   delete d;
   c->gridPrm = nullptr;
 }
@@ -1285,27 +1376,37 @@ extern bool vl_debug_capture(const vloam_b200_ctx* c);
 // LM.cpp:492-500: VoxelGrid of this frame's less-sharp / less-flat clouds.  They depend on scan
 // registration only, so the odometry stage enqueues them on the side stream right after its first sync
 // point and they run underneath the odometry kernels; solveMapping waits on evStacks.
-int vl_lm_enqueue_stacks(vloam_b200_ctx* c, const float4* corner, int nc, const float4* surf, int ns) {
+// The filters only conflict with the previous map update through rf_keys, the one kernel that reads the previous
+// stacks (evKeys), not with the rest of the update or the speculative sub-map behind it.
+// early = true (the counts were known when the sweep arrived: look-ahead scan registration): the helper thread
+// issues the ~14 launches while the caller queues the odometry, so the stacks are ready well before the mapping
+// front needs them; whoever needs evStacks joins the helper first (vl_lm_run does).
+static int lm_issue_stacks(vloam_b200_ctx* c, const float4* corner, int nc, const float4* surf, int ns) {
   LmDevice* d = lmdev(c);
-  VL_TRY(vl_lm_join(c));  // evMap of the previous frame must have been recorded before it is waited on below
-  cudaStream_t main = c->stream;
+  struct Restore { cudaStream_t prev; ~Restore() { vl_tls_stream = prev; } } restore{vl_tls_stream};
   // surf filter on stream2 (scratch lane 0), corner filter beside it on stream4 (scratch lane 1)
-  c->stream = c->stream2;
-  cudaStreamWaitEvent(c->stream2, c->evMap, 0);  // the previous frame's map update still reads the previous stacks
+  vl_tls_stream = c->stream2;
+  cudaStreamWaitEvent(c->stream2, c->evKeys, 0);
   int r = vl_reserve(c, c->stackS, (size_t)max(ns, 1));
   if (r == VLOAM_OK) r = vl_voxel_grid_device(c, surf, ns, nullptr, c->prm.plane_res, c->stackS.p, d->dQ + 1, 0);
   if (c->timing) cudaEventRecord(c->evx[3], c->stream2);
-  c->stream = c->stream4;
-  cudaStreamWaitEvent(c->stream4, c->evMap, 0);
+  vl_tls_stream = c->stream4;
+  cudaStreamWaitEvent(c->stream4, c->evKeys, 0);
   if (r == VLOAM_OK) r = vl_reserve(c, c->stackC, (size_t)max(nc, 1));
   if (r == VLOAM_OK) r = vl_voxel_grid_device(c, corner, nc, nullptr, c->prm.line_res, c->stackC.p, d->dQ, 1);
   if (c->timing) cudaEventRecord(c->evx[4], c->stream4);
-  c->stream = main;
   if (r != VLOAM_OK) return r;
   VL_CUDA(cudaEventRecord(c->evStacks, c->stream2));
   VL_CUDA(cudaEventRecord(c->evStacksC, c->stream4));
   c->stacksReady = true;
   return VLOAM_OK;
+}
+int vl_lm_enqueue_stacks(vloam_b200_ctx* c, const float4* corner, int nc, const float4* surf, int ns, bool early) {
+  VL_TRY(vl_lm_join(c));  // evKeys of the previous frame's update must have been recorded before it is waited on
+  static const bool noWorker = getenv("VLOAM_NO_WORKER") != nullptr;
+  if (early && !noWorker && !c->prof_name[0] && !vl_debug_capture(c))
+    return lm_submit(c, [=]() -> int { return lm_issue_stacks(c, corner, nc, surf, ns); });
+  return lm_issue_stacks(c, corner, nc, surf, ns);
 }
 
 // in-line sub-map build of this frame (one cooperative launch; returns at once on the device when *specOK)
@@ -1449,18 +1550,16 @@ int vl_lm_run(vloam_b200_ctx* c) {
     VL_TRY(vl_reserve(c, c->staging, (size_t)Mc + Ms + nKeys + 1, false, (size_t)(Mc + Ms) / 2 + (1 << 20)));
     VL_LAUNCH(rf_keys, vl_div_up(nKeys, 256), 256, 0, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, c->stackC.p, c->stackS.p,
               d->newPts.p, d->newCube.p, keysIn, nKeys);
-    VL_LAUNCH(rf_seg_scan, 1, 256, 0, d->work);
+    VL_CUDA(cudaEventRecord(c->evKeys, c->stream3));  // nothing below reads the stacks any more: the next sweep's filters may overwrite them
     VL_LAUNCH(rf_seg_scatter, vl_div_up(nKeys, 256), 256, 0, keysIn, nKeys, d->work, keysSorted);
     VL_BYTES(16.0 * nKeys);
     static const int segCap = getenv("VLOAM_SEG_CAP") ? max(8, min(atoi(getenv("VLOAM_SEG_CAP")), RF_SEG_CAP)) : RF_SEG_CAP;  // tests force the global path
     VL_LAUNCH(rf_seg_sort, LM_NSEG, RF_SEG_THREADS, (size_t)RF_SEG_CAP * 8, keysSorted, d->work, c->tailKeys.p + 2 * N, segCap);
     VL_LAUNCH(rf_match, vl_div_up(nKeys, 256), 256, 0, keysSorted, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, d->unmatched.p);
     VL_LAUNCH(rf_scan_layout, 1, 1024, 0, d->unmatched.p, c->lmm, d->work, c->cubeC, c->cubeS);
-    VL_LAUNCH(rf_emit_new, vl_div_up(nKeys, 256), 256, 0, keysSorted, d->unmatched.p, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p,
-              c->poolS.p, d->newPts.p, c->staging.p);
     VL_BYTES(32.0 * (Mc + Ms));  // read every prefix point once, write it once to staging
-    VL_LAUNCH(rf_emit_prefix, gsGrid, 256, 0, keysSorted, d->unmatched.p, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p,
-              d->newPts.p, c->staging.p);
+    VL_LAUNCH(rf_emit, vl_div_up(nKeys, 256) + gsGrid, 256, 0, vl_div_up(nKeys, 256), keysSorted, d->unmatched.p, c->lmm, d->work, c->prm, c->cubeC,
+              c->cubeS, c->poolC.p, c->poolS.p, d->newPts.p, c->staging.p);
     VL_LAUNCH(rf_alloc, 1, 256, 0, c->lmm, d->work, c->cubeC, c->cubeS, (int)c->poolC.cap, (int)c->poolS.cap);
     VL_BYTES(32.0 * (Mc + Ms + nq));  // staging -> pool copy
     VL_LAUNCH(rf_commit, gsGrid, 256, 0, c->staging.p, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p);
@@ -1497,7 +1596,7 @@ int vl_lm_run(vloam_b200_ctx* c) {
     VL_BYTES(56.0 * (double)tb);
     VL_LAUNCH(lm_gather_count, gsGrid, 256, 0, d->subSpec, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, c->fromMapC.p, c->fromMapS.p, d->cellCount,
               d->cellOfPoint.p);
-    VL_TRY(vl_scan_exclusive(c, d->cellCount, 2 * LM_NCELL, d->tileSum, d->cellStart, nullptr));
+    VL_TRY(vl_scan_exclusive(c, d->cellCount, 2 * LM_NCELL, &d->scan, d->cellStart, nullptr));
     VL_BYTES(44.0 * (double)tb);
     VL_LAUNCH(lm_grid_fill, gsGrid, 256, 0, d->subSpec, (const int*)nullptr, c->fromMapC.p, c->fromMapS.p, d->cellOfPoint.p, d->cellStart, d->cellFill,
               d->sortedPts.p);
@@ -1612,22 +1711,18 @@ int vl_lm_preload(vloam_b200_ctx* c) {  // see vl_sr_set_attrs: load every kerne
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_spec_prepare));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_grid_zero));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_gather_count));
-  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_scan_tiles));
-  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_scan_sums));
-  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_scan_apply));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_scan_chained));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_grid_fill));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_inline_build));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_knn));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_fit));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_transform_update));
   VL_CUDA(cudaFuncGetAttributes(&fa_, rf_keys));
-  VL_CUDA(cudaFuncGetAttributes(&fa_, rf_seg_scan));
   VL_CUDA(cudaFuncGetAttributes(&fa_, rf_seg_scatter));
   VL_CUDA(cudaFuncGetAttributes(&fa_, rf_seg_sort));
   VL_CUDA(cudaFuncGetAttributes(&fa_, rf_match));
   VL_CUDA(cudaFuncGetAttributes(&fa_, rf_scan_layout));
-  VL_CUDA(cudaFuncGetAttributes(&fa_, rf_emit_new));
-  VL_CUDA(cudaFuncGetAttributes(&fa_, rf_emit_prefix));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, rf_emit));
   VL_CUDA(cudaFuncGetAttributes(&fa_, rf_alloc));
   VL_CUDA(cudaFuncGetAttributes(&fa_, rf_commit));
   VL_CUDA(cudaFuncGetAttributes(&fa_, rf_finish));

@@ -253,6 +253,7 @@ __global__ void __launch_bounds__(LO_QPB * 32) lo_assoc(const float4* __restrict
 #define LOG_NY 256
 #define LOG_NZ 32
 #define LOG_NCELL (LOG_NX * LOG_NY * LOG_NZ)
+#define LOG_STRIDE (2 * LOG_NCELL + 4)  // ints per cell array (counts / starts / fill), a multiple of 4: 128-bit access in the scan
 #define LOG_INV 0.78125f     // 1 / 1.28
 #define LOG_NEAR1 1.5625f    // (1.25 m)^2 < cell^2: a minimum below this found in the 3x3x3 block is global
 #define LOG_NEAR2 6.25f      // (2.5 m)^2 < (2 cells)^2: same for the 5x5x5 block; the 9x9x9 block covers the 5 m gate
@@ -514,15 +515,16 @@ int vl_lo_build_last(vloam_b200_ctx* c, int set, const float4* corner, int nc, c
   VL_LAUNCH(lo_ring_table, dim3(vl_div_up(max(max(nc, ns), LO_TBL + 1), 256), 2), 256, 0, corner, nc, surf, ns, tbl);
   VL_CUDA(cudaMemcpyAsync(&c->h_vScalars[8 + 2 * set], tbl + LO_TBL, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   VL_CUDA(cudaMemcpyAsync(&c->h_vScalars[9 + 2 * set], tbl + (LO_TBL + 1) + LO_TBL, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  VL_TRY(vl_reserve(c, c->loGridCells[set], (size_t)3 * (2 * LOG_NCELL + 1) + (2 * LOG_NCELL) / 1024 + 8));  // counts, starts, fill, tile sums
+  VL_TRY(vl_reserve(c, c->loGridCells[set], (size_t)3 * LOG_STRIDE));  // counts, starts, fill (16-byte aligned each)
+  VL_TRY(vl_scan_alloc(&c->loScan[set], 2 * LOG_NCELL));
   VL_TRY(vl_reserve(c, c->loGridCellOf, (size_t)max(n, 1), false, (size_t)n / 2));
   VL_TRY(vl_reserve(c, c->loGridSorted[set], (size_t)max(n, 1), false, (size_t)n / 2));
   if (n > 0 && n < (1 << 24)) {
-    int* cnt = c->loGridCells[set].p; int* start = cnt + (2 * LOG_NCELL + 1); int* fill = start + (2 * LOG_NCELL + 1);
+    int* cnt = c->loGridCells[set].p; int* start = cnt + LOG_STRIDE; int* fill = start + LOG_STRIDE;
     VL_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * (2 * LOG_NCELL + 1), c->stream));
     VL_CUDA(cudaMemsetAsync(fill, 0, sizeof(int) * (2 * LOG_NCELL + 1), c->stream));
     VL_LAUNCH(lo_grid_count, vl_div_up(n, 256), 256, 0, corner, nc, surf, ns, cnt, c->loGridCellOf.p);
-    VL_TRY(vl_scan_exclusive(c, cnt, 2 * LOG_NCELL, fill + (2 * LOG_NCELL + 1), start));
+    VL_TRY(vl_scan_exclusive(c, cnt, 2 * LOG_NCELL, &c->loScan[set], start));
     VL_LAUNCH(lo_grid_fill, vl_div_up(n, 256), 256, 0, corner, nc, surf, ns, c->loGridCellOf.p, start, fill, c->loGridSorted[set].p);
     c->loGridValid[set] = true;
   } else c->loGridValid[set] = false;
@@ -543,7 +545,7 @@ static int lo_associate(vloam_b200_ctx* c, const double* d_pose, const float4* c
   // h_vScalars[8/9]: int(intensity) of the corner / surf cloud is non-decreasing (read after a sync point)
   const int set = c->lastSet;
   const bool gridC = c->loGridValid[set] && c->h_vScalars[8 + 2 * set] != 0, gridS = c->loGridValid[set] && c->h_vScalars[9 + 2 * set] != 0;
-  const int* start = c->loGridCells[set].p ? c->loGridCells[set].p + (2 * LOG_NCELL + 1) : nullptr;
+  const int* start = c->loGridCells[set].p ? c->loGridCells[set].p + LOG_STRIDE : nullptr;
   const float4* gsorted = c->loGridSorted[set].p;
   const int* rtbl = c->loRingTbl + set * 2 * (LO_TBL + 1);
   if (gridC && gridS && nS + nF > 0) {
@@ -609,6 +611,15 @@ int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, i
   const int set = c->lastSet;
   const bool early = c->loGridValid[set] && c->h_vScalars[8 + 2 * set] != 0 && c->h_vScalars[9 + 2 * set] != 0 && !vl_debug_capture(c);
   if (!early) VL_TRY(vl_sr_sync_counts(c));
+  // Scan registration already complete when the sweep arrived (look-ahead): sync point S1 is free, and the stack
+  // filters of this sweep go to the helper thread now instead of behind the odometry launches.
+  const bool mapThisFrame = ((c->lo_frameCount + 1) % c->prm.mapping_skip_frame) == 0;  // LO.cpp:668
+  bool stacksQueued = false;
+  if (early && mapThisFrame && cudaEventQuery(c->evSR) == cudaSuccess) {
+    VL_TRY(vl_sr_sync_counts(c));
+    VL_TRY(vl_lm_enqueue_stacks(c, c->lessSharp[c->cur].p, c->nLessSharp, c->lessFlat[c->cur].p, c->nLessFlat, true));
+    stacksQueued = true;
+  }
   double* d_pose = c->los->para_q;  // para_q[4] + para_t[3] are contiguous
   if (c->lo_inited) {  // LO.cpp:209-217: the first frame only initialises
     const float4* cornerLast = c->cornerLastPtr; const float4* surfLast = c->surfLastPtr;
@@ -635,7 +646,7 @@ int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, i
   VL_TRY(vl_launch_lookahead(c));  // the next sweep's scan registration, if one is registered, goes to its side stream now
   VL_HOST_MARK(2);
   VL_TRY(vl_sr_sync_counts(c));  // sync point S1 (event after scan registration; the odometry above is already queued)
-  if (((c->lo_frameCount + 1) % c->prm.mapping_skip_frame) == 0)  // mapping will run on this frame (LO.cpp:668)
+  if (mapThisFrame && !stacksQueued)
     VL_TRY(vl_lm_enqueue_stacks(c, c->lessSharp[c->cur].p, c->nLessSharp, c->lessFlat[c->cur].p, c->nLessFlat));
   {  // LO.cpp:573-574 (setInputCloud on both KD-trees) for the clouds that become "last" after this solve:
      // they are this frame's less-sharp / less-flat clouds, final since scan registration, so the side

@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(VG_BLOCK) vg_centroid(const float4* __restrict
 }
 
 int vl_voxel_grid_device(vloam_b200_ctx* c, const float4* d_in, int n, const int* d_n, float leaf, float4* d_out, int* d_count, int lane) {
-  if (n <= 0) { VL_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), c->stream)); return VLOAM_OK; }
+  if (n <= 0) { VL_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), VL_STREAM(c))); return VLOAM_OK; }
   int P = 2; while (P < n) P <<= 1;
   const int nb = min(vl_div_up(n, VG_BLOCK), 256);
   const int nTiles = vl_div_up(n, 1024);
