@@ -80,14 +80,17 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   // VLOAM_NO_PRIORITIES=1: all streams at the default priority.
   int prLow = 0, prHigh = 0;
   VL_CUDA_CREATE(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
-  if (getenv("VLOAM_NO_PRIORITIES")) prHigh = prLow;
-  const int prMid = prHigh < prLow ? prHigh + 1 : prLow;
-  VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prHigh));
-  VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prMid));
-  VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, prLow));
-  VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->stream4, cudaStreamNonBlocking, prMid));
+  int lv[4] = {2, 1, 0, 0};  // levels above the lowest priority: main | stack filters | map update | look-ahead scan registration
+  if (const char* e = getenv("VLOAM_PRIO")) sscanf(e, "%d,%d,%d,%d", &lv[0], &lv[1], &lv[2], &lv[3]);
+  if (getenv("VLOAM_NO_PRIORITIES")) lv[0] = lv[1] = lv[2] = lv[3] = 0;
+  int pr[4];
+  for (int k = 0; k < 4; ++k) pr[k] = max(prLow - lv[k], prHigh);  // (numerically lower = more urgent)
+  VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, pr[0]));
+  VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, pr[1]));
+  VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, pr[2]));
+  VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->stream4, cudaStreamNonBlocking, pr[1]));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evStacksC, cudaEventDisableTiming));
-  VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->streamAux, cudaStreamNonBlocking, prLow));
+  VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->streamAux, cudaStreamNonBlocking, pr[2]));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evAux, cudaEventDisableTiming));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evAuxZero, cudaEventDisableTiming));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evUpd, cudaEventDisableTiming));
@@ -104,8 +107,11 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   vl_sr_swap(c, *c->srNext);      // the spare set gets its own fixed-size arrays, counters and event
   { const int r_ = alloc_sr_fixed(c); vl_sr_swap(c, *c->srNext); if (r_ != VLOAM_OK) return r_; }
   c->srNextKey = nullptr; c->srNextValid = false; c->srPendKey = nullptr; c->srPendDevice = false;
-  VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->streamSR, cudaStreamNonBlocking, prLow));
+  VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->streamSR, cudaStreamNonBlocking, pr[3]));
   VL_CUDA_CREATE(cudaMalloc(&c->los, sizeof(LoScalars)));
+  VL_CUDA_CREATE(cudaMalloc(&c->losNext, sizeof(LoScalars)));
+  VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evS2, cudaEventDisableTiming));
+  c->loNextValid = c->srAdopted = c->s2Done = false;
   VL_CUDA_CREATE(cudaMallocHost(&c->h_los, sizeof(LoScalars)));
   LoScalars hl; memset(&hl, 0, sizeof hl); hl.para_q[3] = 1.0; hl.q_w[3] = 1.0;  // LO.cpp:81-91
   VL_CUDA_CREATE(cudaMemcpy(c->los, &hl, sizeof hl, cudaMemcpyHostToDevice));
@@ -150,7 +156,8 @@ void vloam_b200_destroy(vloam_b200_ctx* c) {
   cudaStreamDestroy(c->streamSR);
   vl_lm_free(c);
   vl_scan_free(&c->loScan[0]); vl_scan_free(&c->loScan[1]);
-  void* singles[] = {c->los, c->evalOut, c->lms, c->lmm, c->cubeC, c->cubeS, c->vScalars, c->loRingTbl, c->loGridCells[0].p, c->loGridCells[1].p,
+  cudaEventDestroy(c->evS2);
+  void* singles[] = {c->los, c->losNext, c->evalOut, c->lms, c->lmm, c->cubeC, c->cubeS, c->vScalars, c->loRingTbl, c->loGridCells[0].p, c->loGridCells[1].p,
                      c->loGridCellOf.p, c->loGridSorted[0].p, c->loGridSorted[1].p, c->dbgLoCorner[0].p, c->dbgLoCorner[1].p, c->dbgLoSurf[0].p,
                      c->dbgLoSurf[1].p, c->dbgKnnIdx[0][0].p, c->dbgKnnIdx[0][1].p, c->dbgKnnIdx[1][0].p, c->dbgKnnIdx[1][1].p, c->dbgKnnD2[0][0].p,
                      c->dbgKnnD2[0][1].p, c->dbgKnnD2[1][0].p, c->dbgKnnD2[1][1].p, c->dbgKnnOk[0][0].p, c->dbgKnnOk[0][1].p, c->dbgKnnOk[1][0].p,
@@ -231,7 +238,9 @@ static bool adopt_lookahead(vloam_b200_ctx* c, const float* key, int n, int stri
 int vloam_b200_scan_registration_device(vloam_b200_ctx* c, const float* d_xyz, int n, int stride) {
   if (n < 0 || stride < 3) { snprintf(c->err, sizeof c->err, "bad cloud shape"); return VLOAM_E_INVALID; }
   if (c->timing) VL_CUDA(cudaEventRecord(c->ev[0], c->stream));
-  if (!adopt_lookahead(c, d_xyz, n, stride)) {
+  c->srAdopted = adopt_lookahead(c, d_xyz, n, stride);
+  if (!c->srAdopted) {
+    c->loNextValid = false;
     c->srNextValid = false;  // a look-ahead result for another sweep targets the generation this run is about to write
     VL_TRY(vl_sr_run(c, d_xyz, n, stride));
   }
@@ -242,7 +251,9 @@ int vloam_b200_scan_registration_device(vloam_b200_ctx* c, const float* d_xyz, i
 int vloam_b200_scan_registration(vloam_b200_ctx* c, const float* xyz, int n, int stride) {
   if (n < 0 || stride < 3 || (n > 0 && !xyz)) { snprintf(c->err, sizeof c->err, "bad cloud shape"); return VLOAM_E_INVALID; }
   if (c->timing) VL_CUDA(cudaEventRecord(c->ev[0], c->stream));
-  if (!adopt_lookahead(c, xyz, n, stride)) {
+  c->srAdopted = adopt_lookahead(c, xyz, n, stride);
+  if (!c->srAdopted) {
+    c->loNextValid = false;
     c->srNextValid = false;
     VL_TRY(vl_reserve(c, c->in, (size_t)max(n, 1) * stride));
     if (n > 0) VL_CUDA(cudaMemcpyAsync(c->in.p, xyz, (size_t)n * stride * sizeof(float), cudaMemcpyHostToDevice, c->stream));
@@ -321,11 +332,14 @@ static int process_common(vloam_b200_ctx* c, double* pose_out) {
   VL_HOST_MARK(1);
   VL_TRY(vloam_b200_laser_odometry(c, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr));
   if (pose_out) {
+    c->s2Done = false;
     VL_TRY(vl_lm_run(c));
     if (c->timing) VL_CUDA(cudaEventRecord(c->ev[3], c->stream));
-    VL_CUDA(cudaMemcpyAsync(c->h_los, c->los, sizeof(LoScalars), cudaMemcpyDeviceToHost, c->stream));
-    VL_CUDA(cudaMemcpyAsync(c->h_lmm, c->lmm, sizeof(LmScalars), cudaMemcpyDeviceToHost, c->stream));
-    VL_CUDA(cudaStreamSynchronize(c->stream));
+    if (!c->s2Done) {  // (mapping skipped on this frame) -- otherwise sync point S2 already brought both structs over
+      VL_CUDA(cudaMemcpyAsync(c->h_los, c->los, sizeof(LoScalars), cudaMemcpyDeviceToHost, c->stream));
+      VL_CUDA(cudaMemcpyAsync(c->h_lmm, c->lmm, sizeof(LmScalars), cudaMemcpyDeviceToHost, c->stream));
+      VL_CUDA(cudaStreamSynchronize(c->stream));
+    }
     if (c->h_lmm->overflow) { snprintf(c->err, sizeof c->err, "map pool exhausted"); return VLOAM_E_CAPACITY; }
     memcpy(pose_out, c->h_los->q_w, 32); memcpy(pose_out + 4, c->h_los->t_w, 24);
     memcpy(pose_out + 7, c->skip_frame ? c->h_lmm->q_hf : c->h_lmm->pose, 32);
@@ -535,6 +549,7 @@ long vloam_b200_debug_get(vloam_b200_ctx* c, const char* name, void* out, long c
 int vloam_b200_debug_set(vloam_b200_ctx* c, const char* name, const void* data, long bytes) {
   const std::string n(name);
   VL_TRY(vloam_b200_synchronize(c));
+  c->loNextValid = false;  // whatever is set below may change what the next odometry solve starts from
   if (n == "debug.capture") { c->h_vScalars[0] = (bytes >= 4 && *(const int*)data) ? 1 : 0; return VLOAM_OK; }
   if (n == "lo.last") {  // blob: int nc, int ns, corner points, surf points  (the state solveLO swaps in, LO.cpp:558-574)
     const int* hdr = (const int*)data;

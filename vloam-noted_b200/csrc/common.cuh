@@ -159,6 +159,9 @@ struct vloam_b200_ctx {
 
   // ---- laser odometry
   LoScalars* los; LoScalars* h_los;
+  LoScalars* losNext;         // odometry state after the look-ahead odometry of sweep srNextKey (valid when loNextValid)
+  bool loNextValid, srAdopted, s2Done;
+  cudaEvent_t evS2;           // sync point S2 (pose + sizes copied to the host)
   int nCornerLast, nSurfLast;  // host counts of the "last" clouds (= other buffer of the pair)
   bool lo_inited; int lo_frameCount;
   float4* cornerLastPtr; float4* surfLastPtr;  // after solveLO's swap
@@ -322,6 +325,7 @@ int vl_sr_set_attrs(vloam_b200_ctx* c);
 int vl_sort_set_attrs(vloam_b200_ctx* c);
 int vl_solver_set_attrs(vloam_b200_ctx* c);
 int vl_lo_preload(vloam_b200_ctx* c);
+int vl_lo_lookahead(vloam_b200_ctx* c);  // queue the NEXT sweep's odometry solve behind this sweep's mapping (no-op unless its scan registration is in flight)
 int vl_vg_preload(vloam_b200_ctx* c);
 int vl_lm_preload(vloam_b200_ctx* c);
 int vl_lm_register_full(vloam_b200_ctx* c, const float4* d_in, int n, float4* d_out);

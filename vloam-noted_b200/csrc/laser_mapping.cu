@@ -1504,9 +1504,15 @@ int vl_lm_run(vloam_b200_ctx* c) {
   // read the pose, and the next frame's scan registration + odometry can start, while the map is brought up to date.
   VL_CUDA(cudaEventRecord(c->evPose, c->stream));
   // ---- sync point S2: sizes for the map update (and the pose, which is final now)
+  VL_CUDA(cudaMemcpyAsync(c->h_los, c->los, sizeof(LoScalars), cudaMemcpyDeviceToHost, c->stream));
   VL_CUDA(cudaMemcpyAsync(c->h_lmm, c->lmm, sizeof(LmScalars), cudaMemcpyDeviceToHost, c->stream));
+  VL_CUDA(cudaEventRecord(c->evS2, c->stream));
   VL_HOST_MARK(5);
-  VL_CUDA(cudaStreamSynchronize(c->stream));
+  // While the device finishes this sweep's mapping, the next sweep's odometry solve is queued behind it (replays with a
+  // registered look-ahead sweep): the device then runs on without the S2 -> caller -> next call round trip (~40 us).
+  if (!capture) VL_TRY(vl_lo_lookahead(c));
+  VL_CUDA(cudaEventSynchronize(c->evS2));
+  c->s2Done = true;
   VL_HOST_MARK(6);
   const int Mc = c->h_lmm->Mc, Ms = c->h_lmm->Ms;
   Qc = c->h_lmm->Qc; Qs = c->h_lmm->Qs;

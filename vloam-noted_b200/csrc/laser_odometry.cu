@@ -603,25 +603,10 @@ int vl_lo_trace(vloam_b200_ctx* c, int* out, int n) {
   return VLOAM_OK;
 }
 
-int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, int use_prior) {
-  VL_CUDA(cudaEventSynchronize(c->evLast));  // set [lastSet] (built underneath the previous frame) and its flags are complete
-  // The grid kernels read the query counts on the device, so the odometry can be queued before the host
-  // has them (sync point S1 then costs no GPU idle time).  The ballot fallback and the debug snapshots
-  // need host counts first.
-  const int set = c->lastSet;
-  const bool early = c->loGridValid[set] && c->h_vScalars[8 + 2 * set] != 0 && c->h_vScalars[9 + 2 * set] != 0 && !vl_debug_capture(c);
-  if (!early) VL_TRY(vl_sr_sync_counts(c));
-  // Scan registration already complete when the sweep arrived (look-ahead): sync point S1 is free, and the stack
-  // filters of this sweep go to the helper thread now instead of behind the odometry launches.
-  const bool mapThisFrame = ((c->lo_frameCount + 1) % c->prm.mapping_skip_frame) == 0;  // LO.cpp:668
-  bool stacksQueued = false;
-  if (early && mapThisFrame && cudaEventQuery(c->evSR) == cudaSuccess) {
-    VL_TRY(vl_sr_sync_counts(c));
-    VL_TRY(vl_lm_enqueue_stacks(c, c->lessSharp[c->cur].p, c->nLessSharp, c->lessFlat[c->cur].p, c->nLessFlat, true));
-    stacksQueued = true;
-  }
+// The two association + solve passes (LO.cpp:224-553) and the pose accumulation, queued on the current stream against
+// the context's current scan-registration set and odometry state (c->los).
+static int lo_queue_solve(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, int use_prior) {
   double* d_pose = c->los->para_q;  // para_q[4] + para_t[3] are contiguous
-  if (c->lo_inited) {  // LO.cpp:209-217: the first frame only initialises
     const float4* cornerLast = c->cornerLastPtr; const float4* surfLast = c->surfLastPtr;
     double* d_prior = reinterpret_cast<double*>(c->vScalars + 32);  // 8-byte aligned scratch (7 doubles)
     if (use_prior) {
@@ -642,7 +627,61 @@ int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, i
       VL_TRY(vl_solve(c, nslots, &c->srs->nQueries, d_pose, vl_debug_capture(c) ? &c->dbgLoCost[pass * 2] : nullptr, c->nSharp + c->nFlat));
     }
     VL_LAUNCH(lo_accumulate, 1, 32, 0, c->los);
+  return VLOAM_OK;
+}
+
+// Look-ahead odometry.  Called by the mapping stage just before it waits at sync point S2: when the next sweep's scan
+// registration is already in flight (vl_launch_lookahead), its odometry solve depends on nothing the host still has to
+// decide -- the "last" clouds and their search structures are this sweep's (evLast), the counts are read on the
+// device -- so it is queued now, behind this sweep's mapping, on a COPY of the odometry state.  The next
+// laser_odometry call adopts the copy if it is for that sweep and ignores it otherwise.
+int vl_lo_lookahead(vloam_b200_ctx* c) {
+  static const bool off = getenv("VLOAM_NO_LO_LOOKAHEAD") != nullptr;
+  c->loNextValid = false;
+  if (off || !c->srNextValid || !c->lo_inited || c->timing || c->prof_name[0] || vl_debug_capture(c)) return VLOAM_OK;
+  VL_CUDA(cudaEventSynchronize(c->evLast));  // the structures over this sweep's clouds (built on the side stream) and their flags
+  const int set = c->lastSet;
+  if (!(c->loGridValid[set] && c->h_vScalars[8 + 2 * set] != 0 && c->h_vScalars[9 + 2 * set] != 0)) return VLOAM_OK;
+  VL_CUDA(cudaStreamWaitEvent(c->stream, c->srNext->evSR, 0));
+  VL_CUDA(cudaMemcpyAsync(c->losNext, c->los, sizeof(LoScalars), cudaMemcpyDeviceToDevice, c->stream));
+  const int curNow = c->cur;
+  vl_sr_swap(c, *c->srNext);
+  const bool cv = c->sr_counts_valid;
+  c->sr_counts_valid = false;  // the spare set's host counts are those of an older sweep: use the bounds, counts are read on the device
+  { LoScalars* t_ = c->los; c->los = c->losNext; c->losNext = t_; }
+  const int r = lo_queue_solve(c, nullptr, nullptr, 0);
+  { LoScalars* t_ = c->los; c->los = c->losNext; c->losNext = t_; }
+  c->sr_counts_valid = cv;
+  vl_sr_swap(c, *c->srNext);
+  c->cur = curNow;
+  if (r != VLOAM_OK) return r;
+  c->loNextValid = true;
+  return VLOAM_OK;
+}
+
+int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, int use_prior) {
+  VL_CUDA(cudaEventSynchronize(c->evLast));  // set [lastSet] (built underneath the previous frame) and its flags are complete
+  // The grid kernels read the query counts on the device, so the odometry can be queued before the host
+  // has them (sync point S1 then costs no GPU idle time).  The ballot fallback and the debug snapshots
+  // need host counts first.
+  const int set = c->lastSet;
+  const bool early = c->loGridValid[set] && c->h_vScalars[8 + 2 * set] != 0 && c->h_vScalars[9 + 2 * set] != 0 && !vl_debug_capture(c);
+  if (!early) VL_TRY(vl_sr_sync_counts(c));
+  // Scan registration already complete when the sweep arrived (look-ahead): sync point S1 is free, and the stack
+  // filters of this sweep go to the helper thread now instead of behind the odometry launches.
+  const bool mapThisFrame = ((c->lo_frameCount + 1) % c->prm.mapping_skip_frame) == 0;  // LO.cpp:668
+  bool stacksQueued = false;
+  if (early && mapThisFrame && cudaEventQuery(c->evSR) == cudaSuccess) {
+    VL_TRY(vl_sr_sync_counts(c));
+    VL_TRY(vl_lm_enqueue_stacks(c, c->lessSharp[c->cur].p, c->nLessSharp, c->lessFlat[c->cur].p, c->nLessFlat, true));
+    stacksQueued = true;
   }
+  // The solve of this sweep was queued behind the previous sweep's mapping (vl_lo_lookahead) into the spare state:
+  // adopting it is a pointer swap.  Anything that could make it stale clears loNextValid.
+  const bool adoptLO = c->loNextValid && c->srAdopted && !use_prior && !vl_debug_capture(c) && c->lo_inited;
+  c->loNextValid = false;
+  if (adoptLO) { LoScalars* t_ = c->los; c->los = c->losNext; c->losNext = t_; }
+  else if (c->lo_inited) VL_TRY(lo_queue_solve(c, prior_q, prior_t, use_prior));  // LO.cpp:209-217: the first frame only initialises
   VL_TRY(vl_launch_lookahead(c));  // the next sweep's scan registration, if one is registered, goes to its side stream now
   VL_HOST_MARK(2);
   VL_TRY(vl_sr_sync_counts(c));  // sync point S1 (event after scan registration; the odometry above is already queued)
