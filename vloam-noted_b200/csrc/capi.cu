@@ -111,7 +111,7 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   VL_CUDA_CREATE(cudaMalloc(&c->los, sizeof(LoScalars)));
   VL_CUDA_CREATE(cudaMalloc(&c->losNext, sizeof(LoScalars)));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evS2, cudaEventDisableTiming));
-  c->loNextValid = c->srAdopted = c->s2Done = false;
+  c->loNextValid = c->srAdopted = c->s2Done = false; c->loAssumeMonotone = c->inProcessFrame = c->loDeferred = false; c->loNextSet = 0;
   VL_CUDA_CREATE(cudaMallocHost(&c->h_los, sizeof(LoScalars)));
   LoScalars hl; memset(&hl, 0, sizeof hl); hl.para_q[3] = 1.0; hl.q_w[3] = 1.0;  // LO.cpp:81-91
   VL_CUDA_CREATE(cudaMemcpy(c->los, &hl, sizeof hl, cudaMemcpyHostToDevice));
@@ -330,7 +330,10 @@ int vloam_b200_register_full_cloud(vloam_b200_ctx* c, float* out, int cap_points
 
 static int process_common(vloam_b200_ctx* c, double* pose_out) {
   VL_HOST_MARK(1);
-  VL_TRY(vloam_b200_laser_odometry(c, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr));
+  c->inProcessFrame = true;
+  const int rlo = vloam_b200_laser_odometry(c, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+  c->inProcessFrame = false;
+  if (rlo != VLOAM_OK) return rlo;
   if (pose_out) {
     c->s2Done = false;
     VL_TRY(vl_lm_run(c));
@@ -363,6 +366,7 @@ int vloam_b200_process_frame_device(vloam_b200_ctx* c, const float* d_xyz, int n
 }
 
 int vloam_b200_synchronize(vloam_b200_ctx* c) {
+  VL_TRY(vl_lo_flush_deferred(c));
   VL_TRY(vl_lm_join(c));
   VL_CUDA(cudaStreamSynchronize(c->streamSR));
   VL_CUDA(cudaStreamSynchronize(c->streamAux));

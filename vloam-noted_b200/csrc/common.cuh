@@ -161,6 +161,10 @@ struct vloam_b200_ctx {
   LoScalars* los; LoScalars* h_los;
   LoScalars* losNext;         // odometry state after the look-ahead odometry of sweep srNextKey (valid when loNextValid)
   bool loNextValid, srAdopted, s2Done;
+  int loNextSet;              // the "last" set the look-ahead odometry searched (it assumed monotone rings: checked at adoption)
+  bool loAssumeMonotone;      // lo_associate: take the grid path without the host flags (look-ahead only)
+  bool inProcessFrame;        // inside process_frame: mapping follows the odometry in the same call
+  bool loDeferred; int defSet, defNc, defNs; const float4* defCorner; const float4* defSurf;  // side-stream work of the odometry stage queued after the mapping
   cudaEvent_t evS2;           // sync point S2 (pose + sizes copied to the host)
   int nCornerLast, nSurfLast;  // host counts of the "last" clouds (= other buffer of the pair)
   bool lo_inited; int lo_frameCount;
@@ -325,7 +329,8 @@ int vl_sr_set_attrs(vloam_b200_ctx* c);
 int vl_sort_set_attrs(vloam_b200_ctx* c);
 int vl_solver_set_attrs(vloam_b200_ctx* c);
 int vl_lo_preload(vloam_b200_ctx* c);
-int vl_lo_lookahead(vloam_b200_ctx* c);  // queue the NEXT sweep's odometry solve behind this sweep's mapping (no-op unless its scan registration is in flight)
+int vl_lo_lookahead(vloam_b200_ctx* c);
+int vl_lo_flush_deferred(vloam_b200_ctx* c);  // queue the deferred side-stream work of the last odometry call (look-ahead scan registration, next search structures)  // queue the NEXT sweep's odometry solve behind this sweep's mapping (no-op unless its scan registration is in flight)
 int vl_vg_preload(vloam_b200_ctx* c);
 int vl_lm_preload(vloam_b200_ctx* c);
 int vl_lm_register_full(vloam_b200_ctx* c, const float4* d_in, int n, float4* d_out);

@@ -1440,7 +1440,7 @@ int vl_lm_run(vloam_b200_ctx* c) {
   VL_LAUNCH(lm_prepare, 1, 1024, 0, c->lmm, c->los, c->cubeC, c->cubeS, d->work, skip, c->lm_reset_pending ? 1 : 0, d->subReal, d->subSpec,
             d->specQueued ? 1 : 0, d->specOK);
   c->lm_reset_pending = false;
-  if (skip) { VL_CUDA(cudaGetLastError()); return VLOAM_OK; }
+  if (skip) { VL_TRY(vl_lo_flush_deferred(c)); VL_CUDA(cudaGetLastError()); return VLOAM_OK; }
   const int gsGrid = c->num_sms * 8;
   VL_TRY(vl_reserve(c, c->fromMapC, (size_t)max(d->hMapUpperC, 1LL), false, (size_t)d->hMapUpperC / 2 + (1 << 20)));
   VL_TRY(vl_reserve(c, c->fromMapS, (size_t)max(d->hMapUpperS, 1LL), false, (size_t)d->hMapUpperS / 2 + (1 << 20)));
@@ -1510,6 +1510,7 @@ int vl_lm_run(vloam_b200_ctx* c) {
   VL_HOST_MARK(5);
   // While the device finishes this sweep's mapping, the next sweep's odometry solve is queued behind it (replays with a
   // registered look-ahead sweep): the device then runs on without the S2 -> caller -> next call round trip (~40 us).
+  VL_TRY(vl_lo_flush_deferred(c));
   if (!capture) VL_TRY(vl_lo_lookahead(c));
   VL_CUDA(cudaEventSynchronize(c->evS2));
   c->s2Done = true;
@@ -1536,6 +1537,7 @@ int vl_lm_run(vloam_b200_ctx* c) {
   struct Restore { ~Restore() { vl_tls_stream = nullptr; } } restore;
   VL_CUDA(cudaStreamWaitEvent(c->stream3, c->evPose, 0));
   const bool spec = d->specEnabled && !capture;
+  auto zeroSpecGrid = [&]() -> int {  // (issued after the update's first kernel: that one heads the critical chain)
   if (spec) {  // the cell counters of the speculative grid are zeroed beside the update, not behind it
     VL_CUDA(cudaStreamWaitEvent(c->streamAux, c->evPose, 0));
     vl_tls_stream = c->streamAux;
@@ -1544,7 +1546,10 @@ int vl_lm_run(vloam_b200_ctx* c) {
     vl_tls_stream = c->stream3;
     VL_CUDA(cudaEventRecord(c->evAuxZero, c->streamAux));
   }
+  return VLOAM_OK;
+  };
   const int nKeys = tailTotal + nq;
+  if (nKeys == 0) VL_TRY(zeroSpecGrid());
   if (nKeys > 0) {
     const size_t N = ((size_t)nKeys + 255) & ~(size_t)255;
     VL_TRY(vl_reserve(c, c->tailKeys, 4 * N, false, 4 * N));  // [0, N) unsorted keys | [N, 2N) bucketed + sorted | [2N, 4N) scratch for oversize segments
@@ -1557,6 +1562,7 @@ int vl_lm_run(vloam_b200_ctx* c) {
     VL_LAUNCH(rf_keys, vl_div_up(nKeys, 256), 256, 0, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, c->stackC.p, c->stackS.p,
               d->newPts.p, d->newCube.p, keysIn, nKeys);
     VL_CUDA(cudaEventRecord(c->evKeys, c->stream3));  // nothing below reads the stacks any more: the next sweep's filters may overwrite them
+    VL_TRY(zeroSpecGrid());
     VL_LAUNCH(rf_seg_scatter, vl_div_up(nKeys, 256), 256, 0, keysIn, nKeys, d->work, keysSorted);
     VL_BYTES(16.0 * nKeys);
     static const int segCap = getenv("VLOAM_SEG_CAP") ? max(8, min(atoi(getenv("VLOAM_SEG_CAP")), RF_SEG_CAP)) : RF_SEG_CAP;  // tests force the global path

@@ -544,7 +544,8 @@ static int lo_associate(vloam_b200_ctx* c, const double* d_pose, const float4* c
   VL_TRY(vl_reserve(c, c->factorValid, (size_t)max(nS + nF, 1)));
   // h_vScalars[8/9]: int(intensity) of the corner / surf cloud is non-decreasing (read after a sync point)
   const int set = c->lastSet;
-  const bool gridC = c->loGridValid[set] && c->h_vScalars[8 + 2 * set] != 0, gridS = c->loGridValid[set] && c->h_vScalars[9 + 2 * set] != 0;
+  const bool gridC = c->loGridValid[set] && (c->loAssumeMonotone || c->h_vScalars[8 + 2 * set] != 0);
+  const bool gridS = c->loGridValid[set] && (c->loAssumeMonotone || c->h_vScalars[9 + 2 * set] != 0);
   const int* start = c->loGridCells[set].p ? c->loGridCells[set].p + LOG_STRIDE : nullptr;
   const float4* gsorted = c->loGridSorted[set].p;
   const int* rtbl = c->loRingTbl + set * 2 * (LO_TBL + 1);
@@ -638,10 +639,14 @@ static int lo_queue_solve(vloam_b200_ctx* c, const double* prior_q, const double
 int vl_lo_lookahead(vloam_b200_ctx* c) {
   static const bool off = getenv("VLOAM_NO_LO_LOOKAHEAD") != nullptr;
   c->loNextValid = false;
-  if (off || !c->srNextValid || !c->lo_inited || c->timing || c->prof_name[0] || vl_debug_capture(c)) return VLOAM_OK;
-  VL_CUDA(cudaEventSynchronize(c->evLast));  // the structures over this sweep's clouds (built on the side stream) and their flags
+  VL_TRY(vl_lo_flush_deferred(c));  // (launches the look-ahead scan registration, records evLast)
+  if (off || !c->srNextValid || !c->lo_inited || c->prof_name[0] || vl_debug_capture(c)) return VLOAM_OK;
+  // The structures over this sweep's clouds are still being built on the side stream: wait for them on the DEVICE and
+  // assume what the host cannot know yet -- that both clouds have monotone ring ids, i.e. the grid search applies.
+  // The flags are checked when the result is adopted; a wrong guess only discards the look-ahead.
   const int set = c->lastSet;
-  if (!(c->loGridValid[set] && c->h_vScalars[8 + 2 * set] != 0 && c->h_vScalars[9 + 2 * set] != 0)) return VLOAM_OK;
+  if (!c->loGridValid[set]) return VLOAM_OK;
+  VL_CUDA(cudaStreamWaitEvent(c->stream, c->evLast, 0));
   VL_CUDA(cudaStreamWaitEvent(c->stream, c->srNext->evSR, 0));
   VL_CUDA(cudaMemcpyAsync(c->losNext, c->los, sizeof(LoScalars), cudaMemcpyDeviceToDevice, c->stream));
   const int curNow = c->cur;
@@ -649,17 +654,34 @@ int vl_lo_lookahead(vloam_b200_ctx* c) {
   const bool cv = c->sr_counts_valid;
   c->sr_counts_valid = false;  // the spare set's host counts are those of an older sweep: use the bounds, counts are read on the device
   { LoScalars* t_ = c->los; c->los = c->losNext; c->losNext = t_; }
+  c->loAssumeMonotone = true;
   const int r = lo_queue_solve(c, nullptr, nullptr, 0);
+  c->loAssumeMonotone = false;
   { LoScalars* t_ = c->los; c->los = c->losNext; c->losNext = t_; }
   c->sr_counts_valid = cv;
   vl_sr_swap(c, *c->srNext);
   c->cur = curNow;
   if (r != VLOAM_OK) return r;
-  c->loNextValid = true;
+  c->loNextValid = true; c->loNextSet = set;
+  return VLOAM_OK;
+}
+
+int vl_lo_flush_deferred(vloam_b200_ctx* c) {
+  if (!c->loDeferred) return VLOAM_OK;
+  c->loDeferred = false;
+  VL_TRY(vl_launch_lookahead(c));
+  cudaStream_t mainStream = c->stream;
+  c->stream = c->stream2;
+  const int r = vl_lo_build_last(c, c->defSet, c->defCorner, c->defNc, c->defSurf, c->defNs);
+  c->stream = mainStream;
+  if (r != VLOAM_OK) return r;
+  VL_CUDA(cudaEventRecord(c->evLast, c->stream2));
+  if (c->timing) VL_CUDA(cudaEventRecord(c->evx[5], c->stream2));
   return VLOAM_OK;
 }
 
 int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, int use_prior) {
+  VL_TRY(vl_lo_flush_deferred(c));
   VL_CUDA(cudaEventSynchronize(c->evLast));  // set [lastSet] (built underneath the previous frame) and its flags are complete
   // The grid kernels read the query counts on the device, so the odometry can be queued before the host
   // has them (sync point S1 then costs no GPU idle time).  The ballot fallback and the debug snapshots
@@ -678,16 +700,23 @@ int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, i
   }
   // The solve of this sweep was queued behind the previous sweep's mapping (vl_lo_lookahead) into the spare state:
   // adopting it is a pointer swap.  Anything that could make it stale clears loNextValid.
-  const bool adoptLO = c->loNextValid && c->srAdopted && !use_prior && !vl_debug_capture(c) && c->lo_inited;
+  const bool adoptLO = c->loNextValid && c->srAdopted && !use_prior && early && c->lo_inited && c->loNextSet == set;  // (early: grid valid, both flags set, no capture)
   c->loNextValid = false;
   if (adoptLO) { LoScalars* t_ = c->los; c->los = c->losNext; c->losNext = t_; }
   else if (c->lo_inited) VL_TRY(lo_queue_solve(c, prior_q, prior_t, use_prior));  // LO.cpp:209-217: the first frame only initialises
-  VL_TRY(vl_launch_lookahead(c));  // the next sweep's scan registration, if one is registered, goes to its side stream now
+  // With the solve adopted, the stacks queued and the mapping stage following in the same call, nothing on the pose
+  // chain depends on the rest of this stage: the look-ahead scan registration and the search structures of the next
+  // "last" clouds are queued by the mapping stage right after its own launches (vl_lo_flush_deferred).
+  const bool defer = adoptLO && stacksQueued && c->inProcessFrame;
+  if (!defer) VL_TRY(vl_launch_lookahead(c));  // the next sweep's scan registration, if one is registered, goes to its side stream now
   VL_HOST_MARK(2);
   VL_TRY(vl_sr_sync_counts(c));  // sync point S1 (event after scan registration; the odometry above is already queued)
   if (mapThisFrame && !stacksQueued)
     VL_TRY(vl_lm_enqueue_stacks(c, c->lessSharp[c->cur].p, c->nLessSharp, c->lessFlat[c->cur].p, c->nLessFlat));
-  {  // LO.cpp:573-574 (setInputCloud on both KD-trees) for the clouds that become "last" after this solve:
+  if (defer) {
+    c->loDeferred = true; c->defSet = c->lastSet ^ 1;
+    c->defCorner = c->lessSharp[c->cur].p; c->defNc = c->nLessSharp; c->defSurf = c->lessFlat[c->cur].p; c->defNs = c->nLessFlat;
+  } else {  // LO.cpp:573-574 (setInputCloud on both KD-trees) for the clouds that become "last" after this solve:
      // they are this frame's less-sharp / less-flat clouds, final since scan registration, so the side
      // stream builds them while the odometry still searches the previous set
     cudaStream_t mainStream = c->stream;
