@@ -111,7 +111,7 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   VL_CUDA_CREATE(cudaMalloc(&c->los, sizeof(LoScalars)));
   VL_CUDA_CREATE(cudaMalloc(&c->losNext, sizeof(LoScalars)));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evS2, cudaEventDisableTiming));
-  c->loNextValid = c->srAdopted = c->s2Done = false; c->loAssumeMonotone = c->inProcessFrame = c->loDeferred = false; c->loNextSet = 0;
+  c->loNextValid = c->srAdopted = c->s2Done = false; c->loAssumeMonotone = c->inProcessFrame = c->loDeferred = false; c->loNextSet = 0; c->stackSel = 0; c->stacksNextReady = false;
   VL_CUDA_CREATE(cudaMallocHost(&c->h_los, sizeof(LoScalars)));
   LoScalars hl; memset(&hl, 0, sizeof hl); hl.para_q[3] = 1.0; hl.q_w[3] = 1.0;  // LO.cpp:81-91
   VL_CUDA_CREATE(cudaMemcpy(c->los, &hl, sizeof hl, cudaMemcpyHostToDevice));
@@ -164,7 +164,7 @@ void vloam_b200_destroy(vloam_b200_ctx* c) {
                      c->dbgKnnOk[1][1].p};
   for (void* p : singles) if (p) cudaFree(p);
   void* bufs[] = {c->lessSharp[0].p, c->lessSharp[1].p, c->lessSharp[2].p, c->lessFlat[0].p, c->lessFlat[1].p, c->lessFlat[2].p, c->loCornerIdx.p, c->loSurfIdx.p, c->factors.p, c->factorValid.p, c->evalPartials.p,
-                  c->poolC.p, c->poolS.p, c->stackC.p, c->stackS.p, c->fromMapC.p, c->fromMapS.p, c->knnIdx.p, c->knnD2.p, c->knnOk.p,
+                  c->poolC.p, c->poolS.p, c->stackC.p, c->stackS.p, c->stackCN.p, c->stackSN.p, c->fromMapC.p, c->fromMapS.p, c->knnIdx.p, c->knnD2.p, c->knnOk.p,
                   c->vKeys.p, c->vKeys2.p, c->vHead.p, c->vScan.p, c->vScan2.p, c->vOut.p, c->vIn.p, c->regOut.p, c->tailKeys.p, c->staging.p};
   for (void* p : bufs) if (p) cudaFree(p);
   cudaFreeHost(c->h_los); cudaFreeHost(c->h_lms); cudaFreeHost(c->h_lmm); cudaFreeHost(c->h_vScalars);

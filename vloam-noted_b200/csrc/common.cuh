@@ -190,6 +190,8 @@ struct vloam_b200_ctx {
   MapCubeTable* cubeC; MapCubeTable* cubeS;  // device
   DBuf<float4> poolC, poolS;
   DBuf<float4> stackC, stackS;
+  DBuf<float4> stackCN, stackSN;  // the NEXT sweep's stacks (filtered during this sweep when its scan registration finished early); swapped in at adoption
+  int stackSel; bool stacksNextReady;  // which pair of device counts (LmDevice::dQ) belongs to stackC / stackS
   DBuf<float4> fromMapC, fromMapS;
   int lm_frameCount;
   int lm_optimized;  // host copy: did the last solveMapping run the optimisation (LM.cpp:514)
@@ -322,6 +324,8 @@ int vl_lo_associate_only(vloam_b200_ctx* c, const double* x, int* corner_idx, in
 int vl_lo_build_last(vloam_b200_ctx* c, int set, const float4* corner, int nc, const float4* surf, int ns);
 int vl_lm_run(vloam_b200_ctx* c);
 int vl_lm_enqueue_stacks(vloam_b200_ctx* c, const float4* corner, int nc, const float4* surf, int ns, bool early = false);
+int vl_lm_enqueue_stacks_next(vloam_b200_ctx* c, const float4* corner, int nc, const float4* surf, int ns);  // into the spare stack buffers (helper thread)
+int vl_lm_adopt_stacks_next(vloam_b200_ctx* c);  // make the spare stack buffers current
 int vl_lm_init(vloam_b200_ctx* c);
 void vl_lm_free(vloam_b200_ctx* c);
 extern "C" int vl_launch_lookahead(vloam_b200_ctx* c);  // capi.cu: queue the registered look-ahead scan registration (no-op without one)

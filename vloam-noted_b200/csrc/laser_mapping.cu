@@ -1306,7 +1306,7 @@ struct LmDevice {  // extra device state owned by this file
   DBuf<float4> sortedPts;
   DBuf<float4> newPts; DBuf<int> newCube;
   DBuf<int> unmatched;
-  int* dQ;          // two device ints: Qc, Qs from the voxel filters
+  int* dQ;          // 2 x two device ints: Qc, Qs from the voxel filters (pair ctx::stackSel is current)
   long long hMapUpperC, hMapUpperS;  // host upper bounds on the total map size
   LmSub* subReal; LmSub* subSpec;    // sub-map window descriptors (this frame's / the speculative one)
   int* specOK;                       // device flag written by lm_prepare: the speculative sub-map is this frame's
@@ -1326,7 +1326,8 @@ int vl_lm_init(vloam_b200_ctx* c) {
   VL_CUDA(cudaMalloc(&d->cellFill, sizeof(int) * (2 * LM_NCELL + 1)));
   VL_CUDA(cudaMalloc(&d->tileSum, sizeof(int) * (vl_div_up(2 * LM_NCELL, 1024) + 1)));
   VL_TRY(vl_scan_alloc(&d->scan, 2 * LM_NCELL));
-  VL_CUDA(cudaMalloc(&d->dQ, sizeof(int) * 2));
+  VL_CUDA(cudaMalloc(&d->dQ, sizeof(int) * 4));
+  VL_CUDA(cudaMemset(d->dQ, 0, sizeof(int) * 4));
   VL_CUDA(cudaMalloc(&d->subReal, sizeof(LmSub))); VL_CUDA(cudaMemset(d->subReal, 0, sizeof(LmSub)));
   VL_CUDA(cudaMalloc(&d->subSpec, sizeof(LmSub))); VL_CUDA(cudaMemset(d->subSpec, 0, sizeof(LmSub)));
   VL_CUDA(cudaMalloc(&d->specOK, sizeof(int))); VL_CUDA(cudaMemset(d->specOK, 0, sizeof(int)));
@@ -1381,32 +1382,54 @@ extern bool vl_debug_capture(const vloam_b200_ctx* c);
 // early = true (the counts were known when the sweep arrived: look-ahead scan registration): the helper thread
 // issues the ~14 launches while the caller queues the odometry, so the stacks are ready well before the mapping
 // front needs them; whoever needs evStacks joins the helper first (vl_lm_run does).
-static int lm_issue_stacks(vloam_b200_ctx* c, const float4* corner, int nc, const float4* surf, int ns) {
+static int lm_issue_stacks(vloam_b200_ctx* c, const float4* corner, int nc, const float4* surf, int ns, bool toNext) {
   LmDevice* d = lmdev(c);
   struct Restore { cudaStream_t prev; ~Restore() { vl_tls_stream = prev; } } restore{vl_tls_stream};
+  DBuf<float4>& dstS = toNext ? c->stackSN : c->stackS;
+  DBuf<float4>& dstC = toNext ? c->stackCN : c->stackC;
+  int* dq = d->dQ + 2 * (toNext ? c->stackSel ^ 1 : c->stackSel);
   // surf filter on stream2 (scratch lane 0), corner filter beside it on stream4 (scratch lane 1)
   vl_tls_stream = c->stream2;
-  cudaStreamWaitEvent(c->stream2, c->evKeys, 0);
-  int r = vl_reserve(c, c->stackS, (size_t)max(ns, 1));
-  if (r == VLOAM_OK) r = vl_voxel_grid_device(c, surf, ns, nullptr, c->prm.plane_res, c->stackS.p, d->dQ + 1, 0);
+  if (!toNext) cudaStreamWaitEvent(c->stream2, c->evKeys, 0);  // (the spare buffers were last read two sweeps ago)
+  int r = vl_reserve(c, dstS, (size_t)max(ns, 1));
+  if (r == VLOAM_OK) r = vl_voxel_grid_device(c, surf, ns, nullptr, c->prm.plane_res, dstS.p, dq + 1, 0);
   if (c->timing) cudaEventRecord(c->evx[3], c->stream2);
   vl_tls_stream = c->stream4;
-  cudaStreamWaitEvent(c->stream4, c->evKeys, 0);
-  if (r == VLOAM_OK) r = vl_reserve(c, c->stackC, (size_t)max(nc, 1));
-  if (r == VLOAM_OK) r = vl_voxel_grid_device(c, corner, nc, nullptr, c->prm.line_res, c->stackC.p, d->dQ, 1);
+  if (!toNext) cudaStreamWaitEvent(c->stream4, c->evKeys, 0);
+  if (r == VLOAM_OK) r = vl_reserve(c, dstC, (size_t)max(nc, 1));
+  if (r == VLOAM_OK) r = vl_voxel_grid_device(c, corner, nc, nullptr, c->prm.line_res, dstC.p, dq, 1);
   if (c->timing) cudaEventRecord(c->evx[4], c->stream4);
   if (r != VLOAM_OK) return r;
   VL_CUDA(cudaEventRecord(c->evStacks, c->stream2));
   VL_CUDA(cudaEventRecord(c->evStacksC, c->stream4));
-  c->stacksReady = true;
+  if (!toNext) c->stacksReady = true;
   return VLOAM_OK;
 }
 int vl_lm_enqueue_stacks(vloam_b200_ctx* c, const float4* corner, int nc, const float4* surf, int ns, bool early) {
   VL_TRY(vl_lm_join(c));  // evKeys of the previous frame's update must have been recorded before it is waited on
   static const bool noWorker = getenv("VLOAM_NO_WORKER") != nullptr;
   if (early && !noWorker && !c->prof_name[0] && !vl_debug_capture(c))
-    return lm_submit(c, [=]() -> int { return lm_issue_stacks(c, corner, nc, surf, ns); });
-  return lm_issue_stacks(c, corner, nc, surf, ns);
+    return lm_submit(c, [=]() -> int { return lm_issue_stacks(c, corner, nc, surf, ns, false); });
+  return lm_issue_stacks(c, corner, nc, surf, ns, false);
+}
+// The next sweep's stacks, filtered while this sweep's mapping still runs (its scan registration finished early): they
+// go to the spare buffers and the spare pair of counts, so nothing of this sweep is disturbed -- this sweep's mapping has
+// been queued already (it holds its own wait on evStacks), its map update reads the current buffers.
+int vl_lm_enqueue_stacks_next(vloam_b200_ctx* c, const float4* corner, int nc, const float4* surf, int ns) {
+  c->stacksNextReady = false;
+  static const bool noWorker = getenv("VLOAM_NO_WORKER") != nullptr;
+  if (noWorker) VL_TRY(lm_issue_stacks(c, corner, nc, surf, ns, true));
+  else VL_TRY(lm_submit(c, [=]() -> int { return lm_issue_stacks(c, corner, nc, surf, ns, true); }));
+  c->stacksNextReady = true;
+  return VLOAM_OK;
+}
+int vl_lm_adopt_stacks_next(vloam_b200_ctx* c) {
+  VL_TRY(vl_lm_join(c));  // the helper may still be issuing them (it owns the spare DBufs until it is done)
+  { DBuf<float4> t_ = c->stackC; c->stackC = c->stackCN; c->stackCN = t_; }
+  { DBuf<float4> t_ = c->stackS; c->stackS = c->stackSN; c->stackSN = t_; }
+  c->stackSel ^= 1;
+  c->stacksReady = true;
+  return VLOAM_OK;
 }
 
 // in-line sub-map build of this frame (one cooperative launch; returns at once on the device when *specOK)
@@ -1464,7 +1487,7 @@ int vl_lm_run(vloam_b200_ctx* c) {
     // only now are this frame's downsampled stacks needed (they were filtered on the side streams)
     VL_CUDA(cudaStreamWaitEvent(c->stream, c->evStacks, 0));
     VL_CUDA(cudaStreamWaitEvent(c->stream, c->evStacksC, 0));
-    VL_LAUNCH(lm_set_counts, 1, 32, 0, c->lmm, d->work, d->dQ, d->dQ + 1);
+    VL_LAUNCH(lm_set_counts, 1, 32, 0, c->lmm, d->work, d->dQ + 2 * c->stackSel, d->dQ + 2 * c->stackSel + 1);
     if (c->timing) VL_CUDA(cudaEventRecord(c->evx[1], c->stream));
     if (capture) {
       VL_CUDA(cudaMemcpyAsync(c->h_lmm, c->lmm, sizeof(LmScalars), cudaMemcpyDeviceToHost, c->stream));
@@ -1532,6 +1555,7 @@ int vl_lm_run(vloam_b200_ctx* c) {
   const int nq = Qc + Qs;
   c->lm_optimized = c->h_lmm->optimized;
   const long long totalC = c->h_lmm->totalC, totalS = c->h_lmm->totalS;
+  const float4* const stackCp = c->stackC.p; const float4* const stackSp = c->stackS.p;  // (the next frame may swap the buffers while the helper issues this)
   auto update = [=]() -> int {
   vl_tls_stream = c->stream3;  // every launch helper below issues on the update's stream, whichever thread runs this
   struct Restore { ~Restore() { vl_tls_stream = nullptr; } } restore;
@@ -1559,7 +1583,7 @@ int vl_lm_run(vloam_b200_ctx* c) {
     VL_TRY(vl_reserve(c, d->newCube, (size_t)max(nq, 1)));
     VL_TRY(vl_reserve(c, d->unmatched, (size_t)nKeys + 2, false, (size_t)nKeys + (1 << 16)));
     VL_TRY(vl_reserve(c, c->staging, (size_t)Mc + Ms + nKeys + 1, false, (size_t)(Mc + Ms) / 2 + (1 << 20)));
-    VL_LAUNCH(rf_keys, vl_div_up(nKeys, 256), 256, 0, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, c->stackC.p, c->stackS.p,
+    VL_LAUNCH(rf_keys, vl_div_up(nKeys, 256), 256, 0, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, stackCp, stackSp,
               d->newPts.p, d->newCube.p, keysIn, nKeys);
     VL_CUDA(cudaEventRecord(c->evKeys, c->stream3));  // nothing below reads the stacks any more: the next sweep's filters may overwrite them
     VL_TRY(zeroSpecGrid());

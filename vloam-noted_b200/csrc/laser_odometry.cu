@@ -639,7 +639,7 @@ static int lo_queue_solve(vloam_b200_ctx* c, const double* prior_q, const double
 int vl_lo_lookahead(vloam_b200_ctx* c) {
   static const bool off = getenv("VLOAM_NO_LO_LOOKAHEAD") != nullptr;
   c->loNextValid = false;
-  VL_TRY(vl_lo_flush_deferred(c));  // (launches the look-ahead scan registration, records evLast)
+  VL_TRY(vl_lo_flush_deferred(c));  // (records evLast)
   if (off || !c->srNextValid || !c->lo_inited || c->prof_name[0] || vl_debug_capture(c)) return VLOAM_OK;
   // The structures over this sweep's clouds are still being built on the side stream: wait for them on the DEVICE and
   // assume what the host cannot know yet -- that both clouds have monotone ring ids, i.e. the grid search applies.
@@ -651,16 +651,30 @@ int vl_lo_lookahead(vloam_b200_ctx* c) {
   VL_CUDA(cudaMemcpyAsync(c->losNext, c->los, sizeof(LoScalars), cudaMemcpyDeviceToDevice, c->stream));
   const int curNow = c->cur;
   vl_sr_swap(c, *c->srNext);
-  const bool cv = c->sr_counts_valid;
-  c->sr_counts_valid = false;  // the spare set's host counts are those of an older sweep: use the bounds, counts are read on the device
   { LoScalars* t_ = c->los; c->los = c->losNext; c->losNext = t_; }
   c->loAssumeMonotone = true;
-  const int r = lo_queue_solve(c, nullptr, nullptr, 0);
+  int r = lo_queue_solve(c, nullptr, nullptr, 0);  // (host counts of that sweep not known yet: bounds, the kernels read the counts on the device)
   c->loAssumeMonotone = false;
   { LoScalars* t_ = c->los; c->los = c->losNext; c->losNext = t_; }
-  c->sr_counts_valid = cv;
+  // The host only waits for S2 from here on.  If the look-ahead scan registration finishes before this sweep's mapping
+  // does, the next sweep's stack filters (LM.cpp:492-500) are issued now as well, into the spare stack buffers.
+  const bool mapNext = ((c->lo_frameCount + 1) % c->prm.mapping_skip_frame) == 0;
+  static const bool noStacksNext = getenv("VLOAM_NO_STACKS_LOOKAHEAD") != nullptr;
+  bool srDone = false;
+  if (r == VLOAM_OK && mapNext && !noStacksNext) {
+    for (;;) {
+      if (cudaEventQuery(c->evSR) == cudaSuccess) { srDone = true; break; }
+      if (cudaEventQuery(c->evS2) == cudaSuccess) break;  // never hold the pose back for it
+    }
+  }
+  const float4* nCorner = nullptr; const float4* nSurf = nullptr; int nNc = 0, nNs = 0;
+  if (srDone) {
+    r = vl_sr_sync_counts(c);
+    nCorner = c->lessSharp[c->cur].p; nNc = c->nLessSharp; nSurf = c->lessFlat[c->cur].p; nNs = c->nLessFlat;
+  }
   vl_sr_swap(c, *c->srNext);
   c->cur = curNow;
+  if (r == VLOAM_OK && srDone) r = vl_lm_enqueue_stacks_next(c, nCorner, nNc, nSurf, nNs);
   if (r != VLOAM_OK) return r;
   c->loNextValid = true; c->loNextSet = set;
   return VLOAM_OK;
@@ -669,7 +683,6 @@ int vl_lo_lookahead(vloam_b200_ctx* c) {
 int vl_lo_flush_deferred(vloam_b200_ctx* c) {
   if (!c->loDeferred) return VLOAM_OK;
   c->loDeferred = false;
-  VL_TRY(vl_launch_lookahead(c));
   cudaStream_t mainStream = c->stream;
   c->stream = c->stream2;
   const int r = vl_lo_build_last(c, c->defSet, c->defCorner, c->defNc, c->defSurf, c->defNs);
@@ -693,7 +706,11 @@ int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, i
   // filters of this sweep go to the helper thread now instead of behind the odometry launches.
   const bool mapThisFrame = ((c->lo_frameCount + 1) % c->prm.mapping_skip_frame) == 0;  // LO.cpp:668
   bool stacksQueued = false;
-  if (early && mapThisFrame && cudaEventQuery(c->evSR) == cudaSuccess) {
+  if (c->stacksNextReady) {  // this sweep's stacks were filtered underneath the previous sweep's mapping
+    c->stacksNextReady = false;
+    if (c->srAdopted && mapThisFrame) { VL_TRY(vl_sr_sync_counts(c)); VL_TRY(vl_lm_adopt_stacks_next(c)); stacksQueued = true; }
+  }
+  if (!stacksQueued && early && mapThisFrame && cudaEventQuery(c->evSR) == cudaSuccess) {
     VL_TRY(vl_sr_sync_counts(c));
     VL_TRY(vl_lm_enqueue_stacks(c, c->lessSharp[c->cur].p, c->nLessSharp, c->lessFlat[c->cur].p, c->nLessFlat, true));
     stacksQueued = true;
@@ -705,10 +722,10 @@ int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, i
   if (adoptLO) { LoScalars* t_ = c->los; c->los = c->losNext; c->losNext = t_; }
   else if (c->lo_inited) VL_TRY(lo_queue_solve(c, prior_q, prior_t, use_prior));  // LO.cpp:209-217: the first frame only initialises
   // With the solve adopted, the stacks queued and the mapping stage following in the same call, nothing on the pose
-  // chain depends on the rest of this stage: the look-ahead scan registration and the search structures of the next
-  // "last" clouds are queued by the mapping stage right after its own launches (vl_lo_flush_deferred).
+  // chain depends on the search structures of the next "last" clouds: they are queued by the mapping stage right after
+  // its own launches (vl_lo_flush_deferred).
   const bool defer = adoptLO && stacksQueued && c->inProcessFrame;
-  if (!defer) VL_TRY(vl_launch_lookahead(c));  // the next sweep's scan registration, if one is registered, goes to its side stream now
+  VL_TRY(vl_launch_lookahead(c));  // the next sweep's scan registration, if one is registered, goes to its side stream now
   VL_HOST_MARK(2);
   VL_TRY(vl_sr_sync_counts(c));  // sync point S1 (event after scan registration; the odometry above is already queued)
   if (mapThisFrame && !stacksQueued)
