@@ -489,15 +489,15 @@ __device__ __forceinline__ void lm_dev_scan_apply(const int* __restrict__ in, in
   if (tile == nTiles - 1 && threadIdx.x == 0) out[n] = running;  // total
 }
 // ---- single-launch exclusive scan (chained tiles with look-back) --------------------------------------
-// out[0..n] = exclusive scan of in[0..n) (out[n] = total).  A tile is 1024 counts (4 consecutive per thread, one
-// 128-bit load and store each).  Tiles take their index from a ticket counter, so every predecessor of a running
+// out[0..n] = exclusive scan of in[0..n) (out[n] = total).  A tile is 4096 counts (16 consecutive per thread, four
+// 128-bit loads and stores each).  Tiles take their index from a ticket counter, so every predecessor of a running
 // tile is itself running or done; a tile publishes its own sum at once ("aggregate"), warp 0 then walks the status
-// words of the tiles before it, 32 at a time, until it meets one that already knows its inclusive prefix, and
+// words of the tiles before it, 64 at a time, until it meets one that already knows its inclusive prefix, and
 // publishes its own.  Status word: [63:34] epoch of this launch | [33:32] 1 aggregate / 2 inclusive | [31:0] value --
 // written and read as one 64-bit word, and stale words of earlier launches simply read as "not ready", so nothing
 // has to be cleared between launches.  The three-kernel version (tile sums, scan of sums, apply) cost two more
 // dependent launches and a second read of the counts on the update -> sub-map chain.
-#define SCAN_TILE 1024
+#define SCAN_TILE 4096  // 256 threads x 16 consecutive counts
 __global__ void __launch_bounds__(256) lm_scan_chained(const int* __restrict__ in, int n, unsigned long long* __restrict__ state,
                                                        unsigned epoch, int* __restrict__ out, const int* __restrict__ skip) {
   VL_PDL_WAIT();
@@ -513,12 +513,23 @@ __global__ void __launch_bounds__(256) lm_scan_chained(const int* __restrict__ i
   }
   __syncthreads();
   const int tile = sTile;
-  const int base = tile * SCAN_TILE + threadIdx.x * 4;
-  int4 v = make_int4(0, 0, 0, 0);
-  if (base + 3 < n) v = *reinterpret_cast<const int4*>(in + base);
-  else { if (base < n) v.x = in[base]; if (base + 1 < n) v.y = in[base + 1]; if (base + 2 < n) v.z = in[base + 2]; }
+  const int base = tile * SCAN_TILE + threadIdx.x * 16;
+  int v[16];
+  if (base + 15 < n) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int4 x = *reinterpret_cast<const int4*>(in + base + 4 * q);
+      v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = base + k < n ? in[base + k] : 0;
+  }
+  int own = 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) own += v[k];
   int tot = 0;
-  const int ex = vl_block_excl_scan<256>(v.x + v.y + v.z + v.w, ws, &tot);
+  const int ex = vl_block_excl_scan<256>(own, ws, &tot);
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
     const unsigned long long tag = (unsigned long long)epoch << 34;
@@ -526,30 +537,49 @@ __global__ void __launch_bounds__(256) lm_scan_chained(const int* __restrict__ i
     int excl = 0;
     if (tile > 0) {
       if (lane == 0) st[tile] = tag | (1ull << 32) | (unsigned)tot;
+      // Tiles start together, so a far tile may walk a long way back over aggregates: 64 status words per step
+      // (group 0: the 32 nearest tiles, group 1: the 32 before them).
       int look = tile - 1;
       for (;;) {
-        const int idx = look - lane;
-        const unsigned long long wd = idx >= 0 ? st[idx] : (tag | (2ull << 32));  // before tile 0: inclusive prefix 0
-        const int status = (wd >> 34) == (unsigned long long)epoch ? (int)((wd >> 32) & 3) : 0;
-        const unsigned notReady = __ballot_sync(0xffffffffu, status == 0);
-        const unsigned incl = __ballot_sync(0xffffffffu, status == 2);
-        const int f = incl ? __ffs(incl) - 1 : 32;                                  // nearest tile with an inclusive prefix
-        const unsigned need = f >= 31 ? 0xffffffffu : ((2u << f) - 1u);           // lanes 0..f (all 32 when there is none)
-        if (notReady & need) continue;                                             // a tile in between has not published yet
-        int val = lane <= f ? (int)(unsigned)wd : 0;
+        const int i0 = look - lane, i1 = look - 32 - lane;
+        const unsigned long long w0 = i0 >= 0 ? st[i0] : (tag | (2ull << 32));  // before tile 0: inclusive prefix 0
+        const unsigned long long w1 = i1 >= 0 ? st[i1] : (tag | (2ull << 32));
+        const int s0 = (w0 >> 34) == (unsigned long long)epoch ? (int)((w0 >> 32) & 3) : 0;
+        const int s1 = (w1 >> 34) == (unsigned long long)epoch ? (int)((w1 >> 32) & 3) : 0;
+        const unsigned nr0 = __ballot_sync(0xffffffffu, s0 == 0), in0 = __ballot_sync(0xffffffffu, s0 == 2);
+        const unsigned nr1 = __ballot_sync(0xffffffffu, s1 == 0), in1 = __ballot_sync(0xffffffffu, s1 == 2);
+        int val; bool done = false; int step = 0;
+        if (in0) {  // an inclusive prefix among the 32 nearest: lanes 0..f of group 0 close the walk
+          const int f = __ffs(in0) - 1;
+          const unsigned need = f >= 31 ? 0xffffffffu : ((2u << f) - 1u);
+          if (nr0 & need) continue;
+          val = lane <= f ? (int)(unsigned)w0 : 0; done = true;
+        } else {
+          if (nr0) continue;  // group 0 is all aggregates once everything there is published
+          val = (int)(unsigned)w0; step = 32;
+          const int f = in1 ? __ffs(in1) - 1 : 32;
+          const unsigned need = f >= 31 ? 0xffffffffu : ((2u << f) - 1u);
+          if (!(nr1 & need)) { val += lane <= f ? (int)(unsigned)w1 : 0; step = 64; done = f < 32; }
+        }
         for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
         excl += val;
-        if (f < 32) break;
-        look -= 32;
+        if (done) break;
+        look -= step;
       }
     }
     if (lane == 0) { st[tile] = tag | (2ull << 32) | (unsigned)(excl + tot); sPrefix = excl; }
   }
   __syncthreads();
-  const int p0 = sPrefix + ex;
-  const int4 o = make_int4(p0, p0 + v.x, p0 + v.x + v.y, p0 + v.x + v.y + v.z);
-  if (base + 3 < n) *reinterpret_cast<int4*>(out + base) = o;
-  else { if (base < n) out[base] = o.x; if (base + 1 < n) out[base + 1] = o.y; if (base + 2 < n) out[base + 2] = o.z; }
+  int run = sPrefix + ex;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) { const int t = v[k]; v[k] = run; run += t; }
+  if (base + 15 < n) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) *reinterpret_cast<int4*>(out + base + 4 * q) = make_int4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) if (base + k < n) out[base + k] = v[k];
+  }
   if (tile == (int)gridDim.x - 1 && threadIdx.x == 0) out[n] = sPrefix + tot;
 }
 int vl_scan_alloc(VlScan* sc, int n) {
