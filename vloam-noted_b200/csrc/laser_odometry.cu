@@ -663,9 +663,13 @@ int vl_lo_lookahead(vloam_b200_ctx* c) {
   bool srDone = false;
   if (r == VLOAM_OK && mapNext && !noStacksNext) {
     for (;;) {
-      if (cudaEventQuery(c->evSR) == cudaSuccess) { srDone = true; break; }
-      if (cudaEventQuery(c->evS2) == cudaSuccess) break;  // never hold the pose back for it
+      cudaError_t e = cudaEventQuery(c->evSR);
+      if (e == cudaSuccess) { srDone = true; break; }
+      if (e != cudaErrorNotReady) break;                  // a real error: the next checked call reports it
+      e = cudaEventQuery(c->evS2);
+      if (e != cudaErrorNotReady) break;                  // mapping finished first: never hold the pose back for the stacks
     }
+    (void)cudaGetLastError();  // (cudaErrorNotReady is a status, not a failure: do not leave it for the next cudaGetLastError check)
   }
   const float4* nCorner = nullptr; const float4* nSurf = nullptr; int nNc = 0, nNs = 0;
   if (srDone) {
