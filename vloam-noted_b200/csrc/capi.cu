@@ -605,6 +605,7 @@ int vloam_b200_debug_set(vloam_b200_ctx* c, const char* name, const void* data, 
 
 int vloam_b200_voxel_grid(vloam_b200_ctx* c, const float* in, int n, float leaf, float* out, int cap_points) {
   if (n < 0 || !(leaf > 0.f)) return VLOAM_E_INVALID;
+  VL_TRY(vloam_b200_synchronize(c));  // look-ahead stack filters of a registered sweep may still be using the filter scratch
   VL_TRY(vl_reserve(c, c->vIn, (size_t)max(n, 1)));
   VL_TRY(vl_reserve(c, c->vOut, (size_t)max(n, 1)));
   if (n) VL_CUDA(cudaMemcpyAsync(c->vIn.p, in, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
