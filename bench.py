@@ -9,17 +9,21 @@ One "step" = one sweep through the whole per-frame chain (MAIN.cpp:143-144, 186-
   python bench.py --impl reference [...]                       the CPU restatement of the reference
                                                                (oracle/, KD-tree mode) on the host cores
 
+The K-step window is measured R times (--repeats, default min(25, 700 // K)), every window on a fresh context
+with the same W + 1 warm-up sweeps, with a barrier + synchronize on both sides; `value` / `e2e` are the medians
+over the windows (max over ranks inside each window), min / max are reported beside them.
+
 Under torchrun (N > 1) every rank replays its own independent sequence (weak scaling, no data-path
-collective); poses and timings are gathered with one NCCL all_gather at the end.
+collective); poses and timings are gathered with one NCCL all_gather at the end (parallel.gather_results).
 """
 import argparse
 import importlib
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -28,17 +32,40 @@ sys.path.insert(0, ROOT)
 
 SENSOR = 1  # HDL-64E
 WORKLOAD = "C3: synthetic HDL-64E sweeps (~118k pts), full scanRegistration+laserOdometry+laserMapping per sweep, planted ~1M-point cube map"
+KW = dict(n_scans=64, minimum_range=5.0, line_res=0.4, plane_res=0.8)
+POS_TOL, ROT_TOL = 1e-4, 1e-5  # BASELINE.json north_star
+
+
+def _gen_scans(pkg, world, traj, seeds, threads=None):
+    """Synthetic sweeps in parallel (the generator is a C library: ctypes releases the GIL)."""
+    n = len(seeds)
+    if n <= 8:
+        return [world.scan(SENSOR, traj[k], seeds[k]) for k in range(n)]
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    with ThreadPoolExecutor(max_workers=max(1, min(threads or cores, 16))) as ex:
+        return list(ex.map(lambda k: world.scan(SENSOR, traj[k], seeds[k]), range(n)))
 
 
 def make_sequence(pkg, seq_id, n_frames, world_kind=1):
     synth = pkg.synth
     world = synth.World(1234, world_kind, 190.0)
     traj = synth.trajectory(n_frames, seed=77 + seq_id)
-    scans = [world.scan(SENSOR, traj[k], 1000 + 7919 * seq_id + k) for k in range(n_frames)]
+    scans = _gen_scans(pkg, world, traj, [1000 + 7919 * seq_id + k for k in range(n_frames)])
     corner = world.plant(0, 0.4, seed=99)
     surf = world.plant(1, 0.8, seed=98)
     cblob, sblob = synth.cubes_blob(corner, 0.4), synth.cubes_blob(surf, 0.8)
     return scans, traj, cblob, sblob
+
+
+def bench_config(map_points, points_per_sweep):
+    """`config` of the JSON line: the same dict in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "map_points": int(map_points), "points_per_sweep": int(points_per_sweep),
+            "l2": "inputs larger than L2: every sweep is a new 1.9 MB input and the device-resident sweeps of a window total > L2 "
+                  "together with the ~1 GB map pools; the persistent search state stays L2-resident across sweeps as it does in "
+                  "deployment; `cold_l2` repeats the measurement with L2 flushed before every sweep",
+            "parallelism": "independent sequences, one per GPU",
+            "mode": "replay: the next sweep is registered (vloam_b200_prefetch_scan[_device]) before each process_frame call; `online` "
+                    "reports the one-sweep-at-a-time case"}
 
 
 class ClockSampler:
@@ -48,6 +75,7 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.idx, self.rows, self.stop_flag, self.thread, self.nv = gpu_index, [], False, None, None
+        self.active = False  # rows are kept only while a timed region is open
 
     def start(self):
         try:
@@ -65,7 +93,7 @@ class ClockSampler:
 
     def _loop(self):
         nv = self.nv
-        period = float(os.environ.get("BENCH_SMI_MS", "50")) / 1e3
+        period = float(os.environ.get("BENCH_SMI_MS", "20")) / 1e3
         while not self.stop_flag:
             try:
                 sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
@@ -73,7 +101,7 @@ class ClockSampler:
                     reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                self.rows.append((sm, reasons))
+                self.rows.append((sm, reasons, self.active))
             except Exception:
                 pass
             time.sleep(period)
@@ -85,13 +113,14 @@ class ClockSampler:
         if not self.nv or not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         nv = self.nv
+        rows = [r for r in self.rows if r[2]] or self.rows
         names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
                  "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
                  "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
                  "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
-        seen = sorted(n for n, bit in names.items() if any(r & bit for _, r in self.rows))
-        return {"sm_mhz": float(np.median([r[0] for r in self.rows])), "sm_max_mhz": float(self.sm_max), "reasons": seen,
-                "samples": len(self.rows)}
+        seen = sorted(n for n, bit in names.items() if any(r[1] & bit for r in rows))
+        return {"sm_mhz": float(np.median([r[0] for r in rows])), "sm_max_mhz": float(self.sm_max), "reasons": seen,
+                "samples": len(rows), "samples_total": len(self.rows)}
 
 
 def measured_peak():
@@ -101,77 +130,166 @@ def measured_peak():
     return 6650.0, "fallback"
 
 
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def pin_rank_threads(local_rank, local_world):
+    """One process per GPU on a shared host: give every local rank its own slice of the cores (caller thread, the context's
+    helper thread, NCCL's proxy / watchdog threads and torch's pool all inherit it), so that eight ranks do not
+    migrate across -- and pre-empt each other on -- the same cores inside a millisecond-scale timed window."""
+    if local_world <= 1 or not hasattr(os, "sched_setaffinity"):
+        return None
+    cores = sorted(os.sched_getaffinity(0))
+    per = len(cores) // local_world
+    if per < 2:
+        return None
+    mine = cores[local_rank * per:(local_rank + 1) * per]
+    os.sched_setaffinity(0, mine)
+    return mine
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU side: the oracle (test infrastructure) as the timed CPU baseline and as the parity witness of the GPU run
+# ---------------------------------------------------------------------------------------------------------------
+def oracle_replay(scans, cblob, sblob, frames, want_maps=True):
+    """The CPU restatement on sweeps [0, frames): per-frame wall time, stage times, poses and the final maps."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as op
+    o = op.Oracle(knn_backend=1, **KW)
+    o.set("lm.cornerMap", cblob); o.set("lm.surfMap", sblob)
+    times, stages, poses = [], [], np.zeros((frames, 14))
+    for k in range(frames):
+        t0 = time.perf_counter()
+        o.process(scans[k])
+        times.append(time.perf_counter() - t0)
+        stages.append(o.get("timing")[:3])
+        poses[k, :7] = o.get("lo.pose")[:7]
+        poses[k, 7:] = o.get("lm.pose")[:7]
+    maps = (o.get("lm.cornerMap"), o.get("lm.surfMap")) if want_maps else None
+    return times, np.array(stages), poses, maps
+
+
+def compare_maps(a, b):
+    """Two `lm.*Map` blobs (int32 counts[4851] + float32 points): exact equality and, when they differ, by how much."""
+    if a == b:
+        return {"equal": True, "cubes_differing": 0, "floats_differing": 0}
+    n = 4851 * 4
+    ca, cb = np.frombuffer(a[:n], np.int32), np.frombuffer(b[:n], np.int32)
+    out = {"equal": False, "cubes_differing": int((ca != cb).sum()), "points": [int(ca.sum()), int(cb.sum())]}
+    if (ca == cb).all():
+        fa, fb = np.frombuffer(a[n:], np.float32), np.frombuffer(b[n:], np.float32)
+        d = fa != fb
+        out["floats_differing"] = int(d.sum())
+        out["max_abs_diff"] = float(np.abs(fa[d] - fb[d]).max()) if d.any() else 0.0
+    return out
+
+
+def gpu_replay_lookahead(pkg, torch, local_rank, scans, cblob, sblob, frames, lookahead=True, pinned=None):
+    """The benchmarked path: host buffers through vloam_b200_prefetch_scan + vloam_b200_process_frame (look-ahead scan
+    registration / odometry / stack filters, speculation and the helper thread all on, no debug capture)."""
+    ctx = pkg.Context(device=local_rank, **KW)
+    ctx.set("lm.cornerMap", cblob); ctx.set("lm.surfMap", sblob)
+    pinned = pinned or [torch.from_numpy(s).pin_memory() for s in scans[:frames + 1]]
+    pose, poses = np.zeros(14), np.zeros((frames, 14))
+    for k in range(frames):
+        if lookahead and k + 1 < len(pinned):
+            ctx.prefetch_ptr(pinned[k + 1].data_ptr(), pinned[k + 1].shape[0], 4)
+        ctx.process_frame_ptr(pinned[k].data_ptr(), pinned[k].shape[0], 4, pose.ctypes.data)
+        poses[k] = pose
+    maps = (ctx.get("lm.cornerMap"), ctx.get("lm.surfMap"))
+    ctx.close()
+    return poses, maps
+
+
+def parity_report(gpu_poses, gpu_maps, cpu_poses, cpu_maps, truth=None):
+    """`parity` block: the CUDA path against the oracle on the same sweeps, free-running from the same planted map."""
+    n = min(len(gpu_poses), len(cpu_poses))
+    g, c = gpu_poses[:n], cpu_poses[:n]
+    dt = max(np.abs(g[:, 4:7] - c[:, 4:7]).max(), np.abs(g[:, 11:14] - c[:, 11:14]).max())
+    dq = max(np.abs(g[:, 0:4] - c[:, 0:4]).max(), np.abs(g[:, 7:11] - c[:, 7:11]).max())
+    mc, ms = compare_maps(gpu_maps[0], cpu_maps[0]), compare_maps(gpu_maps[1], cpu_maps[1])
+    out = {"frames": int(n), "max_dt_m": float(dt), "max_dq": float(dq), "tolerance": [POS_TOL, ROT_TOL],
+           "within_tolerance": bool(dt < POS_TOL and dq < ROT_TOL), "poses_bit_identical": bool((g == c).all()),
+           "map_bytes_equal": bool(mc["equal"] and ms["equal"]),
+           "against": "oracle/ (KD-tree mode), free-running on the same sweeps and planted map; GPU side = prefetch_scan + process_frame with host buffers"}
+    if not out["map_bytes_equal"]:
+        out["map_diff"] = {"corner": mc, "surf": ms}
+    if truth is not None:
+        out["final_pose_error_m"] = {"gpu": float(np.linalg.norm(g[-1, 11:14] - truth[n - 1][:3])), "cpu": float(np.linalg.norm(c[-1, 11:14] - truth[n - 1][:3]))}
+    return out
+
+
 def run_reference(args, rank, world_size):
-    """CPU arm: the oracle in baseline mode (KD-tree kNN, std::sort voxel grids, restated Ceres LM),
-    one single-threaded replica per host core like the reference (MAIN.cpp:277-282)."""
+    """CPU arm: the oracle in baseline mode (KD-tree kNN, std::sort voxel grids, restated Ceres LM), one
+    single-threaded replica per host core -- the reference itself is single-threaded (MAIN.cpp:277-282), so all
+    the host threads it can use means one sequence per core."""
     if rank != 0:
         return
     pkg = importlib.import_module("vloam-noted_b200")
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py as op
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    replicas = max(1, min(cores, 16))
-    budget_s = 200.0
-    n_frames = args.warmup + args.steps + 1
-    scans, traj, cblob, sblob = make_sequence(pkg, 0, min(n_frames, 64))
+    K, W = args.steps, max(args.warmup, 3)
+    replicas = max(1, host_cores())
+    budget_s = 240.0
+    n_frames = W + 1 + K
+    scans, traj, cblob, sblob = make_sequence(pkg, 0, n_frames + 1)
 
     def replica(out, idx):
-        o = op.Oracle(n_scans=64, minimum_range=5.0, line_res=0.4, plane_res=0.8, knn_backend=1)
+        o = op.Oracle(knn_backend=1, **KW)
         o.set("lm.cornerMap", cblob); o.set("lm.surfMap", sblob)
         times = []
         t_start = time.perf_counter()
         for k in range(n_frames):
-            s = scans[k % len(scans)]
             t0 = time.perf_counter()
-            o.process(s)
+            o.process(scans[k])
             times.append(time.perf_counter() - t0)
-            if time.perf_counter() - t_start > budget_s:
+            if time.perf_counter() - t_start > budget_s and k >= W + 1:
                 break
         out[idx] = times
 
     results = [None] * replicas
     th = [threading.Thread(target=replica, args=(results, i)) for i in range(replicas)]
-    t0 = time.perf_counter()
     for t in th: t.start()
     for t in th: t.join()
     done = min(len(r) for r in results)
-    w = min(args.warmup + 1, max(done - 1, 0))
+    w = W + 1  # the same W + 1 untimed sweeps as the CUDA arm's windows
     timed = done - w
     per_rep = [sum(r[w:done]) for r in results]
     wall = max(per_rep)
     value = replicas * timed / wall if wall > 0 else 0.0
     single = timed / float(np.mean(per_rep)) if timed else 0.0
+    map_points = int(pkg.synth.blob_counts(cblob).sum() + pkg.synth.blob_counts(sblob).sum())
     line = {
-        "impl": "reference", "metric": "scans/sec", "value": value, "unit": "scans/s", "n_gpus": args.gpus, "steps": timed, "warmup": w,
+        "impl": "reference", "metric": "scans/sec", "value": value, "unit": "scans/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * wall / max(timed, 1) / replicas, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "map_points": int(pkg.synth.blob_counts(cblob).sum() + pkg.synth.blob_counts(sblob).sum())},
+        "data": "synthetic", "config": bench_config(map_points, np.mean([len(s) for s in scans])),
+        "steps_completed": timed,
         "cpu_baseline": {"value": value, "unit": "scans/s", "cores": replicas, "kind": "port",
-                         "sample": "%d frames x %d single-threaded replicas of oracle/ (KD-tree mode); one replica alone: %.3f scans/s; p50 %.1f ms/frame"
-                                   % (timed, replicas, single, 1e3 * float(np.median(np.concatenate([r[w:done] for r in results])))) if timed else "none"},
+                         "sample": "%d frames x %d single-threaded replicas of oracle/ (KD-tree mode) on %d host cores; one replica alone: %.3f scans/s; p50 %.1f ms/frame"
+                                   % (timed, replicas, host_cores(), single, 1e3 * float(np.median(np.concatenate([r[w:done] for r in results])))) if timed else "none"},
         "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_sample(pkg, scans, cblob, sblob, frames=4):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle_py as op
-    o = op.Oracle(n_scans=64, minimum_range=5.0, line_res=0.4, plane_res=0.8, knn_backend=1)
-    o.set("lm.cornerMap", cblob); o.set("lm.surfMap", sblob)
-    times, stages = [], []
-    for k in range(frames + 1):
-        t0 = time.perf_counter()
-        o.process(scans[k])
-        times.append(time.perf_counter() - t0)
-        stages.append(o.get("timing")[:3])
+def cpu_baseline_and_parity(pkg, torch, local_rank, scans, traj, cblob, sblob, frames):
+    """cpu_baseline (the oracle, one core, `frames` sweeps after one warm-up sweep) and the parity block: the very poses
+    and maps of that CPU run against a GPU replay of the same sweeps through the benchmarked (look-ahead) path."""
+    n = frames + 1
+    times, stages, cpu_poses, cpu_maps = oracle_replay(scans, cblob, sblob, n)
     t = times[1:]
-    st = np.mean(np.array(stages[1:]), axis=0)
-    return {"value": len(t) / sum(t), "unit": "scans/s", "cores": 1, "kind": "port",
-            "sample": "%d frames of the same workload after 1 warm-up frame, single thread like the reference; mean ms SR/LO/LM = %.1f/%.1f/%.1f"
-                      % (len(t), st[0], st[1], st[2])}
+    st = stages[1:].mean(axis=0)
+    cpu = {"value": len(t) / sum(t), "unit": "scans/s", "cores": 1, "kind": "port",
+           "sample": "%d frames of the same workload after 1 warm-up frame, single thread like the reference; mean ms SR/LO/LM = %.1f/%.1f/%.1f"
+                     % (len(t), st[0], st[1], st[2])}
+    gpu_poses, gpu_maps = gpu_replay_lookahead(pkg, torch, local_rank, scans, cblob, sblob, n)
+    return cpu, parity_report(gpu_poses, gpu_maps, cpu_poses, cpu_maps, traj)
 
 
-
+# ---------------------------------------------------------------------------------------------------------------
+# GPU side
+# ---------------------------------------------------------------------------------------------------------------
 def _time_frames(ctx, torch, ext, frames, warm, fn):
     """Device time of `fn(k)` over frames[warm:], CUDA events on the context's stream; returns ms per frame."""
     for k in range(warm):
@@ -210,51 +328,62 @@ def other_workloads(pkg, torch, local_rank, frames=70, warm=10):
                 ctx.begin_frame(); ctx.scan_registration_device(d[k].data_ptr(), d[k].shape[0], 4); ctx.laser_odometry(want_pose=False)
         ms = _time_frames(ctx, torch, ext, frames, warm, fn)
         out[name] = {"scans_per_s": 1e3 / ms, "ms_per_sweep": ms, "points_per_sweep": int(np.mean([len(x) for x in scans])),
-                     "map_points": int(sum(synth.blob_counts(b).sum() for b in blobs)) if blobs else 0, "stages": "SR+LO+LM" if mapping else "SR+LO"}
+                     "map_points": int(sum(synth.blob_counts(b).sum() for b in blobs)) if blobs else 0, "stages": "SR+LO+LM" if mapping else "SR+LO",
+                     "mode": "online (no look-ahead)"}
         ctx.close()
 
     run("C1_vlp16", synth.World(1234, 0, 160.0), 0, pkg.Context(n_scans=16, minimum_range=0.3, line_res=0.2, plane_res=0.4, device=local_rank), None, True)
-    run("C2_hdl64_sr_lo", synth.World(1234, 1, 190.0), 1, pkg.Context(n_scans=64, minimum_range=5.0, line_res=0.4, plane_res=0.8, device=local_rank), None, False)
+    run("C2_hdl64_sr_lo", synth.World(1234, 1, 190.0), 1, pkg.Context(device=local_rank, **KW), None, False)
     w4 = synth.World(1234, 2, 190.0)
     blobs4 = (synth.cubes_blob(w4.plant(0, 0.4, seed=99), 0.4), synth.cubes_blob(w4.plant(1, 0.8, seed=98), 0.8))
     run("C4_os1_128", w4, 2, pkg.Context(n_scans=128, minimum_range=0.3, line_res=0.4, plane_res=0.8, device=local_rank), blobs4, True)
     return out
 
 
-def batched_sequences(pkg, torch, local_rank, cblob, sblob, nseq=4, frames=70, warm=10, first_seq=0, seq_stride=1):
-    """BASELINE config C5 on one GPU: `nseq` independent sequences, one context (4 streams + its helper thread) and
-    one host thread each, replayed concurrently.  A single sequence leaves the GPU mostly idle (the frame is a
-    chain of short dependent kernels), so concurrent sequences overlap almost freely."""
+def batched_sequences(pkg, torch, local_rank, cblob, sblob, nseq=4, frames=70, warm=10, first_seq=0, seq_stride=1, sync=None, step=1.0):
+    """BASELINE config C5 on one GPU: `nseq` independent sequences, one context (its streams + helper thread) and
+    one host thread each, replayed concurrently (device-resident sweeps, look-ahead registration, every frame returns
+    its pose).  A single sequence leaves the GPU mostly idle (the frame is a chain of short dependent kernels), so
+    concurrent sequences overlap almost freely.  sync(): called by the timing thread before the timed region (barrier
+    across ranks)."""
     seqs = []
+    world = pkg.synth.World(1234, 1, 190.0)
     for q in range(nseq):
-        world = pkg.synth.World(1234, 1, 190.0)
         sid = first_seq + q * seq_stride
-        traj = pkg.synth.trajectory(frames, seed=177 + sid)
-        scans = [world.scan(SENSOR, traj[k], 9000 + 7919 * sid + k) for k in range(frames)]
-        ctx = pkg.Context(n_scans=64, minimum_range=5.0, line_res=0.4, plane_res=0.8, device=local_rank)
+        traj = pkg.synth.trajectory(frames + 1, seed=177 + sid, step=step)
+        scans = _gen_scans(pkg, world, traj, [9000 + 7919 * sid + k for k in range(frames + 1)])
+        ctx = pkg.Context(device=local_rank, **KW)
         ctx.set("lm.cornerMap", cblob); ctx.set("lm.surfMap", sblob)
         seqs.append((ctx, [torch.from_numpy(x).cuda(local_rank) for x in scans]))
     lat = [[] for _ in range(nseq)]
     barrier = threading.Barrier(nseq + 1)
+    failed = []
 
     def worker(q):
-        ctx, d = seqs[q]
-        torch.cuda.set_device(local_rank)
-        pose = np.zeros(14)
-        for k in range(warm):
-            ctx.process_frame_device(d[k].data_ptr(), d[k].shape[0], 4, pose.ctypes.data)
-        ctx.synchronize()
-        barrier.wait(); barrier.wait()
-        for k in range(warm, frames):
-            t1 = time.perf_counter()
-            ctx.process_frame_device(d[k].data_ptr(), d[k].shape[0], 4, pose.ctypes.data)
-            lat[q].append(time.perf_counter() - t1)
-        ctx.synchronize()
-        barrier.wait()
+        try:
+            ctx, d = seqs[q]
+            torch.cuda.set_device(local_rank)
+            pose = np.zeros(14)
+            for k in range(warm):
+                ctx.prefetch_device(d[k + 1].data_ptr(), d[k + 1].shape[0], 4)
+                ctx.process_frame_device(d[k].data_ptr(), d[k].shape[0], 4, pose.ctypes.data)
+            ctx.synchronize()
+            barrier.wait(); barrier.wait()
+            for k in range(warm, frames):
+                t1 = time.perf_counter()
+                ctx.prefetch_device(d[k + 1].data_ptr(), d[k + 1].shape[0], 4)
+                ctx.process_frame_device(d[k].data_ptr(), d[k].shape[0], 4, pose.ctypes.data)
+                lat[q].append(time.perf_counter() - t1)
+            ctx.synchronize()
+            barrier.wait()
+        except Exception as e:  # never leave the timing thread waiting on a dead worker
+            failed.append(repr(e))
+            barrier.abort()
 
     th = [threading.Thread(target=worker, args=(q,)) for q in range(nseq)]
     for t in th: t.start()
     barrier.wait()
+    if sync: sync()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -262,6 +391,8 @@ def batched_sequences(pkg, torch, local_rank, cblob, sblob, nseq=4, frames=70, w
     barrier.wait()
     e1.record(); torch.cuda.synchronize()
     for t in th: t.join()
+    if failed:
+        raise RuntimeError("batched sequence worker failed: %s" % failed[0])
     ms = e0.elapsed_time(e1)
     for ctx, _ in seqs: ctx.close()
     allat = np.concatenate([np.array(x) for x in lat]) * 1e3
@@ -284,131 +415,194 @@ def cold_l2_frames(ctx, torch, local_rank, dscans, first, n=40):
         ctx.synchronize()
         e1.record(ext); torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1))
-    return {"ms_per_step_median": float(np.median(ms)), "frames": n, "flush": "512 MB device fill before every sweep; includes the map update and the speculative sub-map build"}
+    return {"ms_per_step_median": float(np.median(ms)), "frames": n, "flush": "512 MB device fill before every sweep; includes the map update and the search-structure update"}
+
+
+def _stats(x):
+    x = np.asarray(x, float)
+    return {"median": float(np.median(x)), "min": float(x.min()), "max": float(x.max()), "windows": int(len(x))}
 
 
 def run_ours(args, rank, world_size, local_rank):
     import torch
     pkg = importlib.import_module("vloam-noted_b200")
     pkg.load_lib()  # raises if the CUDA library is missing: there is no fallback
+    par = pkg.parallel
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world_size))
+    pinned_cores = None if args.no_pin else pin_rank_threads(local_rank, local_world)
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     dist = None
     if world_size > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=dev)
     K, W = args.steps, max(args.warmup, 3)
-    n_frames = W + K + 1
-    scans, traj, cblob, sblob = make_sequence(pkg, rank, n_frames)
+    R = args.repeats if args.repeats > 0 else max(3, min(25, 700 // max(K, 1)))
+    n_frames = W + K + 2
+    scans, traj, cblob, sblob = make_sequence(pkg, par.sequences_of_rank(world_size, rank, world_size)[0], n_frames)  # sequence r on rank r
     map_points = int(pkg.synth.blob_counts(cblob).sum() + pkg.synth.blob_counts(sblob).sum())
 
     def fresh():
-        ctx = pkg.Context(n_scans=64, minimum_range=5.0, line_res=0.4, plane_res=0.8, device=local_rank)
+        ctx = pkg.Context(device=local_rank, **KW)
         ctx.set("lm.cornerMap", cblob); ctx.set("lm.surfMap", sblob)
         return ctx
 
+    def barrier():
+        if dist: dist.barrier()
+        torch.cuda.synchronize()
+
     sampler = ClockSampler(local_rank)
-    if rank == 0 and os.environ.get("BENCH_SMI_MS", "50") != "0":
+    if rank == 0 and os.environ.get("BENCH_SMI_MS", "20") != "0":
         sampler.start()
-    # ---- leg 1: device-resident inputs (value) ------------------------------------------------
-    ctx = fresh()
-    ext = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
     dscans = [torch.from_numpy(s).cuda(local_rank) for s in scans]
+    pinned = [torch.from_numpy(s).pin_memory() for s in scans]
     torch.cuda.synchronize()
-    # a replay knows the next sweep: registering it lets its scan registration run underneath this sweep's odometry
-    # and mapping (vloam_b200_prefetch_scan_device); the sweep timed first was registered during the warm-up
-    for k in range(W + 1):
-        ctx.prefetch_device(dscans[k + 1].data_ptr(), dscans[k + 1].shape[0], 4)
-        ctx.process_frame_device(dscans[k].data_ptr(), dscans[k].shape[0], 4)
-    ctx.synchronize()
-    if dist: dist.barrier()
-    torch.cuda.synchronize()
-    l0 = ctx.kernel_launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(ext)
-    for k in range(W + 1, W + 1 + K):
-        if k + 1 < len(dscans): ctx.prefetch_device(dscans[k + 1].data_ptr(), dscans[k + 1].shape[0], 4)
-        ctx.process_frame_device(dscans[k].data_ptr(), dscans[k].shape[0], 4)
-    ctx.synchronize()  # the last frame's map update runs on a side stream: include it
-    e1.record(ext)
-    ctx.synchronize(); torch.cuda.synchronize()
-    if dist: dist.barrier()
-    dev_ms = e0.elapsed_time(e1)
-    launches = ctx.kernel_launches - l0
+    first = W + 1  # first timed sweep
+
+    # ---- leg 1: device-resident inputs (value); leg 2: end to end through the C ABI with host buffers (e2e) -----
+    # Every window: fresh context, W + 1 warm-up sweeps, barrier + synchronize, K timed sweeps, synchronize.
+    dev_ms, e2e_ms, launches, lat = [], [], [], []
+    poses = np.zeros((K, 14))
+    last_ctx = None
+    for r in range(R):
+        ctx = fresh()
+        ext = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+        # a replay knows the next sweep: registering it lets its scan registration run underneath this sweep's odometry
+        # and mapping (vloam_b200_prefetch_scan_device); the sweep timed first was registered during the warm-up
+        for k in range(first):
+            ctx.prefetch_device(dscans[k + 1].data_ptr(), dscans[k + 1].shape[0], 4)
+            ctx.process_frame_device(dscans[k].data_ptr(), dscans[k].shape[0], 4)
+        ctx.synchronize()
+        barrier()
+        l0 = ctx.kernel_launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.active = True
+        e0.record(ext)
+        for k in range(first, first + K):
+            ctx.prefetch_device(dscans[k + 1].data_ptr(), dscans[k + 1].shape[0], 4)
+            ctx.process_frame_device(dscans[k].data_ptr(), dscans[k].shape[0], 4)
+        ctx.synchronize()  # the last frame's map update runs on a side stream: include it
+        e1.record(ext)
+        ctx.synchronize(); torch.cuda.synchronize()
+        sampler.active = False
+        dev_ms.append(e0.elapsed_time(e1))
+        launches.append(ctx.kernel_launches - l0)
+        if r == R - 1: last_ctx = ctx
+        else: ctx.close()
+    for r in range(R):
+        ctx = fresh()
+        pose = np.zeros(14)
+        for k in range(first):
+            ctx.prefetch_ptr(pinned[k + 1].data_ptr(), pinned[k + 1].shape[0], 4)
+            ctx.process_frame_ptr(pinned[k].data_ptr(), pinned[k].shape[0], 4, pose.ctypes.data)
+        ctx.synchronize()
+        barrier()
+        sampler.active = True
+        t0 = time.perf_counter()
+        for i, k in enumerate(range(first, first + K)):
+            t1 = time.perf_counter()
+            ctx.prefetch_ptr(pinned[k + 1].data_ptr(), pinned[k + 1].shape[0], 4)  # upload + scan registration of the next sweep overlap this one
+            ctx.process_frame_ptr(pinned[k].data_ptr(), pinned[k].shape[0], 4, pose.ctypes.data)
+            lat.append(time.perf_counter() - t1)
+            poses[i] = pose
+        ctx.synchronize()  # like the device-timed leg: the last sweep's map update belongs to the window
+        e2e_ms.append((time.perf_counter() - t0) * 1e3)
+        sampler.active = False
+        ctx.close()
+    clocks = sampler.stop() if rank == 0 else None
+    h2d = float(np.mean([s.shape[0] * 16 for s in scans[first:first + K]]))
+    err = float(np.linalg.norm(poses[-1, 11:14] - traj[first + K - 1][:3]))
+    lat_ms = np.array(lat) * 1e3
+
     # dominant-kernel timing (CUDA events around that kernel's launches, on the launching stream)
-    roof, ktable = profile_dominant(ctx, dscans, W + 1, K, map_points)
+    ctx = last_ctx
+    roof, ktable = profile_dominant(ctx, dscans, first, K, map_points)
     extras = {}
     if world_size == 1 and not args.no_extras:
-        extras["cold_l2"] = cold_l2_frames(ctx, torch, local_rank, dscans, W + 1, min(K, 40))
+        extras["cold_l2"] = cold_l2_frames(ctx, torch, local_rank, dscans, first, min(K, 40))
     ctx.close()
+
+    # ---- online: one sweep at a time, nothing known about the next (what a ROS callback sees, MAIN.cpp:143) -------
+    online = None
+    if not args.no_extras:
+        ctx = fresh()
+        ext = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+        ms = _time_frames(ctx, torch, ext, first + K, first, lambda k: ctx.process_frame_device(dscans[k].data_ptr(), dscans[k].shape[0], 4))
+        ctx.close()
+        online = {"value": 1e3 / ms, "unit": "scans/s", "ms_per_step": ms}
+        for name, bufs in (("e2e", pinned), ("e2e_pageable", scans)):
+            ctx = fresh()
+            pose = np.zeros(14)
+            ptr = (lambda k: bufs[k].data_ptr()) if name == "e2e" else (lambda k: bufs[k].ctypes.data)
+            for k in range(first):
+                ctx.process_frame_ptr(ptr(k), bufs[k].shape[0], 4, pose.ctypes.data)
+            ctx.synchronize()
+            ol = []
+            t0 = time.perf_counter()
+            for k in range(first, first + K):
+                t1 = time.perf_counter()
+                ctx.process_frame_ptr(ptr(k), bufs[k].shape[0], 4, pose.ctypes.data)
+                ol.append(time.perf_counter() - t1)
+            ctx.synchronize()
+            online[name] = K / (time.perf_counter() - t0)
+            online["p50_ms_" + name] = float(np.median(ol) * 1e3)
+            ctx.close()
+        online["note"] = ("no vloam_b200_prefetch_scan: process_frame[_device] called with one sweep at a time; e2e = pinned host buffers, "
+                          "e2e_pageable = plain malloc'ed host buffers (a ROS / PCL caller); one %d-sweep window" % K)
+
+    # ---- BASELINE config C5 inside the default line: 8 sequences over the N GPUs, >= 200 sweeps each --------------
+    c5 = None
+    if not args.no_extras and not args.no_c5:
+        mine = par.sequences_of_rank(8, rank, world_size)
+        r5 = batched_sequences(pkg, torch, local_rank, cblob, sblob, nseq=len(mine), frames=args.c5_frames + 10, warm=10,
+                               first_seq=rank, seq_stride=world_size, sync=barrier, step=0.5)
+        t5 = np.array([r5["device_ms"], r5["p50_ms_per_frame"], r5["p99_ms_per_frame"], float(len(mine) * r5["frames_per_sequence"])])
+        _, a5 = par.gather_results(dist, np.zeros((1, 14)), t5, device=dev)
+        c5 = {"value": float(a5[:, 3].sum() / (a5[:, 0].max() * 1e-3)), "unit": "scans/s", "scaling": "strong", "sequences": 8,
+              "sequences_per_gpu": len(mine), "frames_per_sequence": args.c5_frames, "p50_ms_per_frame": float(a5[:, 1].max()),
+              "p99_ms_per_frame": float(a5[:, 2].max()), "per_rank_device_ms": [float(v) for v in a5[:, 0]],
+              "workload": "C5: 8 independent synthetic HDL-64E sequences (0.5 m per sweep so that %d sweeps stay inside the planted map) batched across %d GPU(s), "
+                          "sequence s on rank s mod N, device-resident sweeps, look-ahead registration, every frame returns its pose" % (args.c5_frames + 10, world_size)}
     if world_size == 1 and not args.no_extras:
-        extras["batched"] = batched_sequences(pkg, torch, local_rank, cblob, sblob)
         extras["workloads"] = other_workloads(pkg, torch, local_rank)
 
-    # ---- leg 2: end to end through the C ABI with host buffers (e2e) --------------------------
-    ctx = fresh()
-    pinned = [torch.from_numpy(s).pin_memory() for s in scans]
-    pose = np.zeros(14)
-    lat = []
-    for k in range(W + 1):
-        ctx.prefetch_ptr(pinned[k + 1].data_ptr(), pinned[k + 1].shape[0], 4)
-        ctx.process_frame_ptr(pinned[k].data_ptr(), pinned[k].shape[0], 4, pose.ctypes.data)
-    if dist: dist.barrier()
-    t0 = time.perf_counter()
-    poses = np.zeros((K, 14))
-    for i, k in enumerate(range(W + 1, W + 1 + K)):
-        t1 = time.perf_counter()
-        if k + 1 < len(pinned): ctx.prefetch_ptr(pinned[k + 1].data_ptr(), pinned[k + 1].shape[0], 4)  # upload + scan registration of the next sweep overlap this one
-        ctx.process_frame_ptr(pinned[k].data_ptr(), pinned[k].shape[0], 4, pose.ctypes.data)
-        lat.append(time.perf_counter() - t1)
-        poses[i] = pose
-    e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
-    ctx.close()
-    h2d = float(np.mean([s.shape[0] * 16 for s in scans[W + 1:W + 1 + K]]))
-
-    # trajectory sanity against the generator's ground truth (frame W+K)
-    err = float(np.linalg.norm(poses[-1, 11:14] - traj[W + K][:3]))
-
-    # ---- max over ranks; one collective: gather of poses + timings ----------------------------
-    lat_ms = np.array(lat) * 1e3
-    slow = [(int(i), round(float(lat_ms[i]), 2)) for i in np.argsort(-lat_ms)[:5]]  # frame index within the timed region, ms
-    times = torch.tensor([dev_ms, e2e_s * 1e3, float(np.median(lat)) * 1e3, err], dtype=torch.float64, device="cuda")
-    if dist:
-        allt = [torch.zeros_like(times) for _ in range(world_size)]
-        dist.all_gather(allt, times)
-        gp = [torch.zeros(K, 14, dtype=torch.float64, device="cuda") for _ in range(world_size)]
-        dist.all_gather(gp, torch.from_numpy(poses).cuda())
-        allt = torch.stack(allt).cpu().numpy()
-    else:
-        allt = times.cpu().numpy()[None]
+    # ---- one collective: gather of per-window timings + poses (parallel.gather_results) ---------------------------
+    mine_t = np.concatenate([dev_ms, e2e_ms, [float(np.median(lat_ms)), float(np.percentile(lat_ms, 99)), err]])
+    allp, allt = par.gather_results(dist, poses, mine_t, device=dev)  # poses [world, K, 14] of every rank's last window, timings [world, 2R + 3]
     if rank != 0:
         if dist: dist.destroy_process_group()
         return
-    dev_ms_max, e2e_ms_max = float(allt[:, 0].max()), float(allt[:, 1].max())
-    value = world_size * K / (dev_ms_max * 1e-3)
-    e2e_value = world_size * K / (e2e_ms_max * 1e-3)
-    cpu = cpu_baseline_sample(pkg, scans, cblob, sblob) if world_size == 1 and not args.no_cpu_baseline else None
+    dev_w, e2e_w = allt[:, :R].max(axis=0), allt[:, R:2 * R].max(axis=0)  # max over ranks inside every window
+    dev_med, e2e_med = float(np.median(dev_w)), float(np.median(e2e_w))
+    value = world_size * K / (dev_med * 1e-3)
+    e2e_value = world_size * K / (e2e_med * 1e-3)
+    cpu = parity = None
+    if world_size == 1 and not args.no_cpu_baseline:
+        cpu, parity = cpu_baseline_and_parity(pkg, torch, local_rank, scans, traj, cblob, sblob, min(args.cpu_frames, len(scans) - 2))
     line = {
         "metric": "scans/sec", "value": value, "unit": "scans/s", "n_gpus": world_size, "steps": K, "warmup": W,
-        "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
-        "data": "synthetic",
-        "config": {"workload": WORKLOAD, "map_points": map_points, "points_per_sweep": int(np.mean([len(s) for s in scans])),
-                   "l2": "every sweep is a new 1.9 MB input (the %d device-resident sweeps total > 3x L2); the persistent state (~16 MB sub-map + grids) "
-                         "stays L2-resident across sweeps as it does in deployment; `cold_l2` repeats the measurement with L2 flushed before every sweep" % len(scans),
-                   "parallelism": "independent sequences, one per GPU",
-                   "lookahead": "replay mode: the next sweep is registered with vloam_b200_prefetch_scan[_device] before each process_frame call, so its upload "
-                                "and scan registration run underneath the current sweep; every sweep's own H2D copy and pose read-back stay inside the timed region"},
-        "p50_ms_per_frame_e2e": float(np.max(allt[:, 2])), "p99_ms_per_frame_e2e": float(np.percentile(lat_ms, 99)),
-        "slowest_frames_e2e": slow, "final_pose_error_m": float(allt[:, 3].max()),
+        "ms_per_step": dev_med / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
+        "data": "synthetic", "config": bench_config(map_points, np.mean([len(s) for s in scans])),
+        "windows": {"repeats": R, "what": "every window = fresh context + %d warm-up sweeps + barrier/synchronize + %d timed sweeps + synchronize; value / e2e = median over windows of the max over ranks" % (first, K),
+                    "value_scans_per_s": {k: (world_size * K / (v * 1e-3) if k != "windows" else v) for k, v in _stats(dev_w).items()},
+                    "e2e_scans_per_s": {k: (world_size * K / (v * 1e-3) if k != "windows" else v) for k, v in _stats(e2e_w).items()},
+                    "per_rank_ms_per_step_median": [float(np.median(allt[q, :R])) / K for q in range(world_size)],
+                    "per_rank_e2e_ms_per_step_median": [float(np.median(allt[q, R:2 * R])) / K for q in range(world_size)]},
+        "p50_ms_per_frame_e2e": float(allt[:, 2 * R].max()), "p99_ms_per_frame_e2e": float(allt[:, 2 * R + 1].max()),
+        "final_pose_error_m": float(allt[:, 2 * R + 2].max()),
         "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 14 * 8 + 352 + 720},
-        "gpu_launches": int(launches), "clocks": clocks,
+        "gpu_launches": int(np.median(launches)), "clocks": clocks, "host": {"cores": host_cores(), "pinned_cores_rank0": pinned_cores},
+        "poses_gathered": list(allp.shape),
     }
+    if online: line["online"] = online
+    if c5: line["c5"] = c5
     line.update(extras)
     if roof:
-        roof["whole_frame"] = {"algorithmic_bytes": 58e6, "achieved_gbs": 58e6 / (dev_ms_max / K * 1e-3) / 1e9, "frac": 58e6 / (dev_ms_max / K * 1e-3) / 1e9 / roof["peak"]}
+        roof["whole_frame"] = {"algorithmic_bytes": 58e6, "achieved_gbs": 58e6 / (dev_med / K * 1e-3) / 1e9, "frac": 58e6 / (dev_med / K * 1e-3) / 1e9 / roof["peak"]}
         line["roofline"] = roof
     if ktable: line["kernels"] = ktable
     if cpu: line["cpu_baseline"] = cpu
+    if parity: line["parity"] = parity
     print(json.dumps(line), flush=True)
     if dist: dist.destroy_process_group()
 
@@ -440,7 +634,7 @@ def profile_dominant(ctx, dscans, first, K, map_points):
     rows.sort(key=lambda r: -r[2])
     peak, how = measured_peak()
     table = [{"kernel": nm, "launches_per_frame": cnt / n, "us_per_frame": 1e3 * ms / n, "share": ms / total,
-              "achieved_gbs": (byt / (ms * 1e-3) / 1e9) if byt > 0 and ms > 0 else None} for nm, cnt, ms, byt in rows[:12]]
+              "achieved_gbs": (byt / (ms * 1e-3) / 1e9) if byt > 0 and ms > 0 else None} for nm, cnt, ms, byt in rows[:14]]
     nm, cnt, ms, byt = rows[0]
     achieved = byt / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
     traffic = None
@@ -451,42 +645,40 @@ def profile_dominant(ctx, dscans, first, K, map_points):
             "peak_source": how, "launches_timed": cnt, "avg_us": 1e3 * ms / cnt, "algorithmic_bytes_per_launch": byt / cnt,
             "share_of_kernel_time": ms / total,
             "note": "the frame is dependency-latency bound (SURVEY 8d): ~60 MB of algorithmic traffic per sweep, i.e. ~9 us at the HBM peak, "
-                    "spread over ~60 short dependent kernels; per-kernel times here come from event pairs around every launch (serialised)"}
+                    "spread over short dependent kernels; per-kernel times here come from event pairs around every launch (serialised); "
+                    "achieved = SURVEY 8(d) algorithmic bytes of that kernel's term / its event-timed duration"}
     return roof, table
 
 
-
 def run_c5(args, rank, world_size, local_rank):
-    """BASELINE config C5: 8 independent HDL-64E sequences batched across the GPUs of one box (strong scaling): sequence
-    s runs on rank s mod G, each rank replays its 8/G sequences concurrently (one context + host thread each), poses and
-    timings are gathered with one NCCL all_gather.  `python bench.py --workload c5 [--frames F]` (F = 1000 in BASELINE;
-    the default keeps synthetic-sweep generation to a minute)."""
+    """BASELINE config C5 on its own (`--workload c5 [--frames F]`, F = 1000 in BASELINE): 8 independent HDL-64E sequences
+    batched across the GPUs of one box (strong scaling): sequence s runs on rank s mod G, each rank replays its 8/G
+    sequences concurrently (one context + host thread each), timings are gathered with one NCCL all_gather.  The default
+    bench line carries the same measurement at 200 sweeps per sequence in its `c5` block."""
     import torch
     pkg = importlib.import_module("vloam-noted_b200")
     pkg.load_lib()
+    par = pkg.parallel
     torch.cuda.set_device(local_rank)
     dist = None
     if world_size > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    total = 8
-    mine = len(range(rank, total, world_size))
+    mine = par.sequences_of_rank(8, rank, world_size)
     _, _, cblob, sblob = make_sequence(pkg, 0, 1)
-    if dist: dist.barrier()
-    r = batched_sequences(pkg, torch, local_rank, cblob, sblob, nseq=mine, frames=args.frames, warm=min(10, args.frames // 4),
-                          first_seq=rank, seq_stride=world_size)
-    t = torch.tensor([r["device_ms"], r["p50_ms_per_frame"], r["p99_ms_per_frame"], float(mine * r["frames_per_sequence"])], dtype=torch.float64, device="cuda")
-    if dist:
-        allt = [torch.zeros_like(t) for _ in range(world_size)]
-        dist.all_gather(allt, t)
-        allt = torch.stack(allt).cpu().numpy()
-    else:
-        allt = t.cpu().numpy()[None]
+
+    def barrier():
+        if dist: dist.barrier()
+        torch.cuda.synchronize()
+    r = batched_sequences(pkg, torch, local_rank, cblob, sblob, nseq=len(mine), frames=args.frames, warm=min(10, args.frames // 4),
+                          first_seq=rank, seq_stride=world_size, sync=barrier, step=1.0 if args.frames <= 120 else 0.25)
+    t = np.array([r["device_ms"], r["p50_ms_per_frame"], r["p99_ms_per_frame"], float(len(mine) * r["frames_per_sequence"])])
+    _, allt = par.gather_results(dist, np.zeros((1, 14)), t, device=torch.device("cuda", local_rank))
     if rank == 0:
         print(json.dumps({"metric": "scans/sec", "value": float(allt[:, 3].sum() / (allt[:, 0].max() * 1e-3)), "unit": "scans/s", "n_gpus": world_size,
                           "higher_is_better": True, "scaling": "strong", "dtype": "f32+f64", "data": "synthetic",
                           "config": {"workload": "C5: 8 independent synthetic HDL-64E sequences, %d timed sweeps each, batched across %d GPU(s)" % (r["frames_per_sequence"], world_size),
-                                     "sequences_per_gpu": mine},
+                                     "sequences_per_gpu": len(mine)},
                           "p50_ms_per_frame": float(allt[:, 1].max()), "p99_ms_per_frame": float(allt[:, 2].max())}), flush=True)
     if dist: dist.destroy_process_group()
 
@@ -494,11 +686,16 @@ def run_c5(args, rank, world_size, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--repeats", type=int, default=0, help="timed windows of --steps sweeps each (0 = min(25, 700 // steps), at least 3)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the cold-L2, batched-sequence and C1/C2/C4 legs")
+    ap.add_argument("--cpu-frames", type=int, default=25, help="sweeps of the cpu_baseline / parity sample (one more is run as warm-up)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the online, cold-L2, C5 and C1/C2/C4 legs")
+    ap.add_argument("--no-c5", action="store_true")
+    ap.add_argument("--c5-frames", type=int, default=200, help="timed sweeps per sequence of the c5 block")
+    ap.add_argument("--no-pin", action="store_true", help="do not pin this rank's threads to its slice of the host cores (N > 1)")
     ap.add_argument("--workload", default="c3", choices=["c3", "c5"], help="c3: the headline (default); c5: 8 sequences batched across the GPUs")
     ap.add_argument("--frames", type=int, default=110, help="sweeps per sequence for --workload c5")
     args = ap.parse_args()

@@ -12,9 +12,22 @@
  * records a message readable with vloam_b200_last_error().  Quaternions are
  * x,y,z,w (the order of para_q, laser_odometry.cpp:84-91).  Points are
  * 16-byte {x,y,z,intensity} floats (pcl::PointXYZI without its padding,
- * common.h:42).  One context = one CUDA stream = one sequence; contexts are not
- * thread-safe, like the reference objects.  All compute runs in hand-written
- * CUDA kernels on the context's stream; there is no CPU fallback.
+ * common.h:42).  One context = one sequence; contexts are not thread-safe, like
+ * the reference objects (different contexts may be driven from different
+ * threads).  All compute runs in hand-written CUDA kernels; there is no CPU
+ * fallback.
+ *
+ * Execution model.  A context owns several CUDA streams (the pose chain, side
+ * streams for the stack filters / search structures / map update / look-ahead
+ * scan registration) and one helper host thread that issues the map update.
+ * Calls queue work and return early where they can; the host blocks at
+ *   S1  after scan registration, for the feature counts (inside laser_odometry),
+ *   S2  after the mapping solve, for the pose and map sizes (inside
+ *       laser_mapping on every MAPPED frame, with or without output pointers),
+ * and inside every getter.  A frame on which mapping is skipped
+ * (mapping_skip_frame > 1) with NULL output pointers returns without S2; the
+ * device-side ordering between frames never depends on those host waits.
+ * vloam_b200_synchronize() drains everything, including the helper thread.
  */
 #ifndef VLOAM_B200_H_
 #define VLOAM_B200_H_
@@ -74,9 +87,11 @@ int vloam_b200_scan_registration(vloam_b200_ctx* c, const float* xyz, int n, int
 /* Optional look-ahead for replays: register the NEXT sweep (host pointer -- pinned for an asynchronous copy -- or
  * device pointer).  Its scan registration is queued on a side stream from inside the processing of the current
  * sweep and runs underneath that sweep's odometry and mapping; the following scan_registration / process_frame
- * call with the same (pointer, n, stride) finds the work done, any other call ignores it.  The buffer must stay
- * unchanged until then.  Results are bit-identical with or without it.  No reference counterpart: the bag player
- * hands over one sweep at a time (MAIN.cpp:143). */
+ * call with the same (pointer, n, stride) finds the work done, any other call ignores it.  CONTRACT: adoption is keyed
+ * on (pointer, n, stride) only -- the buffer must stay valid AND UNCHANGED from this call until the scan_registration /
+ * process_frame call that consumes it returns; a caller that refills one buffer in place must not register it.
+ * Results are bit-identical with or without the look-ahead.  No reference counterpart: the bag player hands over one
+ * sweep at a time (MAIN.cpp:143). */
 int vloam_b200_prefetch_scan(vloam_b200_ctx* c, const float* xyz, int n, int stride);
 int vloam_b200_prefetch_scan_device(vloam_b200_ctx* c, const float* d_xyz, int n, int stride);
 /* Same, but xyz is a DEVICE pointer already resident in HBM. */
@@ -109,14 +124,15 @@ int vloam_b200_register_full_cloud(vloam_b200_ctx* c, float* out_xyzi, int cap_p
 
 /* MAIN.cpp:143-144, 186-190 in one call: begin_frame, scan_registration,
  * laser_odometry, laser_mapping.  pose_out (may be NULL): 14 doubles
- * {odom q[4], odom t[3], mapped q[4], mapped t[3]}.  Synchronises the stream
- * only when pose_out is non-NULL. */
+ * {odom q[4], odom t[3], mapped q[4], mapped t[3]}.  On a mapped frame the call
+ * returns after sync point S2 (the pose is final; the map update continues on a
+ * side stream); on a skipped frame it blocks only when pose_out is non-NULL. */
 int vloam_b200_process_frame(vloam_b200_ctx* c, const float* xyz, int n, int stride, double* pose_out);
 int vloam_b200_process_frame_device(vloam_b200_ctx* c, const float* d_xyz, int n, int stride, double* pose_out);
 
-/* Block until all work queued on the context's stream has finished. */
+/* Block until all work queued on any of the context's streams (and by its helper thread) has finished. */
 int vloam_b200_synchronize(vloam_b200_ctx* c);
-/* The context's cudaStream_t (as void*), for timing with CUDA events. */
+/* The context's main (pose-chain) cudaStream_t (as void*), for timing with CUDA events after vloam_b200_synchronize. */
 void* vloam_b200_stream(vloam_b200_ctx* c);
 /* Number of kernels this context has launched since creation. */
 long long vloam_b200_kernel_launches(const vloam_b200_ctx* c);
@@ -163,6 +179,13 @@ int vloam_b200_evaluate(vloam_b200_ctx* c, const double* factors, int nf, const 
                         double* g);
 /* ceres::Solve as configured by the reference on the same factor list. */
 int vloam_b200_solve(vloam_b200_ctx* c, const double* factors, int nf, double* x, double* log4);
+
+/* The two neighbourhood fits of solveMapping on caller-supplied five-point sets (float32[n][5][3], the map
+ * neighbours as the kNN returns them): kind 0 = 3x3 covariance + SelfAdjointEigenSolver line test, accepted when
+ * lambda_2 > 3 lambda_1 (LM.cpp:559-603); kind 1 = colPivHouseholderQr plane with the 0.2 m check (LM.cpp:637-680).
+ * ok[n]: accept flags; params[n][6]: {a[3], b[3]} of the LidarEdgeFactor / {unit normal[3], d, 0, 0} of the
+ * LidarPlaneNormFactor (zeros when rejected).  Same device code as the mapping stage. */
+int vloam_b200_fit(vloam_b200_ctx* c, const float* near_xyz, int n, int kind, int* ok, double* params);
 
 #ifdef __cplusplus
 }

@@ -110,6 +110,10 @@ int vloam_oracle_get(void* h, const char* name, void* out, long cap) {
     double v[14]; memcpy(v, p->lm.parameters, 56); memcpy(v + 7, p->lm.q_wmap_wodom, 32); memcpy(v + 11, p->lm.t_wmap_wodom, 24);
     return put(v, sizeof v, out, cap);
   }
+  if (n == "lm.poseHighFreq") {  // q_w_curr_highfreq[4] t_w_curr_highfreq[3] (LM.cpp:197-201: the pose of a skipped frame)
+    double v[7]; memcpy(v, p->lm.q_hf, 32); memcpy(v + 4, p->lm.t_hf, 24);
+    return put(v, sizeof v, out, cap);
+  }
   if (n == "lm.state") { int v[5] = {p->lm.cenW, p->lm.cenH, p->lm.cenD, p->lm.frameCount, p->lm.optimized ? 1 : 0}; return put(v, sizeof v, out, cap); }
   if (n == "lm.fullResRegistered") {  // LM.cpp:901-905: laserCloudFullRes through pointAssociateToMap (publish path)
     Cloud reg = p->lo.fullRes;
@@ -190,6 +194,15 @@ int vloam_oracle_knn(const float* cloud, int n, const float* queries, int nq, in
 }
 void vloam_oracle_sym_eig3(const double* A, double* evals, double* evecs) { sym_eig3(A, evals, evecs); }
 int vloam_oracle_qr_solve_5x3(const double* A, const double* b, double* x) { return colpiv_qr_solve_5x3(A, b, x) ? 1 : 0; }
+// n five-point sets (float32[n][5][3]); kind 0: PCA line fit, 1: plane fit.  ok[n], params[n][6] = {a, b} / {normal, d, 0, 0}
+void vloam_oracle_fit(const float* near, int n, int kind, int* ok, double* params) {
+  for (int i = 0; i < n; ++i) {
+    double* o = params + (size_t)i * 6;
+    for (int k = 0; k < 6; ++k) o[k] = 0;
+    if (kind == 0) ok[i] = fit_line5(near + (size_t)i * 15, o, o + 3) ? 1 : 0;
+    else { double d = 0; ok[i] = fit_plane5(near + (size_t)i * 15, o, &d) ? 1 : 0; if (ok[i]) o[3] = d; }
+  }
+}
 // factors: nf x 10 doubles {type, p[3], a[3], b[3]}
 static std::vector<Factor> unpack(const double* f, int nf) {
   std::vector<Factor> fs(nf);

@@ -203,45 +203,167 @@ int kd_knn(const KdTree* t, const Cloud& c, const P4& q, int k, int* idx, float*
 }
 
 // ---------------------------------------------------------------------------
-// Eigen::SelfAdjointEigenSolver<Matrix3d> contract (LM.cpp:583-591): eigenvalues
-// ascending, unit eigenvectors in columns, sign unspecified.  Restated with the
-// cyclic Jacobi method (same contract; agrees with Eigen's tridiagonal QR to a
-// few ulp -- the departure is documented in DESIGN.md).
+// Eigen::SelfAdjointEigenSolver<Matrix3d>::compute (LM.cpp:583-591), restated as Eigen 3.3 runs it
+// (Eigen/src/Eigenvalues/SelfAdjointEigenSolver.h: compute() -> tridiagonalization_inplace (the closed
+// 3x3 special case of Tridiagonalization.h) -> computeFromTridiagonal_impl: implicit symmetric QR steps
+// with Wilkinson shift and Givens rotations (tridiagonal_qr_step, Jacobi.h makeGivens), deflation test
+// |e_i| <= eps * sqrt(|d_i| + |d_i+1|), selection sort of the eigenvalues, ascending):
+//   1. scale = max |a_ij| (1 if the matrix is zero); work on A / scale; eigenvalues are scaled back.
+//   2. one Householder-like reflection zeroes a(2,0).
+//   3. QR steps on the largest unreduced trailing block until every sub-diagonal entry deflates
+//      (at most 30 * n steps).
+// Eigenvalues ascending, unit eigenvectors in columns, sign unspecified by the contract.  The CUDA
+// path uses a cyclic Jacobi solver instead: this routine is its INDEPENDENT
+// witness -- a different algorithm, so agreement (accept flags, factors to ~1e-15) is evidence and
+// not an identity.  Eigen itself is not in this container: restated from its published source.
 // ---------------------------------------------------------------------------
+namespace {
+struct Givens { double c, s; };
+inline Givens make_givens(double p, double q) {  // Eigen JacobiRotation<double>::makeGivens (real case)
+  Givens g;
+  if (q == 0.0) { g.c = p < 0.0 ? -1.0 : 1.0; g.s = 0.0; }
+  else if (p == 0.0) { g.c = 0.0; g.s = q < 0.0 ? 1.0 : -1.0; }
+  else if (fabs(p) > fabs(q)) {
+    const double t = q / p;
+    double u = sqrt(1.0 + t * t);
+    if (p < 0.0) u = -u;
+    g.c = 1.0 / u; g.s = -t * g.c;
+  } else {
+    const double t = p / q;
+    double u = sqrt(1.0 + t * t);
+    if (q < 0.0) u = -u;
+    g.s = -1.0 / u; g.c = -t * g.s;
+  }
+  return g;
+}
+// one implicit QR step on the unreduced block [start, end] of the tridiagonal (diag, subdiag); Q <- Q G_k
+inline void tridiagonal_qr_step(double* diag, double* subdiag, int start, int end, double Q[3][3]) {
+  const double td = (diag[end - 1] - diag[end]) * 0.5;
+  const double e = subdiag[end - 1];
+  double mu = diag[end];
+  if (td == 0.0) mu -= fabs(e);
+  else if (e != 0.0) {
+    const double e2 = e * e;
+    const double h = hypot(td, e);
+    if (e2 == 0.0) mu -= e / ((td + (td > 0.0 ? h : -h)) / e);
+    else mu -= e2 / (td + (td > 0.0 ? h : -h));
+  }
+  double x = diag[start] - mu;
+  double z = subdiag[start];
+  for (int k = start; k < end && z != 0.0; ++k) {
+    const Givens r = make_givens(x, z);
+    const double sdk = r.s * diag[k] + r.c * subdiag[k];
+    const double dkp1 = r.s * subdiag[k] + r.c * diag[k + 1];
+    diag[k] = r.c * (r.c * diag[k] - r.s * subdiag[k]) - r.s * (r.c * subdiag[k] - r.s * diag[k + 1]);
+    diag[k + 1] = r.s * sdk + r.c * dkp1;
+    subdiag[k] = r.c * sdk - r.s * dkp1;
+    if (k > start) subdiag[k - 1] = r.c * subdiag[k - 1] - r.s * z;
+    x = subdiag[k];
+    if (k < end - 1) { z = -r.s * subdiag[k + 1]; subdiag[k + 1] = r.c * subdiag[k + 1]; }
+    for (int i = 0; i < 3; ++i) {  // applyOnTheRight(k, k + 1, rot)
+      const double xi = Q[i][k], yi = Q[i][k + 1];
+      Q[i][k] = r.c * xi - r.s * yi;
+      Q[i][k + 1] = r.s * xi + r.c * yi;
+    }
+  }
+}
+}  // namespace
+
 void sym_eig3(const double Ain[9], double evals[3], double evecs[9]) {
-  double a[3][3], v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  // (Eigen reads the lower triangle only)
+  double m[3][3];
+  double scale = 0.0;
   for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) a[i][j] = Ain[i * 3 + j];
-  for (int sweep = 0; sweep < 30; ++sweep) {
-    const double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
-    if (off == 0.0) break;
-    for (int p = 0; p < 2; ++p)
-      for (int q = p + 1; q < 3; ++q) {
-        if (a[p][q] == 0.0) continue;
-        const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
-        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-        const double apq = a[p][q];
-        a[p][p] -= t * apq;
-        a[q][q] += t * apq;
-        a[p][q] = a[q][p] = 0.0;
-        const int r = 3 - p - q;
-        const double arp = a[r][p], arq = a[r][q];
-        a[r][p] = a[p][r] = c * arp - s * arq;
-        a[r][q] = a[q][r] = s * arp + c * arq;
-        for (int k = 0; k < 3; ++k) {
-          const double vkp = v[k][p], vkq = v[k][q];
-          v[k][p] = c * vkp - s * vkq;
-          v[k][q] = s * vkp + c * vkq;
-        }
+    for (int j = 0; j <= i; ++j) scale = fmax(scale, fabs(Ain[i * 3 + j]));
+  if (scale == 0.0) scale = 1.0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) m[i][j] = Ain[(i >= j ? i * 3 + j : j * 3 + i)] / scale;
+  double diag[3], subdiag[2], Q[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  // tridiagonalization_inplace_selector<MatrixType, 3, false>
+  diag[0] = m[0][0];
+  const double v1norm2 = m[2][0] * m[2][0];
+  if (v1norm2 <= DBL_MIN) {
+    diag[1] = m[1][1]; diag[2] = m[2][2];
+    subdiag[0] = m[1][0]; subdiag[1] = m[2][1];
+  } else {
+    const double beta = sqrt(m[1][0] * m[1][0] + v1norm2);
+    const double invBeta = 1.0 / beta;
+    const double m01 = m[1][0] * invBeta, m02 = m[2][0] * invBeta;
+    const double q = 2.0 * m01 * m[2][1] + m02 * (m[2][2] - m[1][1]);
+    diag[1] = m[1][1] + m02 * q;
+    diag[2] = m[2][2] - m02 * q;
+    subdiag[0] = beta;
+    subdiag[1] = m[2][1] - m01 * q;
+    Q[1][1] = m01; Q[1][2] = m02; Q[2][1] = m02; Q[2][2] = -m01;
+  }
+  // computeFromTridiagonal_impl
+  const int n = 3, maxIterations = 30;
+  int end = n - 1, start = 0, iter = 0;
+  const double considerAsZero = DBL_MIN, precision_inv = 1.0 / DBL_EPSILON;
+  while (end > 0) {
+    for (int i = start; i < end; ++i) {
+      if (fabs(subdiag[i]) < considerAsZero) subdiag[i] = 0.0;
+      else {
+        const double scaled = precision_inv * subdiag[i];
+        if (scaled * scaled <= fabs(diag[i]) + fabs(diag[i + 1])) subdiag[i] = 0.0;
       }
+    }
+    while (end > 0 && subdiag[end - 1] == 0.0) end--;
+    if (end <= 0) break;
+    if (++iter > maxIterations * n) break;
+    start = end - 1;
+    while (start > 0 && subdiag[start - 1] != 0.0) start--;
+    tridiagonal_qr_step(diag, subdiag, start, end, Q);
   }
-  int ord[3] = {0, 1, 2};
-  std::sort(ord, ord + 3, [&](int i, int j) { return a[i][i] < a[j][j]; });
+  for (int i = 0; i < n - 1; ++i) {  // selection sort, ascending
+    int k = 0;
+    for (int j = 1; j < n - i; ++j) if (diag[i + j] < diag[i + k]) k = j;
+    if (k > 0) {
+      std::swap(diag[i], diag[i + k]);
+      for (int r = 0; r < 3; ++r) std::swap(Q[r][i], Q[r][i + k]);
+    }
+  }
   for (int c = 0; c < 3; ++c) {
-    evals[c] = a[ord[c]][ord[c]];
-    for (int r = 0; r < 3; ++r) evecs[r * 3 + c] = v[r][ord[c]];
+    evals[c] = diag[c] * scale;
+    for (int r = 0; r < 3; ++r) evecs[r * 3 + c] = Q[r][c];
   }
+}
+
+// The two fits of LaserMapping::solveMapping on five f32 neighbours (LM.cpp:559-603, 637-680), callable on their own
+// (vloam_oracle_fit): returns the accept flag and writes the factor parameters {a[3], b[3]} (edge: the two synthetic
+// line points; plane: unit normal and {d, 0, 0}).
+bool fit_line5(const float near_f[15], double a[3], double b[3]) {
+  double c[3] = {0, 0, 0}, near[5][3];
+  for (int j = 0; j < 5; j++) {
+    for (int k = 0; k < 3; ++k) { near[j][k] = near_f[j * 3 + k]; c[k] = c[k] + near[j][k]; }
+  }
+  for (int k = 0; k < 3; ++k) c[k] = c[k] / 5.0;
+  double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int j = 0; j < 5; j++) {
+    const double z[3] = {near[j][0] - c[0], near[j][1] - c[1], near[j][2] - c[2]};
+    for (int p = 0; p < 3; ++p) for (int q = 0; q < 3; ++q) cov[p * 3 + q] = cov[p * 3 + q] + z[p] * z[q];
+  }
+  double ev[3], evec[9]; sym_eig3(cov, ev, evec);
+  if (!(ev[2] > 3 * ev[1])) return false;
+  for (int k = 0; k < 3; ++k) {
+    const double u = evec[k * 3 + 2];
+    a[k] = 0.1 * u + c[k];
+    b[k] = -0.1 * u + c[k];
+  }
+  return true;
+}
+bool fit_plane5(const float near_f[15], double nrm[3], double* d) {
+  double A[15], B[5] = {-1, -1, -1, -1, -1};
+  for (int j = 0; j < 15; j++) A[j] = near_f[j];
+  double norm[3]; colpiv_qr_solve_5x3(A, B, norm);
+  const double nn = sqrt(norm[0] * norm[0] + norm[1] * norm[1] + norm[2] * norm[2]);
+  const double negative_OA_dot_norm = 1 / nn;
+  if (nn > 0) { norm[0] /= nn; norm[1] /= nn; norm[2] /= nn; }  // Eigen normalize()
+  for (int j = 0; j < 5; j++)
+    if (fabs(norm[0] * A[j * 3] + norm[1] * A[j * 3 + 1] + norm[2] * A[j * 3 + 2] + negative_OA_dot_norm) > 0.2) return false;
+  for (int k = 0; k < 3; ++k) nrm[k] = norm[k];
+  *d = negative_OA_dot_norm;
+  return true;
 }
 
 // ---------------------------------------------------------------------------

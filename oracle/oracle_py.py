@@ -37,6 +37,7 @@ def lib():
         L.vloam_oracle_knn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.vloam_oracle_sym_eig3.argtypes = [ctypes.c_void_p] * 3
         L.vloam_oracle_qr_solve_5x3.argtypes = [ctypes.c_void_p] * 3
+        L.vloam_oracle_fit.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.vloam_oracle_ceres_solve.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.vloam_oracle_evaluate.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 4
         L.vloam_oracle_quat.argtypes = [ctypes.c_void_p] * 6
@@ -45,7 +46,7 @@ def lib():
 
 
 _DTYPES = {"sr.curvature": np.float32, "sr.label": np.int32, "sr.scanStartInd": np.int32, "sr.scanEndInd": np.int32,
-           "lo.pose": np.float64, "lm.pose": np.float64, "lm.state": np.int32, "lm.validInd": np.int32,
+           "lo.pose": np.float64, "lm.pose": np.float64, "lm.poseHighFreq": np.float64, "lm.state": np.int32, "lm.validInd": np.int32,
            "lo.costs": np.float64, "lm.costs": np.float64, "timing": np.float64}
 
 
@@ -163,6 +164,15 @@ def qr_solve_5x3(A, b):
     x = np.empty(3)
     ok = lib().vloam_oracle_qr_solve_5x3(A.ctypes.data, b.ctypes.data, x.ctypes.data)
     return x, bool(ok)
+
+
+def fit(near, kind):
+    """LM.cpp:559-603 (kind 0) / 637-680 (kind 1) on n five-point sets float32[n,5,3] -> (ok[n], params[n,6])."""
+    a = np.ascontiguousarray(near, np.float32).reshape(-1, 15)
+    ok = np.zeros(len(a), np.int32)
+    prm = np.zeros((len(a), 6))
+    lib().vloam_oracle_fit(a.ctypes.data, len(a), kind, ok.ctypes.data, prm.ctypes.data)
+    return ok, prm
 
 
 def ceres_solve(factors, x):

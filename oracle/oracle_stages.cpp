@@ -385,26 +385,11 @@ void LaserMapping::associate(const double pose[7], std::vector<Factor>* fs, int 
     if (found < 5) continue;
     for (int j = 0; j < 5; ++j) { cidx[(size_t)i * 5 + j] = ind[j]; cd2[(size_t)i * 5 + j] = d2[j]; }
     if (d2[4] < 1.0) {
-      double c[3] = {0, 0, 0}, near[5][3];
-      for (int j = 0; j < 5; j++) {
-        near[j][0] = cornerFromMap[ind[j]].x; near[j][1] = cornerFromMap[ind[j]].y; near[j][2] = cornerFromMap[ind[j]].z;
-        for (int k = 0; k < 3; ++k) c[k] = c[k] + near[j][k];
-      }
-      for (int k = 0; k < 3; ++k) c[k] = c[k] / 5.0;
-      double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-      for (int j = 0; j < 5; j++) {
-        const double z[3] = {near[j][0] - c[0], near[j][1] - c[1], near[j][2] - c[2]};
-        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) cov[a * 3 + b] = cov[a * 3 + b] + z[a] * z[b];
-      }
-      double ev[3], evec[9]; sym_eig3(cov, ev, evec);
-      if (ev[2] > 3 * ev[1]) {
-        Factor f; f.type = 0;
+      float near[15];
+      for (int j = 0; j < 5; j++) { near[j * 3] = cornerFromMap[ind[j]].x; near[j * 3 + 1] = cornerFromMap[ind[j]].y; near[j * 3 + 2] = cornerFromMap[ind[j]].z; }
+      Factor f; f.type = 0;
+      if (fit_line5(near, f.a, f.b)) {  // LM.cpp:559-603
         f.p[0] = pointOri.x; f.p[1] = pointOri.y; f.p[2] = pointOri.z;
-        for (int k = 0; k < 3; ++k) {
-          const double u = evec[k * 3 + 2];
-          f.a[k] = 0.1 * u + c[k];
-          f.b[k] = -0.1 * u + c[k];
-        }
         if (fs) fs->push_back(f);
         dbg_cok[pass][i] = 1;
       }
@@ -418,21 +403,13 @@ void LaserMapping::associate(const double pose[7], std::vector<Factor>* fs, int 
     if (found < 5) continue;
     for (int j = 0; j < 5; ++j) { sidx[(size_t)i * 5 + j] = ind[j]; sd2[(size_t)i * 5 + j] = d2[j]; }
     if (d2[4] < 1.0) {
-      double A[15], B[5] = {-1, -1, -1, -1, -1};
-      for (int j = 0; j < 5; j++) { A[j * 3] = surfFromMap[ind[j]].x; A[j * 3 + 1] = surfFromMap[ind[j]].y; A[j * 3 + 2] = surfFromMap[ind[j]].z; }
-      double norm[3]; colpiv_qr_solve_5x3(A, B, norm);
-      const double nn = sqrt(norm[0] * norm[0] + norm[1] * norm[1] + norm[2] * norm[2]);
-      const double negative_OA_dot_norm = 1 / nn;
-      if (nn > 0) { norm[0] /= nn; norm[1] /= nn; norm[2] /= nn; }  // Eigen normalize()
-      bool planeValid = true;
-      for (int j = 0; j < 5; j++) {
-        if (fabs(norm[0] * A[j * 3] + norm[1] * A[j * 3 + 1] + norm[2] * A[j * 3 + 2] + negative_OA_dot_norm) > 0.2) { planeValid = false; break; }
-      }
-      if (planeValid) {
-        Factor f; f.type = 2;
+      float near[15];
+      for (int j = 0; j < 5; j++) { near[j * 3] = surfFromMap[ind[j]].x; near[j * 3 + 1] = surfFromMap[ind[j]].y; near[j * 3 + 2] = surfFromMap[ind[j]].z; }
+      Factor f; f.type = 2;
+      double d = 0;
+      if (fit_plane5(near, f.a, &d)) {  // LM.cpp:637-680
         f.p[0] = pointOri.x; f.p[1] = pointOri.y; f.p[2] = pointOri.z;
-        for (int k = 0; k < 3; ++k) { f.a[k] = norm[k]; f.b[k] = 0; }
-        f.b[0] = negative_OA_dot_norm;
+        f.b[0] = d; f.b[1] = 0; f.b[2] = 0;
         if (fs) fs->push_back(f);
         dbg_sok[pass][i] = 1;
       }

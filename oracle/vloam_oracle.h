@@ -53,6 +53,8 @@ int brute_knn(const Cloud& c, const P4& q, int k, int* idx, float* d2);
 
 void sym_eig3(const double A[9], double evals[3], double evecs[9]);  // ascending, columns
 bool colpiv_qr_solve_5x3(const double A[15], const double b[5], double x[3]);
+bool fit_line5(const float near[15], double a[3], double b[3]);     // LM.cpp:559-603 on five neighbours
+bool fit_plane5(const float near[15], double nrm[3], double* d);    // LM.cpp:637-680
 
 // ---- Ceres restatement -----------------------------------------------------
 struct Factor {

@@ -217,3 +217,61 @@ def test_ceres_solve_no_factors_leaves_x(op):
     x0 = np.array([0.1, 0.2, 0.3, 0.9, 1, 2, 3], np.float64)
     x, log = op.ceres_solve(np.zeros((0, 10)), x0)
     assert (x == x0).all()
+
+
+def _witness(gold, prefix):
+    return {k[len(prefix):]: v for k, v in gold.items() if k.startswith(prefix) and k not in (prefix + "sets", prefix + "family")}
+
+
+def test_fits_match_numpy_fixture(op):
+    """tests/golden/fit_sets.npz (numpy eigh / lstsq answers, generator tests/make_golden_fit.py): the oracle's restated
+    Eigen algorithms -- tridiagonal QR eigen-solver, column-pivoted Householder -- against an independent LAPACK witness on
+    4096 five-point sets per kind, degenerate families included; and the witness fields regenerate identically."""
+    import os
+    import fit_checks as fc
+    import make_golden_fit as mg
+    gold = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fit_sets.npz")))
+    sets, _ = mg.fit_sets(4096, 4101)
+    assert (sets == gold["line_sets"]).all(), "the committed fixture is not what its generator makes"
+    ok, prm = op.fit(gold["line_sets"], 0)
+    r = fc.check_line(ok, prm, _witness(gold, "line_"))
+    assert r["accepted"] > 2000 and r["decided"] > 3000
+    ok, prm = op.fit(gold["plane_sets"], 1)
+    r = fc.check_plane(ok, prm, _witness(gold, "plane_"))
+    assert r["accepted"] > 2000
+    # degenerate families never produce NaN parameters or accepted garbage
+    assert np.isfinite(prm).all()
+
+
+def corridor_factors(rng, pose_q, pose_t, n, kind):
+    """Ill-conditioned mapping problems: `corridor` = plane-norm factors on two walls and the floor only (translation along
+    the corridor axis unobserved but for a few far-away, nearly parallel planes); `single_plane` = one ground plane (x, y,
+    yaw unobserved but for rounding-level tilt).  cond(J^T J) >= 1e8 at the solution."""
+    from scipy.spatial.transform import Rotation as R
+    Rm = R.from_quat(pose_q).as_matrix()
+    f = []
+    for i in range(n):
+        p = np.array([rng.uniform(-40, 40), rng.uniform(-3, 3), rng.uniform(-1.5, 2.0)])
+        w = Rm @ p + pose_t
+        if kind == "corridor":
+            nrm = [np.array([0.0, 1.0, 0.0]), np.array([0.0, -1.0, 0.0]), np.array([0.0, 0.0, 1.0])][i % 3]
+            nrm = nrm + np.array([1e-5 * rng.randn(), 0.0, 0.0])   # walls are parallel to x to within 1e-5 rad
+        else:
+            nrm = np.array([1e-6 * rng.randn(), 1e-6 * rng.randn(), 1.0])
+        nrm = nrm / np.linalg.norm(nrm)
+        f.append([2, *p, *nrm, -float(nrm @ w) + 0.01 * rng.randn(), 0, 0])
+    return np.array(f, np.float64)
+
+
+def test_corridor_problems_are_ill_conditioned(op):
+    from scipy.spatial.transform import Rotation as R
+    rng = np.random.RandomState(31)
+    q = R.from_euler("xyz", [0.01, -0.02, 0.03]).as_quat()
+    t = np.array([0.8, -0.1, 0.05])
+    for kind in ("corridor", "single_plane"):
+        f = corridor_factors(rng, q, t, 900, kind)
+        _, H, _ = op.evaluate(f, np.concatenate([q, t]))
+        ev = np.linalg.eigvalsh(H)
+        assert ev[-1] / max(ev[0], 1e-300) >= 1e8, (kind, ev)
+        x, log = op.ceres_solve(f, np.concatenate([q, t + [0.05, 0.02, -0.03]]))
+        assert np.isfinite(x).all() and log[3] <= log[2]

@@ -10,3 +10,4 @@ from .api import (Context, Params, VloamError, load_lib, EXPORTS, ScanRegistrati
                   CLOUD_CORNER_LAST, CLOUD_SURF_LAST)
 from . import synth  # noqa: F401
 from . import kitti_io  # noqa: F401
+from . import parallel  # noqa: F401

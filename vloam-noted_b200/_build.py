@@ -26,12 +26,26 @@ def _stale(target, sources):
 
 
 def build_cuda(force=False, verbose=False):
+    """One nvcc -c per source file, in parallel, into build/ (git-ignored), then one link step."""
+    from concurrent.futures import ThreadPoolExecutor
     srcs = [os.path.join(CSRC, s) for s in CU_SOURCES]
-    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh", ".hpp"))]
-    deps.append(os.path.join(ROOT, "include", "vloam_b200.h"))
-    if force or _stale(LIB, deps):
-        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
-        subprocess.run(cmd, check=True)
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh", ".hpp"))]
+    hdrs.append(os.path.join(ROOT, "include", "vloam_b200.h"))
+    hdrs.append(os.path.abspath(__file__))
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    objs = [os.path.join(objdir, os.path.basename(s)[:-3] + ".o") for s in srcs]
+
+    def compile_one(i):
+        if force or _stale(objs[i], [srcs[i]] + hdrs):
+            subprocess.run(["nvcc"] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", objs[i], srcs[i]], check=True)
+            return True
+        return False
+    with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
+        rebuilt = list(ex.map(compile_one, range(len(srcs))))
+    if any(rebuilt) or _stale(LIB, objs):
+        subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", LIB] + objs, check=True)
     return LIB
 
 

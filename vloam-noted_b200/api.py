@@ -15,7 +15,7 @@ EXPORTS = [
     "vloam_b200_scan_registration", "vloam_b200_prefetch_scan", "vloam_b200_prefetch_scan_device", "vloam_b200_scan_registration_device", "vloam_b200_get_cloud", "vloam_b200_laser_odometry",
     "vloam_b200_laser_mapping", "vloam_b200_process_frame", "vloam_b200_process_frame_device", "vloam_b200_synchronize",
     "vloam_b200_stream", "vloam_b200_kernel_launches", "vloam_b200_set_timing", "vloam_b200_stage_ms", "vloam_b200_debug_get",
-    "vloam_b200_debug_set", "vloam_b200_profile_kernel", "vloam_b200_profile_result", "vloam_b200_profile_table", "vloam_b200_profile_timeline", "vloam_b200_register_full_cloud", "vloam_b200_lo_associate", "vloam_b200_voxel_grid", "vloam_b200_evaluate", "vloam_b200_solve",
+    "vloam_b200_debug_set", "vloam_b200_profile_kernel", "vloam_b200_profile_result", "vloam_b200_profile_table", "vloam_b200_profile_timeline", "vloam_b200_register_full_cloud", "vloam_b200_lo_associate", "vloam_b200_voxel_grid", "vloam_b200_evaluate", "vloam_b200_solve", "vloam_b200_fit",
 ]
 
 
@@ -73,6 +73,7 @@ def load_lib(build=False):
     L.vloam_b200_evaluate.argtypes = [vp, vp, ci, vp, vp, vp, vp]
     L.vloam_b200_solve.argtypes = [vp, vp, ci, vp, vp]
     L.vloam_b200_register_full_cloud.argtypes = [vp, vp, ci]
+    L.vloam_b200_fit.argtypes = [vp, vp, ci, ci, vp, vp]
     _lib = L
     return L
 
@@ -82,7 +83,7 @@ def _decode(name, raw):
         return raw
     dt = {"sr.curvature": np.float32, "sr.label": np.int32, "sr.scanStartInd": np.int32, "sr.scanEndInd": np.int32,
           "lo.pose": np.float64, "lm.pose": np.float64, "lm.state": np.int32, "lm.validInd": np.int32,
-          "lo.costs": np.float64, "lm.costs": np.float64}
+          "lo.costs": np.float64, "lm.costs": np.float64, "alloc.count": np.int64}
     if name in dt:
         return np.frombuffer(raw, dt[name]).copy()
     if name.startswith("lo.assoc.corner"):
@@ -100,7 +101,7 @@ def _decode(name, raw):
 
 
 class Context:
-    """One vloam_b200_ctx: one CUDA stream, one sequence."""
+    """One vloam_b200_ctx: one sequence (several CUDA streams and a helper thread inside, include/vloam_b200.h)."""
 
     def __init__(self, n_scans=64, minimum_range=5.0, line_res=0.4, plane_res=0.8, mapping_skip_frame=1, device=0):
         self.L = load_lib()
@@ -254,6 +255,14 @@ class Context:
         cost, H, g = np.zeros(1), np.zeros((6, 6)), np.zeros(6)
         self._chk(self.L.vloam_b200_evaluate(self.h, f.ctypes.data, len(f), x.ctypes.data, cost.ctypes.data, H.ctypes.data, g.ctypes.data))
         return cost[0], H, g
+
+    def fit(self, near, kind):
+        """Line (kind 0) / plane (kind 1) fit of the mapping stage on five-point sets float32[n,5,3] -> (ok[n], params[n,6])."""
+        a = np.ascontiguousarray(near, np.float32).reshape(-1, 15)
+        ok = np.zeros(max(len(a), 1), np.int32)
+        prm = np.zeros((max(len(a), 1), 6))
+        self._chk(self.L.vloam_b200_fit(self.h, a.ctypes.data, len(a), kind, ok.ctypes.data, prm.ctypes.data))
+        return ok[:len(a)], prm[:len(a)]
 
     def solve(self, factors, x):
         f = np.ascontiguousarray(factors, np.float64)

@@ -57,13 +57,23 @@ static void free_sr_set(vloam_b200_ctx* c) {  // the set currently swapped into 
   if (c->evSR) cudaEventDestroy(c->evSR);
 }
 
+static int create_impl(vloam_b200_ctx* c, const vloam_b200_params* p, int device);
+
 int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** out) {
   if (!p || !out) return VLOAM_E_INVALID;
+  *out = nullptr;
   // SR.cpp:58-61, 255-259: only 16 / 32 / 64 beams (128 = builder extension)
   if (p->n_scans != 16 && p->n_scans != 32 && p->n_scans != 64 && p->n_scans != 128) return VLOAM_E_INVALID;
   if (!(p->line_res >= 0.05f) || !(p->plane_res >= 0.05f) || p->mapping_skip_frame < 1) return VLOAM_E_INVALID;
   VL_CUDA_CREATE(cudaSetDevice(device));
-  vloam_b200_ctx* c = new vloam_b200_ctx();
+  vloam_b200_ctx* c = new vloam_b200_ctx();  // value-initialised: every pointer / handle starts out null
+  const int r = create_impl(c, p, device);
+  if (r != VLOAM_OK) { vloam_b200_destroy(c); (void)cudaGetLastError(); return r; }  // destroy tolerates a half-built context: nothing leaks
+  *out = c;
+  return VLOAM_OK;
+}
+
+static int create_impl(vloam_b200_ctx* c, const vloam_b200_params* p, int device) {
   c->prm = *p; c->device = device; c->err[0] = 0; c->launches = 0; c->worker = nullptr; c->timing = false; c->cur = 0;
   c->sr_counts_valid = false; c->n_in = 0; c->lo_inited = false; c->lo_frameCount = 0; c->lm_frameCount = 0; c->lm_optimized = 0; c->skip_frame = false;
   c->nKept = c->nSharp = c->nLessSharp = c->nFlat = c->nLessFlat = 0; c->nCornerLast = c->nSurfLast = 0;
@@ -99,6 +109,7 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evPose, cudaEventDisableTiming));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evMap, cudaEventDisableTiming));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evKeys, cudaEventDisableTiming));
+  for (int k = 0; k < 2; ++k) VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evKeysSel[k], cudaEventDisableTiming));
   c->stacksReady = false; c->lm_reset_pending = true; c->lastSet = 0; c->loGridValid[0] = c->loGridValid[1] = false;
   for (int k = 0; k < 4; ++k) VL_CUDA_CREATE(cudaEventCreate(&c->ev[k]));
   for (int k = 0; k < 8; ++k) { VL_CUDA_CREATE(cudaEventCreate(&c->evx[k])); VL_CUDA_CREATE(cudaEventRecord(c->evx[k], c->stream)); }
@@ -111,6 +122,7 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   VL_CUDA_CREATE(cudaMalloc(&c->los, sizeof(LoScalars)));
   VL_CUDA_CREATE(cudaMalloc(&c->losNext, sizeof(LoScalars)));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evS2, cudaEventDisableTiming));
+  VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evLoSolve, cudaEventDisableTiming));
   c->loNextValid = c->srAdopted = c->s2Done = false; c->loAssumeMonotone = c->inProcessFrame = c->loDeferred = false; c->loNextSet = 0; c->stackSel = 0; c->stacksNextReady = false;
   VL_CUDA_CREATE(cudaMallocHost(&c->h_los, sizeof(LoScalars)));
   LoScalars hl; memset(&hl, 0, sizeof hl); hl.para_q[3] = 1.0; hl.q_w[3] = 1.0;  // LO.cpp:81-91
@@ -140,7 +152,6 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   if (r == VLOAM_OK) r = vl_lm_preload(c);
   if (r != VLOAM_OK) { fprintf(stderr, "vloam_b200_create: %s\n", c->err); return r; }
   VL_CUDA_CREATE(cudaDeviceSynchronize());
-  *out = c;
   return VLOAM_OK;
 }
 
@@ -156,7 +167,7 @@ void vloam_b200_destroy(vloam_b200_ctx* c) {
   cudaStreamDestroy(c->streamSR);
   vl_lm_free(c);
   vl_scan_free(&c->loScan[0]); vl_scan_free(&c->loScan[1]);
-  cudaEventDestroy(c->evS2);
+  cudaEventDestroy(c->evS2); cudaEventDestroy(c->evLoSolve);
   void* singles[] = {c->los, c->losNext, c->evalOut, c->lms, c->lmm, c->cubeC, c->cubeS, c->vScalars, c->loRingTbl, c->loGridCells[0].p, c->loGridCells[1].p,
                      c->loGridCellOf.p, c->loGridSorted[0].p, c->loGridSorted[1].p, c->dbgLoCorner[0].p, c->dbgLoCorner[1].p, c->dbgLoSurf[0].p,
                      c->dbgLoSurf[1].p, c->dbgKnnIdx[0][0].p, c->dbgKnnIdx[0][1].p, c->dbgKnnIdx[1][0].p, c->dbgKnnIdx[1][1].p, c->dbgKnnD2[0][0].p,
@@ -171,7 +182,7 @@ void vloam_b200_destroy(vloam_b200_ctx* c) {
   for (int k = 0; k < 4; ++k) cudaEventDestroy(c->ev[k]);
   for (int k = 0; k < 8; ++k) cudaEventDestroy(c->evx[k]);
   cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream3);
-  cudaEventDestroy(c->evStacks); cudaEventDestroy(c->evLast); cudaEventDestroy(c->evPose); cudaEventDestroy(c->evMap); cudaEventDestroy(c->evKeys);
+  cudaEventDestroy(c->evStacks); cudaEventDestroy(c->evLast); cudaEventDestroy(c->evPose); cudaEventDestroy(c->evMap); cudaEventDestroy(c->evKeys); cudaEventDestroy(c->evKeysSel[0]); cudaEventDestroy(c->evKeysSel[1]);
   cudaEventDestroy(c->evStacksC);
   cudaStreamSynchronize(c->streamAux); cudaEventDestroy(c->evAux); cudaEventDestroy(c->evAuxZero); cudaEventDestroy(c->evUpd); cudaStreamDestroy(c->streamAux);
   cudaStreamDestroy(c->stream2); cudaStreamDestroy(c->stream3); cudaStreamDestroy(c->stream4);
@@ -180,6 +191,7 @@ void vloam_b200_destroy(vloam_b200_ctx* c) {
 }
 
 int vloam_b200_begin_frame(vloam_b200_ctx* c) {
+  if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
   VL_CUDA(cudaSetDevice(c->device));
   c->lm_reset_pending = true;  // applied by the next solveMapping (the map update of the previous frame may still be reading the list)
   return VLOAM_OK;
@@ -191,11 +203,13 @@ int vloam_b200_begin_frame(vloam_b200_ctx* c) {
 // finds the work done.  Any other call ignores (and later overwrites) it.  The buffer must stay valid and unchanged
 // until that call.  No reference counterpart: the bag player hands over one sweep at a time (MAIN.cpp:143).
 int vloam_b200_prefetch_scan_device(vloam_b200_ctx* c, const float* d_xyz, int n, int stride) {
+  if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
   if (n <= 0 || stride < 3 || !d_xyz) { snprintf(c->err, sizeof c->err, "bad cloud shape"); return VLOAM_E_INVALID; }
   c->srPendKey = d_xyz; c->srPendN = n; c->srPendStride = stride; c->srPendDevice = true;
   return VLOAM_OK;
 }
 int vloam_b200_prefetch_scan(vloam_b200_ctx* c, const float* xyz, int n, int stride) {
+  if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
   if (n <= 0 || stride < 3 || !xyz) { snprintf(c->err, sizeof c->err, "bad cloud shape"); return VLOAM_E_INVALID; }
   c->srPendKey = xyz; c->srPendN = n; c->srPendStride = stride; c->srPendDevice = false;
   return VLOAM_OK;
@@ -212,6 +226,10 @@ int vl_launch_lookahead(vloam_b200_ctx* c) {
   vl_sr_swap(c, *c->srNext);
   c->cur = curNow;  // vl_sr_run advances it: the look-ahead writes the generation after this sweep's
   vl_tls_stream = c->streamSR;
+  // The spare generation of the less-sharp / less-flat clouds this run overwrites was the "last" cloud of the odometry
+  // solve before the current one: order the overwrite behind the solves queued so far on the DEVICE (a caller that never
+  // syncs -- skipped mapping frames with pose_out == NULL -- gives no host-side guarantee).
+  cudaStreamWaitEvent(c->streamSR, c->evLoSolve, 0);
   int r = VLOAM_OK;
   const float* d_xyz = key;
   if (!dev) {
@@ -236,6 +254,7 @@ static bool adopt_lookahead(vloam_b200_ctx* c, const float* key, int n, int stri
 }
 
 int vloam_b200_scan_registration_device(vloam_b200_ctx* c, const float* d_xyz, int n, int stride) {
+  if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
   if (n < 0 || stride < 3) { snprintf(c->err, sizeof c->err, "bad cloud shape"); return VLOAM_E_INVALID; }
   if (c->timing) VL_CUDA(cudaEventRecord(c->ev[0], c->stream));
   c->srAdopted = adopt_lookahead(c, d_xyz, n, stride);
@@ -249,6 +268,7 @@ int vloam_b200_scan_registration_device(vloam_b200_ctx* c, const float* d_xyz, i
 }
 
 int vloam_b200_scan_registration(vloam_b200_ctx* c, const float* xyz, int n, int stride) {
+  if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
   if (n < 0 || stride < 3 || (n > 0 && !xyz)) { snprintf(c->err, sizeof c->err, "bad cloud shape"); return VLOAM_E_INVALID; }
   if (c->timing) VL_CUDA(cudaEventRecord(c->ev[0], c->stream));
   c->srAdopted = adopt_lookahead(c, xyz, n, stride);
@@ -264,6 +284,7 @@ int vloam_b200_scan_registration(vloam_b200_ctx* c, const float* xyz, int n, int
 }
 
 int vloam_b200_get_cloud(vloam_b200_ctx* c, int which, float* out, int cap_points) {
+  if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
   VL_TRY(vl_sr_sync_counts(c));
   const float4* src = nullptr; int n = 0;
   switch (which) {
@@ -286,6 +307,7 @@ int vloam_b200_get_cloud(vloam_b200_ctx* c, int which, float* out, int cap_point
 
 int vloam_b200_laser_odometry(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, int use_prior, double* q_w, double* t_w,
                               double* q_lc, double* t_lc, int* skip_frame) {
+  if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
   if (use_prior && (!prior_q || !prior_t)) { snprintf(c->err, sizeof c->err, "use_prior without a prior"); return VLOAM_E_INVALID; }
   VL_TRY(vl_lo_run(c, prior_q, prior_t, use_prior));
   if (c->timing) VL_CUDA(cudaEventRecord(c->ev[2], c->stream));
@@ -302,6 +324,7 @@ int vloam_b200_laser_odometry(vloam_b200_ctx* c, const double* prior_q, const do
 }
 
 int vloam_b200_laser_mapping(vloam_b200_ctx* c, double* q_w, double* t_w) {
+  if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
   VL_TRY(vl_lm_run(c));
   if (c->timing) VL_CUDA(cudaEventRecord(c->ev[3], c->stream));
   if (q_w || t_w) {
@@ -317,6 +340,7 @@ int vloam_b200_laser_mapping(vloam_b200_ctx* c, double* q_w, double* t_w) {
 }
 
 int vloam_b200_register_full_cloud(vloam_b200_ctx* c, float* out, int cap_points) {
+  if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
   VL_TRY(vl_sr_sync_counts(c));
   const int n = c->nKept;
   if (!out || n == 0) return n;
@@ -353,12 +377,14 @@ static int process_common(vloam_b200_ctx* c, double* pose_out) {
 }
 
 int vloam_b200_process_frame(vloam_b200_ctx* c, const float* xyz, int n, int stride, double* pose_out) {
+  if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
   VL_HOST_MARK(0);
   VL_TRY(vloam_b200_begin_frame(c));
   VL_TRY(vloam_b200_scan_registration(c, xyz, n, stride));
   return process_common(c, pose_out);
 }
 int vloam_b200_process_frame_device(vloam_b200_ctx* c, const float* d_xyz, int n, int stride, double* pose_out) {
+  if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
   VL_HOST_MARK(0);
   VL_TRY(vloam_b200_begin_frame(c));
   VL_TRY(vloam_b200_scan_registration_device(c, d_xyz, n, stride));
@@ -366,6 +392,7 @@ int vloam_b200_process_frame_device(vloam_b200_ctx* c, const float* d_xyz, int n
 }
 
 int vloam_b200_synchronize(vloam_b200_ctx* c) {
+  if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
   VL_TRY(vl_lo_flush_deferred(c));
   VL_TRY(vl_lm_join(c));
   VL_CUDA(cudaStreamSynchronize(c->streamSR));
@@ -374,10 +401,11 @@ int vloam_b200_synchronize(vloam_b200_ctx* c) {
   VL_CUDA(cudaStreamSynchronize(c->stream4));
   return VLOAM_OK;
 }
-void* vloam_b200_stream(vloam_b200_ctx* c) { return (void*)c->stream; }
-long long vloam_b200_kernel_launches(const vloam_b200_ctx* c) { return c->launches; }
-int vloam_b200_set_timing(vloam_b200_ctx* c, int enabled) { c->timing = enabled != 0; return VLOAM_OK; }
+void* vloam_b200_stream(vloam_b200_ctx* c) { if (!c) return nullptr; return (void*)c->stream; }
+long long vloam_b200_kernel_launches(const vloam_b200_ctx* c) { if (!c) return 0; return c->launches; }
+int vloam_b200_set_timing(vloam_b200_ctx* c, int enabled) { if (!c) return VLOAM_E_INVALID; c->timing = enabled != 0; return VLOAM_OK; }
 int vloam_b200_stage_ms(vloam_b200_ctx* c, float* ms3) {
+  if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
   if (!c->timing) { snprintf(c->err, sizeof c->err, "timing is off"); return VLOAM_E_INVALID; }
   VL_CUDA(cudaStreamSynchronize(c->stream));
   for (int k = 0; k < 3; ++k) VL_CUDA(cudaEventElapsedTime(&ms3[k], c->ev[k], c->ev[k + 1]));
@@ -386,6 +414,7 @@ int vloam_b200_stage_ms(vloam_b200_ctx* c, float* ms3) {
 
 // Time one named kernel: CUDA events are recorded around each of its launches on the context's stream.
 int vloam_b200_profile_kernel(vloam_b200_ctx* c, const char* name) {
+  if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
   VL_TRY(vl_lm_join(c));
   VL_CUDA(cudaStreamSynchronize(c->stream));
   if (!c->prof_created) {
@@ -398,6 +427,7 @@ int vloam_b200_profile_kernel(vloam_b200_ctx* c, const char* name) {
   return VLOAM_OK;
 }
 int vloam_b200_profile_result(vloam_b200_ctx* c, int* launches, double* total_ms, double* total_bytes) {
+  if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
   VL_CUDA(cudaStreamSynchronize(c->stream));
   double ms = 0;
   for (int k = 0; k < c->prof_n; ++k) { float t = 0; VL_CUDA(cudaEventElapsedTime(&t, c->prof_ev[k][0], c->prof_ev[k][1])); ms += t; }
@@ -408,6 +438,7 @@ int vloam_b200_profile_result(vloam_b200_ctx* c, int* launches, double* total_ms
 // Per-kernel table of the launches timed since vloam_b200_profile_kernel(c, "*"): writes lines
 // "name count total_ms total_bytes\n" into buf (NUL-terminated); returns the number of distinct kernels.
 int vloam_b200_profile_table(vloam_b200_ctx* c, char* buf, int cap) {
+  if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
   VL_TRY(vloam_b200_synchronize(c));
   std::vector<std::string> names; std::vector<int> cnt; std::vector<double> ms, by;
   for (int k = 0; k < c->prof_n; ++k) {
@@ -430,6 +461,7 @@ int vloam_b200_profile_table(vloam_b200_ctx* c, char* buf, int cap) {
 // serialise neighbouring launches a little (no programmatic overlap across an event), so this shows the
 // dependency structure and the gaps, not the exact production schedule.
 int vloam_b200_profile_timeline(vloam_b200_ctx* c, char* buf, int cap) {
+  if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
   VL_TRY(vloam_b200_synchronize(c));
   std::string out;
   const cudaStream_t ss[6] = {c->stream, c->stream2, c->stream3, c->stream4, c->streamSR, c->streamAux};
@@ -446,7 +478,7 @@ int vloam_b200_profile_timeline(vloam_b200_ctx* c, char* buf, int cap) {
   return c->prof_n;
 }
 
-int vloam_b200_lo_associate(vloam_b200_ctx* c, const double* x, int* corner_idx, int* surf_idx) { return vl_lo_associate_only(c, x, corner_idx, surf_idx); }
+int vloam_b200_lo_associate(vloam_b200_ctx* c, const double* x, int* corner_idx, int* surf_idx) { if (!c) return VLOAM_E_INVALID; return vl_lo_associate_only(c, x, corner_idx, surf_idx); }
 
 // ---- name-keyed state access ----------------------------------------------------------------
 static long put_dev(vloam_b200_ctx* c, const void* dsrc, size_t bytes, void* out, long cap) {
@@ -460,6 +492,7 @@ static long put_dev(vloam_b200_ctx* c, const void* dsrc, size_t bytes, void* out
 static long put_host(const void* src, size_t bytes, void* out, long cap) { if (out && (long)bytes <= cap && bytes) memcpy(out, src, bytes); return (long)bytes; }
 
 long vloam_b200_debug_get(vloam_b200_ctx* c, const char* name, void* out, long cap) {
+  if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
   const std::string n(name);
   if (n.rfind("sr.", 0) == 0 || n.rfind("lo.", 0) == 0) { if (vl_sr_sync_counts(c) != VLOAM_OK) return VLOAM_E_CUDA; }
   if (vloam_b200_synchronize(c) != VLOAM_OK) return VLOAM_E_CUDA;
@@ -529,6 +562,7 @@ long vloam_b200_debug_get(vloam_b200_ctx* c, const char* name, void* out, long c
     if (vl_solver_trace(c, v) != VLOAM_OK) return VLOAM_E_CUDA;
     return put_host(v, sizeof v, out, cap);
   }
+  if (n == "alloc.count") { const long long v = c->regrows; return put_host(&v, sizeof v, out, cap); }  // device buffer (re)allocations so far
   if (n == "lo.costs") return put_host(c->dbgLoCost, sizeof c->dbgLoCost, out, cap);
   if (n == "lm.costs") return put_host(c->dbgLmCost, sizeof c->dbgLmCost, out, cap);
   if (n == "lm.pose" || n == "lm.state" || n == "lm.validInd") {
@@ -551,6 +585,7 @@ long vloam_b200_debug_get(vloam_b200_ctx* c, const char* name, void* out, long c
 }
 
 int vloam_b200_debug_set(vloam_b200_ctx* c, const char* name, const void* data, long bytes) {
+  if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
   const std::string n(name);
   VL_TRY(vloam_b200_synchronize(c));
   c->loNextValid = false;  // whatever is set below may change what the next odometry solve starts from
@@ -565,7 +600,7 @@ int vloam_b200_debug_set(vloam_b200_ctx* c, const char* name, const void* data, 
     const char* p = (const char*)data + 8;
     if (hdr[0]) VL_CUDA(cudaMemcpy(c->lessSharp[o].p, p, (size_t)hdr[0] * 16, cudaMemcpyHostToDevice));
     if (hdr[1]) VL_CUDA(cudaMemcpy(c->lessFlat[o].p, p + (size_t)hdr[0] * 16, (size_t)hdr[1] * 16, cudaMemcpyHostToDevice));
-    // make that buffer the current one so the next frame (cur ^= 1) writes the other
+    // make that buffer the current one so the next frame (cur = (cur + 1) % 3) writes the generation after it
     c->cur = o;
     c->cornerLastPtr = c->lessSharp[o].p; c->surfLastPtr = c->lessFlat[o].p;
     c->nCornerLast = hdr[0]; c->nSurfLast = hdr[1];
@@ -604,6 +639,7 @@ int vloam_b200_debug_set(vloam_b200_ctx* c, const char* name, const void* data, 
 }
 
 int vloam_b200_voxel_grid(vloam_b200_ctx* c, const float* in, int n, float leaf, float* out, int cap_points) {
+  if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
   if (n < 0 || !(leaf > 0.f)) return VLOAM_E_INVALID;
   VL_TRY(vloam_b200_synchronize(c));  // look-ahead stack filters of a registered sweep may still be using the filter scratch
   VL_TRY(vl_reserve(c, c->vIn, (size_t)max(n, 1)));
@@ -632,6 +668,7 @@ static int upload_factors(vloam_b200_ctx* c, const double* factors, int nf) {
 }
 
 int vloam_b200_evaluate(vloam_b200_ctx* c, const double* factors, int nf, const double* x, double* cost, double* H, double* g) {
+  if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
   VL_TRY(upload_factors(c, factors, nf));
   double* d_x = reinterpret_cast<double*>(c->vScalars + 32);
   VL_CUDA(cudaMemcpyAsync(d_x, x, 56, cudaMemcpyHostToDevice, c->stream));
@@ -646,7 +683,28 @@ int vloam_b200_evaluate(vloam_b200_ctx* c, const double* factors, int nf, const 
   return VLOAM_OK;
 }
 
+// n five-point sets (float32[n][5][3]) through the line (kind 0, LM.cpp:559-603) or plane (kind 1, LM.cpp:637-680) fit of the
+// mapping stage: accept flags ok[n] and parameters params[n][6] ({a, b} of the edge factor / {unit normal, d, 0, 0}).
+int vloam_b200_fit(vloam_b200_ctx* c, const float* near, int n, int kind, int* ok, double* params) {
+  if (!c) return VLOAM_E_INVALID;
+  if (n < 0 || (kind != 0 && kind != 1) || (n > 0 && (!near || !ok || !params))) return VLOAM_E_INVALID;
+  if (n == 0) return VLOAM_OK;
+  VL_TRY(vloam_b200_synchronize(c));
+  float* d_near = nullptr; int* d_ok = nullptr; double* d_prm = nullptr;
+  int r = VLOAM_OK;
+  if (cudaMalloc(&d_near, (size_t)n * 60) != cudaSuccess || cudaMalloc(&d_ok, (size_t)n * 4) != cudaSuccess || cudaMalloc(&d_prm, (size_t)n * 48) != cudaSuccess) r = VLOAM_E_CUDA;
+  if (r == VLOAM_OK && cudaMemcpyAsync(d_near, near, (size_t)n * 60, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) r = VLOAM_E_CUDA;
+  if (r == VLOAM_OK) r = vl_lm_fit_sets(c, d_near, n, kind, d_ok, d_prm);
+  if (r == VLOAM_OK && (cudaMemcpyAsync(ok, d_ok, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                        cudaMemcpyAsync(params, d_prm, (size_t)n * 48, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                        cudaStreamSynchronize(c->stream) != cudaSuccess)) r = VLOAM_E_CUDA;
+  if (r == VLOAM_E_CUDA) snprintf(c->err, sizeof c->err, "vloam_b200_fit: %s", cudaGetErrorString(cudaGetLastError()));
+  cudaFree(d_near); cudaFree(d_ok); cudaFree(d_prm);
+  return r;
+}
+
 int vloam_b200_solve(vloam_b200_ctx* c, const double* factors, int nf, double* x, double* log4) {
+  if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
   VL_TRY(upload_factors(c, factors, nf));
   double* d_x = reinterpret_cast<double*>(c->vScalars + 32);
   VL_CUDA(cudaMemcpyAsync(d_x, x, 56, cudaMemcpyHostToDevice, c->stream));

@@ -113,10 +113,12 @@ struct vloam_b200_ctx {
   cudaEvent_t evPose;         // solveMapping's pose is final (the map update may start)
   cudaEvent_t evMap;          // the map update has finished (the next solveMapping may start)
   cudaEvent_t evKeys;         // the map update has read the stacks (rf_keys): the next sweep's stack filters may start
+  cudaEvent_t evKeysSel[2];   // same, per stack buffer pair (index = stackSel the update read): the look-ahead filters wait on the pair they overwrite
   bool stacksReady;
   bool lm_reset_pending;      // LaserMapping::reset was called since the last solveMapping
   char err[512];
   long long launches;         // updated with __atomic_fetch_add (two issuing threads)
+  long long regrows;          // device buffer (re)allocations after creation (vl_reserve): each one stalls a stream for ~ms
   VlWorker* worker;           // helper thread that issues the map update (created on first use)
   int num_sms;
   bool timing;
@@ -166,6 +168,7 @@ struct vloam_b200_ctx {
   bool inProcessFrame;        // inside process_frame: mapping follows the odometry in the same call
   bool loDeferred; int defSet, defNc, defNs; const float4* defCorner; const float4* defSurf;  // side-stream work of the odometry stage queued after the mapping
   cudaEvent_t evS2;           // sync point S2 (pose + sizes copied to the host)
+  cudaEvent_t evLoSolve;      // the last queued odometry solve (and every one before it) has finished reading the "last" clouds and their grids
   int nCornerLast, nSurfLast;  // host counts of the "last" clouds (= other buffer of the pair)
   bool lo_inited; int lo_frameCount;
   float4* cornerLastPtr; float4* surfLastPtr;  // after solveLO's swap
@@ -305,6 +308,7 @@ static inline int vl_reserve(vloam_b200_ctx* c, DBuf<T>& b, size_t n, bool keep 
   while (ncap < n) ncap *= 2;
   if (ncap * sizeof(T) <= ((size_t)32 << 20)) ncap *= 2;  // HBM is plentiful: head room so a count hovering at a power of two never regrows
   T* np = nullptr;
+  __atomic_fetch_add(&c->regrows, 1LL, __ATOMIC_RELAXED);
   static const bool trace = getenv("VLOAM_TRACE_ALLOC") != nullptr;
   if (trace) fprintf(stderr, "[vloam_b200] grow buffer to %zu x %zu B (frame %d)\n", ncap, sizeof(T), c->lo_frameCount);
   VL_CUDA(cudaMalloc(&np, ncap * sizeof(T)));
@@ -338,6 +342,7 @@ int vl_lo_flush_deferred(vloam_b200_ctx* c);  // queue the deferred side-stream 
 int vl_vg_preload(vloam_b200_ctx* c);
 int vl_lm_preload(vloam_b200_ctx* c);
 int vl_lm_register_full(vloam_b200_ctx* c, const float4* d_in, int n, float4* d_out);
+int vl_lm_fit_sets(vloam_b200_ctx* c, const float* d_near, int n, int kind, int* d_ok, double* d_prm);  // vloam_b200_fit
 int vl_lm_join(vloam_b200_ctx* c);      // wait until the helper thread has issued the pending map update; returns its status
 void vl_lm_shutdown(vloam_b200_ctx* c);  // stop the helper thread
 int vl_lm_export_map(vloam_b200_ctx* c, int which, void* out, long cap, long* bytes);

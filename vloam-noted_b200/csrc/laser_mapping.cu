@@ -114,8 +114,11 @@ static int lm_submit(vloam_b200_ctx* c, std::function<int()> f) {
   VlWorker* w = c->worker;
   VL_TRY(vl_lm_join(c));
   w->task = std::move(f);
-  w->state.store(1, std::memory_order_release);
-  if (w->sleeping.load()) { std::lock_guard<std::mutex> lk(w->m); w->cv.notify_all(); }
+  // Publish under the worker's mutex and always notify: a worker that is between its last poll of `state` and
+  // cv.wait() holds the mutex, so it either sees state == 1 in the wait predicate or receives this notification
+  // (checking `sleeping` without the lock could miss both: the store and the load may be reordered on x86).
+  { std::lock_guard<std::mutex> lk(w->m); w->state.store(1, std::memory_order_seq_cst); }
+  w->cv.notify_one();
   return VLOAM_OK;
 }
 
@@ -600,7 +603,7 @@ int vl_scan_exclusive(vloam_b200_ctx* c, const int* in, int n, VlScan* sc, int* 
     sc->epoch = 0;
   }
   ++sc->epoch;
-  VL_BYTES(8.0 * n);
+  // (a scan over cell counters is search-structure overhead: SURVEY 8(d) assigns it no algorithmic bytes -> achieved GB/s is not reported for it)
   VL_LAUNCH(lm_scan_chained, sc->tiles, 256, 0, in, n, sc->state, sc->epoch, out, d_skip);
   return VLOAM_OK;
 }
@@ -655,7 +658,8 @@ __global__ void __launch_bounds__(256) lm_inline_build(LmInlineArgs a) {
 }
 
 // ---- fits -------------------------------------------------------------------------------------
-// Same cyclic-Jacobi routine as the oracle's restatement of SelfAdjointEigenSolver (oracle_math.cpp).
+// Eigen::SelfAdjointEigenSolver<Matrix3d> contract (ascending eigenvalues, unit eigenvectors) by the cyclic Jacobi method: branch-light
+// and register-resident.  The oracle restates Eigen's own tridiagonal-QR algorithm (oracle_math.cpp), so the two are independent witnesses.
 __device__ void lm_sym_eig3(double a[3][3], double evals[3], double evecs[3][3]) {
   double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
   for (int sweep = 0; sweep < 30; ++sweep) {
@@ -805,6 +809,37 @@ __global__ void __launch_bounds__(256) lm_knn(const LmScalars* __restrict__ s, c
   }
 }
 
+// The two fits of LM.cpp:559-603 / 637-680 on five neighbours (f64 from f32 coordinates).  o6: edge -> {a, b} (the two
+// synthetic line points), plane -> {unit normal, d, 0, 0}.  Returns the accept flag.
+__device__ __forceinline__ bool lm_fit_one(int kind, double P[5][3], double o6[6]) {
+  if (!kind) {  // LM.cpp:559-603: PCA line test
+    double cen[3] = {0, 0, 0};
+    for (int j = 0; j < 5; ++j) for (int k = 0; k < 3; ++k) cen[k] = cen[k] + P[j][k];
+    for (int k = 0; k < 3; ++k) cen[k] = cen[k] / 5.0;
+    double cov[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int j = 0; j < 5; ++j) {
+      const double z[3] = {P[j][0] - cen[0], P[j][1] - cen[1], P[j][2] - cen[2]};
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) cov[a][b] = cov[a][b] + z[a] * z[b];
+    }
+    double ev[3], evec[3][3];
+    lm_sym_eig3(cov, ev, evec);
+    if (!(ev[2] > 3 * ev[1])) return false;
+    for (int k = 0; k < 3; ++k) { const double u = evec[k][2]; o6[k] = 0.1 * u + cen[k]; o6[3 + k] = -0.1 * u + cen[k]; }
+    return true;
+  }
+  // LM.cpp:637-680: least-squares plane n.p + 1 = 0, 0.2 m flatness check
+  double A[5][3], B[5] = {-1, -1, -1, -1, -1}, nrm[3];
+  for (int j = 0; j < 5; ++j) for (int k = 0; k < 3; ++k) A[j][k] = P[j][k];
+  lm_qr_solve_5x3(A, B, nrm);
+  const double nn = sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
+  const double d = 1 / nn;
+  if (nn > 0) { nrm[0] /= nn; nrm[1] /= nn; nrm[2] /= nn; }
+  for (int j = 0; j < 5; ++j)
+    if (fabs(nrm[0] * P[j][0] + nrm[1] * P[j][1] + nrm[2] * P[j][2] + d) > 0.2) return false;
+  o6[0] = nrm[0]; o6[1] = nrm[1]; o6[2] = nrm[2]; o6[3] = d; o6[4] = 0; o6[5] = 0;
+  return true;
+}
+
 // Line / plane fit of one feature per THREAD (the f64 eigen / QR work of 32 features shares a warp's
 // issue slots instead of idling 31 lanes behind lane 0 of the search kernel).
 __global__ void __launch_bounds__(128) lm_fit(const LmScalars* __restrict__ s, const float4* __restrict__ stackC, const float4* __restrict__ stackS,
@@ -830,42 +865,34 @@ __global__ void __launch_bounds__(128) lm_fit(const LmScalars* __restrict__ s, c
     double P[5][3];
 #pragma unroll
     for (int j = 0; j < 5; ++j) { const float4 t = map[ni[j]]; P[j][0] = t.x; P[j][1] = t.y; P[j][2] = t.z; }
-    if (!kind) {  // LM.cpp:559-603: PCA line test
-      double cen[3] = {0, 0, 0};
-      for (int j = 0; j < 5; ++j) for (int k = 0; k < 3; ++k) cen[k] = cen[k] + P[j][k];
-      for (int k = 0; k < 3; ++k) cen[k] = cen[k] / 5.0;
-      double cov[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-      for (int j = 0; j < 5; ++j) {
-        const double z[3] = {P[j][0] - cen[0], P[j][1] - cen[1], P[j][2] - cen[2]};
-        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) cov[a][b] = cov[a][b] + z[a] * z[b];
-      }
-      double ev[3], evec[3][3];
-      lm_sym_eig3(cov, ev, evec);
-      if (ev[2] > 3 * ev[1]) {
-        ok = true;
-        f[0] = 0.0; f[1] = po.x; f[2] = po.y; f[3] = po.z;
-        for (int k = 0; k < 3; ++k) { const double u = evec[k][2]; f[4 + k] = 0.1 * u + cen[k]; f[7 + k] = -0.1 * u + cen[k]; }
-      }
-    } else {  // LM.cpp:637-680: least-squares plane n.p + 1 = 0, 0.2 m flatness check
-      double A[5][3], B[5] = {-1, -1, -1, -1, -1}, nrm[3];
-      for (int j = 0; j < 5; ++j) for (int k = 0; k < 3; ++k) A[j][k] = P[j][k];
-      lm_qr_solve_5x3(A, B, nrm);
-      const double nn = sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
-      const double d = 1 / nn;
-      if (nn > 0) { nrm[0] /= nn; nrm[1] /= nn; nrm[2] /= nn; }
-      bool planeValid = true;
-      for (int j = 0; j < 5; ++j)
-        if (fabs(nrm[0] * P[j][0] + nrm[1] * P[j][1] + nrm[2] * P[j][2] + d) > 0.2) { planeValid = false; break; }
-      if (planeValid) {
-        ok = true;
-        f[0] = 2.0; f[1] = po.x; f[2] = po.y; f[3] = po.z;
-        f[4] = nrm[0]; f[5] = nrm[1]; f[6] = nrm[2]; f[7] = d; f[8] = 0; f[9] = 0;
-      }
+    double o6[6];
+    ok = lm_fit_one(kind, P, o6);
+    if (ok) {
+      f[0] = kind ? 2.0 : 0.0; f[1] = po.x; f[2] = po.y; f[3] = po.z;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) f[4 + k] = o6[k];
     }
   }
   valid[qi] = ok ? 1 : 0;
   knnOk[qi] = ok ? 1 : 0;
   }
+}
+
+// vloam_b200_fit: the same fits on caller-supplied five-point sets (parity tests against an independent witness)
+__global__ void __launch_bounds__(128) lm_fit_sets(const float* __restrict__ near, int n, int kind, int* __restrict__ ok, double* __restrict__ prm) {
+  VL_PDL_WAIT();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double P[5][3], o6[6] = {0, 0, 0, 0, 0, 0};
+  for (int j = 0; j < 5; ++j) for (int k = 0; k < 3; ++k) P[j][k] = near[(size_t)i * 15 + j * 3 + k];
+  const bool a = lm_fit_one(kind, P, o6);
+  ok[i] = a ? 1 : 0;
+  for (int k = 0; k < 6; ++k) prm[(size_t)i * 6 + k] = a ? o6[k] : 0.0;
+}
+int vl_lm_fit_sets(vloam_b200_ctx* c, const float* d_near, int n, int kind, int* d_ok, double* d_prm) {
+  VL_LAUNCH(lm_fit_sets, vl_div_up(max(n, 1), 128), 128, 0, d_near, n, kind, d_ok, d_prm);
+  VL_CUDA(cudaGetLastError());
+  return VLOAM_OK;
 }
 
 __global__ void lm_transform_update(LmScalars* s) {
@@ -1420,12 +1447,14 @@ static int lm_issue_stacks(vloam_b200_ctx* c, const float4* corner, int nc, cons
   int* dq = d->dQ + 2 * (toNext ? c->stackSel ^ 1 : c->stackSel);
   // surf filter on stream2 (scratch lane 0), corner filter beside it on stream4 (scratch lane 1)
   vl_tls_stream = c->stream2;
-  if (!toNext) cudaStreamWaitEvent(c->stream2, c->evKeys, 0);  // (the spare buffers were last read two sweeps ago)
+  // the buffers about to be overwritten were last read by rf_keys of the update that used this pair (stream3)
+  const int pairW = toNext ? c->stackSel ^ 1 : c->stackSel;
+  cudaStreamWaitEvent(c->stream2, toNext ? c->evKeysSel[pairW] : c->evKeys, 0);
   int r = vl_reserve(c, dstS, (size_t)max(ns, 1));
   if (r == VLOAM_OK) r = vl_voxel_grid_device(c, surf, ns, nullptr, c->prm.plane_res, dstS.p, dq + 1, 0);
   if (c->timing) cudaEventRecord(c->evx[3], c->stream2);
   vl_tls_stream = c->stream4;
-  if (!toNext) cudaStreamWaitEvent(c->stream4, c->evKeys, 0);
+  cudaStreamWaitEvent(c->stream4, toNext ? c->evKeysSel[pairW] : c->evKeys, 0);
   if (r == VLOAM_OK) r = vl_reserve(c, dstC, (size_t)max(nc, 1));
   if (r == VLOAM_OK) r = vl_voxel_grid_device(c, corner, nc, nullptr, c->prm.line_res, dstC.p, dq, 1);
   if (c->timing) cudaEventRecord(c->evx[4], c->stream4);
@@ -1586,6 +1615,7 @@ int vl_lm_run(vloam_b200_ctx* c) {
   c->lm_optimized = c->h_lmm->optimized;
   const long long totalC = c->h_lmm->totalC, totalS = c->h_lmm->totalS;
   const float4* const stackCp = c->stackC.p; const float4* const stackSp = c->stackS.p;  // (the next frame may swap the buffers while the helper issues this)
+  const int stackSelNow = c->stackSel;
   auto update = [=]() -> int {
   vl_tls_stream = c->stream3;  // every launch helper below issues on the update's stream, whichever thread runs this
   struct Restore { ~Restore() { vl_tls_stream = nullptr; } } restore;
@@ -1616,6 +1646,7 @@ int vl_lm_run(vloam_b200_ctx* c) {
     VL_LAUNCH(rf_keys, vl_div_up(nKeys, 256), 256, 0, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, stackCp, stackSp,
               d->newPts.p, d->newCube.p, keysIn, nKeys);
     VL_CUDA(cudaEventRecord(c->evKeys, c->stream3));  // nothing below reads the stacks any more: the next sweep's filters may overwrite them
+    VL_CUDA(cudaEventRecord(c->evKeysSel[stackSelNow], c->stream3));
     VL_TRY(zeroSpecGrid());
     VL_LAUNCH(rf_seg_scatter, vl_div_up(nKeys, 256), 256, 0, keysIn, nKeys, d->work, keysSorted);
     VL_BYTES(16.0 * nKeys);
@@ -1782,6 +1813,7 @@ int vl_lm_preload(vloam_b200_ctx* c) {  // see vl_sr_set_attrs: load every kerne
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_inline_build));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_knn));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_fit));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_fit_sets));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_transform_update));
   VL_CUDA(cudaFuncGetAttributes(&fa_, rf_keys));
   VL_CUDA(cudaFuncGetAttributes(&fa_, rf_seg_scatter));

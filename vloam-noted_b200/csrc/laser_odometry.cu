@@ -510,6 +510,8 @@ __global__ void lo_set_prior(LoScalars* s, const double* __restrict__ prior) {
 // copied to pinned host memory; the next frame's first sync point makes them readable.
 int vl_lo_build_last(vloam_b200_ctx* c, int set, const float4* corner, int nc, const float4* surf, int ns) {
   const int n = nc + ns;
+  // set `set` was searched by the odometry solve before the current one: rebuild it only behind the solves queued so far
+  VL_CUDA(cudaStreamWaitEvent(c->stream, c->evLoSolve, 0));
   int* tbl = c->loRingTbl + set * 2 * (LO_TBL + 1);
   VL_LAUNCH(lo_ring_table_init, 1, 32, 0, tbl);
   VL_LAUNCH(lo_ring_table, dim3(vl_div_up(max(max(nc, ns), LO_TBL + 1), 256), 2), 256, 0, corner, nc, surf, ns, tbl);
@@ -550,7 +552,7 @@ static int lo_associate(vloam_b200_ctx* c, const double* d_pose, const float4* c
   const float4* gsorted = c->loGridSorted[set].p;
   const int* rtbl = c->loRingTbl + set * 2 * (LO_TBL + 1);
   if (gridC && gridS && nS + nF > 0) {
-    VL_BYTES(16.0 * (nS + nF) * 2 * 600);
+    VL_BYTES(16.0 * ((double)c->nSharp + c->nFlat + nCL + nSL));  // SURVEY 8(d) B_lo, one pass: every query and every point of the two last clouds once
     VL_LAUNCH(lo_assoc_grid_both, vl_div_up((long long)(nS + nF) * 32, 256), 256, 0, c->sharp.p, c->flat.p, nS + nF, c->srs, cornerLast, surfLast,
               gsorted, start, d_pose, c->loCornerIdx.p, c->loSurfIdx.p, c->factors.p, c->factorValid.p);
     VL_CUDA(cudaGetLastError());
@@ -566,7 +568,7 @@ static int lo_associate(vloam_b200_ctx* c, const double* d_pose, const float4* c
   }
   if (nF > 0) {
     if (gridS) {
-      VL_BYTES(16.0 * nF * 2 * 1500);
+      VL_BYTES(16.0 * ((double)nF + nSL));
       VL_LAUNCH(lo_assoc_grid<true>, vl_div_up((long long)nF * 32, 256), 256, 0, c->flat.p, nF, surfLast, gsorted, start, d_pose,
                 c->loSurfIdx.p, c->factors.p, c->factorValid.p, nS);
     } else
@@ -628,6 +630,7 @@ static int lo_queue_solve(vloam_b200_ctx* c, const double* prior_q, const double
       VL_TRY(vl_solve(c, nslots, &c->srs->nQueries, d_pose, vl_debug_capture(c) ? &c->dbgLoCost[pass * 2] : nullptr, c->nSharp + c->nFlat));
     }
     VL_LAUNCH(lo_accumulate, 1, 32, 0, c->los);
+  VL_CUDA(cudaEventRecord(c->evLoSolve, c->stream));
   return VLOAM_OK;
 }
 
