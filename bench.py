@@ -584,8 +584,8 @@ def run_ours(args, rank, world_size, local_rank):
         "ms_per_step": dev_med / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
         "data": "synthetic", "config": bench_config(map_points, np.mean([len(s) for s in scans])),
         "windows": {"repeats": R, "what": "every window = fresh context + %d warm-up sweeps + barrier/synchronize + %d timed sweeps + synchronize; value / e2e = median over windows of the max over ranks" % (first, K),
-                    "value_scans_per_s": {k: (world_size * K / (v * 1e-3) if k != "windows" else v) for k, v in _stats(dev_w).items()},
-                    "e2e_scans_per_s": {k: (world_size * K / (v * 1e-3) if k != "windows" else v) for k, v in _stats(e2e_w).items()},
+                    "value_scans_per_s": _stats(world_size * K / (dev_w * 1e-3)),
+                    "e2e_scans_per_s": _stats(world_size * K / (e2e_w * 1e-3)),
                     "per_rank_ms_per_step_median": [float(np.median(allt[q, :R])) / K for q in range(world_size)],
                     "per_rank_e2e_ms_per_step_median": [float(np.median(allt[q, R:2 * R])) / K for q in range(world_size)]},
         "p50_ms_per_frame_e2e": float(allt[:, 2 * R].max()), "p99_ms_per_frame_e2e": float(allt[:, 2 * R + 1].max()),

@@ -51,8 +51,14 @@ typedef struct vloam_b200_params {
   float line_res;         /* mapping_line_resolution */
   float plane_res;        /* mapping_plane_resolution */
   int mapping_skip_frame; /* mapping_skip_frame */
-  int reserved;           /* must be 0 */
+  int reserved;           /* flags: VLOAM_FLAG_DISTORTION or 0 */
 } vloam_b200_params;
+
+/* LaserOdometry::DISTORTION (laser_odometry.h:90; a compile-time `false` in the reference): with this flag set in
+ * vloam_b200_params.reserved the odometry de-skews every feature point by its sweep phase s = (intensity -
+ * int(intensity)) / SCAN_PERIOD: TransformToStart uses Identity.slerp(s, q_last_curr) and s * t_last_curr
+ * (laser_odometry.cpp:152-173) and the two odometry functors interpolate the same way (lidarFactor.hpp:29-33, 86-90). */
+#define VLOAM_FLAG_DISTORTION 1
 
 typedef struct vloam_b200_ctx vloam_b200_ctx;
 
@@ -179,6 +185,12 @@ int vloam_b200_evaluate(vloam_b200_ctx* c, const double* factors, int nf, const 
                         double* g);
 /* ceres::Solve as configured by the reference on the same factor list. */
 int vloam_b200_solve(vloam_b200_ctx* c, const double* factors, int nf, double* x, double* log4);
+/* The same two calls with a per-factor interpolation ratio s[nf] (DISTORTION: LidarEdgeFactor / LidarPlaneFactor evaluate
+ * Identity.slerp(s, q) * p + s t and are differentiated through the slerp, lidarFactor.hpp:29-36, 86-93); s == NULL is
+ * the plain call. */
+int vloam_b200_evaluate_deskew(vloam_b200_ctx* c, const double* factors, const double* s, int nf, const double* x, double* cost,
+                               double* H, double* g);
+int vloam_b200_solve_deskew(vloam_b200_ctx* c, const double* factors, const double* s, int nf, double* x, double* log4);
 
 /* The two neighbourhood fits of solveMapping on caller-supplied five-point sets (float32[n][5][3], the map
  * neighbours as the kNN returns them): kind 0 = 3x3 covariance + SelfAdjointEigenSolver line test, accepted when

@@ -15,6 +15,7 @@ struct OracleParamsC {  // same layout as vloam_b200_params
   float line_res, plane_res;
   int mapping_skip_frame;
   int knn_backend;
+  int distortion;  // LaserOdometry::DISTORTION
 };
 
 static int put(const void* src, size_t bytes, void* out, long cap) {
@@ -44,7 +45,7 @@ extern "C" {
 void* vloam_oracle_create(const OracleParamsC* pc) {
   Params p;
   p.n_scans = pc->n_scans; p.minimum_range = pc->minimum_range; p.line_res = pc->line_res; p.plane_res = pc->plane_res;
-  p.mapping_skip_frame = pc->mapping_skip_frame; p.knn_backend = pc->knn_backend;
+  p.mapping_skip_frame = pc->mapping_skip_frame; p.knn_backend = pc->knn_backend; p.distortion = pc->distortion;
   return new Pipeline(p);
 }
 void vloam_oracle_destroy(void* h) { delete (Pipeline*)h; }
@@ -211,6 +212,21 @@ static std::vector<Factor> unpack(const double* f, int nf) {
     for (int k = 0; k < 3; ++k) { fs[i].p[k] = f[i * 10 + 1 + k]; fs[i].a[k] = f[i * 10 + 4 + k]; fs[i].b[k] = f[i * 10 + 7 + k]; }
   }
   return fs;
+}
+// the same with a per-factor interpolation ratio s[nf] (DISTORTION == true: slerp(s, q), s * t inside the functors)
+static std::vector<Factor> unpack_s(const double* f, const double* s, int nf) {
+  std::vector<Factor> fs = unpack(f, nf);
+  for (int i = 0; i < nf; ++i) { fs[i].s = s[i]; fs[i].slerp = true; }
+  return fs;
+}
+int vloam_oracle_ceres_solve_s(const double* f, const double* s, int nf, double* x, double* log4) {
+  SolveLog lg; ceres_solve(unpack_s(f, s, nf), x, &lg);
+  if (log4) { log4[0] = lg.iterations; log4[1] = lg.successful; log4[2] = lg.initial_cost; log4[3] = lg.final_cost; }
+  return 0;
+}
+int vloam_oracle_evaluate_s(const double* f, const double* s, int nf, const double* x, double* cost, double* H, double* g) {
+  evaluate_normal_eq(unpack_s(f, s, nf), x, cost, H, g);
+  return 0;
 }
 int vloam_oracle_ceres_solve(const double* f, int nf, double* x, double* log4) {
   SolveLog lg; ceres_solve(unpack(f, nf), x, &lg);

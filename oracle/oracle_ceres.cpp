@@ -48,15 +48,51 @@ template <typename T> static inline V3<T> rot(const T q[4], const V3<T>& v) {
   return V3<T>{(v.x + q[3] * uv.x) + c.x, (v.y + q[3] * uv.y) + c.y, (v.z + q[3] * uv.z) + c.z};
 }
 
-// The functors pass q through Identity.slerp(T(s), q) with s == 1 (DISTORTION is
-// false, LO.h:90; mapping passes 1.0, LM.cpp:600).  For s == 1 Eigen's slerp
-// returns scale0*I + scale1*q with scale0 == 0 and scale1 == +-1 exactly, with
-// exactly-zero derivatives of the scales, so value and Jacobian equal the plain
-// q*cp + t; the restatement therefore applies q directly.
+// ceres::Jet overloads of the functions Eigen's slerp calls (jet.h: abs, acos, sin)
+static inline Jet jabs(const Jet& x) { Jet r; r.a = fabs(x.a); const double sg = x.a < 0.0 ? -1.0 : 1.0; for (int k = 0; k < 7; ++k) r.v[k] = sg * x.v[k]; return r; }
+static inline Jet jacos(const Jet& x) { Jet r; r.a = acos(x.a); const double h = -1.0 / sqrt(1.0 - x.a * x.a); for (int k = 0; k < 7; ++k) r.v[k] = h * x.v[k]; return r; }
+static inline Jet jsin(const Jet& x) { Jet r; r.a = sin(x.a); const double c = cos(x.a); for (int k = 0; k < 7; ++k) r.v[k] = c * x.v[k]; return r; }
+static inline double jabs(double x) { return fabs(x); }
+static inline double jacos(double x) { return acos(x); }
+static inline double jsin(double x) { return sin(x); }
+
+// Eigen::QuaternionBase::slerp(t, other) with *this = Identity (Eigen/src/Geometry/Quaternion.h), on T = double or Jet:
+//   d = this.dot(other) = w;  |d| >= 1 - eps: scale0 = 1 - t, scale1 = t;  else theta = acos(|d|),
+//   scale0 = sin((1 - t) theta) / sin(theta), scale1 = sin(t theta) / sin(theta);  d < 0: scale1 = -scale1;
+//   result coeffs = scale0 * Identity + scale1 * other.   (Jet comparisons look at the value part only.)
+template <typename T> static inline void slerp_identity(double t, const T q[4], T out[4]) {
+  const double one = 1.0 - DBL_EPSILON;
+  const T d = q[3];
+  const T absD = jabs(d);
+  T scale0, scale1;
+  if (val(absD) >= one) { scale0 = T(1.0 - t); scale1 = T(t); }
+  else {
+    const T theta = jacos(absD);
+    const T sinTheta = jsin(theta);
+    scale0 = jsin(T(1.0 - t) * theta) / sinTheta;
+    scale1 = jsin(T(t) * theta) / sinTheta;
+  }
+  if (val(d) < 0.0) scale1 = T(0.0) - scale1;
+  out[0] = scale1 * q[0]; out[1] = scale1 * q[1]; out[2] = scale1 * q[2];
+  out[3] = scale0 * T(1.0) + scale1 * q[3];
+}
+void slerp_identity_d(double t, const double q[4], double out[4]) { slerp_identity<double>(t, q, out); }
+
+// The functors pass q through Identity.slerp(T(s), q) and scale t by s (LF.hpp:29-33, 86-90).  With s == 1 (DISTORTION
+// false, LO.h:90; mapping always passes 1.0, LM.cpp:600) slerp returns scale0*I + scale1*q with scale0 == 0 and
+// scale1 == +-1 exactly, with exactly-zero derivatives of the scales, so value and Jacobian equal the plain q*cp + t
+//  and the restatement applies q directly; factors built under DISTORTION (f.slerp) take the literal path.
 template <typename T> static int eval_factor(const Factor& f, const T q[4], const T t[3], T r[3]) {
   const V3<T> cp{T(f.p[0]), T(f.p[1]), T(f.p[2])};
-  V3<T> lp = rot(q, cp);
-  lp = V3<T>{lp.x + t[0], lp.y + t[1], lp.z + t[2]};
+  V3<T> lp;
+  if (f.slerp && f.type != 2) {
+    T qs[4]; slerp_identity<T>(f.s, q, qs);
+    lp = rot(qs, cp);
+    lp = V3<T>{lp.x + T(f.s) * t[0], lp.y + T(f.s) * t[1], lp.z + T(f.s) * t[2]};
+  } else {
+    lp = rot(q, cp);
+    lp = V3<T>{lp.x + t[0], lp.y + t[1], lp.z + t[2]};
+  }
   if (f.type == 0) {  // LidarEdgeFactor LF.hpp:22-50
     const V3<T> lpa{T(f.a[0]), T(f.a[1]), T(f.a[2])}, lpb{T(f.b[0]), T(f.b[1]), T(f.b[2])};
     const V3<T> nu = cross(V3<T>{lp.x - lpa.x, lp.y - lpa.y, lp.z - lpa.z},

@@ -12,7 +12,7 @@ _lib = None
 
 class Params(ctypes.Structure):
     _fields_ = [("n_scans", ctypes.c_int), ("minimum_range", ctypes.c_float), ("line_res", ctypes.c_float),
-                ("plane_res", ctypes.c_float), ("mapping_skip_frame", ctypes.c_int), ("knn_backend", ctypes.c_int)]
+                ("plane_res", ctypes.c_float), ("mapping_skip_frame", ctypes.c_int), ("knn_backend", ctypes.c_int), ("distortion", ctypes.c_int)]
 
 
 def lib():
@@ -40,6 +40,8 @@ def lib():
         L.vloam_oracle_fit.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.vloam_oracle_ceres_solve.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.vloam_oracle_evaluate.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 4
+        L.vloam_oracle_ceres_solve_s.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.vloam_oracle_evaluate_s.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 4
         L.vloam_oracle_quat.argtypes = [ctypes.c_void_p] * 6
         _lib = L
     return _lib
@@ -71,8 +73,8 @@ def decode(name, raw):
 
 
 class Oracle:
-    def __init__(self, n_scans=64, minimum_range=5.0, line_res=0.4, plane_res=0.8, mapping_skip_frame=1, knn_backend=0):
-        self.p = Params(n_scans, minimum_range, line_res, plane_res, mapping_skip_frame, knn_backend)
+    def __init__(self, n_scans=64, minimum_range=5.0, line_res=0.4, plane_res=0.8, mapping_skip_frame=1, knn_backend=0, distortion=0):
+        self.p = Params(n_scans, minimum_range, line_res, plane_res, mapping_skip_frame, knn_backend, distortion)
         self.h = lib().vloam_oracle_create(ctypes.byref(self.p))
 
     def __del__(self):
@@ -175,21 +177,30 @@ def fit(near, kind):
     return ok, prm
 
 
-def ceres_solve(factors, x):
+def ceres_solve(factors, x, s=None):
+    """s: per-factor interpolation ratio (DISTORTION == true: the functors slerp q by s and scale t by s); None = the s == 1 path."""
     f = np.ascontiguousarray(factors, np.float64)
     x = np.array(x, np.float64)
     log = np.zeros(4)
-    lib().vloam_oracle_ceres_solve(f.ctypes.data, len(f), x.ctypes.data, log.ctypes.data)
+    if s is None:
+        lib().vloam_oracle_ceres_solve(f.ctypes.data, len(f), x.ctypes.data, log.ctypes.data)
+    else:
+        sv = np.ascontiguousarray(s, np.float64)
+        lib().vloam_oracle_ceres_solve_s(f.ctypes.data, sv.ctypes.data, len(f), x.ctypes.data, log.ctypes.data)
     return x, log
 
 
-def evaluate(factors, x):
+def evaluate(factors, x, s=None):
     f = np.ascontiguousarray(factors, np.float64)
     x = np.ascontiguousarray(x, np.float64)
     cost = np.zeros(1)
     H = np.zeros((6, 6))
     g = np.zeros(6)
-    lib().vloam_oracle_evaluate(f.ctypes.data, len(f), x.ctypes.data, cost.ctypes.data, H.ctypes.data, g.ctypes.data)
+    if s is None:
+        lib().vloam_oracle_evaluate(f.ctypes.data, len(f), x.ctypes.data, cost.ctypes.data, H.ctypes.data, g.ctypes.data)
+    else:
+        sv = np.ascontiguousarray(s, np.float64)
+        lib().vloam_oracle_evaluate_s(f.ctypes.data, sv.ctypes.data, len(f), x.ctypes.data, cost.ctypes.data, H.ctypes.data, g.ctypes.data)
     return cost[0], H, g
 
 

@@ -206,12 +206,24 @@ void LaserOdometry::set_last(const Cloud& corner, const Cloud& surf) {
   systemInited = true;
 }
 
-// TransformToStart with DISTORTION == false (LO.cpp:152-173): s = 1,
-// Identity.slerp(1, q) == +-q, f64 math stored to f32.
-static inline P4 transform_to_start(const P4& pi, const double q[4], const double t[3]) {
+void slerp_identity_d(double t, const double q[4], double out[4]);  // oracle_ceres.cpp: Eigen's Identity.slerp(t, q)
+
+// interpolation ratio of a point (LO.cpp:156-160, 371, 475): (intensity - int(intensity)) is a float, SCAN_PERIOD a double
+static inline double point_s(const P4& pi, bool distortion) {
+  const double SCAN_PERIOD = 0.1;  // LO.h:93
+  if (distortion) return (pi.i - int(pi.i)) / SCAN_PERIOD;
+  return 1.0;
+}
+
+// TransformToStart (LO.cpp:152-173).  DISTORTION == false: s = 1 and Identity.slerp(1, q) == +-q;
+// DISTORTION == true: q_point_last = Identity.slerp(s, q), t_point_last = s * t.  f64 math stored to f32.
+static inline P4 transform_to_start(const P4& pi, const double q[4], const double t[3], bool distortion) {
   const double v[3] = {pi.x, pi.y, pi.z};
-  double r[3]; q_rot(q, v, r);
-  const double tl[3] = {1.0 * t[0], 1.0 * t[1], 1.0 * t[2]};
+  const double s = point_s(pi, distortion);
+  double qs[4] = {q[0], q[1], q[2], q[3]};
+  if (distortion) slerp_identity_d(s, q, qs);
+  double r[3]; q_rot(qs, v, r);
+  const double tl[3] = {s * t[0], s * t[1], s * t[2]};
   P4 po; po.x = (float)(r[0] + tl[0]); po.y = (float)(r[1] + tl[1]); po.z = (float)(r[2] + tl[2]); po.i = pi.i;
   return po;
 }
@@ -229,7 +241,7 @@ void LaserOdometry::associate(const double q[4], const double t[3], std::vector<
   corner_correspondence = 0; plane_correspondence = 0;
   const Cloud& CL = cornerLast; const Cloud& SL = surfLast;
   for (int i = 0; i < nSharp; ++i) {  // LO.cpp:282-383
-    const P4 pointSel = transform_to_start(cornerSharp[i], q, t);
+    const P4 pointSel = transform_to_start(cornerSharp[i], q, t, prm.distortion != 0);
     int nn; float nd;
     const int found = kdCorner ? kd_knn(kdCorner, CL, pointSel, 1, &nn, &nd) : brute_knn(CL, pointSel, 1, &nn, &nd);
     int closestPointInd = -1, minPointInd2 = -1;
@@ -256,12 +268,13 @@ void LaserOdometry::associate(const double q[4], const double t[3], std::vector<
       f.p[0] = cornerSharp[i].x; f.p[1] = cornerSharp[i].y; f.p[2] = cornerSharp[i].z;
       f.a[0] = CL[closestPointInd].x; f.a[1] = CL[closestPointInd].y; f.a[2] = CL[closestPointInd].z;
       f.b[0] = CL[minPointInd2].x; f.b[1] = CL[minPointInd2].y; f.b[2] = CL[minPointInd2].z;
+      f.s = point_s(cornerSharp[i], prm.distortion != 0); f.slerp = prm.distortion != 0;  // LO.cpp:368-372
       if (fs) fs->push_back(f);
       corner_correspondence++;
     }
   }
   for (int i = 0; i < nFlat; ++i) {  // LO.cpp:387-485
-    const P4 pointSel = transform_to_start(surfFlat[i], q, t);
+    const P4 pointSel = transform_to_start(surfFlat[i], q, t, prm.distortion != 0);
     int nn; float nd;
     const int found = kdSurf ? kd_knn(kdSurf, SL, pointSel, 1, &nn, &nd) : brute_knn(SL, pointSel, 1, &nn, &nd);
     int closestPointInd = -1, minPointInd2 = -1, minPointInd3 = -1;
@@ -295,6 +308,7 @@ void LaserOdometry::associate(const double q[4], const double t[3], std::vector<
       const double n2 = nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2];
       if (n2 > 0) { const double n = sqrt(n2); nrm[0] /= n; nrm[1] /= n; nrm[2] /= n; }  // Eigen normalize(): only if z > 0
       for (int k = 0; k < 3; ++k) { f.a[k] = J[k]; f.b[k] = nrm[k]; }
+      f.s = point_s(surfFlat[i], prm.distortion != 0); f.slerp = prm.distortion != 0;  // LO.cpp:472-476
       if (fs) fs->push_back(f);
       plane_correspondence++;
     }

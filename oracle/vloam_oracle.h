@@ -39,6 +39,7 @@ struct Params {
   float plane_res = 0.8f;        // mapping_plane_resolution (LM.cpp:101)
   int mapping_skip_frame = 1;    // (LO.cpp:53, LM.cpp:125)
   int knn_backend = 0;           // 0 = brute force (truth), 1 = KD-tree (timing baseline)
+  int distortion = 0;            // LaserOdometry::DISTORTION (LO.h:90, `false` in the reference): 1 = de-skew with s = relTime
 };
 
 // ---- third-party semantics -------------------------------------------------
@@ -62,6 +63,8 @@ struct Factor {
   double p[3];  // curr_point
   double a[3];  // edge: last_point_a | plane: last_point_j | planeNorm: unit normal
   double b[3];  // edge: last_point_b | plane: ljm_norm     | planeNorm: {d, -, -}
+  double s = 1.0;        // interpolation ratio of LidarEdgeFactor / LidarPlaneFactor (LF.hpp:17, 66); 1.0 unless DISTORTION
+  bool slerp = false;    // evaluate Identity.slerp(s, q) and s * t literally (LF.hpp:29-33, 86-90) instead of the s == 1 shortcut
 };
 struct SolveLog {
   int iterations = 0;       // attempted LM iterations (<= 4)

@@ -37,10 +37,14 @@ def check_plane(ok, prm, w, tol=1e-9):
             "max_err_d": float(ed.max()) if len(sel) else 0.0}
 
 
-def check_same(ok_a, prm_a, ok_b, prm_b, kind, tol=1e-12):
-    """Two implementations against each other on ALL sets (degenerate ones included): flags equal except where the
-    witness-free margin is at rounding level, parameters equal up to the line's sign freedom."""
+def check_same(ok_a, prm_a, ok_b, prm_b, kind, decided=None):
+    """Two implementations against each other on ALL sets (degenerate ones included): number of differing accept flags
+    (on the sets `decided` marks -- a knife-edge set such as a lattice with lambda_2 == 3 lambda_1 exactly is decided by the
+    last rounding of whichever eigen-solver runs), and the largest scaled parameter difference on sets both accept, up to
+    the line's sign freedom."""
     ok_a, ok_b = np.asarray(ok_a).astype(bool), np.asarray(ok_b).astype(bool)
+    if decided is not None:
+        ok_a = ok_a & decided; ok_b = ok_b & decided
     both = ok_a & ok_b
     if kind == 0:
         e1 = np.maximum(np.abs(prm_a[:, :3] - prm_b[:, :3]).max(1), np.abs(prm_a[:, 3:] - prm_b[:, 3:]).max(1))

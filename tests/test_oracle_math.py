@@ -275,3 +275,42 @@ def test_corridor_problems_are_ill_conditioned(op):
         assert ev[-1] / max(ev[0], 1e-300) >= 1e8, (kind, ev)
         x, log = op.ceres_solve(f, np.concatenate([q, t + [0.05, 0.02, -0.03]]))
         assert np.isfinite(x).all() and log[3] <= log[2]
+
+
+def test_deskew_functors_slerp_and_gradient(op):
+    """DISTORTION == true (LO.cpp:368-372, LF.hpp:29-36): the functors evaluate Identity.slerp(s, q) * p + s t.  With s == 1
+    the literal slerp path equals the shortcut exactly (value and Jacobian: SURVEY A.5); with random s the dual-number
+    gradient matches central differences of the robust cost; s = 0 removes the pose from the residual altogether."""
+    from scipy.spatial.transform import Rotation as R
+    rng = np.random.RandomState(3)
+    q = R.from_euler("xyz", [0.02, -0.03, 0.05]).as_quat()
+    t = np.array([0.9, -0.2, 0.1])
+    f = make_factors(rng, q, t, 60, 60, 0, noise=0.05)
+    for x in (np.concatenate([R.from_euler("xyz", [0.03, -0.01, 0.02]).as_quat(), [0.5, -0.1, 0.3]]),
+              np.concatenate([-R.from_euler("xyz", [0.3, -0.2, 0.4]).as_quat(), [0.5, -0.1, 0.3]]),      # w < 0: slerp flips scale1
+              np.array([0, 0, 0, 1.0, 0.4, 0.0, 0.0])):                                                    # |w| >= 1 - eps: linear branch
+        c0, H0, g0 = op.evaluate(f, x)
+        c1, H1, g1 = op.evaluate(f, x, np.ones(len(f)))
+        assert c0 == c1 and (H0 == H1).all() and (g0 == g1).all()
+        s = rng.uniform(0, 1, len(f))
+        cost, H, g = op.evaluate(f, x, s)
+        eps = 1e-6
+        for k in range(6):
+            d = np.zeros(6); d[k] = eps
+            num = (op.evaluate(f, plus(x, d), s)[0] - op.evaluate(f, plus(x, -d), s)[0]) / (2 * eps)
+            assert abs(num - g[k]) < 2e-5 * max(1.0, abs(g[k])), (k, num, g[k])
+        _, Hz, gz = op.evaluate(f, x, np.zeros(len(f)))
+        assert np.abs(Hz).max() == 0 and np.abs(gz).max() == 0
+
+
+def test_deskew_pipeline_runs_and_differs(op, synth, street):
+    """distortion = 1 changes the odometry (s < 1 for most points) but keeps the pipeline sane on a static-snapshot sweep."""
+    traj = synth.trajectory(3)
+    a = op.Oracle(n_scans=16, minimum_range=0.3, line_res=0.2, plane_res=0.4)
+    b = op.Oracle(n_scans=16, minimum_range=0.3, line_res=0.2, plane_res=0.4, distortion=1)
+    for k in range(3):
+        scan = street.scan(0, traj[k], 1000 + k)
+        a.process(scan); b.process(scan)
+    pa, pb = a.get("lo.pose"), b.get("lo.pose")
+    assert np.isfinite(pb).all() and np.abs(pa - pb).max() > 1e-6
+    assert (a.get("sr.sharp") == b.get("sr.sharp")).all()   # scan registration is not affected

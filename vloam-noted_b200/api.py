@@ -15,7 +15,7 @@ EXPORTS = [
     "vloam_b200_scan_registration", "vloam_b200_prefetch_scan", "vloam_b200_prefetch_scan_device", "vloam_b200_scan_registration_device", "vloam_b200_get_cloud", "vloam_b200_laser_odometry",
     "vloam_b200_laser_mapping", "vloam_b200_process_frame", "vloam_b200_process_frame_device", "vloam_b200_synchronize",
     "vloam_b200_stream", "vloam_b200_kernel_launches", "vloam_b200_set_timing", "vloam_b200_stage_ms", "vloam_b200_debug_get",
-    "vloam_b200_debug_set", "vloam_b200_profile_kernel", "vloam_b200_profile_result", "vloam_b200_profile_table", "vloam_b200_profile_timeline", "vloam_b200_register_full_cloud", "vloam_b200_lo_associate", "vloam_b200_voxel_grid", "vloam_b200_evaluate", "vloam_b200_solve", "vloam_b200_fit",
+    "vloam_b200_debug_set", "vloam_b200_profile_kernel", "vloam_b200_profile_result", "vloam_b200_profile_table", "vloam_b200_profile_timeline", "vloam_b200_register_full_cloud", "vloam_b200_lo_associate", "vloam_b200_voxel_grid", "vloam_b200_evaluate", "vloam_b200_solve", "vloam_b200_fit", "vloam_b200_evaluate_deskew", "vloam_b200_solve_deskew",
 ]
 
 
@@ -72,6 +72,8 @@ def load_lib(build=False):
     L.vloam_b200_voxel_grid.argtypes = [vp, vp, ci, ctypes.c_float, vp, ci]
     L.vloam_b200_evaluate.argtypes = [vp, vp, ci, vp, vp, vp, vp]
     L.vloam_b200_solve.argtypes = [vp, vp, ci, vp, vp]
+    L.vloam_b200_evaluate_deskew.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp]
+    L.vloam_b200_solve_deskew.argtypes = [vp, vp, vp, ci, vp, vp]
     L.vloam_b200_register_full_cloud.argtypes = [vp, vp, ci]
     L.vloam_b200_fit.argtypes = [vp, vp, ci, ci, vp, vp]
     _lib = L
@@ -103,9 +105,9 @@ def _decode(name, raw):
 class Context:
     """One vloam_b200_ctx: one sequence (several CUDA streams and a helper thread inside, include/vloam_b200.h)."""
 
-    def __init__(self, n_scans=64, minimum_range=5.0, line_res=0.4, plane_res=0.8, mapping_skip_frame=1, device=0):
+    def __init__(self, n_scans=64, minimum_range=5.0, line_res=0.4, plane_res=0.8, mapping_skip_frame=1, device=0, distortion=0):
         self.L = load_lib()
-        self.params = Params(n_scans, minimum_range, line_res, plane_res, mapping_skip_frame, 0)
+        self.params = Params(n_scans, minimum_range, line_res, plane_res, mapping_skip_frame, 1 if distortion else 0)  # reserved: VLOAM_FLAG_DISTORTION
         h = ctypes.c_void_p()
         r = self.L.vloam_b200_create(ctypes.byref(self.params), device, ctypes.byref(h))
         if r != 0:
@@ -249,11 +251,13 @@ class Context:
         n = self._chk(self.L.vloam_b200_voxel_grid(self.h, c.ctypes.data, len(c), leaf, out.ctypes.data, len(out)))
         return out[:n].copy()
 
-    def evaluate(self, factors, x):
+    def evaluate(self, factors, x, s=None):
         f = np.ascontiguousarray(factors, np.float64)
         x = np.ascontiguousarray(x, np.float64)
         cost, H, g = np.zeros(1), np.zeros((6, 6)), np.zeros(6)
-        self._chk(self.L.vloam_b200_evaluate(self.h, f.ctypes.data, len(f), x.ctypes.data, cost.ctypes.data, H.ctypes.data, g.ctypes.data))
+        sv = None if s is None else np.ascontiguousarray(s, np.float64)
+        self._chk(self.L.vloam_b200_evaluate_deskew(self.h, f.ctypes.data, None if sv is None else sv.ctypes.data, len(f), x.ctypes.data,
+                                                    cost.ctypes.data, H.ctypes.data, g.ctypes.data))
         return cost[0], H, g
 
     def fit(self, near, kind):
@@ -264,11 +268,12 @@ class Context:
         self._chk(self.L.vloam_b200_fit(self.h, a.ctypes.data, len(a), kind, ok.ctypes.data, prm.ctypes.data))
         return ok[:len(a)], prm[:len(a)]
 
-    def solve(self, factors, x):
+    def solve(self, factors, x, s=None):
         f = np.ascontiguousarray(factors, np.float64)
         x = np.array(x, np.float64)
         log = np.zeros(4)
-        self._chk(self.L.vloam_b200_solve(self.h, f.ctypes.data, len(f), x.ctypes.data, log.ctypes.data))
+        sv = None if s is None else np.ascontiguousarray(s, np.float64)
+        self._chk(self.L.vloam_b200_solve_deskew(self.h, f.ctypes.data, None if sv is None else sv.ctypes.data, len(f), x.ctypes.data, log.ctypes.data))
         return x, log
 
 

@@ -65,6 +65,7 @@ int vloam_b200_create(const vloam_b200_params* p, int device, vloam_b200_ctx** o
   // SR.cpp:58-61, 255-259: only 16 / 32 / 64 beams (128 = builder extension)
   if (p->n_scans != 16 && p->n_scans != 32 && p->n_scans != 64 && p->n_scans != 128) return VLOAM_E_INVALID;
   if (!(p->line_res >= 0.05f) || !(p->plane_res >= 0.05f) || p->mapping_skip_frame < 1) return VLOAM_E_INVALID;
+  if (p->reserved & ~VLOAM_FLAG_DISTORTION) return VLOAM_E_INVALID;
   VL_CUDA_CREATE(cudaSetDevice(device));
   vloam_b200_ctx* c = new vloam_b200_ctx();  // value-initialised: every pointer / handle starts out null
   const int r = create_impl(c, p, device);
@@ -174,7 +175,7 @@ void vloam_b200_destroy(vloam_b200_ctx* c) {
                      c->dbgKnnD2[0][1].p, c->dbgKnnD2[1][0].p, c->dbgKnnD2[1][1].p, c->dbgKnnOk[0][0].p, c->dbgKnnOk[0][1].p, c->dbgKnnOk[1][0].p,
                      c->dbgKnnOk[1][1].p};
   for (void* p : singles) if (p) cudaFree(p);
-  void* bufs[] = {c->lessSharp[0].p, c->lessSharp[1].p, c->lessSharp[2].p, c->lessFlat[0].p, c->lessFlat[1].p, c->lessFlat[2].p, c->loCornerIdx.p, c->loSurfIdx.p, c->factors.p, c->factorValid.p, c->evalPartials.p,
+  void* bufs[] = {c->lessSharp[0].p, c->lessSharp[1].p, c->lessSharp[2].p, c->lessFlat[0].p, c->lessFlat[1].p, c->lessFlat[2].p, c->loCornerIdx.p, c->loSurfIdx.p, c->factors.p, c->factorS.p, c->factorValid.p, c->evalPartials.p,
                   c->poolC.p, c->poolS.p, c->stackC.p, c->stackS.p, c->stackCN.p, c->stackSN.p, c->fromMapC.p, c->fromMapS.p, c->knnIdx.p, c->knnD2.p, c->knnOk.p,
                   c->vKeys.p, c->vKeys2.p, c->vHead.p, c->vScan.p, c->vScan2.p, c->vOut.p, c->vIn.p, c->regOut.p, c->tailKeys.p, c->staging.p};
   for (void* p : bufs) if (p) cudaFree(p);
@@ -667,12 +668,20 @@ static int upload_factors(vloam_b200_ctx* c, const double* factors, int nf) {
   return VLOAM_OK;
 }
 
-int vloam_b200_evaluate(vloam_b200_ctx* c, const double* factors, int nf, const double* x, double* cost, double* H, double* g) {
-  if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
+static int upload_s(vloam_b200_ctx* c, const double* s, int nf) {
+  VL_TRY(vl_reserve(c, c->factorS, (size_t)max(nf, 1)));
+  if (nf) { VL_CUDA(cudaMemcpyAsync(c->factorS.p, s, (size_t)nf * 8, cudaMemcpyHostToDevice, c->stream)); VL_CUDA(cudaStreamSynchronize(c->stream)); }
+  return VLOAM_OK;
+}
+
+int vloam_b200_evaluate_deskew(vloam_b200_ctx* c, const double* factors, const double* s, int nf, const double* x, double* cost, double* H, double* g) {
+  if (!c) return VLOAM_E_INVALID;
+  VL_TRY(vloam_b200_synchronize(c));
   VL_TRY(upload_factors(c, factors, nf));
+  if (s) VL_TRY(upload_s(c, s, nf));
   double* d_x = reinterpret_cast<double*>(c->vScalars + 32);
   VL_CUDA(cudaMemcpyAsync(d_x, x, 56, cudaMemcpyHostToDevice, c->stream));
-  VL_TRY(vl_evaluate_once(c, nf, d_x, c->evalOut));
+  VL_TRY(vl_evaluate_once(c, nf, d_x, c->evalOut, s ? c->factorS.p : nullptr));
   EvalOut h;
   VL_CUDA(cudaMemcpyAsync(&h, c->evalOut, sizeof h, cudaMemcpyDeviceToHost, c->stream));
   VL_CUDA(cudaStreamSynchronize(c->stream));
@@ -681,6 +690,27 @@ int vloam_b200_evaluate(vloam_b200_ctx* c, const double* factors, int nf, const 
   for (int i = 0; i < 6; ++i) g[i] = h.v[21 + i];
   *cost = h.v[27];
   return VLOAM_OK;
+}
+int vloam_b200_evaluate(vloam_b200_ctx* c, const double* factors, int nf, const double* x, double* cost, double* H, double* g) {
+  return vloam_b200_evaluate_deskew(c, factors, nullptr, nf, x, cost, H, g);
+}
+
+int vloam_b200_solve_deskew(vloam_b200_ctx* c, const double* factors, const double* s, int nf, double* x, double* log4) {
+  if (!c) return VLOAM_E_INVALID;
+  VL_TRY(vloam_b200_synchronize(c));
+  VL_TRY(upload_factors(c, factors, nf));
+  if (s) VL_TRY(upload_s(c, s, nf));
+  double* d_x = reinterpret_cast<double*>(c->vScalars + 32);
+  VL_CUDA(cudaMemcpyAsync(d_x, x, 56, cudaMemcpyHostToDevice, c->stream));
+  double costs[2] = {0, 0};
+  VL_TRY(vl_solve(c, nf, nullptr, d_x, costs, 0, s ? c->factorS.p : nullptr));
+  VL_CUDA(cudaMemcpyAsync(x, d_x, 56, cudaMemcpyDeviceToHost, c->stream));
+  VL_CUDA(cudaStreamSynchronize(c->stream));
+  if (log4) { log4[0] = nf ? c->h_lms->iter : 0; log4[1] = 0; log4[2] = costs[0]; log4[3] = costs[1]; }
+  return VLOAM_OK;
+}
+int vloam_b200_solve(vloam_b200_ctx* c, const double* factors, int nf, double* x, double* log4) {
+  return vloam_b200_solve_deskew(c, factors, nullptr, nf, x, log4);
 }
 
 // n five-point sets (float32[n][5][3]) through the line (kind 0, LM.cpp:559-603) or plane (kind 1, LM.cpp:637-680) fit of the
@@ -701,19 +731,6 @@ int vloam_b200_fit(vloam_b200_ctx* c, const float* near, int n, int kind, int* o
   if (r == VLOAM_E_CUDA) snprintf(c->err, sizeof c->err, "vloam_b200_fit: %s", cudaGetErrorString(cudaGetLastError()));
   cudaFree(d_near); cudaFree(d_ok); cudaFree(d_prm);
   return r;
-}
-
-int vloam_b200_solve(vloam_b200_ctx* c, const double* factors, int nf, double* x, double* log4) {
-  if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
-  VL_TRY(upload_factors(c, factors, nf));
-  double* d_x = reinterpret_cast<double*>(c->vScalars + 32);
-  VL_CUDA(cudaMemcpyAsync(d_x, x, 56, cudaMemcpyHostToDevice, c->stream));
-  double costs[2] = {0, 0};
-  VL_TRY(vl_solve(c, nf, nullptr, d_x, costs));
-  VL_CUDA(cudaMemcpyAsync(x, d_x, 56, cudaMemcpyDeviceToHost, c->stream));
-  VL_CUDA(cudaStreamSynchronize(c->stream));
-  if (log4) { log4[0] = nf ? c->h_lms->iter : 0; log4[1] = 0; log4[2] = costs[0]; log4[3] = costs[1]; }
-  return VLOAM_OK;
 }
 
 }  // extern "C"

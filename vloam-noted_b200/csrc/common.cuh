@@ -180,6 +180,7 @@ struct vloam_b200_ctx {
   int lastSet;
   DBuf<int> loCornerIdx, loSurfIdx;   // association results (2 / 3 ints per query)
   DBuf<double> factors;               // 10 doubles per factor slot
+  DBuf<double> factorS;               // DISTORTION only: interpolation ratio s of every odometry factor slot (LO.cpp:368-372, 472-476)
   DBuf<int> factorValid;
   DBuf<EvalOut> evalPartials;
   EvalOut* evalOut;
@@ -361,9 +362,11 @@ int vl_voxel_grid_device(vloam_b200_ctx* c, const float4* d_in, int n, const int
 
 // solver (lm_solver.cu): evaluates factor slots [0, nslots) with validity flags.
 // nslots: host bound on the factor slots; d_nslots (device, may be null): actual count, min() of both is used
+// d_s (device, may be null): per-slot interpolation ratio; non-null = the functors slerp q by s and scale t by s (DISTORTION)
 int vl_solve(vloam_b200_ctx* c, int nslots, const int* d_nslots, double* d_x_inout, double* costs2 /* host, may be null */,
-             int hint = 0 /* last known actual slot count, 0 = none */);
-int vl_evaluate_once(vloam_b200_ctx* c, int nslots, const double* d_x, EvalOut* d_out);
+             int hint = 0 /* last known actual slot count, 0 = none */, const double* d_s = nullptr);
+int vl_evaluate_once(vloam_b200_ctx* c, int nslots, const double* d_x, EvalOut* d_out, const double* d_s = nullptr);
+static inline bool vl_distortion(const vloam_b200_ctx* c) { return (c->prm.reserved & 1) != 0; }  // LaserOdometry::DISTORTION (LO.h:90)
 
 // ---- shared device helpers -----------------------------------------------------
 #ifdef __CUDACC__
@@ -390,6 +393,39 @@ __device__ __forceinline__ void vl_qmul(const double a[4], const double b[4], do
   const double z = aw * bz + az * bw + ax * by - ay * bx;
   o[0] = x; o[1] = y; o[2] = z; o[3] = w;
 }
+// Eigen::Quaterniond::Identity().slerp(t, q) (Eigen/src/Geometry/Quaternion.h), used by TransformToStart and the odometry
+// functors when DISTORTION is on (LO.cpp:163, LF.hpp:29-33, 86-90): d = w; |d| >= 1 - eps -> (1 - t) I + t q, else
+// theta = acos(|d|), scale0 = sin((1 - t) theta) / sin(theta), scale1 = sin(t theta) / sin(theta); d < 0 flips scale1.
+__device__ __forceinline__ void vl_slerp_identity(double t, const double q[4], double out[4]) {
+  const double one = 1.0 - 2.220446049250313e-16;
+  const double d = q[3], absD = fabs(d);
+  double scale0, scale1;
+  if (absD >= one) { scale0 = 1.0 - t; scale1 = t; }
+  else {
+    const double theta = acos(absD), sinTheta = sin(theta);
+    scale0 = sin((1.0 - t) * theta) / sinTheta;
+    scale1 = sin(t * theta) / sinTheta;
+  }
+  if (d < 0.0) scale1 = -scale1;
+  out[0] = scale1 * q[0]; out[1] = scale1 * q[1]; out[2] = scale1 * q[2]; out[3] = scale0 + scale1 * q[3];
+}
+// interpolation ratio of a point: (intensity - int(intensity)) is a float, SCAN_PERIOD a double (LO.cpp:156-160)
+__device__ __forceinline__ double vl_point_s(float intensity) { return (double)__fsub_rn(intensity, (float)(int)intensity) / 0.1; }
+// TransformToStart (LO.cpp:152-173): pose = {q_last_curr, t_last_curr}; deskew: slerp(s, q), s * t with s from the point
+__device__ __forceinline__ void vl_transform_to_start(const double* pose, const float4 p, int deskew, float& sx, float& sy, float& sz) {
+  double r[3];
+  if (deskew) {
+    const double s = vl_point_s(p.w);
+    double qs[4];
+    vl_slerp_identity(s, pose, qs);
+    vl_qrot(qs, (double)p.x, (double)p.y, (double)p.z, r);
+    sx = (float)(r[0] + s * pose[4]); sy = (float)(r[1] + s * pose[5]); sz = (float)(r[2] + s * pose[6]);
+  } else {
+    vl_qrot(pose, (double)p.x, (double)p.y, (double)p.z, r);
+    sx = (float)(r[0] + pose[4]); sy = (float)(r[1] + pose[5]); sz = (float)(r[2] + pose[6]);
+  }
+}
+
 // Visit every element of up to 32 index ranges of ARRAY (float4) with all lanes busy, 128 elements per step.
 // Lane r owns range [myBeg, myBeg + myLen) (myLen = 0 when it has none), so the look-ups that produced
 // the ranges were issued together (one memory latency, not one per range).  Non-empty ranges are compacted

@@ -75,9 +75,10 @@ __global__ void lo_ring_table_init(int* __restrict__ tbl) {
 template <bool SURF>
 __global__ void __launch_bounds__(LO_QPB * 32) lo_assoc(const float4* __restrict__ query, int nq, const float4* __restrict__ target, int nt,
                                                         const double* __restrict__ pose, const int* __restrict__ tbl, int* __restrict__ outIdx,
-                                                        double* __restrict__ factors, int* __restrict__ valid, int slotBase) {
+                                                        double* __restrict__ factors, int* __restrict__ valid, int slotBase, double* __restrict__ factorS) {
   VL_PDL_WAIT();
 
+  const int deskew = factorS != nullptr;
   __shared__ float sq[LO_QPB][3];
   __shared__ Best sbest[LO_QPB][LO_QPB];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -85,12 +86,7 @@ __global__ void __launch_bounds__(LO_QPB * 32) lo_assoc(const float4* __restrict
   if (threadIdx.x < LO_QPB) {
     const int qi = q0 + threadIdx.x;
     float sx = 0.f, sy = 0.f, sz = 0.f;
-    if (qi < nq) {  // TransformToStart, DISTORTION == false (LO.cpp:152-173): f64 math, f32 store
-      const float4 p = query[qi];
-      double r[3];
-      vl_qrot(pose, (double)p.x, (double)p.y, (double)p.z, r);
-      sx = (float)(r[0] + pose[4]); sy = (float)(r[1] + pose[5]); sz = (float)(r[2] + pose[6]);
-    }
+    if (qi < nq) vl_transform_to_start(pose, query[qi], deskew, sx, sy, sz);  // TransformToStart (LO.cpp:152-173): f64 math, f32 store
     sq[threadIdx.x][0] = sx; sq[threadIdx.x][1] = sy; sq[threadIdx.x][2] = sz;
   }
   __syncthreads();
@@ -212,6 +208,7 @@ __global__ void __launch_bounds__(LO_QPB * 32) lo_assoc(const float4* __restrict
   const int slot = slotBase + qi;
   double* f = factors + (size_t)slot * 10;
   const float4 cp = query[qi];
+  if (deskew) factorS[slot] = vl_point_s(cp.w);
   if (SURF) {
     outIdx[qi * 3] = closest; outIdx[qi * 3 + 1] = ind2; outIdx[qi * 3 + 2] = ind3;
     const bool ok = closest >= 0 && ind2 >= 0 && ind3 >= 0;
@@ -339,13 +336,12 @@ template <bool SURF>
 __device__ __forceinline__ void lo_assoc_grid_dev(int qi, int lane, const float4* __restrict__ query, const float4* __restrict__ target,
                                                   const float4* __restrict__ sorted, const int* __restrict__ cellStart,
                                                   const double* __restrict__ pose, int* __restrict__ outIdx,
-                                                  double* __restrict__ factors, int* __restrict__ valid, int slotBase) {
+                                                  double* __restrict__ factors, int* __restrict__ valid, int slotBase, double* __restrict__ factorS) {
   const long long tr0 = g_lo_trace ? clock64() : 0;
   int trFlags = 0;
   const float4 cp = query[qi];
-  double r[3];
-  vl_qrot(pose, (double)cp.x, (double)cp.y, (double)cp.z, r);  // TransformToStart (LO.cpp:152-173)
-  const float sx = (float)(r[0] + pose[4]), sy = (float)(r[1] + pose[5]), sz = (float)(r[2] + pose[6]);
+  float sx, sy, sz;
+  vl_transform_to_start(pose, cp, factorS != nullptr, sx, sy, sz);  // TransformToStart (LO.cpp:152-173)
   const int cx = log_cx(sx), cy = log_cx(sy), cz = log_cz(sz);
   const int cellBase = SURF ? LOG_NCELL : 0;
   // ---- pass A: exact nearest neighbour, ties by index
@@ -431,6 +427,7 @@ __device__ __forceinline__ void lo_assoc_grid_dev(int qi, int lane, const float4
   const int slot = slotBase + qi;
   if (g_lo_trace) { g_lo_trace[2 * slot] = (int)(clock64() - tr0); g_lo_trace[2 * slot + 1] = trFlags | (SURF ? 4 : 0); }
   double* f = factors + (size_t)slot * 10;
+  if (factorS) factorS[slot] = vl_point_s(cp.w);
   if (SURF) {
     outIdx[qi * 3] = closest; outIdx[qi * 3 + 1] = ind2; outIdx[qi * 3 + 2] = ind3;
     const bool ok = closest >= 0 && ind2 >= 0 && ind3 >= 0;
@@ -461,13 +458,13 @@ template <bool SURF>
 __global__ void __launch_bounds__(256) lo_assoc_grid(const float4* __restrict__ query, int nq, const float4* __restrict__ target,
                                                      const float4* __restrict__ sorted, const int* __restrict__ cellStart,
                                                      const double* __restrict__ pose, int* __restrict__ outIdx,
-                                                     double* __restrict__ factors, int* __restrict__ valid, int slotBase) {
+                                                     double* __restrict__ factors, int* __restrict__ valid, int slotBase, double* __restrict__ factorS) {
   VL_PDL_WAIT();
 
   const int lane = threadIdx.x & 31;
   const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (qi >= nq) return;
-  lo_assoc_grid_dev<SURF>(qi, lane, query, target, sorted, cellStart, pose, outIdx, factors, valid, slotBase);
+  lo_assoc_grid_dev<SURF>(qi, lane, query, target, sorted, cellStart, pose, outIdx, factors, valid, slotBase, factorS);
 }
 
 // sharp and flat queries in one launch: warps [0, nS) run the corner association, [nS, nS + nF) the surf one
@@ -475,15 +472,15 @@ __global__ void __launch_bounds__(256) lo_assoc_grid_both(const float4* __restri
                                                           const SrScalars* __restrict__ srs, const float4* __restrict__ cornerLast, const float4* __restrict__ surfLast,
                                                           const float4* __restrict__ sorted, const int* __restrict__ cellStart,
                                                           const double* __restrict__ pose, int* __restrict__ cornerIdx, int* __restrict__ surfIdx,
-                                                          double* __restrict__ factors, int* __restrict__ valid) {
+                                                          double* __restrict__ factors, int* __restrict__ valid, double* __restrict__ factorS) {
   VL_PDL_WAIT();
 
   const int lane = threadIdx.x & 31;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nS = srs->nSharp, nF = srs->nFlat;  // device-side counts: the host may not know them yet
   if (w >= nS + nF) { if (w < slotBound && lane == 0) valid[w] = 0; return; }
-  if (w < nS) lo_assoc_grid_dev<false>(w, lane, sharp, cornerLast, sorted, cellStart, pose, cornerIdx, factors, valid, 0);
-  else if (w < nS + nF) lo_assoc_grid_dev<true>(w - nS, lane, flat, surfLast, sorted, cellStart, pose, surfIdx, factors, valid, nS);
+  if (w < nS) lo_assoc_grid_dev<false>(w, lane, sharp, cornerLast, sorted, cellStart, pose, cornerIdx, factors, valid, 0, factorS);
+  else if (w < nS + nF) lo_assoc_grid_dev<true>(w - nS, lane, flat, surfLast, sorted, cellStart, pose, surfIdx, factors, valid, nS, factorS);
 }
 
 __global__ void lo_accumulate(LoScalars* s) {
@@ -544,6 +541,8 @@ static int lo_associate(vloam_b200_ctx* c, const double* d_pose, const float4* c
   VL_TRY(vl_reserve(c, c->loSurfIdx, (size_t)max(nF, 1) * 3));
   VL_TRY(vl_reserve(c, c->factors, (size_t)max(nS + nF, 1) * 10));
   VL_TRY(vl_reserve(c, c->factorValid, (size_t)max(nS + nF, 1)));
+  if (vl_distortion(c)) VL_TRY(vl_reserve(c, c->factorS, (size_t)max(nS + nF, 1)));
+  double* fS = vl_distortion(c) ? c->factorS.p : nullptr;
   // h_vScalars[8/9]: int(intensity) of the corner / surf cloud is non-decreasing (read after a sync point)
   const int set = c->lastSet;
   const bool gridC = c->loGridValid[set] && (c->loAssumeMonotone || c->h_vScalars[8 + 2 * set] != 0);
@@ -554,26 +553,26 @@ static int lo_associate(vloam_b200_ctx* c, const double* d_pose, const float4* c
   if (gridC && gridS && nS + nF > 0) {
     VL_BYTES(16.0 * ((double)c->nSharp + c->nFlat + nCL + nSL));  // SURVEY 8(d) B_lo, one pass: every query and every point of the two last clouds once
     VL_LAUNCH(lo_assoc_grid_both, vl_div_up((long long)(nS + nF) * 32, 256), 256, 0, c->sharp.p, c->flat.p, nS + nF, c->srs, cornerLast, surfLast,
-              gsorted, start, d_pose, c->loCornerIdx.p, c->loSurfIdx.p, c->factors.p, c->factorValid.p);
+              gsorted, start, d_pose, c->loCornerIdx.p, c->loSurfIdx.p, c->factors.p, c->factorValid.p, fS);
     VL_CUDA(cudaGetLastError());
     return VLOAM_OK;
   }
   if (nS > 0) {
     if (gridC)
       VL_LAUNCH(lo_assoc_grid<false>, vl_div_up((long long)nS * 32, 256), 256, 0, c->sharp.p, nS, cornerLast, gsorted, start, d_pose,
-                c->loCornerIdx.p, c->factors.p, c->factorValid.p, 0);
+                c->loCornerIdx.p, c->factors.p, c->factorValid.p, 0, fS);
     else
       VL_LAUNCH(lo_assoc<false>, vl_div_up(nS, LO_QPB), LO_QPB * 32, 0, c->sharp.p, nS, cornerLast, nCL, d_pose, rtbl, c->loCornerIdx.p,
-                c->factors.p, c->factorValid.p, 0);
+                c->factors.p, c->factorValid.p, 0, fS);
   }
   if (nF > 0) {
     if (gridS) {
       VL_BYTES(16.0 * ((double)nF + nSL));
       VL_LAUNCH(lo_assoc_grid<true>, vl_div_up((long long)nF * 32, 256), 256, 0, c->flat.p, nF, surfLast, gsorted, start, d_pose,
-                c->loSurfIdx.p, c->factors.p, c->factorValid.p, nS);
+                c->loSurfIdx.p, c->factors.p, c->factorValid.p, nS, fS);
     } else
       VL_LAUNCH(lo_assoc<true>, vl_div_up(nF, LO_QPB), LO_QPB * 32, 0, c->flat.p, nF, surfLast, nSL, d_pose, rtbl + (LO_TBL + 1), c->loSurfIdx.p,
-                c->factors.p, c->factorValid.p, nS);
+                c->factors.p, c->factorValid.p, nS, fS);
   }
   VL_CUDA(cudaGetLastError());
   return VLOAM_OK;
@@ -627,7 +626,8 @@ static int lo_queue_solve(vloam_b200_ctx* c, const double* prior_q, const double
         VL_CUDA(cudaMemcpyAsync(c->dbgLoSurf[pass].p, c->loSurfIdx.p, sizeof(int) * 3 * c->nFlat, cudaMemcpyDeviceToDevice, c->stream));
       }
       const int nslots = c->sr_counts_valid ? c->nSharp + c->nFlat : lo_sharp_bound(c) + lo_flat_bound(c);
-      VL_TRY(vl_solve(c, nslots, &c->srs->nQueries, d_pose, vl_debug_capture(c) ? &c->dbgLoCost[pass * 2] : nullptr, c->nSharp + c->nFlat));
+      VL_TRY(vl_solve(c, nslots, &c->srs->nQueries, d_pose, vl_debug_capture(c) ? &c->dbgLoCost[pass * 2] : nullptr, c->nSharp + c->nFlat,
+                      vl_distortion(c) ? c->factorS.p : nullptr));
     }
     VL_LAUNCH(lo_accumulate, 1, 32, 0, c->los);
   VL_CUDA(cudaEventRecord(c->evLoSolve, c->stream));

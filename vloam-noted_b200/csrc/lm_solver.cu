@@ -67,6 +67,90 @@ __device__ __forceinline__ void lm_factor(const double* __restrict__ f, const do
   }
 }
 
+// DISTORTION == true (LO.cpp:368-372, 472-476): the functors evaluate lp = Identity.slerp(s, q) * cp + s t (LF.hpp:29-36, 86-93),
+// and Ceres differentiates THROUGH the slerp with respect to the four quaternion coefficients before contracting with the
+// 4x3 plus-Jacobian.  Analytic form of that chain (validated against the oracle's dual numbers, which run Eigen's slerp on
+// ceres::Jet-like duals): q_s = sc0 e_w + sc1 q with sc0, sc1 functions of w only (theta = acos|w|);
+//   V(U, W) = p + 2 W (U x p) + 2 U x (U x p)   (Eigen's quaternion * vector, no normalisation)
+//   dV/dW = 2 (U x p),   dV/dU = -2 W [p]x - 2 [U x p]x - 2 [U]x [p]x
+//   G = dV/dq (3x4): columns x,y,z = dV/dU * sc1; column w = dV/dU u sc1' + dV/dW (sc0' + sc1 + w sc1')
+//   local Jacobian = D [ G P(q) | s I ] with D = d r / d lp ([w_dir]x for the edge factor, n^T for the plane factor).
+__device__ void lm_factor_deskew(const double* __restrict__ f, const double s, const double* __restrict__ x, FactorRow& o) {
+  const int type = (int)f[0];
+  const double p[3] = {f[1], f[2], f[3]};
+  const double qx = x[0], qy = x[1], qz = x[2], qw = x[3];
+  const double one = 1.0 - DBL_EPSILON;
+  const double absD = fabs(qw);
+  double sc0, sc1, dsc0 = 0.0, dsc1 = 0.0;
+  if (absD >= one) { sc0 = 1.0 - s; sc1 = s; }
+  else {
+    const double th = acos(absD), sth = sin(th), cth = cos(th);
+    const double a0 = (1.0 - s) * th, a1 = s * th;
+    const double s0 = sin(a0), s1 = sin(a1);
+    sc0 = s0 / sth; sc1 = s1 / sth;
+    const double dth = (qw < 0.0 ? 1.0 : -1.0) / sqrt(1.0 - absD * absD);  // d acos|w| / dw
+    dsc0 = (((1.0 - s) * cos(a0)) * sth - s0 * cth) / (sth * sth) * dth;
+    dsc1 = ((s * cos(a1)) * sth - s1 * cth) / (sth * sth) * dth;
+  }
+  if (qw < 0.0) { sc1 = -sc1; dsc1 = -dsc1; }
+  const double qs[4] = {sc1 * qx, sc1 * qy, sc1 * qz, sc0 + sc1 * qw};
+  double rp[3];
+  vl_qrot(qs, p[0], p[1], p[2], rp);
+  const double lp[3] = {rp[0] + s * x[4], rp[1] + s * x[5], rp[2] + s * x[6]};
+  const double U[3] = {qs[0], qs[1], qs[2]}, W = qs[3];
+  const double up[3] = {U[1] * p[2] - U[2] * p[1], U[2] * p[0] - U[0] * p[2], U[0] * p[1] - U[1] * p[0]};  // U x p
+  // A = dV/dU = -2 (W [p]x + [U x p]x + [U]x [p]x);  [U]x [p]x = p U^T - (U . p) I
+  const double udp = U[0] * p[0] + U[1] * p[1] + U[2] * p[2];
+  double A[3][3];
+  const double m[3] = {W * p[0] + up[0], W * p[1] + up[1], W * p[2] + up[2]};  // [m]x = W [p]x + [U x p]x
+  A[0][0] = -2.0 * (p[0] * U[0] - udp);            A[0][1] = -2.0 * (-m[2] + p[0] * U[1]);        A[0][2] = -2.0 * (m[1] + p[0] * U[2]);
+  A[1][0] = -2.0 * (m[2] + p[1] * U[0]);           A[1][1] = -2.0 * (p[1] * U[1] - udp);          A[1][2] = -2.0 * (-m[0] + p[1] * U[2]);
+  A[2][0] = -2.0 * (-m[1] + p[2] * U[0]);          A[2][1] = -2.0 * (m[0] + p[2] * U[1]);         A[2][2] = -2.0 * (p[2] * U[2] - udp);
+  double G[3][4];
+  const double kw = dsc0 + sc1 + qw * dsc1;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    G[i][0] = A[i][0] * sc1; G[i][1] = A[i][1] * sc1; G[i][2] = A[i][2] * sc1;
+    G[i][3] = (A[i][0] * qx + A[i][1] * qy + A[i][2] * qz) * dsc1 + 2.0 * up[i] * kw;
+  }
+  // L = G P(q), P rows: [w, z, -y; -z, w, x; y, -x, w; -x, -y, -z]  (EigenQuaternionParameterization)
+  double L[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    L[i][0] = G[i][0] * qw - G[i][1] * qz + G[i][2] * qy - G[i][3] * qx;
+    L[i][1] = G[i][0] * qz + G[i][1] * qw - G[i][2] * qx - G[i][3] * qy;
+    L[i][2] = -G[i][0] * qy + G[i][1] * qx + G[i][2] * qw - G[i][3] * qz;
+  }
+  if (type == 0) {
+    const double a[3] = {f[4], f[5], f[6]}, b[3] = {f[7], f[8], f[9]};
+    const double u[3] = {lp[0] - a[0], lp[1] - a[1], lp[2] - a[2]}, v[3] = {lp[0] - b[0], lp[1] - b[1], lp[2] - b[2]};
+    const double nu[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+    const double de[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};
+    const double inv = 1.0 / sqrt(de[0] * de[0] + de[1] * de[1] + de[2] * de[2]);
+    o.nr = 3;
+    o.r[0] = nu[0] * inv; o.r[1] = nu[1] * inv; o.r[2] = nu[2] * inv;
+    const double w[3] = {-de[0] * inv, -de[1] * inv, -de[2] * inv};
+    const double D[3][3] = {{0.0, -w[2], w[1]}, {w[2], 0.0, -w[0]}, {-w[1], w[0], 0.0}};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+      for (int cidx = 0; cidx < 3; ++cidx) {
+        o.J[k][cidx] = D[k][0] * L[0][cidx] + D[k][1] * L[1][cidx] + D[k][2] * L[2][cidx];
+        o.J[k][3 + cidx] = D[k][cidx] * s;
+      }
+    }
+  } else {  // type 1 (LidarPlaneFactor); the plane-norm factor of the mapping stage has no s (LF.hpp:121-133)
+    const double n[3] = {f[7], f[8], f[9]};
+    o.nr = 1;
+    o.r[0] = (lp[0] - f[4]) * n[0] + (lp[1] - f[5]) * n[1] + (lp[2] - f[6]) * n[2];
+#pragma unroll
+    for (int cidx = 0; cidx < 3; ++cidx) {
+      o.J[0][cidx] = n[0] * L[0][cidx] + n[1] * L[1][cidx] + n[2] * L[2][cidx];
+      o.J[0][3 + cidx] = n[cidx] * s;
+    }
+  }
+}
+
 // EigenQuaternionParameterization::Plus on q, plain addition on t
 __device__ void lm_plus(const double x[7], const double d[6], double o[7]) {
   const double n = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
@@ -297,7 +381,7 @@ __device__ __forceinline__ void lm_accumulate(const FactorRow& fr, double* __res
 // equations themselves with the oracle's).  The last CTA to finish adds the per-CTA partials in order.
 __global__ void __launch_bounds__(LM_BLOCK) lm_eval(const double* __restrict__ factors, const int* __restrict__ valid, int nslots,
                                                     const double* __restrict__ xEval, EvalOut* __restrict__ partials,
-                                                    EvalOut* __restrict__ evalOut, unsigned int* __restrict__ counter) {
+                                                    EvalOut* __restrict__ evalOut, unsigned int* __restrict__ counter, const double* __restrict__ sArr) {
   VL_PDL_WAIT();
 
   double x[7];
@@ -309,7 +393,8 @@ __global__ void __launch_bounds__(LM_BLOCK) lm_eval(const double* __restrict__ f
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslots; i += gridDim.x * blockDim.x) {
     if (!valid[i]) continue;
     FactorRow fr;
-    lm_factor(factors + (size_t)i * 10, x, fr);
+    if (sArr && (int)factors[(size_t)i * 10] != 2) lm_factor_deskew(factors + (size_t)i * 10, sArr[i], x, fr);
+    else lm_factor(factors + (size_t)i * 10, x, fr);
     lm_accumulate(fr, acc);
   }
   __shared__ double red[LM_BLOCK / 32][28];
@@ -445,7 +530,7 @@ __device__ __forceinline__ void lm_warp_transpose_reduce(double (&v)[32], int la
 template <int FPT, int THREADS>
 __global__ void __launch_bounds__(THREADS, LMC_MIN_CTAS)
 lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ valid, int nslotsBound, const int* __restrict__ d_nslots,
-                 double* __restrict__ x_inout, LmSolveState* __restrict__ st_out, long long* __restrict__ trace) {
+                 double* __restrict__ x_inout, LmSolveState* __restrict__ st_out, long long* __restrict__ trace, const double* __restrict__ sArr) {
   VL_PDL_WAIT();
 
   cg::cluster_group cluster = cg::this_cluster();
@@ -513,7 +598,8 @@ lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ val
       for (int i = threadIdx.x * LMC_CTAS + (int)rank; i < nslots; i += THREADS * LMC_CTAS) {
         if (!valid[i]) continue;
         FactorRow fr;
-        lm_factor(factors + (size_t)i * 10, x, fr);
+        if (FPT == 0 && sArr && (int)factors[(size_t)i * 10] != 2) lm_factor_deskew(factors + (size_t)i * 10, sArr[i], x, fr);  // DISTORTION: only the streaming variant
+        else lm_factor(factors + (size_t)i * 10, x, fr);
         lm_accumulate(fr, acc);
       }
     }
@@ -579,9 +665,9 @@ int vl_solver_trace(vloam_b200_ctx* c, long long* out16) {
 
 template <int FPT, int THREADS>
 static cudaError_t lm_launch(cudaLaunchConfig_t& cfg, const double* cf, const int* cv, int nslots, const int* d_nslots, double* x,
-                             LmSolveState* so, long long* trace) {
+                             LmSolveState* so, long long* trace, const double* sArr = nullptr) {
   cfg.blockDim = dim3(THREADS);
-  return cudaLaunchKernelEx(&cfg, lm_solve_cluster<FPT, THREADS>, cf, cv, nslots, d_nslots, x, so, trace);
+  return cudaLaunchKernelEx(&cfg, lm_solve_cluster<FPT, THREADS>, cf, cv, nslots, d_nslots, x, so, trace, sArr);
 }
 
 // function attributes are per device: set when a context is created on it (vloam_b200_create)
@@ -600,7 +686,7 @@ int vl_solver_set_attrs(vloam_b200_ctx* c) {
   return VLOAM_OK;
 }
 
-int vl_solve(vloam_b200_ctx* c, int nslots, const int* d_nslots, double* d_x_inout, double* costs2, int hint) {
+int vl_solve(vloam_b200_ctx* c, int nslots, const int* d_nslots, double* d_x_inout, double* costs2, int hint, const double* d_s) {
   if (nslots > 0) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(LMC_CTAS); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
@@ -618,7 +704,8 @@ int vl_solve(vloam_b200_ctx* c, int nslots, const int* d_nslots, double* d_x_ino
     // actual count.  The variant only decides how many slots a thread can keep in registers: a solve whose
     // actual count exceeds it streams the factors from memory at every evaluation instead.
     const int est = hint > 0 ? min(nslots, hint + hint / 32 + 64) : nslots;  // counts move by a few per cent between sweeps; a miss only costs speed
-    if (est <= LMC_CTAS * 256) VL_CUDA((lm_launch<1, 256>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr)));
+    if (d_s) VL_CUDA((lm_launch<0, 256>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr, d_s)));  // DISTORTION: factors + s streamed from memory
+    else if (est <= LMC_CTAS * 256) VL_CUDA((lm_launch<1, 256>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr)));
     else if (est <= LMC_CTAS * 512) VL_CUDA((lm_launch<2, 256>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr)));
     else if (est <= LMC_CTAS * 1024) VL_CUDA((lm_launch<4, 256>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr)));
     else VL_CUDA((lm_launch<0, 256>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr)));
@@ -637,11 +724,11 @@ int vl_solve(vloam_b200_ctx* c, int nslots, const int* d_nslots, double* d_x_ino
   return VLOAM_OK;
 }
 
-int vl_evaluate_once(vloam_b200_ctx* c, int nslots, const double* d_x, EvalOut* d_out) {
+int vl_evaluate_once(vloam_b200_ctx* c, int nslots, const double* d_x, EvalOut* d_out, const double* d_s) {
   const int nb = max(1, min(vl_div_up(nslots, LM_BLOCK), LM_MAX_BLOCKS));
   VL_TRY(vl_reserve(c, c->evalPartials, LM_MAX_BLOCKS));
   unsigned int* counter = reinterpret_cast<unsigned int*>(c->vScalars + 60);
-  VL_LAUNCH(lm_eval, nb, LM_BLOCK, 0, c->factors.p, c->factorValid.p, nslots, d_x, c->evalPartials.p, d_out, counter);
+  VL_LAUNCH(lm_eval, nb, LM_BLOCK, 0, c->factors.p, c->factorValid.p, nslots, d_x, c->evalPartials.p, d_out, counter, d_s);
   VL_CUDA(cudaGetLastError());
   return VLOAM_OK;
 }
