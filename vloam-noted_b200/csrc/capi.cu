@@ -124,6 +124,8 @@ static int create_impl(vloam_b200_ctx* c, const vloam_b200_params* p, int device
   VL_CUDA_CREATE(cudaMalloc(&c->losNext, sizeof(LoScalars)));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evS2, cudaEventDisableTiming));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evLoSolve, cudaEventDisableTiming));
+  VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evLoNext, cudaEventDisableTiming));
+  VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->streamLO, cudaStreamNonBlocking, pr[0]));
   c->loNextValid = c->srAdopted = c->s2Done = false; c->loAssumeMonotone = c->inProcessFrame = c->loDeferred = false; c->loNextSet = 0; c->stackSel = 0; c->stacksNextReady = false;
   VL_CUDA_CREATE(cudaMallocHost(&c->h_los, sizeof(LoScalars)));
   LoScalars hl; memset(&hl, 0, sizeof hl); hl.para_q[3] = 1.0; hl.q_w[3] = 1.0;  // LO.cpp:81-91
@@ -168,14 +170,15 @@ void vloam_b200_destroy(vloam_b200_ctx* c) {
   cudaStreamDestroy(c->streamSR);
   vl_lm_free(c);
   vl_scan_free(&c->loScan[0]); vl_scan_free(&c->loScan[1]);
-  cudaEventDestroy(c->evS2); cudaEventDestroy(c->evLoSolve);
+  if (c->streamLO) { cudaStreamSynchronize(c->streamLO); cudaStreamDestroy(c->streamLO); }
+  cudaEventDestroy(c->evS2); cudaEventDestroy(c->evLoSolve); cudaEventDestroy(c->evLoNext);
   void* singles[] = {c->los, c->losNext, c->evalOut, c->lms, c->lmm, c->cubeC, c->cubeS, c->vScalars, c->loRingTbl, c->loGridCells[0].p, c->loGridCells[1].p,
                      c->loGridCellOf.p, c->loGridSorted[0].p, c->loGridSorted[1].p, c->dbgLoCorner[0].p, c->dbgLoCorner[1].p, c->dbgLoSurf[0].p,
                      c->dbgLoSurf[1].p, c->dbgKnnIdx[0][0].p, c->dbgKnnIdx[0][1].p, c->dbgKnnIdx[1][0].p, c->dbgKnnIdx[1][1].p, c->dbgKnnD2[0][0].p,
                      c->dbgKnnD2[0][1].p, c->dbgKnnD2[1][0].p, c->dbgKnnD2[1][1].p, c->dbgKnnOk[0][0].p, c->dbgKnnOk[0][1].p, c->dbgKnnOk[1][0].p,
                      c->dbgKnnOk[1][1].p};
   for (void* p : singles) if (p) cudaFree(p);
-  void* bufs[] = {c->lessSharp[0].p, c->lessSharp[1].p, c->lessSharp[2].p, c->lessFlat[0].p, c->lessFlat[1].p, c->lessFlat[2].p, c->loCornerIdx.p, c->loSurfIdx.p, c->factors.p, c->factorS.p, c->factorValid.p, c->evalPartials.p,
+  void* bufs[] = {c->lessSharp[0].p, c->lessSharp[1].p, c->lessSharp[2].p, c->lessFlat[0].p, c->lessFlat[1].p, c->lessFlat[2].p, c->loCornerIdx.p, c->loSurfIdx.p, c->factors.p, c->factorS.p, c->factorValid.p, c->loFactors.p, c->loFactorValid.p, c->evalPartials.p,
                   c->poolC.p, c->poolS.p, c->stackC.p, c->stackS.p, c->stackCN.p, c->stackSN.p, c->fromMapC.p, c->fromMapS.p, c->knnIdx.p, c->knnD2.p, c->knnOk.p,
                   c->vKeys.p, c->vKeys2.p, c->vHead.p, c->vScan.p, c->vScan2.p, c->vOut.p, c->vIn.p, c->regOut.p, c->tailKeys.p, c->staging.p};
   for (void* p : bufs) if (p) cudaFree(p);
@@ -397,6 +400,7 @@ int vloam_b200_synchronize(vloam_b200_ctx* c) {
   VL_TRY(vl_lo_flush_deferred(c));
   VL_TRY(vl_lm_join(c));
   VL_CUDA(cudaStreamSynchronize(c->streamSR));
+  VL_CUDA(cudaStreamSynchronize(c->streamLO));
   VL_CUDA(cudaStreamSynchronize(c->streamAux));
   VL_CUDA(cudaStreamSynchronize(c->stream)); VL_CUDA(cudaStreamSynchronize(c->stream2)); VL_CUDA(cudaStreamSynchronize(c->stream3));
   VL_CUDA(cudaStreamSynchronize(c->stream4));
@@ -465,12 +469,12 @@ int vloam_b200_profile_timeline(vloam_b200_ctx* c, char* buf, int cap) {
   if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
   VL_TRY(vloam_b200_synchronize(c));
   std::string out;
-  const cudaStream_t ss[6] = {c->stream, c->stream2, c->stream3, c->stream4, c->streamSR, c->streamAux};
+  const cudaStream_t ss[7] = {c->stream, c->stream2, c->stream3, c->stream4, c->streamSR, c->streamAux, c->streamLO};
   for (int k = 0; k < c->prof_n; ++k) {
     float t0 = 0, t1 = 0;
     VL_CUDA(cudaEventElapsedTime(&t0, c->prof_ev[0][0], c->prof_ev[k][0]));
     VL_CUDA(cudaEventElapsedTime(&t1, c->prof_ev[0][0], c->prof_ev[k][1]));
-    int si = 0; for (int q = 0; q < 6; ++q) if (ss[q] == c->prof_kstream[k]) si = q;
+    int si = 0; for (int q = 0; q < 7; ++q) if (ss[q] == c->prof_kstream[k]) si = q;
     char line[256]; snprintf(line, sizeof line, "%s %d %.3f %.3f\n", c->prof_kname[k], si, t0 * 1e3, t1 * 1e3);
     out += line;
   }
@@ -589,6 +593,7 @@ int vloam_b200_debug_set(vloam_b200_ctx* c, const char* name, const void* data, 
   if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
   const std::string n(name);
   VL_TRY(vloam_b200_synchronize(c));
+  if (n.rfind("lm.", 0) == 0) VL_TRY(vl_lm_sync_pools(c));  // edits of the mapping state work on the cube pools
   c->loNextValid = false;  // whatever is set below may change what the next odometry solve starts from
   if (n == "debug.capture") { c->h_vScalars[0] = (bytes >= 4 && *(const int*)data) ? 1 : 0; return VLOAM_OK; }
   if (n == "lo.last") {  // blob: int nc, int ns, corner points, surf points  (the state solveLO swaps in, LO.cpp:558-574)

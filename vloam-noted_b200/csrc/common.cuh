@@ -66,6 +66,9 @@ struct LmScalars {
   int overflow;                     // set when a pool / buffer bound was hit
   int optimized;
   int totalC, totalS;               // points in all 4851 cubes before this frame's update (bounds the next sub-map)
+  int needSlow;                     // lm_prepare_fast: this sweep cannot use the in-place grid path (window moved / grid dirty): the host repeats it on the pool path
+  int gridCount;                    // live points in the grid (both kinds)
+  int gridTop, gridDirty, gridDead; // voxel-hash grid: chunks in use, dirty flag, tombstones (copied by lm_transform_update for the host's bookkeeping)
   double pose[7];                   // q_w_curr, t_w_curr (parameters[7], laser_mapping.h:156)
   double q_wmap_wodom[4], t_wmap_wodom[3];
   double q_wodom[4], t_wodom[3];
@@ -168,6 +171,8 @@ struct vloam_b200_ctx {
   bool inProcessFrame;        // inside process_frame: mapping follows the odometry in the same call
   bool loDeferred; int defSet, defNc, defNs; const float4* defCorner; const float4* defSurf;  // side-stream work of the odometry stage queued after the mapping
   cudaEvent_t evS2;           // sync point S2 (pose + sizes copied to the host)
+  cudaStream_t streamLO;      // the look-ahead odometry of the NEXT sweep runs here, beside this sweep's mapping (own factor buffers)
+  cudaEvent_t evLoNext;       // that look-ahead solve has finished (its result is in losNext)
   cudaEvent_t evLoSolve;      // the last queued odometry solve (and every one before it) has finished reading the "last" clouds and their grids
   int nCornerLast, nSurfLast;  // host counts of the "last" clouds (= other buffer of the pair)
   bool lo_inited; int lo_frameCount;
@@ -179,7 +184,8 @@ struct vloam_b200_ctx {
   DBuf<int> loGridCells[2], loGridCellOf; DBuf<float4> loGridSorted[2]; bool loGridValid[2];
   int lastSet;
   DBuf<int> loCornerIdx, loSurfIdx;   // association results (2 / 3 ints per query)
-  DBuf<double> factors;               // 10 doubles per factor slot
+  DBuf<double> factors;               // 10 doubles per factor slot (mapping stage, C-ABI evaluate / solve)
+  DBuf<double> loFactors; DBuf<int> loFactorValid;  // the odometry stage's own factor slots: its look-ahead solve overlaps the mapping solve
   DBuf<double> factorS;               // DISTORTION only: interpolation ratio s of every odometry factor slot (LO.cpp:368-372, 472-476)
   DBuf<int> factorValid;
   DBuf<EvalOut> evalPartials;
@@ -200,6 +206,7 @@ struct vloam_b200_ctx {
   int lm_frameCount;
   int lm_optimized;  // host copy: did the last solveMapping run the optimisation (LM.cpp:514)
   DBuf<int> knnIdx; DBuf<float> knnD2; DBuf<int> knnOk;
+  DBuf<float4> knnPts; DBuf<unsigned long long> knnKey;  // the five neighbours themselves (the grid has no stable point ids) and their keys (debug capture)
   DBuf<int> dbgKnnIdx[2][2]; DBuf<float> dbgKnnD2[2][2]; DBuf<int> dbgKnnOk[2][2];
   double dbgLmCost[4];
   struct GridParams* gridPrm;  // device [2]
@@ -347,6 +354,7 @@ int vl_lm_fit_sets(vloam_b200_ctx* c, const float* d_near, int n, int kind, int*
 int vl_lm_join(vloam_b200_ctx* c);      // wait until the helper thread has issued the pending map update; returns its status
 void vl_lm_shutdown(vloam_b200_ctx* c);  // stop the helper thread
 int vl_lm_export_map(vloam_b200_ctx* c, int which, void* out, long cap, long* bytes);
+int vl_lm_sync_pools(vloam_b200_ctx* c);  // write the in-place grid updates back to the cube pools (no-op when they are current)
 int vl_lm_import_map(vloam_b200_ctx* c, int which, const void* data, long bytes);
 
 // out[0..n] = exclusive scan of in[0..n) in ONE launch (chained scan with look-back, laser_mapping.cu).  `in` and `out`
@@ -365,6 +373,8 @@ int vl_voxel_grid_device(vloam_b200_ctx* c, const float4* d_in, int n, const int
 // d_s (device, may be null): per-slot interpolation ratio; non-null = the functors slerp q by s and scale t by s (DISTORTION)
 int vl_solve(vloam_b200_ctx* c, int nslots, const int* d_nslots, double* d_x_inout, double* costs2 /* host, may be null */,
              int hint = 0 /* last known actual slot count, 0 = none */, const double* d_s = nullptr);
+int vl_solve_buf(vloam_b200_ctx* c, const double* d_factors, const int* d_valid, int nslots, const int* d_nslots, double* d_x_inout, double* costs2, int hint,
+                 const double* d_s);  // same on explicit factor buffers, on the calling thread's current stream (VL_STREAM)
 int vl_evaluate_once(vloam_b200_ctx* c, int nslots, const double* d_x, EvalOut* d_out, const double* d_s = nullptr);
 static inline bool vl_distortion(const vloam_b200_ctx* c) { return (c->prm.reserved & 1) != 0; }  // LaserOdometry::DISTORTION (LO.h:90)
 

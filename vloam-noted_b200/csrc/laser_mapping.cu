@@ -25,6 +25,7 @@
 #include <cooperative_groups.h>
 #include "common.cuh"
 #include "bitonic.cuh"
+#include "lm_grid.cuh"
 namespace cg = cooperative_groups;
 #include <atomic>
 #include <chrono>
@@ -182,6 +183,8 @@ __device__ __forceinline__ unsigned lm_vox_key_cube(const float4 p, float inv, i
   return lm_vox_key(p, inv, ci, cj, ck, s->cenW, s->cenH, s->cenD);
 }
 
+__device__ __forceinline__ float lm_leaf_inv(const vloam_b200_params& p, int kind) { return __fdiv_rn(1.0f, kind ? p.plane_res : p.line_res); }
+
 // exclusive scan of one int per thread over the first 256 threads of the block (all threads must call)
 __device__ __forceinline__ int lm_scan256(int v, int* buf, int* total) {
   // exclusive scan over threads 0..255 (block of 256 or 1024 threads; every thread must call): warp shuffles, then
@@ -202,15 +205,14 @@ __device__ __forceinline__ int lm_scan256(int v, int* buf, int* total) {
 // ---- LaserMapping::input (LM.cpp:178-209) + centre cube / roll / valid list (LM.cpp:228-466)
 __global__ void __launch_bounds__(1024) lm_prepare(LmScalars* __restrict__ s, const LoScalars* __restrict__ lo, MapCubeTable* __restrict__ tc,
                                                    MapCubeTable* __restrict__ ts, RfWork* __restrict__ w, int skip, int resetValid,
-                                                   LmSub* __restrict__ real, const LmSub* __restrict__ spec, int specQueued, int* __restrict__ specOK) {
+                                                   LmSub* __restrict__ real) {
   VL_PDL_WAIT();
 
   __shared__ int shift[3];
   __shared__ int center[3];
-  __shared__ int sFresh;
   if (threadIdx.x == 0) {
+    s->needSlow = 0;
     if (resetValid) s->validNum = 0;  // LaserMapping::reset (LM.cpp:132-136)
-    sFresh = s->validNum == 0;
     for (int k = 0; k < 4; ++k) s->q_wodom[k] = lo->q_w[k];
     for (int k = 0; k < 3; ++k) s->t_wodom[k] = lo->t_w[k];
     double r[3];
@@ -321,12 +323,6 @@ __global__ void __launch_bounds__(1024) lm_prepare(LmScalars* __restrict__ s, co
   if (t == 0) {
     s->Mc = sMc; s->Ms = total - sMc; w->gatherOff[0][VL_MAX_VALID] = sMc; w->gatherOff[1][VL_MAX_VALID] = total - sMc;
     real->Mc = sMc; real->Ms = total - sMc; real->gatherOff[0][VL_MAX_VALID] = sMc; real->gatherOff[1][VL_MAX_VALID] = total - sMc; real->ok = 1;
-    // The sub-map gathered and cell-sorted after the previous map update is this frame's sub-map when the
-    // window did not move: same centre cube, no roll, a freshly reset valid list.  The cube tables have not
-    // changed since, so equal windows mean equal offsets; the sizes are compared as a last line of defence.
-    *specOK = (specQueued && spec->ok && sFresh && shift[0] == 0 && shift[1] == 0 && shift[2] == 0 && spec->cI == center[0] &&
-               spec->cJ == center[1] && spec->cK == center[2] && spec->cenW == s->cenW && spec->cenH == s->cenH && spec->cenD == s->cenD &&
-               spec->validNum == nv && spec->Mc == sMc && spec->Ms == total - sMc) ? 1 : 0;
   }
   int tailTotal = 0, prefTotal = 0;
   const int tl = cnt - srt;
@@ -375,17 +371,6 @@ __global__ void __launch_bounds__(256) lm_spec_prepare(const LmSub* __restrict__
   if (t == 0) { spec->Mc = sMc; spec->Ms = total - sMc; spec->gatherOff[0][VL_MAX_VALID] = sMc; spec->gatherOff[1][VL_MAX_VALID] = total - sMc; spec->ok = 1; }
 }
 
-// zero the two cell-counter arrays of the search grid (a kernel, not a memset, so that it can be skipped)
-__device__ __forceinline__ void lm_dev_zero(int* __restrict__ a, int* __restrict__ b, int n) {
-  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) { a[g] = 0; b[g] = 0; }
-}
-__global__ void __launch_bounds__(256) lm_grid_zero(int* __restrict__ a, int* __restrict__ b, int n, const int* __restrict__ skip) {
-  VL_PDL_WAIT();
-
-  if (skip && *skip) return;
-  lm_dev_zero(a, b, n);
-}
-
 // LM.cpp:476-485: concatenate the valid cubes (loop order of LM.cpp:448-452) into the sub-map clouds.
 // skip (may be null): device flag "the speculative build already produced exactly this" -> nothing to do.
 __device__ __forceinline__ void lm_dev_gather(const LmSub* __restrict__ sub, const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts,
@@ -403,93 +388,10 @@ __device__ __forceinline__ void lm_dev_gather(const LmSub* __restrict__ sub, con
     else outC[e] = poolC[tc->start[cb] + (e - off[lo])];
   }
 }
-// ---- search grid: counting sort of both sub-maps into 2 m cells --------------------------------
+// 2 m search cells over the 250 x 250 x 150 m window
 __device__ __forceinline__ int lm_cell_coord(float v, float o, int n) {
   const int cidx = (int)floorf(__fmul_rn(__fsub_rn(v, o), 1.0f / LM_CELL));
   return min(max(cidx, 0), n - 1);
-}
-__device__ __forceinline__ void lm_dev_count(const LmSub* __restrict__ sub, const float4* __restrict__ mapC, const float4* __restrict__ mapS,
-                                             int* __restrict__ cellCount, int* __restrict__ cellOfPoint) {
-  const int mc = sub->Mc, total = sub->Mc + sub->Ms;
-  const float ox = sub->gridOrigin[0], oy = sub->gridOrigin[1], oz = sub->gridOrigin[2];
-  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
-    const int kind = g >= mc;
-    const float4 p = kind ? mapS[g - mc] : mapC[g];
-    const int cell = kind * LM_NCELL + lm_cell_coord(p.x, ox, LM_GX) + LM_GX * (lm_cell_coord(p.y, oy, LM_GY) + LM_GY * lm_cell_coord(p.z, oz, LM_GZ));
-    cellOfPoint[g] = cell;
-    atomicAdd(&cellCount[cell], 1);
-  }
-}
-// Speculative path: gather and cell count in one pass -- each point is read from the pool once, written to the
-// sub-map cloud and binned (one launch and one re-read of the gathered cloud less on the update -> sub-map chain).
-__global__ void __launch_bounds__(256) lm_gather_count(const LmSub* __restrict__ sub, const MapCubeTable* __restrict__ tc,
-                                                       const MapCubeTable* __restrict__ ts, const float4* __restrict__ poolC,
-                                                       const float4* __restrict__ poolS, float4* __restrict__ outC, float4* __restrict__ outS,
-                                                       int* __restrict__ cellCount, int* __restrict__ cellOfPoint) {
-  VL_PDL_WAIT();
-
-  const int nv = sub->validNum, mc = sub->Mc, total = sub->Mc + sub->Ms;
-  const float ox = sub->gridOrigin[0], oy = sub->gridOrigin[1], oz = sub->gridOrigin[2];
-  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
-    const int kind = g >= mc;
-    const int e = kind ? g - mc : g;
-    const int* off = sub->gatherOff[kind];
-    int lo = 0, hi = nv;
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid] <= e) lo = mid; else hi = mid; }
-    const int cb = sub->validInd[lo];
-    const float4 p = kind ? poolS[ts->start[cb] + (e - off[lo])] : poolC[tc->start[cb] + (e - off[lo])];
-    if (kind) outS[e] = p; else outC[e] = p;
-    const int cell = kind * LM_NCELL + lm_cell_coord(p.x, ox, LM_GX) + LM_GX * (lm_cell_coord(p.y, oy, LM_GY) + LM_GY * lm_cell_coord(p.z, oz, LM_GZ));
-    cellOfPoint[g] = cell;
-    atomicAdd(&cellCount[cell], 1);
-  }
-}
-// exclusive scan over 2*LM_NCELL counts, three-phase form for the cooperative in-line build: tile sums (1024 per
-// block) -> scan of tile sums -> apply
-__device__ __forceinline__ void lm_dev_scan_tile(const int* __restrict__ in, int n, int* __restrict__ tileSum, int tile) {  // 256 threads
-  int acc = 0;
-  const int base = tile * 1024;
-  for (int q = 0; q < 4; ++q) { const int t = base + q * 256 + threadIdx.x; if (t < n) acc += in[t]; }
-  __shared__ int ws[8];
-  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-  __syncthreads();  // (ws may still be read by the previous tile of a looping caller)
-  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) { int v = 0; for (int k = 0; k < 8; ++k) v += ws[k]; tileSum[tile] = v; }
-}
-// exclusive scan of the tile sums in place by ONE block of T threads (T a power of two <= 1024)
-template <int T>
-__device__ __forceinline__ void lm_dev_scan_sums(int* __restrict__ tileSum, int nTiles) {
-  __shared__ int ws[32];
-  int carry = 0;  // the same value in every thread
-  for (int base = 0; base < nTiles; base += T) {
-    const int b = base + threadIdx.x;
-    const int own = b < nTiles ? tileSum[b] : 0;
-    int tot = 0;
-    const int ex = vl_block_excl_scan<T>(own, ws, &tot);
-    if (b < nTiles) tileSum[b] = carry + ex;
-    carry += tot;
-  }
-}
-__device__ __forceinline__ void lm_dev_scan_apply(const int* __restrict__ in, int n, const int* __restrict__ tileSum, int* __restrict__ out,
-                                                  int tile, int nTiles) {  // 256 threads
-  __shared__ int ws[8];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int running = tileSum[tile];
-  for (int q = 0; q < 4; ++q) {
-    const int t = tile * 1024 + q * 256 + threadIdx.x;
-    const int v = t < n ? in[t] : 0;
-    int inc = v;
-    for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
-    __syncthreads();  // (ws may still be read by the previous round / tile)
-    if (lane == 31) ws[warp] = inc;
-    __syncthreads();
-    int before = 0, all = 0;
-    for (int k = 0; k < 8; ++k) { if (k < warp) before += ws[k]; all += ws[k]; }
-    if (t < n) out[t] = running + before + inc - v;
-    running += all;
-  }
-  if (tile == nTiles - 1 && threadIdx.x == 0) out[n] = running;  // total
 }
 // ---- single-launch exclusive scan (chained tiles with look-back) --------------------------------------
 // out[0..n] = exclusive scan of in[0..n) (out[n] = total).  A tile is 4096 counts (16 consecutive per thread, four
@@ -608,53 +510,208 @@ int vl_scan_exclusive(vloam_b200_ctx* c, const int* in, int n, VlScan* sc, int* 
   return VLOAM_OK;
 }
 
-__device__ __forceinline__ void lm_dev_fill(const LmSub* __restrict__ sub, const float4* __restrict__ mapC, const float4* __restrict__ mapS,
-                                            const int* __restrict__ cellOfPoint, const int* __restrict__ cellStart, int* __restrict__ cellFill,
-                                            float4* __restrict__ sortedPts) {
-  const int mc = sub->Mc, total = sub->Mc + sub->Ms;
-  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
-    const int kind = g >= mc;
-    const int id = kind ? g - mc : g;  // canonical index inside its own sub-map cloud
-    const float4 p = kind ? mapS[id] : mapC[id];
-    const int cell = cellOfPoint[g];
-    const int pos = cellStart[cell] + atomicAdd(&cellFill[cell], 1);
-    sortedPts[pos] = make_float4(p.x, p.y, p.z, __int_as_float(id));
+// ---- persistent voxel-hash grid (lm_grid.cuh): rebuild from the cube pools ------------------------------------------
+__device__ __forceinline__ int lg_cell_of(const float4 p, const float* o) {
+  return lm_cell_coord(p.x, o[0], LM_GX) + LM_GX * (lm_cell_coord(p.y, o[1], LM_GY) + LM_GY * lm_cell_coord(p.z, o[2], LM_GZ));
+}
+// empty directory, reset chunk allocator, header <- the window `sub` describes
+__global__ void __launch_bounds__(256) lg_zero(LgGrid g, const LmSub* __restrict__ sub) {
+  VL_PDL_WAIT();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * LM_NCELL; i += gridDim.x * blockDim.x) g.dir[i] = make_int2(0, -1);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *g.top = 0;
+    LgHeader* h = g.hdr;
+    h->valid = 1; h->dirty = 0; h->dead = 0; h->nOps = 0;
+    h->cI = sub->cI; h->cJ = sub->cJ; h->cK = sub->cK; h->cenW = sub->cenW; h->cenH = sub->cenH; h->cenD = sub->cenD;
+    h->validNum = sub->validNum; h->count[0] = sub->Mc; h->count[1] = sub->Ms;
+    for (int k = 0; k < VL_MAX_VALID; ++k) h->validInd[k] = k < sub->validNum ? sub->validInd[k] : 0;
+    for (int k = 0; k < 3; ++k) h->origin[k] = sub->gridOrigin[k];
   }
 }
-__global__ void __launch_bounds__(256) lm_grid_fill(const LmSub* __restrict__ sub, const int* __restrict__ skip, const float4* __restrict__ mapC,
-                                                    const float4* __restrict__ mapS, const int* __restrict__ cellOfPoint,
-                                                    const int* __restrict__ cellStart, int* __restrict__ cellFill,
-                                                    float4* __restrict__ sortedPts) {
+// every point of the valid cubes (loop order of LM.cpp:448-452) -> its cell; key = (slot, voxel key) for the filtered prefix,
+// (slot, TAIL | position) for unfiltered tail points (they make the grid `dirty`: the next update must take the pool path)
+__global__ void __launch_bounds__(256) lg_rebuild(LgGrid g, const LmSub* __restrict__ sub, const LmScalars* __restrict__ s, vloam_b200_params prm,
+                                                  const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts,
+                                                  const float4* __restrict__ poolC, const float4* __restrict__ poolS) {
   VL_PDL_WAIT();
-
-  if (skip && *skip) return;
-  lm_dev_fill(sub, mapC, mapS, cellOfPoint, cellStart, cellFill, sortedPts);
+  const int nv = sub->validNum, mc = sub->Mc, total = sub->Mc + sub->Ms;
+  const float o[3] = {sub->gridOrigin[0], sub->gridOrigin[1], sub->gridOrigin[2]};
+  for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < total; gi += gridDim.x * blockDim.x) {
+    const int kind = gi >= mc;
+    const int e = kind ? gi - mc : gi;
+    const int* off = sub->gatherOff[kind];
+    int lo = 0, hi = nv;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid] <= e) lo = mid; else hi = mid; }
+    const int cb = sub->validInd[lo];
+    const MapCubeTable* tb = kind ? ts : tc;
+    const int pos = e - off[lo];
+    const float4 p = (kind ? poolS : poolC)[tb->start[cb] + pos];
+    unsigned low;
+    if (pos >= tb->sorted[cb]) { low = LG_TAIL | (unsigned)pos; g.hdr->dirty = 1; }
+    else low = lm_vox_key_cube(p, lm_leaf_inv(prm, kind), cb, s);
+    lg_insert(g, kind * LM_NCELL + lg_cell_of(p, o), p, ((unsigned long long)lo << 32) | low, pos);
+  }
 }
 
-// The whole in-line sub-map build (gather, zero, count, scan, fill) as ONE cooperative launch.  It runs every
-// frame on the main stream but does real work only when the window moved: with the speculative build valid it
-// is a single grid that returns at once, where eight separately launched early-exit kernels cost ~20 us of
-// dependent launch latency.  Grid barriers separate the phases when it does run.
-struct LmInlineArgs {
-  const LmSub* sub; const int* skip; const MapCubeTable* tc; const MapCubeTable* ts; const float4* poolC; const float4* poolS;
-  float4* outC; float4* outS; int* cellCount; int* cellFill; int* cellStart; int* tileSum; int* cellOfPoint; float4* sortedPts; int nCells;
-};
-__global__ void __launch_bounds__(256) lm_inline_build(LmInlineArgs a) {
-  if (*a.skip) return;  // uniform over the grid
-  cg::grid_group grid = cg::this_grid();
-  lm_dev_gather(a.sub, a.tc, a.ts, a.poolC, a.poolS, a.outC, a.outS);
-  lm_dev_zero(a.cellCount, a.cellFill, a.nCells + 1);
-  grid.sync();
-  lm_dev_count(a.sub, a.outC, a.outS, a.cellCount, a.cellOfPoint);
-  grid.sync();
-  const int nTiles = (a.nCells + 1023) / 1024;
-  for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) lm_dev_scan_tile(a.cellCount, a.nCells, a.tileSum, tile);
-  grid.sync();
-  if (blockIdx.x == 0) lm_dev_scan_sums<256>(a.tileSum, nTiles);
-  grid.sync();
-  for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) lm_dev_scan_apply(a.cellCount, a.nCells, a.tileSum, a.cellStart, tile, nTiles);
-  grid.sync();
-  lm_dev_fill(a.sub, a.outC, a.outS, a.cellOfPoint, a.cellStart, a.cellFill, a.sortedPts);
+// LaserMapping::input (LM.cpp:178-209) + the window test of the in-place path: when the centre cube did not move, nothing
+// rolls, the valid list was reset (LM.cpp:132-136) and the grid is clean, this sweep's sub-map IS the grid: no table
+// is touched.  Otherwise needSlow is raised: every later kernel of the sweep returns at once and the host repeats the
+// mapping stage through lm_prepare (the pool path).  The pose arithmetic is lm_prepare's, statement for statement.
+__global__ void __launch_bounds__(256) lm_prepare_fast(LmScalars* __restrict__ s, const LoScalars* __restrict__ lo, RfWork* __restrict__ w,
+                                                       LgHeader* __restrict__ gh, int skip, int resetValid) {
+  VL_PDL_WAIT();
+  if (threadIdx.x <= LM_NSEG && !skip) { w->segCount[threadIdx.x] = 0; w->segFill[threadIdx.x] = 0; }
+  if (threadIdx.x != 0) return;
+  for (int k = 0; k < 4; ++k) s->q_wodom[k] = lo->q_w[k];
+  for (int k = 0; k < 3; ++k) s->t_wodom[k] = lo->t_w[k];
+  double r[3];
+  vl_qrot(s->q_wmap_wodom, s->t_wodom[0], s->t_wodom[1], s->t_wodom[2], r);
+  if (skip) {
+    vl_qmul(s->q_wmap_wodom, s->q_wodom, s->q_hf);
+    for (int k = 0; k < 3; ++k) s->t_hf[k] = r[k] + s->t_wmap_wodom[k];
+    return;
+  }
+  double qn[4];
+  vl_qmul(s->q_wmap_wodom, s->q_wodom, qn);
+  for (int k = 0; k < 4; ++k) s->pose[k] = qn[k];
+  for (int k = 0; k < 3; ++k) s->pose[4 + k] = r[k] + s->t_wmap_wodom[k];
+  int cI = (int)((s->pose[4] + 25.0) / 50.0) + s->cenW;
+  int cJ = (int)((s->pose[5] + 25.0) / 50.0) + s->cenH;
+  int cK = (int)((s->pose[6] + 25.0) / 50.0) + s->cenD;
+  if (s->pose[4] + 25.0 < 0) cI--;
+  if (s->pose[5] + 25.0 < 0) cJ--;
+  if (s->pose[6] + 25.0 < 0) cK--;
+  const bool roll = cI < 3 || cI >= VL_CUBE_W - 3 || cJ < 3 || cJ >= VL_CUBE_H - 3 || cK < 3 || cK >= VL_CUBE_D - 3;
+  // (a freshly reset valid list refilled for the same centre cube IS the grid's list: validInd is left as the last pool-path sweep wrote it)
+  const bool same = gh->valid && !gh->dirty && !roll && resetValid && cI == gh->cI && cJ == gh->cJ && cK == gh->cK && s->cenW == gh->cenW &&
+                    s->cenH == gh->cenH && s->cenD == gh->cenD;
+  s->needSlow = same ? 0 : 1;
+  if (same) { s->validNum = gh->validNum; s->Mc = gh->count[0]; s->Ms = gh->count[1]; gh->nOps = 0; }
+}
+
+// One warp per downsampled feature: 5-NN in the 3x3x3 cell neighbourhood of the voxel-hash grid (exact inside the 1 m
+// acceptance ball), ordered by (d2, key) == (d2, canonical id).  Lane r < 27 looks up cell r's directory entry
+// (one memory latency for all 27), then the chunks of all cells are visited with every lane busy (VL_WARP_VISIT_FLAT); cells
+// with more than LG_C points take further rounds along their chunk chains.
+__global__ void __launch_bounds__(256) lg_knn(const LmScalars* __restrict__ s, LgGrid g, const float4* __restrict__ stackC,
+                                              const float4* __restrict__ stackS, float4* __restrict__ knnPts, float* __restrict__ knnD2,
+                                              unsigned long long* __restrict__ knnKey) {
+  VL_PDL_WAIT();
+
+  const int lane = threadIdx.x & 31;
+  const int Qc = s->Qc, Qs = s->Qs, opt = s->optimized;
+  double pose[7];  // loaded with the counts: one memory latency instead of two
+#pragma unroll
+  for (int k = 0; k < 7; ++k) pose[k] = s->pose[k];
+  const float ox = g.hdr->origin[0], oy = g.hdr->origin[1], oz = g.hdr->origin[2];
+  if (!opt) return;
+  const int nWarps = (gridDim.x * blockDim.x) >> 5;
+  for (int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; qi < Qc + Qs; qi += nWarps) {
+    const int kind = qi >= Qc;
+    const float4 po = kind ? stackS[qi - Qc] : stackC[qi];
+    double r[3];
+    vl_qrot(pose, (double)po.x, (double)po.y, (double)po.z, r);  // pointAssociateToMap (LM.cpp:154-164)
+    const float sx = (float)(r[0] + pose[4]), sy = (float)(r[1] + pose[5]), sz = (float)(r[2] + pose[6]);
+    const int cx = (int)floorf(__fmul_rn(__fsub_rn(sx, ox), 1.0f / LM_CELL));
+    const int cy = (int)floorf(__fmul_rn(__fsub_rn(sy, oy), 1.0f / LM_CELL));
+    const int cz = (int)floorf(__fmul_rn(__fsub_rn(sz, oz), 1.0f / LM_CELL));
+    float bd[5]; int br[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { bd[k] = CUDART_INF_F; br[k] = -1; }
+    int cnt = 0, head = -1;
+    if (lane < 27) {
+      const int xx = cx - 1 + lane % 3, yy = cy - 1 + (lane / 3) % 3, zz = cz - 1 + lane / 9;
+      if (xx >= 0 && xx < LM_GX && yy >= 0 && yy < LM_GY && zz >= 0 && zz < LM_GZ) {
+        const int2 d = g.dir[kind * LM_NCELL + xx + LM_GX * (yy + LM_GY * zz)];
+        cnt = d.x; head = d.y;
+      }
+    }
+    while (__any_sync(0xffffffffu, cnt > 0)) {
+      const int rb = cnt > 0 ? head * LG_C : 0, rl = min(max(cnt, 0), LG_C);
+      VL_WARP_VISIT_FLAT(rb, rl, lane, g.pts, {
+        const float d = vl_dist2(sx, sy, sz, t.x, t.y, t.z);
+        if (d < bd[4] || (d == bd[4] && d < CUDART_INF_F && lg_key_less(g, p, br[4]))) {  // insertion into the lane-local sorted top-5
+          bd[4] = d; br[4] = p;
+#pragma unroll
+          for (int k = 4; k > 0; --k)
+            if (bd[k] < bd[k - 1] || (bd[k] == bd[k - 1] && lg_key_less(g, br[k], br[k - 1]))) {
+              const float td = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td;
+              const int ti = br[k]; br[k] = br[k - 1]; br[k - 1] = ti;
+            }
+        }
+      });
+      cnt -= LG_C;
+      if (cnt > 0) head = g.next[head];
+    }
+    // merge the 32 lane-local lists: pop the global minimum of (d2, key) five times.  d2 >= 0, so its bit pattern orders
+    // like the value: one hardware warp reduction per pop; equal distances (rare) are resolved on the 64-bit keys
+    float nd[5]; int nr[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const unsigned hb = __float_as_uint(bd[0]);  // +inf (empty list) sorts last
+      const unsigned gmin = __reduce_min_sync(0xffffffffu, hb);
+      unsigned tie = __ballot_sync(0xffffffffu, hb == gmin && br[0] >= 0);
+      int win = -1;
+      if (tie) {
+        if (__popc(tie) > 1) {
+          const unsigned long long ky = (hb == gmin && br[0] >= 0) ? g.key[br[0]] : LG_DEAD;
+          const unsigned khi = __reduce_min_sync(0xffffffffu, (unsigned)(ky >> 32));
+          const unsigned klo = __reduce_min_sync(0xffffffffu, (unsigned)(ky >> 32) == khi ? (unsigned)ky : 0xffffffffu);
+          tie = __ballot_sync(0xffffffffu, ky == (((unsigned long long)khi << 32) | klo));
+        }
+        win = __ffs(tie) - 1;
+      }
+      nd[k] = win >= 0 ? __uint_as_float(gmin) : CUDART_INF_F;
+      nr[k] = win >= 0 ? __shfl_sync(0xffffffffu, br[0], win) : -1;
+      if (lane == win) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { bd[q] = bd[q + 1]; br[q] = br[q + 1]; }
+        bd[4] = CUDART_INF_F; br[4] = -1;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      if (lane == k) {
+        knnPts[qi * 5 + k] = nr[k] >= 0 ? g.pts[nr[k]] : make_float4(0.f, 0.f, 0.f, 0.f);
+        knnD2[qi * 5 + k] = nd[k];
+        if (knnKey) knnKey[qi * 5 + k] = nr[k] >= 0 ? g.key[nr[k]] : LG_DEAD;
+      }
+    }
+  }
+}
+
+// debug capture: key -> canonical id of the concatenated sub-map cloud (LM.cpp:476-485); needs the pools in step with the grid
+__global__ void __launch_bounds__(256) lg_keys_to_ids(const unsigned long long* __restrict__ keys, int n, int Qc, const LmSub* __restrict__ sub,
+                                                      const LmScalars* __restrict__ s, vloam_b200_params prm, const MapCubeTable* __restrict__ tc,
+                                                      const MapCubeTable* __restrict__ ts, const float4* __restrict__ poolC,
+                                                      const float4* __restrict__ poolS, int* __restrict__ ids) {
+  VL_PDL_WAIT();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const unsigned long long key = keys[t];
+  if (key == LG_DEAD) { ids[t] = -1; return; }
+  const int kind = (t / 5) >= Qc;
+  const int slot = (int)(key >> 32);
+  const unsigned low = (unsigned)key;
+  const int cb = sub->validInd[slot];
+  const MapCubeTable* tb = kind ? ts : tc;
+  int pos;
+  if (low & LG_TAIL) pos = (int)(low & ~LG_TAIL);
+  else {
+    const float4* pool = (kind ? poolS : poolC) + tb->start[cb];
+    const float inv = lm_leaf_inv(prm, kind);
+    int lo = 0, hi = tb->sorted[cb];
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (lm_vox_key_cube(pool[mid], inv, cb, s) < low) lo = mid + 1; else hi = mid; }
+    pos = lo;
+  }
+  ids[t] = sub->gatherOff[kind][slot] + pos;
+}
+// debug capture: the concatenated sub-map clouds themselves (LM.cpp:476-485)
+__global__ void __launch_bounds__(256) lm_gather(const LmSub* __restrict__ sub, const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts,
+                                                 const float4* __restrict__ poolC, const float4* __restrict__ poolS, float4* __restrict__ outC,
+                                                 float4* __restrict__ outS) {
+  VL_PDL_WAIT();
+  lm_dev_gather(sub, tc, ts, poolC, poolS, outC, outS);
 }
 
 // ---- fits -------------------------------------------------------------------------------------
@@ -732,83 +789,6 @@ __device__ void lm_qr_solve_5x3(double A[5][3], double b[5], double x[3]) {
   for (int k = 0; k < 3; ++k) x[perm[k]] = y[k];
 }
 
-// One warp per downsampled feature: 5-NN in the 3x3x3 cell neighbourhood (exact inside the 1 m
-// acceptance ball), ordered by (d2, canonical id); then the line / plane fit.
-__global__ void __launch_bounds__(256) lm_knn(const LmScalars* __restrict__ s, const RfWork* __restrict__ w,
-                                                  const float4* __restrict__ stackC, const float4* __restrict__ stackS,
-                                                  const float4* __restrict__ mapC, const float4* __restrict__ mapS,
-                                                  const int* __restrict__ cellStart, const float4* __restrict__ sortedPts,
-                                                  int* __restrict__ knnIdx, float* __restrict__ knnD2, int* __restrict__ knnOk,
-                                                  double* __restrict__ factors, int* __restrict__ valid) {
-  VL_PDL_WAIT();
-
-  const int lane = threadIdx.x & 31;
-  const int Qc = s->Qc, Qs = s->Qs, opt = s->optimized;
-  double pose[7];  // loaded with the counts: one memory latency instead of two
-#pragma unroll
-  for (int k = 0; k < 7; ++k) pose[k] = s->pose[k];
-  const float ox = w->gridOrigin[0], oy = w->gridOrigin[1], oz = w->gridOrigin[2];
-  if (!opt) return;
-  const int nWarps = (gridDim.x * blockDim.x) >> 5;
-  for (int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; qi < Qc + Qs; qi += nWarps) {
-  const int kind = qi >= Qc;
-  const float4 po = kind ? stackS[qi - Qc] : stackC[qi];
-  double r[3];
-  vl_qrot(pose, (double)po.x, (double)po.y, (double)po.z, r);  // pointAssociateToMap (LM.cpp:154-164)
-  const float sx = (float)(r[0] + pose[4]), sy = (float)(r[1] + pose[5]), sz = (float)(r[2] + pose[6]);
-  const int cx = (int)floorf(__fmul_rn(__fsub_rn(sx, ox), 1.0f / LM_CELL));
-  const int cy = (int)floorf(__fmul_rn(__fsub_rn(sy, oy), 1.0f / LM_CELL));
-  const int cz = (int)floorf(__fmul_rn(__fsub_rn(sz, oz), 1.0f / LM_CELL));
-  float bd[5]; int bi[5];
-#pragma unroll
-  for (int k = 0; k < 5; ++k) { bd[k] = CUDART_INF_F; bi[k] = 0x7fffffff; }
-  {  // 9 (y,z) rows; the 3 x-adjacent cells of a row are contiguous.  Lane r < 9 looks up row r.
-    int rb = 0, rl = 0;
-    if (lane < 9) {
-      const int yy = cy - 1 + lane % 3, zz = cz - 1 + lane / 3;
-      const int x0 = max(cx - 1, 0), x1 = min(cx + 1, LM_GX - 1);
-      if (yy >= 0 && yy < LM_GY && zz >= 0 && zz < LM_GZ && x0 <= x1) {
-        const int c0 = kind * LM_NCELL + x0 + LM_GX * (yy + LM_GY * zz);
-        rb = cellStart[c0];
-        rl = cellStart[c0 + (x1 - x0) + 1] - rb;
-      }
-    }
-    VL_WARP_VISIT_FLAT(rb, rl, lane, sortedPts, {
-      const float d = vl_dist2(sx, sy, sz, t.x, t.y, t.z);
-      const int id = __float_as_int(t.w);
-      if (d < bd[4] || (d == bd[4] && id < bi[4])) {  // insertion into the lane-local sorted top-5
-        bd[4] = d; bi[4] = id;
-#pragma unroll
-        for (int k = 4; k > 0; --k)
-          if (bd[k] < bd[k - 1] || (bd[k] == bd[k - 1] && bi[k] < bi[k - 1])) {
-            const float td = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td;
-            const int ti = bi[k]; bi[k] = bi[k - 1]; bi[k - 1] = ti;
-          }
-      }
-    });
-  }
-  // merge the 32 lane-local lists: pop the global minimum of (d2, id) five times.  d2 >= 0, so its bit pattern
-  // orders like the value: two hardware warp reductions per pop (smallest d2, then the smallest id holding it)
-  float nd[5]; int ni[5];
-#pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    const unsigned hb = __float_as_uint(bd[0]);  // +inf (empty list) sorts last
-    const unsigned gmin = __reduce_min_sync(0xffffffffu, hb);
-    const unsigned imin = __reduce_min_sync(0xffffffffu, hb == gmin ? (unsigned)bi[0] : 0x7fffffffu);
-    nd[k] = __uint_as_float(gmin); ni[k] = (int)imin;
-    if (hb == gmin && (unsigned)bi[0] == imin && imin != 0x7fffffffu) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) { bd[q] = bd[q + 1]; bi[q] = bi[q + 1]; }
-      bd[4] = CUDART_INF_F; bi[4] = 0x7fffffff;
-    }
-  }
-  if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < 5; ++k) { knnIdx[qi * 5 + k] = (ni[k] == 0x7fffffff) ? -1 : ni[k]; knnD2[qi * 5 + k] = nd[k]; }
-  }
-  }
-}
-
 // The two fits of LM.cpp:559-603 / 637-680 on five neighbours (f64 from f32 coordinates).  o6: edge -> {a, b} (the two
 // synthetic line points), plane -> {unit normal, d, 0, 0}.  Returns the accept flag.
 __device__ __forceinline__ bool lm_fit_one(int kind, double P[5][3], double o6[6]) {
@@ -843,9 +823,8 @@ __device__ __forceinline__ bool lm_fit_one(int kind, double P[5][3], double o6[6
 // Line / plane fit of one feature per THREAD (the f64 eigen / QR work of 32 features shares a warp's
 // issue slots instead of idling 31 lanes behind lane 0 of the search kernel).
 __global__ void __launch_bounds__(128) lm_fit(const LmScalars* __restrict__ s, const float4* __restrict__ stackC, const float4* __restrict__ stackS,
-                                              const float4* __restrict__ mapC, const float4* __restrict__ mapS, const int* __restrict__ knnIdx,
-                                              const float* __restrict__ knnD2, int* __restrict__ knnOk, double* __restrict__ factors,
-                                              int* __restrict__ valid) {
+                                              const float4* __restrict__ knnPts, const float* __restrict__ knnD2, int* __restrict__ knnOk,
+                                              double* __restrict__ factors, int* __restrict__ valid) {
   VL_PDL_WAIT();
 
   const int Qc = s->Qc, Qs = s->Qs;
@@ -853,18 +832,13 @@ __global__ void __launch_bounds__(128) lm_fit(const LmScalars* __restrict__ s, c
   for (int qi = blockIdx.x * blockDim.x + threadIdx.x; qi < Qc + Qs; qi += gridDim.x * blockDim.x) {
   const int kind = qi >= Qc;
   const float4 po = kind ? stackS[qi - Qc] : stackC[qi];
-  int ni[5];
-#pragma unroll
-  for (int k = 0; k < 5; ++k) ni[k] = knnIdx[qi * 5 + k];
-  const bool have5 = ni[4] >= 0;
-  const float d4 = knnD2[qi * 5 + 4];
+  const float d4 = knnD2[qi * 5 + 4];  // +inf when fewer than five neighbours were found
   bool ok = false;
   double* f = factors + (size_t)qi * 10;
-  if (have5 && (double)d4 < 1.0) {
-    const float4* map = kind ? mapS : mapC;
+  if ((double)d4 < 1.0) {
     double P[5][3];
 #pragma unroll
-    for (int j = 0; j < 5; ++j) { const float4 t = map[ni[j]]; P[j][0] = t.x; P[j][1] = t.y; P[j][2] = t.z; }
+    for (int j = 0; j < 5; ++j) { const float4 t = knnPts[qi * 5 + j]; P[j][0] = t.x; P[j][1] = t.y; P[j][2] = t.z; }
     double o6[6];
     ok = lm_fit_one(kind, P, o6);
     if (ok) {
@@ -895,10 +869,12 @@ int vl_lm_fit_sets(vloam_b200_ctx* c, const float* d_near, int n, int kind, int*
   return VLOAM_OK;
 }
 
-__global__ void lm_transform_update(LmScalars* s) {
+__global__ void lm_transform_update(LmScalars* s, const LgHeader* __restrict__ gh, const int* __restrict__ gridTop) {
   VL_PDL_WAIT();
   // LM.cpp:147-151
   if (threadIdx.x != 0) return;
+  s->gridTop = *gridTop; s->gridDirty = gh->dirty; s->gridDead = gh->dead; s->gridCount = gh->count[0] + gh->count[1];
+  if (s->needSlow) return;  // the sweep is repeated on the pool path: leave the state untouched
   const double* q = s->q_wodom;
   const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
   const double qi[4] = {-q[0] / n2, -q[1] / n2, -q[2] / n2, q[3] / n2};
@@ -911,19 +887,18 @@ __global__ void lm_transform_update(LmScalars* s) {
 // ---- map update: insert (LM.cpp:741-788) + per-cube VoxelGrid re-filter (LM.cpp:795-808) -------
 // sort key: [63:56] segment (kind*125 + valid slot) | [55:26] voxel (iz,iy,ix) | [25:0] order
 // order: existing tail point -> its position in the cube; new point -> 2^25 + stack index.
-__device__ __forceinline__ float lm_leaf_inv(const vloam_b200_params& p, int kind) { return __fdiv_rn(1.0f, kind ? p.plane_res : p.line_res); }
 
 __global__ void __launch_bounds__(256) rf_keys(const LmScalars* __restrict__ s, RfWork* __restrict__ w, vloam_b200_params prm,
                                                const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts,
                                                const float4* __restrict__ poolC, const float4* __restrict__ poolS,
                                                const float4* __restrict__ stackC, const float4* __restrict__ stackS,
                                                float4* __restrict__ newPts, int* __restrict__ newCube,
-                                               unsigned long long* __restrict__ keys, int P) {
+                                               unsigned long long* __restrict__ keys, int P, int noTails) {
   VL_PDL_WAIT();
 
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= P) return;
-  const int tailTotal = w->tailOff[LM_NSEG];
+  const int tailTotal = noTails ? 0 : w->tailOff[LM_NSEG];  // (in-place grid update: every valid cube is filtered, only this sweep's points are keyed)
   const int Qc = s->Qc, Qs = s->Qs;
   unsigned long long key = ~0ull;
   if (g < tailTotal) {  // an existing tail point of a valid cube
@@ -1320,6 +1295,165 @@ __global__ void __launch_bounds__(1024) rf_append_outside(LmScalars* __restrict_
   }
 }
 
+// ---- in-place map update on the voxel-hash grid (LM.cpp:741-808 without touching the other ~1M points) -------------------
+// Input: this sweep's keys (segment | voxel | stack order), bucketed and sorted per segment (rf_keys with noTails,
+// rf_seg_scatter, rf_seg_sort).  One thread per run of equal (segment, voxel): the map point of that voxel, if there is one,
+// is found in the grid -- it lies inside the voxel's box, i.e. in one of the <= 2x2x2 cells the box overlaps -- and the
+// run is folded exactly as pcl::VoxelGrid does on [cube cloud ; appended points]: map point first (it has the lower index),
+// then the new points in stack order, f32 sums, one division.  The centroid is stored back in place; it becomes a pending
+// insert when the voxel is new or the centroid left its 2 m cell (the old entry is tombstoned).  Structural changes
+// (appends to cell chains) happen in mu_insert, a separate launch: no thread scans a chain while another one grows it.
+// A centroid that no longer maps to its own voxel (f32 rounding at a voxel face) is legal -- the next VoxelGrid pass re-keys
+// it -- but outside the in-place scheme: it raises `dirty`, and the next sweep runs the pool path on materialised cubes.
+__global__ void __launch_bounds__(128) mu_apply(const unsigned long long* __restrict__ keys, const LmScalars* __restrict__ s, const RfWork* __restrict__ w,
+                                                vloam_b200_params prm, LgGrid g, const float4* __restrict__ newPts, LgOp* __restrict__ ops) {
+  VL_PDL_WAIT();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= w->nKeysValid) return;
+  const unsigned long long key = keys[t];
+  const int sg = (int)(key >> 56);
+  const unsigned vk = RF_VOX(key);
+  if (t != w->tailBegin[sg] && RF_VOX(keys[t - 1]) == vk) return;  // not the head of its run
+  const int kind = sg / VL_MAX_VALID, slot = sg % VL_MAX_VALID, cb = s->validInd[slot];
+  const float leaf = kind ? prm.plane_res : prm.line_res;
+  const float inv = lm_leaf_inv(prm, kind);
+  const int ci = cb % VL_CUBE_W, cj = (cb / VL_CUBE_W) % VL_CUBE_H, ck = cb / (VL_CUBE_W * VL_CUBE_H);
+  // world voxel index of the run: inverse of lm_vox_key
+  const int gx = (int)(vk & 1023u) + (int)floorf(__fmul_rn((float)(50 * (ci - s->cenW) - 25), inv)) - 2;
+  const int gy = (int)((vk >> 10) & 1023u) + (int)floorf(__fmul_rn((float)(50 * (cj - s->cenH) - 25), inv)) - 2;
+  const int gz = (int)(vk >> 20) + (int)floorf(__fmul_rn((float)(50 * (ck - s->cenD) - 25), inv)) - 2;
+  const float* o = g.hdr->origin;
+  const float eps = 0.02f * leaf;  // p * inv is rounded: a point of voxel gx may sit a few ulp outside [gx, gx + 1) * leaf
+  const int x0 = lm_cell_coord((float)gx * leaf - eps, o[0], LM_GX), x1 = lm_cell_coord((float)(gx + 1) * leaf + eps, o[0], LM_GX);
+  const int y0 = lm_cell_coord((float)gy * leaf - eps, o[1], LM_GY), y1 = lm_cell_coord((float)(gy + 1) * leaf + eps, o[1], LM_GY);
+  const int z0 = lm_cell_coord((float)gz * leaf - eps, o[2], LM_GZ), z1 = lm_cell_coord((float)(gz + 1) * leaf + eps, o[2], LM_GZ);
+  const unsigned long long want = ((unsigned long long)slot << 32) | vk;
+  int found = -1, foundCell = -1;
+  if (x1 - x0 <= 1 && y1 - y0 <= 1 && z1 - z0 <= 1) {
+    // leaf <= 2 m: the box spans at most 2 x 2 x 2 cells.  All directory entries, then the first chunk of every cell, are
+    // loaded without waiting for one another (a serial walk is ~20 dependent L2 round trips per voxel: 40 us per update)
+    int cellId[8]; int2 dd[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int xx = x0 + (q & 1), yy = y0 + ((q >> 1) & 1), zz = z0 + (q >> 2);
+      const bool on = xx <= x1 && yy <= y1 && zz <= z1;
+      cellId[q] = kind * LM_NCELL + xx + LM_GX * (yy + LM_GY * zz);
+      dd[q] = on ? g.dir[cellId[q]] : make_int2(0, -1);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (dd[q].x <= 0) continue;
+      const ulonglong2* kp = reinterpret_cast<const ulonglong2*>(g.key + (size_t)dd[q].y * LG_C);
+      const int m = min(dd[q].x, LG_C);
+#pragma unroll
+      for (int i = 0; i < LG_C / 2; ++i) {
+        const ulonglong2 kk = kp[i];
+        if (2 * i < m && kk.x == want) { found = dd[q].y * LG_C + 2 * i; foundCell = cellId[q]; }
+        if (2 * i + 1 < m && kk.y == want) { found = dd[q].y * LG_C + 2 * i + 1; foundCell = cellId[q]; }
+      }
+    }
+    if (found < 0) {
+#pragma unroll 1
+      for (int q = 0; q < 8 && found < 0; ++q) {  // longer chains (> LG_C points in a cell)
+        int chunk = dd[q].y;
+        for (int left = dd[q].x - LG_C; left > 0 && found < 0; left -= LG_C) {
+          chunk = g.next[chunk];
+          const int m = min(left, LG_C);
+          for (int i = 0; i < m; ++i)
+            if (g.key[chunk * LG_C + i] == want) { found = chunk * LG_C + i; foundCell = cellId[q]; break; }
+        }
+      }
+    }
+  } else {
+    for (int zz = z0; zz <= z1 && found < 0; ++zz)
+      for (int yy = y0; yy <= y1 && found < 0; ++yy)
+        for (int xx = x0; xx <= x1 && found < 0; ++xx) {
+          const int cell = kind * LM_NCELL + xx + LM_GX * (yy + LM_GY * zz);
+          const int2 d = g.dir[cell];
+          int chunk = d.y;
+          for (int left = d.x; left > 0 && found < 0; left -= LG_C, chunk = left > 0 ? g.next[chunk] : -1) {
+            const int m = min(left, LG_C);
+            for (int i = 0; i < m; ++i)
+              if (g.key[chunk * LG_C + i] == want) { found = chunk * LG_C + i; foundCell = cell; break; }
+          }
+        }
+  }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int cnt = 0;
+  if (found >= 0) { acc = rf_fold(acc, g.pts[found]); cnt = 1; }
+  const int segEnd = w->tailBegin[sg + 1];
+  for (int q = t; q < segEnd && RF_VOX(keys[q]) == vk; ++q) { acc = rf_fold(acc, newPts[(unsigned)(keys[q] & 0x3ffffffull) - (1u << 25)]); ++cnt; }
+  const float4 c = rf_centroid(acc, cnt);
+  if (lm_vox_key(c, inv, ci, cj, ck, s->cenW, s->cenH, s->cenD) != vk) g.hdr->dirty = 1;  // drifted across a voxel face: pool path next sweep
+  const int cell = kind * LM_NCELL + lg_cell_of(c, o);
+  if (found >= 0 && cell == foundCell) { g.pts[found] = c; return; }
+  if (found >= 0) { g.pts[found].x = CUDART_INF_F; g.key[found] = LG_DEAD; atomicAdd(&g.hdr->dead, 1); }
+  else atomicAdd(&g.hdr->count[kind], 1);
+  LgOp op; op.p = c; op.key = want; op.cell = cell; op.pos = found >= 0 ? g.posOf[found] : -1;
+  ops[atomicAdd(&g.hdr->nOps, 1)] = op;
+}
+__global__ void __launch_bounds__(128) mu_insert(LgGrid g, const LgOp* __restrict__ ops) {
+  VL_PDL_WAIT();
+  const int n = g.hdr->nOps;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) lg_insert(g, ops[t].cell, ops[t].p, ops[t].key, ops[t].pos);
+}
+
+// ---- grid -> cube pools (the pools are the exchange format: export, window moves, the pool-path update) ----------------------
+// In-place updates leave the valid cubes' pool segments behind in two ways: coordinates of voxels that absorbed new points, and
+// voxels that did not exist when the grid was built.  mz_collect walks the grid once: an entry that came from the pools writes
+// its current coordinates back to its old position (the filtered prefix keeps its order: voxel keys do not change); a voxel
+// created since becomes a "new point" of ONE ordinary pool-path merge (rf_seg_scatter ... rf_finish with no stack points):
+// unique voxel keys, so the merge only moves each of them to its sorted position -- the cubes come out exactly as
+// pcl::VoxelGrid leaves them (LM.cpp:795-808), through the same code the pool path runs every sweep.
+__global__ void __launch_bounds__(256) mz_layout_for_grid(LmScalars* __restrict__ s, RfWork* __restrict__ w, LgHeader* __restrict__ gh,
+                                                          const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts) {
+  VL_PDL_WAIT();
+  __shared__ int sbuf[256];
+  const int t = threadIdx.x;
+  const int nv = gh->validNum;
+  if (t < VL_MAX_VALID && t < nv) s->validInd[t] = gh->validInd[t];  // the merge below addresses cubes through the context's list
+  if (t == 0) { s->validNum = nv; gh->nOps = 0; }
+  if (t <= LM_NSEG) { w->segCount[t] = 0; w->segFill[t] = 0; }
+  const int kind = t / VL_MAX_VALID, slot = t % VL_MAX_VALID;
+  int cnt = 0, srt = 0;
+  if (t < LM_NSEG && slot < nv) {
+    const MapCubeTable* tb = kind ? ts : tc;
+    cnt = tb->count[gh->validInd[slot]]; srt = tb->sorted[gh->validInd[slot]];
+  }
+  int tailTotal = 0, prefTotal = 0;
+  const int offTail = lm_scan256(cnt - srt, sbuf, &tailTotal);
+  const int offPref = lm_scan256(srt, sbuf, &prefTotal);
+  if (t < LM_NSEG) { w->tailOff[t] = offTail; w->prefOff[t] = offPref; }
+  if (t == 0) { w->tailOff[LM_NSEG] = tailTotal; w->prefOff[LM_NSEG] = prefTotal; }
+}
+__global__ void __launch_bounds__(256) mz_collect(LgGrid g, RfWork* __restrict__ w, const MapCubeTable* __restrict__ tc, const MapCubeTable* __restrict__ ts,
+                                                  float4* __restrict__ poolC, float4* __restrict__ poolS, float4* __restrict__ newPts,
+                                                  int* __restrict__ newCube, unsigned long long* __restrict__ keys, int cap) {
+  VL_PDL_WAIT();
+  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < 2 * LM_NCELL; cell += gridDim.x * blockDim.x) {
+    const int2 d = g.dir[cell];
+    const int kind = cell >= LM_NCELL;
+    int chunk = d.y;
+    for (int left = d.x; left > 0; left -= LG_C, chunk = left > 0 ? g.next[chunk] : -1) {
+      const int m = min(left, LG_C);
+      for (int i = 0; i < m; ++i) {
+        const int e = chunk * LG_C + i;
+        const unsigned long long key = g.key[e];
+        if (key == LG_DEAD) continue;
+        const int slot = (int)(key >> 32), cb = g.hdr->validInd[slot];
+        const int pos = g.posOf[e];
+        if (pos >= 0) { (kind ? poolS : poolC)[(kind ? ts : tc)->start[cb] + pos] = g.pts[e]; continue; }
+        const int j = atomicAdd(&g.hdr->nOps, 1);
+        if (j >= cap) { g.hdr->dirty = 1; continue; }  // (the host bounds the voxels created since the last build: cannot happen)
+        const int sg = kind * VL_MAX_VALID + slot;
+        newPts[j] = g.pts[e]; newCube[j] = -1;
+        keys[j] = ((unsigned long long)sg << 56) | ((unsigned long long)((unsigned)key & 0x3fffffffu) << 26) | (unsigned long long)((1u << 25) + (unsigned)j);
+        atomicAdd(&w->segCount[sg], 1);
+      }
+    }
+  }
+}
+
 // after an import: longest strictly increasing voxel-key prefix of every cube
 __global__ void __launch_bounds__(256) lm_scan_sorted(const LmScalars* __restrict__ s, vloam_b200_params prm, MapCubeTable* __restrict__ t,
                                                       const float4* __restrict__ pool, int kind) {
@@ -1344,7 +1478,7 @@ __global__ void lm_set_counts(LmScalars* s, RfWork* w, const int* qc, const int*
   if (threadIdx.x != 0) return;
   s->Qc = *qc; s->Qs = *qs;
   // LM.cpp:514: optimise only against a sub-map with > 10 corner and > 50 surf points
-  s->optimized = (s->Mc > 10 && s->Ms > 50 && *qc + *qs > 0) ? 1 : 0;
+  s->optimized = (s->Mc > 10 && s->Ms > 50 && *qc + *qs > 0 && !s->needSlow) ? 1 : 0;
   w->nq = s->optimized ? *qc + *qs : 0;  // factor slots the solver looks at
 }
 
@@ -1354,46 +1488,61 @@ __global__ void lm_set_counts(LmScalars* s, RfWork* w, const int* qc, const int*
 
 struct LmDevice {  // extra device state owned by this file
   RfWork* work;
-  int* cellCount;   // 2*LM_NCELL + 1 (scan output in place: cellStart)
-  int* cellStart;
-  int* cellFill;
-  int* tileSum;  // in-line (cooperative) build only
-  VlScan scan;   // speculative build: single-launch scan
-  DBuf<int> cellOfPoint;
-  DBuf<float4> sortedPts;
   DBuf<float4> newPts; DBuf<int> newCube;
   DBuf<int> unmatched;
   int* dQ;          // 2 x two device ints: Qc, Qs from the voxel filters (pair ctx::stackSel is current)
   long long hMapUpperC, hMapUpperS;  // host upper bounds on the total map size
-  LmSub* subReal; LmSub* subSpec;    // sub-map window descriptors (this frame's / the speculative one)
-  int* specOK;                       // device flag written by lm_prepare: the speculative sub-map is this frame's
-  bool specQueued;                   // host: a speculative build was queued after the last map update and nothing touched the map since
-  bool specEnabled;
-  int inlineGrid;                    // co-resident grid of lm_inline_build (cooperative launch)
+  LmSub* subReal; LmSub* subSpec;    // sub-map window descriptors (lm_prepare's / the one rebuilt after a pool-path update)
+  // ---- the persistent voxel-hash grid (lm_grid.cuh)
+  LgGrid grid;                       // device pointers (dir, chunks, allocator, header)
+  DBuf<LgOp> ops;                    // pending inserts of the in-place update
+  DBuf<int> knnIds;                  // debug capture: canonical ids of the neighbours
+  bool gridEnabled;                  // VLOAM_NO_SPECULATION / VLOAM_NO_GRID unset: in-place updates and the post-update rebuild are on
+  bool gridValid;                    // host: the grid was (re)built behind the last map update and nothing edited the map since
+  bool poolsStale;                   // host: the valid cubes' pools are behind the grid (in-place updates since the last materialisation)
+  long long gridTopUpper;            // host bound on the chunks in use
+  long long newVoxUpper;             // host bound on the voxels created by in-place updates since the grid was built
+  long long builtCount;              // live points the grid held when it was built
 };
 static LmDevice* lmdev(vloam_b200_ctx* c) { return reinterpret_cast<LmDevice*>(c->gridPrm); }
+
+// chunk pool of the grid: P points occupy at most min(P, cells) + P / LG_C chunks (every cell ends in one partly filled chunk)
+// (+ P / 4: chunks leaked by lost CAS races while many threads open the same cell at once)
+static long long lg_chunk_bound(long long points) { return (points < 2LL * LM_NCELL ? points : 2LL * LM_NCELL) + points / LG_C + points / 4 + 4096; }
+static int lg_reserve(vloam_b200_ctx* c, LmDevice* d, long long chunks) {
+  if (chunks <= d->grid.cap) return VLOAM_OK;
+  long long ncap = d->grid.cap ? d->grid.cap : (1LL << 20);
+  while (ncap < chunks) ncap *= 2;
+  VL_CUDA(cudaStreamSynchronize(VL_STREAM(c)));  // (only ever called right before a full rebuild: the old contents are dead)
+  if (d->grid.pts) { cudaFree(d->grid.pts); cudaFree(d->grid.key); cudaFree(d->grid.next); cudaFree(d->grid.posOf); }
+  __atomic_fetch_add(&c->regrows, 1LL, __ATOMIC_RELAXED);
+  VL_CUDA(cudaMalloc(&d->grid.pts, (size_t)ncap * LG_C * sizeof(float4)));
+  VL_CUDA(cudaMalloc(&d->grid.key, (size_t)ncap * LG_C * sizeof(unsigned long long)));
+  VL_CUDA(cudaMalloc(&d->grid.next, (size_t)ncap * sizeof(int)));
+  VL_CUDA(cudaMalloc(&d->grid.posOf, (size_t)ncap * LG_C * sizeof(int)));
+  d->grid.cap = (int)ncap;
+  return VLOAM_OK;
+}
 
 int vl_lm_init(vloam_b200_ctx* c) {
   LmDevice* d = new LmDevice();
   c->gridPrm = reinterpret_cast<GridParams*>(d);
   VL_CUDA(cudaMalloc(&d->work, sizeof(RfWork)));
   VL_CUDA(cudaMemset(d->work, 0, sizeof(RfWork)));
-  VL_CUDA(cudaMalloc(&d->cellCount, sizeof(int) * (2 * LM_NCELL + 1)));
-  VL_CUDA(cudaMalloc(&d->cellStart, sizeof(int) * (2 * LM_NCELL + 1)));
-  VL_CUDA(cudaMalloc(&d->cellFill, sizeof(int) * (2 * LM_NCELL + 1)));
-  VL_CUDA(cudaMalloc(&d->tileSum, sizeof(int) * (vl_div_up(2 * LM_NCELL, 1024) + 1)));
-  VL_TRY(vl_scan_alloc(&d->scan, 2 * LM_NCELL));
   VL_CUDA(cudaMalloc(&d->dQ, sizeof(int) * 4));
   VL_CUDA(cudaMemset(d->dQ, 0, sizeof(int) * 4));
   VL_CUDA(cudaMalloc(&d->subReal, sizeof(LmSub))); VL_CUDA(cudaMemset(d->subReal, 0, sizeof(LmSub)));
   VL_CUDA(cudaMalloc(&d->subSpec, sizeof(LmSub))); VL_CUDA(cudaMemset(d->subSpec, 0, sizeof(LmSub)));
-  VL_CUDA(cudaMalloc(&d->specOK, sizeof(int))); VL_CUDA(cudaMemset(d->specOK, 0, sizeof(int)));
-  d->specQueued = false;
-  d->specEnabled = getenv("VLOAM_NO_SPECULATION") == nullptr;
+  memset(&d->grid, 0, sizeof d->grid);
+  VL_CUDA(cudaMalloc(&d->grid.dir, sizeof(int2) * 2 * LM_NCELL));
+  VL_CUDA(cudaMalloc(&d->grid.top, sizeof(int)));
+  VL_CUDA(cudaMemset(d->grid.top, 0, sizeof(int)));
+  VL_CUDA(cudaMalloc(&d->grid.hdr, sizeof(LgHeader)));
+  VL_CUDA(cudaMemset(d->grid.hdr, 0, sizeof(LgHeader)));
+  VL_TRY(lg_reserve(c, d, 1 << 21));  // 2 Mi chunks (~0.8 GB of the 180 GB): a ~30M-point sub-map before the first regrow
+  d->gridEnabled = getenv("VLOAM_NO_SPECULATION") == nullptr && getenv("VLOAM_NO_GRID") == nullptr;
+  d->gridValid = false; d->poolsStale = false; d->gridTopUpper = 0; d->newVoxUpper = 0; d->builtCount = 0;
   VL_CUDA(cudaFuncSetAttribute(rf_seg_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, RF_SEG_CAP * 8));
-  int perSm = 0;
-  VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, lm_inline_build, 256, 0));
-  d->inlineGrid = c->num_sms * max(1, min(perSm, 4));
   d->hMapUpperC = d->hMapUpperS = 0;
   // Map pools: bump allocation with doubling per cube; when a pool is half full it is doubled (copy) at sync point
   // S2, so a long drive degrades into a rare ~ms stall instead of VLOAM_E_CAPACITY.  VLOAM_POOL_POINTS: initial
@@ -1421,10 +1570,9 @@ int vl_lm_init(vloam_b200_ctx* c) {
 void vl_lm_free(vloam_b200_ctx* c) {  // everything vl_lm_init and this file's reserves own (the pools are freed by capi.cu)
   LmDevice* d = lmdev(c);
   if (!d) return;
-  void* dev[] = {d->work, d->cellCount, d->cellStart, d->cellFill, d->tileSum, d->dQ, d->subReal, d->subSpec, d->specOK,
-                 d->cellOfPoint.p, d->sortedPts.p, d->newPts.p, d->newCube.p, d->unmatched.p};
+  void* dev[] = {d->work, d->dQ, d->subReal, d->subSpec, d->newPts.p, d->newCube.p, d->unmatched.p, d->grid.dir, d->grid.top, d->grid.hdr,
+                 d->grid.pts, d->grid.key, d->grid.next, d->grid.posOf, d->ops.p, d->knnIds.p};
   for (void* p : dev) if (p) cudaFree(p);
-  vl_scan_free(&d->scan);
   delete d;
   c->gridPrm = nullptr;
 }
@@ -1491,23 +1639,149 @@ int vl_lm_adopt_stacks_next(vloam_b200_ctx* c) {
   return VLOAM_OK;
 }
 
-// in-line sub-map build of this frame (one cooperative launch; returns at once on the device when *specOK)
-static int lm_inline_launch(vloam_b200_ctx* c, LmDevice* d, long long totalBound) {
-  LmInlineArgs a;
-  a.sub = d->subReal; a.skip = d->specOK; a.tc = c->cubeC; a.ts = c->cubeS; a.poolC = c->poolC.p; a.poolS = c->poolS.p;
-  a.outC = c->fromMapC.p; a.outS = c->fromMapS.p; a.cellCount = d->cellCount; a.cellFill = d->cellFill; a.cellStart = d->cellStart;
-  a.tileSum = d->tileSum; a.cellOfPoint = d->cellOfPoint.p; a.sortedPts = d->sortedPts.p; a.nCells = 2 * LM_NCELL;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(d->inlineGrid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = VL_STREAM(c);
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  const bool prof = c->prof_name[0] && vl_prof_match(c, "lm_inline_build") && c->prof_n < VL_PROF_MAX;
-  if (prof) cudaEventRecord(c->prof_ev[c->prof_n][0], VL_STREAM(c));
-  VL_CUDA(cudaLaunchKernelEx(&cfg, lm_inline_build, a));
-  if (prof) { cudaEventRecord(c->prof_ev[c->prof_n][1], VL_STREAM(c)); c->prof_kname[c->prof_n] = "lm_inline_build";
-              c->prof_kbytes[c->prof_n] = 100.0 * (double)totalBound; c->prof_kstream[c->prof_n] = VL_STREAM(c); c->prof_n++; }
-  __atomic_fetch_add(&c->launches, 1LL, __ATOMIC_RELAXED);
+// ---- host side of the voxel-hash grid ------------------------------------------------------------------------------------
+// (re)build the grid for the window `sub` describes from the cube pools, on the calling thread's stream
+static int lg_rebuild_launch(vloam_b200_ctx* c, LmDevice* d, const LmSub* sub, long long pointsBound) {
+  VL_TRY(lg_reserve(c, d, lg_chunk_bound(pointsBound)));
+  const int gsGrid = c->num_sms * 8;
+  VL_BYTES(16.0 * LM_NCELL);
+  VL_LAUNCH(lg_zero, gsGrid, 256, 0, d->grid, sub);
+  VL_BYTES(16.0 * (double)pointsBound);  // SURVEY 8(d) B_lm: the sub-map is read once to build the search structure
+  VL_LAUNCH(lg_rebuild, gsGrid, 256, 0, d->grid, sub, c->lmm, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p);
+  d->gridTopUpper = lg_chunk_bound(pointsBound);
+  d->newVoxUpper = 0; d->builtCount = -1;  // (-1: taken from the device count at the next sync point S2)
+  return VLOAM_OK;
+}
+
+// Pool head room: a cube that outgrows its segment gets a new one of twice its new size, so one pass over the valid cubes
+// allocates at most 2 x (points + inserts) + 256 per touched cube.  When that no longer fits the pool is doubled (copy) --
+// only ever called where the previous update is complete and the next one has not been issued.
+static int lm_pool_headroom(vloam_b200_ctx* c, long long totalC, long long totalS, int Qc, int Qs) {
+  const size_t needC = 2 * ((size_t)totalC + Qc) + 256 * (size_t)(VL_MAX_VALID + min(Qc, VL_CUBE_NUM));
+  const size_t needS = 2 * ((size_t)totalS + Qs) + 256 * (size_t)(VL_MAX_VALID + min(Qs, VL_CUBE_NUM));
+  if ((size_t)c->h_lmm->poolTopC + needC > c->poolC.cap) VL_TRY(vl_reserve(c, c->poolC, 2 * ((size_t)c->h_lmm->poolTopC + needC), true));
+  if ((size_t)c->h_lmm->poolTopS + needS > c->poolS.cap) VL_TRY(vl_reserve(c, c->poolS, 2 * ((size_t)c->h_lmm->poolTopS + needS), true));
+  return VLOAM_OK;
+}
+
+// grid -> pools for the valid cubes of the grid's window (the in-place updates left those pools behind); on the calling thread's stream
+#define LG_NEWVOX_MAX (1 << 20)  // voxels the in-place updates may create before the pools are brought up to date (bounds the merge's buffers)
+// buffers of the grid -> pools merge, sized once (a first window move must not stall on five cudaMallocs)
+static int lm_reserve_merge(vloam_b200_ctx* c, LmDevice* d, long long total) {
+  const size_t P = LG_NEWVOX_MAX, N = P;
+  VL_TRY(vl_reserve(c, c->tailKeys, 4 * N));
+  VL_TRY(vl_reserve(c, d->newPts, P));
+  VL_TRY(vl_reserve(c, d->newCube, P));
+  VL_TRY(vl_reserve(c, d->unmatched, P + 2));
+  VL_TRY(vl_reserve(c, c->staging, (size_t)total + P + 1, false, (size_t)total / 2 + (1 << 20)));
+  return VLOAM_OK;
+}
+
+static int lm_materialize(vloam_b200_ctx* c, LmDevice* d) {
+  const long long total = d->hMapUpperC + d->hMapUpperS;
+  const int P = (int)max(min(d->newVoxUpper, (long long)LG_NEWVOX_MAX), 1LL);   // bound on the voxels created since the grid was built
+  VL_TRY(lm_pool_headroom(c, d->hMapUpperC, d->hMapUpperS, 0, 0));
+  const size_t N = ((size_t)P + 255) & ~(size_t)255;
+  VL_TRY(vl_reserve(c, c->tailKeys, 4 * N, false, 4 * N));  // [0, N) unsorted keys | [N, 2N) bucketed + sorted | [2N, 4N) scratch for oversize segments
+  unsigned long long* keysIn = c->tailKeys.p;
+  unsigned long long* keysSorted = c->tailKeys.p + N;
+  VL_TRY(vl_reserve(c, d->newPts, (size_t)P));
+  VL_TRY(vl_reserve(c, d->newCube, (size_t)P));
+  VL_TRY(vl_reserve(c, d->unmatched, (size_t)P + 2, false, (size_t)P + (1 << 16)));
+  VL_TRY(vl_reserve(c, c->staging, (size_t)total + P + 1, false, (size_t)total / 2 + (1 << 20)));
+  const int gsGrid = c->num_sms * 8;
+  VL_CUDA(cudaMemsetAsync(keysIn, 0xff, N * sizeof(unsigned long long), VL_STREAM(c)));  // unused key slots read as "no key"
+  VL_LAUNCH(mz_layout_for_grid, 1, 256, 0, c->lmm, d->work, d->grid.hdr, c->cubeC, c->cubeS);
+  VL_BYTES(32.0 * (double)total);
+  VL_LAUNCH(mz_collect, gsGrid, 256, 0, d->grid, d->work, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, d->newPts.p, d->newCube.p, keysIn, P);
+  VL_LAUNCH(rf_seg_scatter, vl_div_up(P, 256), 256, 0, keysIn, P, d->work, keysSorted);
+  VL_LAUNCH(rf_seg_sort, LM_NSEG, RF_SEG_THREADS, (size_t)RF_SEG_CAP * 8, keysSorted, d->work, c->tailKeys.p + 2 * N, RF_SEG_CAP);
+  VL_LAUNCH(rf_match, vl_div_up(P, 256), 256, 0, keysSorted, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, d->unmatched.p);
+  VL_LAUNCH(rf_scan_layout, 1, 1024, 0, d->unmatched.p, c->lmm, d->work, c->cubeC, c->cubeS);
+  VL_BYTES(32.0 * (double)total);
+  VL_LAUNCH(rf_emit, vl_div_up(P, 256) + gsGrid, 256, 0, vl_div_up(P, 256), keysSorted, d->unmatched.p, c->lmm, d->work, c->prm, c->cubeC,
+            c->cubeS, c->poolC.p, c->poolS.p, d->newPts.p, c->staging.p);
+  VL_LAUNCH(rf_alloc, 1, 256, 0, c->lmm, d->work, c->cubeC, c->cubeS, (int)c->poolC.cap, (int)c->poolS.cap);
+  VL_BYTES(32.0 * (double)total);
+  VL_LAUNCH(rf_commit, gsGrid, 256, 0, c->staging.p, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p);
+  VL_LAUNCH(rf_finish, 1, 256, 0, c->lmm, d->work, c->cubeC, c->cubeS);
+  d->poolsStale = false;
+  d->gridValid = false;  // (the entries' pool positions are no longer the pools': the grid is rebuilt before its next use)
+  d->newVoxUpper = 0;
+  VL_CUDA(cudaGetLastError());
+  return VLOAM_OK;
+}
+
+// make the cube pools current (export, import, external edits): nothing to do unless in-place updates ran since
+int vl_lm_sync_pools(vloam_b200_ctx* c) {
+  LmDevice* d = lmdev(c);
+  if (!d || !d->poolsStale) return VLOAM_OK;
+  VL_TRY(vl_lm_join(c));
+  VL_CUDA(cudaStreamWaitEvent(c->stream, c->evMap, 0));
+  VL_CUDA(cudaMemcpyAsync(c->h_lmm, c->lmm, sizeof(LmScalars), cudaMemcpyDeviceToHost, c->stream));  // poolTop for the head-room check
+  VL_CUDA(cudaStreamSynchronize(c->stream));
+  VL_TRY(lm_materialize(c, d));
+  VL_CUDA(cudaStreamSynchronize(c->stream));
+  return VLOAM_OK;
+}
+
+// the two association + solve passes of LM.cpp:526-717 and transformUpdate (LM.cpp:737); every kernel reads its sizes on the device
+static int lm_queue_passes(vloam_b200_ctx* c, LmDevice* d, int nqBound, bool capture, const LmSub* sub) {
+  VL_CUDA(cudaStreamWaitEvent(c->stream, c->evStacks, 0));   // only now are this frame's downsampled stacks needed (side streams)
+  VL_CUDA(cudaStreamWaitEvent(c->stream, c->evStacksC, 0));
+  VL_LAUNCH(lm_set_counts, 1, 32, 0, c->lmm, d->work, d->dQ + 2 * c->stackSel, d->dQ + 2 * c->stackSel + 1);
+  if (c->timing) VL_CUDA(cudaEventRecord(c->evx[1], c->stream));
+  int Qc = 0, Qs = 0;
+  if (capture) {  // debug snapshots need host counts first
+    VL_CUDA(cudaMemcpyAsync(c->h_lmm, c->lmm, sizeof(LmScalars), cudaMemcpyDeviceToHost, c->stream));
+    VL_CUDA(cudaStreamSynchronize(c->stream));
+    Qc = c->h_lmm->Qc; Qs = c->h_lmm->Qs;
+    VL_TRY(vl_reserve(c, c->knnKey, (size_t)nqBound * 5));
+    VL_TRY(vl_reserve(c, d->knnIds, (size_t)nqBound * 5));
+  }
+  for (int pass = 0; pass < 2; ++pass) {  // LM.cpp:526
+    VL_BYTES(16.0 * (double)max(c->h_lmm->Qc + c->h_lmm->Qs, 1) * 6);  // query + 5 neighbours, last known Qc + Qs
+    VL_LAUNCH(lg_knn, c->num_sms * 8, 256, 0, c->lmm, d->grid, c->stackC.p, c->stackS.p, c->knnPts.p, c->knnD2.p, capture ? c->knnKey.p : (unsigned long long*)nullptr);
+    VL_BYTES((16.0 * 6 + 24.0 + 84.0) * (double)max(c->h_lmm->Qc + c->h_lmm->Qs, 1));
+    VL_LAUNCH(lm_fit, c->num_sms, 128, 0, c->lmm, c->stackC.p, c->stackS.p, c->knnPts.p, c->knnD2.p, c->knnOk.p, c->factors.p, c->factorValid.p);
+    if (capture) {
+      const int nq = Qc + Qs;
+      if (nq > 0) VL_LAUNCH(lg_keys_to_ids, vl_div_up(nq * 5, 256), 256, 0, c->knnKey.p, nq * 5, Qc, sub, c->lmm, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, d->knnIds.p);
+      for (int kind = 0; kind < 2; ++kind) {
+        const int n = kind ? Qs : Qc, off = kind ? Qc : 0;
+        VL_TRY(vl_reserve(c, c->dbgKnnIdx[pass][kind], (size_t)max(n, 1) * 5));
+        VL_TRY(vl_reserve(c, c->dbgKnnD2[pass][kind], (size_t)max(n, 1) * 5));
+        VL_TRY(vl_reserve(c, c->dbgKnnOk[pass][kind], (size_t)max(n, 1)));
+        if (n == 0) continue;
+        VL_CUDA(cudaMemcpyAsync(c->dbgKnnIdx[pass][kind].p, d->knnIds.p + (size_t)off * 5, sizeof(int) * 5 * n, cudaMemcpyDeviceToDevice, c->stream));
+        VL_CUDA(cudaMemcpyAsync(c->dbgKnnD2[pass][kind].p, c->knnD2.p + (size_t)off * 5, sizeof(float) * 5 * n, cudaMemcpyDeviceToDevice, c->stream));
+        VL_CUDA(cudaMemcpyAsync(c->dbgKnnOk[pass][kind].p, c->knnOk.p + off, sizeof(int) * n, cudaMemcpyDeviceToDevice, c->stream));
+      }
+    }
+    VL_TRY(vl_solve(c, nqBound, &d->work->nq, c->lmm->pose, capture ? &c->dbgLmCost[pass * 2] : nullptr, c->h_lmm->Qc + c->h_lmm->Qs));
+    if (c->timing && pass == 0) VL_CUDA(cudaEventRecord(c->evx[2], c->stream));
+  }
+  VL_LAUNCH(lm_transform_update, 1, 32, 0, c->lmm, d->grid.hdr, d->grid.top);  // LM.cpp:737 (runs even when the optimisation was skipped)
+  return VLOAM_OK;
+}
+
+// sync point S2: the pose is final; sizes for the map update.  While the device finishes this sweep's mapping, the next sweep's
+// odometry solve is queued (replays with a registered look-ahead sweep) -- once per call of vl_lm_run.
+static int lm_sync_s2(vloam_b200_ctx* c, bool capture, bool* lookaheadDone) {
+  VL_CUDA(cudaEventRecord(c->evPose, c->stream));
+  VL_CUDA(cudaMemcpyAsync(c->h_los, c->los, sizeof(LoScalars), cudaMemcpyDeviceToHost, c->stream));
+  VL_CUDA(cudaMemcpyAsync(c->h_lmm, c->lmm, sizeof(LmScalars), cudaMemcpyDeviceToHost, c->stream));
+  VL_CUDA(cudaEventRecord(c->evS2, c->stream));
+  VL_HOST_MARK(5);
+  if (!*lookaheadDone) {
+    VL_TRY(vl_lo_flush_deferred(c));
+    if (!capture) VL_TRY(vl_lo_lookahead(c));
+    *lookaheadDone = true;
+  }
+  VL_CUDA(cudaEventSynchronize(c->evS2));
+  c->s2Done = true;
+  VL_HOST_MARK(6);
+  if (c->h_lmm->overflow) { snprintf(c->err, sizeof c->err, "map pool exhausted"); return VLOAM_E_CAPACITY; }
   return VLOAM_OK;
 }
 
@@ -1517,123 +1791,122 @@ int vl_lm_run(vloam_b200_ctx* c) {
   VL_TRY(vl_lm_join(c));  // the previous frame's map update has been issued (evMap recorded, host bounds updated)
   VL_HOST_MARK(4);
   const int skip = c->skip_frame ? 1 : 0;
-  VL_CUDA(cudaStreamWaitEvent(c->stream, c->evMap, 0));  // the previous frame's map update (stream3) must be complete
-  VL_CUDA(cudaStreamWaitEvent(c->stream, c->evAux, 0));  // ... including its outside appends (streamAux)
-  VL_LAUNCH(lm_prepare, 1, 1024, 0, c->lmm, c->los, c->cubeC, c->cubeS, d->work, skip, c->lm_reset_pending ? 1 : 0, d->subReal, d->subSpec,
-            d->specQueued ? 1 : 0, d->specOK);
+  const int resetValid = c->lm_reset_pending ? 1 : 0;
   c->lm_reset_pending = false;
-  if (skip) { VL_TRY(vl_lo_flush_deferred(c)); VL_CUDA(cudaGetLastError()); return VLOAM_OK; }
+  VL_CUDA(cudaStreamWaitEvent(c->stream, c->evMap, 0));  // the previous frame's map update (stream3) must be complete
+  VL_CUDA(cudaStreamWaitEvent(c->stream, c->evAux, 0));  // ... including its outside appends (streamAux, pool path)
+  if (skip) {  // LM.cpp:197-201: only the high-frequency pose is propagated
+    VL_LAUNCH(lm_prepare_fast, 1, 256, 0, c->lmm, c->los, d->work, d->grid.hdr, 1, resetValid);
+    VL_TRY(vl_lo_flush_deferred(c)); VL_CUDA(cudaGetLastError());
+    return VLOAM_OK;
+  }
   const int gsGrid = c->num_sms * 8;
-  VL_TRY(vl_reserve(c, c->fromMapC, (size_t)max(d->hMapUpperC, 1LL), false, (size_t)d->hMapUpperC / 2 + (1 << 20)));
-  VL_TRY(vl_reserve(c, c->fromMapS, (size_t)max(d->hMapUpperS, 1LL), false, (size_t)d->hMapUpperS / 2 + (1 << 20)));
   if (!c->stacksReady) {  // laser_mapping called without this frame's laser_odometry having queued them
     VL_CUDA(cudaStreamSynchronize(c->stream));
     VL_TRY(vl_lm_enqueue_stacks(c, c->cornerLastPtr, c->nCornerLast, c->surfLastPtr, c->nSurfLast));
   }
   c->stacksReady = false;
-  // The search / fit / solve kernels read the sizes (Mc, Ms, Qc, Qs) and the LM.cpp:514 decision on the
-  // device, so they are queued without waiting for the host; sync point S2 sits after the solve, where
-  // the pose has to be final anyway.  (Debug snapshots need host counts first and sync here.)
   const bool capture = vl_debug_capture(c);
-  int Qc = 0, Qs = 0;
-  const long long totalBound = d->hMapUpperC + d->hMapUpperS;
   const int nqBound = max(c->nCornerLast + c->nSurfLast, 1);  // a voxel filter never grows a cloud
-  {
-    VL_TRY(vl_reserve(c, d->cellOfPoint, (size_t)max(totalBound, 1LL), false, (size_t)totalBound / 2 + (1 << 20)));
-    VL_TRY(vl_reserve(c, d->sortedPts, (size_t)max(totalBound, 1LL), false, (size_t)totalBound / 2 + (1 << 20)));
-    VL_TRY(lm_inline_launch(c, d, totalBound));  // returns at once on the device when lm_prepare found the speculative build valid
+  VL_TRY(vl_reserve(c, c->knnPts, (size_t)nqBound * 5));
+  VL_TRY(vl_reserve(c, c->knnD2, (size_t)nqBound * 5));
+  VL_TRY(vl_reserve(c, c->knnOk, (size_t)nqBound));
+  VL_TRY(vl_reserve(c, c->factors, (size_t)nqBound * 10));
+  VL_TRY(vl_reserve(c, c->factorValid, (size_t)nqBound));
+  bool lookaheadDone = false;
+  static const bool noWorker = getenv("VLOAM_NO_WORKER") != nullptr;
+  const bool inlineUpdate = noWorker || capture || c->prof_name[0];  // profiling and debug snapshots serialise everything
+
+  // ---- in-place path: the grid describes this sweep's sub-map unless lm_prepare_fast finds the window moved / the grid dirty
+  if (d->gridEnabled && d->gridValid && !capture && d->gridTopUpper + 2LL * nqBound <= d->grid.cap && d->newVoxUpper + nqBound <= LG_NEWVOX_MAX) {
+    VL_LAUNCH(lm_prepare_fast, 1, 256, 0, c->lmm, c->los, d->work, d->grid.hdr, 0, resetValid);
     if (c->timing) VL_CUDA(cudaEventRecord(c->evx[0], c->stream));
-    // only now are this frame's downsampled stacks needed (they were filtered on the side streams)
-    VL_CUDA(cudaStreamWaitEvent(c->stream, c->evStacks, 0));
-    VL_CUDA(cudaStreamWaitEvent(c->stream, c->evStacksC, 0));
-    VL_LAUNCH(lm_set_counts, 1, 32, 0, c->lmm, d->work, d->dQ + 2 * c->stackSel, d->dQ + 2 * c->stackSel + 1);
-    if (c->timing) VL_CUDA(cudaEventRecord(c->evx[1], c->stream));
-    if (capture) {
-      VL_CUDA(cudaMemcpyAsync(c->h_lmm, c->lmm, sizeof(LmScalars), cudaMemcpyDeviceToHost, c->stream));
-      VL_CUDA(cudaStreamSynchronize(c->stream));
-      Qc = c->h_lmm->Qc; Qs = c->h_lmm->Qs;
-    }
-    VL_TRY(vl_reserve(c, c->knnIdx, (size_t)nqBound * 5));
-    VL_TRY(vl_reserve(c, c->knnD2, (size_t)nqBound * 5));
-    VL_TRY(vl_reserve(c, c->knnOk, (size_t)nqBound));
-    VL_TRY(vl_reserve(c, c->factors, (size_t)nqBound * 10));
-    VL_TRY(vl_reserve(c, c->factorValid, (size_t)nqBound));
-    for (int pass = 0; pass < 2; ++pass) {  // LM.cpp:526
-      VL_BYTES(16.0 * 7000 * 6);  // query + 5 neighbours, typical Qc + Qs
-      VL_LAUNCH(lm_knn, c->num_sms * 8, 256, 0, c->lmm, d->work, c->stackC.p, c->stackS.p, c->fromMapC.p,
-                c->fromMapS.p, d->cellStart, d->sortedPts.p, c->knnIdx.p, c->knnD2.p, c->knnOk.p, c->factors.p, c->factorValid.p);
-      VL_BYTES((16.0 * 6 + 24.0 + 84.0) * 7000);
-      VL_LAUNCH(lm_fit, c->num_sms, 128, 0, c->lmm, c->stackC.p, c->stackS.p, c->fromMapC.p, c->fromMapS.p, c->knnIdx.p, c->knnD2.p,
-                c->knnOk.p, c->factors.p, c->factorValid.p);
-      if (capture) {
-        for (int kind = 0; kind < 2; ++kind) {
-          const int n = kind ? Qs : Qc, off = kind ? Qc : 0;
-          VL_TRY(vl_reserve(c, c->dbgKnnIdx[pass][kind], (size_t)max(n, 1) * 5));
-          VL_TRY(vl_reserve(c, c->dbgKnnD2[pass][kind], (size_t)max(n, 1) * 5));
-          VL_TRY(vl_reserve(c, c->dbgKnnOk[pass][kind], (size_t)max(n, 1)));
-          if (n == 0) continue;
-          VL_CUDA(cudaMemcpyAsync(c->dbgKnnIdx[pass][kind].p, c->knnIdx.p + (size_t)off * 5, sizeof(int) * 5 * n, cudaMemcpyDeviceToDevice, c->stream));
-          VL_CUDA(cudaMemcpyAsync(c->dbgKnnD2[pass][kind].p, c->knnD2.p + (size_t)off * 5, sizeof(float) * 5 * n, cudaMemcpyDeviceToDevice, c->stream));
-          VL_CUDA(cudaMemcpyAsync(c->dbgKnnOk[pass][kind].p, c->knnOk.p + off, sizeof(int) * n, cudaMemcpyDeviceToDevice, c->stream));
+    VL_TRY(lm_queue_passes(c, d, nqBound, false, d->subReal));
+    VL_TRY(lm_sync_s2(c, false, &lookaheadDone));
+    if (!c->h_lmm->needSlow) {
+      const int Qc = c->h_lmm->Qc, Qs = c->h_lmm->Qs, nq = Qc + Qs;
+      if (d->builtCount < 0) d->builtCount = c->h_lmm->gridCount;  // first in-place sweep after a rebuild: nothing created yet
+      c->lm_optimized = c->h_lmm->optimized;
+      const float4* const stackCp = c->stackC.p; const float4* const stackSp = c->stackS.p;  // (the next frame may swap the buffers while the helper issues this)
+      const int stackSelNow = c->stackSel;
+      d->gridTopUpper = (long long)c->h_lmm->gridTop + nq;  // chunks in use before this update + at most one new chunk per new voxel
+      VL_TRY(lm_pool_headroom(c, 0, 0, Qc, Qs));  // (points outside the window are appended raw to their cubes' pool segments)
+      d->hMapUpperC += Qc; d->hMapUpperS += Qs;
+      d->newVoxUpper = (long long)c->h_lmm->gridCount - d->builtCount + nq;  // voxels created so far (device count at S2) + at most nq by this update
+      if (nq > 0) d->poolsStale = true;
+      auto update = [=]() -> int {
+        vl_tls_stream = c->stream3;
+        struct Restore { ~Restore() { vl_tls_stream = nullptr; } } restore;
+        VL_CUDA(cudaStreamWaitEvent(c->stream3, c->evPose, 0));
+        if (nq > 0) {
+          const size_t N = ((size_t)nq + 255) & ~(size_t)255;
+          VL_TRY(vl_reserve(c, c->tailKeys, 4 * N, false, 4 * N));
+          unsigned long long* keysIn = c->tailKeys.p;
+          unsigned long long* keysSorted = c->tailKeys.p + N;
+          VL_TRY(vl_reserve(c, d->newPts, (size_t)nq));
+          VL_TRY(vl_reserve(c, d->newCube, (size_t)nq));
+          VL_TRY(vl_reserve(c, d->ops, (size_t)nq));
+          VL_BYTES(16.0 * nq);  // SURVEY 8(d) B_lm insert term: every new point once
+          VL_LAUNCH(rf_keys, vl_div_up(nq, 256), 256, 0, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, stackCp, stackSp,
+                    d->newPts.p, d->newCube.p, keysIn, nq, 1);
+          VL_CUDA(cudaEventRecord(c->evKeys, c->stream3));  // nothing below reads the stacks any more: the next sweep's filters may overwrite them
+          VL_CUDA(cudaEventRecord(c->evKeysSel[stackSelNow], c->stream3));
+          VL_LAUNCH(rf_seg_scatter, vl_div_up(nq, 256), 256, 0, keysIn, nq, d->work, keysSorted);
+          static const int segCap = getenv("VLOAM_SEG_CAP") ? max(8, min(atoi(getenv("VLOAM_SEG_CAP")), RF_SEG_CAP)) : RF_SEG_CAP;  // tests force the global path
+          VL_BYTES(16.0 * nq);
+          VL_LAUNCH(rf_seg_sort, LM_NSEG, RF_SEG_THREADS, (size_t)RF_SEG_CAP * 8, keysSorted, d->work, c->tailKeys.p + 2 * N, segCap);
+          VL_BYTES(2.0 * 32.0 * nq);  // read + write of the ~nq map points that change (SURVEY 8(d) re-filter term restricted to what changes)
+          VL_LAUNCH(mu_apply, vl_div_up(nq, 128), 128, 0, keysSorted, c->lmm, d->work, c->prm, d->grid, d->newPts.p, d->ops.p);
+          VL_LAUNCH(mu_insert, min(vl_div_up(nq, 128), c->num_sms * 4), 128, 0, d->grid, d->ops.p);
+          VL_LAUNCH(rf_append_outside, 1, 1024, 0, c->lmm, d->newPts.p, d->newCube.p, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, (int)c->poolC.cap,
+                    (int)c->poolS.cap);
         }
-      }
-      VL_TRY(vl_solve(c, nqBound, &d->work->nq, c->lmm->pose, capture ? &c->dbgLmCost[pass * 2] : nullptr, c->h_lmm->Qc + c->h_lmm->Qs));
-      if (c->timing && pass == 0) VL_CUDA(cudaEventRecord(c->evx[2], c->stream));
+        VL_CUDA(cudaEventRecord(c->evMap, c->stream3));
+        return VLOAM_OK;
+      };
+      c->lm_frameCount++;
+      if (inlineUpdate) { const int rmap = update(); if (rmap != VLOAM_OK) return rmap; }
+      else VL_TRY(lm_submit(c, update));
+      VL_HOST_MARK(7);
+      VL_CUDA(cudaGetLastError());
+      return VLOAM_OK;
     }
+    // needSlow: nothing of this sweep's mapping was applied (every kernel above returned at once); repeat it on the pool path
   }
-  VL_LAUNCH(lm_transform_update, 1, 32, 0, c->lmm);  // LM.cpp:737 (runs even when the optimisation was skipped)
+
+  // ---- pool path (round 1's): cube tables, sorted pools; the grid is rebuilt for the window lm_prepare finds
+  if (d->poolsStale) VL_TRY(lm_materialize(c, d));  // the in-place updates since the last pool-path sweep, written back first (main stream)
+  VL_LAUNCH(lm_prepare, 1, 1024, 0, c->lmm, c->los, c->cubeC, c->cubeS, d->work, 0, resetValid, d->subReal);
+  const long long totalBound = d->hMapUpperC + d->hMapUpperS;
+  if (d->gridEnabled) VL_TRY(lm_reserve_merge(c, d, totalBound));
+  VL_TRY(lg_rebuild_launch(c, d, d->subReal, totalBound));
+  if (c->timing) VL_CUDA(cudaEventRecord(c->evx[0], c->stream));
+  if (capture) {  // the debug getters read the concatenated sub-map clouds (LM.cpp:476-485)
+    VL_TRY(vl_reserve(c, c->fromMapC, (size_t)max(d->hMapUpperC, 1LL), false, (size_t)d->hMapUpperC / 2 + (1 << 20)));
+    VL_TRY(vl_reserve(c, c->fromMapS, (size_t)max(d->hMapUpperS, 1LL), false, (size_t)d->hMapUpperS / 2 + (1 << 20)));
+    VL_LAUNCH(lm_gather, gsGrid, 256, 0, d->subReal, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, c->fromMapC.p, c->fromMapS.p);
+  }
+  VL_TRY(lm_queue_passes(c, d, nqBound, capture, d->subReal));
   // ---- map update (LM.cpp:741-808).  The pose is final here; the update runs on stream3 so that the caller can
   // read the pose, and the next frame's scan registration + odometry can start, while the map is brought up to date.
-  VL_CUDA(cudaEventRecord(c->evPose, c->stream));
-  // ---- sync point S2: sizes for the map update (and the pose, which is final now)
-  VL_CUDA(cudaMemcpyAsync(c->h_los, c->los, sizeof(LoScalars), cudaMemcpyDeviceToHost, c->stream));
-  VL_CUDA(cudaMemcpyAsync(c->h_lmm, c->lmm, sizeof(LmScalars), cudaMemcpyDeviceToHost, c->stream));
-  VL_CUDA(cudaEventRecord(c->evS2, c->stream));
-  VL_HOST_MARK(5);
-  // While the device finishes this sweep's mapping, the next sweep's odometry solve is queued behind it (replays with a
-  // registered look-ahead sweep): the device then runs on without the S2 -> caller -> next call round trip (~40 us).
-  VL_TRY(vl_lo_flush_deferred(c));
-  if (!capture) VL_TRY(vl_lo_lookahead(c));
-  VL_CUDA(cudaEventSynchronize(c->evS2));
-  c->s2Done = true;
-  VL_HOST_MARK(6);
+  VL_TRY(lm_sync_s2(c, capture, &lookaheadDone));
   const int Mc = c->h_lmm->Mc, Ms = c->h_lmm->Ms;
-  Qc = c->h_lmm->Qc; Qs = c->h_lmm->Qs;
-  if (c->h_lmm->overflow) { snprintf(c->err, sizeof c->err, "map pool exhausted"); return VLOAM_E_CAPACITY; }
-  // Pool head room for this frame's update: a cube that outgrows its segment gets a new one of twice its new size,
-  // so the update allocates at most 2 x (points in the map + inserts) + 256 per touched cube.  When that no longer
-  // fits, the pool is doubled (copy) now: the previous update is complete (this stream waited on evMap), the next
-  // one has not been issued, and the copy keeps every cube's offset valid.
-  {
-    const size_t needC = 2 * ((size_t)c->h_lmm->totalC + Qc) + 256 * (size_t)(VL_MAX_VALID + min(Qc, VL_CUBE_NUM));
-    const size_t needS = 2 * ((size_t)c->h_lmm->totalS + Qs) + 256 * (size_t)(VL_MAX_VALID + min(Qs, VL_CUBE_NUM));
-    if ((size_t)c->h_lmm->poolTopC + needC > c->poolC.cap) VL_TRY(vl_reserve(c, c->poolC, 2 * ((size_t)c->h_lmm->poolTopC + needC), true));
-    if ((size_t)c->h_lmm->poolTopS + needS > c->poolS.cap) VL_TRY(vl_reserve(c, c->poolS, 2 * ((size_t)c->h_lmm->poolTopS + needS), true));
-  }
+  const int Qc = c->h_lmm->Qc, Qs = c->h_lmm->Qs;
+  // the previous update is complete (this stream waited on evMap), the next one has not been issued, and a pool copy keeps every cube's offset valid
+  VL_TRY(lm_pool_headroom(c, c->h_lmm->totalC, c->h_lmm->totalS, Qc, Qs));
   const int tailTotal = c->h_lmm->tailC + c->h_lmm->tailS;
   const int nq = Qc + Qs;
   c->lm_optimized = c->h_lmm->optimized;
   const long long totalC = c->h_lmm->totalC, totalS = c->h_lmm->totalS;
   const float4* const stackCp = c->stackC.p; const float4* const stackSp = c->stackS.p;  // (the next frame may swap the buffers while the helper issues this)
   const int stackSelNow = c->stackSel;
+  const bool rebuildAfter = d->gridEnabled && !capture;
+  d->gridValid = false;
   auto update = [=]() -> int {
   vl_tls_stream = c->stream3;  // every launch helper below issues on the update's stream, whichever thread runs this
   struct Restore { ~Restore() { vl_tls_stream = nullptr; } } restore;
   VL_CUDA(cudaStreamWaitEvent(c->stream3, c->evPose, 0));
-  const bool spec = d->specEnabled && !capture;
-  auto zeroSpecGrid = [&]() -> int {  // (issued after the update's first kernel: that one heads the critical chain)
-  if (spec) {  // the cell counters of the speculative grid are zeroed beside the update, not behind it
-    VL_CUDA(cudaStreamWaitEvent(c->streamAux, c->evPose, 0));
-    vl_tls_stream = c->streamAux;
-    VL_BYTES(8.0 * (2 * LM_NCELL + 1));
-    VL_LAUNCH(lm_grid_zero, gsGrid, 256, 0, d->cellCount, d->cellFill, 2 * LM_NCELL + 1, (const int*)nullptr);
-    vl_tls_stream = c->stream3;
-    VL_CUDA(cudaEventRecord(c->evAuxZero, c->streamAux));
-  }
-  return VLOAM_OK;
-  };
   const int nKeys = tailTotal + nq;
-  if (nKeys == 0) VL_TRY(zeroSpecGrid());
   if (nKeys > 0) {
     const size_t N = ((size_t)nKeys + 255) & ~(size_t)255;
     VL_TRY(vl_reserve(c, c->tailKeys, 4 * N, false, 4 * N));  // [0, N) unsorted keys | [N, 2N) bucketed + sorted | [2N, 4N) scratch for oversize segments
@@ -1644,10 +1917,9 @@ int vl_lm_run(vloam_b200_ctx* c) {
     VL_TRY(vl_reserve(c, d->unmatched, (size_t)nKeys + 2, false, (size_t)nKeys + (1 << 16)));
     VL_TRY(vl_reserve(c, c->staging, (size_t)Mc + Ms + nKeys + 1, false, (size_t)(Mc + Ms) / 2 + (1 << 20)));
     VL_LAUNCH(rf_keys, vl_div_up(nKeys, 256), 256, 0, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, stackCp, stackSp,
-              d->newPts.p, d->newCube.p, keysIn, nKeys);
+              d->newPts.p, d->newCube.p, keysIn, nKeys, 0);
     VL_CUDA(cudaEventRecord(c->evKeys, c->stream3));  // nothing below reads the stacks any more: the next sweep's filters may overwrite them
     VL_CUDA(cudaEventRecord(c->evKeysSel[stackSelNow], c->stream3));
-    VL_TRY(zeroSpecGrid());
     VL_LAUNCH(rf_seg_scatter, vl_div_up(nKeys, 256), 256, 0, keysIn, nKeys, d->work, keysSorted);
     VL_BYTES(16.0 * nKeys);
     static const int segCap = getenv("VLOAM_SEG_CAP") ? max(8, min(atoi(getenv("VLOAM_SEG_CAP")), RF_SEG_CAP)) : RF_SEG_CAP;  // tests force the global path
@@ -1662,8 +1934,8 @@ int vl_lm_run(vloam_b200_ctx* c) {
     VL_LAUNCH(rf_commit, gsGrid, 256, 0, c->staging.p, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p);
     VL_LAUNCH(rf_finish, 1, 256, 0, c->lmm, d->work, c->cubeC, c->cubeS);
     if (nq > 0) {
-      // Points that fell outside the 5x5x3 window go to cubes the speculative sub-map never reads: this single-CTA
-      // kernel (~20 us) runs beside the sub-map build; the next solveMapping waits on both (evMap, evAux).
+      // Points that fell outside the 5x5x3 window go to cubes the sub-map never reads: this single-CTA
+      // kernel (~20 us) runs beside the grid rebuild; the next solveMapping waits on both (evMap, evAux).
       VL_CUDA(cudaEventRecord(c->evUpd, c->stream3));
       VL_CUDA(cudaStreamWaitEvent(c->streamAux, c->evUpd, 0));
       vl_tls_stream = c->streamAux;
@@ -1675,38 +1947,20 @@ int vl_lm_run(vloam_b200_ctx* c) {
   VL_CUDA(cudaEventRecord(c->evAux, c->streamAux));
   // the map after this frame's update holds at most the points it held before plus this frame's inserts
   d->hMapUpperC = totalC + Qc; d->hMapUpperS = totalS + Qs;
-  // ---- speculative sub-map of the NEXT frame.  Gathering the 75 valid cubes and cell-sorting ~1M points is
-  // ~80 us of dependent kernels that only depend on the pose through the window centre, and the window moves
-  // once per 50 m.  So the work is done here, behind the map update on its side stream (underneath the next
-  // sweep's scan registration and odometry), for the window this frame used; the next lm_prepare checks the
-  // window and lets the in-line build run only when it moved.  Debug snapshots read this frame's sub-map
-  // after the call returns, so capture mode keeps the in-line build.
-  d->specQueued = false;
-  if (spec) {
-    const long long tb = d->hMapUpperC + d->hMapUpperS;
-    VL_TRY(vl_reserve(c, c->fromMapC, (size_t)max(d->hMapUpperC, 1LL), false, (size_t)d->hMapUpperC / 2 + (1 << 20)));
-    VL_TRY(vl_reserve(c, c->fromMapS, (size_t)max(d->hMapUpperS, 1LL), false, (size_t)d->hMapUpperS / 2 + (1 << 20)));
-    VL_TRY(vl_reserve(c, d->cellOfPoint, (size_t)max(tb, 1LL), false, (size_t)tb / 2 + (1 << 20)));
-    VL_TRY(vl_reserve(c, d->sortedPts, (size_t)max(tb, 1LL), false, (size_t)tb / 2 + (1 << 20)));
+  // ---- the grid of the NEXT sweep: rebuilt here, behind the update on its side stream, for the window this sweep used (a cube
+  // is 50 m wide, so the next sweep almost always uses the same one and runs the in-place path; lm_prepare_fast checks).
+  // Debug snapshots keep the pool path every sweep.
+  if (rebuildAfter) {
     VL_LAUNCH(lm_spec_prepare, 1, 256, 0, d->subReal, c->cubeC, c->cubeS, d->subSpec);
-    VL_CUDA(cudaStreamWaitEvent(c->stream3, c->evAuxZero, 0));  // the cell counters were zeroed on streamAux
-    VL_BYTES(56.0 * (double)tb);
-    VL_LAUNCH(lm_gather_count, gsGrid, 256, 0, d->subSpec, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, c->fromMapC.p, c->fromMapS.p, d->cellCount,
-              d->cellOfPoint.p);
-    VL_TRY(vl_scan_exclusive(c, d->cellCount, 2 * LM_NCELL, &d->scan, d->cellStart, nullptr));
-    VL_BYTES(44.0 * (double)tb);
-    VL_LAUNCH(lm_grid_fill, gsGrid, 256, 0, d->subSpec, (const int*)nullptr, c->fromMapC.p, c->fromMapS.p, d->cellOfPoint.p, d->cellStart, d->cellFill,
-              d->sortedPts.p);
-    d->specQueued = true;
+    VL_TRY(lg_rebuild_launch(c, d, d->subSpec, d->hMapUpperC + d->hMapUpperS));
+    d->gridValid = true;
   }
   VL_CUDA(cudaEventRecord(c->evMap, c->stream3));
   return VLOAM_OK;
   };
   c->lm_frameCount++;
-  // profiling and debug snapshots serialise everything; otherwise the helper thread issues the update while
-  // the caller returns with its pose (whoever needs the map next joins it first: vl_lm_join)
-  static const bool noWorker = getenv("VLOAM_NO_WORKER") != nullptr;
-  if (noWorker || capture || c->prof_name[0]) { const int rmap = update(); if (rmap != VLOAM_OK) return rmap; }
+  // otherwise the helper thread issues the update while the caller returns with its pose (whoever needs the map next joins it first: vl_lm_join)
+  if (inlineUpdate) { const int rmap = update(); if (rmap != VLOAM_OK) return rmap; }
   else VL_TRY(lm_submit(c, update));
   VL_HOST_MARK(7);
   VL_CUDA(cudaGetLastError());
@@ -1737,7 +1991,7 @@ int vl_lm_register_full(vloam_b200_ctx* c, const float4* d_in, int n, float4* d_
 }
 
 int vl_lm_rescan_sorted(vloam_b200_ctx* c) {
-  lmdev(c)->specQueued = false;  // the state behind the speculative sub-map was edited from outside
+  lmdev(c)->gridValid = false;  // the state behind the grid was edited from outside
   VL_LAUNCH(lm_scan_sorted, VL_CUBE_NUM, 256, 0, c->lmm, c->prm, c->cubeC, c->poolC.p, 0);
   VL_LAUNCH(lm_scan_sorted, VL_CUBE_NUM, 256, 0, c->lmm, c->prm, c->cubeS, c->poolS.p, 1);
   VL_CUDA(cudaStreamSynchronize(c->stream));
@@ -1746,6 +2000,7 @@ int vl_lm_rescan_sorted(vloam_b200_ctx* c) {
 
 // blob = int32 counts[4851] followed by the points of all cubes in cube-index order
 int vl_lm_export_map(vloam_b200_ctx* c, int which, void* out, long cap, long* bytes) {
+  VL_TRY(vl_lm_sync_pools(c));  // in-place grid updates leave the valid cubes' pools behind: write them back first
   MapCubeTable h;
   VL_CUDA(cudaStreamSynchronize(c->stream));
   VL_CUDA(cudaMemcpy(&h, which ? c->cubeS : c->cubeC, sizeof h, cudaMemcpyDeviceToHost));
@@ -1766,7 +2021,7 @@ int vl_lm_export_map(vloam_b200_ctx* c, int which, void* out, long cap, long* by
 
 int vl_lm_import_map(vloam_b200_ctx* c, int which, const void* data, long bytes) {
   LmDevice* d = lmdev(c);
-  d->specQueued = false;  // the map behind the speculative sub-map is replaced
+  d->gridValid = false;  // the map behind the grid is replaced
   if (bytes < (long)VL_CUBE_NUM * 4) { snprintf(c->err, sizeof c->err, "map blob too short"); return VLOAM_E_INVALID; }
   const int* counts = (const int*)data;
   long long total = 0;
@@ -1806,13 +2061,12 @@ int vl_lm_preload(vloam_b200_ctx* c) {  // see vl_sr_set_attrs: load every kerne
   cudaFuncAttributes fa_;
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_prepare));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_spec_prepare));
-  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_grid_zero));
-  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_gather_count));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_scan_chained));
-  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_grid_fill));
-  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_inline_build));
-  VL_CUDA(cudaFuncGetAttributes(&fa_, lm_knn));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_fit));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lg_zero)); VL_CUDA(cudaFuncGetAttributes(&fa_, lg_rebuild)); VL_CUDA(cudaFuncGetAttributes(&fa_, lm_prepare_fast));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lg_knn)); VL_CUDA(cudaFuncGetAttributes(&fa_, lg_keys_to_ids)); VL_CUDA(cudaFuncGetAttributes(&fa_, lm_gather));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, mu_apply)); VL_CUDA(cudaFuncGetAttributes(&fa_, mu_insert)); VL_CUDA(cudaFuncGetAttributes(&fa_, mz_collect));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, mz_layout_for_grid));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_fit_sets));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_transform_update));
   VL_CUDA(cudaFuncGetAttributes(&fa_, rf_keys));

@@ -539,8 +539,8 @@ static int lo_associate(vloam_b200_ctx* c, const double* d_pose, const float4* c
   const int nS = c->sr_counts_valid ? c->nSharp : lo_sharp_bound(c), nF = c->sr_counts_valid ? c->nFlat : lo_flat_bound(c);
   VL_TRY(vl_reserve(c, c->loCornerIdx, (size_t)max(nS, 1) * 2));
   VL_TRY(vl_reserve(c, c->loSurfIdx, (size_t)max(nF, 1) * 3));
-  VL_TRY(vl_reserve(c, c->factors, (size_t)max(nS + nF, 1) * 10));
-  VL_TRY(vl_reserve(c, c->factorValid, (size_t)max(nS + nF, 1)));
+  VL_TRY(vl_reserve(c, c->loFactors, (size_t)max(nS + nF, 1) * 10));
+  VL_TRY(vl_reserve(c, c->loFactorValid, (size_t)max(nS + nF, 1)));
   if (vl_distortion(c)) VL_TRY(vl_reserve(c, c->factorS, (size_t)max(nS + nF, 1)));
   double* fS = vl_distortion(c) ? c->factorS.p : nullptr;
   // h_vScalars[8/9]: int(intensity) of the corner / surf cloud is non-decreasing (read after a sync point)
@@ -553,26 +553,26 @@ static int lo_associate(vloam_b200_ctx* c, const double* d_pose, const float4* c
   if (gridC && gridS && nS + nF > 0) {
     VL_BYTES(16.0 * ((double)c->nSharp + c->nFlat + nCL + nSL));  // SURVEY 8(d) B_lo, one pass: every query and every point of the two last clouds once
     VL_LAUNCH(lo_assoc_grid_both, vl_div_up((long long)(nS + nF) * 32, 256), 256, 0, c->sharp.p, c->flat.p, nS + nF, c->srs, cornerLast, surfLast,
-              gsorted, start, d_pose, c->loCornerIdx.p, c->loSurfIdx.p, c->factors.p, c->factorValid.p, fS);
+              gsorted, start, d_pose, c->loCornerIdx.p, c->loSurfIdx.p, c->loFactors.p, c->loFactorValid.p, fS);
     VL_CUDA(cudaGetLastError());
     return VLOAM_OK;
   }
   if (nS > 0) {
     if (gridC)
       VL_LAUNCH(lo_assoc_grid<false>, vl_div_up((long long)nS * 32, 256), 256, 0, c->sharp.p, nS, cornerLast, gsorted, start, d_pose,
-                c->loCornerIdx.p, c->factors.p, c->factorValid.p, 0, fS);
+                c->loCornerIdx.p, c->loFactors.p, c->loFactorValid.p, 0, fS);
     else
       VL_LAUNCH(lo_assoc<false>, vl_div_up(nS, LO_QPB), LO_QPB * 32, 0, c->sharp.p, nS, cornerLast, nCL, d_pose, rtbl, c->loCornerIdx.p,
-                c->factors.p, c->factorValid.p, 0, fS);
+                c->loFactors.p, c->loFactorValid.p, 0, fS);
   }
   if (nF > 0) {
     if (gridS) {
       VL_BYTES(16.0 * ((double)nF + nSL));
       VL_LAUNCH(lo_assoc_grid<true>, vl_div_up((long long)nF * 32, 256), 256, 0, c->flat.p, nF, surfLast, gsorted, start, d_pose,
-                c->loSurfIdx.p, c->factors.p, c->factorValid.p, nS, fS);
+                c->loSurfIdx.p, c->loFactors.p, c->loFactorValid.p, nS, fS);
     } else
       VL_LAUNCH(lo_assoc<true>, vl_div_up(nF, LO_QPB), LO_QPB * 32, 0, c->flat.p, nF, surfLast, nSL, d_pose, rtbl + (LO_TBL + 1), c->loSurfIdx.p,
-                c->factors.p, c->factorValid.p, nS, fS);
+                c->loFactors.p, c->loFactorValid.p, nS, fS);
   }
   VL_CUDA(cudaGetLastError());
   return VLOAM_OK;
@@ -613,8 +613,8 @@ static int lo_queue_solve(vloam_b200_ctx* c, const double* prior_q, const double
     double* d_prior = reinterpret_cast<double*>(c->vScalars + 32);  // 8-byte aligned scratch (7 doubles)
     if (use_prior) {
       double h[7] = {prior_q[0], prior_q[1], prior_q[2], prior_q[3], prior_t[0], prior_t[1], prior_t[2]};
-      VL_CUDA(cudaMemcpyAsync(d_prior, h, sizeof h, cudaMemcpyHostToDevice, c->stream));
-      VL_CUDA(cudaStreamSynchronize(c->stream));  // h is a stack buffer
+      VL_CUDA(cudaMemcpyAsync(d_prior, h, sizeof h, cudaMemcpyHostToDevice, VL_STREAM(c)));
+      VL_CUDA(cudaStreamSynchronize(VL_STREAM(c)));  // h is a stack buffer
     }
     for (int pass = 0; pass < 2; ++pass) {  // LO.cpp:224
       if (use_prior) VL_LAUNCH(lo_set_prior, 1, 32, 0, c->los, d_prior);
@@ -622,15 +622,15 @@ static int lo_queue_solve(vloam_b200_ctx* c, const double* prior_q, const double
       if (vl_debug_capture(c)) {
         VL_TRY(vl_reserve(c, c->dbgLoCorner[pass], (size_t)max(c->nSharp, 1) * 2));
         VL_TRY(vl_reserve(c, c->dbgLoSurf[pass], (size_t)max(c->nFlat, 1) * 3));
-        VL_CUDA(cudaMemcpyAsync(c->dbgLoCorner[pass].p, c->loCornerIdx.p, sizeof(int) * 2 * c->nSharp, cudaMemcpyDeviceToDevice, c->stream));
-        VL_CUDA(cudaMemcpyAsync(c->dbgLoSurf[pass].p, c->loSurfIdx.p, sizeof(int) * 3 * c->nFlat, cudaMemcpyDeviceToDevice, c->stream));
+        VL_CUDA(cudaMemcpyAsync(c->dbgLoCorner[pass].p, c->loCornerIdx.p, sizeof(int) * 2 * c->nSharp, cudaMemcpyDeviceToDevice, VL_STREAM(c)));
+        VL_CUDA(cudaMemcpyAsync(c->dbgLoSurf[pass].p, c->loSurfIdx.p, sizeof(int) * 3 * c->nFlat, cudaMemcpyDeviceToDevice, VL_STREAM(c)));
       }
       const int nslots = c->sr_counts_valid ? c->nSharp + c->nFlat : lo_sharp_bound(c) + lo_flat_bound(c);
-      VL_TRY(vl_solve(c, nslots, &c->srs->nQueries, d_pose, vl_debug_capture(c) ? &c->dbgLoCost[pass * 2] : nullptr, c->nSharp + c->nFlat,
-                      vl_distortion(c) ? c->factorS.p : nullptr));
+      VL_TRY(vl_solve_buf(c, c->loFactors.p, c->loFactorValid.p, nslots, &c->srs->nQueries, d_pose, vl_debug_capture(c) ? &c->dbgLoCost[pass * 2] : nullptr,
+                          c->nSharp + c->nFlat, vl_distortion(c) ? c->factorS.p : nullptr));
     }
     VL_LAUNCH(lo_accumulate, 1, 32, 0, c->los);
-  VL_CUDA(cudaEventRecord(c->evLoSolve, c->stream));
+  VL_CUDA(cudaEventRecord(c->evLoSolve, VL_STREAM(c)));
   return VLOAM_OK;
 }
 
@@ -649,14 +649,20 @@ int vl_lo_lookahead(vloam_b200_ctx* c) {
   // The flags are checked when the result is adopted; a wrong guess only discards the look-ahead.
   const int set = c->lastSet;
   if (!c->loGridValid[set]) return VLOAM_OK;
-  VL_CUDA(cudaStreamWaitEvent(c->stream, c->evLast, 0));
-  VL_CUDA(cudaStreamWaitEvent(c->stream, c->srNext->evSR, 0));
-  VL_CUDA(cudaMemcpyAsync(c->losNext, c->los, sizeof(LoScalars), cudaMemcpyDeviceToDevice, c->stream));
+  // It runs on its own stream, BESIDE this sweep's mapping (own factor slots): it needs this sweep's odometry result (evLoSolve),
+  // the structures over this sweep's clouds (evLast) and the next sweep's features (evSR) -- nothing of the mapping.
+  VL_CUDA(cudaStreamWaitEvent(c->streamLO, c->evLoSolve, 0));
+  VL_CUDA(cudaStreamWaitEvent(c->streamLO, c->evLast, 0));
+  VL_CUDA(cudaStreamWaitEvent(c->streamLO, c->srNext->evSR, 0));
+  VL_CUDA(cudaMemcpyAsync(c->losNext, c->los, sizeof(LoScalars), cudaMemcpyDeviceToDevice, c->streamLO));
   const int curNow = c->cur;
   vl_sr_swap(c, *c->srNext);
   { LoScalars* t_ = c->los; c->los = c->losNext; c->losNext = t_; }
   c->loAssumeMonotone = true;
+  vl_tls_stream = c->streamLO;
   int r = lo_queue_solve(c, nullptr, nullptr, 0);  // (host counts of that sweep not known yet: bounds, the kernels read the counts on the device)
+  vl_tls_stream = nullptr;
+  if (r == VLOAM_OK && cudaEventRecord(c->evLoNext, c->streamLO) != cudaSuccess) r = VLOAM_E_CUDA;
   c->loAssumeMonotone = false;
   { LoScalars* t_ = c->los; c->los = c->losNext; c->losNext = t_; }
   // The host only waits for S2 from here on.  If the look-ahead scan registration finishes before this sweep's mapping
@@ -702,6 +708,7 @@ int vl_lo_flush_deferred(vloam_b200_ctx* c) {
 
 int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, int use_prior) {
   VL_TRY(vl_lo_flush_deferred(c));
+  VL_CUDA(cudaStreamWaitEvent(c->stream, c->evLoNext, 0));  // a look-ahead solve (adopted below, or stale) owns the odometry's factor slots until it is done
   VL_CUDA(cudaEventSynchronize(c->evLast));  // set [lastSet] (built underneath the previous frame) and its flags are complete
   // The grid kernels read the query counts on the device, so the odometry can be queued before the host
   // has them (sync point S1 then costs no GPU idle time).  The ballot fallback and the debug snapshots

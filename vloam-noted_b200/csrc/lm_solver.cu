@@ -687,9 +687,15 @@ int vl_solver_set_attrs(vloam_b200_ctx* c) {
 }
 
 int vl_solve(vloam_b200_ctx* c, int nslots, const int* d_nslots, double* d_x_inout, double* costs2, int hint, const double* d_s) {
+  return vl_solve_buf(c, c->factors.p, c->factorValid.p, nslots, d_nslots, d_x_inout, costs2, hint, d_s);
+}
+
+int vl_solve_buf(vloam_b200_ctx* c, const double* cf, const int* cv, int nslots, const int* d_nslots, double* d_x_inout, double* costs2, int hint,
+                 const double* d_s) {
+  cudaStream_t st = VL_STREAM(c);
   if (nslots > 0) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(LMC_CTAS); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+    cfg.gridDim = dim3(LMC_CTAS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
     cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = LMC_CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -697,8 +703,8 @@ int vl_solve(vloam_b200_ctx* c, int nslots, const int* d_nslots, double* d_x_ino
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 2;
     const bool prof = c->prof_name[0] && vl_prof_match(c, "lm_solve_cluster") && c->prof_n < VL_PROF_MAX;
-    if (prof) cudaEventRecord(c->prof_ev[c->prof_n][0], c->stream);
-    const double* cf = c->factors.p; const int* cv = c->factorValid.p; LmSolveState* so = costs2 ? c->lms : nullptr;
+    if (prof) cudaEventRecord(c->prof_ev[c->prof_n][0], st);
+    LmSolveState* so = costs2 ? c->lms : nullptr;
     long long* tr = g_solver_trace;
     // nslots is a host BOUND (buffer capacity when the count still lives on the device); `hint` is the last known
     // actual count.  The variant only decides how many slots a thread can keep in registers: a solve whose
@@ -710,14 +716,14 @@ int vl_solve(vloam_b200_ctx* c, int nslots, const int* d_nslots, double* d_x_ino
     else if (est <= LMC_CTAS * 1024) VL_CUDA((lm_launch<4, 256>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr)));
     else VL_CUDA((lm_launch<0, 256>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr)));
     // algorithmic bytes: the factor slots (80 B + flag) are read once; the 5 evaluations run from registers
-    if (prof) { cudaEventRecord(c->prof_ev[c->prof_n][1], c->stream); c->prof_kname[c->prof_n] = "lm_solve_cluster"; c->prof_kbytes[c->prof_n] = 84.0 * nslots; c->prof_kstream[c->prof_n] = c->stream;
-                c->prof_n++; c->prof_bytes += 84.0 * nslots; }
+    if (prof) { cudaEventRecord(c->prof_ev[c->prof_n][1], st); c->prof_kname[c->prof_n] = "lm_solve_cluster"; c->prof_kbytes[c->prof_n] = 84.0 * min(nslots, max(hint, 1)); c->prof_kstream[c->prof_n] = st;
+                c->prof_n++; c->prof_bytes += 84.0 * min(nslots, max(hint, 1)); }
     __atomic_fetch_add(&c->launches, 1LL, __ATOMIC_RELAXED);
   }
   if (costs2) {
     if (nslots > 0) {
-      VL_CUDA(cudaMemcpyAsync(c->h_lms, c->lms, sizeof(LmSolveState), cudaMemcpyDeviceToHost, c->stream));
-      VL_CUDA(cudaStreamSynchronize(c->stream));
+      VL_CUDA(cudaMemcpyAsync(c->h_lms, c->lms, sizeof(LmSolveState), cudaMemcpyDeviceToHost, st));
+      VL_CUDA(cudaStreamSynchronize(st));
       costs2[0] = c->h_lms->initial_cost; costs2[1] = c->h_lms->final_cost;
     } else { costs2[0] = costs2[1] = 0; }
   }
