@@ -48,6 +48,10 @@ print("stage ms mean   SR/LO/LM:", rows.mean(0).round(3))
 dm = np.median(np.array(detail)[8:], 0)
 print("ms since frame start (median): SR end %.3f | LO end %.3f | sub-map build end %.3f | stacks awaited %.3f | solve 1 end %.3f | LM end %.3f" % (dm[0], dm[1], dm[3], dm[4], dm[5], dm[2]))
 print("   side streams: surf stack ready %.3f | corner stack ready %.3f | next LO grid ready %.3f" % (dm[6], dm[7], dm[8]))
+if len(dm) >= 14:
+    print("   next sweep: sharp/flat features ready %.3f | scan registration complete %.3f | look-ahead odometry starts %.3f" % (dm[11], dm[13], dm[12]))
+if len(dm) >= 11:
+    print("   look-ahead odometry of the next sweep done %.3f | in-place map update done %.3f  (ms since this sweep's start; events of the PREVIOUS sweep when negative or > 1)" % (dm[9], dm[10]))
 if LOOKAHEAD:
     hm = np.median(np.array(host)[8:], 0)
     print("host clock inside process_frame, us (median): SR adopted %.0f | odometry + look-ahead queued %.0f | S1 + side streams queued %.0f | helper joined %.0f | mapping queued %.0f | S2 passed %.0f | update submitted %.0f" % tuple(hm))

@@ -30,6 +30,7 @@ const char* vloam_b200_last_error(const vloam_b200_ctx* c) { return c ? c->err :
 static int alloc_sr_fixed(vloam_b200_ctx* c) {
   const int R = VL_MAX_RINGS, S = VL_MAX_RINGS * VL_SECTORS;
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evSR, cudaEventDisableTiming));
+  VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evSRfeat, cudaEventDisableTiming));
   VL_CUDA_CREATE(cudaMalloc(&c->ringCount, sizeof(int) * R));
   VL_CUDA_CREATE(cudaMalloc(&c->ringStart, sizeof(int) * (R + 1)));
   VL_CUDA_CREATE(cudaMemset(c->ringCount, 0, sizeof(int) * R));
@@ -52,9 +53,10 @@ static void free_sr_set(vloam_b200_ctx* c) {  // the set currently swapped into 
   void* dev[] = {c->ringCount, c->ringStart, c->srs, c->provSharp, c->provLess, c->provFlat, c->cntSharp, c->cntLess, c->cntFlat, c->offSharp,
                  c->offLess, c->offFlat, c->ringDsCount, c->ringDsOff, c->in.p, c->ring.p, c->ori.p, c->blockHist.p, c->cloud.p, c->curv.p,
                  c->label.p, c->picked.p, c->sortScratch.p, c->lessFlatProv.p, c->selIdx.p, c->sharp.p, c->flat.p};
-  for (void* p : dev) if (p) cudaFree(p);
+  for (void* p : dev) vl_dev_free(c, p);
   if (c->h_srs) cudaFreeHost(c->h_srs);
   if (c->evSR) cudaEventDestroy(c->evSR);
+  if (c->evSRfeat) cudaEventDestroy(c->evSRfeat);
 }
 
 static int create_impl(vloam_b200_ctx* c, const vloam_b200_params* p, int device);
@@ -82,6 +84,12 @@ static int create_impl(vloam_b200_ctx* c, const vloam_b200_params* p, int device
   for (int k = 0; k < 4; ++k) c->dbgLoCost[k] = c->dbgLmCost[k] = 0;
   for (int k = 0; k < 3; ++k) c->stage_ms[k] = 0;
   c->prof_name[0] = 0; c->prof_n = 0; c->prof_created = 0; c->prof_bytes = 0; c->prof_next_bytes = 0;
+  {  // the arena behind vl_reserve (common.cuh); VLOAM_ARENA_MB = 0 turns it off (every buffer its own cudaMalloc)
+    const char* e = getenv("VLOAM_ARENA_MB");
+    const size_t mb = e ? (size_t)max(atoll(e), 0LL) : 1024;
+    c->arena = nullptr; c->arenaCap = 0; c->arenaTop = 0;
+    if (mb) { VL_CUDA_CREATE(cudaMalloc(&c->arena, mb << 20)); c->arenaCap = mb << 20; }
+  }
   cudaDeviceProp prop;
   VL_CUDA_CREATE(cudaGetDeviceProperties(&prop, device));
   c->num_sms = prop.multiProcessorCount;
@@ -91,11 +99,15 @@ static int create_impl(vloam_b200_ctx* c, const vloam_b200_params* p, int device
   // VLOAM_NO_PRIORITIES=1: all streams at the default priority.
   int prLow = 0, prHigh = 0;
   VL_CUDA_CREATE(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
-  int lv[4] = {2, 1, 0, 0};  // levels above the lowest priority: main | stack filters | map update | look-ahead scan registration
-  if (const char* e = getenv("VLOAM_PRIO")) sscanf(e, "%d,%d,%d,%d", &lv[0], &lv[1], &lv[2], &lv[3]);
-  if (getenv("VLOAM_NO_PRIORITIES")) lv[0] = lv[1] = lv[2] = lv[3] = 0;
-  int pr[4];
+  // (round 2: the in-place map update is ~3 short kernels the NEXT sweep's mapping waits for directly: it runs at the pose chain's priority)
+  // ... and so does the look-ahead scan registration: the NEXT sweep's odometry (own stream, beside this sweep's mapping) starts when it is done
+  int lv[4] = {2, 1, 2, 2};  // levels above the lowest priority: main | stack filters | map update | look-ahead scan registration
+  int lvLO = 2;                // the look-ahead odometry stream
+  if (const char* e = getenv("VLOAM_PRIO")) sscanf(e, "%d,%d,%d,%d,%d", &lv[0], &lv[1], &lv[2], &lv[3], &lvLO);
+  if (getenv("VLOAM_NO_PRIORITIES")) lv[0] = lv[1] = lv[2] = lv[3] = lvLO = 0;
+  int pr[5];
   for (int k = 0; k < 4; ++k) pr[k] = max(prLow - lv[k], prHigh);  // (numerically lower = more urgent)
+  pr[4] = max(prLow - lvLO, prHigh);
   VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, pr[0]));
   VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, pr[1]));
   VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, pr[2]));
@@ -113,7 +125,7 @@ static int create_impl(vloam_b200_ctx* c, const vloam_b200_params* p, int device
   for (int k = 0; k < 2; ++k) VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evKeysSel[k], cudaEventDisableTiming));
   c->stacksReady = false; c->lm_reset_pending = true; c->lastSet = 0; c->loGridValid[0] = c->loGridValid[1] = false;
   for (int k = 0; k < 4; ++k) VL_CUDA_CREATE(cudaEventCreate(&c->ev[k]));
-  for (int k = 0; k < 8; ++k) { VL_CUDA_CREATE(cudaEventCreate(&c->evx[k])); VL_CUDA_CREATE(cudaEventRecord(c->evx[k], c->stream)); }
+  for (int k = 0; k < 12; ++k) { VL_CUDA_CREATE(cudaEventCreate(&c->evx[k])); VL_CUDA_CREATE(cudaEventRecord(c->evx[k], c->stream)); }
   VL_TRY(alloc_sr_fixed(c));
   c->srNext = new SrSet();
   vl_sr_swap(c, *c->srNext);      // the spare set gets its own fixed-size arrays, counters and event
@@ -125,8 +137,8 @@ static int create_impl(vloam_b200_ctx* c, const vloam_b200_params* p, int device
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evS2, cudaEventDisableTiming));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evLoSolve, cudaEventDisableTiming));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evLoNext, cudaEventDisableTiming));
-  VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->streamLO, cudaStreamNonBlocking, pr[0]));
-  c->loNextValid = c->srAdopted = c->s2Done = false; c->loAssumeMonotone = c->inProcessFrame = c->loDeferred = false; c->loNextSet = 0; c->stackSel = 0; c->stacksNextReady = false;
+  VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->streamLO, cudaStreamNonBlocking, pr[4]));
+  c->loNextValid = c->loNextQueued = c->srAdopted = c->s2Done = false; c->loAssumeMonotone = c->inProcessFrame = c->loDeferred = false; c->srDeferred = c->sideSubmitted = false; c->loNextSet = 0; c->stackSel = 0; c->stacksNextReady = false;
   VL_CUDA_CREATE(cudaMallocHost(&c->h_los, sizeof(LoScalars)));
   LoScalars hl; memset(&hl, 0, sizeof hl); hl.para_q[3] = 1.0; hl.q_w[3] = 1.0;  // LO.cpp:81-91
   VL_CUDA_CREATE(cudaMemcpy(c->los, &hl, sizeof hl, cudaMemcpyHostToDevice));
@@ -177,20 +189,21 @@ void vloam_b200_destroy(vloam_b200_ctx* c) {
                      c->dbgLoSurf[1].p, c->dbgKnnIdx[0][0].p, c->dbgKnnIdx[0][1].p, c->dbgKnnIdx[1][0].p, c->dbgKnnIdx[1][1].p, c->dbgKnnD2[0][0].p,
                      c->dbgKnnD2[0][1].p, c->dbgKnnD2[1][0].p, c->dbgKnnD2[1][1].p, c->dbgKnnOk[0][0].p, c->dbgKnnOk[0][1].p, c->dbgKnnOk[1][0].p,
                      c->dbgKnnOk[1][1].p};
-  for (void* p : singles) if (p) cudaFree(p);
+  for (void* p : singles) vl_dev_free(c, p);
   void* bufs[] = {c->lessSharp[0].p, c->lessSharp[1].p, c->lessSharp[2].p, c->lessFlat[0].p, c->lessFlat[1].p, c->lessFlat[2].p, c->loCornerIdx.p, c->loSurfIdx.p, c->factors.p, c->factorS.p, c->factorValid.p, c->loFactors.p, c->loFactorValid.p, c->evalPartials.p,
                   c->poolC.p, c->poolS.p, c->stackC.p, c->stackS.p, c->stackCN.p, c->stackSN.p, c->fromMapC.p, c->fromMapS.p, c->knnIdx.p, c->knnD2.p, c->knnOk.p,
                   c->vKeys.p, c->vKeys2.p, c->vHead.p, c->vScan.p, c->vScan2.p, c->vOut.p, c->vIn.p, c->regOut.p, c->tailKeys.p, c->staging.p};
-  for (void* p : bufs) if (p) cudaFree(p);
+  for (void* p : bufs) vl_dev_free(c, p);
   cudaFreeHost(c->h_los); cudaFreeHost(c->h_lms); cudaFreeHost(c->h_lmm); cudaFreeHost(c->h_vScalars);
   for (int k = 0; k < 4; ++k) cudaEventDestroy(c->ev[k]);
-  for (int k = 0; k < 8; ++k) cudaEventDestroy(c->evx[k]);
+  for (int k = 0; k < 12; ++k) cudaEventDestroy(c->evx[k]);
   cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream3);
   cudaEventDestroy(c->evStacks); cudaEventDestroy(c->evLast); cudaEventDestroy(c->evPose); cudaEventDestroy(c->evMap); cudaEventDestroy(c->evKeys); cudaEventDestroy(c->evKeysSel[0]); cudaEventDestroy(c->evKeysSel[1]);
   cudaEventDestroy(c->evStacksC);
   cudaStreamSynchronize(c->streamAux); cudaEventDestroy(c->evAux); cudaEventDestroy(c->evAuxZero); cudaEventDestroy(c->evUpd); cudaStreamDestroy(c->streamAux);
   cudaStreamDestroy(c->stream2); cudaStreamDestroy(c->stream3); cudaStreamDestroy(c->stream4);
   cudaStreamDestroy(c->stream);
+  if (c->arena) cudaFree(c->arena);
   delete c;
 }
 
@@ -546,10 +559,12 @@ long vloam_b200_debug_get(vloam_b200_ctx* c, const char* name, void* out, long c
   }
   if (n == "timing.detail") {  // timing mode: ms since the start of the frame's scan registration
     // {SR end, LO end, LM end, sub-map build end, stacks awaited + counts set, first solve end, surf stack ready, corner stack ready, next LO grid ready}
-    float v[9] = {0};
+    // ..., look-ahead odometry of the NEXT sweep finished (streamLO), map update of this sweep finished (stream3)}
+    // ..., next sweep's sharp / flat features ready (streamSR), look-ahead odometry started (streamLO), next sweep's scan registration complete}
+    float v[15] = {0};
     if (!c->timing) { snprintf(c->err, sizeof c->err, "timing is off"); return VLOAM_E_INVALID; }
     for (int k = 0; k < 3; ++k) cudaEventElapsedTime(&v[k], c->ev[0], c->ev[k + 1]);
-    for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&v[3 + k], c->ev[0], c->evx[k]);
+    for (int k = 0; k < 12; ++k) cudaEventElapsedTime(&v[3 + k], c->ev[0], c->evx[k]);
     return put_host(v, sizeof v, out, cap);
   }
   if (n == "sr.trace") {  // clock64 phase stamps of the last sr_pick (CTAs 0..127) and sr_ring_voxel (128..255) launches

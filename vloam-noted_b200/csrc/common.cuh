@@ -68,6 +68,8 @@ struct LmScalars {
   int totalC, totalS;               // points in all 4851 cubes before this frame's update (bounds the next sub-map)
   int needSlow;                     // lm_prepare_fast: this sweep cannot use the in-place grid path (window moved / grid dirty): the host repeats it on the pool path
   int gridCount;                    // live points in the grid (both kinds)
+  int gridCountC;                   // ... of them corner points
+  int outsideC, outsideS;           // points appended raw to cubes outside the 5x5x3 window so far (rf_append_outside), per kind
   int gridTop, gridDirty, gridDead; // voxel-hash grid: chunks in use, dirty flag, tombstones (copied by lm_transform_update for the host's bookkeeping)
   double pose[7];                   // q_w_curr, t_w_curr (parameters[7], laser_mapping.h:156)
   double q_wmap_wodom[4], t_wmap_wodom[3];
@@ -111,6 +113,7 @@ struct vloam_b200_ctx {
   cudaEvent_t evAux, evAuxZero, evUpd;
   cudaStream_t stream3;       // map update of frame k runs here while frame k+1's scan registration / odometry run on `stream`
   cudaEvent_t evSR;           // scan registration of this frame finished and its counts are in h_srs
+  cudaEvent_t evSRfeat;       // ... its sharp / less-sharp / flat clouds are complete (the per-ring voxel filter of the less-flat cloud may still run)
   cudaEvent_t evStacks;       // this frame's downsampled stacks are ready
   cudaEvent_t evLast;         // search structures over the next "last" clouds are built
   cudaEvent_t evPose;         // solveMapping's pose is final (the map update may start)
@@ -122,12 +125,16 @@ struct vloam_b200_ctx {
   char err[512];
   long long launches;         // updated with __atomic_fetch_add (two issuing threads)
   long long regrows;          // device buffer (re)allocations after creation (vl_reserve): each one stalls a stream for ~ms
+  // One device arena per context, allocated in create: vl_reserve carves the ~60 per-sweep buffers out of it with a bump pointer.
+  // (A cudaMalloc costs 2-35 ms on a B200 box with a driver that has >1 GB mapped: the first sweep of a context spent 210 ms in
+  // 56 of them, and every later regrow stalled a sweep by several ms.)  Requests that do not fit fall back to cudaMalloc.
+  char* arena; size_t arenaCap; size_t arenaTop;
   VlWorker* worker;           // helper thread that issues the map update (created on first use)
   int num_sms;
   bool timing;
   cudaEvent_t ev[4];
   double hostT[8];     // timing mode only: host clock (us) at marks inside a frame (see "timing.host" in capi.cu)
-  cudaEvent_t evx[8];  // timing mode only: finer marks (see "timing.detail" in capi.cu)
+  cudaEvent_t evx[12]; // timing mode only: finer marks (see "timing.detail" in capi.cu)
   float stage_ms[3];
 
   // ---- scan registration
@@ -165,10 +172,11 @@ struct vloam_b200_ctx {
   // ---- laser odometry
   LoScalars* los; LoScalars* h_los;
   LoScalars* losNext;         // odometry state after the look-ahead odometry of sweep srNextKey (valid when loNextValid)
-  bool loNextValid, srAdopted, s2Done;
+  bool loNextValid, loNextQueued, srAdopted, s2Done;
   int loNextSet;              // the "last" set the look-ahead odometry searched (it assumed monotone rings: checked at adoption)
   bool loAssumeMonotone;      // lo_associate: take the grid path without the host flags (look-ahead only)
   bool inProcessFrame;        // inside process_frame: mapping follows the odometry in the same call
+  bool srDeferred, sideSubmitted;  // the registered look-ahead scan registration is issued with the deferred structures; that side work is with the helper thread
   bool loDeferred; int defSet, defNc, defNs; const float4* defCorner; const float4* defSurf;  // side-stream work of the odometry stage queued after the mapping
   cudaEvent_t evS2;           // sync point S2 (pose + sizes copied to the host)
   cudaStream_t streamLO;      // the look-ahead odometry of the NEXT sweep runs here, beside this sweep's mapping (own factor buffers)
@@ -181,7 +189,7 @@ struct vloam_b200_ctx {
   // while the side stream builds set [lastSet ^ 1] from this frame's clouds
   int* loRingTbl;                     // 2 sets x 2 clouds x (144 + 1) ints: ring-value -> first index tables
   VlScan loScan[2];
-  DBuf<int> loGridCells[2], loGridCellOf; DBuf<float4> loGridSorted[2]; bool loGridValid[2];
+  DBuf<int> loGridCells[2], loGridCellOf; DBuf<float4> loGridSorted[2]; bool loGridValid[2]; int loGridMask[2];  // hash of occupied 1.28 m cells per set
   int lastSet;
   DBuf<int> loCornerIdx, loSurfIdx;   // association results (2 / 3 ints per query)
   DBuf<double> factors;               // 10 doubles per factor slot (mapping stage, C-ABI evaluate / solve)
@@ -239,7 +247,7 @@ struct vloam_b200_ctx {
   X(int*, provSharp) X(int*, provLess) X(int*, provFlat) X(int*, cntSharp) X(int*, cntLess) X(int*, cntFlat)          \
   X(int*, offSharp) X(int*, offLess) X(int*, offFlat) X(DBuf<float4>, lessFlatProv) X(int*, ringDsCount) X(int*, ringDsOff) \
   X(DBuf<int>, selIdx) X(DBuf<float4>, sharp) X(DBuf<float4>, flat) X(int, cur)                                      \
-  X(int, nKept) X(int, nSharp) X(int, nLessSharp) X(int, nFlat) X(int, nLessFlat) X(bool, sr_counts_valid) X(cudaEvent_t, evSR)
+  X(int, nKept) X(int, nSharp) X(int, nLessSharp) X(int, nFlat) X(int, nLessFlat) X(bool, sr_counts_valid) X(cudaEvent_t, evSR) X(cudaEvent_t, evSRfeat)
 struct SrSet {
 #define VL_X(type, name) type name{};
   VL_SR_FIELDS(VL_X)
@@ -306,6 +314,13 @@ static inline bool vl_prof_match(const vloam_b200_ctx* c, const char* k) {
   return strncmp(c->prof_name, k, n) == 0 && (k[n] == 0 || k[n] == '<');
 }
 
+// cudaFree for anything vl_reserve handed out: blocks inside the arena are released with it
+static inline void vl_dev_free(vloam_b200_ctx* c, void* p) {
+  if (!p) return;
+  if (c->arena && (char*)p >= c->arena && (char*)p < c->arena + c->arenaCap) return;
+  cudaFree(p);
+}
+
 // Grows (never shrinks).  cudaMalloc / cudaFree stall the stream for milliseconds, so buffers whose
 // size follows the map ask for `slack` extra elements: growth then happens once per ~hundreds of frames.
 template <typename T>
@@ -317,11 +332,23 @@ static inline int vl_reserve(vloam_b200_ctx* c, DBuf<T>& b, size_t n, bool keep 
   if (ncap * sizeof(T) <= ((size_t)32 << 20)) ncap *= 2;  // HBM is plentiful: head room so a count hovering at a power of two never regrows
   T* np = nullptr;
   __atomic_fetch_add(&c->regrows, 1LL, __ATOMIC_RELAXED);
+  const size_t bytes_ = (ncap * sizeof(T) + 511) & ~(size_t)511;
+  if (c->arena && bytes_ <= c->arenaCap / 4) {  // bump allocation from the context's arena (grown-out blocks are not reused: they are few and small)
+    const size_t at = __atomic_fetch_add(&c->arenaTop, bytes_, __ATOMIC_RELAXED);
+    if (at + bytes_ <= c->arenaCap) np = reinterpret_cast<T*>(c->arena + at);
+  }
+  if (np) {
+    if (keep && b.p && b.cap) VL_CUDA(cudaMemcpyAsync(np, b.p, b.cap * sizeof(T), cudaMemcpyDeviceToDevice, VL_STREAM(c)));
+    if (b.p) { VL_CUDA(cudaStreamSynchronize(VL_STREAM(c))); vl_dev_free(c, b.p); }
+    b.p = np; b.cap = ncap;
+    return VLOAM_OK;
+  }
   static const bool trace = getenv("VLOAM_TRACE_ALLOC") != nullptr;
-  if (trace) fprintf(stderr, "[vloam_b200] grow buffer to %zu x %zu B (frame %d)\n", ncap, sizeof(T), c->lo_frameCount);
+  const double t0_ = trace ? vl_now_us() : 0.0;
   VL_CUDA(cudaMalloc(&np, ncap * sizeof(T)));
+  if (trace) fprintf(stderr, "[vloam_b200] grow buffer to %zu x %zu B (frame %d): cudaMalloc %.0f us\n", ncap, sizeof(T), c->lo_frameCount, vl_now_us() - t0_);
   if (keep && b.p && b.cap) VL_CUDA(cudaMemcpyAsync(np, b.p, b.cap * sizeof(T), cudaMemcpyDeviceToDevice, VL_STREAM(c)));
-  if (b.p) { VL_CUDA(cudaStreamSynchronize(VL_STREAM(c))); VL_CUDA(cudaFree(b.p)); }
+  if (b.p) { VL_CUDA(cudaStreamSynchronize(VL_STREAM(c))); vl_dev_free(c, b.p); }
   b.p = np; b.cap = ncap;
   return VLOAM_OK;
 }
@@ -346,12 +373,17 @@ int vl_sort_set_attrs(vloam_b200_ctx* c);
 int vl_solver_set_attrs(vloam_b200_ctx* c);
 int vl_lo_preload(vloam_b200_ctx* c);
 int vl_lo_lookahead(vloam_b200_ctx* c);
+int vl_lo_lookahead_solve(vloam_b200_ctx* c);   // part 1: queue the next sweep's odometry solve on its own stream
+int vl_lo_lookahead_stacks(vloam_b200_ctx* c);  // part 2 (after S2 is recorded): the next sweep's stack filters, if its scan registration is done
 int vl_lo_flush_deferred(vloam_b200_ctx* c);  // queue the deferred side-stream work of the last odometry call (look-ahead scan registration, next search structures)  // queue the NEXT sweep's odometry solve behind this sweep's mapping (no-op unless its scan registration is in flight)
 int vl_vg_preload(vloam_b200_ctx* c);
 int vl_lm_preload(vloam_b200_ctx* c);
 int vl_lm_register_full(vloam_b200_ctx* c, const float4* d_in, int n, float4* d_out);
 int vl_lm_fit_sets(vloam_b200_ctx* c, const float* d_near, int n, int kind, int* d_ok, double* d_prm);  // vloam_b200_fit
 int vl_lm_join(vloam_b200_ctx* c);      // wait until the helper thread has issued the pending map update; returns its status
+int vl_lm_submit_task(vloam_b200_ctx* c, int (*fn)(vloam_b200_ctx*));  // hand a launch-issuing task to the helper thread (joins the previous one first)
+int vl_lo_side_work(vloam_b200_ctx* c);  // the deferred side-stream work of the odometry stage (look-ahead scan registration, next search structures)
+int vl_lo_submit_side(vloam_b200_ctx* c);  // ... issued by the helper thread while the caller queues the mapping
 void vl_lm_shutdown(vloam_b200_ctx* c);  // stop the helper thread
 int vl_lm_export_map(vloam_b200_ctx* c, int which, void* out, long cap, long* bytes);
 int vl_lm_sync_pools(vloam_b200_ctx* c);  // write the in-place grid updates back to the cube pools (no-op when they are current)
@@ -374,7 +406,7 @@ int vl_voxel_grid_device(vloam_b200_ctx* c, const float4* d_in, int n, const int
 int vl_solve(vloam_b200_ctx* c, int nslots, const int* d_nslots, double* d_x_inout, double* costs2 /* host, may be null */,
              int hint = 0 /* last known actual slot count, 0 = none */, const double* d_s = nullptr);
 int vl_solve_buf(vloam_b200_ctx* c, const double* d_factors, const int* d_valid, int nslots, const int* d_nslots, double* d_x_inout, double* costs2, int hint,
-                 const double* d_s);  // same on explicit factor buffers, on the calling thread's current stream (VL_STREAM)
+                 const double* d_s, int ncta = 16);  // same on explicit factor buffers; ncta: CTAs of the solver's cluster (8 or 16: it fixes the summation order), on the calling thread's current stream (VL_STREAM)
 int vl_evaluate_once(vloam_b200_ctx* c, int nslots, const double* d_x, EvalOut* d_out, const double* d_s = nullptr);
 static inline bool vl_distortion(const vloam_b200_ctx* c) { return (c->prm.reserved & 1) != 0; }  // LaserOdometry::DISTORTION (LO.h:90)
 

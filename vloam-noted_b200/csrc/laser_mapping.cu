@@ -105,6 +105,7 @@ void vl_lm_shutdown(vloam_b200_ctx* c) {
   c->worker = nullptr;
 }
 
+int vl_lm_submit_task(vloam_b200_ctx* c, int (*fn)(vloam_b200_ctx*));
 static int lm_submit(vloam_b200_ctx* c, std::function<int()> f) {
   if (!c->worker) {
     VlWorker* w = new VlWorker();
@@ -123,6 +124,7 @@ static int lm_submit(vloam_b200_ctx* c, std::function<int()> f) {
   return VLOAM_OK;
 }
 
+int vl_lm_submit_task(vloam_b200_ctx* c, int (*fn)(vloam_b200_ctx*)) { return lm_submit(c, [c, fn]() -> int { return fn(c); }); }
 
 #define LM_CELL 2.0f
 #define LM_GX 125
@@ -873,7 +875,7 @@ __global__ void lm_transform_update(LmScalars* s, const LgHeader* __restrict__ g
   VL_PDL_WAIT();
   // LM.cpp:147-151
   if (threadIdx.x != 0) return;
-  s->gridTop = *gridTop; s->gridDirty = gh->dirty; s->gridDead = gh->dead; s->gridCount = gh->count[0] + gh->count[1];
+  s->gridTop = *gridTop; s->gridDirty = gh->dirty; s->gridDead = gh->dead; s->gridCount = gh->count[0] + gh->count[1]; s->gridCountC = gh->count[0];
   if (s->needSlow) return;  // the sweep is repeated on the pool path: leave the state untouched
   const double* q = s->q_wodom;
   const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
@@ -1222,18 +1224,21 @@ __global__ void rf_finish(LmScalars* __restrict__ s, const RfWork* __restrict__ 
 __global__ void __launch_bounds__(1024) rf_append_outside(LmScalars* __restrict__ s, const float4* __restrict__ newPts,
                                                           const int* __restrict__ newCube, MapCubeTable* __restrict__ tc,
                                                           MapCubeTable* __restrict__ ts, float4* __restrict__ poolC, float4* __restrict__ poolS,
-                                                          int poolCapC, int poolCapS) {
+                                                          int poolCapC, int poolCapS, const int* __restrict__ anyOutside) {
   VL_PDL_WAIT();
 
+  if (anyOutside && (s->needSlow || !*anyOutside)) return;  // (in-place path: mu_keys saw no point outside the window)
   const int Qc = s->Qc, total = s->Qc + s->Qs;
   __shared__ int lIdx[1024], lKey[1024];
   __shared__ int gKey[1024], gOld[1024], gNew[1024], gCnt[1024];
   __shared__ int warpSum[32];
   __shared__ int nGrow;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int any = 0;
-  for (int i = threadIdx.x; i < total; i += 1024) any |= (newCube[i] >= 0);
+  int any = 0, outC = 0, outS = 0;
+  for (int i = threadIdx.x; i < total; i += 1024) if (newCube[i] >= 0) { any = 1; if (i < Qc) ++outC; else ++outS; }
   if (__syncthreads_or(any) == 0) return;
+  if (outC) atomicAdd(&s->outsideC, outC);  // (the host's bound on the map size follows these counts, read at the next S2)
+  if (outS) atomicAdd(&s->outsideS, outS);
   for (int base = 0; base < total; base += 1024) {
     const int i = base + threadIdx.x;
     const int cb = i < total ? newCube[i] : -1;
@@ -1296,24 +1301,86 @@ __global__ void __launch_bounds__(1024) rf_append_outside(LmScalars* __restrict_
 }
 
 // ---- in-place map update on the voxel-hash grid (LM.cpp:741-808 without touching the other ~1M points) -------------------
-// Input: this sweep's keys (segment | voxel | stack order), bucketed and sorted per segment (rf_keys with noTails,
-// rf_seg_scatter, rf_seg_sort).  One thread per run of equal (segment, voxel): the map point of that voxel, if there is one,
-// is found in the grid -- it lies inside the voxel's box, i.e. in one of the <= 2x2x2 cells the box overlaps -- and the
-// run is folded exactly as pcl::VoxelGrid does on [cube cloud ; appended points]: map point first (it has the lower index),
-// then the new points in stack order, f32 sums, one division.  The centroid is stored back in place; it becomes a pending
-// insert when the voxel is new or the centroid left its 2 m cell (the old entry is tombstoned).  Structural changes
-// (appends to cell chains) happen in mu_insert, a separate launch: no thread scans a chain while another one grows it.
+// pcl::VoxelGrid over [cube cloud ; this sweep's points] changes only the voxels the new points fall into.  Three launches:
+//   mu_keys   every new point: world transform (LM.cpp:744, 768), cube, voxel key; points of the same (cube, voxel) meet in a
+//             small open-addressing hash table, whose entry keeps the lowest stack index as the group's leader
+//   mu_group  every other point of a group registers with its leader
+//   mu_apply  every leader: its members in stack order (<= 8: the stacks are voxel-filtered at the same leaf), the map point
+//             of that voxel looked up IN THE GRID -- it lies inside the voxel's box, i.e. in one of the <= 2x2x2 cells the box
+//             overlaps -- and the fold exactly as VoxelGrid does it: map point first (it has the lower index), then the new
+//             points in stack order, f32 sums, one division.  The centroid is stored back in place, or appended to its cell
+//             when the voxel is new or the centroid left its 2 m cell (the old entry is tombstoned).
+// No sort: round 1's update sorted (segment | voxel | order) keys, 30 us for the one cube that holds most of a sweep.
 // A centroid that no longer maps to its own voxel (f32 rounding at a voxel face) is legal -- the next VoxelGrid pass re-keys
 // it -- but outside the in-place scheme: it raises `dirty`, and the next sweep runs the pool path on materialised cubes.
-__global__ void __launch_bounds__(128) mu_apply(const unsigned long long* __restrict__ keys, const LmScalars* __restrict__ s, const RfWork* __restrict__ w,
-                                                vloam_b200_params prm, LgGrid g, const float4* __restrict__ newPts, LgOp* __restrict__ ops) {
+#define MU_MEMBERS 15
+struct MuWork {            // device scratch of one update (sized by the host for nq points)
+  unsigned long long* hkey;  // [H] hash table: (segment << 32 | voxel key) or empty
+  int* hlead;                // [H] lowest stack index of the group
+  int H;                     // power of two >= 4 nq
+  int* slotOf;               // [nq] hash slot of point i, -1: not in a valid cube
+  int* memberCnt;            // [nq]
+  int* members;              // [nq * MU_MEMBERS]
+  int* anyOutside;           // a point fell into a cube outside the 5x5x3 window (rf_append_outside has work)
+};
+__device__ __forceinline__ unsigned mu_hash(unsigned long long k) { k ^= k >> 31; k *= 0x9E3779B97F4A7C15ull; k ^= k >> 29; return (unsigned)k; }
+
+__global__ void __launch_bounds__(256) mu_keys(const LmScalars* __restrict__ s, const RfWork* __restrict__ w, vloam_b200_params prm,
+                                               const float4* __restrict__ stackC, const float4* __restrict__ stackS, float4* __restrict__ newPts,
+                                               int* __restrict__ newCube, MuWork m) {
+  VL_PDL_WAIT();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Qc = s->Qc, Qs = s->Qs;
+  if (s->needSlow || i >= Qc + Qs) return;  // (queued before the host knows whether the sweep stays on the in-place path, and with a bound on the count)
+  const int kind = i >= Qc;
+  const float4 po = kind ? stackS[i - Qc] : stackC[i];
+  double r[3];
+  vl_qrot(s->pose, (double)po.x, (double)po.y, (double)po.z, r);
+  const float4 p = make_float4((float)(r[0] + s->pose[4]), (float)(r[1] + s->pose[5]), (float)(r[2] + s->pose[6]), po.w);
+  const int ci = lm_cube_of(p.x, s->cenW), cj = lm_cube_of(p.y, s->cenH), ck = lm_cube_of(p.z, s->cenD);
+  int cb = -1;
+  if (ci >= 0 && ci < VL_CUBE_W && cj >= 0 && cj < VL_CUBE_H && ck >= 0 && ck < VL_CUBE_D) cb = ci + VL_CUBE_W * cj + VL_CUBE_W * VL_CUBE_H * ck;
+  newPts[i] = p;
+  const int slot = cb >= 0 ? w->slotOfCube[cb] : -1;
+  newCube[i] = (cb >= 0 && slot < 0) ? cb : -1;  // only cubes outside the window need the raw append path
+  m.memberCnt[i] = 0;
+  int hs = -1;
+  if (slot >= 0) {
+    const unsigned vk = lm_vox_key(p, lm_leaf_inv(prm, kind), ci, cj, ck, s->cenW, s->cenH, s->cenD);
+    const unsigned long long key = ((unsigned long long)(kind * VL_MAX_VALID + slot) << 32) | vk;
+    unsigned h = mu_hash(key) & (unsigned)(m.H - 1);
+    for (;;) {
+      const unsigned long long prev = atomicCAS(&m.hkey[h], ~0ull, key);
+      if (prev == ~0ull || prev == key) break;
+      h = (h + 1) & (unsigned)(m.H - 1);
+    }
+    atomicMin(&m.hlead[h], i);
+    hs = (int)h;
+  } else if (cb >= 0) *m.anyOutside = 1;
+  m.slotOf[i] = hs;
+}
+__global__ void __launch_bounds__(256) mu_group(const LmScalars* __restrict__ s, MuWork m) {
+  VL_PDL_WAIT();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s->needSlow || i >= s->Qc + s->Qs) return;
+  const int hs = m.slotOf[i];
+  if (hs < 0) return;
+  const int L = m.hlead[hs];
+  if (L == i) return;
+  const int pos = atomicAdd(&m.memberCnt[L], 1);
+  if (pos < MU_MEMBERS) m.members[L * MU_MEMBERS + pos] = i;
+}
+__global__ void __launch_bounds__(128) mu_apply(const LmScalars* __restrict__ s, vloam_b200_params prm, LgGrid g, const float4* __restrict__ newPts,
+                                                MuWork mw) {
   VL_PDL_WAIT();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= w->nKeysValid) return;
-  const unsigned long long key = keys[t];
-  const int sg = (int)(key >> 56);
-  const unsigned vk = RF_VOX(key);
-  if (t != w->tailBegin[sg] && RF_VOX(keys[t - 1]) == vk) return;  // not the head of its run
+  const int nq = s->needSlow ? 0 : s->Qc + s->Qs;
+  const int hs = t < nq ? mw.slotOf[t] : -1;
+  int bornKind = -1, died = 0;  // bookkeeping of this thread's voxel, added up per warp at the end (thousands of atomics on ONE address cost ~50 us)
+  if (hs >= 0 && mw.hlead[hs] == t) {  // the leader of its voxel
+  const unsigned long long hk = mw.hkey[hs];
+  const int sg = (int)(hk >> 32);
+  const unsigned vk = (unsigned)hk;
   const int kind = sg / VL_MAX_VALID, slot = sg % VL_MAX_VALID, cb = s->validInd[slot];
   const float leaf = kind ? prm.plane_res : prm.line_res;
   const float inv = lm_leaf_inv(prm, kind);
@@ -1331,36 +1398,42 @@ __global__ void __launch_bounds__(128) mu_apply(const unsigned long long* __rest
   int found = -1, foundCell = -1;
   if (x1 - x0 <= 1 && y1 - y0 <= 1 && z1 - z0 <= 1) {
     // leaf <= 2 m: the box spans at most 2 x 2 x 2 cells.  All directory entries, then the first chunk of every cell, are
-    // loaded without waiting for one another (a serial walk is ~20 dependent L2 round trips per voxel: 40 us per update)
+    // loaded without waiting for one another (a serial walk is ~20 dependent L2 round trips per voxel)
     int cellId[8]; int2 dd[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int xx = x0 + (q & 1), yy = y0 + ((q >> 1) & 1), zz = z0 + (q >> 2);
       const bool on = xx <= x1 && yy <= y1 && zz <= z1;
       cellId[q] = kind * LM_NCELL + xx + LM_GX * (yy + LM_GY * zz);
-      dd[q] = on ? g.dir[cellId[q]] : make_int2(0, -1);
+      dd[q] = on ? __ldcg(&g.dir[cellId[q]]) : make_int2(0, -1);  // (L2: other voxels' appends to these cells may be in flight)
     }
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      if (dd[q].x <= 0) continue;
+      if (dd[q].x <= 0 || dd[q].y < 0) continue;
       const ulonglong2* kp = reinterpret_cast<const ulonglong2*>(g.key + (size_t)dd[q].y * LG_C);
       const int m = min(dd[q].x, LG_C);
 #pragma unroll
       for (int i = 0; i < LG_C / 2; ++i) {
-        const ulonglong2 kk = kp[i];
+        const ulonglong2 kk = __ldcg(&kp[i]);
         if (2 * i < m && kk.x == want) { found = dd[q].y * LG_C + 2 * i; foundCell = cellId[q]; }
         if (2 * i + 1 < m && kk.y == want) { found = dd[q].y * LG_C + 2 * i + 1; foundCell = cellId[q]; }
       }
     }
     if (found < 0) {
-#pragma unroll 1
-      for (int q = 0; q < 8 && found < 0; ++q) {  // longer chains (> LG_C points in a cell)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {  // longer chains (> LG_C points in a cell)
         int chunk = dd[q].y;
-        for (int left = dd[q].x - LG_C; left > 0 && found < 0; left -= LG_C) {
-          chunk = g.next[chunk];
+        for (int left = dd[q].x - LG_C; left > 0 && found < 0 && chunk >= 0; left -= LG_C) {
+          chunk = __ldcg(&g.next[chunk]);
+          if (chunk < 0) break;  // (another voxel's append is still extending this chain: nothing of ours can be beyond)
           const int m = min(left, LG_C);
-          for (int i = 0; i < m; ++i)
-            if (g.key[chunk * LG_C + i] == want) { found = chunk * LG_C + i; foundCell = cellId[q]; break; }
+          const ulonglong2* kp = reinterpret_cast<const ulonglong2*>(g.key + (size_t)chunk * LG_C);
+#pragma unroll
+          for (int i = 0; i < LG_C / 2; ++i) {  // all 16 keys of the chunk in flight at once (a scalar loop with an early exit is 16 dependent L2 round trips)
+            const ulonglong2 kk = __ldcg(&kp[i]);
+            if (2 * i < m && kk.x == want) { found = chunk * LG_C + 2 * i; foundCell = cellId[q]; }
+            if (2 * i + 1 < m && kk.y == want) { found = chunk * LG_C + 2 * i + 1; foundCell = cellId[q]; }
+          }
         }
       }
     }
@@ -1369,33 +1442,50 @@ __global__ void __launch_bounds__(128) mu_apply(const unsigned long long* __rest
       for (int yy = y0; yy <= y1 && found < 0; ++yy)
         for (int xx = x0; xx <= x1 && found < 0; ++xx) {
           const int cell = kind * LM_NCELL + xx + LM_GX * (yy + LM_GY * zz);
-          const int2 d = g.dir[cell];
+          const int2 d = __ldcg(&g.dir[cell]);
           int chunk = d.y;
-          for (int left = d.x; left > 0 && found < 0; left -= LG_C, chunk = left > 0 ? g.next[chunk] : -1) {
+          for (int left = d.x; left > 0 && found < 0 && chunk >= 0; left -= LG_C, chunk = left > 0 ? __ldcg(&g.next[chunk]) : -1) {
             const int m = min(left, LG_C);
             for (int i = 0; i < m; ++i)
-              if (g.key[chunk * LG_C + i] == want) { found = chunk * LG_C + i; foundCell = cell; break; }
+              if (__ldcg(&g.key[chunk * LG_C + i]) == want) { found = chunk * LG_C + i; foundCell = cell; break; }
           }
         }
   }
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   int cnt = 0;
   if (found >= 0) { acc = rf_fold(acc, g.pts[found]); cnt = 1; }
-  const int segEnd = w->tailBegin[sg + 1];
-  for (int q = t; q < segEnd && RF_VOX(keys[q]) == vk; ++q) { acc = rf_fold(acc, newPts[(unsigned)(keys[q] & 0x3ffffffull) - (1u << 25)]); ++cnt; }
+  acc = rf_fold(acc, newPts[t]); ++cnt;       // the leader has the lowest stack index of its group
+  const int nm = mw.memberCnt[t];
+  if (nm <= MU_MEMBERS) {
+    // registration order is arbitrary: take the members in stack order (nm is 0..2 for nearly every voxel: the stacks are
+    // voxel-filtered at the same leaf, so a world voxel collects at most the points of the ~8 lidar-frame voxels it overlaps)
+    int last = t;
+    for (int q = 0; q < nm; ++q) {
+      int best = 0x7fffffff;
+      for (int r = 0; r < nm; ++r) { const int v = mw.members[t * MU_MEMBERS + r]; if (v > last && v < best) best = v; }
+      acc = rf_fold(acc, newPts[best]); ++cnt;
+      last = best;
+    }
+  } else {
+    for (int j = t + 1; j < nq; ++j) if (mw.slotOf[j] == hs) { acc = rf_fold(acc, newPts[j]); ++cnt; }  // (more members than slots: walk the stack)
+  }
   const float4 c = rf_centroid(acc, cnt);
   if (lm_vox_key(c, inv, ci, cj, ck, s->cenW, s->cenH, s->cenD) != vk) g.hdr->dirty = 1;  // drifted across a voxel face: pool path next sweep
   const int cell = kind * LM_NCELL + lg_cell_of(c, o);
-  if (found >= 0 && cell == foundCell) { g.pts[found] = c; return; }
-  if (found >= 0) { g.pts[found].x = CUDART_INF_F; g.key[found] = LG_DEAD; atomicAdd(&g.hdr->dead, 1); }
-  else atomicAdd(&g.hdr->count[kind], 1);
-  LgOp op; op.p = c; op.key = want; op.cell = cell; op.pos = found >= 0 ? g.posOf[found] : -1;
-  ops[atomicAdd(&g.hdr->nOps, 1)] = op;
-}
-__global__ void __launch_bounds__(128) mu_insert(LgGrid g, const LgOp* __restrict__ ops) {
-  VL_PDL_WAIT();
-  const int n = g.hdr->nOps;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) lg_insert(g, ops[t].cell, ops[t].p, ops[t].key, ops[t].pos);
+  if (found >= 0 && cell == foundCell) g.pts[found] = c;
+  else {
+    int pos = -1;
+    if (found >= 0) { pos = g.posOf[found]; g.pts[found].x = CUDART_INF_F; *(volatile unsigned long long*)&g.key[found] = LG_DEAD; died = 1; }
+    else bornKind = kind;
+    lg_insert(g, cell, c, want, pos);
+  }
+  }
+  const unsigned b0 = __ballot_sync(0xffffffffu, bornKind == 0), b1 = __ballot_sync(0xffffffffu, bornKind == 1), bd = __ballot_sync(0xffffffffu, died);
+  if ((threadIdx.x & 31) == 0) {
+    if (b0) atomicAdd(&g.hdr->count[0], __popc(b0));
+    if (b1) atomicAdd(&g.hdr->count[1], __popc(b1));
+    if (bd) atomicAdd(&g.hdr->dead, __popc(bd));
+  }
 }
 
 // ---- grid -> cube pools (the pools are the exchange format: export, window moves, the pool-path update) ----------------------
@@ -1495,7 +1585,7 @@ struct LmDevice {  // extra device state owned by this file
   LmSub* subReal; LmSub* subSpec;    // sub-map window descriptors (lm_prepare's / the one rebuilt after a pool-path update)
   // ---- the persistent voxel-hash grid (lm_grid.cuh)
   LgGrid grid;                       // device pointers (dir, chunks, allocator, header)
-  DBuf<LgOp> ops;                    // pending inserts of the in-place update
+  DBuf<unsigned long long> muKey; DBuf<int> muInt;  // scratch of the in-place update (MuWork: hash table, groups)
   DBuf<int> knnIds;                  // debug capture: canonical ids of the neighbours
   bool gridEnabled;                  // VLOAM_NO_SPECULATION / VLOAM_NO_GRID unset: in-place updates and the post-update rebuild are on
   bool gridValid;                    // host: the grid was (re)built behind the last map update and nothing edited the map since
@@ -1503,6 +1593,9 @@ struct LmDevice {  // extra device state owned by this file
   long long gridTopUpper;            // host bound on the chunks in use
   long long newVoxUpper;             // host bound on the voxels created by in-place updates since the grid was built
   long long builtCount;              // live points the grid held when it was built
+  long long builtCountC;             // ... of them corner points
+  long long baseC, baseS;            // bound on the map size (all cubes) when the grid was built, and the raw appends outside the window
+  long long outBaseC, outBaseS;      // counted until then: the bound of every later sweep follows the DEVICE counts from there (no drift)
 };
 static LmDevice* lmdev(vloam_b200_ctx* c) { return reinterpret_cast<LmDevice*>(c->gridPrm); }
 
@@ -1571,8 +1664,8 @@ void vl_lm_free(vloam_b200_ctx* c) {  // everything vl_lm_init and this file's r
   LmDevice* d = lmdev(c);
   if (!d) return;
   void* dev[] = {d->work, d->dQ, d->subReal, d->subSpec, d->newPts.p, d->newCube.p, d->unmatched.p, d->grid.dir, d->grid.top, d->grid.hdr,
-                 d->grid.pts, d->grid.key, d->grid.next, d->grid.posOf, d->ops.p, d->knnIds.p};
-  for (void* p : dev) if (p) cudaFree(p);
+                 d->grid.pts, d->grid.key, d->grid.next, d->grid.posOf, d->muKey.p, d->muInt.p, d->knnIds.p};
+  for (void* p : dev) vl_dev_free(c, p);
   delete d;
   c->gridPrm = nullptr;
 }
@@ -1775,9 +1868,10 @@ static int lm_sync_s2(vloam_b200_ctx* c, bool capture, bool* lookaheadDone) {
   VL_HOST_MARK(5);
   if (!*lookaheadDone) {
     VL_TRY(vl_lo_flush_deferred(c));
-    if (!capture) VL_TRY(vl_lo_lookahead(c));
+    if (!capture) VL_TRY(vl_lo_lookahead_solve(c));
     *lookaheadDone = true;
   }
+  if (!capture) VL_TRY(vl_lo_lookahead_stacks(c));  // (no-op unless a look-ahead solve was queued in this call)
   VL_CUDA(cudaEventSynchronize(c->evS2));
   c->s2Done = true;
   VL_HOST_MARK(6);
@@ -1819,54 +1913,72 @@ int vl_lm_run(vloam_b200_ctx* c) {
 
   // ---- in-place path: the grid describes this sweep's sub-map unless lm_prepare_fast finds the window moved / the grid dirty
   if (d->gridEnabled && d->gridValid && !capture && d->gridTopUpper + 2LL * nqBound <= d->grid.cap && d->newVoxUpper + nqBound <= LG_NEWVOX_MAX) {
+    if (!inlineUpdate) VL_TRY(vl_lo_submit_side(c));  // the helper thread issues the look-ahead scan registration + the next odometry structures meanwhile
     VL_LAUNCH(lm_prepare_fast, 1, 256, 0, c->lmm, c->los, d->work, d->grid.hdr, 0, resetValid);
     if (c->timing) VL_CUDA(cudaEventRecord(c->evx[0], c->stream));
     VL_TRY(lm_queue_passes(c, d, nqBound, false, d->subReal));
+    // The in-place map update is queued NOW, behind the pose (evPose) on its own stream, before the host waits at S2: its kernels
+    // read the counts and the needSlow flag on the device (sizes here are bounds), so the device runs it the moment the pose is
+    // final instead of waiting for S2 -> host -> helper thread -> launch (~45 us on the chain the next sweep's mapping waits for).
+    // the next sweep's odometry solve goes to its own stream first: its inputs are ready long before this sweep's pose is
+    VL_TRY(vl_lo_flush_deferred(c));
+    VL_TRY(vl_lo_lookahead_solve(c));
+    lookaheadDone = true;
+    VL_TRY(lm_pool_headroom(c, 0, 0, nqBound, nqBound));  // (points outside the window are appended raw to their cubes' pool segments: room for them
+                                                          // is checked BEFORE the append is queued, with the bound, against the pool top of the last S2)
+    VL_CUDA(cudaEventRecord(c->evPose, c->stream));
+    {
+      const int nq = nqBound;
+      const float4* const stackCp = c->stackC.p; const float4* const stackSp = c->stackS.p;
+      vl_tls_stream = c->stream3;
+      struct Restore { ~Restore() { vl_tls_stream = nullptr; } } restore;
+      VL_CUDA(cudaStreamWaitEvent(c->stream3, c->evPose, 0));
+      int H = 1024; while (H < 4 * nq) H <<= 1;
+      VL_TRY(vl_reserve(c, d->newPts, (size_t)nq));
+      VL_TRY(vl_reserve(c, d->newCube, (size_t)nq));
+      VL_TRY(vl_reserve(c, d->muKey, (size_t)H));
+      VL_TRY(vl_reserve(c, d->muInt, (size_t)H + (size_t)nq * (2 + MU_MEMBERS) + 4));
+      MuWork mw;
+      mw.hkey = d->muKey.p; mw.H = H; mw.hlead = d->muInt.p; mw.slotOf = mw.hlead + H; mw.memberCnt = mw.slotOf + nq;
+      mw.members = mw.memberCnt + nq; mw.anyOutside = mw.members + (size_t)nq * MU_MEMBERS;
+      VL_CUDA(cudaMemsetAsync(mw.hkey, 0xff, (size_t)H * 8, c->stream3));   // empty slots
+      VL_CUDA(cudaMemsetAsync(mw.hlead, 0x7f, (size_t)H * 4, c->stream3));  // "no leader yet" (0x7f7f7f7f > any stack index)
+      VL_CUDA(cudaMemsetAsync(mw.anyOutside, 0, 4, c->stream3));
+      VL_BYTES(16.0 * max(c->h_lmm->Qc + c->h_lmm->Qs, 1));  // SURVEY 8(d) B_lm insert term: every new point once (last known count)
+      VL_LAUNCH(mu_keys, vl_div_up(nq, 256), 256, 0, c->lmm, d->work, c->prm, stackCp, stackSp, d->newPts.p, d->newCube.p, mw);
+      VL_CUDA(cudaEventRecord(c->evKeys, c->stream3));  // nothing below reads the stacks any more: the next sweep's filters may overwrite them
+      VL_CUDA(cudaEventRecord(c->evKeysSel[c->stackSel], c->stream3));
+      // points outside the 5x5x3 window go to cubes the grid does not hold: appended raw to their pool segments beside the in-place update
+      VL_CUDA(cudaEventRecord(c->evUpd, c->stream3));
+      VL_CUDA(cudaStreamWaitEvent(c->streamAux, c->evUpd, 0));
+      vl_tls_stream = c->streamAux;
+      VL_LAUNCH(rf_append_outside, 1, 1024, 0, c->lmm, d->newPts.p, d->newCube.p, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, (int)c->poolC.cap,
+                (int)c->poolS.cap, (const int*)mw.anyOutside);
+      vl_tls_stream = c->stream3;
+      VL_CUDA(cudaEventRecord(c->evAux, c->streamAux));
+      VL_LAUNCH(mu_group, vl_div_up(nq, 256), 256, 0, c->lmm, mw);
+      VL_BYTES(2.0 * 32.0 * max(c->h_lmm->Qc + c->h_lmm->Qs, 1));  // read + write of the map points that change (SURVEY 8(d) re-filter term restricted to what changes)
+      VL_LAUNCH(mu_apply, vl_div_up(nq, 128), 128, 0, c->lmm, c->prm, d->grid, d->newPts.p, mw);
+      VL_CUDA(cudaEventRecord(c->evMap, c->stream3));
+      if (c->timing) VL_CUDA(cudaEventRecord(c->evx[7], c->stream3));
+    }
     VL_TRY(lm_sync_s2(c, false, &lookaheadDone));
     if (!c->h_lmm->needSlow) {
       const int Qc = c->h_lmm->Qc, Qs = c->h_lmm->Qs, nq = Qc + Qs;
-      if (d->builtCount < 0) d->builtCount = c->h_lmm->gridCount;  // first in-place sweep after a rebuild: nothing created yet
+      if (d->builtCount < 0) {  // first in-place sweep after a rebuild: nothing created yet
+        d->builtCount = c->h_lmm->gridCount; d->builtCountC = c->h_lmm->gridCountC;
+        d->baseC = d->hMapUpperC; d->baseS = d->hMapUpperS; d->outBaseC = c->h_lmm->outsideC; d->outBaseS = c->h_lmm->outsideS;
+      }
       c->lm_optimized = c->h_lmm->optimized;
-      const float4* const stackCp = c->stackC.p; const float4* const stackSp = c->stackS.p;  // (the next frame may swap the buffers while the helper issues this)
-      const int stackSelNow = c->stackSel;
       d->gridTopUpper = (long long)c->h_lmm->gridTop + nq;  // chunks in use before this update + at most one new chunk per new voxel
-      VL_TRY(lm_pool_headroom(c, 0, 0, Qc, Qs));  // (points outside the window are appended raw to their cubes' pool segments)
-      d->hMapUpperC += Qc; d->hMapUpperS += Qs;
+      // map size after this update <= size at the build + voxels created in the grid + raw appends outside the window (device counts
+      // at this S2: everything up to the previous update) + this sweep's points.  (Adding Qc + Qs per sweep drifts by ~15k points a
+      // sweep -- most of them merge into existing voxels -- and made the next window move regrow the grid and the merge buffers.)
+      d->hMapUpperC = d->baseC + (c->h_lmm->gridCountC - d->builtCountC) + (c->h_lmm->outsideC - d->outBaseC) + Qc;
+      d->hMapUpperS = d->baseS + ((c->h_lmm->gridCount - c->h_lmm->gridCountC) - (d->builtCount - d->builtCountC)) + (c->h_lmm->outsideS - d->outBaseS) + Qs;
       d->newVoxUpper = (long long)c->h_lmm->gridCount - d->builtCount + nq;  // voxels created so far (device count at S2) + at most nq by this update
       if (nq > 0) d->poolsStale = true;
-      auto update = [=]() -> int {
-        vl_tls_stream = c->stream3;
-        struct Restore { ~Restore() { vl_tls_stream = nullptr; } } restore;
-        VL_CUDA(cudaStreamWaitEvent(c->stream3, c->evPose, 0));
-        if (nq > 0) {
-          const size_t N = ((size_t)nq + 255) & ~(size_t)255;
-          VL_TRY(vl_reserve(c, c->tailKeys, 4 * N, false, 4 * N));
-          unsigned long long* keysIn = c->tailKeys.p;
-          unsigned long long* keysSorted = c->tailKeys.p + N;
-          VL_TRY(vl_reserve(c, d->newPts, (size_t)nq));
-          VL_TRY(vl_reserve(c, d->newCube, (size_t)nq));
-          VL_TRY(vl_reserve(c, d->ops, (size_t)nq));
-          VL_BYTES(16.0 * nq);  // SURVEY 8(d) B_lm insert term: every new point once
-          VL_LAUNCH(rf_keys, vl_div_up(nq, 256), 256, 0, c->lmm, d->work, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, stackCp, stackSp,
-                    d->newPts.p, d->newCube.p, keysIn, nq, 1);
-          VL_CUDA(cudaEventRecord(c->evKeys, c->stream3));  // nothing below reads the stacks any more: the next sweep's filters may overwrite them
-          VL_CUDA(cudaEventRecord(c->evKeysSel[stackSelNow], c->stream3));
-          VL_LAUNCH(rf_seg_scatter, vl_div_up(nq, 256), 256, 0, keysIn, nq, d->work, keysSorted);
-          static const int segCap = getenv("VLOAM_SEG_CAP") ? max(8, min(atoi(getenv("VLOAM_SEG_CAP")), RF_SEG_CAP)) : RF_SEG_CAP;  // tests force the global path
-          VL_BYTES(16.0 * nq);
-          VL_LAUNCH(rf_seg_sort, LM_NSEG, RF_SEG_THREADS, (size_t)RF_SEG_CAP * 8, keysSorted, d->work, c->tailKeys.p + 2 * N, segCap);
-          VL_BYTES(2.0 * 32.0 * nq);  // read + write of the ~nq map points that change (SURVEY 8(d) re-filter term restricted to what changes)
-          VL_LAUNCH(mu_apply, vl_div_up(nq, 128), 128, 0, keysSorted, c->lmm, d->work, c->prm, d->grid, d->newPts.p, d->ops.p);
-          VL_LAUNCH(mu_insert, min(vl_div_up(nq, 128), c->num_sms * 4), 128, 0, d->grid, d->ops.p);
-          VL_LAUNCH(rf_append_outside, 1, 1024, 0, c->lmm, d->newPts.p, d->newCube.p, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, (int)c->poolC.cap,
-                    (int)c->poolS.cap);
-        }
-        VL_CUDA(cudaEventRecord(c->evMap, c->stream3));
-        return VLOAM_OK;
-      };
       c->lm_frameCount++;
-      if (inlineUpdate) { const int rmap = update(); if (rmap != VLOAM_OK) return rmap; }
-      else VL_TRY(lm_submit(c, update));
       VL_HOST_MARK(7);
       VL_CUDA(cudaGetLastError());
       return VLOAM_OK;
@@ -1940,7 +2052,7 @@ int vl_lm_run(vloam_b200_ctx* c) {
       VL_CUDA(cudaStreamWaitEvent(c->streamAux, c->evUpd, 0));
       vl_tls_stream = c->streamAux;
       VL_LAUNCH(rf_append_outside, 1, 1024, 0, c->lmm, d->newPts.p, d->newCube.p, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, (int)c->poolC.cap,
-                (int)c->poolS.cap);
+                (int)c->poolS.cap, (const int*)nullptr);
       vl_tls_stream = c->stream3;
     }
   }
@@ -2065,7 +2177,7 @@ int vl_lm_preload(vloam_b200_ctx* c) {  // see vl_sr_set_attrs: load every kerne
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_fit));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lg_zero)); VL_CUDA(cudaFuncGetAttributes(&fa_, lg_rebuild)); VL_CUDA(cudaFuncGetAttributes(&fa_, lm_prepare_fast));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lg_knn)); VL_CUDA(cudaFuncGetAttributes(&fa_, lg_keys_to_ids)); VL_CUDA(cudaFuncGetAttributes(&fa_, lm_gather));
-  VL_CUDA(cudaFuncGetAttributes(&fa_, mu_apply)); VL_CUDA(cudaFuncGetAttributes(&fa_, mu_insert)); VL_CUDA(cudaFuncGetAttributes(&fa_, mz_collect));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, mu_apply)); VL_CUDA(cudaFuncGetAttributes(&fa_, mu_keys)); VL_CUDA(cudaFuncGetAttributes(&fa_, mu_group)); VL_CUDA(cudaFuncGetAttributes(&fa_, mz_collect));
   VL_CUDA(cudaFuncGetAttributes(&fa_, mz_layout_for_grid));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_fit_sets));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_transform_update));

@@ -250,7 +250,6 @@ __global__ void __launch_bounds__(LO_QPB * 32) lo_assoc(const float4* __restrict
 #define LOG_NY 256
 #define LOG_NZ 32
 #define LOG_NCELL (LOG_NX * LOG_NY * LOG_NZ)
-#define LOG_STRIDE (2 * LOG_NCELL + 4)  // ints per cell array (counts / starts / fill), a multiple of 4: 128-bit access in the scan
 #define LOG_INV 0.78125f     // 1 / 1.28
 #define LOG_NEAR1 1.5625f    // (1.25 m)^2 < cell^2: a minimum below this found in the 3x3x3 block is global
 #define LOG_NEAR2 6.25f      // (2.5 m)^2 < (2 cells)^2: same for the 5x5x5 block; the 9x9x9 block covers the 5 m gate
@@ -261,21 +260,35 @@ __device__ __forceinline__ int log_cx(float v) { return min(max((int)floorf((v -
 __device__ __forceinline__ int log_cz(float v) { return min(max((int)floorf((v - LOG_OZ) * LOG_INV), 0), LOG_NZ - 1); }
 __device__ __forceinline__ int log_cell(float x, float y, float z) { return log_cx(x) + LOG_NX * (log_cx(y) + LOG_NY * log_cz(z)); }
 
+// Round 1 counted into -- and scanned -- a dense array of 2 x 2.1M cells for ~56k points (16.8 MB read + zeroing + write per
+// sweep to index 0.9 MB of points).  The occupied cells (~25k) now live in an open-addressing hash table of H slots
+// (H >= 4 x points): slot = {cell id, count, start}; the counting sort runs over slots, the scan over H ints (0.5 MB).
+// Layout of one set (ints): hkey[H] | hcnt[H] | hfill[H] | hstart[H + 4]
+#define LOG_EMPTY 0xffffffffu
+struct LoHash { const unsigned* key; const int* cnt; const int* start; int mask; };
+__device__ __forceinline__ unsigned log_hash(unsigned id) { id ^= id >> 15; id *= 0x9E3779B1u; id ^= id >> 13; return id; }
+
 __global__ void __launch_bounds__(256) lo_grid_count(const float4* __restrict__ corner, int nc, const float4* __restrict__ surf, int ns,
-                                                     int* __restrict__ cellCount, int* __restrict__ cellOf) {
+                                                     unsigned* __restrict__ hkey, int* __restrict__ hcnt, int mask, int* __restrict__ slotOf) {
   VL_PDL_WAIT();
 
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= nc + ns) return;
   const int which = g >= nc;
   const float4 p = which ? surf[g - nc] : corner[g];
-  const int cell = which * LOG_NCELL + log_cell(p.x, p.y, p.z);
-  cellOf[g] = cell;
-  atomicAdd(&cellCount[cell], 1);
+  const unsigned id = (unsigned)(which * LOG_NCELL + log_cell(p.x, p.y, p.z));
+  unsigned h = log_hash(id) & (unsigned)mask;
+  for (;;) {
+    const unsigned prev = atomicCAS(&hkey[h], LOG_EMPTY, id);
+    if (prev == LOG_EMPTY || prev == id) break;
+    h = (h + 1) & (unsigned)mask;
+  }
+  slotOf[g] = (int)h;
+  atomicAdd(&hcnt[h], 1);
 }
 __global__ void __launch_bounds__(256) lo_grid_fill(const float4* __restrict__ corner, int nc, const float4* __restrict__ surf, int ns,
-                                                    const int* __restrict__ cellOf, const int* __restrict__ cellStart,
-                                                    int* __restrict__ cellFill, float4* __restrict__ sorted) {
+                                                    const int* __restrict__ slotOf, const int* __restrict__ hstart,
+                                                    int* __restrict__ hfill, float4* __restrict__ sorted) {
   VL_PDL_WAIT();
 
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -283,10 +296,20 @@ __global__ void __launch_bounds__(256) lo_grid_fill(const float4* __restrict__ c
   const int which = g >= nc;
   const int j = which ? g - nc : g;
   const float4 p = which ? surf[j] : corner[j];
-  const int cell = cellOf[g];
-  const int pos = cellStart[cell] + atomicAdd(&cellFill[cell], 1);
+  const int slot = slotOf[g];
+  const int pos = hstart[slot] + atomicAdd(&hfill[slot], 1);
   const unsigned v = (unsigned)min(max((int)p.w, 0), 255);
   sorted[pos] = make_float4(p.x, p.y, p.z, __uint_as_float((unsigned)j | (v << 24)));
+}
+// point range of one cell (empty when the cell holds nothing)
+__device__ __forceinline__ void log_lookup(const LoHash& H, unsigned id, int& beg, int& len) {
+  unsigned h = log_hash(id) & (unsigned)H.mask;
+  for (;;) {
+    const unsigned k = H.key[h];
+    if (k == id) { beg = H.start[h]; len = H.cnt[h]; return; }
+    if (k == LOG_EMPTY) { beg = 0; len = 0; return; }
+    h = (h + 1) & (unsigned)H.mask;
+  }
 }
 
 __device__ __forceinline__ Best warp_best_v(Best v, unsigned& tag, bool preferLow) {
@@ -303,24 +326,21 @@ __device__ __forceinline__ Best warp_best_v(Best v, unsigned& tag, bool preferLo
 // reference's forward scan then visits exactly {j > closest : ring_j <= id + 2} and the backward scan
 // {j < closest : ring_j >= id - 2}; candidates farther than 5 m can never win because the running
 // minima start at DISTANCE_SQ_THRESHOLD = 25).  One warp per query, two passes over its 27 cells.
-// Visit the (2R+1)^3 block of cells around (cx, cy, cz), R = 1, 2 or 4.  A block is (2R+1)^2 rows of
-// contiguous cells; lane r looks up the point range of row r (all cell-start reads in one memory latency;
-// the 81 rows of R = 4 take three rounds) and VL_WARP_VISIT_FLAT spreads the candidates of all rows over
+// Visit the (2R+1)^3 block of cells around (cx, cy, cz), R = 1, 2 or 4.  Lane r looks up the point range of cell r in the
+// hash of occupied cells (all look-ups of a round in ~one memory latency;
+// the 729 cells of R = 4 take 23 rounds, rare) and VL_WARP_VISIT_FLAT spreads the candidates of all cells over
 // the lanes.  A larger block simply revisits the smaller one: every update in the bodies below is an
 // idempotent minimum, and escalation only happens where the inner block was nearly empty.  BODY sees float4 t.
 #define LOG_VISIT(R, BODY)                                                                                   \
   do {                                                                                                       \
     const int side_ = 2 * (R) + 1;                                                                           \
-    for (int r0_ = 0; r0_ < side_ * side_; r0_ += 32) {                                                      \
+    for (int r0_ = 0; r0_ < side_ * side_ * side_; r0_ += 32) {                                              \
       const int rr_ = r0_ + lane;                                                                            \
       int beg_ = 0, len_ = 0;                                                                                \
-      if (rr_ < side_ * side_) {                                                                             \
-        const int zz_ = cz + rr_ / side_ - (R), yy_ = cy + rr_ % side_ - (R);                                \
-        if (zz_ >= 0 && zz_ < LOG_NZ && yy_ >= 0 && yy_ < LOG_NY) {                                          \
-          const int row_ = cellBase + LOG_NX * (yy_ + LOG_NY * zz_);                                         \
-          beg_ = cellStart[row_ + max(cx - (R), 0)];                                                         \
-          len_ = cellStart[row_ + min(cx + (R), LOG_NX - 1) + 1] - beg_;                                     \
-        }                                                                                                    \
+      if (rr_ < side_ * side_ * side_) {                                                                     \
+        const int xx_ = cx + rr_ % side_ - (R), yy_ = cy + (rr_ / side_) % side_ - (R), zz_ = cz + rr_ / (side_ * side_) - (R); \
+        if (zz_ >= 0 && zz_ < LOG_NZ && yy_ >= 0 && yy_ < LOG_NY && xx_ >= 0 && xx_ < LOG_NX)                \
+          log_lookup(H, (unsigned)(cellBase + xx_ + LOG_NX * (yy_ + LOG_NY * zz_)), beg_, len_);            \
       }                                                                                                      \
       VL_WARP_VISIT_FLAT(beg_, len_, lane, sorted, BODY);                                                    \
     }                                                                                                        \
@@ -334,7 +354,7 @@ __device__ int* g_lo_trace = nullptr;  // debug: per query warp {cycles, flags: 
 
 template <bool SURF>
 __device__ __forceinline__ void lo_assoc_grid_dev(int qi, int lane, const float4* __restrict__ query, const float4* __restrict__ target,
-                                                  const float4* __restrict__ sorted, const int* __restrict__ cellStart,
+                                                  const float4* __restrict__ sorted, const LoHash H,
                                                   const double* __restrict__ pose, int* __restrict__ outIdx,
                                                   double* __restrict__ factors, int* __restrict__ valid, int slotBase, double* __restrict__ factorS) {
   const long long tr0 = g_lo_trace ? clock64() : 0;
@@ -456,7 +476,7 @@ __device__ __forceinline__ void lo_assoc_grid_dev(int qi, int lane, const float4
 
 template <bool SURF>
 __global__ void __launch_bounds__(256) lo_assoc_grid(const float4* __restrict__ query, int nq, const float4* __restrict__ target,
-                                                     const float4* __restrict__ sorted, const int* __restrict__ cellStart,
+                                                     const float4* __restrict__ sorted, const LoHash H,
                                                      const double* __restrict__ pose, int* __restrict__ outIdx,
                                                      double* __restrict__ factors, int* __restrict__ valid, int slotBase, double* __restrict__ factorS) {
   VL_PDL_WAIT();
@@ -464,13 +484,13 @@ __global__ void __launch_bounds__(256) lo_assoc_grid(const float4* __restrict__ 
   const int lane = threadIdx.x & 31;
   const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (qi >= nq) return;
-  lo_assoc_grid_dev<SURF>(qi, lane, query, target, sorted, cellStart, pose, outIdx, factors, valid, slotBase, factorS);
+  lo_assoc_grid_dev<SURF>(qi, lane, query, target, sorted, H, pose, outIdx, factors, valid, slotBase, factorS);
 }
 
 // sharp and flat queries in one launch: warps [0, nS) run the corner association, [nS, nS + nF) the surf one
 __global__ void __launch_bounds__(256) lo_assoc_grid_both(const float4* __restrict__ sharp, const float4* __restrict__ flat, int slotBound,
                                                           const SrScalars* __restrict__ srs, const float4* __restrict__ cornerLast, const float4* __restrict__ surfLast,
-                                                          const float4* __restrict__ sorted, const int* __restrict__ cellStart,
+                                                          const float4* __restrict__ sorted, const LoHash H,
                                                           const double* __restrict__ pose, int* __restrict__ cornerIdx, int* __restrict__ surfIdx,
                                                           double* __restrict__ factors, int* __restrict__ valid, double* __restrict__ factorS) {
   VL_PDL_WAIT();
@@ -479,8 +499,8 @@ __global__ void __launch_bounds__(256) lo_assoc_grid_both(const float4* __restri
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nS = srs->nSharp, nF = srs->nFlat;  // device-side counts: the host may not know them yet
   if (w >= nS + nF) { if (w < slotBound && lane == 0) valid[w] = 0; return; }
-  if (w < nS) lo_assoc_grid_dev<false>(w, lane, sharp, cornerLast, sorted, cellStart, pose, cornerIdx, factors, valid, 0, factorS);
-  else if (w < nS + nF) lo_assoc_grid_dev<true>(w - nS, lane, flat, surfLast, sorted, cellStart, pose, surfIdx, factors, valid, nS, factorS);
+  if (w < nS) lo_assoc_grid_dev<false>(w, lane, sharp, cornerLast, sorted, H, pose, cornerIdx, factors, valid, 0, factorS);
+  else if (w < nS + nF) lo_assoc_grid_dev<true>(w - nS, lane, flat, surfLast, sorted, H, pose, surfIdx, factors, valid, nS, factorS);
 }
 
 __global__ void lo_accumulate(LoScalars* s) {
@@ -507,23 +527,29 @@ __global__ void lo_set_prior(LoScalars* s, const double* __restrict__ prior) {
 // copied to pinned host memory; the next frame's first sync point makes them readable.
 int vl_lo_build_last(vloam_b200_ctx* c, int set, const float4* corner, int nc, const float4* surf, int ns) {
   const int n = nc + ns;
+  cudaStream_t st = VL_STREAM(c);  // (the caller selects the side stream through vl_tls_stream: the helper thread may be the one issuing this)
   // set `set` was searched by the odometry solve before the current one: rebuild it only behind the solves queued so far
-  VL_CUDA(cudaStreamWaitEvent(c->stream, c->evLoSolve, 0));
+  VL_CUDA(cudaStreamWaitEvent(st, c->evLoSolve, 0));
   int* tbl = c->loRingTbl + set * 2 * (LO_TBL + 1);
   VL_LAUNCH(lo_ring_table_init, 1, 32, 0, tbl);
   VL_LAUNCH(lo_ring_table, dim3(vl_div_up(max(max(nc, ns), LO_TBL + 1), 256), 2), 256, 0, corner, nc, surf, ns, tbl);
-  VL_CUDA(cudaMemcpyAsync(&c->h_vScalars[8 + 2 * set], tbl + LO_TBL, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  VL_CUDA(cudaMemcpyAsync(&c->h_vScalars[9 + 2 * set], tbl + (LO_TBL + 1) + LO_TBL, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  VL_TRY(vl_reserve(c, c->loGridCells[set], (size_t)3 * LOG_STRIDE));  // counts, starts, fill (16-byte aligned each)
-  VL_TRY(vl_scan_alloc(&c->loScan[set], 2 * LOG_NCELL));
+  VL_CUDA(cudaMemcpyAsync(&c->h_vScalars[8 + 2 * set], tbl + LO_TBL, sizeof(int), cudaMemcpyDeviceToHost, st));
+  VL_CUDA(cudaMemcpyAsync(&c->h_vScalars[9 + 2 * set], tbl + (LO_TBL + 1) + LO_TBL, sizeof(int), cudaMemcpyDeviceToHost, st));
+  // hash of occupied cells: H >= 4 x points slots; ints: hkey[H] | hcnt[H] | hfill[H] | hstart[H + 4]
+  int H = 1 << 17; while (H < 4 * n) H <<= 1;
+  VL_TRY(vl_reserve(c, c->loGridCells[set], (size_t)4 * H + 4));
+  VL_TRY(vl_scan_alloc(&c->loScan[set], H));
+  c->loGridMask[set] = H - 1;
   VL_TRY(vl_reserve(c, c->loGridCellOf, (size_t)max(n, 1), false, (size_t)n / 2));
   VL_TRY(vl_reserve(c, c->loGridSorted[set], (size_t)max(n, 1), false, (size_t)n / 2));
   if (n > 0 && n < (1 << 24)) {
-    int* cnt = c->loGridCells[set].p; int* start = cnt + LOG_STRIDE; int* fill = start + LOG_STRIDE;
-    VL_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * (2 * LOG_NCELL + 1), c->stream));
-    VL_CUDA(cudaMemsetAsync(fill, 0, sizeof(int) * (2 * LOG_NCELL + 1), c->stream));
-    VL_LAUNCH(lo_grid_count, vl_div_up(n, 256), 256, 0, corner, nc, surf, ns, cnt, c->loGridCellOf.p);
-    VL_TRY(vl_scan_exclusive(c, cnt, 2 * LOG_NCELL, &c->loScan[set], start));
+    unsigned* hkey = reinterpret_cast<unsigned*>(c->loGridCells[set].p); int* cnt = c->loGridCells[set].p + H; int* fill = cnt + H; int* start = fill + H;
+    VL_CUDA(cudaMemsetAsync(hkey, 0xff, sizeof(int) * H, st));
+    VL_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * 2 * H, st));  // counts and fill cursors
+    VL_BYTES(16.0 * n);  // SURVEY 8(d) B_lo: the clouds that become "last" are read once to build their search structure
+    VL_LAUNCH(lo_grid_count, vl_div_up(n, 256), 256, 0, corner, nc, surf, ns, hkey, cnt, H - 1, c->loGridCellOf.p);
+    VL_TRY(vl_scan_exclusive(c, cnt, H, &c->loScan[set], start));
+    VL_BYTES(32.0 * n);
     VL_LAUNCH(lo_grid_fill, vl_div_up(n, 256), 256, 0, corner, nc, surf, ns, c->loGridCellOf.p, start, fill, c->loGridSorted[set].p);
     c->loGridValid[set] = true;
   } else c->loGridValid[set] = false;
@@ -547,7 +573,9 @@ static int lo_associate(vloam_b200_ctx* c, const double* d_pose, const float4* c
   const int set = c->lastSet;
   const bool gridC = c->loGridValid[set] && (c->loAssumeMonotone || c->h_vScalars[8 + 2 * set] != 0);
   const bool gridS = c->loGridValid[set] && (c->loAssumeMonotone || c->h_vScalars[9 + 2 * set] != 0);
-  const int* start = c->loGridCells[set].p ? c->loGridCells[set].p + LOG_STRIDE : nullptr;
+  LoHash start;  // (hash of the occupied cells of set `set`: keys, counts, starts)
+  { const int H = c->loGridMask[set] + 1; const int* b = c->loGridCells[set].p;
+    start.key = reinterpret_cast<const unsigned*>(b); start.cnt = b ? b + H : nullptr; start.start = b ? b + 3 * H : nullptr; start.mask = H - 1; }
   const float4* gsorted = c->loGridSorted[set].p;
   const int* rtbl = c->loRingTbl + set * 2 * (LO_TBL + 1);
   if (gridC && gridS && nS + nF > 0) {
@@ -627,7 +655,7 @@ static int lo_queue_solve(vloam_b200_ctx* c, const double* prior_q, const double
       }
       const int nslots = c->sr_counts_valid ? c->nSharp + c->nFlat : lo_sharp_bound(c) + lo_flat_bound(c);
       VL_TRY(vl_solve_buf(c, c->loFactors.p, c->loFactorValid.p, nslots, &c->srs->nQueries, d_pose, vl_debug_capture(c) ? &c->dbgLoCost[pass * 2] : nullptr,
-                          c->nSharp + c->nFlat, vl_distortion(c) ? c->factorS.p : nullptr));
+                          c->nSharp + c->nFlat, vl_distortion(c) ? c->factorS.p : nullptr, 8));
     }
     VL_LAUNCH(lo_accumulate, 1, 32, 0, c->los);
   VL_CUDA(cudaEventRecord(c->evLoSolve, VL_STREAM(c)));
@@ -639,9 +667,11 @@ static int lo_queue_solve(vloam_b200_ctx* c, const double* prior_q, const double
 // decide -- the "last" clouds and their search structures are this sweep's (evLast), the counts are read on the
 // device -- so it is queued now, behind this sweep's mapping, on a COPY of the odometry state.  The next
 // laser_odometry call adopts the copy if it is for that sweep and ignores it otherwise.
-int vl_lo_lookahead(vloam_b200_ctx* c) {
+// Part 1 (vl_lo_lookahead_solve) queues the solve; part 2 (vl_lo_lookahead_stacks), called after sync point S2 has been recorded, issues the next
+// sweep's stack filters if its scan registration finishes before this sweep's mapping does.
+int vl_lo_lookahead_solve(vloam_b200_ctx* c) {
   static const bool off = getenv("VLOAM_NO_LO_LOOKAHEAD") != nullptr;
-  c->loNextValid = false;
+  c->loNextValid = false; c->loNextQueued = false;
   VL_TRY(vl_lo_flush_deferred(c));  // (records evLast)
   if (off || !c->srNextValid || !c->lo_inited || c->prof_name[0] || vl_debug_capture(c)) return VLOAM_OK;
   // The structures over this sweep's clouds are still being built on the side stream: wait for them on the DEVICE and
@@ -650,10 +680,11 @@ int vl_lo_lookahead(vloam_b200_ctx* c) {
   const int set = c->lastSet;
   if (!c->loGridValid[set]) return VLOAM_OK;
   // It runs on its own stream, BESIDE this sweep's mapping (own factor slots): it needs this sweep's odometry result (evLoSolve),
-  // the structures over this sweep's clouds (evLast) and the next sweep's features (evSR) -- nothing of the mapping.
+  // the structures over this sweep's clouds (evLast) and the next sweep's features (evSRfeat) -- nothing of the mapping.
   VL_CUDA(cudaStreamWaitEvent(c->streamLO, c->evLoSolve, 0));
   VL_CUDA(cudaStreamWaitEvent(c->streamLO, c->evLast, 0));
-  VL_CUDA(cudaStreamWaitEvent(c->streamLO, c->srNext->evSR, 0));
+  VL_CUDA(cudaStreamWaitEvent(c->streamLO, c->srNext->evSRfeat, 0));  // (sharp + flat of the next sweep: not its per-ring voxel filter)
+  if (c->timing) cudaEventRecord(c->evx[9], c->streamLO);
   VL_CUDA(cudaMemcpyAsync(c->losNext, c->los, sizeof(LoScalars), cudaMemcpyDeviceToDevice, c->streamLO));
   const int curNow = c->cur;
   vl_sr_swap(c, *c->srNext);
@@ -663,16 +694,27 @@ int vl_lo_lookahead(vloam_b200_ctx* c) {
   int r = lo_queue_solve(c, nullptr, nullptr, 0);  // (host counts of that sweep not known yet: bounds, the kernels read the counts on the device)
   vl_tls_stream = nullptr;
   if (r == VLOAM_OK && cudaEventRecord(c->evLoNext, c->streamLO) != cudaSuccess) r = VLOAM_E_CUDA;
+  if (c->timing) cudaEventRecord(c->evx[6], c->streamLO);
   c->loAssumeMonotone = false;
   { LoScalars* t_ = c->los; c->los = c->losNext; c->losNext = t_; }
+  vl_sr_swap(c, *c->srNext);
+  c->cur = curNow;
+  if (r != VLOAM_OK) return r;
+  c->loNextQueued = true; c->loNextSet = set;
+  return VLOAM_OK;
+}
+int vl_lo_lookahead_stacks(vloam_b200_ctx* c) {
+  if (!c->loNextQueued) return VLOAM_OK;
+  c->loNextQueued = false;
   // The host only waits for S2 from here on.  If the look-ahead scan registration finishes before this sweep's mapping
   // does, the next sweep's stack filters (LM.cpp:492-500) are issued now as well, into the spare stack buffers.
   const bool mapNext = ((c->lo_frameCount + 1) % c->prm.mapping_skip_frame) == 0;
   static const bool noStacksNext = getenv("VLOAM_NO_STACKS_LOOKAHEAD") != nullptr;
   bool srDone = false;
-  if (r == VLOAM_OK && mapNext && !noStacksNext) {
+  int r = VLOAM_OK;
+  if (mapNext && !noStacksNext) {
     for (;;) {
-      cudaError_t e = cudaEventQuery(c->evSR);
+      cudaError_t e = cudaEventQuery(c->srNext->evSR);
       if (e == cudaSuccess) { srDone = true; break; }
       if (e != cudaErrorNotReady) break;                  // a real error: the next checked call reports it
       e = cudaEventQuery(c->evS2);
@@ -680,30 +722,51 @@ int vl_lo_lookahead(vloam_b200_ctx* c) {
     }
     (void)cudaGetLastError();  // (cudaErrorNotReady is a status, not a failure: do not leave it for the next cudaGetLastError check)
   }
-  const float4* nCorner = nullptr; const float4* nSurf = nullptr; int nNc = 0, nNs = 0;
   if (srDone) {
+    const int curNow = c->cur;
+    vl_sr_swap(c, *c->srNext);
     r = vl_sr_sync_counts(c);
-    nCorner = c->lessSharp[c->cur].p; nNc = c->nLessSharp; nSurf = c->lessFlat[c->cur].p; nNs = c->nLessFlat;
+    const float4* nCorner = c->lessSharp[c->cur].p; const int nNc = c->nLessSharp; const float4* nSurf = c->lessFlat[c->cur].p; const int nNs = c->nLessFlat;
+    vl_sr_swap(c, *c->srNext);
+    c->cur = curNow;
+    if (r == VLOAM_OK) r = vl_lm_enqueue_stacks_next(c, nCorner, nNc, nSurf, nNs);
   }
-  vl_sr_swap(c, *c->srNext);
-  c->cur = curNow;
-  if (r == VLOAM_OK && srDone) r = vl_lm_enqueue_stacks_next(c, nCorner, nNc, nSurf, nNs);
   if (r != VLOAM_OK) return r;
-  c->loNextValid = true; c->loNextSet = set;
+  c->loNextValid = true;
   return VLOAM_OK;
 }
+int vl_lo_lookahead(vloam_b200_ctx* c) {
+  VL_TRY(vl_lo_lookahead_solve(c));
+  return vl_lo_lookahead_stacks(c);
+}
 
-int vl_lo_flush_deferred(vloam_b200_ctx* c) {
-  if (!c->loDeferred) return VLOAM_OK;
-  c->loDeferred = false;
-  cudaStream_t mainStream = c->stream;
-  c->stream = c->stream2;
-  const int r = vl_lo_build_last(c, c->defSet, c->defCorner, c->defNc, c->defSurf, c->defNs);
-  c->stream = mainStream;
-  if (r != VLOAM_OK) return r;
-  VL_CUDA(cudaEventRecord(c->evLast, c->stream2));
-  if (c->timing) VL_CUDA(cudaEventRecord(c->evx[5], c->stream2));
+// The side-stream work a look-ahead replay defers out of the odometry call: the registered next sweep's upload + scan
+// registration (streamSR) and the search structures over this sweep's clouds (stream2).  Thread-agnostic: the helper thread runs it
+// while the caller queues the mapping stage (vl_lo_submit_side), or the caller itself (vl_lo_flush_deferred).
+int vl_lo_side_work(vloam_b200_ctx* c) {
+  int r = VLOAM_OK;
+  if (c->srDeferred) { c->srDeferred = false; r = vl_launch_lookahead(c); }
+  if (r == VLOAM_OK && c->loDeferred) {
+    c->loDeferred = false;
+    cudaStream_t prev = vl_tls_stream;
+    vl_tls_stream = c->stream2;
+    r = vl_lo_build_last(c, c->defSet, c->defCorner, c->defNc, c->defSurf, c->defNs);
+    vl_tls_stream = prev;
+    if (r != VLOAM_OK) return r;
+    VL_CUDA(cudaEventRecord(c->evLast, c->stream2));
+    if (c->timing) VL_CUDA(cudaEventRecord(c->evx[5], c->stream2));
+  }
+  return r;
+}
+int vl_lo_submit_side(vloam_b200_ctx* c) {
+  if (!c->srDeferred && !c->loDeferred) return VLOAM_OK;
+  VL_TRY(vl_lm_submit_task(c, vl_lo_side_work));
+  c->sideSubmitted = true;
   return VLOAM_OK;
+}
+int vl_lo_flush_deferred(vloam_b200_ctx* c) {
+  if (c->sideSubmitted) { c->sideSubmitted = false; VL_TRY(vl_lm_join(c)); }  // the helper thread has it: wait until it is issued
+  return vl_lo_side_work(c);
 }
 
 int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, int use_prior) {
@@ -738,8 +801,13 @@ int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, i
   // With the solve adopted, the stacks queued and the mapping stage following in the same call, nothing on the pose
   // chain depends on the search structures of the next "last" clouds: they are queued by the mapping stage right after
   // its own launches (vl_lo_flush_deferred).
-  const bool defer = adoptLO && stacksQueued && c->inProcessFrame;
-  VL_TRY(vl_launch_lookahead(c));  // the next sweep's scan registration, if one is registered, goes to its side stream now
+  // (round 1 queued them after the mapping launches to keep the main stream's launch latency low; now the look-ahead odometry of the
+  // NEXT sweep runs beside this sweep's mapping and waits for exactly these structures, while the mapping itself waits for the previous
+  // map update anyway: they are issued at once.  VLOAM_DEFER_LO_GRIDS=1 restores the old order.)
+  static const bool noSide = getenv("VLOAM_NO_SIDE_DEFER") != nullptr;
+  const bool defer = !noSide && adoptLO && stacksQueued && c->inProcessFrame && mapThisFrame;
+  if (defer) c->srDeferred = c->srPendKey != nullptr;  // ... and so is the next sweep's scan registration: the helper thread issues both while the caller queues the mapping
+  else VL_TRY(vl_launch_lookahead(c));  // the next sweep's scan registration, if one is registered, goes to its side stream now
   VL_HOST_MARK(2);
   VL_TRY(vl_sr_sync_counts(c));  // sync point S1 (event after scan registration; the odometry above is already queued)
   if (mapThisFrame && !stacksQueued)
@@ -750,10 +818,9 @@ int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, i
   } else {  // LO.cpp:573-574 (setInputCloud on both KD-trees) for the clouds that become "last" after this solve:
      // they are this frame's less-sharp / less-flat clouds, final since scan registration, so the side
      // stream builds them while the odometry still searches the previous set
-    cudaStream_t mainStream = c->stream;
-    c->stream = c->stream2;
+    vl_tls_stream = c->stream2;
     const int r = vl_lo_build_last(c, c->lastSet ^ 1, c->lessSharp[c->cur].p, c->nLessSharp, c->lessFlat[c->cur].p, c->nLessFlat);
-    c->stream = mainStream;
+    vl_tls_stream = nullptr;
     if (r != VLOAM_OK) return r;
     VL_CUDA(cudaEventRecord(c->evLast, c->stream2));
     if (c->timing) VL_CUDA(cudaEventRecord(c->evx[5], c->stream2));

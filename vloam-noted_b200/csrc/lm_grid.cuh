@@ -53,10 +53,10 @@ struct LgGrid {  // passed by value to kernels
   LgHeader* hdr;
 };
 
-struct LgOp { float4 p; unsigned long long key; int cell; int pos; };  // pending insert (pos: posOf of a moved entry, -1 for a new voxel)
-
 // Append one entry to a cell.  The position is claimed with one atomic; the chain is extended with a CAS (a thread that
-// loses the race leaks its chunk: the bump allocator is reset at the next rebuild).  Readers only run in later kernels.
+// loses the race leaks its chunk: the bump allocator is reset at the next rebuild).  A new chunk is filled with tombstone
+// keys BEFORE it is published, so a thread that scans a cell while another one appends to it reads either a dead key or
+// a finished one (8-byte stores are atomic): the in-place update can look voxels up and insert new ones in one kernel.
 __device__ __forceinline__ int lg_insert(const LgGrid& g, int cell, const float4 p, unsigned long long key, int poolPos) {
   int2* d = &g.dir[cell];
   const int pos = atomicAdd(&d->x, 1);
@@ -70,6 +70,9 @@ __device__ __forceinline__ int lg_insert(const LgGrid& g, int cell, const float4
       if (nw >= g.cap) { g.hdr->dirty = 1; return -1; }  // cannot happen when the host sized the chunk pool (it bounds the demand before every launch);
                                                          // the claimed slot stays unwritten, `dirty` forces a rebuild before the next read
       g.next[nw] = -1;
+      ulonglong2* kk = reinterpret_cast<ulonglong2*>(g.key + (size_t)nw * LG_C);
+#pragma unroll
+      for (int q = 0; q < LG_C / 2; ++q) kk[q] = make_ulonglong2(LG_DEAD, LG_DEAD);
       __threadfence();
       const int old = atomicCAS(link, -1, nw);
       cur = old < 0 ? nw : old;
@@ -79,8 +82,9 @@ __device__ __forceinline__ int lg_insert(const LgGrid& g, int cell, const float4
   }
   const int e = chunk * LG_C + (pos % LG_C);
   g.pts[e] = p;
-  g.key[e] = key;
   g.posOf[e] = poolPos;
+  // (no fence: a concurrent scanner only ever reads pts[] of the entry whose key it was looking for, and this key is another voxel's)
+  *(volatile unsigned long long*)&g.key[e] = key;
   return e;
 }
 

@@ -527,7 +527,9 @@ __device__ __forceinline__ void lm_warp_transpose_reduce(double (&v)[32], int la
 // FPT: factor slots held in registers per thread (0 = read them from memory at every evaluation).
 // Slot i belongs to CTA i % 16 (thread (i / 16) % THREADS): the edge factors, which cost three times a
 // plane factor and sit at the front of the slot array, are spread evenly over the CTAs.
-template <int FPT, int THREADS>
+// NCTA: CTAs of the cluster -- 16 (non-portable maximum: a whole GPC) for the mapping stage's ~7000 factors, 8 for the odometry's ~1800
+// (a cluster of 8 is placed as soon as 8 SMs of a GPC are free: the look-ahead odometry runs beside the mapping stage's wide kernels).
+template <int FPT, int THREADS, int NCTA>
 __global__ void __launch_bounds__(THREADS, LMC_MIN_CTAS)
 lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ valid, int nslotsBound, const int* __restrict__ d_nslots,
                  double* __restrict__ x_inout, LmSolveState* __restrict__ st_out, long long* __restrict__ trace, const double* __restrict__ sArr) {
@@ -541,7 +543,7 @@ lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ val
   if (FPT > 0) {
 #pragma unroll
     for (int j = 0; j < FPT; ++j) {
-      const int i = (j * THREADS + threadIdx.x) * LMC_CTAS + (int)rank;
+      const int i = (j * THREADS + threadIdx.x) * NCTA + (int)rank;
       const bool inb = i < nslotsBound;
       vflag[j] = inb ? valid[i] : 0;
 #pragma unroll
@@ -552,7 +554,7 @@ lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ val
   if (nslots <= 0) return;  // no residual blocks: Ceres leaves the parameters untouched (uniform over the cluster)
   __shared__ double part[2][28];
   __shared__ double red[THREADS / 32][28];
-  __shared__ double gath[LMC_CTAS][28];
+  __shared__ double gath[NCTA][28];
   __shared__ double xnext[8];
   __shared__ double best[7];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -571,12 +573,12 @@ lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ val
   if (lane < 21) { int t = lane, i = 0; while (t >= 6 - i) { t -= 6 - i; ++i; } S.li = i; S.lj = i + t; }
   else if (lane < 27) S.li = lane - 21;
   // the host picks FPT from a hint (last frame's count); the actual count decides here, uniformly over the cluster
-  const bool inreg = FPT > 0 && nslots <= FPT * THREADS * LMC_CTAS;
+  const bool inreg = FPT > 0 && nslots <= FPT * THREADS * NCTA;
   LmFactorReg fr_[FPT > 0 ? FPT : 1];
   if (inreg) {
 #pragma unroll
     for (int j = 0; j < FPT; ++j) {
-      const int i = (j * THREADS + threadIdx.x) * LMC_CTAS + (int)rank;
+      const int i = (j * THREADS + threadIdx.x) * NCTA + (int)rank;
       lm_factor_load(raw[j], i < nslots && vflag[j] != 0, fr_[j]);
     }
   }
@@ -595,7 +597,7 @@ lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ val
         lm_accumulate(fr, acc);
       }
     } else {
-      for (int i = threadIdx.x * LMC_CTAS + (int)rank; i < nslots; i += THREADS * LMC_CTAS) {
+      for (int i = threadIdx.x * NCTA + (int)rank; i < nslots; i += THREADS * NCTA) {
         if (!valid[i]) continue;
         FactorRow fr;
         if (FPT == 0 && sArr && (int)factors[(size_t)i * 10] != 2) lm_factor_deskew(factors + (size_t)i * 10, sArr[i], x, fr);  // DISTORTION: only the streaming variant
@@ -617,7 +619,7 @@ lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ val
     if (it == LM_TRACE_IT) LM_TRACE(3);
     cluster.sync();  // every CTA's partial of this evaluation is visible cluster-wide
     if (it == LM_TRACE_IT) LM_TRACE(4);
-    for (int t = threadIdx.x; t < 28 * LMC_CTAS; t += THREADS) {
+    for (int t = threadIdx.x; t < 28 * NCTA; t += THREADS) {
       const int r = t / 28, k = t - r * 28;
       gath[r][k] = cluster.map_shared_rank(mine, r)[k];
     }
@@ -627,7 +629,7 @@ lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ val
       double v = 0;
       if (lane < 28) {
 #pragma unroll
-        for (int r = 0; r < LMC_CTAS; ++r) v += gath[r][lane];  // rank order: deterministic
+        for (int r = 0; r < NCTA; ++r) v += gath[r][lane];  // rank order: deterministic
       }
       lm_logic_warp(S, v, lane, best, (it == LM_TRACE_IT && rank == 0) ? trace : nullptr);
       if (lane == 0) {
@@ -663,35 +665,39 @@ int vl_solver_trace(vloam_b200_ctx* c, long long* out16) {
   return VLOAM_OK;
 }
 
-template <int FPT, int THREADS>
+template <int FPT, int THREADS, int NCTA = LMC_CTAS>
 static cudaError_t lm_launch(cudaLaunchConfig_t& cfg, const double* cf, const int* cv, int nslots, const int* d_nslots, double* x,
                              LmSolveState* so, long long* trace, const double* sArr = nullptr) {
   cfg.blockDim = dim3(THREADS);
-  return cudaLaunchKernelEx(&cfg, lm_solve_cluster<FPT, THREADS>, cf, cv, nslots, d_nslots, x, so, trace, sArr);
+  cfg.gridDim = dim3(NCTA);
+  cfg.attrs[0].val.clusterDim.x = NCTA;
+  return cudaLaunchKernelEx(&cfg, lm_solve_cluster<FPT, THREADS, NCTA>, cf, cv, nslots, d_nslots, x, so, trace, sArr);
 }
 
 // function attributes are per device: set when a context is created on it (vloam_b200_create)
 int vl_solver_set_attrs(vloam_b200_ctx* c) {
-  VL_CUDA(cudaFuncSetAttribute(lm_solve_cluster<1, 256>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  VL_CUDA(cudaFuncSetAttribute(lm_solve_cluster<2, 256>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  VL_CUDA(cudaFuncSetAttribute(lm_solve_cluster<4, 256>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  VL_CUDA(cudaFuncSetAttribute(lm_solve_cluster<0, 256>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  VL_CUDA(cudaFuncSetAttribute((lm_solve_cluster<1, 256, 16>), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  VL_CUDA(cudaFuncSetAttribute((lm_solve_cluster<2, 256, 16>), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  VL_CUDA(cudaFuncSetAttribute((lm_solve_cluster<4, 256, 16>), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  VL_CUDA(cudaFuncSetAttribute((lm_solve_cluster<0, 256, 16>), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   // lazy module loading would otherwise charge each kernel's first launch (~1 ms apiece) to the first sweeps
   cudaFuncAttributes fa_;
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_eval));
-  VL_CUDA(cudaFuncGetAttributes(&fa_, (lm_solve_cluster<1, 256>)));
-  VL_CUDA(cudaFuncGetAttributes(&fa_, (lm_solve_cluster<2, 256>)));
-  VL_CUDA(cudaFuncGetAttributes(&fa_, (lm_solve_cluster<4, 256>)));
-  VL_CUDA(cudaFuncGetAttributes(&fa_, (lm_solve_cluster<0, 256>)));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, (lm_solve_cluster<1, 256, 16>)));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, (lm_solve_cluster<2, 256, 16>)));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, (lm_solve_cluster<4, 256, 16>)));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, (lm_solve_cluster<0, 256, 16>)));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, (lm_solve_cluster<1, 256, 8>)));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, (lm_solve_cluster<2, 256, 8>)));
   return VLOAM_OK;
 }
 
 int vl_solve(vloam_b200_ctx* c, int nslots, const int* d_nslots, double* d_x_inout, double* costs2, int hint, const double* d_s) {
-  return vl_solve_buf(c, c->factors.p, c->factorValid.p, nslots, d_nslots, d_x_inout, costs2, hint, d_s);
+  return vl_solve_buf(c, c->factors.p, c->factorValid.p, nslots, d_nslots, d_x_inout, costs2, hint, d_s, 16);
 }
 
 int vl_solve_buf(vloam_b200_ctx* c, const double* cf, const int* cv, int nslots, const int* d_nslots, double* d_x_inout, double* costs2, int hint,
-                 const double* d_s) {
+                 const double* d_s, int ncta) {
   cudaStream_t st = VL_STREAM(c);
   if (nslots > 0) {
     cudaLaunchConfig_t cfg = {};
@@ -711,6 +717,11 @@ int vl_solve_buf(vloam_b200_ctx* c, const double* cf, const int* cv, int nslots,
     // actual count exceeds it streams the factors from memory at every evaluation instead.
     const int est = hint > 0 ? min(nslots, hint + hint / 32 + 64) : nslots;  // counts move by a few per cent between sweeps; a miss only costs speed
     if (d_s) VL_CUDA((lm_launch<0, 256>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr, d_s)));  // DISTORTION: factors + s streamed from memory
+    // The cluster size fixes the order of the sums (slot i belongs to CTA i % NCTA), so it must not follow the hint: the caller
+    // names it -- 8 for the odometry stage, whichever path (plain or look-ahead, with different hints) queues the solve.  The
+    // register variants of one cluster size are bit-identical to each other.
+    else if (ncta == 8 && est <= 8 * 256) VL_CUDA((lm_launch<1, 256, 8>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr)));
+    else if (ncta == 8) VL_CUDA((lm_launch<2, 256, 8>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr)));  // (streams from memory above 4096 slots)
     else if (est <= LMC_CTAS * 256) VL_CUDA((lm_launch<1, 256>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr)));
     else if (est <= LMC_CTAS * 512) VL_CUDA((lm_launch<2, 256>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr)));
     else if (est <= LMC_CTAS * 1024) VL_CUDA((lm_launch<4, 256>(cfg, cf, cv, nslots, d_nslots, d_x_inout, so, tr)));

@@ -779,7 +779,9 @@ __global__ void __launch_bounds__(SR_PICK_THREADS) sr_ring_voxel(const float4* _
 
 // Exclusive scans of the pick counts (ring-major, sector, pick order = the reference's
 // push_back order) and of the per-ring DS counts.
-__global__ void __launch_bounds__(1024) sr_offsets(int nscans, const int* __restrict__ cntSharp, const int* __restrict__ cntLess,
+// phase 1: the three pick-based clouds (all the odometry of this sweep needs: it may start before the per-ring voxel filter
+// has run); phase 2: the per-ring downsampled less-flat cloud.
+__global__ void __launch_bounds__(1024) sr_offsets(int nscans, int phase, const int* __restrict__ cntSharp, const int* __restrict__ cntLess,
                                                    const int* __restrict__ cntFlat, const int* __restrict__ dsCount,
                                                    int* __restrict__ offSharp, int* __restrict__ offLess, int* __restrict__ offFlat,
                                                    int* __restrict__ dsOff, SrScalars* __restrict__ s) {
@@ -788,16 +790,22 @@ __global__ void __launch_bounds__(1024) sr_offsets(int nscans, const int* __rest
   __shared__ int ws[32];
   const int t = threadIdx.x;
   const int nslots = nscans * VL_SECTORS;
-  const int own[4] = {t < nslots ? cntSharp[t] : 0, t < nslots ? cntLess[t] : 0, t < nslots ? cntFlat[t] : 0, t < nscans ? dsCount[t] : 0};
-  int ex[4], tot[4];
+  if (phase == 1) {
+    const int own[3] = {t < nslots ? cntSharp[t] : 0, t < nslots ? cntLess[t] : 0, t < nslots ? cntFlat[t] : 0};
+    int ex[3], tot[3];
 #pragma unroll
-  for (int a = 0; a < 4; ++a) ex[a] = vl_block_excl_scan<1024>(own[a], ws, &tot[a]);
-  if (t < nslots) { offSharp[t] = ex[0]; offLess[t] = ex[1]; offFlat[t] = ex[2]; }
-  if (t < nscans) dsOff[t] = ex[3];
-  if (t == 0) { s->nSharp = tot[0]; s->nLessSharp = tot[1]; s->nFlat = tot[2]; s->nLessFlat = tot[3]; s->nQueries = tot[0] + tot[2]; }
+    for (int a = 0; a < 3; ++a) ex[a] = vl_block_excl_scan<1024>(own[a], ws, &tot[a]);
+    if (t < nslots) { offSharp[t] = ex[0]; offLess[t] = ex[1]; offFlat[t] = ex[2]; }
+    if (t == 0) { s->nSharp = tot[0]; s->nLessSharp = tot[1]; s->nFlat = tot[2]; s->nQueries = tot[0] + tot[2]; }
+  } else {
+    int tot = 0;
+    const int ex = vl_block_excl_scan<1024>(t < nscans ? dsCount[t] : 0, ws, &tot);
+    if (t < nscans) dsOff[t] = ex;
+    if (t == 0) s->nLessFlat = tot;
+  }
 }
 
-__global__ void __launch_bounds__(SR_BLOCK) sr_gather(const float4* __restrict__ cloud, int nscans, const SrScalars* __restrict__ s,
+__global__ void __launch_bounds__(SR_BLOCK) sr_gather(const float4* __restrict__ cloud, int nscans, int phase, const SrScalars* __restrict__ s,
                                                       const int* __restrict__ provSharp, const int* __restrict__ provLess,
                                                       const int* __restrict__ provFlat, const int* __restrict__ cntSharp,
                                                       const int* __restrict__ cntLess, const int* __restrict__ cntFlat,
@@ -810,12 +818,14 @@ __global__ void __launch_bounds__(SR_BLOCK) sr_gather(const float4* __restrict__
 
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int nslots = nscans * VL_SECTORS;
-  if (t < nslots * 2) { const int sl = t / 2, k = t - sl * 2; if (k < cntSharp[sl]) sharp[offSharp[sl] + k] = cloud[provSharp[t]]; return; }
-  t -= nslots * 2;
-  if (t < nslots * 20) { const int sl = t / 20, k = t - sl * 20; if (k < cntLess[sl]) lessSharp[offLess[sl] + k] = cloud[provLess[t]]; return; }
-  t -= nslots * 20;
-  if (t < nslots * 4) { const int sl = t / 4, k = t - sl * 4; if (k < cntFlat[sl]) flat[offFlat[sl] + k] = cloud[provFlat[t]]; return; }
-  t -= nslots * 4;
+  if (phase == 1) {
+    if (t < nslots * 2) { const int sl = t / 2, k = t - sl * 2; if (k < cntSharp[sl]) sharp[offSharp[sl] + k] = cloud[provSharp[t]]; return; }
+    t -= nslots * 2;
+    if (t < nslots * 20) { const int sl = t / 20, k = t - sl * 20; if (k < cntLess[sl]) lessSharp[offLess[sl] + k] = cloud[provLess[t]]; return; }
+    t -= nslots * 20;
+    if (t < nslots * 4) { const int sl = t / 4, k = t - sl * 4; if (k < cntFlat[sl]) flat[offFlat[sl] + k] = cloud[provFlat[t]]; }
+    return;
+  }
   if (t >= s->count) return;
   int lo = 0, hi = nscans;  // ring of position t: largest r with ringStart[r] <= t
   while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ringStart[mid] <= t) lo = mid; else hi = mid; }
@@ -833,6 +843,7 @@ int vl_sr_run(vloam_b200_ctx* c, const float* d_xyz, int n, int stride) {
     VL_CUDA(cudaMemsetAsync(c->srs, 0, sizeof(SrScalars), VL_STREAM(c)));
     VL_CUDA(cudaMemsetAsync(c->ringCount, 0, sizeof(int) * VL_MAX_RINGS, VL_STREAM(c)));
     VL_CUDA(cudaMemsetAsync(c->ringStart, 0, sizeof(int) * (VL_MAX_RINGS + 1), VL_STREAM(c)));
+    VL_CUDA(cudaEventRecord(c->evSRfeat, VL_STREAM(c)));
     VL_CUDA(cudaEventRecord(c->evSR, VL_STREAM(c)));
     return VLOAM_OK;
   }
@@ -868,18 +879,26 @@ int vl_sr_run(vloam_b200_ctx* c, const float* d_xyz, int n, int stride) {
   VL_BYTES(40.0 * n);  // 2 points + curvature per ring point in, labels + picks out (upper bound: n kept)
   VL_LAUNCH(sr_pick, R, SR_PICK_THREADS, pickSmem, c->cloud.p, c->curv.p, c->label.p, c->picked.p, c->picked.p + n, c->sortScratch.p, c->ringStart, c->ringCount,
             c->provSharp, c->provLess, c->provFlat, c->cntSharp, c->cntLess, c->cntFlat);
+  // sharp / less-sharp / flat are complete here: the odometry of this sweep waits on evSRfeat, not on the per-ring voxel filter below
+  VL_LAUNCH(sr_offsets, 1, 1024, 0, R, 1, c->cntSharp, c->cntLess, c->cntFlat, c->ringDsCount, c->offSharp, c->offLess, c->offFlat,
+            c->ringDsOff, c->srs);
+  VL_LAUNCH(sr_gather, vl_div_up(R * VL_SECTORS * 26, SR_BLOCK), SR_BLOCK, 0, c->cloud.p, R, 1, c->srs, c->provSharp, c->provLess, c->provFlat,
+            c->cntSharp, c->cntLess, c->cntFlat, c->offSharp, c->offLess, c->offFlat, c->ringStart, c->ringDsCount, c->ringDsOff,
+            c->lessFlatProv.p, c->sharp.p, c->lessSharp[c->cur].p, c->flat.p, c->lessFlat[c->cur].p);
+  VL_CUDA(cudaEventRecord(c->evSRfeat, VL_STREAM(c)));
+  if (c->timing && VL_STREAM(c) == c->streamSR) cudaEventRecord(c->evx[8], c->streamSR);
   const size_t voxSmem = (size_t)SR_VOX_CAP * (sizeof(unsigned long long) + sizeof(float4));
   VL_BYTES(36.0 * n);
   VL_LAUNCH(sr_ring_voxel, R, SR_PICK_THREADS, voxSmem, c->cloud.p, c->label.p, c->ringStart, c->ringCount, c->selIdx.p, c->sortScratch.p,
             c->lessFlatProv.p, c->ringDsCount, 0.2f);
-  VL_LAUNCH(sr_offsets, 1, 1024, 0, R, c->cntSharp, c->cntLess, c->cntFlat, c->ringDsCount, c->offSharp, c->offLess, c->offFlat,
+  VL_LAUNCH(sr_offsets, 1, 1024, 0, R, 2, c->cntSharp, c->cntLess, c->cntFlat, c->ringDsCount, c->offSharp, c->offLess, c->offFlat,
             c->ringDsOff, c->srs);
-  const int gatherThreads = R * VL_SECTORS * 26 + n;
-  VL_LAUNCH(sr_gather, vl_div_up(gatherThreads, SR_BLOCK), SR_BLOCK, 0, c->cloud.p, R, c->srs, c->provSharp, c->provLess, c->provFlat,
+  VL_LAUNCH(sr_gather, vl_div_up(n, SR_BLOCK), SR_BLOCK, 0, c->cloud.p, R, 2, c->srs, c->provSharp, c->provLess, c->provFlat,
             c->cntSharp, c->cntLess, c->cntFlat, c->offSharp, c->offLess, c->offFlat, c->ringStart, c->ringDsCount, c->ringDsOff,
             c->lessFlatProv.p, c->sharp.p, c->lessSharp[c->cur].p, c->flat.p, c->lessFlat[c->cur].p);
   VL_CUDA(cudaMemcpyAsync(c->h_srs, c->srs, sizeof(SrScalars), cudaMemcpyDeviceToHost, VL_STREAM(c)));
   VL_CUDA(cudaEventRecord(c->evSR, VL_STREAM(c)));
+  if (c->timing && VL_STREAM(c) == c->streamSR) cudaEventRecord(c->evx[10], c->streamSR);
   VL_CUDA(cudaGetLastError());
   return VLOAM_OK;
 }
