@@ -261,34 +261,69 @@ __device__ __forceinline__ int log_cz(float v) { return min(max((int)floorf((v -
 __device__ __forceinline__ int log_cell(float x, float y, float z) { return log_cx(x) + LOG_NX * (log_cx(y) + LOG_NY * log_cz(z)); }
 
 // Round 1 counted into -- and scanned -- a dense array of 2 x 2.1M cells for ~56k points (16.8 MB read + zeroing + write per
-// sweep to index 0.9 MB of points).  The occupied cells (~25k) now live in an open-addressing hash table of H slots
-// (H >= 4 x points): slot = {cell id, count, start}; the counting sort runs over slots, the scan over H ints (0.5 MB).
-// Layout of one set (ints): hkey[H] | hcnt[H] | hfill[H] | hstart[H + 4]
+// sweep to index 0.9 MB of points).  Now only the occupied part of the grid exists: a row of the grid (fixed y, z) is cut into
+// GROUPS of 8 consecutive x-cells, and the occupied groups (~10k) live in an open-addressing hash table of H >= points slots.
+// A slot is one 64-byte line {group id, start[0..8]}: the points of the group are contiguous in the cell-sorted copy, sub-cell
+// after sub-cell, so the row segment [x - R, x + R] the search visits is ONE range per group it touches (<= 2 groups for
+// R <= 4) and a look-up is one dependent memory access after the probe (same line).  (A hash of single cells needed 27 / 125 /
+// 729 look-ups per query for R = 1 / 2 / 4; corner queries often reach R = 4 and the kernel took 64 us instead of 35.)
+// Build: lo_grid_count (probe / claim the slot, count per sub-cell), lo_grid_alloc (one thread per slot: a contiguous range for
+// the group from a bump counter -- one atomic per CTA -- and the nine starts), lo_grid_fill.  No scan.
+// Layout of one set (ints): LoSlot[H] | cnt[8 H] | top[4]
 #define LOG_EMPTY 0xffffffffu
-struct LoHash { const unsigned* key; const int* cnt; const int* start; int mask; };
+#define LOG_G 8
+#define LOG_NGX (LOG_NX / LOG_G)
+#define LOG_NGROUP (LOG_NCELL / LOG_G)
+struct __align__(64) LoSlot { unsigned key; int start[LOG_G + 1]; int pad[6]; };
+struct LoHash { const LoSlot* slot; int mask; };
 __device__ __forceinline__ unsigned log_hash(unsigned id) { id ^= id >> 15; id *= 0x9E3779B1u; id ^= id >> 13; return id; }
 
 __global__ void __launch_bounds__(256) lo_grid_count(const float4* __restrict__ corner, int nc, const float4* __restrict__ surf, int ns,
-                                                     unsigned* __restrict__ hkey, int* __restrict__ hcnt, int mask, int* __restrict__ slotOf) {
+                                                     LoSlot* __restrict__ slots, int* __restrict__ cnt, int mask, int* __restrict__ subOf) {
   VL_PDL_WAIT();
 
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= nc + ns) return;
   const int which = g >= nc;
   const float4 p = which ? surf[g - nc] : corner[g];
-  const unsigned id = (unsigned)(which * LOG_NCELL + log_cell(p.x, p.y, p.z));
+  const int cx = log_cx(p.x);
+  const unsigned id = (unsigned)(which * LOG_NGROUP + (cx >> 3) + LOG_NGX * (log_cx(p.y) + LOG_NY * log_cz(p.z)));
   unsigned h = log_hash(id) & (unsigned)mask;
   for (;;) {
-    const unsigned prev = atomicCAS(&hkey[h], LOG_EMPTY, id);
+    const unsigned prev = atomicCAS(&slots[h].key, LOG_EMPTY, id);
     if (prev == LOG_EMPTY || prev == id) break;
     h = (h + 1) & (unsigned)mask;
   }
-  slotOf[g] = (int)h;
-  atomicAdd(&hcnt[h], 1);
+  const int so = (int)h * LOG_G + (cx & 7);
+  subOf[g] = so;
+  atomicAdd(&cnt[so], 1);
+}
+// one thread per slot: the group's range in the sorted copy and the starts of its sub-cells; the counters become the fill cursors
+__global__ void __launch_bounds__(256) lo_grid_alloc(LoSlot* __restrict__ slots, int* __restrict__ cnt, int* __restrict__ top) {
+  VL_PDL_WAIT();
+
+  __shared__ int ws[32];
+  __shared__ int sBase;
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool used = slots[h].key != LOG_EMPTY;
+  int4 a = make_int4(0, 0, 0, 0), b = a;
+  if (used) { a = *reinterpret_cast<const int4*>(cnt + (size_t)h * LOG_G); b = *reinterpret_cast<const int4*>(cnt + (size_t)h * LOG_G + 4); }
+  const int total = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+  int blockTotal = 0;
+  const int ex = vl_block_excl_scan<256>(total, ws, &blockTotal);
+  if (threadIdx.x == 0) sBase = blockTotal > 0 ? atomicAdd(top, blockTotal) : 0;
+  __syncthreads();
+  if (!used) return;
+  int st = sBase + ex;
+  int* o = slots[h].start;
+  o[0] = st; st += a.x; o[1] = st; st += a.y; o[2] = st; st += a.z; o[3] = st; st += a.w;
+  o[4] = st; st += b.x; o[5] = st; st += b.y; o[6] = st; st += b.z; o[7] = st; st += b.w; o[8] = st;
+  *reinterpret_cast<int4*>(cnt + (size_t)h * LOG_G) = make_int4(0, 0, 0, 0);
+  *reinterpret_cast<int4*>(cnt + (size_t)h * LOG_G + 4) = make_int4(0, 0, 0, 0);
 }
 __global__ void __launch_bounds__(256) lo_grid_fill(const float4* __restrict__ corner, int nc, const float4* __restrict__ surf, int ns,
-                                                    const int* __restrict__ slotOf, const int* __restrict__ hstart,
-                                                    int* __restrict__ hfill, float4* __restrict__ sorted) {
+                                                    const int* __restrict__ subOf, const LoSlot* __restrict__ slots,
+                                                    int* __restrict__ fill, float4* __restrict__ sorted) {
   VL_PDL_WAIT();
 
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -296,17 +331,18 @@ __global__ void __launch_bounds__(256) lo_grid_fill(const float4* __restrict__ c
   const int which = g >= nc;
   const int j = which ? g - nc : g;
   const float4 p = which ? surf[j] : corner[j];
-  const int slot = slotOf[g];
-  const int pos = hstart[slot] + atomicAdd(&hfill[slot], 1);
+  const int so = subOf[g];
+  const int pos = slots[so >> 3].start[so & 7] + atomicAdd(&fill[so], 1);
   const unsigned v = (unsigned)min(max((int)p.w, 0), 255);
   sorted[pos] = make_float4(p.x, p.y, p.z, __uint_as_float((unsigned)j | (v << 24)));
 }
-// point range of one cell (empty when the cell holds nothing)
-__device__ __forceinline__ void log_lookup(const LoHash& H, unsigned id, int& beg, int& len) {
+// point range of sub-cells [lo, hi] of one group (empty when the group holds nothing)
+__device__ __forceinline__ void log_lookup(const LoHash& H, unsigned id, int lo, int hi, int& beg, int& len) {
   unsigned h = log_hash(id) & (unsigned)H.mask;
   for (;;) {
-    const unsigned k = H.key[h];
-    if (k == id) { beg = H.start[h]; len = H.cnt[h]; return; }
+    const LoSlot* sl = H.slot + h;
+    const unsigned k = __ldg(&sl->key);
+    if (k == id) { beg = __ldg(&sl->start[lo]); len = __ldg(&sl->start[hi + 1]) - beg; return; }
     if (k == LOG_EMPTY) { beg = 0; len = 0; return; }
     h = (h + 1) & (unsigned)H.mask;
   }
@@ -326,21 +362,26 @@ __device__ __forceinline__ Best warp_best_v(Best v, unsigned& tag, bool preferLo
 // reference's forward scan then visits exactly {j > closest : ring_j <= id + 2} and the backward scan
 // {j < closest : ring_j >= id - 2}; candidates farther than 5 m can never win because the running
 // minima start at DISTANCE_SQ_THRESHOLD = 25).  One warp per query, two passes over its 27 cells.
-// Visit the (2R+1)^3 block of cells around (cx, cy, cz), R = 1, 2 or 4.  Lane r looks up the point range of cell r in the
-// hash of occupied cells (all look-ups of a round in ~one memory latency;
-// the 729 cells of R = 4 take 23 rounds, rare) and VL_WARP_VISIT_FLAT spreads the candidates of all cells over
-// the lanes.  A larger block simply revisits the smaller one: every update in the bodies below is an
-// idempotent minimum, and escalation only happens where the inner block was nearly empty.  BODY sees float4 t.
+// Visit the (2R+1)^3 block of cells around (cx, cy, cz), R = 1, 2 or 4.  A block is (2R+1)^2 rows; the cells [cx - R, cx + R]
+// of a row lie in one or two groups of the hash: lane l looks up (row l / 2, group l % 2) -- all look-ups of a round in ~two
+// memory latencies (probe, starts on the same line); R = 1 takes one round, R = 2 two, R = 4 six -- and VL_WARP_VISIT_FLAT
+// spreads the candidates of all ranges over the lanes.  A larger block simply revisits the smaller one: every update in the
+// bodies below is an idempotent minimum, and escalation only happens where the inner block was nearly empty.  BODY sees float4 t.
 #define LOG_VISIT(R, BODY)                                                                                   \
   do {                                                                                                       \
     const int side_ = 2 * (R) + 1;                                                                           \
-    for (int r0_ = 0; r0_ < side_ * side_ * side_; r0_ += 32) {                                              \
-      const int rr_ = r0_ + lane;                                                                            \
+    const int xs_ = max(cx - (R), 0), xe_ = min(cx + (R), LOG_NX - 1);                                       \
+    const int g0_ = xs_ >> 3, g1_ = xe_ >> 3;                                                                \
+    for (int r0_ = 0; r0_ < 2 * side_ * side_; r0_ += 32) {                                                  \
+      const int it_ = r0_ + lane, rr_ = it_ >> 1, part_ = it_ & 1;                                           \
       int beg_ = 0, len_ = 0;                                                                                \
-      if (rr_ < side_ * side_ * side_) {                                                                     \
-        const int xx_ = cx + rr_ % side_ - (R), yy_ = cy + (rr_ / side_) % side_ - (R), zz_ = cz + rr_ / (side_ * side_) - (R); \
-        if (zz_ >= 0 && zz_ < LOG_NZ && yy_ >= 0 && yy_ < LOG_NY && xx_ >= 0 && xx_ < LOG_NX)                \
-          log_lookup(H, (unsigned)(cellBase + xx_ + LOG_NX * (yy_ + LOG_NY * zz_)), beg_, len_);            \
+      if (rr_ < side_ * side_ && (part_ == 0 || g1_ != g0_)) {                                               \
+        const int zz_ = cz + rr_ / side_ - (R), yy_ = cy + rr_ % side_ - (R);                                \
+        if (zz_ >= 0 && zz_ < LOG_NZ && yy_ >= 0 && yy_ < LOG_NY) {                                          \
+          const int g_ = part_ ? g1_ : g0_;                                                                  \
+          log_lookup(H, (unsigned)(groupBase + g_ + LOG_NGX * (yy_ + LOG_NY * zz_)), part_ ? 0 : (xs_ & 7),  \
+                     g_ == g1_ ? (xe_ & 7) : 7, beg_, len_);                                                 \
+        }                                                                                                    \
       }                                                                                                      \
       VL_WARP_VISIT_FLAT(beg_, len_, lane, sorted, BODY);                                                    \
     }                                                                                                        \
@@ -363,7 +404,7 @@ __device__ __forceinline__ void lo_assoc_grid_dev(int qi, int lane, const float4
   float sx, sy, sz;
   vl_transform_to_start(pose, cp, factorS != nullptr, sx, sy, sz);  // TransformToStart (LO.cpp:152-173)
   const int cx = log_cx(sx), cy = log_cx(sy), cz = log_cz(sz);
-  const int cellBase = SURF ? LOG_NCELL : 0;
+  const int groupBase = SURF ? LOG_NGROUP : 0;
   // ---- pass A: exact nearest neighbour, ties by index
   Best nn{3.0e38f, 0x7fffffff};
   unsigned nnv = 0;
@@ -535,22 +576,21 @@ int vl_lo_build_last(vloam_b200_ctx* c, int set, const float4* corner, int nc, c
   VL_LAUNCH(lo_ring_table, dim3(vl_div_up(max(max(nc, ns), LO_TBL + 1), 256), 2), 256, 0, corner, nc, surf, ns, tbl);
   VL_CUDA(cudaMemcpyAsync(&c->h_vScalars[8 + 2 * set], tbl + LO_TBL, sizeof(int), cudaMemcpyDeviceToHost, st));
   VL_CUDA(cudaMemcpyAsync(&c->h_vScalars[9 + 2 * set], tbl + (LO_TBL + 1) + LO_TBL, sizeof(int), cudaMemcpyDeviceToHost, st));
-  // hash of occupied cells: H >= 4 x points slots; ints: hkey[H] | hcnt[H] | hfill[H] | hstart[H + 4]
-  int H = 1 << 17; while (H < 4 * n) H <<= 1;
-  VL_TRY(vl_reserve(c, c->loGridCells[set], (size_t)4 * H + 4));
-  VL_TRY(vl_scan_alloc(&c->loScan[set], H));
+  // hash of occupied 8-cell row groups: H >= points slots of 16 ints, then 8 H sub-cell counters and the bump counter
+  int H = 1 << 15; while (H < n) H <<= 1;
+  VL_TRY(vl_reserve(c, c->loGridCells[set], (size_t)24 * H + 4));
   c->loGridMask[set] = H - 1;
   VL_TRY(vl_reserve(c, c->loGridCellOf, (size_t)max(n, 1), false, (size_t)n / 2));
   VL_TRY(vl_reserve(c, c->loGridSorted[set], (size_t)max(n, 1), false, (size_t)n / 2));
   if (n > 0 && n < (1 << 24)) {
-    unsigned* hkey = reinterpret_cast<unsigned*>(c->loGridCells[set].p); int* cnt = c->loGridCells[set].p + H; int* fill = cnt + H; int* start = fill + H;
-    VL_CUDA(cudaMemsetAsync(hkey, 0xff, sizeof(int) * H, st));
-    VL_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * 2 * H, st));  // counts and fill cursors
+    LoSlot* slots = reinterpret_cast<LoSlot*>(c->loGridCells[set].p); int* cnt = c->loGridCells[set].p + (size_t)16 * H; int* top = cnt + (size_t)8 * H;
+    VL_CUDA(cudaMemsetAsync(slots, 0xff, sizeof(LoSlot) * H, st));                 // every key = LOG_EMPTY
+    VL_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)8 * H + 4), st));      // counters and the bump counter
     VL_BYTES(16.0 * n);  // SURVEY 8(d) B_lo: the clouds that become "last" are read once to build their search structure
-    VL_LAUNCH(lo_grid_count, vl_div_up(n, 256), 256, 0, corner, nc, surf, ns, hkey, cnt, H - 1, c->loGridCellOf.p);
-    VL_TRY(vl_scan_exclusive(c, cnt, H, &c->loScan[set], start));
+    VL_LAUNCH(lo_grid_count, vl_div_up(n, 256), 256, 0, corner, nc, surf, ns, slots, cnt, H - 1, c->loGridCellOf.p);
+    VL_LAUNCH(lo_grid_alloc, H / 256, 256, 0, slots, cnt, top);
     VL_BYTES(32.0 * n);
-    VL_LAUNCH(lo_grid_fill, vl_div_up(n, 256), 256, 0, corner, nc, surf, ns, c->loGridCellOf.p, start, fill, c->loGridSorted[set].p);
+    VL_LAUNCH(lo_grid_fill, vl_div_up(n, 256), 256, 0, corner, nc, surf, ns, c->loGridCellOf.p, (const LoSlot*)slots, cnt, c->loGridSorted[set].p);
     c->loGridValid[set] = true;
   } else c->loGridValid[set] = false;
   VL_CUDA(cudaGetLastError());
@@ -573,9 +613,8 @@ static int lo_associate(vloam_b200_ctx* c, const double* d_pose, const float4* c
   const int set = c->lastSet;
   const bool gridC = c->loGridValid[set] && (c->loAssumeMonotone || c->h_vScalars[8 + 2 * set] != 0);
   const bool gridS = c->loGridValid[set] && (c->loAssumeMonotone || c->h_vScalars[9 + 2 * set] != 0);
-  LoHash start;  // (hash of the occupied cells of set `set`: keys, counts, starts)
-  { const int H = c->loGridMask[set] + 1; const int* b = c->loGridCells[set].p;
-    start.key = reinterpret_cast<const unsigned*>(b); start.cnt = b ? b + H : nullptr; start.start = b ? b + 3 * H : nullptr; start.mask = H - 1; }
+  LoHash start;  // (hash of the occupied row groups of set `set`)
+  start.slot = reinterpret_cast<const LoSlot*>(c->loGridCells[set].p); start.mask = c->loGridMask[set];
   const float4* gsorted = c->loGridSorted[set].p;
   const int* rtbl = c->loRingTbl + set * 2 * (LO_TBL + 1);
   if (gridC && gridS && nS + nF > 0) {
@@ -610,7 +649,7 @@ int vl_lo_preload(vloam_b200_ctx* c) {  // see vl_sr_set_attrs: load every kerne
   cudaFuncAttributes fa_;
   VL_CUDA(cudaFuncGetAttributes(&fa_, lo_ring_table)); VL_CUDA(cudaFuncGetAttributes(&fa_, lo_ring_table_init));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lo_assoc<false>)); VL_CUDA(cudaFuncGetAttributes(&fa_, lo_assoc<true>));
-  VL_CUDA(cudaFuncGetAttributes(&fa_, lo_grid_count)); VL_CUDA(cudaFuncGetAttributes(&fa_, lo_grid_fill));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, lo_grid_count)); VL_CUDA(cudaFuncGetAttributes(&fa_, lo_grid_alloc)); VL_CUDA(cudaFuncGetAttributes(&fa_, lo_grid_fill));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lo_assoc_grid<false>)); VL_CUDA(cudaFuncGetAttributes(&fa_, lo_assoc_grid<true>));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lo_assoc_grid_both)); VL_CUDA(cudaFuncGetAttributes(&fa_, lo_accumulate));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lo_set_prior));
