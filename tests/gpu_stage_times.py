@@ -31,11 +31,13 @@ torch.cuda.synchronize()
 rows = []
 detail = []
 walls = []
-LOOKAHEAD = os.environ.get("LOOKAHEAD") == "1"   # replay mode: register the next sweep, no full synchronize between sweeps
+LOOKAHEAD = os.environ.get("LOOKAHEAD") in ("1", "2")  # 2: two sweeps registered ahead (what bench.py does)
+TWO = os.environ.get("LOOKAHEAD") == "2"   # replay mode: register the next sweep, no full synchronize between sweeps
 host = []
 for k in range(N):
     t0 = time.perf_counter()
     if LOOKAHEAD and k + 1 < N: ctx.prefetch_device(d[k + 1].data_ptr(), d[k + 1].shape[0], 4)
+    if TWO and k + 2 < N: ctx.prefetch_device(d[k + 2].data_ptr(), d[k + 2].shape[0], 4)
     ctx.process_frame_device(d[k].data_ptr(), d[k].shape[0], 4)
     if not LOOKAHEAD: ctx.synchronize()
     host.append(np.frombuffer(ctx.get_raw("timing.host"), np.float64).copy()) if LOOKAHEAD else None

@@ -14,14 +14,17 @@ d = [torch.from_numpy(s).cuda() for s in scans]
 L = ctx.L
 L.vloam_b200_profile_kernel.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
 L.vloam_b200_profile_timeline.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]
-LOOKAHEAD = os.environ.get("LOOKAHEAD") == "1"
+LOOKAHEAD = os.environ.get("LOOKAHEAD") in ("1", "2")  # 2: two sweeps registered ahead (what bench.py does)
+TWO = os.environ.get("LOOKAHEAD") == "2"
 for k in range(N - 2):
     if LOOKAHEAD: ctx.prefetch_device(d[k + 1].data_ptr(), d[k + 1].shape[0], 4)
+    if TWO and k + 2 < N: ctx.prefetch_device(d[k + 2].data_ptr(), d[k + 2].shape[0], 4)
     ctx.process_frame_device(d[k].data_ptr(), d[k].shape[0], 4)
 ctx.synchronize()
 L.vloam_b200_profile_kernel(ctx.h, b"*")
 for k in range(N - 2, N):
     if LOOKAHEAD and k + 1 < N: ctx.prefetch_device(d[k + 1].data_ptr(), d[k + 1].shape[0], 4)
+    if TWO and k + 2 < N: ctx.prefetch_device(d[k + 2].data_ptr(), d[k + 2].shape[0], 4)
     ctx.process_frame_device(d[k].data_ptr(), d[k].shape[0], 4)
 ctx.synchronize()
 buf = ctypes.create_string_buffer(1 << 18)

@@ -115,7 +115,7 @@ def test_c5_concurrent_sequences_match_oracle_with_checkpoints(pkg, op):
                 checkpoints += 1
                 continue
             o.process(scans[k])
-            g.prefetch_ptr(pinned[k + 1].data_ptr(), pinned[k + 1].shape[0], 4)
+            bench.prefetch_ahead(g, pinned, k, False)  # the next two sweeps, as bench.py registers them
             g.process_frame_ptr(pinned[k].data_ptr(), pinned[k].shape[0], 4, pose.ctypes.data)
             lo, lm = o.get("lo.pose"), o.get("lm.pose")
             pose_close(lo[:7], pose[:7]); pose_close(lm[:7], pose[7:])
@@ -157,7 +157,7 @@ def test_grid_update_equals_pool_update(pkg):
         g.set("lm.cornerMap", cb); g.set("lm.surfMap", sb)
         pose, poses, centres = np.zeros(14), [], set()
         for k in range(n):
-            g.prefetch_device(dev[k + 1].data_ptr(), dev[k + 1].shape[0], 4)
+            bench.prefetch_ahead(g, dev, k, True)
             g.process_frame_device(dev[k].data_ptr(), dev[k].shape[0], 4, pose.ctypes.data)
             poses.append(pose.copy())
             if k % 5 == 4: centres.add(int(g.get("lm.validInd")[0]))
@@ -187,6 +187,7 @@ def test_skip_frame_lookahead_null_pose_matches_plain_path(pkg, synth, street):
         pose = np.zeros(14)
         for k in range(12):
             b.prefetch_device(dev[k + 1].data_ptr(), dev[k + 1].shape[0], 4)
+            if trial > 0 and k + 2 < 13: b.prefetch_device(dev[k + 2].data_ptr(), dev[k + 2].shape[0], 4)  # (trials 1, 2: two sweeps ahead)
             last = k == 11
             b.process_frame_device(dev[k].data_ptr(), dev[k].shape[0], 4, pose.ctypes.data if last else None)
         assert (pose == ref[11]).all(), "trial %d: final pose differs in the asynchronous skip-frame replay" % trial

@@ -728,11 +728,27 @@ def test_lookahead_scan_registration_gives_identical_results(pkg, synth, street)
     a.close()
     pinned = [torch.from_numpy(s).pin_memory() for s in scans]
     dev = [torch.from_numpy(s).cuda() for s in scans]
-    for mode in ("device", "host", "mixed"):
+    for mode in ("device", "host", "device2", "host2", "mixed2", "mixed"):
         b = pkg.Context(**KW[1])
         pose = np.zeros(14)
         for k in range(8):
-            if mode == "device":
+            if mode == "device2":  # two sweeps registered ahead: sweep k+2 is uploaded + registered while sweep k+1's odometry runs beside sweep k's mapping
+                for j in (k + 1, k + 2):
+                    if j < 8: b.prefetch_device(dev[j].data_ptr(), dev[j].shape[0], 4)
+                b.process_frame_device(dev[k].data_ptr(), dev[k].shape[0], 4, pose.ctypes.data)
+            elif mode == "host2":
+                for j in (k + 1, k + 2):
+                    if j < 8: b.prefetch_ptr(pinned[j].data_ptr(), pinned[j].shape[0], 4)
+                b.process_frame_ptr(pinned[k].data_ptr(), pinned[k].shape[0], 4, pose.ctypes.data)
+            elif mode == "mixed2":  # two ahead with a sweep that never comes (k = 2 registers 3 and 7), a gap (nothing registered at k = 4) and a re-start
+                if k < 2 or k > 4:
+                    for j in (k + 1, k + 2):
+                        if j < 8: b.prefetch_ptr(pinned[j].data_ptr(), pinned[j].shape[0], 4)
+                if k == 2: b.prefetch_ptr(pinned[3].data_ptr(), pinned[3].shape[0], 4); b.prefetch_device(dev[7].data_ptr(), dev[7].shape[0], 4)
+                if k == 3: b.prefetch_device(dev[0].data_ptr(), dev[0].shape[0], 4)
+                if k % 2: b.process_frame_device(dev[k].data_ptr(), dev[k].shape[0], 4, pose.ctypes.data)
+                else: b.process_frame_ptr(pinned[k].data_ptr(), pinned[k].shape[0], 4, pose.ctypes.data)
+            elif mode == "device":
                 if k + 1 < 8: b.prefetch_device(dev[k + 1].data_ptr(), dev[k + 1].shape[0], 4)
                 b.process_frame_device(dev[k].data_ptr(), dev[k].shape[0], 4, pose.ctypes.data)
             elif mode == "host":

@@ -130,7 +130,10 @@ static int create_impl(vloam_b200_ctx* c, const vloam_b200_params* p, int device
   c->srNext = new SrSet();
   vl_sr_swap(c, *c->srNext);      // the spare set gets its own fixed-size arrays, counters and event
   { const int r_ = alloc_sr_fixed(c); vl_sr_swap(c, *c->srNext); if (r_ != VLOAM_OK) return r_; }
-  c->srNextKey = nullptr; c->srNextValid = false; c->srPendKey = nullptr; c->srPendDevice = false;
+  c->srNext2 = new SrSet();
+  vl_sr_swap(c, *c->srNext2);
+  { const int r_ = alloc_sr_fixed(c); vl_sr_swap(c, *c->srNext2); if (r_ != VLOAM_OK) return r_; }
+  c->srNextKey = c->srNext2Key = nullptr; c->srNextValid = c->srNext2Valid = false; c->srPendCount = 0;
   VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->streamSR, cudaStreamNonBlocking, pr[3]));
   VL_CUDA_CREATE(cudaMalloc(&c->los, sizeof(LoScalars)));
   VL_CUDA_CREATE(cudaMalloc(&c->losNext, sizeof(LoScalars)));
@@ -179,6 +182,7 @@ void vloam_b200_destroy(vloam_b200_ctx* c) {
   cudaStreamSynchronize(c->streamSR);
   free_sr_set(c);
   if (c->srNext) { vl_sr_swap(c, *c->srNext); free_sr_set(c); delete c->srNext; c->srNext = nullptr; }
+  if (c->srNext2) { vl_sr_swap(c, *c->srNext2); free_sr_set(c); delete c->srNext2; c->srNext2 = nullptr; }
   cudaStreamDestroy(c->streamSR);
   vl_lm_free(c);
   vl_scan_free(&c->loScan[0]); vl_scan_free(&c->loScan[1]);
@@ -214,58 +218,86 @@ int vloam_b200_begin_frame(vloam_b200_ctx* c) {
   return VLOAM_OK;
 }
 
-// Look-ahead for replays: register the NEXT sweep (device or host pointer).  Its scan registration is queued on a side
-// stream from inside the processing of the current sweep, into the spare field set, so it runs underneath this sweep's
-// odometry and mapping; the following scan_registration / process_frame call with the same (pointer, n, stride)
-// finds the work done.  Any other call ignores (and later overwrites) it.  The buffer must stay valid and unchanged
-// until that call.  No reference counterpart: the bag player hands over one sweep at a time (MAIN.cpp:143).
+// Look-ahead for replays: register the NEXT sweep -- or the next TWO sweeps, in order -- (device or host pointer).  The upload
+// and scan registration of a registered sweep are queued on a side stream from inside the processing of the current sweep, into
+// a spare field set, so they run underneath this sweep's odometry and mapping; the scan_registration / process_frame call that
+// comes with the same (pointer, n, stride) finds the work done.  With two sweeps registered, the odometry of sweep k+1 (whose
+// scan registration ran during sweep k-1) starts at once beside the mapping of sweep k while sweep k+2 is uploaded and
+// registered: nothing of the chain upload -> scan registration -> odometry is left on the critical path.  A call with any other
+// buffer drops what was registered.  A registered buffer must stay valid and unchanged until the call that processes it;
+// registering a buffer that is already registered is a no-op.  No reference counterpart: the bag player hands over one sweep at
+// a time (MAIN.cpp:143).
+static int register_pending(vloam_b200_ctx* c, const float* key, int n, int stride, bool dev) {
+  if (n <= 0 || stride < 3 || !key) { snprintf(c->err, sizeof c->err, "bad cloud shape"); return VLOAM_E_INVALID; }
+  if (c->srNextValid && key == c->srNextKey && n == c->srNextN && stride == c->srNextStride) return VLOAM_OK;
+  if (c->srNext2Valid && key == c->srNext2Key && n == c->srNext2N && stride == c->srNext2Stride) return VLOAM_OK;
+  for (int k = 0; k < c->srPendCount; ++k)
+    if (c->srPend[k].key == key && c->srPend[k].n == n && c->srPend[k].stride == stride) return VLOAM_OK;
+  if (c->srPendCount == 2) c->srPendCount = 1;  // more than two ahead: the newest registration replaces the last one
+  c->srPend[c->srPendCount].key = key; c->srPend[c->srPendCount].n = n; c->srPend[c->srPendCount].stride = stride; c->srPend[c->srPendCount].dev = dev;
+  c->srPendCount++;
+  return VLOAM_OK;
+}
 int vloam_b200_prefetch_scan_device(vloam_b200_ctx* c, const float* d_xyz, int n, int stride) {
   if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
-  if (n <= 0 || stride < 3 || !d_xyz) { snprintf(c->err, sizeof c->err, "bad cloud shape"); return VLOAM_E_INVALID; }
-  c->srPendKey = d_xyz; c->srPendN = n; c->srPendStride = stride; c->srPendDevice = true;
-  return VLOAM_OK;
+  return register_pending(c, d_xyz, n, stride, true);
 }
 int vloam_b200_prefetch_scan(vloam_b200_ctx* c, const float* xyz, int n, int stride) {
   if (!c) return VLOAM_E_INVALID;  // ABI boundary: a null context is the caller's error, not a crash
-  if (n <= 0 || stride < 3 || !xyz) { snprintf(c->err, sizeof c->err, "bad cloud shape"); return VLOAM_E_INVALID; }
-  c->srPendKey = xyz; c->srPendN = n; c->srPendStride = stride; c->srPendDevice = false;
-  return VLOAM_OK;
+  return register_pending(c, xyz, n, stride, false);
 }
 
-// queue the registered look-ahead: spare set swapped in, scan registration on streamSR, set swapped back out.
+// queue the registered look-ahead sweeps: spare set swapped in, upload + scan registration on streamSR, set swapped back out.
 // Called by the odometry stage once its own kernels are queued (the host would only wait at S1 otherwise): issuing
 // these ~10 launches before the odometry delays the sweep that is being processed.
 int vl_launch_lookahead(vloam_b200_ctx* c) {
-  if (!c->srPendKey) return VLOAM_OK;
-  const float* key = c->srPendKey; const int n = c->srPendN, stride = c->srPendStride; const bool dev = c->srPendDevice;
-  c->srPendKey = nullptr;
-  const int curNow = c->cur;
-  vl_sr_swap(c, *c->srNext);
-  c->cur = curNow;  // vl_sr_run advances it: the look-ahead writes the generation after this sweep's
-  vl_tls_stream = c->streamSR;
-  // The spare generation of the less-sharp / less-flat clouds this run overwrites was the "last" cloud of the odometry
-  // solve before the current one: order the overwrite behind the solves queued so far on the DEVICE (a caller that never
-  // syncs -- skipped mapping frames with pose_out == NULL -- gives no host-side guarantee).
-  cudaStreamWaitEvent(c->streamSR, c->evLoSolve, 0);
   int r = VLOAM_OK;
-  const float* d_xyz = key;
-  if (!dev) {
-    r = vl_reserve(c, c->in, (size_t)n * stride);
-    if (r == VLOAM_OK && cudaMemcpyAsync(c->in.p, key, (size_t)n * stride * sizeof(float), cudaMemcpyHostToDevice, c->streamSR) != cudaSuccess) r = VLOAM_E_CUDA;
-    d_xyz = c->in.p;
+  while (r == VLOAM_OK && c->srPendCount > 0) {
+    const int slot = !c->srNextValid ? 0 : (!c->srNext2Valid ? 1 : -1);
+    if (slot < 0) break;  // both spare sets hold sweeps that have not been processed yet: the registration waits
+    const vloam_b200_ctx::SrPend pd = c->srPend[0];
+    c->srPend[0] = c->srPend[1]; c->srPendCount--;
+    SrSet* S = slot ? c->srNext2 : c->srNext;
+    const int curNow = c->cur;
+    vl_sr_swap(c, *S);
+    c->cur = (curNow + slot) % 3;  // vl_sr_run advances it: the look-ahead writes the generation after this sweep's (slot 1: the one after that,
+                                   // i.e. the generation of the sweep BEFORE this one, dead once this sweep's odometry solve is done)
+    vl_tls_stream = c->streamSR;
+    // The generation of the less-sharp / less-flat clouds this run overwrites was the "last" cloud of an odometry solve that is
+    // queued already (the previous sweep's, or this sweep's): order the overwrite behind the solves queued so far on the DEVICE
+    // (a caller that never syncs -- skipped mapping frames with pose_out == NULL -- gives no host-side guarantee).
+    cudaStreamWaitEvent(c->streamSR, c->evLoSolve, 0);
+    const float* d_xyz = pd.key;
+    if (!pd.dev) {
+      r = vl_reserve(c, c->in, (size_t)pd.n * pd.stride);
+      if (r == VLOAM_OK && cudaMemcpyAsync(c->in.p, pd.key, (size_t)pd.n * pd.stride * sizeof(float), cudaMemcpyHostToDevice, c->streamSR) != cudaSuccess) r = VLOAM_E_CUDA;
+      d_xyz = c->in.p;
+    }
+    if (r == VLOAM_OK) r = vl_sr_run(c, d_xyz, pd.n, pd.stride);
+    vl_tls_stream = nullptr;
+    vl_sr_swap(c, *S);  // (the context's own `cur` comes back with its set)
+    if (slot) { c->srNext2Valid = r == VLOAM_OK; c->srNext2Key = pd.key; c->srNext2N = pd.n; c->srNext2Stride = pd.stride; }
+    else { c->srNextValid = r == VLOAM_OK; c->srNextKey = pd.key; c->srNextN = pd.n; c->srNextStride = pd.stride; }
   }
-  if (r == VLOAM_OK) r = vl_sr_run(c, d_xyz, n, stride);
-  vl_tls_stream = nullptr;
-  vl_sr_swap(c, *c->srNext);
-  c->srNextValid = r == VLOAM_OK; c->srNextKey = key; c->srNextN = n; c->srNextStride = stride;
   return r;
+}
+
+// Drop every look-ahead result (the sweep that arrived is not the registered one, or the state they were computed from was
+// edited).  Their kernels may still be running on streamSR, writing generations the fresh run is about to use: wait for them.
+void vl_drop_lookahead(vloam_b200_ctx* c) {
+  if (c->srNextValid || c->srNext2Valid) cudaStreamSynchronize(c->streamSR);
+  c->srNextValid = c->srNext2Valid = false;
+  c->loNextValid = false;
 }
 
 // this sweep was registered ahead: adopt the spare set (its kernels may still be running on streamSR)
 static bool adopt_lookahead(vloam_b200_ctx* c, const float* key, int n, int stride) {
   if (!c->srNextValid || key != c->srNextKey || n != c->srNextN || stride != c->srNextStride) return false;
   vl_sr_swap(c, *c->srNext);
-  c->srNextValid = false;
+  // the set of the sweep after this one moves up; the set that just came out of the context is the free one
+  { SrSet* t_ = c->srNext; c->srNext = c->srNext2; c->srNext2 = t_; }
+  c->srNextValid = c->srNext2Valid; c->srNextKey = c->srNext2Key; c->srNextN = c->srNext2N; c->srNextStride = c->srNext2Stride;
+  c->srNext2Valid = false;
   cudaStreamWaitEvent(c->stream, c->evSR, 0);
   return true;
 }
@@ -276,8 +308,7 @@ int vloam_b200_scan_registration_device(vloam_b200_ctx* c, const float* d_xyz, i
   if (c->timing) VL_CUDA(cudaEventRecord(c->ev[0], c->stream));
   c->srAdopted = adopt_lookahead(c, d_xyz, n, stride);
   if (!c->srAdopted) {
-    c->loNextValid = false;
-    c->srNextValid = false;  // a look-ahead result for another sweep targets the generation this run is about to write
+    vl_drop_lookahead(c);  // a look-ahead result for another sweep targets the generation this run is about to write
     VL_TRY(vl_sr_run(c, d_xyz, n, stride));
   }
   if (c->timing) VL_CUDA(cudaEventRecord(c->ev[1], c->stream));
@@ -290,8 +321,7 @@ int vloam_b200_scan_registration(vloam_b200_ctx* c, const float* xyz, int n, int
   if (c->timing) VL_CUDA(cudaEventRecord(c->ev[0], c->stream));
   c->srAdopted = adopt_lookahead(c, xyz, n, stride);
   if (!c->srAdopted) {
-    c->loNextValid = false;
-    c->srNextValid = false;
+    vl_drop_lookahead(c);
     VL_TRY(vl_reserve(c, c->in, (size_t)max(n, 1) * stride));
     if (n > 0) VL_CUDA(cudaMemcpyAsync(c->in.p, xyz, (size_t)n * stride * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     VL_TRY(vl_sr_run(c, c->in.p, n, stride));
@@ -615,7 +645,7 @@ int vloam_b200_debug_set(vloam_b200_ctx* c, const char* name, const void* data, 
     const int* hdr = (const int*)data;
     if (bytes < 8 || bytes != 8 + ((long)hdr[0] + hdr[1]) * 16) { snprintf(c->err, sizeof c->err, "lo.last blob size mismatch"); return VLOAM_E_INVALID; }
     const int o = (c->cur + 1) % 3;  // (cur becomes o below, so the next sweep's scan registration writes (o + 1) % 3)
-    c->srNextValid = false;        // a look-ahead result was computed into buffer o: drop it
+    vl_drop_lookahead(c);          // a look-ahead result was computed into buffer o: drop it
     VL_TRY(vl_reserve(c, c->lessSharp[o], (size_t)max(hdr[0], 1)));
     VL_TRY(vl_reserve(c, c->lessFlat[o], (size_t)max(hdr[1], 1)));
     const char* p = (const char*)data + 8;

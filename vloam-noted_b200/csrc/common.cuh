@@ -164,9 +164,15 @@ struct vloam_b200_ctx {
   int nKept, nSharp, nLessSharp, nFlat, nLessFlat;  // host copies (valid after the SR sync point)
   bool sr_counts_valid;
   // look-ahead scan registration (vloam_b200_prefetch_scan[_device]): a second set of every field above (VL_SR_FIELDS)
+  // ... and a third one: a replay may register TWO sweeps ahead.  While sweep k is mapped, sweep k+1's set (srNext, filled during
+  // sweep k-1) feeds the look-ahead odometry and stack filters, and sweep k+2's upload + scan registration run into srNext2; when
+  // sweep k+1 is processed its set is swapped into the context and srNext2 becomes srNext.
   struct SrSet* srNext;       // spare set; holds the results for srNextKey when srNextValid
   const float* srNextKey; int srNextN, srNextStride; bool srNextValid;
-  const float* srPendKey; int srPendN, srPendStride; bool srPendDevice;  // registered, not yet launched
+  struct SrSet* srNext2;      // second spare set (the sweep after srNextKey)
+  const float* srNext2Key; int srNext2N, srNext2Stride; bool srNext2Valid;
+  struct SrPend { const float* key; int n, stride; bool dev; } srPend[2];  // registered, not yet launched (in order)
+  int srPendCount;
   cudaStream_t streamSR;
 
   // ---- laser odometry

@@ -784,7 +784,11 @@ int vl_lo_lookahead(vloam_b200_ctx* c) {
 // while the caller queues the mapping stage (vl_lo_submit_side), or the caller itself (vl_lo_flush_deferred).
 int vl_lo_side_work(vloam_b200_ctx* c) {
   int r = VLOAM_OK;
-  if (c->srDeferred) { c->srDeferred = false; r = vl_launch_lookahead(c); }
+  // Two sweeps registered ahead: the next sweep's scan registration is already done and its look-ahead odometry waits for
+  // nothing but the structures over this sweep's clouds -- they go first, the upload + scan registration of the sweep after next
+  // follow.  One sweep ahead: its scan registration heads the chain SR -> odometry and goes first.
+  const bool srFirst = c->srDeferred && !c->srNextValid;
+  if (srFirst) { c->srDeferred = false; r = vl_launch_lookahead(c); }
   if (r == VLOAM_OK && c->loDeferred) {
     c->loDeferred = false;
     cudaStream_t prev = vl_tls_stream;
@@ -795,6 +799,7 @@ int vl_lo_side_work(vloam_b200_ctx* c) {
     VL_CUDA(cudaEventRecord(c->evLast, c->stream2));
     if (c->timing) VL_CUDA(cudaEventRecord(c->evx[5], c->stream2));
   }
+  if (r == VLOAM_OK && c->srDeferred) { c->srDeferred = false; r = vl_launch_lookahead(c); }
   return r;
 }
 int vl_lo_submit_side(vloam_b200_ctx* c) {
@@ -845,7 +850,7 @@ int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, i
   // map update anyway: they are issued at once.  VLOAM_DEFER_LO_GRIDS=1 restores the old order.)
   static const bool noSide = getenv("VLOAM_NO_SIDE_DEFER") != nullptr;
   const bool defer = !noSide && adoptLO && stacksQueued && c->inProcessFrame && mapThisFrame;
-  if (defer) c->srDeferred = c->srPendKey != nullptr;  // ... and so is the next sweep's scan registration: the helper thread issues both while the caller queues the mapping
+  if (defer) c->srDeferred = c->srPendCount > 0;  // ... and so is the next sweep's scan registration: the helper thread issues both while the caller queues the mapping
   else VL_TRY(vl_launch_lookahead(c));  // the next sweep's scan registration, if one is registered, goes to its side stream now
   VL_HOST_MARK(2);
   VL_TRY(vl_sr_sync_counts(c));  // sync point S1 (event after scan registration; the odometry above is already queued)
