@@ -141,7 +141,7 @@ static int create_impl(vloam_b200_ctx* c, const vloam_b200_params* p, int device
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evLoSolve, cudaEventDisableTiming));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evLoNext, cudaEventDisableTiming));
   VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->streamLO, cudaStreamNonBlocking, pr[4]));
-  c->loNextValid = c->loNextQueued = c->srAdopted = c->s2Done = false; c->loAssumeMonotone = c->inProcessFrame = c->loDeferred = false; c->srDeferred = c->sideSubmitted = false; c->loNextSet = 0; c->stackSel = 0; c->stacksNextReady = false;
+  c->loNextValid = c->loNextQueued = c->srAdopted = c->s2Done = false; c->loAssumeMonotone = c->inProcessFrame = c->loDeferred = false; c->srDeferred = c->sideSubmitted = false; c->preDeferred = c->loPreValid = c->sideWaitsIssued = c->earlyLoArmed = false; c->loNextSet = 0; c->stackSel = 0; c->stacksNextReady = false;
   VL_CUDA_CREATE(cudaMallocHost(&c->h_los, sizeof(LoScalars)));
   LoScalars hl; memset(&hl, 0, sizeof hl); hl.para_q[3] = 1.0; hl.q_w[3] = 1.0;  // LO.cpp:81-91
   VL_CUDA_CREATE(cudaMemcpy(c->los, &hl, sizeof hl, cudaMemcpyHostToDevice));
@@ -266,7 +266,7 @@ int vl_launch_lookahead(vloam_b200_ctx* c) {
     // The generation of the less-sharp / less-flat clouds this run overwrites was the "last" cloud of an odometry solve that is
     // queued already (the previous sweep's, or this sweep's): order the overwrite behind the solves queued so far on the DEVICE
     // (a caller that never syncs -- skipped mapping frames with pose_out == NULL -- gives no host-side guarantee).
-    cudaStreamWaitEvent(c->streamSR, c->evLoSolve, 0);
+    if (!c->sideWaitsIssued) cudaStreamWaitEvent(c->streamSR, c->evLoSolve, 0);
     const float* d_xyz = pd.key;
     if (!pd.dev) {
       r = vl_reserve(c, c->in, (size_t)pd.n * pd.stride);
@@ -285,9 +285,11 @@ int vl_launch_lookahead(vloam_b200_ctx* c) {
 // Drop every look-ahead result (the sweep that arrived is not the registered one, or the state they were computed from was
 // edited).  Their kernels may still be running on streamSR, writing generations the fresh run is about to use: wait for them.
 void vl_drop_lookahead(vloam_b200_ctx* c) {
+  if (c->sideSubmitted) { c->sideSubmitted = false; vl_lm_join(c); }  // (the helper thread may still be issuing side work that sets these flags)
   if (c->srNextValid || c->srNext2Valid) cudaStreamSynchronize(c->streamSR);
   c->srNextValid = c->srNext2Valid = false;
   c->loNextValid = false;
+  c->loPreValid = false;
 }
 
 // this sweep was registered ahead: adopt the spare set (its kernels may still be running on streamSR)

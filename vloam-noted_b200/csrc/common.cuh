@@ -184,6 +184,12 @@ struct vloam_b200_ctx {
   bool inProcessFrame;        // inside process_frame: mapping follows the odometry in the same call
   bool srDeferred, sideSubmitted;  // the registered look-ahead scan registration is issued with the deferred structures; that side work is with the helper thread
   bool loDeferred; int defSet, defNc, defNs; const float4* defCorner; const float4* defSurf;  // side-stream work of the odometry stage queued after the mapping
+  // Two sweeps registered ahead: the search structures over the NEXT sweep's clouds (its scan registration finished a sweep ago)
+  // are built during THIS sweep, into the set this sweep's odometry searched; the next call finds them (loPreValid + the keys below)
+  // and its look-ahead odometry can be queued at once.  preDeferred: that build is part of the deferred side work of this call.
+  bool preDeferred, loPreValid; int preSet, preNc, preNs; const float4* preCorner; const float4* preSurf;
+  bool earlyLoArmed;          // the next sweep's look-ahead odometry is the first item of the side work (its stream waits are issued)
+  bool sideWaitsIssued;       // the caller already ordered streamSR / stream2 behind the last odometry solve (before queuing the next one)
   cudaEvent_t evS2;           // sync point S2 (pose + sizes copied to the host)
   cudaStream_t streamLO;      // the look-ahead odometry of the NEXT sweep runs here, beside this sweep's mapping (own factor buffers)
   cudaEvent_t evLoNext;       // that look-ahead solve has finished (its result is in losNext)
@@ -379,7 +385,9 @@ int vl_sort_set_attrs(vloam_b200_ctx* c);
 int vl_solver_set_attrs(vloam_b200_ctx* c);
 int vl_lo_preload(vloam_b200_ctx* c);
 int vl_lo_lookahead(vloam_b200_ctx* c);
-int vl_lo_lookahead_solve(vloam_b200_ctx* c);   // part 1: queue the next sweep's odometry solve on its own stream
+int vl_lo_lookahead_solve(vloam_b200_ctx* c, bool flush = true, bool waitsIssued = false);   // part 1: queue the next sweep's odometry solve on its own stream (flush: issue the deferred side work first)
+int vl_lo_plan_prebuild(vloam_b200_ctx* c);     // two sweeps ahead: plan the build of the next sweep's search structures as part of this call's side work
+int vl_lo_early_lookahead(vloam_b200_ctx* c, bool* armed);  // ... and queue the next sweep's odometry before this sweep's mapping when its structures are pre-built
 int vl_lo_lookahead_stacks(vloam_b200_ctx* c);  // part 2 (after S2 is recorded): the next sweep's stack filters, if its scan registration is done
 int vl_lo_flush_deferred(vloam_b200_ctx* c);  // queue the deferred side-stream work of the last odometry call (look-ahead scan registration, next search structures)  // queue the NEXT sweep's odometry solve behind this sweep's mapping (no-op unless its scan registration is in flight)
 int vl_vg_preload(vloam_b200_ctx* c);

@@ -875,7 +875,7 @@ __global__ void lm_transform_update(LmScalars* s, const LgHeader* __restrict__ g
   VL_PDL_WAIT();
   // LM.cpp:147-151
   if (threadIdx.x != 0) return;
-  s->gridTop = *gridTop; s->gridDirty = gh->dirty; s->gridDead = gh->dead; s->gridCount = gh->count[0] + gh->count[1]; s->gridCountC = gh->count[0];
+  if (gh) { s->gridTop = *gridTop; s->gridDirty = gh->dirty; s->gridDead = gh->dead; s->gridCount = gh->count[0] + gh->count[1]; s->gridCountC = gh->count[0]; }
   if (s->needSlow) return;  // the sweep is repeated on the pool path: leave the state untouched
   const double* q = s->q_wodom;
   const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
@@ -1562,10 +1562,13 @@ __global__ void __launch_bounds__(256) lm_scan_sorted(const LmScalars* __restric
   if (threadIdx.x == 0) t->sorted[cb] = min(n, firstBad);
 }
 
-__global__ void lm_set_counts(LmScalars* s, RfWork* w, const int* qc, const int* qs) {
+// gh != null (in-place path): the grid's bookkeeping for the host (read at S2) is taken HERE, before this sweep's in-place update can
+// touch it -- that update starts the moment the pose is final, beside lm_transform_update.
+__global__ void lm_set_counts(LmScalars* s, RfWork* w, const int* qc, const int* qs, const LgHeader* __restrict__ gh, const int* __restrict__ gridTop) {
   VL_PDL_WAIT();
 
   if (threadIdx.x != 0) return;
+  if (gh) { s->gridTop = *gridTop; s->gridDirty = gh->dirty; s->gridDead = gh->dead; s->gridCount = gh->count[0] + gh->count[1]; s->gridCountC = gh->count[0]; }
   s->Qc = *qc; s->Qs = *qs;
   // LM.cpp:514: optimise only against a sub-map with > 10 corner and > 50 surf points
   s->optimized = (s->Mc > 10 && s->Ms > 50 && *qc + *qs > 0 && !s->needSlow) ? 1 : 0;
@@ -1819,10 +1822,11 @@ int vl_lm_sync_pools(vloam_b200_ctx* c) {
 }
 
 // the two association + solve passes of LM.cpp:526-717 and transformUpdate (LM.cpp:737); every kernel reads its sizes on the device
-static int lm_queue_passes(vloam_b200_ctx* c, LmDevice* d, int nqBound, bool capture, const LmSub* sub) {
+static int lm_queue_passes(vloam_b200_ctx* c, LmDevice* d, int nqBound, bool capture, const LmSub* sub, bool earlyLO = false, bool earlyPose = false) {
   VL_CUDA(cudaStreamWaitEvent(c->stream, c->evStacks, 0));   // only now are this frame's downsampled stacks needed (side streams)
   VL_CUDA(cudaStreamWaitEvent(c->stream, c->evStacksC, 0));
-  VL_LAUNCH(lm_set_counts, 1, 32, 0, c->lmm, d->work, d->dQ + 2 * c->stackSel, d->dQ + 2 * c->stackSel + 1);
+  VL_LAUNCH(lm_set_counts, 1, 32, 0, c->lmm, d->work, d->dQ + 2 * c->stackSel, d->dQ + 2 * c->stackSel + 1, (const LgHeader*)(earlyPose ? d->grid.hdr : nullptr),
+            (const int*)d->grid.top);
   if (c->timing) VL_CUDA(cudaEventRecord(c->evx[1], c->stream));
   int Qc = 0, Qs = 0;
   if (capture) {  // debug snapshots need host counts first
@@ -1854,13 +1858,16 @@ static int lm_queue_passes(vloam_b200_ctx* c, LmDevice* d, int nqBound, bool cap
     VL_TRY(vl_solve(c, nqBound, &d->work->nq, c->lmm->pose, capture ? &c->dbgLmCost[pass * 2] : nullptr, c->h_lmm->Qc + c->h_lmm->Qs));
     if (c->timing && pass == 0) VL_CUDA(cudaEventRecord(c->evx[2], c->stream));
   }
-  VL_LAUNCH(lm_transform_update, 1, 32, 0, c->lmm, d->grid.hdr, d->grid.top);  // LM.cpp:737 (runs even when the optimisation was skipped)
+  // in-place path: the pose is final HERE -- the map update (own stream) does not wait for transformUpdate
+  if (earlyPose) VL_CUDA(cudaEventRecord(c->evPose, c->stream));
+  VL_LAUNCH(lm_transform_update, 1, 32, 0, c->lmm, (const LgHeader*)(earlyPose ? nullptr : d->grid.hdr), (const int*)d->grid.top);  // LM.cpp:737 (runs even when the optimisation was skipped)
   return VLOAM_OK;
 }
 
 // sync point S2: the pose is final; sizes for the map update.  While the device finishes this sweep's mapping, the next sweep's
 // odometry solve is queued (replays with a registered look-ahead sweep) -- once per call of vl_lm_run.
 static int lm_sync_s2(vloam_b200_ctx* c, bool capture, bool* lookaheadDone) {
+  if (c->sideSubmitted) { c->sideSubmitted = false; VL_TRY(vl_lm_join(c)); }  // (see vl_lm_run: the helper must be done with the context's fields)
   VL_CUDA(cudaEventRecord(c->evPose, c->stream));
   VL_CUDA(cudaMemcpyAsync(c->h_los, c->los, sizeof(LoScalars), cudaMemcpyDeviceToHost, c->stream));
   VL_CUDA(cudaMemcpyAsync(c->h_lmm, c->lmm, sizeof(LmScalars), cudaMemcpyDeviceToHost, c->stream));
@@ -1907,32 +1914,40 @@ int vl_lm_run(vloam_b200_ctx* c) {
   VL_TRY(vl_reserve(c, c->knnOk, (size_t)nqBound));
   VL_TRY(vl_reserve(c, c->factors, (size_t)nqBound * 10));
   VL_TRY(vl_reserve(c, c->factorValid, (size_t)nqBound));
-  bool lookaheadDone = false;
+  bool lookaheadDone = false, earlyLO = false;
   static const bool noWorker = getenv("VLOAM_NO_WORKER") != nullptr;
   const bool inlineUpdate = noWorker || capture || c->prof_name[0];  // profiling and debug snapshots serialise everything
 
   // ---- in-place path: the grid describes this sweep's sub-map unless lm_prepare_fast finds the window moved / the grid dirty
   if (d->gridEnabled && d->gridValid && !capture && d->gridTopUpper + 2LL * nqBound <= d->grid.cap && d->newVoxUpper + nqBound <= LG_NEWVOX_MAX) {
-    if (!inlineUpdate) VL_TRY(vl_lo_submit_side(c));  // the helper thread issues the look-ahead scan registration + the next odometry structures meanwhile
+    if (!inlineUpdate) {
+      VL_TRY(vl_lo_early_lookahead(c, &earlyLO));  // (two sweeps ahead, structures pre-built: the next sweep's odometry heads the side work)
+      lookaheadDone = earlyLO;
+      VL_TRY(vl_lo_plan_prebuild(c));
+    }
     VL_LAUNCH(lm_prepare_fast, 1, 256, 0, c->lmm, c->los, d->work, d->grid.hdr, 0, resetValid);
+    // the helper thread issues the next sweep's odometry (early mode), the look-ahead scan registration and the next odometry structures
+    // meanwhile.  (It swaps scan-registration sets and the odometry state in and out of the context while it does: submitted only
+    // after the launch above has read c->los, joined before lm_sync_s2 reads it again.)
+    if (!inlineUpdate) VL_TRY(vl_lo_submit_side(c));
     if (c->timing) VL_CUDA(cudaEventRecord(c->evx[0], c->stream));
-    VL_TRY(lm_queue_passes(c, d, nqBound, false, d->subReal));
+    VL_TRY(lm_queue_passes(c, d, nqBound, false, d->subReal, earlyLO, true));
     // The in-place map update is queued NOW, behind the pose (evPose) on its own stream, before the host waits at S2: its kernels
     // read the counts and the needSlow flag on the device (sizes here are bounds), so the device runs it the moment the pose is
     // final instead of waiting for S2 -> host -> helper thread -> launch (~45 us on the chain the next sweep's mapping waits for).
     // the next sweep's odometry solve goes to its own stream first: its inputs are ready long before this sweep's pose is
-    VL_TRY(vl_lo_flush_deferred(c));
-    VL_TRY(vl_lo_lookahead_solve(c));
-    lookaheadDone = true;
+    if (!lookaheadDone) {
+      VL_TRY(vl_lo_flush_deferred(c));
+      VL_TRY(vl_lo_lookahead_solve(c));
+      lookaheadDone = true;
+    }
     VL_TRY(lm_pool_headroom(c, 0, 0, nqBound, nqBound));  // (points outside the window are appended raw to their cubes' pool segments: room for them
                                                           // is checked BEFORE the append is queued, with the bound, against the pool top of the last S2)
-    VL_CUDA(cudaEventRecord(c->evPose, c->stream));
     {
       const int nq = nqBound;
       const float4* const stackCp = c->stackC.p; const float4* const stackSp = c->stackS.p;
       vl_tls_stream = c->stream3;
       struct Restore { ~Restore() { vl_tls_stream = nullptr; } } restore;
-      VL_CUDA(cudaStreamWaitEvent(c->stream3, c->evPose, 0));
       int H = 1024; while (H < 4 * nq) H <<= 1;
       VL_TRY(vl_reserve(c, d->newPts, (size_t)nq));
       VL_TRY(vl_reserve(c, d->newCube, (size_t)nq));
@@ -1941,9 +1956,12 @@ int vl_lm_run(vloam_b200_ctx* c) {
       MuWork mw;
       mw.hkey = d->muKey.p; mw.H = H; mw.hlead = d->muInt.p; mw.slotOf = mw.hlead + H; mw.memberCnt = mw.slotOf + nq;
       mw.members = mw.memberCnt + nq; mw.anyOutside = mw.members + (size_t)nq * MU_MEMBERS;
+      // (the scratch is cleared behind the previous update, on its stream, BEFORE the wait for this sweep's pose: off the chain)
+      VL_CUDA(cudaStreamWaitEvent(c->stream3, c->evAux, 0));                // (anyOutside is read by the previous sweep's append on streamAux)
       VL_CUDA(cudaMemsetAsync(mw.hkey, 0xff, (size_t)H * 8, c->stream3));   // empty slots
       VL_CUDA(cudaMemsetAsync(mw.hlead, 0x7f, (size_t)H * 4, c->stream3));  // "no leader yet" (0x7f7f7f7f > any stack index)
       VL_CUDA(cudaMemsetAsync(mw.anyOutside, 0, 4, c->stream3));
+      VL_CUDA(cudaStreamWaitEvent(c->stream3, c->evPose, 0));
       VL_BYTES(16.0 * max(c->h_lmm->Qc + c->h_lmm->Qs, 1));  // SURVEY 8(d) B_lm insert term: every new point once (last known count)
       VL_LAUNCH(mu_keys, vl_div_up(nq, 256), 256, 0, c->lmm, d->work, c->prm, stackCp, stackSp, d->newPts.p, d->newCube.p, mw);
       VL_CUDA(cudaEventRecord(c->evKeys, c->stream3));  // nothing below reads the stacks any more: the next sweep's filters may overwrite them

@@ -570,7 +570,7 @@ int vl_lo_build_last(vloam_b200_ctx* c, int set, const float4* corner, int nc, c
   const int n = nc + ns;
   cudaStream_t st = VL_STREAM(c);  // (the caller selects the side stream through vl_tls_stream: the helper thread may be the one issuing this)
   // set `set` was searched by the odometry solve before the current one: rebuild it only behind the solves queued so far
-  VL_CUDA(cudaStreamWaitEvent(st, c->evLoSolve, 0));
+  if (!c->sideWaitsIssued) VL_CUDA(cudaStreamWaitEvent(st, c->evLoSolve, 0));
   int* tbl = c->loRingTbl + set * 2 * (LO_TBL + 1);
   VL_LAUNCH(lo_ring_table_init, 1, 32, 0, tbl);
   VL_LAUNCH(lo_ring_table, dim3(vl_div_up(max(max(nc, ns), LO_TBL + 1), 256), 2), 256, 0, corner, nc, surf, ns, tbl);
@@ -708,21 +708,27 @@ static int lo_queue_solve(vloam_b200_ctx* c, const double* prior_q, const double
 // laser_odometry call adopts the copy if it is for that sweep and ignores it otherwise.
 // Part 1 (vl_lo_lookahead_solve) queues the solve; part 2 (vl_lo_lookahead_stacks), called after sync point S2 has been recorded, issues the next
 // sweep's stack filters if its scan registration finishes before this sweep's mapping does.
-int vl_lo_lookahead_solve(vloam_b200_ctx* c) {
+static bool lo_lookahead_possible(const vloam_b200_ctx* c) {
   static const bool off = getenv("VLOAM_NO_LO_LOOKAHEAD") != nullptr;
-  c->loNextValid = false; c->loNextQueued = false;
-  VL_TRY(vl_lo_flush_deferred(c));  // (records evLast)
-  if (off || !c->srNextValid || !c->lo_inited || c->prof_name[0] || vl_debug_capture(c)) return VLOAM_OK;
-  // The structures over this sweep's clouds are still being built on the side stream: wait for them on the DEVICE and
-  // assume what the host cannot know yet -- that both clouds have monotone ring ids, i.e. the grid search applies.
-  // The flags are checked when the result is adopted; a wrong guess only discards the look-ahead.
-  const int set = c->lastSet;
-  if (!c->loGridValid[set]) return VLOAM_OK;
-  // It runs on its own stream, BESIDE this sweep's mapping (own factor slots): it needs this sweep's odometry result (evLoSolve),
-  // the structures over this sweep's clouds (evLast) and the next sweep's features (evSRfeat) -- nothing of the mapping.
+  return !off && c->srNextValid && c->lo_inited && !c->prof_name[0] && !vl_debug_capture(c) && c->loGridValid[c->lastSet];
+}
+// It runs on its own stream, BESIDE this sweep's mapping (own factor slots): it needs this sweep's odometry result (evLoSolve),
+// the structures over this sweep's clouds (evLast) and the next sweep's features (evSRfeat) -- nothing of the mapping.
+static int lo_lookahead_waits(vloam_b200_ctx* c) {
   VL_CUDA(cudaStreamWaitEvent(c->streamLO, c->evLoSolve, 0));
   VL_CUDA(cudaStreamWaitEvent(c->streamLO, c->evLast, 0));
   VL_CUDA(cudaStreamWaitEvent(c->streamLO, c->srNext->evSRfeat, 0));  // (sharp + flat of the next sweep: not its per-ring voxel filter)
+  return VLOAM_OK;
+}
+int vl_lo_lookahead_solve(vloam_b200_ctx* c, bool flush, bool waitsIssued) {
+  c->loNextValid = false; c->loNextQueued = false;
+  if (flush) VL_TRY(vl_lo_flush_deferred(c));  // (records evLast)
+  // The structures over this sweep's clouds may still be being built on the side stream: wait for them on the DEVICE and
+  // assume what the host cannot know yet -- that both clouds have monotone ring ids, i.e. the grid search applies.
+  // The flags are checked when the result is adopted; a wrong guess only discards the look-ahead.
+  if (!lo_lookahead_possible(c)) return VLOAM_OK;
+  const int set = c->lastSet;
+  if (!waitsIssued) VL_TRY(lo_lookahead_waits(c));
   if (c->timing) cudaEventRecord(c->evx[9], c->streamLO);
   VL_CUDA(cudaMemcpyAsync(c->losNext, c->los, sizeof(LoScalars), cudaMemcpyDeviceToDevice, c->streamLO));
   const int curNow = c->cur;
@@ -775,7 +781,7 @@ int vl_lo_lookahead_stacks(vloam_b200_ctx* c) {
   return VLOAM_OK;
 }
 int vl_lo_lookahead(vloam_b200_ctx* c) {
-  VL_TRY(vl_lo_lookahead_solve(c));
+  VL_TRY(vl_lo_lookahead_solve(c, true));
   return vl_lo_lookahead_stacks(c);
 }
 
@@ -784,26 +790,68 @@ int vl_lo_lookahead(vloam_b200_ctx* c) {
 // while the caller queues the mapping stage (vl_lo_submit_side), or the caller itself (vl_lo_flush_deferred).
 int vl_lo_side_work(vloam_b200_ctx* c) {
   int r = VLOAM_OK;
-  // Two sweeps registered ahead: the next sweep's scan registration is already done and its look-ahead odometry waits for
-  // nothing but the structures over this sweep's clouds -- they go first, the upload + scan registration of the sweep after next
-  // follow.  One sweep ahead: its scan registration heads the chain SR -> odometry and goes first.
-  const bool srFirst = c->srDeferred && !c->srNextValid;
+  // One sweep ahead: its scan registration heads the chain SR -> odometry and goes first.  Two sweeps ahead: the next sweep's scan
+  // registration is done; when its odometry is queued already (sideWaitsIssued) nothing waits for the builds and the upload +
+  // scan registration of the sweep after next, the longest chain, goes first; otherwise that odometry waits for the structures over
+  // this sweep's clouds and they go first.
+  if (c->earlyLoArmed) {  // the next sweep's odometry: its stream waits were issued by the caller before anything below re-records their events
+    c->earlyLoArmed = false;
+    r = vl_lo_lookahead_solve(c, false, true);
+    if (r != VLOAM_OK) { c->sideWaitsIssued = false; return r; }
+  }
+  const bool srFirst = c->srDeferred && (!c->srNextValid || c->sideWaitsIssued);
   if (srFirst) { c->srDeferred = false; r = vl_launch_lookahead(c); }
-  if (r == VLOAM_OK && c->loDeferred) {
-    c->loDeferred = false;
+  if (r == VLOAM_OK && (c->loDeferred || c->preDeferred)) {
     cudaStream_t prev = vl_tls_stream;
     vl_tls_stream = c->stream2;
-    r = vl_lo_build_last(c, c->defSet, c->defCorner, c->defNc, c->defSurf, c->defNs);
+    if (c->loDeferred) { c->loDeferred = false; r = vl_lo_build_last(c, c->defSet, c->defCorner, c->defNc, c->defSurf, c->defNs); }
+    if (r == VLOAM_OK && c->preDeferred) {  // the structures of the NEXT sweep, into the set this sweep's odometry searched
+      c->preDeferred = false;
+      r = vl_lo_build_last(c, c->preSet, c->preCorner, c->preNc, c->preSurf, c->preNs);
+      c->loPreValid = r == VLOAM_OK;
+    }
     vl_tls_stream = prev;
-    if (r != VLOAM_OK) return r;
+    if (r != VLOAM_OK) { c->sideWaitsIssued = false; return r; }
     VL_CUDA(cudaEventRecord(c->evLast, c->stream2));
     if (c->timing) VL_CUDA(cudaEventRecord(c->evx[5], c->stream2));
   }
   if (r == VLOAM_OK && c->srDeferred) { c->srDeferred = false; r = vl_launch_lookahead(c); }
+  c->sideWaitsIssued = false;
   return r;
 }
+// Plan the pre-build (caller thread, before the side work is submitted): the next sweep's clouds and counts are known when its
+// scan registration has finished.  Set lastSet ^ 1 is the one this sweep's odometry searched.
+int vl_lo_plan_prebuild(vloam_b200_ctx* c) {
+  c->preDeferred = false;
+  static const bool off = getenv("VLOAM_NO_PREBUILD") != nullptr;
+  if (off || !c->srNextValid || c->loPreValid || cudaEventQuery(c->srNext->evSR) != cudaSuccess) { (void)cudaGetLastError(); return VLOAM_OK; }
+  vl_sr_swap(c, *c->srNext);
+  const int r = vl_sr_sync_counts(c);
+  c->preCorner = c->lessSharp[c->cur].p; c->preNc = c->nLessSharp; c->preSurf = c->lessFlat[c->cur].p; c->preNs = c->nLessFlat;
+  vl_sr_swap(c, *c->srNext);
+  if (r != VLOAM_OK) return r;
+  c->preSet = c->lastSet ^ 1;
+  c->preDeferred = true;
+  return VLOAM_OK;
+}
+// Early look-ahead (two sweeps ahead, structures pre-built): the next sweep's odometry is queued BEFORE this sweep's mapping
+// launches -- its inputs are complete -- and the side streams are ordered behind the odometry solves queued so far first, because
+// the solve queued here re-records evLoSolve (the side work must wait for this sweep's solve, not for the next one's).
+// Only the stream WAITS are issued here (they capture the events' current records: evLast before the side work re-records it,
+// evLoSolve before the solve itself does); the launches follow once the first mapping pass is queued (vl_lo_lookahead_solve with
+// waitsIssued), so the mapping's first kernels are not held back by ~20 us of launch calls.
+int vl_lo_early_lookahead(vloam_b200_ctx* c, bool* armed) {
+  *armed = false;
+  if (c->loDeferred || c->sideSubmitted || !c->srAdopted || !lo_lookahead_possible(c)) return VLOAM_OK;  // (loDeferred: the structures over this sweep's clouds are not built yet)
+  VL_CUDA(cudaStreamWaitEvent(c->streamSR, c->evLoSolve, 0));
+  VL_CUDA(cudaStreamWaitEvent(c->stream2, c->evLoSolve, 0));
+  c->sideWaitsIssued = true;
+  VL_TRY(lo_lookahead_waits(c));
+  *armed = true; c->earlyLoArmed = true;
+  return VLOAM_OK;
+}
 int vl_lo_submit_side(vloam_b200_ctx* c) {
-  if (!c->srDeferred && !c->loDeferred) return VLOAM_OK;
+  if (!c->srDeferred && !c->loDeferred && !c->preDeferred && !c->earlyLoArmed) { c->sideWaitsIssued = false; return VLOAM_OK; }
   VL_TRY(vl_lm_submit_task(c, vl_lo_side_work));
   c->sideSubmitted = true;
   return VLOAM_OK;
@@ -856,7 +904,13 @@ int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, i
   VL_TRY(vl_sr_sync_counts(c));  // sync point S1 (event after scan registration; the odometry above is already queued)
   if (mapThisFrame && !stacksQueued)
     VL_TRY(vl_lm_enqueue_stacks(c, c->lessSharp[c->cur].p, c->nLessSharp, c->lessFlat[c->cur].p, c->nLessFlat));
-  if (defer) {
+  // built during the previous sweep (two sweeps registered ahead)?
+  const bool preHit = c->loPreValid && c->srAdopted && c->preSet == (c->lastSet ^ 1) && c->preCorner == c->lessSharp[c->cur].p && c->preNc == c->nLessSharp &&
+                      c->preSurf == c->lessFlat[c->cur].p && c->preNs == c->nLessFlat && c->loGridValid[c->lastSet ^ 1];
+  c->loPreValid = false;
+  if (preHit) {
+    // nothing to build: evLast was recorded behind that build
+  } else if (defer) {
     c->loDeferred = true; c->defSet = c->lastSet ^ 1;
     c->defCorner = c->lessSharp[c->cur].p; c->defNc = c->nLessSharp; c->defSurf = c->lessFlat[c->cur].p; c->defNs = c->nLessFlat;
   } else {  // LO.cpp:573-574 (setInputCloud on both KD-trees) for the clouds that become "last" after this solve:
