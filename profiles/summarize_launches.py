@@ -1,4 +1,7 @@
-"""Summarise an ncu `--metrics gpu__time_duration.sum --csv` launch list: per-kernel share of the last frame."""
+"""Summarise an ncu `--metrics gpu__time_duration.sum --csv` launch list: per-kernel time per sweep and share.
+With two sweeps registered ahead the launches of three sweeps interleave (scan registration of k+2, odometry of k+1, mapping of
+k), so the list is not cut into frames: totals over the capture are divided by the number of mapping stages in it
+(one lm_prepare_fast / lm_prepare per sweep)."""
 import collections, csv, io, sys
 path = sys.argv[1]
 lines = [l for l in open(path) if not l.startswith("==")]
@@ -9,14 +12,13 @@ for row in csv.DictReader(io.StringIO("".join(lines))):
     v = float(row["Metric Value"].replace(",", ""))
     unit = row["Metric Unit"]
     v = v / 1e3 if unit == "ns" else (v * 1e3 if unit == "ms" else v)
-    rows.append((row["Kernel Name"].split("(")[0].replace("void ", ""), v))
-starts = [i for i, (n, _) in enumerate(rows) if n.startswith("sr_find_bounds")]
-last = rows[starts[-2]:starts[-1]] if len(starts) >= 2 else rows
+    rows.append((row["Kernel Name"].split("(")[0].replace("void ", "").split("<")[0], v))
+frames = max(1, sum(1 for n, _ in rows if n in ("lm_prepare_fast", "lm_prepare")))
 tot, cnt = collections.defaultdict(float), collections.Counter()
-for n, v in last:
+for n, v in rows:
     tot[n] += v; cnt[n] += 1
 s = sum(tot.values())
-print("last complete frame of %s: %d launches, %.1f us of kernel time (ncu: cold cache, serialised)" % (path, len(last), s))
-print("%-28s %6s %10s %7s" % ("kernel", "count", "us", "share"))
+print("%s: %d launches over %d sweeps = %.1f launches and %.1f us of kernel time per sweep (ncu: cold cache, serialised)" % (path, len(rows), frames, len(rows) / frames, s / frames))
+print("%-28s %10s %12s %7s" % ("kernel", "per sweep", "us / sweep", "share"))
 for n, v in sorted(tot.items(), key=lambda x: -x[1]):
-    print("%-28s %6d %10.1f %6.1f%%" % (n, cnt[n], v, 100 * v / s))
+    print("%-28s %10.2f %12.1f %6.1f%%" % (n, cnt[n] / frames, v / frames, 100 * v / s))
