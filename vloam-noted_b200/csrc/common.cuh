@@ -188,6 +188,7 @@ struct vloam_b200_ctx {
   // are built during THIS sweep, into the set this sweep's odometry searched; the next call finds them (loPreValid + the keys below)
   // and its look-ahead odometry can be queued at once.  preDeferred: that build is part of the deferred side work of this call.
   bool preDeferred, loPreValid; int preSet, preNc, preNs; const float4* preCorner; const float4* preSurf;
+  bool stacksAdopted;         // this sweep's stacks were filtered during the previous sweep (look-ahead) and adopted
   bool earlyLoArmed;          // the next sweep's look-ahead odometry is the first item of the side work (its stream waits are issued)
   bool sideWaitsIssued;       // the caller already ordered streamSR / stream2 behind the last odometry solve (before queuing the next one)
   cudaEvent_t evS2;           // sync point S2 (pose + sizes copied to the host)

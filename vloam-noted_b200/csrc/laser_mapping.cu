@@ -559,8 +559,11 @@ __global__ void __launch_bounds__(256) lg_rebuild(LgGrid g, const LmSub* __restr
 // rolls, the valid list was reset (LM.cpp:132-136) and the grid is clean, this sweep's sub-map IS the grid: no table
 // is touched.  Otherwise needSlow is raised: every later kernel of the sweep returns at once and the host repeats the
 // mapping stage through lm_prepare (the pool path).  The pose arithmetic is lm_prepare's, statement for statement.
+// qc != null: lm_set_counts' work is done here as well (in-place path: one launch fewer on the pose chain; the stacks are filtered
+// long before the odometry result arrives).
 __global__ void __launch_bounds__(256) lm_prepare_fast(LmScalars* __restrict__ s, const LoScalars* __restrict__ lo, RfWork* __restrict__ w,
-                                                       LgHeader* __restrict__ gh, int skip, int resetValid) {
+                                                       LgHeader* __restrict__ gh, int skip, int resetValid, const int* __restrict__ qc = nullptr,
+                                                       const int* __restrict__ qs = nullptr, const int* __restrict__ gridTop = nullptr) {
   VL_PDL_WAIT();
   if (threadIdx.x <= LM_NSEG && !skip) { w->segCount[threadIdx.x] = 0; w->segFill[threadIdx.x] = 0; }
   if (threadIdx.x != 0) return;
@@ -589,6 +592,12 @@ __global__ void __launch_bounds__(256) lm_prepare_fast(LmScalars* __restrict__ s
                     s->cenH == gh->cenH && s->cenD == gh->cenD;
   s->needSlow = same ? 0 : 1;
   if (same) { s->validNum = gh->validNum; s->Mc = gh->count[0]; s->Ms = gh->count[1]; gh->nOps = 0; }
+  if (qc) {  // == lm_set_counts
+    s->gridTop = *gridTop; s->gridDirty = gh->dirty; s->gridDead = gh->dead; s->gridCount = gh->count[0] + gh->count[1]; s->gridCountC = gh->count[0];
+    s->Qc = *qc; s->Qs = *qs;
+    s->optimized = (s->Mc > 10 && s->Ms > 50 && *qc + *qs > 0 && !s->needSlow) ? 1 : 0;
+    w->nq = s->optimized ? *qc + *qs : 0;
+  }
 }
 
 // One warp per downsampled feature: 5-NN in the 3x3x3 cell neighbourhood of the voxel-hash grid (exact inside the 1 m
@@ -1822,10 +1831,13 @@ int vl_lm_sync_pools(vloam_b200_ctx* c) {
 }
 
 // the two association + solve passes of LM.cpp:526-717 and transformUpdate (LM.cpp:737); every kernel reads its sizes on the device
-static int lm_queue_passes(vloam_b200_ctx* c, LmDevice* d, int nqBound, bool capture, const LmSub* sub, bool earlyLO = false, bool earlyPose = false) {
+static int lm_queue_passes(vloam_b200_ctx* c, LmDevice* d, int nqBound, bool capture, const LmSub* sub, bool earlyLO = false, bool earlyPose = false,
+                           bool countsSet = false) {
+  if (!countsSet) {
   VL_CUDA(cudaStreamWaitEvent(c->stream, c->evStacks, 0));   // only now are this frame's downsampled stacks needed (side streams)
   VL_CUDA(cudaStreamWaitEvent(c->stream, c->evStacksC, 0));
-  VL_LAUNCH(lm_set_counts, 1, 32, 0, c->lmm, d->work, d->dQ + 2 * c->stackSel, d->dQ + 2 * c->stackSel + 1, (const LgHeader*)(earlyPose ? d->grid.hdr : nullptr),
+  }
+  if (!countsSet) VL_LAUNCH(lm_set_counts, 1, 32, 0, c->lmm, d->work, d->dQ + 2 * c->stackSel, d->dQ + 2 * c->stackSel + 1, (const LgHeader*)(earlyPose ? d->grid.hdr : nullptr),
             (const int*)d->grid.top);
   if (c->timing) VL_CUDA(cudaEventRecord(c->evx[1], c->stream));
   int Qc = 0, Qs = 0;
@@ -1897,7 +1909,7 @@ int vl_lm_run(vloam_b200_ctx* c) {
   VL_CUDA(cudaStreamWaitEvent(c->stream, c->evMap, 0));  // the previous frame's map update (stream3) must be complete
   VL_CUDA(cudaStreamWaitEvent(c->stream, c->evAux, 0));  // ... including its outside appends (streamAux, pool path)
   if (skip) {  // LM.cpp:197-201: only the high-frequency pose is propagated
-    VL_LAUNCH(lm_prepare_fast, 1, 256, 0, c->lmm, c->los, d->work, d->grid.hdr, 1, resetValid);
+    VL_LAUNCH(lm_prepare_fast, 1, 256, 0, c->lmm, c->los, d->work, d->grid.hdr, 1, resetValid, (const int*)nullptr, (const int*)nullptr, (const int*)nullptr);
     VL_TRY(vl_lo_flush_deferred(c)); VL_CUDA(cudaGetLastError());
     return VLOAM_OK;
   }
@@ -1925,13 +1937,21 @@ int vl_lm_run(vloam_b200_ctx* c) {
       lookaheadDone = earlyLO;
       VL_TRY(vl_lo_plan_prebuild(c));
     }
-    VL_LAUNCH(lm_prepare_fast, 1, 256, 0, c->lmm, c->los, d->work, d->grid.hdr, 0, resetValid);
+    // stacks filtered a sweep ago (look-ahead): the counts are set by lm_prepare_fast itself, one launch fewer on the pose chain
+    const bool countsSet = c->stacksAdopted;
+    if (countsSet) {
+      VL_CUDA(cudaStreamWaitEvent(c->stream, c->evStacks, 0));
+      VL_CUDA(cudaStreamWaitEvent(c->stream, c->evStacksC, 0));
+      VL_LAUNCH(lm_prepare_fast, 1, 256, 0, c->lmm, c->los, d->work, d->grid.hdr, 0, resetValid, (const int*)(d->dQ + 2 * c->stackSel),
+                (const int*)(d->dQ + 2 * c->stackSel + 1), (const int*)d->grid.top);
+    } else
+    VL_LAUNCH(lm_prepare_fast, 1, 256, 0, c->lmm, c->los, d->work, d->grid.hdr, 0, resetValid, (const int*)nullptr, (const int*)nullptr, (const int*)nullptr);
     // the helper thread issues the next sweep's odometry (early mode), the look-ahead scan registration and the next odometry structures
     // meanwhile.  (It swaps scan-registration sets and the odometry state in and out of the context while it does: submitted only
     // after the launch above has read c->los, joined before lm_sync_s2 reads it again.)
     if (!inlineUpdate) VL_TRY(vl_lo_submit_side(c));
     if (c->timing) VL_CUDA(cudaEventRecord(c->evx[0], c->stream));
-    VL_TRY(lm_queue_passes(c, d, nqBound, false, d->subReal, earlyLO, true));
+    VL_TRY(lm_queue_passes(c, d, nqBound, false, d->subReal, earlyLO, true, countsSet));
     // The in-place map update is queued NOW, behind the pose (evPose) on its own stream, before the host waits at S2: its kernels
     // read the counts and the needSlow flag on the device (sizes here are bounds), so the device runs it the moment the pose is
     // final instead of waiting for S2 -> host -> helper thread -> launch (~45 us on the chain the next sweep's mapping waits for).

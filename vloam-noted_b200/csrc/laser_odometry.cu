@@ -875,9 +875,10 @@ int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, i
   // filters of this sweep go to the helper thread now instead of behind the odometry launches.
   const bool mapThisFrame = ((c->lo_frameCount + 1) % c->prm.mapping_skip_frame) == 0;  // LO.cpp:668
   bool stacksQueued = false;
+  c->stacksAdopted = false;
   if (c->stacksNextReady) {  // this sweep's stacks were filtered underneath the previous sweep's mapping
     c->stacksNextReady = false;
-    if (c->srAdopted && mapThisFrame) { VL_TRY(vl_sr_sync_counts(c)); VL_TRY(vl_lm_adopt_stacks_next(c)); stacksQueued = true; }
+    if (c->srAdopted && mapThisFrame) { VL_TRY(vl_sr_sync_counts(c)); VL_TRY(vl_lm_adopt_stacks_next(c)); stacksQueued = true; c->stacksAdopted = true; }
   }
   if (!stacksQueued && early && mapThisFrame && cudaEventQuery(c->evSR) == cudaSuccess) {
     VL_TRY(vl_sr_sync_counts(c));
