@@ -19,7 +19,8 @@
  *
  * Execution model.  A context owns several CUDA streams (the pose chain, side
  * streams for the stack filters / search structures / map update / look-ahead
- * scan registration) and one helper host thread that issues the map update.
+ * scan registration and look-ahead odometry) and one helper host thread that issues side-stream launches.
+ * The laserMapping sub-map is a persistent device voxel-hash grid that the per-sweep map update edits in place.
  * Calls queue work and return early where they can; the host blocks at
  *   S1  after scan registration, for the feature counts (inside laser_odometry),
  *   S2  after the mapping solve, for the pose and map sizes (inside
@@ -90,10 +91,13 @@ int vloam_b200_begin_frame(vloam_b200_ctx* c);
  * `stride` floats apart (3 for packed XYZ, 4 for KITTI x,y,z,r).  Asynchronous
  * with respect to the host unless a getter is called. */
 int vloam_b200_scan_registration(vloam_b200_ctx* c, const float* xyz, int n, int stride);
-/* Optional look-ahead for replays: register the NEXT sweep (host pointer -- pinned for an asynchronous copy -- or
- * device pointer).  Its scan registration is queued on a side stream from inside the processing of the current
- * sweep and runs underneath that sweep's odometry and mapping; the following scan_registration / process_frame
- * call with the same (pointer, n, stride) finds the work done, any other call ignores it.  CONTRACT: adoption is keyed
+/* Optional look-ahead for replays: register the NEXT sweep, or the next TWO sweeps in order (host pointer -- pinned for
+ * an asynchronous copy -- or device pointer; registering a buffer that is already registered is a no-op, a third pending
+ * registration replaces the second).  Upload and scan registration of a registered sweep are queued on a side stream from
+ * inside the processing of the current sweep and run underneath that sweep's odometry and mapping; with two sweeps ahead the
+ * odometry and the stack filters of sweep k+1 run beside the mapping of sweep k as well.  The scan_registration /
+ * process_frame call with the same (pointer, n, stride) finds the work done; a call with any other buffer drops everything
+ * that was registered or computed ahead and runs the plain path.  CONTRACT: adoption is keyed
  * on (pointer, n, stride) only -- the buffer must stay valid AND UNCHANGED from this call until the scan_registration /
  * process_frame call that consumes it returns; a caller that refills one buffer in place must not register it.
  * Results are bit-identical with or without the look-ahead.  No reference counterpart: the bag player hands over one
