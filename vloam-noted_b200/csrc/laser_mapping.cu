@@ -1310,86 +1310,36 @@ __global__ void __launch_bounds__(1024) rf_append_outside(LmScalars* __restrict_
 }
 
 // ---- in-place map update on the voxel-hash grid (LM.cpp:741-808 without touching the other ~1M points) -------------------
-// pcl::VoxelGrid over [cube cloud ; this sweep's points] changes only the voxels the new points fall into.  Three launches:
+// pcl::VoxelGrid over [cube cloud ; this sweep's points] changes only the voxels the new points fall into.  Two launches:
 //   mu_keys   every new point: world transform (LM.cpp:744, 768), cube, voxel key; points of the same (cube, voxel) meet in a
-//             small open-addressing hash table, whose entry keeps the lowest stack index as the group's leader
-//   mu_group  every other point of a group registers with its leader
-//   mu_apply  every leader: its members in stack order (<= 8: the stacks are voxel-filtered at the same leaf), the map point
-//             of that voxel looked up IN THE GRID -- it lies inside the voxel's box, i.e. in one of the <= 2x2x2 cells the box
-//             overlaps -- and the fold exactly as VoxelGrid does it: map point first (it has the lower index), then the new
-//             points in stack order, f32 sums, one division.  The centroid is stored back in place, or appended to its cell
+//             small open-addressing hash table: the point that claims the slot leads the group and looks the map point of that
+//             voxel up IN THE GRID -- it lies inside the voxel's box, i.e. in one of the <= 2x2x2 cells the box overlaps --
+//             and every point appends itself to the slot's member list
+//   mu_apply  every leader: the fold exactly as VoxelGrid does it: map point first (it has the lower index), then the members
+//             in stack order, f32 sums, one division.  The centroid is stored back in place, or appended to its cell
 //             when the voxel is new or the centroid left its 2 m cell (the old entry is tombstoned).
 // No sort: round 1's update sorted (segment | voxel | order) keys, 30 us for the one cube that holds most of a sweep.
 // A centroid that no longer maps to its own voxel (f32 rounding at a voxel face) is legal -- the next VoxelGrid pass re-keys
 // it -- but outside the in-place scheme: it raises `dirty`, and the next sweep runs the pool path on materialised cubes.
-#define MU_MEMBERS 15
+#define MU_CAP 16           // members of a voxel group kept in its slot (a world voxel collects at most the points of the ~8 lidar-frame
+                            // voxels it overlaps -- the stacks are voxel-filtered at the same leaf; more: the leader walks the stack)
 struct MuWork {            // device scratch of one update (sized by the host for nq points)
   unsigned long long* hkey;  // [H] hash table: (segment << 32 | voxel key) or empty
-  int* hlead;                // [H] lowest stack index of the group
+  int* cnt;                  // [H] points of the group
   int H;                     // power of two >= 4 nq
-  int* slotOf;               // [nq] hash slot of point i, -1: not in a valid cube
-  int* memberCnt;            // [nq]
-  int* members;              // [nq * MU_MEMBERS]
+  int* slotOf;               // [nq] hash slot of point i (| MU_LEAD for the point that claimed the slot), -1: not in a valid cube
+  int* found;                // [nq] leaders: grid entry of the voxel's map point (-1: new voxel), and the cell it sits in
+  int* foundCell;            // [nq]
+  int* members;              // [H * MU_CAP] stack indices, in arrival order
   int* anyOutside;           // a point fell into a cube outside the 5x5x3 window (rf_append_outside has work)
 };
+#define MU_LEAD 0x40000000
 __device__ __forceinline__ unsigned mu_hash(unsigned long long k) { k ^= k >> 31; k *= 0x9E3779B97F4A7C15ull; k ^= k >> 29; return (unsigned)k; }
 
-__global__ void __launch_bounds__(256) mu_keys(const LmScalars* __restrict__ s, const RfWork* __restrict__ w, vloam_b200_params prm,
-                                               const float4* __restrict__ stackC, const float4* __restrict__ stackS, float4* __restrict__ newPts,
-                                               int* __restrict__ newCube, MuWork m) {
-  VL_PDL_WAIT();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int Qc = s->Qc, Qs = s->Qs;
-  if (s->needSlow || i >= Qc + Qs) return;  // (queued before the host knows whether the sweep stays on the in-place path, and with a bound on the count)
-  const int kind = i >= Qc;
-  const float4 po = kind ? stackS[i - Qc] : stackC[i];
-  double r[3];
-  vl_qrot(s->pose, (double)po.x, (double)po.y, (double)po.z, r);
-  const float4 p = make_float4((float)(r[0] + s->pose[4]), (float)(r[1] + s->pose[5]), (float)(r[2] + s->pose[6]), po.w);
-  const int ci = lm_cube_of(p.x, s->cenW), cj = lm_cube_of(p.y, s->cenH), ck = lm_cube_of(p.z, s->cenD);
-  int cb = -1;
-  if (ci >= 0 && ci < VL_CUBE_W && cj >= 0 && cj < VL_CUBE_H && ck >= 0 && ck < VL_CUBE_D) cb = ci + VL_CUBE_W * cj + VL_CUBE_W * VL_CUBE_H * ck;
-  newPts[i] = p;
-  const int slot = cb >= 0 ? w->slotOfCube[cb] : -1;
-  newCube[i] = (cb >= 0 && slot < 0) ? cb : -1;  // only cubes outside the window need the raw append path
-  m.memberCnt[i] = 0;
-  int hs = -1;
-  if (slot >= 0) {
-    const unsigned vk = lm_vox_key(p, lm_leaf_inv(prm, kind), ci, cj, ck, s->cenW, s->cenH, s->cenD);
-    const unsigned long long key = ((unsigned long long)(kind * VL_MAX_VALID + slot) << 32) | vk;
-    unsigned h = mu_hash(key) & (unsigned)(m.H - 1);
-    for (;;) {
-      const unsigned long long prev = atomicCAS(&m.hkey[h], ~0ull, key);
-      if (prev == ~0ull || prev == key) break;
-      h = (h + 1) & (unsigned)(m.H - 1);
-    }
-    atomicMin(&m.hlead[h], i);
-    hs = (int)h;
-  } else if (cb >= 0) *m.anyOutside = 1;
-  m.slotOf[i] = hs;
-}
-__global__ void __launch_bounds__(256) mu_group(const LmScalars* __restrict__ s, MuWork m) {
-  VL_PDL_WAIT();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s->needSlow || i >= s->Qc + s->Qs) return;
-  const int hs = m.slotOf[i];
-  if (hs < 0) return;
-  const int L = m.hlead[hs];
-  if (L == i) return;
-  const int pos = atomicAdd(&m.memberCnt[L], 1);
-  if (pos < MU_MEMBERS) m.members[L * MU_MEMBERS + pos] = i;
-}
-__global__ void __launch_bounds__(128) mu_apply(const LmScalars* __restrict__ s, vloam_b200_params prm, LgGrid g, const float4* __restrict__ newPts,
-                                                MuWork mw) {
-  VL_PDL_WAIT();
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int nq = s->needSlow ? 0 : s->Qc + s->Qs;
-  const int hs = t < nq ? mw.slotOf[t] : -1;
-  int bornKind = -1, died = 0;  // bookkeeping of this thread's voxel, added up per warp at the end (thousands of atomics on ONE address cost ~50 us)
-  if (hs >= 0 && mw.hlead[hs] == t) {  // the leader of its voxel
-  const unsigned long long hk = mw.hkey[hs];
-  const int sg = (int)(hk >> 32);
-  const unsigned vk = (unsigned)hk;
+// where the grid holds the map point of voxel (slot, vk) of kind `kind`: entry index and cell, -1 when the voxel is empty.
+// Called while nothing modifies the grid (mu_keys: the previous update is complete, this one inserts only in mu_apply).
+__device__ __forceinline__ void mu_lookup(const LmScalars* __restrict__ s, const vloam_b200_params& prm, const LgGrid& g, int sg, unsigned vk,
+                                          int& foundOut, int& foundCellOut) {
   const int kind = sg / VL_MAX_VALID, slot = sg % VL_MAX_VALID, cb = s->validInd[slot];
   const float leaf = kind ? prm.plane_res : prm.line_res;
   const float inv = lm_leaf_inv(prm, kind);
@@ -1460,23 +1410,93 @@ __global__ void __launch_bounds__(128) mu_apply(const LmScalars* __restrict__ s,
           }
         }
   }
+  foundOut = found; foundCellOut = foundCell;
+}
+
+// Grouping AND look-up in one launch: the point that claims a voxel's hash slot (CAS winner) becomes the group's leader and looks
+// the voxel's map point up in the grid right away -- its two dependent L2 round trips overlap the other points' hashing --
+// and every point, the leader included, appends itself to the slot's member list.  (Round 2's first version elected the lowest
+// stack index with atomicMin and needed a second launch, mu_group, before anybody knew the leader.)
+__global__ void __launch_bounds__(256) mu_keys(const LmScalars* __restrict__ s, const RfWork* __restrict__ w, vloam_b200_params prm, LgGrid g,
+                                               const float4* __restrict__ stackC, const float4* __restrict__ stackS, float4* __restrict__ newPts,
+                                               int* __restrict__ newCube, MuWork m) {
+  VL_PDL_WAIT();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Qc = s->Qc, Qs = s->Qs;
+  if (s->needSlow || i >= Qc + Qs) return;  // (queued before the host knows whether the sweep stays on the in-place path, and with a bound on the count)
+  const int kind = i >= Qc;
+  const float4 po = kind ? stackS[i - Qc] : stackC[i];
+  double r[3];
+  vl_qrot(s->pose, (double)po.x, (double)po.y, (double)po.z, r);
+  const float4 p = make_float4((float)(r[0] + s->pose[4]), (float)(r[1] + s->pose[5]), (float)(r[2] + s->pose[6]), po.w);
+  const int ci = lm_cube_of(p.x, s->cenW), cj = lm_cube_of(p.y, s->cenH), ck = lm_cube_of(p.z, s->cenD);
+  int cb = -1;
+  if (ci >= 0 && ci < VL_CUBE_W && cj >= 0 && cj < VL_CUBE_H && ck >= 0 && ck < VL_CUBE_D) cb = ci + VL_CUBE_W * cj + VL_CUBE_W * VL_CUBE_H * ck;
+  newPts[i] = p;
+  const int slot = cb >= 0 ? w->slotOfCube[cb] : -1;
+  newCube[i] = (cb >= 0 && slot < 0) ? cb : -1;  // only cubes outside the window need the raw append path
+  int hs = -1;
+  if (slot >= 0) {
+    const unsigned vk = lm_vox_key(p, lm_leaf_inv(prm, kind), ci, cj, ck, s->cenW, s->cenH, s->cenD);
+    const int sg = kind * VL_MAX_VALID + slot;
+    const unsigned long long key = ((unsigned long long)sg << 32) | vk;
+    unsigned h = mu_hash(key) & (unsigned)(m.H - 1);
+    bool won = false;
+    for (;;) {
+      const unsigned long long prev = atomicCAS(&m.hkey[h], ~0ull, key);
+      if (prev == ~0ull) { won = true; break; }
+      if (prev == key) break;
+      h = (h + 1) & (unsigned)(m.H - 1);
+    }
+    const int pos = atomicAdd(&m.cnt[h], 1);
+    if (pos < MU_CAP) m.members[(size_t)h * MU_CAP + pos] = i;
+    hs = (int)h;
+    if (won) {
+      hs |= MU_LEAD;
+      int f, fc;
+      mu_lookup(s, prm, g, sg, vk, f, fc);
+      m.found[i] = f; m.foundCell[i] = fc;
+    }
+  } else if (cb >= 0) *m.anyOutside = 1;
+  m.slotOf[i] = hs;
+}
+__global__ void __launch_bounds__(128) mu_apply(const LmScalars* __restrict__ s, vloam_b200_params prm, LgGrid g, const float4* __restrict__ newPts,
+                                                MuWork mw) {
+  VL_PDL_WAIT();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nq = s->needSlow ? 0 : s->Qc + s->Qs;
+  const int so = t < nq ? mw.slotOf[t] : -1;
+  int bornKind = -1, died = 0;  // bookkeeping of this thread's voxel, added up per warp at the end (thousands of atomics on ONE address cost ~50 us)
+  if (so >= 0 && (so & MU_LEAD)) {  // the leader of its voxel
+  const int hs = so & ~MU_LEAD;
+  const int found = mw.found[t], foundCell = mw.foundCell[t];
+  const int nm = mw.cnt[hs];
+  int mem[MU_CAP];
+#pragma unroll
+  for (int q = 0; q < MU_CAP; ++q) mem[q] = q < nm ? mw.members[(size_t)hs * MU_CAP + q] : 0x7fffffff;
+  const unsigned long long hk = mw.hkey[hs];
+  const int sg = (int)(hk >> 32);
+  const unsigned vk = (unsigned)hk;
+  const int kind = sg / VL_MAX_VALID, slot = sg % VL_MAX_VALID, cb = s->validInd[slot];
+  const float inv = lm_leaf_inv(prm, kind);
+  const int ci = cb % VL_CUBE_W, cj = (cb / VL_CUBE_W) % VL_CUBE_H, ck = cb / (VL_CUBE_W * VL_CUBE_H);
+  const float* o = g.hdr->origin;
+  const unsigned long long want = ((unsigned long long)slot << 32) | vk;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   int cnt = 0;
   if (found >= 0) { acc = rf_fold(acc, g.pts[found]); cnt = 1; }
-  acc = rf_fold(acc, newPts[t]); ++cnt;       // the leader has the lowest stack index of its group
-  const int nm = mw.memberCnt[t];
-  if (nm <= MU_MEMBERS) {
-    // registration order is arbitrary: take the members in stack order (nm is 0..2 for nearly every voxel: the stacks are
-    // voxel-filtered at the same leaf, so a world voxel collects at most the points of the ~8 lidar-frame voxels it overlaps)
-    int last = t;
+  if (nm <= MU_CAP) {
+    // arrival order is arbitrary: take the members in stack order (nm is 1..3 for nearly every voxel)
+    int last = -1;
     for (int q = 0; q < nm; ++q) {
       int best = 0x7fffffff;
-      for (int r = 0; r < nm; ++r) { const int v = mw.members[t * MU_MEMBERS + r]; if (v > last && v < best) best = v; }
+#pragma unroll
+      for (int r = 0; r < MU_CAP; ++r) { const int v = mem[r]; if (v > last && v < best) best = v; }
       acc = rf_fold(acc, newPts[best]); ++cnt;
       last = best;
     }
   } else {
-    for (int j = t + 1; j < nq; ++j) if (mw.slotOf[j] == hs) { acc = rf_fold(acc, newPts[j]); ++cnt; }  // (more members than slots: walk the stack)
+    for (int j = 0; j < nq; ++j) if ((mw.slotOf[j] & ~MU_LEAD) == hs && mw.slotOf[j] >= 0) { acc = rf_fold(acc, newPts[j]); ++cnt; }  // (more members than slots: walk the stack)
   }
   const float4 c = rf_centroid(acc, cnt);
   if (lm_vox_key(c, inv, ci, cj, ck, s->cenW, s->cenH, s->cenD) != vk) g.hdr->dirty = 1;  // drifted across a voxel face: pool path next sweep
@@ -1972,18 +1992,17 @@ int vl_lm_run(vloam_b200_ctx* c) {
       VL_TRY(vl_reserve(c, d->newPts, (size_t)nq));
       VL_TRY(vl_reserve(c, d->newCube, (size_t)nq));
       VL_TRY(vl_reserve(c, d->muKey, (size_t)H));
-      VL_TRY(vl_reserve(c, d->muInt, (size_t)H + (size_t)nq * (2 + MU_MEMBERS) + 4));
+      VL_TRY(vl_reserve(c, d->muInt, (size_t)H * (1 + MU_CAP) + (size_t)nq * 3 + 4));
       MuWork mw;
-      mw.hkey = d->muKey.p; mw.H = H; mw.hlead = d->muInt.p; mw.slotOf = mw.hlead + H; mw.memberCnt = mw.slotOf + nq;
-      mw.members = mw.memberCnt + nq; mw.anyOutside = mw.members + (size_t)nq * MU_MEMBERS;
+      mw.hkey = d->muKey.p; mw.H = H; mw.cnt = d->muInt.p; mw.anyOutside = mw.cnt + H; mw.slotOf = mw.anyOutside + 4; mw.found = mw.slotOf + nq;
+      mw.foundCell = mw.found + nq; mw.members = mw.foundCell + nq;
       // (the scratch is cleared behind the previous update, on its stream, BEFORE the wait for this sweep's pose: off the chain)
       VL_CUDA(cudaStreamWaitEvent(c->stream3, c->evAux, 0));                // (anyOutside is read by the previous sweep's append on streamAux)
       VL_CUDA(cudaMemsetAsync(mw.hkey, 0xff, (size_t)H * 8, c->stream3));   // empty slots
-      VL_CUDA(cudaMemsetAsync(mw.hlead, 0x7f, (size_t)H * 4, c->stream3));  // "no leader yet" (0x7f7f7f7f > any stack index)
-      VL_CUDA(cudaMemsetAsync(mw.anyOutside, 0, 4, c->stream3));
+      VL_CUDA(cudaMemsetAsync(mw.cnt, 0, (size_t)(H + 4) * 4, c->stream3));  // group sizes and the anyOutside flag behind them
       VL_CUDA(cudaStreamWaitEvent(c->stream3, c->evPose, 0));
       VL_BYTES(16.0 * max(c->h_lmm->Qc + c->h_lmm->Qs, 1));  // SURVEY 8(d) B_lm insert term: every new point once (last known count)
-      VL_LAUNCH(mu_keys, vl_div_up(nq, 256), 256, 0, c->lmm, d->work, c->prm, stackCp, stackSp, d->newPts.p, d->newCube.p, mw);
+      VL_LAUNCH(mu_keys, vl_div_up(nq, 256), 256, 0, c->lmm, d->work, c->prm, d->grid, stackCp, stackSp, d->newPts.p, d->newCube.p, mw);
       VL_CUDA(cudaEventRecord(c->evKeys, c->stream3));  // nothing below reads the stacks any more: the next sweep's filters may overwrite them
       VL_CUDA(cudaEventRecord(c->evKeysSel[c->stackSel], c->stream3));
       // points outside the 5x5x3 window go to cubes the grid does not hold: appended raw to their pool segments beside the in-place update
@@ -1994,7 +2013,6 @@ int vl_lm_run(vloam_b200_ctx* c) {
                 (int)c->poolS.cap, (const int*)mw.anyOutside);
       vl_tls_stream = c->stream3;
       VL_CUDA(cudaEventRecord(c->evAux, c->streamAux));
-      VL_LAUNCH(mu_group, vl_div_up(nq, 256), 256, 0, c->lmm, mw);
       VL_BYTES(2.0 * 32.0 * max(c->h_lmm->Qc + c->h_lmm->Qs, 1));  // read + write of the map points that change (SURVEY 8(d) re-filter term restricted to what changes)
       VL_LAUNCH(mu_apply, vl_div_up(nq, 128), 128, 0, c->lmm, c->prm, d->grid, d->newPts.p, mw);
       VL_CUDA(cudaEventRecord(c->evMap, c->stream3));
@@ -2215,7 +2233,7 @@ int vl_lm_preload(vloam_b200_ctx* c) {  // see vl_sr_set_attrs: load every kerne
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_fit));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lg_zero)); VL_CUDA(cudaFuncGetAttributes(&fa_, lg_rebuild)); VL_CUDA(cudaFuncGetAttributes(&fa_, lm_prepare_fast));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lg_knn)); VL_CUDA(cudaFuncGetAttributes(&fa_, lg_keys_to_ids)); VL_CUDA(cudaFuncGetAttributes(&fa_, lm_gather));
-  VL_CUDA(cudaFuncGetAttributes(&fa_, mu_apply)); VL_CUDA(cudaFuncGetAttributes(&fa_, mu_keys)); VL_CUDA(cudaFuncGetAttributes(&fa_, mu_group)); VL_CUDA(cudaFuncGetAttributes(&fa_, mz_collect));
+  VL_CUDA(cudaFuncGetAttributes(&fa_, mu_apply)); VL_CUDA(cudaFuncGetAttributes(&fa_, mu_keys)); VL_CUDA(cudaFuncGetAttributes(&fa_, mz_collect));
   VL_CUDA(cudaFuncGetAttributes(&fa_, mz_layout_for_grid));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_fit_sets));
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_transform_update));
