@@ -138,6 +138,7 @@ static int create_impl(vloam_b200_ctx* c, const vloam_b200_params* p, int device
   VL_CUDA_CREATE(cudaMalloc(&c->los, sizeof(LoScalars)));
   VL_CUDA_CREATE(cudaMalloc(&c->losNext, sizeof(LoScalars)));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evS2, cudaEventDisableTiming));
+  VL_CUDA_CREATE(cudaMallocHost(&c->h_s2flag, 64)); *c->h_s2flag = 0; c->s2seq = 0;
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evLoSolve, cudaEventDisableTiming));
   VL_CUDA_CREATE(cudaEventCreateWithFlags(&c->evLoNext, cudaEventDisableTiming));
   VL_CUDA_CREATE(cudaStreamCreateWithPriority(&c->streamLO, cudaStreamNonBlocking, pr[4]));
@@ -198,6 +199,7 @@ void vloam_b200_destroy(vloam_b200_ctx* c) {
                   c->poolC.p, c->poolS.p, c->stackC.p, c->stackS.p, c->stackCN.p, c->stackSN.p, c->fromMapC.p, c->fromMapS.p, c->knnIdx.p, c->knnD2.p, c->knnOk.p,
                   c->vKeys.p, c->vKeys2.p, c->vHead.p, c->vScan.p, c->vScan2.p, c->vOut.p, c->vIn.p, c->regOut.p, c->tailKeys.p, c->staging.p};
   for (void* p : bufs) vl_dev_free(c, p);
+  if (c->h_s2flag) cudaFreeHost(c->h_s2flag);
   cudaFreeHost(c->h_los); cudaFreeHost(c->h_lms); cudaFreeHost(c->h_lmm); cudaFreeHost(c->h_vScalars);
   for (int k = 0; k < 4; ++k) cudaEventDestroy(c->ev[k]);
   for (int k = 0; k < 12; ++k) cudaEventDestroy(c->evx[k]);

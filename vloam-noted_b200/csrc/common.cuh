@@ -192,6 +192,7 @@ struct vloam_b200_ctx {
   bool earlyLoArmed;          // the next sweep's look-ahead odometry is the first item of the side work (its stream waits are issued)
   bool sideWaitsIssued;       // the caller already ordered streamSR / stream2 behind the last odometry solve (before queuing the next one)
   cudaEvent_t evS2;           // sync point S2 (pose + sizes copied to the host)
+  unsigned* h_s2flag; unsigned s2seq;  // in-place path: lm_transform_update writes the structs + this sequence number into pinned memory
   cudaStream_t streamLO;      // the look-ahead odometry of the NEXT sweep runs here, beside this sweep's mapping (own factor buffers)
   cudaEvent_t evLoNext;       // that look-ahead solve has finished (its result is in losNext)
   cudaEvent_t evLoSolve;      // the last queued odometry solve (and every one before it) has finished reading the "last" clouds and their grids

@@ -880,19 +880,37 @@ int vl_lm_fit_sets(vloam_b200_ctx* c, const float* d_near, int n, int kind, int*
   return VLOAM_OK;
 }
 
-__global__ void lm_transform_update(LmScalars* s, const LgHeader* __restrict__ gh, const int* __restrict__ gridTop) {
+// hostLmm != null (in-place path): sync point S2 without a copy engine round trip -- the warp writes both scalar structs straight
+// into pinned host memory (UVA) and then the frame's sequence number; the host spins on that word.  (Two cudaMemcpyAsync + an
+// event cost ~20 us between the final pose and the caller seeing it, which is host turn-around the next sweep's mapping waits for.)
+__global__ void lm_transform_update(LmScalars* s, const LgHeader* __restrict__ gh, const int* __restrict__ gridTop, const LoScalars* __restrict__ los,
+                                    LmScalars* hostLmm, LoScalars* hostLos, volatile unsigned* hostFlag, unsigned seq) {
   VL_PDL_WAIT();
   // LM.cpp:147-151
-  if (threadIdx.x != 0) return;
-  if (gh) { s->gridTop = *gridTop; s->gridDirty = gh->dirty; s->gridDead = gh->dead; s->gridCount = gh->count[0] + gh->count[1]; s->gridCountC = gh->count[0]; }
-  if (s->needSlow) return;  // the sweep is repeated on the pool path: leave the state untouched
-  const double* q = s->q_wodom;
-  const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
-  const double qi[4] = {-q[0] / n2, -q[1] / n2, -q[2] / n2, q[3] / n2};
-  vl_qmul(s->pose, qi, s->q_wmap_wodom);
-  double r[3];
-  vl_qrot(s->q_wmap_wodom, s->t_wodom[0], s->t_wodom[1], s->t_wodom[2], r);
-  for (int k = 0; k < 3; ++k) s->t_wmap_wodom[k] = s->pose[4 + k] - r[k];
+  if (threadIdx.x == 0) {
+    if (gh) { s->gridTop = *gridTop; s->gridDirty = gh->dirty; s->gridDead = gh->dead; s->gridCount = gh->count[0] + gh->count[1]; s->gridCountC = gh->count[0]; }
+    if (!s->needSlow) {  // (needSlow: the sweep is repeated on the pool path: leave the state untouched)
+      const double* q = s->q_wodom;
+      const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+      const double qi[4] = {-q[0] / n2, -q[1] / n2, -q[2] / n2, q[3] / n2};
+      vl_qmul(s->pose, qi, s->q_wmap_wodom);
+      double r[3];
+      vl_qrot(s->q_wmap_wodom, s->t_wodom[0], s->t_wodom[1], s->t_wodom[2], r);
+      for (int k = 0; k < 3; ++k) s->t_wmap_wodom[k] = s->pose[4 + k] - r[k];
+    }
+  }
+  if (!hostLmm) return;
+  __syncwarp();
+  static_assert(sizeof(LmScalars) % 8 == 0 && sizeof(LoScalars) % 8 == 0, "scalar structs are copied as 8-byte words");
+  const unsigned long long* a = reinterpret_cast<const unsigned long long*>(s);
+  unsigned long long* ha = reinterpret_cast<unsigned long long*>(hostLmm);
+  for (int k = threadIdx.x; k < (int)(sizeof(LmScalars) / 8); k += 32) ha[k] = a[k];
+  const unsigned long long* b = reinterpret_cast<const unsigned long long*>(los);
+  unsigned long long* hb = reinterpret_cast<unsigned long long*>(hostLos);
+  for (int k = threadIdx.x; k < (int)(sizeof(LoScalars) / 8); k += 32) hb[k] = b[k];
+  __threadfence_system();
+  __syncwarp();
+  if (threadIdx.x == 0) *hostFlag = seq;
 }
 
 // ---- map update: insert (LM.cpp:741-788) + per-cube VoxelGrid re-filter (LM.cpp:795-808) -------
@@ -1852,7 +1870,7 @@ int vl_lm_sync_pools(vloam_b200_ctx* c) {
 
 // the two association + solve passes of LM.cpp:526-717 and transformUpdate (LM.cpp:737); every kernel reads its sizes on the device
 static int lm_queue_passes(vloam_b200_ctx* c, LmDevice* d, int nqBound, bool capture, const LmSub* sub, bool earlyLO = false, bool earlyPose = false,
-                           bool countsSet = false) {
+                           bool countsSet = false, const LoScalars* losPub = nullptr) {
   if (!countsSet) {
   VL_CUDA(cudaStreamWaitEvent(c->stream, c->evStacks, 0));   // only now are this frame's downsampled stacks needed (side streams)
   VL_CUDA(cudaStreamWaitEvent(c->stream, c->evStacksC, 0));
@@ -1892,17 +1910,21 @@ static int lm_queue_passes(vloam_b200_ctx* c, LmDevice* d, int nqBound, bool cap
   }
   // in-place path: the pose is final HERE -- the map update (own stream) does not wait for transformUpdate
   if (earlyPose) VL_CUDA(cudaEventRecord(c->evPose, c->stream));
-  VL_LAUNCH(lm_transform_update, 1, 32, 0, c->lmm, (const LgHeader*)(earlyPose ? nullptr : d->grid.hdr), (const int*)d->grid.top);  // LM.cpp:737 (runs even when the optimisation was skipped)
+  if (earlyPose) c->s2seq++;
+  VL_LAUNCH(lm_transform_update, 1, 32, 0, c->lmm, (const LgHeader*)(earlyPose ? nullptr : d->grid.hdr), (const int*)d->grid.top, losPub,
+            earlyPose ? c->h_lmm : (LmScalars*)nullptr, earlyPose ? c->h_los : (LoScalars*)nullptr, (volatile unsigned*)c->h_s2flag, c->s2seq);  // LM.cpp:737 (runs even when the optimisation was skipped)
   return VLOAM_OK;
 }
 
 // sync point S2: the pose is final; sizes for the map update.  While the device finishes this sweep's mapping, the next sweep's
 // odometry solve is queued (replays with a registered look-ahead sweep) -- once per call of vl_lm_run.
-static int lm_sync_s2(vloam_b200_ctx* c, bool capture, bool* lookaheadDone) {
+static int lm_sync_s2(vloam_b200_ctx* c, bool capture, bool* lookaheadDone, bool published = false) {
   if (c->sideSubmitted) { c->sideSubmitted = false; VL_TRY(vl_lm_join(c)); }  // (see vl_lm_run: the helper must be done with the context's fields)
-  VL_CUDA(cudaEventRecord(c->evPose, c->stream));
-  VL_CUDA(cudaMemcpyAsync(c->h_los, c->los, sizeof(LoScalars), cudaMemcpyDeviceToHost, c->stream));
-  VL_CUDA(cudaMemcpyAsync(c->h_lmm, c->lmm, sizeof(LmScalars), cudaMemcpyDeviceToHost, c->stream));
+  if (!published) {
+    VL_CUDA(cudaEventRecord(c->evPose, c->stream));
+    VL_CUDA(cudaMemcpyAsync(c->h_los, c->los, sizeof(LoScalars), cudaMemcpyDeviceToHost, c->stream));
+    VL_CUDA(cudaMemcpyAsync(c->h_lmm, c->lmm, sizeof(LmScalars), cudaMemcpyDeviceToHost, c->stream));
+  }
   VL_CUDA(cudaEventRecord(c->evS2, c->stream));
   VL_HOST_MARK(5);
   if (!*lookaheadDone) {
@@ -1911,7 +1933,23 @@ static int lm_sync_s2(vloam_b200_ctx* c, bool capture, bool* lookaheadDone) {
     *lookaheadDone = true;
   }
   if (!capture) VL_TRY(vl_lo_lookahead_stacks(c));  // (no-op unless a look-ahead solve was queued in this call)
-  VL_CUDA(cudaEventSynchronize(c->evS2));
+  if (published) {
+    // lm_transform_update wrote both structs and then this sweep's sequence number into pinned memory: spin on the word; the
+    // event is looked at now and then so that a failed launch cannot hang the caller
+    volatile unsigned* flag = c->h_s2flag;
+    for (unsigned spin = 1; *flag != c->s2seq; ++spin) {
+      if ((spin & 1023u) == 0) {
+        const cudaError_t e = cudaEventQuery(c->evS2);
+        if (e == cudaSuccess) break;  // (complete: its writes are visible)
+        if (e != cudaErrorNotReady) { snprintf(c->err, sizeof c->err, "%s:%d S2: %s", __FILE__, __LINE__, cudaGetErrorString(e)); return VLOAM_E_CUDA; }
+        (void)cudaGetLastError();
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+  } else VL_CUDA(cudaEventSynchronize(c->evS2));
   c->s2Done = true;
   VL_HOST_MARK(6);
   if (c->h_lmm->overflow) { snprintf(c->err, sizeof c->err, "map pool exhausted"); return VLOAM_E_CAPACITY; }
@@ -1959,6 +1997,7 @@ int vl_lm_run(vloam_b200_ctx* c) {
     }
     // stacks filtered a sweep ago (look-ahead): the counts are set by lm_prepare_fast itself, one launch fewer on the pose chain
     const bool countsSet = c->stacksAdopted;
+    const LoScalars* const losNow = c->los;  // (read before the helper thread may swap the odometry states)
     if (countsSet) {
       VL_CUDA(cudaStreamWaitEvent(c->stream, c->evStacks, 0));
       VL_CUDA(cudaStreamWaitEvent(c->stream, c->evStacksC, 0));
@@ -1971,7 +2010,7 @@ int vl_lm_run(vloam_b200_ctx* c) {
     // after the launch above has read c->los, joined before lm_sync_s2 reads it again.)
     if (!inlineUpdate) VL_TRY(vl_lo_submit_side(c));
     if (c->timing) VL_CUDA(cudaEventRecord(c->evx[0], c->stream));
-    VL_TRY(lm_queue_passes(c, d, nqBound, false, d->subReal, earlyLO, true, countsSet));
+    VL_TRY(lm_queue_passes(c, d, nqBound, false, d->subReal, earlyLO, true, countsSet, losNow));
     // The in-place map update is queued NOW, behind the pose (evPose) on its own stream, before the host waits at S2: its kernels
     // read the counts and the needSlow flag on the device (sizes here are bounds), so the device runs it the moment the pose is
     // final instead of waiting for S2 -> host -> helper thread -> launch (~45 us on the chain the next sweep's mapping waits for).
@@ -2002,6 +2041,8 @@ int vl_lm_run(vloam_b200_ctx* c) {
       VL_CUDA(cudaMemsetAsync(mw.cnt, 0, (size_t)(H + 4) * 4, c->stream3));  // group sizes and the anyOutside flag behind them
       VL_CUDA(cudaStreamWaitEvent(c->stream3, c->evPose, 0));
       VL_BYTES(16.0 * max(c->h_lmm->Qc + c->h_lmm->Qs, 1));  // SURVEY 8(d) B_lm insert term: every new point once (last known count)
+      static const bool xNoUpd = getenv("VLOAM_X_NO_UPDATE") != nullptr;  // EXPERIMENT (the map is never updated): how much of the period is the update?
+      if (!xNoUpd)
       VL_LAUNCH(mu_keys, vl_div_up(nq, 256), 256, 0, c->lmm, d->work, c->prm, d->grid, stackCp, stackSp, d->newPts.p, d->newCube.p, mw);
       VL_CUDA(cudaEventRecord(c->evKeys, c->stream3));  // nothing below reads the stacks any more: the next sweep's filters may overwrite them
       VL_CUDA(cudaEventRecord(c->evKeysSel[c->stackSel], c->stream3));
@@ -2014,11 +2055,12 @@ int vl_lm_run(vloam_b200_ctx* c) {
       vl_tls_stream = c->stream3;
       VL_CUDA(cudaEventRecord(c->evAux, c->streamAux));
       VL_BYTES(2.0 * 32.0 * max(c->h_lmm->Qc + c->h_lmm->Qs, 1));  // read + write of the map points that change (SURVEY 8(d) re-filter term restricted to what changes)
+      if (!xNoUpd)
       VL_LAUNCH(mu_apply, vl_div_up(nq, 128), 128, 0, c->lmm, c->prm, d->grid, d->newPts.p, mw);
       VL_CUDA(cudaEventRecord(c->evMap, c->stream3));
       if (c->timing) VL_CUDA(cudaEventRecord(c->evx[7], c->stream3));
     }
-    VL_TRY(lm_sync_s2(c, false, &lookaheadDone));
+    VL_TRY(lm_sync_s2(c, false, &lookaheadDone, true));
     if (!c->h_lmm->needSlow) {
       const int Qc = c->h_lmm->Qc, Qs = c->h_lmm->Qs, nq = Qc + Qs;
       if (d->builtCount < 0) {  // first in-place sweep after a rebuild: nothing created yet
