@@ -1869,8 +1869,10 @@ int vl_lm_sync_pools(vloam_b200_ctx* c) {
 }
 
 // the two association + solve passes of LM.cpp:526-717 and transformUpdate (LM.cpp:737); every kernel reads its sizes on the device
+// afterHead (may be empty): host work that is not on the pose chain -- arranging and submitting the side work -- runs once the first
+// kNN + fit are queued, so the device already has ~35 us of work when the host turns to it.
 static int lm_queue_passes(vloam_b200_ctx* c, LmDevice* d, int nqBound, bool capture, const LmSub* sub, bool earlyLO = false, bool earlyPose = false,
-                           bool countsSet = false, const LoScalars* losPub = nullptr) {
+                           bool countsSet = false, const LoScalars* losPub = nullptr, const std::function<int()>& afterHead = std::function<int()>()) {
   if (!countsSet) {
   VL_CUDA(cudaStreamWaitEvent(c->stream, c->evStacks, 0));   // only now are this frame's downsampled stacks needed (side streams)
   VL_CUDA(cudaStreamWaitEvent(c->stream, c->evStacksC, 0));
@@ -1891,6 +1893,7 @@ static int lm_queue_passes(vloam_b200_ctx* c, LmDevice* d, int nqBound, bool cap
     VL_LAUNCH(lg_knn, c->num_sms * 8, 256, 0, c->lmm, d->grid, c->stackC.p, c->stackS.p, c->knnPts.p, c->knnD2.p, capture ? c->knnKey.p : (unsigned long long*)nullptr);
     VL_BYTES((16.0 * 6 + 24.0 + 84.0) * (double)max(c->h_lmm->Qc + c->h_lmm->Qs, 1));
     VL_LAUNCH(lm_fit, c->num_sms, 128, 0, c->lmm, c->stackC.p, c->stackS.p, c->knnPts.p, c->knnD2.p, c->knnOk.p, c->factors.p, c->factorValid.p);
+    if (pass == 0 && afterHead) VL_TRY(afterHead());
     if (capture) {
       const int nq = Qc + Qs;
       if (nq > 0) VL_LAUNCH(lg_keys_to_ids, vl_div_up(nq * 5, 256), 256, 0, c->knnKey.p, nq * 5, Qc, sub, c->lmm, c->prm, c->cubeC, c->cubeS, c->poolC.p, c->poolS.p, d->knnIds.p);
@@ -1990,11 +1993,6 @@ int vl_lm_run(vloam_b200_ctx* c) {
 
   // ---- in-place path: the grid describes this sweep's sub-map unless lm_prepare_fast finds the window moved / the grid dirty
   if (d->gridEnabled && d->gridValid && !capture && d->gridTopUpper + 2LL * nqBound <= d->grid.cap && d->newVoxUpper + nqBound <= LG_NEWVOX_MAX) {
-    if (!inlineUpdate) {
-      VL_TRY(vl_lo_early_lookahead(c, &earlyLO));  // (two sweeps ahead, structures pre-built: the next sweep's odometry heads the side work)
-      lookaheadDone = earlyLO;
-      VL_TRY(vl_lo_plan_prebuild(c));
-    }
     // stacks filtered a sweep ago (look-ahead): the counts are set by lm_prepare_fast itself, one launch fewer on the pose chain
     const bool countsSet = c->stacksAdopted;
     const LoScalars* const losNow = c->los;  // (read before the helper thread may swap the odometry states)
@@ -2005,12 +2003,18 @@ int vl_lm_run(vloam_b200_ctx* c) {
                 (const int*)(d->dQ + 2 * c->stackSel + 1), (const int*)d->grid.top);
     } else
     VL_LAUNCH(lm_prepare_fast, 1, 256, 0, c->lmm, c->los, d->work, d->grid.hdr, 0, resetValid, (const int*)nullptr, (const int*)nullptr, (const int*)nullptr);
-    // the helper thread issues the next sweep's odometry (early mode), the look-ahead scan registration and the next odometry structures
-    // meanwhile.  (It swaps scan-registration sets and the odometry state in and out of the context while it does: submitted only
-    // after the launch above has read c->los, joined before lm_sync_s2 reads it again.)
-    if (!inlineUpdate) VL_TRY(vl_lo_submit_side(c));
     if (c->timing) VL_CUDA(cudaEventRecord(c->evx[0], c->stream));
-    VL_TRY(lm_queue_passes(c, d, nqBound, false, d->subReal, earlyLO, true, countsSet, losNow));
+    // The helper thread issues the next sweep's odometry (two sweeps ahead, structures pre-built), the look-ahead scan registration
+    // and the next odometry structures while the caller queues the rest of the mapping stage.  It swaps scan-registration sets and the
+    // odometry state in and out of the context while it does: it is handed the work only after the launch above has read c->los
+    // (and, to keep the head of the pose chain short, after the first kNN + fit are queued) and joined before lm_sync_s2 reads it again.
+    auto sideWork = [&]() -> int {
+      VL_TRY(vl_lo_early_lookahead(c, &earlyLO));
+      lookaheadDone = earlyLO;
+      VL_TRY(vl_lo_plan_prebuild(c));
+      return vl_lo_submit_side(c);
+    };
+    VL_TRY(lm_queue_passes(c, d, nqBound, false, d->subReal, false, true, countsSet, losNow, inlineUpdate ? std::function<int()>() : std::function<int()>(sideWork)));
     // The in-place map update is queued NOW, behind the pose (evPose) on its own stream, before the host waits at S2: its kernels
     // read the counts and the needSlow flag on the device (sizes here are bounds), so the device runs it the moment the pose is
     // final instead of waiting for S2 -> host -> helper thread -> launch (~45 us on the chain the next sweep's mapping waits for).
@@ -2041,8 +2045,6 @@ int vl_lm_run(vloam_b200_ctx* c) {
       VL_CUDA(cudaMemsetAsync(mw.cnt, 0, (size_t)(H + 4) * 4, c->stream3));  // group sizes and the anyOutside flag behind them
       VL_CUDA(cudaStreamWaitEvent(c->stream3, c->evPose, 0));
       VL_BYTES(16.0 * max(c->h_lmm->Qc + c->h_lmm->Qs, 1));  // SURVEY 8(d) B_lm insert term: every new point once (last known count)
-      static const bool xNoUpd = getenv("VLOAM_X_NO_UPDATE") != nullptr;  // EXPERIMENT (the map is never updated): how much of the period is the update?
-      if (!xNoUpd)
       VL_LAUNCH(mu_keys, vl_div_up(nq, 256), 256, 0, c->lmm, d->work, c->prm, d->grid, stackCp, stackSp, d->newPts.p, d->newCube.p, mw);
       VL_CUDA(cudaEventRecord(c->evKeys, c->stream3));  // nothing below reads the stacks any more: the next sweep's filters may overwrite them
       VL_CUDA(cudaEventRecord(c->evKeysSel[c->stackSel], c->stream3));
@@ -2055,7 +2057,6 @@ int vl_lm_run(vloam_b200_ctx* c) {
       vl_tls_stream = c->stream3;
       VL_CUDA(cudaEventRecord(c->evAux, c->streamAux));
       VL_BYTES(2.0 * 32.0 * max(c->h_lmm->Qc + c->h_lmm->Qs, 1));  // read + write of the map points that change (SURVEY 8(d) re-filter term restricted to what changes)
-      if (!xNoUpd)
       VL_LAUNCH(mu_apply, vl_div_up(nq, 128), 128, 0, c->lmm, c->prm, d->grid, d->newPts.p, mw);
       VL_CUDA(cudaEventRecord(c->evMap, c->stream3));
       if (c->timing) VL_CUDA(cudaEventRecord(c->evx[7], c->stream3));
