@@ -616,6 +616,20 @@ long vloam_b200_debug_get(vloam_b200_ctx* c, const char* name, void* out, long c
     if (vl_solver_trace(c, v) != VLOAM_OK) return VLOAM_E_CUDA;
     return put_host(v, sizeof v, out, cap);
   }
+  if (n == "chain.trace") {  // first call arms the device-side timeline of the pose chain; later calls copy it out and reset it
+    static VlChainTrace* d_tr = nullptr;
+    if (!d_tr) {
+      VL_CUDA(cudaMalloc(&d_tr, sizeof(VlChainTrace)));
+      VL_CUDA(cudaMemset(d_tr, 0, sizeof(VlChainTrace)));
+      VL_TRY(vl_chain_trace_arm_lm(d_tr)); VL_TRY(vl_chain_trace_arm_solver(d_tr)); VL_TRY(vl_chain_trace_arm_lo(d_tr));
+      return 0;
+    }
+    VL_TRY(vloam_b200_synchronize(c));
+    if (!out || cap < (long)sizeof(VlChainTrace)) return (long)sizeof(VlChainTrace);
+    VL_CUDA(cudaMemcpy(out, d_tr, sizeof(VlChainTrace), cudaMemcpyDeviceToHost));
+    VL_CUDA(cudaMemset(d_tr, 0, 8));
+    return (long)sizeof(VlChainTrace);
+  }
   if (n == "alloc.count") { const long long v = c->regrows; return put_host(&v, sizeof v, out, cap); }  // device buffer (re)allocations so far
   if (n == "lo.costs") return put_host(c->dbgLoCost, sizeof c->dbgLoCost, out, cap);
   if (n == "lm.costs") return put_host(c->dbgLmCost, sizeof c->dbgLmCost, out, cap);

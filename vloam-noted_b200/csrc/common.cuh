@@ -301,6 +301,23 @@ struct GridParams {
 // (griddepcontrol.wait): the next grid of a dependent chain is already resident when its predecessor
 // drains, which removes most of the launch gap between the ~45 dependent kernels of a frame.
 #define VL_PDL_WAIT() cudaGridDependencySynchronize()
+// debug: device-side timeline of the pose chain (tests/gpu_chain_trace.py).  Each traced kernel stamps %globaltimer when its first
+// thread passes the dependency wait (= its predecessor in the stream has finished and this grid runs); one pointer per
+// translation unit (no relocatable device code), armed by vloam_b200_debug_get("chain.trace").
+#ifdef __CUDACC__
+struct VlChainTrace { unsigned long long n; unsigned long long rec[4096][2]; };
+static __device__ VlChainTrace* g_chain_trace = nullptr;
+__device__ __forceinline__ void vl_chain_stamp(int id) {
+  if (g_chain_trace && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned long long k = atomicAdd(&g_chain_trace->n, 1ull);
+    if (k < 4096) { g_chain_trace->rec[k][0] = (unsigned long long)id; g_chain_trace->rec[k][1] = t; }
+  }
+}
+int vl_chain_trace_arm_lm(void* dev);      // laser_mapping.cu's copy of the pointer
+int vl_chain_trace_arm_solver(void* dev);  // lm_solver.cu's
+int vl_chain_trace_arm_lo(void* dev);      // laser_odometry.cu's
+#endif
 #define VL_LAUNCH(kernel, grid, block, smem, ...)                                              \
   do {                                                                                         \
     const bool prof_ = c->prof_name[0] && vl_prof_match(c, #kernel) && c->prof_n < VL_PROF_MAX; \

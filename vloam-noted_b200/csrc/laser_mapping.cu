@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(256) lg_rebuild(LgGrid g, const LmSub* __restr
 __global__ void __launch_bounds__(256) lm_prepare_fast(LmScalars* __restrict__ s, const LoScalars* __restrict__ lo, RfWork* __restrict__ w,
                                                        LgHeader* __restrict__ gh, int skip, int resetValid, const int* __restrict__ qc = nullptr,
                                                        const int* __restrict__ qs = nullptr, const int* __restrict__ gridTop = nullptr) {
-  VL_PDL_WAIT();
+  VL_PDL_WAIT(); vl_chain_stamp(1);
   if (threadIdx.x <= LM_NSEG && !skip) { w->segCount[threadIdx.x] = 0; w->segFill[threadIdx.x] = 0; }
   if (threadIdx.x != 0) return;
   for (int k = 0; k < 4; ++k) s->q_wodom[k] = lo->q_w[k];
@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(256) lm_prepare_fast(LmScalars* __restrict__ s
 __global__ void __launch_bounds__(256) lg_knn(const LmScalars* __restrict__ s, LgGrid g, const float4* __restrict__ stackC,
                                               const float4* __restrict__ stackS, float4* __restrict__ knnPts, float* __restrict__ knnD2,
                                               unsigned long long* __restrict__ knnKey) {
-  VL_PDL_WAIT();
+  VL_PDL_WAIT(); vl_chain_stamp(2);
 
   const int lane = threadIdx.x & 31;
   const int Qc = s->Qc, Qs = s->Qs, opt = s->optimized;
@@ -836,7 +836,7 @@ __device__ __forceinline__ bool lm_fit_one(int kind, double P[5][3], double o6[6
 __global__ void __launch_bounds__(128) lm_fit(const LmScalars* __restrict__ s, const float4* __restrict__ stackC, const float4* __restrict__ stackS,
                                               const float4* __restrict__ knnPts, const float* __restrict__ knnD2, int* __restrict__ knnOk,
                                               double* __restrict__ factors, int* __restrict__ valid) {
-  VL_PDL_WAIT();
+  VL_PDL_WAIT(); vl_chain_stamp(3);
 
   const int Qc = s->Qc, Qs = s->Qs;
   if (!s->optimized) return;
@@ -885,7 +885,7 @@ int vl_lm_fit_sets(vloam_b200_ctx* c, const float* d_near, int n, int kind, int*
 // event cost ~20 us between the final pose and the caller seeing it, which is host turn-around the next sweep's mapping waits for.)
 __global__ void lm_transform_update(LmScalars* s, const LgHeader* __restrict__ gh, const int* __restrict__ gridTop, const LoScalars* __restrict__ los,
                                     LmScalars* hostLmm, LoScalars* hostLos, volatile unsigned* hostFlag, unsigned seq) {
-  VL_PDL_WAIT();
+  VL_PDL_WAIT(); vl_chain_stamp(5);
   // LM.cpp:147-151
   if (threadIdx.x == 0) {
     if (gh) { s->gridTop = *gridTop; s->gridDirty = gh->dirty; s->gridDead = gh->dead; s->gridCount = gh->count[0] + gh->count[1]; s->gridCountC = gh->count[0]; }
@@ -1438,7 +1438,7 @@ __device__ __forceinline__ void mu_lookup(const LmScalars* __restrict__ s, const
 __global__ void __launch_bounds__(256) mu_keys(const LmScalars* __restrict__ s, const RfWork* __restrict__ w, vloam_b200_params prm, LgGrid g,
                                                const float4* __restrict__ stackC, const float4* __restrict__ stackS, float4* __restrict__ newPts,
                                                int* __restrict__ newCube, MuWork m) {
-  VL_PDL_WAIT();
+  VL_PDL_WAIT(); vl_chain_stamp(6);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int Qc = s->Qc, Qs = s->Qs;
   if (s->needSlow || i >= Qc + Qs) return;  // (queued before the host knows whether the sweep stays on the in-place path, and with a bound on the count)
@@ -1480,7 +1480,7 @@ __global__ void __launch_bounds__(256) mu_keys(const LmScalars* __restrict__ s, 
 }
 __global__ void __launch_bounds__(128) mu_apply(const LmScalars* __restrict__ s, vloam_b200_params prm, LgGrid g, const float4* __restrict__ newPts,
                                                 MuWork mw) {
-  VL_PDL_WAIT();
+  VL_PDL_WAIT(); vl_chain_stamp(7);
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int nq = s->needSlow ? 0 : s->Qc + s->Qs;
   const int so = t < nq ? mw.slotOf[t] : -1;
@@ -2268,6 +2268,7 @@ int vl_lm_import_map(vloam_b200_ctx* c, int which, const void* data, long bytes)
   return VLOAM_OK;
 }
 
+int vl_chain_trace_arm_lm(void* dev) { return cudaMemcpyToSymbol(g_chain_trace, &dev, sizeof(void*)) == cudaSuccess ? VLOAM_OK : VLOAM_E_CUDA; }
 int vl_lm_preload(vloam_b200_ctx* c) {  // see vl_sr_set_attrs: load every kernel of this file when a context is created
   cudaFuncAttributes fa_;
   VL_CUDA(cudaFuncGetAttributes(&fa_, lm_prepare));

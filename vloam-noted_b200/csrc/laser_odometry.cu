@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(256) lo_assoc_grid_both(const float4* __restri
                                                           const float4* __restrict__ sorted, const LoHash H,
                                                           const double* __restrict__ pose, int* __restrict__ cornerIdx, int* __restrict__ surfIdx,
                                                           double* __restrict__ factors, int* __restrict__ valid, double* __restrict__ factorS) {
-  VL_PDL_WAIT();
+  VL_PDL_WAIT(); vl_chain_stamp(11);
 
   const int lane = threadIdx.x & 31;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -645,6 +645,7 @@ static int lo_associate(vloam_b200_ctx* c, const double* d_pose, const float4* c
   return VLOAM_OK;
 }
 
+int vl_chain_trace_arm_lo(void* dev) { return cudaMemcpyToSymbol(g_chain_trace, &dev, sizeof(void*)) == cudaSuccess ? VLOAM_OK : VLOAM_E_CUDA; }
 int vl_lo_preload(vloam_b200_ctx* c) {  // see vl_sr_set_attrs: load every kernel of this file when a context is created
   cudaFuncAttributes fa_;
   VL_CUDA(cudaFuncGetAttributes(&fa_, lo_ring_table)); VL_CUDA(cudaFuncGetAttributes(&fa_, lo_ring_table_init));

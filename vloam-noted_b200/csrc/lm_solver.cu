@@ -533,7 +533,7 @@ template <int FPT, int THREADS, int NCTA>
 __global__ void __launch_bounds__(THREADS, LMC_MIN_CTAS)
 lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ valid, int nslotsBound, const int* __restrict__ d_nslots,
                  double* __restrict__ x_inout, LmSolveState* __restrict__ st_out, long long* __restrict__ trace, const double* __restrict__ sArr) {
-  VL_PDL_WAIT();
+  VL_PDL_WAIT(); vl_chain_stamp(NCTA == 8 ? 14 : 4);
 
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank();
@@ -655,6 +655,7 @@ lm_solve_cluster(const double* __restrict__ factors, const int* __restrict__ val
     }
   }
   LM_TRACE(8);
+  vl_chain_stamp(NCTA == 8 ? 24 : 9);  // (CTA 0 leaves: the pose is final)
 }
 
 static long long* g_solver_trace = nullptr;  // device buffer of 16 clock64 stamps, allocated on first request
@@ -675,6 +676,7 @@ static cudaError_t lm_launch(cudaLaunchConfig_t& cfg, const double* cf, const in
 }
 
 // function attributes are per device: set when a context is created on it (vloam_b200_create)
+int vl_chain_trace_arm_solver(void* dev) { return cudaMemcpyToSymbol(g_chain_trace, &dev, sizeof(void*)) == cudaSuccess ? VLOAM_OK : VLOAM_E_CUDA; }
 int vl_solver_set_attrs(vloam_b200_ctx* c) {
   VL_CUDA(cudaFuncSetAttribute((lm_solve_cluster<1, 256, 16>), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   VL_CUDA(cudaFuncSetAttribute((lm_solve_cluster<2, 256, 16>), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
