@@ -16,6 +16,7 @@ ctx.set("lm.cornerMap", cb); ctx.set("lm.surfMap", sb)
 d = [torch.from_numpy(s).cuda() for s in scans]
 pose = np.zeros(14)
 host = []
+marks = []
 for k in range(N - 2):
     if k == 20:
         ctx.synchronize(); ctx.get_raw("chain.trace")
@@ -23,6 +24,7 @@ for k in range(N - 2):
     t0 = time.perf_counter()
     ctx.process_frame_device(d[k].data_ptr(), d[k].shape[0], 4, pose.ctypes.data)
     host.append((t0, time.perf_counter()))
+    marks.append(np.frombuffer(ctx.get_raw("timing.host"), np.float64).copy())
 raw = np.frombuffer(ctx.get_raw("chain.trace"), np.uint64)
 n = int(raw[0]); rec = raw[1:1 + 2 * min(n, 4096)].reshape(-1, 2)
 order = np.argsort(rec[:, 1], kind="stable"); rec = rec[order]
@@ -37,3 +39,8 @@ for i in range(i0, i1 + 1):
 hp = np.array([b - a for a, b in host[22:]]) * 1e6
 gap = np.array([host[i + 1][0] - host[i][1] for i in range(22, len(host) - 1)]) * 1e6
 print("host: process_frame call %.1f us median, python between calls %.1f us median" % (np.median(hp), np.median(gap)))
+m = np.median(np.array(marks[22:]), 0)
+print("host clock inside process_frame, us since entry (median): SR adopted %.0f | odometry adopted %.0f | lm_run %.0f | helper joined %.0f | S2 recorded %.0f | S2 passed %.0f | bookkeeping done %.0f"
+      % (m[0], m[1], m[2], m[3], m[4], m[5], m[6]))
+print("   in-place path: prepare queued %.0f | first kNN + fit queued %.0f | side work submitted %.0f | passes queued %.0f | update queued %.0f | lm_sync_s2 returned %.0f"
+      % (m[7], m[8], m[9], m[10], m[11], m[12]))

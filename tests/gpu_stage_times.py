@@ -56,7 +56,7 @@ if len(dm) >= 11:
     print("   look-ahead odometry of the next sweep done %.3f | in-place map update done %.3f  (ms since this sweep's start; events of the PREVIOUS sweep when negative or > 1)" % (dm[9], dm[10]))
 if LOOKAHEAD:
     hm = np.median(np.array(host)[8:], 0)
-    print("host clock inside process_frame, us (median): SR adopted %.0f | odometry + look-ahead queued %.0f | S1 + side streams queued %.0f | helper joined %.0f | mapping queued %.0f | S2 passed %.0f | update submitted %.0f" % tuple(hm))
+    print("host clock inside process_frame, us (median): SR adopted %.0f | odometry + look-ahead queued %.0f | S1 + side streams queued %.0f | helper joined %.0f | mapping queued %.0f | S2 passed %.0f | update submitted %.0f" % tuple(hm[:7]))
 print("launches/frame", ctx.kernel_launches / N)
 allr = np.array(walls)
 print("wall ms per frame:", " ".join("%.1f" % v for v in allr))

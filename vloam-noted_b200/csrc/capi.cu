@@ -587,8 +587,10 @@ long vloam_b200_debug_get(vloam_b200_ctx* c, const char* name, void* out, long c
   }
   if (n == "timing.host") {  // timing mode: host clock in us since process_frame was entered
     // {SR queued / adopted, odometry queued (+ look-ahead), S1 passed + side streams queued, helper joined, mapping queued, S2 passed}
-    double v[7];
-    for (int k = 0; k < 7; ++k) v[k] = c->hostT[k + 1] - c->hostT[0];
+    // ..., [7..12] finer marks of the in-place mapping path: prepare queued, first kNN + fit queued, side work submitted, passes queued,
+    //      update queued, lm_sync_s2 returned
+    double v[15];
+    for (int k = 0; k < 15; ++k) v[k] = c->hostT[k + 1] - c->hostT[0];
     return put_host(v, sizeof v, out, cap);
   }
   if (n == "timing.detail") {  // timing mode: ms since the start of the frame's scan registration

@@ -2004,17 +2004,22 @@ int vl_lm_run(vloam_b200_ctx* c) {
     } else
     VL_LAUNCH(lm_prepare_fast, 1, 256, 0, c->lmm, c->los, d->work, d->grid.hdr, 0, resetValid, (const int*)nullptr, (const int*)nullptr, (const int*)nullptr);
     if (c->timing) VL_CUDA(cudaEventRecord(c->evx[0], c->stream));
+    VL_HOST_MARK(8);
     // The helper thread issues the next sweep's odometry (two sweeps ahead, structures pre-built), the look-ahead scan registration
     // and the next odometry structures while the caller queues the rest of the mapping stage.  It swaps scan-registration sets and the
     // odometry state in and out of the context while it does: it is handed the work only after the launch above has read c->los
     // (and, to keep the head of the pose chain short, after the first kNN + fit are queued) and joined before lm_sync_s2 reads it again.
     auto sideWork = [&]() -> int {
+      VL_HOST_MARK(9);
       VL_TRY(vl_lo_early_lookahead(c, &earlyLO));
       lookaheadDone = earlyLO;
       VL_TRY(vl_lo_plan_prebuild(c));
-      return vl_lo_submit_side(c);
+      const int rs = vl_lo_submit_side(c);
+      VL_HOST_MARK(10);
+      return rs;
     };
     VL_TRY(lm_queue_passes(c, d, nqBound, false, d->subReal, false, true, countsSet, losNow, inlineUpdate ? std::function<int()>() : std::function<int()>(sideWork)));
+    VL_HOST_MARK(11);
     // The in-place map update is queued NOW, behind the pose (evPose) on its own stream, before the host waits at S2: its kernels
     // read the counts and the needSlow flag on the device (sizes here are bounds), so the device runs it the moment the pose is
     // final instead of waiting for S2 -> host -> helper thread -> launch (~45 us on the chain the next sweep's mapping waits for).
@@ -2061,7 +2066,9 @@ int vl_lm_run(vloam_b200_ctx* c) {
       VL_CUDA(cudaEventRecord(c->evMap, c->stream3));
       if (c->timing) VL_CUDA(cudaEventRecord(c->evx[7], c->stream3));
     }
+    VL_HOST_MARK(12);
     VL_TRY(lm_sync_s2(c, false, &lookaheadDone, true));
+    VL_HOST_MARK(13);
     if (!c->h_lmm->needSlow) {
       const int Qc = c->h_lmm->Qc, Qs = c->h_lmm->Qs, nq = Qc + Qs;
       if (d->builtCount < 0) {  // first in-place sweep after a rebuild: nothing created yet
