@@ -247,7 +247,7 @@ def run_reference(args, rank, world_size):
     replicas = max(1, host_cores())
     budget_s = 240.0
     n_frames = W + 1 + K
-    scans, traj, cblob, sblob = make_sequence(pkg, 0, n_frames + 1)
+    scans, traj, cblob, sblob = make_sequence(pkg, 0, W + K + 3)  # the same sweeps as the CUDA arm generates (its `config` must be identical)
 
     def replica(out, idx):
         o = op.Oracle(knn_backend=1, **KW)
