@@ -159,7 +159,12 @@ def pin_rank_threads(local_rank, local_world):
     per = len(cores) // local_world
     if per < 2:
         return None
-    mine = cores[local_rank * per:(local_rank + 1) * per]
+    # Interleaved slices (rank r gets cores r, r + N, r + 2N, ...), not contiguous blocks.  Every rank has two spinning threads (the
+    # caller polls a word the GPU writes into pinned memory, the helper thread spins for 1 ms after each task); on the usual
+    # numbering hyper-thread siblings are cpu i and cpu i + n/2, which a stride of N = 2 / 4 / 8 keeps inside one rank, while
+    # contiguous blocks put rank r's spinners on the siblings of rank r + N/2's cores.  (The GPU boxes are VMs that hide the
+    # sibling topology -- thread_siblings_list names every vCPU alone -- so it cannot be read.)  VLOAM_PIN=block restores blocks.
+    mine = cores[local_rank * per:(local_rank + 1) * per] if os.environ.get("VLOAM_PIN") == "block" else cores[local_rank::local_world][:per]
     os.sched_setaffinity(0, mine)
     return mine
 
