@@ -306,7 +306,7 @@ struct GridParams {
 // translation unit (no relocatable device code), armed by vloam_b200_debug_get("chain.trace").
 #ifdef __CUDACC__
 struct VlChainTrace { unsigned long long n; unsigned long long rec[4096][2]; };
-static __device__ VlChainTrace* g_chain_trace = nullptr;
+static __constant__ VlChainTrace* g_chain_trace = nullptr;  // (__constant__: the check costs one LDC, not a global-memory round trip at the start of every kernel)
 __device__ __forceinline__ void vl_chain_stamp(int id) {
   if (g_chain_trace && blockIdx.x == 0 && threadIdx.x == 0) {
     unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

@@ -838,18 +838,23 @@ __global__ void __launch_bounds__(128) lm_fit(const LmScalars* __restrict__ s, c
                                               double* __restrict__ factors, int* __restrict__ valid) {
   VL_PDL_WAIT(); vl_chain_stamp(3);
 
-  const int Qc = s->Qc, Qs = s->Qs;
-  if (!s->optimized) return;
+  const int Qc = s->Qc, Qs = s->Qs, opt = s->optimized;  // (one round trip for the three)
+  if (!opt) return;
   for (int qi = blockIdx.x * blockDim.x + threadIdx.x; qi < Qc + Qs; qi += gridDim.x * blockDim.x) {
   const int kind = qi >= Qc;
-  const float4 po = kind ? stackS[qi - Qc] : stackC[qi];
+  // every load of the query is issued before any of them is used: the neighbours are read whether or not the fifth distance
+  // passes the gate (lg_knn wrote all five slots of every query), one round trip instead of three
   const float d4 = knnD2[qi * 5 + 4];  // +inf when fewer than five neighbours were found
+  float4 nb[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) nb[j] = knnPts[qi * 5 + j];
+  const float4 po = kind ? stackS[qi - Qc] : stackC[qi];
   bool ok = false;
   double* f = factors + (size_t)qi * 10;
   if ((double)d4 < 1.0) {
     double P[5][3];
 #pragma unroll
-    for (int j = 0; j < 5; ++j) { const float4 t = knnPts[qi * 5 + j]; P[j][0] = t.x; P[j][1] = t.y; P[j][2] = t.z; }
+    for (int j = 0; j < 5; ++j) { const float4 t = nb[j]; P[j][0] = t.x; P[j][1] = t.y; P[j][2] = t.z; }
     double o6[6];
     ok = lm_fit_one(kind, P, o6);
     if (ok) {
@@ -1482,8 +1487,9 @@ __global__ void __launch_bounds__(128) mu_apply(const LmScalars* __restrict__ s,
                                                 MuWork mw) {
   VL_PDL_WAIT(); vl_chain_stamp(7);
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int soRaw = mw.slotOf[t];  // (in bounds for every launched thread: the grid covers the host bound the buffer was sized for; issued with the scalars)
   const int nq = s->needSlow ? 0 : s->Qc + s->Qs;
-  const int so = t < nq ? mw.slotOf[t] : -1;
+  const int so = t < nq ? soRaw : -1;
   int bornKind = -1, died = 0;  // bookkeeping of this thread's voxel, added up per warp at the end (thousands of atomics on ONE address cost ~50 us)
   if (so >= 0 && (so & MU_LEAD)) {  // the leader of its voxel
   const int hs = so & ~MU_LEAD;

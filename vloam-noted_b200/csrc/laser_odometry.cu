@@ -391,7 +391,7 @@ __device__ __forceinline__ Best warp_best_v(Best v, unsigned& tag, bool preferLo
 // reference's forward scan then visits exactly {j > closest : ring_j <= id + 2} and the backward scan
 // {j < closest : ring_j >= id - 2}; candidates farther than 5 m can never win because the running
 // minima start at DISTANCE_SQ_THRESHOLD = 25).  One warp per query.
-__device__ int* g_lo_trace = nullptr;  // debug: per query warp {cycles, flags: 1 = shell in the NN pass, 2 = shell in the second pass}
+__constant__ int* g_lo_trace = nullptr;  // debug: per query warp {cycles, flags: 1 = shell in the NN pass, 2 = shell in the second pass}
 
 template <bool SURF>
 __device__ __forceinline__ void lo_assoc_grid_dev(int qi, int lane, const float4* __restrict__ query, const float4* __restrict__ target,
