@@ -203,6 +203,11 @@ int vloam_b200_solve_deskew(vloam_b200_ctx* c, const double* factors, const doub
  * LidarPlaneNormFactor (zeros when rejected).  Same device code as the mapping stage. */
 int vloam_b200_fit(vloam_b200_ctx* c, const float* near_xyz, int n, int kind, int* ok, double* params);
 
+/* atanf(x[i]) and atan2f(y[i], x[i]) exactly as the scan-registration kernels evaluate them on the device (the reference
+ * calls glibc's float routines at SR.cpp:185-187, 217, 263; a 1-ulp difference moves points across ring boundaries, so the
+ * device code carries bit-identical fdlibm restatements).  Host arrays in and out; a test aid. */
+int vloam_b200_exact_math(vloam_b200_ctx* c, const float* y, const float* x, int n, float* atan_x, float* atan2_yx);
+
 #ifdef __cplusplus
 }
 #endif

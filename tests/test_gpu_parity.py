@@ -443,6 +443,43 @@ def test_mirror_classes_follow_reference_call_sequence(pkg, op, synth, street):
     lom.ctx.close()
 
 
+def test_device_exact_math_matches_glibc(pkg):
+    """The DEVICE compile of exact_math.h (the fdlibm atanf / atan2f of the scan-registration kernels, SR.cpp:185-187, 217, 263)
+    against this machine's glibc, bit for bit: 4M bit patterns across every exponent, lidar-like magnitudes, and the special
+    values.  (tests/test_exact_math.py checks the host compile of the same header.)"""
+    import ctypes
+    libm = ctypes.CDLL("libm.so.6")
+    rng = np.random.RandomState(5)
+    n = 1 << 22
+    xb = rng.randint(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    yb = rng.randint(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    x = xb.view(np.float32).copy(); y = yb.view(np.float32).copy()
+    x[n // 2:] = (rng.uniform(-120, 120, n - n // 2) * rng.choice([1.0, 1e-3, 1e-6], n - n // 2)).astype(np.float32)
+    y[n // 2:] = (rng.uniform(-120, 120, n - n // 2) * rng.choice([1.0, 1e-4], n - n // 2)).astype(np.float32)
+    sp = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e-40, -1e-40, 3e38], np.float32)
+    x[:100] = np.repeat(sp, 10); y[:100] = np.tile(sp, 10)
+    g = pkg.Context()
+    a_dev, b_dev = g.exact_math(y, x)
+    g.close()
+    # glibc through a tiny C loop (ctypes per element would take minutes)
+    import subprocess, tempfile
+    src = r'''
+#include <math.h>
+void ref(const float* y, const float* x, int n, float* a, float* b) { for (int i = 0; i < n; ++i) { a[i] = atanf(x[i]); b[i] = atan2f(y[i], x[i]); } }
+'''
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "r.c"), "w").write(src)
+        so = os.path.join(d, "r.so")
+        subprocess.run(["gcc", "-O1", "-fno-builtin", "-ffp-contract=off", "-shared", "-fPIC", os.path.join(d, "r.c"), "-o", so, "-lm"], check=True)
+        L = ctypes.CDLL(so)
+        a_ref, b_ref = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        L.ref(y.ctypes.data_as(ctypes.c_void_p), x.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(n), a_ref.ctypes.data_as(ctypes.c_void_p),
+              b_ref.ctypes.data_as(ctypes.c_void_p))
+    for dev, ref, what in ((a_dev, a_ref, "atanf"), (b_dev, b_ref, "atan2f")):
+        same = (dev.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(dev) & np.isnan(ref))
+        assert same.all(), "%s: %d of %d results differ from glibc, first at x = %r y = %r" % (what, int((~same).sum()), n, x[~same][:1], y[~same][:1])
+
+
 def test_golden_fixture_on_gpu(pkg):
     """tests/golden/vlp16_pair.npz (oracle outputs, made by tests/make_golden.py) reproduced by the CUDA path."""
     gold = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vlp16_pair.npz")))

@@ -15,7 +15,7 @@ EXPORTS = [
     "vloam_b200_scan_registration", "vloam_b200_prefetch_scan", "vloam_b200_prefetch_scan_device", "vloam_b200_scan_registration_device", "vloam_b200_get_cloud", "vloam_b200_laser_odometry",
     "vloam_b200_laser_mapping", "vloam_b200_process_frame", "vloam_b200_process_frame_device", "vloam_b200_synchronize",
     "vloam_b200_stream", "vloam_b200_kernel_launches", "vloam_b200_set_timing", "vloam_b200_stage_ms", "vloam_b200_debug_get",
-    "vloam_b200_debug_set", "vloam_b200_profile_kernel", "vloam_b200_profile_result", "vloam_b200_profile_table", "vloam_b200_profile_timeline", "vloam_b200_register_full_cloud", "vloam_b200_lo_associate", "vloam_b200_voxel_grid", "vloam_b200_evaluate", "vloam_b200_solve", "vloam_b200_fit", "vloam_b200_evaluate_deskew", "vloam_b200_solve_deskew",
+    "vloam_b200_debug_set", "vloam_b200_profile_kernel", "vloam_b200_profile_result", "vloam_b200_profile_table", "vloam_b200_profile_timeline", "vloam_b200_register_full_cloud", "vloam_b200_lo_associate", "vloam_b200_voxel_grid", "vloam_b200_evaluate", "vloam_b200_solve", "vloam_b200_fit", "vloam_b200_evaluate_deskew", "vloam_b200_solve_deskew", "vloam_b200_exact_math",
 ]
 
 
@@ -76,6 +76,7 @@ def load_lib(build=False):
     L.vloam_b200_solve_deskew.argtypes = [vp, vp, vp, ci, vp, vp]
     L.vloam_b200_register_full_cloud.argtypes = [vp, vp, ci]
     L.vloam_b200_fit.argtypes = [vp, vp, ci, ci, vp, vp]
+    L.vloam_b200_exact_math.argtypes = [vp, vp, vp, ci, vp, vp]
     _lib = L
     return L
 
@@ -267,6 +268,13 @@ class Context:
         prm = np.zeros((max(len(a), 1), 6))
         self._chk(self.L.vloam_b200_fit(self.h, a.ctypes.data, len(a), kind, ok.ctypes.data, prm.ctypes.data))
         return ok[:len(a)], prm[:len(a)]
+
+    def exact_math(self, y, x):
+        """(atanf(x), atan2f(y, x)) as the device code evaluates them (float32 arrays)."""
+        y = np.ascontiguousarray(y, np.float32); x = np.ascontiguousarray(x, np.float32)
+        a, b = np.zeros(len(x), np.float32), np.zeros(len(x), np.float32)
+        self._chk(self.L.vloam_b200_exact_math(self.h, y.ctypes.data, x.ctypes.data, len(x), a.ctypes.data, b.ctypes.data))
+        return a, b
 
     def solve(self, factors, x, s=None):
         f = np.ascontiguousarray(factors, np.float64)

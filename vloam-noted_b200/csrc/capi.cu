@@ -803,4 +803,26 @@ int vloam_b200_fit(vloam_b200_ctx* c, const float* near, int n, int kind, int* o
   return r;
 }
 
+// atanf(x[i]) and atan2f(y[i], x[i]) as the scan-registration kernels evaluate them ON THE DEVICE (exact_math.h; SR.cpp:185-187, 217,
+// 263 call glibc's): host arrays in, host arrays out.
+int vloam_b200_exact_math(vloam_b200_ctx* c, const float* y, const float* x, int n, float* atan_x, float* atan2_yx) {
+  if (!c) return VLOAM_E_INVALID;
+  if (n < 0 || (n > 0 && (!y || !x || !atan_x || !atan2_yx))) return VLOAM_E_INVALID;
+  if (n == 0) return VLOAM_OK;
+  VL_TRY(vloam_b200_synchronize(c));
+  float* d = nullptr;
+  int r = VLOAM_OK;
+  const size_t B = (size_t)n * sizeof(float);
+  if (cudaMalloc(&d, 4 * B) != cudaSuccess) r = VLOAM_E_CUDA;
+  if (r == VLOAM_OK && (cudaMemcpyAsync(d, y, B, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+                        cudaMemcpyAsync(d + n, x, B, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)) r = VLOAM_E_CUDA;
+  if (r == VLOAM_OK) r = vl_sr_exact_math(c, d, d + n, n, d + 2 * (size_t)n, d + 3 * (size_t)n);
+  if (r == VLOAM_OK && (cudaMemcpyAsync(atan_x, d + 2 * (size_t)n, B, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                        cudaMemcpyAsync(atan2_yx, d + 3 * (size_t)n, B, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                        cudaStreamSynchronize(c->stream) != cudaSuccess)) r = VLOAM_E_CUDA;
+  if (r == VLOAM_E_CUDA) snprintf(c->err, sizeof c->err, "vloam_b200_exact_math: %s", cudaGetErrorString(cudaGetLastError()));
+  if (d) cudaFree(d);
+  return r;
+}
+
 }  // extern "C"

@@ -389,6 +389,7 @@ static inline int vl_div_up(long long a, long long b) { return (int)((a + b - 1)
 // ---- stage entry points (one per .cu file) ------------------------------------
 int vl_sr_run(vloam_b200_ctx* c, const float* d_xyz, int n, int stride);
 int vl_sr_sync_counts(vloam_b200_ctx* c);
+int vl_sr_exact_math(vloam_b200_ctx* c, const float* d_y, const float* d_x, int n, float* d_atan, float* d_atan2);
 int vl_lo_run(vloam_b200_ctx* c, const double* prior_q, const double* prior_t, int use_prior);
 int vl_lo_associate_only(vloam_b200_ctx* c, const double* x, int* corner_idx, int* surf_idx);
 int vl_lo_build_last(vloam_b200_ctx* c, int set, const float4* corner, int nc, const float4* surf, int ns);

@@ -833,6 +833,21 @@ __global__ void __launch_bounds__(SR_BLOCK) sr_gather(const float4* __restrict__
   if (k < dsCount[lo]) lessFlat[dsOff[lo] + k] = lessFlatProv[t];
 }
 
+// vloam_b200_exact_math: the DEVICE compile of exact_math.h on caller-supplied inputs (tests compare it with glibc bit for bit)
+__global__ void __launch_bounds__(256) sr_exact_math(const float* __restrict__ y, const float* __restrict__ x, int n, float* __restrict__ oAtan,
+                                                     float* __restrict__ oAtan2) {
+  VL_PDL_WAIT();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  oAtan[i] = vlx::atanf_exact(x[i]);
+  oAtan2[i] = vlx::atan2f_exact(y[i], x[i]);
+}
+int vl_sr_exact_math(vloam_b200_ctx* c, const float* d_y, const float* d_x, int n, float* d_atan, float* d_atan2) {
+  VL_LAUNCH(sr_exact_math, vl_div_up(n, 256), 256, 0, d_y, d_x, n, d_atan, d_atan2);
+  VL_CUDA(cudaGetLastError());
+  return VLOAM_OK;
+}
+
 // ---------------------------------------------------------------------------------
 int vl_sr_run(vloam_b200_ctx* c, const float* d_xyz, int n, int stride) {
   const int R = c->prm.n_scans;
