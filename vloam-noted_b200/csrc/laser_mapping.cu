@@ -1259,8 +1259,10 @@ __global__ void __launch_bounds__(1024) rf_append_outside(LmScalars* __restrict_
                                                           int poolCapC, int poolCapS, const int* __restrict__ anyOutside) {
   VL_PDL_WAIT();
 
-  if (anyOutside && (s->needSlow || !*anyOutside)) return;  // (in-place path: mu_keys saw no point outside the window)
-  const int Qc = s->Qc, total = s->Qc + s->Qs;
+  // in-place path: mu_keys left {a point fell outside the window, points, needSlow, Qc} of ITS sweep in anyOutside[0..3] -- the next
+  // sweep's lm_prepare_fast may be rewriting LmScalars while this kernel runs (the pose chain does not wait for it)
+  if (anyOutside && (anyOutside[2] || !*anyOutside)) return;
+  const int Qc = anyOutside ? anyOutside[3] : s->Qc, total = anyOutside ? anyOutside[1] : s->Qc + s->Qs;
   __shared__ int lIdx[1024], lKey[1024];
   __shared__ int gKey[1024], gOld[1024], gNew[1024], gCnt[1024];
   __shared__ int warpSum[32];
@@ -1446,6 +1448,7 @@ __global__ void __launch_bounds__(256) mu_keys(const LmScalars* __restrict__ s, 
   VL_PDL_WAIT(); vl_chain_stamp(6);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int Qc = s->Qc, Qs = s->Qs;
+  if (i == 0) { m.anyOutside[1] = s->needSlow ? 0 : Qc + Qs; m.anyOutside[2] = s->needSlow; m.anyOutside[3] = Qc; }  // (for rf_append_outside)
   if (s->needSlow || i >= Qc + Qs) return;  // (queued before the host knows whether the sweep stays on the in-place path, and with a bound on the count)
   const int kind = i >= Qc;
   const float4 po = kind ? stackS[i - Qc] : stackC[i];
@@ -1974,7 +1977,11 @@ int vl_lm_run(vloam_b200_ctx* c) {
   const int resetValid = c->lm_reset_pending ? 1 : 0;
   c->lm_reset_pending = false;
   VL_CUDA(cudaStreamWaitEvent(c->stream, c->evMap, 0));  // the previous frame's map update (stream3) must be complete
-  VL_CUDA(cudaStreamWaitEvent(c->stream, c->evAux, 0));  // ... including its outside appends (streamAux, pool path)
+  // ... its raw appends to cubes OUTSIDE the window (streamAux) touch pool segments only: nothing of the in-place path reads them
+  // (a single CTA that takes 20-60 us when the sensor nears a window edge: it used to sit on the next sweep's pose chain);
+  // the pool path below waits for them before it reads the cube tables.  VLOAM_WAIT_AUX=1 restores the early wait.
+  static const bool waitAuxEarly = getenv("VLOAM_WAIT_AUX") != nullptr;
+  if (waitAuxEarly) VL_CUDA(cudaStreamWaitEvent(c->stream, c->evAux, 0));
   if (skip) {  // LM.cpp:197-201: only the high-frequency pose is propagated
     VL_LAUNCH(lm_prepare_fast, 1, 256, 0, c->lmm, c->los, d->work, d->grid.hdr, 1, resetValid, (const int*)nullptr, (const int*)nullptr, (const int*)nullptr);
     VL_TRY(vl_lo_flush_deferred(c)); VL_CUDA(cudaGetLastError());
@@ -2099,6 +2106,7 @@ int vl_lm_run(vloam_b200_ctx* c) {
   }
 
   // ---- pool path (round 1's): cube tables, sorted pools; the grid is rebuilt for the window lm_prepare finds
+  VL_CUDA(cudaStreamWaitEvent(c->stream, c->evAux, 0));  // (the previous sweep's raw appends outside the window edit the cube tables)
   if (d->poolsStale) VL_TRY(lm_materialize(c, d));  // the in-place updates since the last pool-path sweep, written back first (main stream)
   VL_LAUNCH(lm_prepare, 1, 1024, 0, c->lmm, c->los, c->cubeC, c->cubeS, d->work, 0, resetValid, d->subReal);
   const long long totalBound = d->hMapUpperC + d->hMapUpperS;
