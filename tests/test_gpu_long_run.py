@@ -35,19 +35,24 @@ def test_long_lookahead_replay_latency_and_regrowth(pkg):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         chunk = []
+        nqs = []
         for i in range(hi - c0):
             t1 = time.perf_counter()
-            ctx.prefetch_device(scans[i + 1].data_ptr(), scans[i + 1].shape[0], 4)
+            bench.prefetch_ahead(ctx, scans, i, True)  # the next two sweeps, as bench.py registers them
             ctx.process_frame_device(scans[i].data_ptr(), scans[i].shape[0], 4, pose.ctypes.data)
             chunk.append((time.perf_counter() - t1) * 1e3)
             if (c0 + i) % 10 == 9:
                 allocs.append((c0 + i, int(ctx.get("alloc.count")[0])))
                 centres.add(int(ctx.get("lm.validInd")[0]))
+                if os.environ.get("VLOAM_LONG_RUN_DIAG"):
+                    nqs.append(len(ctx.get("lm.cornerStack")) + len(ctx.get("lm.surfStack")))
+                    grid = np.frombuffer(ctx.get_raw("lm.grid"), np.int32)
         dt = time.perf_counter() - t0
         lat += chunk
         err = float(np.linalg.norm(pose[11:14] - traj[hi - 1][:3]))
         report.append("sweeps %4d-%4d: %.0f scans/s (incl. the alloc.count reads), p50 %.3f p99 %.3f max %.3f ms, |t - truth| %.3f m"
-                      % (c0, hi - 1, (hi - c0) / dt, np.median(chunk), np.percentile(chunk, 99), max(chunk), err))
+                      % (c0, hi - 1, (hi - c0) / dt, np.median(chunk), np.percentile(chunk, 99), max(chunk), err)
+                      + ((", stack points %.0f, grid chunks %d live %d dead %d" % (np.mean(nqs), grid[0], grid[1], grid[2])) if nqs else ""))
     print("\n".join(report))
     print("first sweeps, ms:", " ".join("%.2f" % v for v in lat[:8]))
     lat = np.array(lat)

@@ -632,6 +632,10 @@ long vloam_b200_debug_get(vloam_b200_ctx* c, const char* name, void* out, long c
     VL_CUDA(cudaMemset(d_tr, 0, 8));
     return (long)sizeof(VlChainTrace);
   }
+  if (n == "lm.grid") {  // bookkeeping of the voxel-hash grid as of the last S2: {chunks in use, live points, tombstones, dirty}
+    const int v[4] = {c->h_lmm->gridTop, c->h_lmm->gridCount, c->h_lmm->gridDead, c->h_lmm->gridDirty};
+    return put_host(v, sizeof v, out, cap);
+  }
   if (n == "alloc.count") { const long long v = c->regrows; return put_host(&v, sizeof v, out, cap); }  // device buffer (re)allocations so far
   if (n == "lo.costs") return put_host(c->dbgLoCost, sizeof c->dbgLoCost, out, cap);
   if (n == "lm.costs") return put_host(c->dbgLmCost, sizeof c->dbgLmCost, out, cap);

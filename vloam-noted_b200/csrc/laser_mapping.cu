@@ -1528,7 +1528,13 @@ __global__ void __launch_bounds__(128) mu_apply(const LmScalars* __restrict__ s,
   const float4 c = rf_centroid(acc, cnt);
   if (lm_vox_key(c, inv, ci, cj, ck, s->cenW, s->cenH, s->cenD) != vk) g.hdr->dirty = 1;  // drifted across a voxel face: pool path next sweep
   const int cell = kind * LM_NCELL + lg_cell_of(c, o);
-  if (found >= 0 && cell == foundCell) g.pts[found] = c;
+  // The entry stays where it is even when the centroid slid into the neighbouring 2 m cell, as long as leaf <= 0.95 m: it cannot leave
+  // its voxel's box (checked above), so it stays within `leaf` of the cell that lists it, and a query that accepts it (d2 < 1 m^2) is
+  // then closer than 2 m to that cell, i.e. still visits it (27-cell search).  Voxels that straddle a cell boundary used to be
+  // tombstoned and re-appended every time their centroid crossed it: ~500 per sweep, 10 % dead entries after 200 sweeps, and the
+  // sweeps before a window move ran 15-20 % slower than the ones after its rebuild (profiles/r2_long_run_1000_sweeps.txt).
+  const float leafK = kind ? prm.plane_res : prm.line_res;
+  if (found >= 0 && (cell == foundCell || leafK <= 0.95f)) g.pts[found] = c;
   else {
     int pos = -1;
     if (found >= 0) { pos = g.posOf[found]; g.pts[found].x = CUDART_INF_F; *(volatile unsigned long long*)&g.key[found] = LG_DEAD; died = 1; }
