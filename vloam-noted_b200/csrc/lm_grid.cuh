@@ -12,10 +12,11 @@
 // kNN visits the 27 cells around a query exactly as before (exact inside the 1 m acceptance ball); ties are
 // ordered by key = (valid-cube slot, voxel key), which is the order of the canonical point ids (position in the
 // concatenated sub-map cloud, LM.cpp:476-485) because a filtered cube is sorted by voxel key.  The per-sweep map update
-// (LM.cpp:741-808) becomes: sort the ~15k new points by (cube, voxel), find the map point of each voxel IN THE GRID (it
-// lies in one of the <= 8 cells the voxel's box overlaps), fold the run in the reference's order (map point first, then
-// the new points in stack order, f32), and store the centroid back -- in place, or as a new entry.  The per-cube sorted
-// pools of laser_mapping.cu stay the exchange format (export, window moves, raw tails): they are brought up to date from
+// (LM.cpp:741-808) becomes: group the ~7-15k new points by (cube, voxel) in a small hash table (no sort), find the map point of
+// each voxel IN THE GRID (it lies in one of the <= 8 cells the voxel's box overlaps), fold the group in the reference's order (map
+// point first, then the new points in stack order, f32), and store the centroid back -- in place, or as a new entry; an entry stays
+// listed in its cell when its centroid slides into the neighbouring one (exact for leaf <= 0.95 m, see mu_apply).  The per-cube
+// sorted pools of laser_mapping.cu stay the exchange format (export, window moves, raw tails): they are brought up to date from
 // the grid only when needed -- every entry remembers its position in its cube's pool segment (refreshed in place), the
 // voxels created since go through ONE pass of the pool path's merge (rf_*), which puts them at their sorted positions.
 //
