@@ -83,3 +83,60 @@ def test_context_fails_loudly_without_gpu(pkg):
     pkg.load_lib(build=True)
     with pytest.raises(pkg.VloamError):
         pkg.Context()
+
+
+def test_prefetch_ahead_keeps_two_sweeps_registered_with_one_call_per_sweep():
+    """bench.prefetch_ahead (the replay loop of bench.py and of the benchmarked-path tests): sweeps k+1 and k+2 are registered
+    before sweep k is processed, every sweep exactly once in steady state, on host and device buffers, and a new buffer list
+    starts over."""
+    import bench
+
+    class Buf:
+        def __init__(self, i): self.i, self.shape = i, (100 + i, 4)
+        def data_ptr(self): return 0x1000 * (self.i + 1)
+
+    class Ctx:
+        def __init__(self): self.calls = []
+        def prefetch_device(self, p, n, s): self.calls.append(("dev", p, n, s))
+        def prefetch_ptr(self, p, n, s): self.calls.append(("host", p, n, s))
+
+    bufs = [Buf(i) for i in range(6)]
+    for device in (True, False):
+        c = Ctx()
+        seen = []
+        for k in range(6):
+            before = len(c.calls)
+            bench.prefetch_ahead(c, bufs, k, device)
+            seen.append([call[1] // 0x1000 - 1 for call in c.calls[before:]])
+        assert seen == [[1, 2], [3], [4], [5], [], []], seen          # two at the start, then one per sweep, none past the end
+        assert all(call[0] == ("dev" if device else "host") and call[3] == 4 for call in c.calls)
+        assert [call[2] for call in c.calls] == [101, 102, 103, 104, 105]
+    c = Ctx()
+    bench.prefetch_ahead(c, bufs, 0, True)
+    other = [Buf(10 + i) for i in range(4)]
+    bench.prefetch_ahead(c, other, 0, True)                             # another list (a new chunk of a long replay): starts over
+    assert [call[1] for call in c.calls] == [0x2000, 0x3000, 0xc000, 0xd000]
+    bench.prefetch_ahead(c, other, 2, True)                             # a skipped sweep: whatever is missing of k+1, k+2
+    assert [call[1] for call in c.calls[4:]] == [0xe000]
+
+
+def test_rank_core_slices_are_disjoint_and_interleaved(monkeypatch):
+    """bench.pin_rank_threads: every local rank gets its own slice of the host cores, interleaved (rank r: r, r + N, ...), so
+    that hyper-thread siblings i and i + n/2 stay inside one rank; one rank alone is not pinned."""
+    import bench
+    if not hasattr(os, "sched_setaffinity"):
+        pytest.skip("no sched_setaffinity")
+    cores = list(range(32))
+    pinned = {}
+    monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(cores))
+    monkeypatch.setattr(os, "sched_setaffinity", lambda pid, s: pinned.__setitem__("last", list(s)))
+    assert bench.pin_rank_threads(0, 1) is None
+    for n in (2, 4, 8):
+        slices = [bench.pin_rank_threads(r, n) for r in range(n)]
+        flat = sorted(x for s in slices for x in s)
+        assert flat == cores and all(len(s) == 32 // n for s in slices)
+        for r, s in enumerate(slices):
+            assert s == list(range(r, 32, n))
+            assert all(((x + 16) % 32) in s for x in s)               # the sibling of every core belongs to the same rank
+    monkeypatch.setenv("VLOAM_PIN", "block")
+    assert bench.pin_rank_threads(1, 4) == list(range(8, 16))
