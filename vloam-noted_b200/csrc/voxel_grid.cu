@@ -22,6 +22,7 @@ namespace cg = cooperative_groups;
 #define BT_TILE 4096
 #define BT_THREADS 512
 #define VG_BLOCK 256
+#define VG_TILE 256   // sorted keys per CTA in vg_head_count / vg_centroid (1024 left the 50k-point stack filter with 49 CTAs on 148 SMs)
 
 __global__ void __launch_bounds__(BT_THREADS) bt_tile_sort(unsigned long long* __restrict__ keys, int tile) {
   VL_PDL_WAIT();
@@ -253,11 +254,15 @@ __global__ void vg_box(const float* __restrict__ partial, int nPartial, int nBou
                        VgBox* __restrict__ box, int* __restrict__ dCount) {
   VL_PDL_WAIT();
 
-  if (threadIdx.x != 0) return;
+  // (launched with one warp: the <= 256 partial boxes are reduced by all 32 lanes -- one lane walking 1536 values took ~20 us)
   const int n = dN ? min(*dN, nBound) : nBound;
   float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
-  for (int b = 0; b < nPartial; ++b)
+  for (int b = threadIdx.x; b < nPartial; b += 32)
     for (int a = 0; a < 3; ++a) { mn[a] = fminf(mn[a], partial[b * 6 + a]); mx[a] = fmaxf(mx[a], partial[b * 6 + 3 + a]); }
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    for (int d = 16; d > 0; d >>= 1) { mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], d)); mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], d)); }
+  if (threadIdx.x != 0) return;
   VgBox bx;
   bx.n = n;
   const float inv = __fdiv_rn(1.0f, leaf);
@@ -287,15 +292,15 @@ __global__ void __launch_bounds__(VG_BLOCK) vg_keys(const float4* __restrict__ i
   keys[i] = (i < b.n && !b.guard) ? (((unsigned long long)vg_idx(in[i], b) << 32) | (unsigned)i) : ~0ull;
 }
 
-// Tile of 1024 sorted keys per block: count run heads.
+// Tile of VG_TILE sorted keys per block: count run heads.
 __global__ void __launch_bounds__(VG_BLOCK) vg_head_count(const unsigned long long* __restrict__ keys, const VgBox* __restrict__ box,
                                                           int* __restrict__ blockCnt) {
   VL_PDL_WAIT();
 
   const int n = box->guard ? 0 : box->n;
   int cnt = 0;
-  const int base = blockIdx.x * 1024;
-  for (int q = 0; q < 4; ++q) {
+  const int base = blockIdx.x * VG_TILE;
+  for (int q = 0; q < VG_TILE / VG_BLOCK; ++q) {
     const int t = base + q * VG_BLOCK + threadIdx.x;
     if (t < n && (t == 0 || (unsigned)(keys[t] >> 32) != (unsigned)(keys[t - 1] >> 32))) ++cnt;
   }
@@ -323,7 +328,7 @@ __global__ void __launch_bounds__(1024) vg_block_scan(int* __restrict__ blockCnt
   if (threadIdx.x == 0) *dCount = box->guard ? box->n : carry;
 }
 
-#define VG_HALO 256
+#define VG_HALO 64
 __global__ void __launch_bounds__(VG_BLOCK) vg_centroid(const float4* __restrict__ in, const unsigned long long* __restrict__ keys,
                                                         const VgBox* __restrict__ box, const int* __restrict__ blockOff,
                                                         float4* __restrict__ out) {
@@ -331,7 +336,7 @@ __global__ void __launch_bounds__(VG_BLOCK) vg_centroid(const float4* __restrict
 
   const VgBox b = *box;
   if (b.guard) {  // leaf too small for the extent: output = input
-    for (int i = blockIdx.x * 1024 + threadIdx.x; i < min(b.n, (int)(blockIdx.x + 1) * 1024); i += VG_BLOCK) out[i] = in[i];
+    for (int i = blockIdx.x * VG_TILE + threadIdx.x; i < min(b.n, (int)(blockIdx.x + 1) * VG_TILE); i += VG_BLOCK) out[i] = in[i];
     return;
   }
   const int n = b.n;
@@ -340,11 +345,11 @@ __global__ void __launch_bounds__(VG_BLOCK) vg_centroid(const float4* __restrict
   // is read from global, which is rare)
   // VG_HALO entries beyond the tile are staged too: the last run of nearly every tile continues into the next
   // one, and finishing it from global memory is a chain of dependent key -> point loads (~1 us per 2 points).
-  __shared__ unsigned svox[1024 + VG_HALO + 1];
-  __shared__ float4 spt[1024 + VG_HALO];
+  __shared__ unsigned svox[VG_TILE + VG_HALO + 1];
+  __shared__ float4 spt[VG_TILE + VG_HALO];
   __shared__ int ws[VG_BLOCK / 32];
-  const int base = blockIdx.x * 1024;
-  for (int t = threadIdx.x; t < 1024 + VG_HALO; t += VG_BLOCK) {
+  const int base = blockIdx.x * VG_TILE;
+  for (int t = threadIdx.x; t < VG_TILE + VG_HALO; t += VG_BLOCK) {
     const int g = base + t;
     if (g < n) { const unsigned long long k = keys[g]; svox[t] = (unsigned)(k >> 32); spt[t] = in[(int)(unsigned)(k & 0xffffffffull)]; }
     else svox[t] = 0xffffffffu;
@@ -352,7 +357,7 @@ __global__ void __launch_bounds__(VG_BLOCK) vg_centroid(const float4* __restrict
   __syncthreads();
   int running = blockOff[blockIdx.x];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < VG_TILE / VG_BLOCK; ++q) {
     const int lt = q * VG_BLOCK + threadIdx.x;
     const int t = base + lt;
     const unsigned vox = svox[lt];
@@ -365,13 +370,13 @@ __global__ void __launch_bounds__(VG_BLOCK) vg_centroid(const float4* __restrict
     if (head) {
       float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f; int nrun = 0;
       int r = lt;
-      for (; r < 1024 + VG_HALO && svox[r] == vox; ++r) {
+      for (; r < VG_TILE + VG_HALO && svox[r] == vox; ++r) {
         const float4 p = spt[r];
         sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
         ++nrun;
       }
-      if (r == 1024 + VG_HALO)
-        for (int g = base + 1024 + VG_HALO; g < n && (unsigned)(keys[g] >> 32) == vox; ++g) {
+      if (r == VG_TILE + VG_HALO)
+        for (int g = base + VG_TILE + VG_HALO; g < n && (unsigned)(keys[g] >> 32) == vox; ++g) {
           const float4 p = in[(int)(unsigned)(keys[g] & 0xffffffffull)];
           sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
           ++nrun;
@@ -389,7 +394,7 @@ int vl_voxel_grid_device(vloam_b200_ctx* c, const float4* d_in, int n, const int
   if (n <= 0) { VL_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), VL_STREAM(c))); return VLOAM_OK; }
   int P = 2; while (P < n) P <<= 1;
   const int nb = min(vl_div_up(n, VG_BLOCK), 256);
-  const int nTiles = vl_div_up(n, 1024);
+  const int nTiles = vl_div_up(n, VG_TILE);
   DBuf<unsigned long long>& vKeys = lane ? c->vKeys2 : c->vKeys;
   DBuf<int>& vScan = lane ? c->vScan2 : c->vScan;
   VL_TRY(vl_reserve(c, vKeys, (size_t)P));
