@@ -18,6 +18,7 @@
 #include <math_constants.h>
 #include "common.cuh"
 #include "exact_math.h"
+extern bool vl_debug_capture(const vloam_b200_ctx* c);
 #include "bitonic.cuh"
 
 #define SR_BLOCK 256
@@ -862,6 +863,8 @@ int vl_sr_run(vloam_b200_ctx* c, const float* d_xyz, int n, int stride) {
     VL_CUDA(cudaEventRecord(c->evSR, VL_STREAM(c)));
     return VLOAM_OK;
   }
+  // (a previous run of this set may have left its tail on the side stream: it reads buffers this run rewrites)
+  if (vl_tls_stream == nullptr) VL_CUDA(cudaStreamWaitEvent(c->stream, c->evSR, 0));
   const int numBlocks = vl_div_up(n, SR_BLOCK);
   VL_TRY(vl_reserve(c, c->ring, n));
   VL_TRY(vl_reserve(c, c->ori, n));
@@ -902,6 +905,14 @@ int vl_sr_run(vloam_b200_ctx* c, const float* d_xyz, int n, int stride) {
             c->lessFlatProv.p, c->sharp.p, c->lessSharp[c->cur].p, c->flat.p, c->lessFlat[c->cur].p);
   VL_CUDA(cudaEventRecord(c->evSRfeat, VL_STREAM(c)));
   if (c->timing && VL_STREAM(c) == c->streamSR) cudaEventRecord(c->evx[8], c->streamSR);
+  // One sweep at a time (this run is on the pose chain's stream): the odometry that follows needs nothing of what comes below --
+  // the per-ring voxel filter of the less-flat cloud, ~40 us -- so that tail goes to the side stream behind evSRfeat and the
+  // odometry starts at once.  Everything that reads the less-flat cloud or the counts waits for evSR anyway (sync point S1, the
+  // stack filters and search structures issued behind it, the getters).  VLOAM_NO_SR_TAIL_ASIDE=1 keeps it on the chain.
+  static const bool noTailAside = getenv("VLOAM_NO_SR_TAIL_ASIDE") != nullptr;
+  const bool tailAside = !noTailAside && vl_tls_stream == nullptr && !c->prof_name[0] && !vl_debug_capture(c);
+  struct TlsRestore { cudaStream_t prev; bool on; ~TlsRestore() { if (on) vl_tls_stream = prev; } } tlsRestore{vl_tls_stream, tailAside};
+  if (tailAside) { VL_CUDA(cudaStreamWaitEvent(c->streamSR, c->evSRfeat, 0)); vl_tls_stream = c->streamSR; }
   const size_t voxSmem = (size_t)SR_VOX_CAP * (sizeof(unsigned long long) + sizeof(float4));
   VL_BYTES(36.0 * n);
   VL_LAUNCH(sr_ring_voxel, R, SR_PICK_THREADS, voxSmem, c->cloud.p, c->label.p, c->ringStart, c->ringCount, c->selIdx.p, c->sortScratch.p,
